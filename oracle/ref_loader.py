@@ -1,0 +1,131 @@
+"""Run the reference's own metric / OSM modules in place (build container only).
+
+TEST INFRASTRUCTURE ONLY - see ``oracle/__init__.py``.  ``/root/reference`` is
+mounted read-only in the build container and does not exist on the GPU box, so
+this loader is used (a) by ``tests/golden/make_golden.py`` to generate the
+committed golden vectors and (b) by CPU tests that skip when the mount is absent.
+
+kikuchipy cannot be imported as a package here (dask, hyperspy, orix, h5py ...
+are not installed, no network).  Its similarity-metric modules only touch dask
+through ``da.asarray / da.einsum / da.Array`` and ``dask.config.set`` and take
+their NumPy branches when handed ndarrays, so a ~15-line ``dask`` stub that
+routes those names to NumPy is enough to execute the reference's real cast /
+mask / normalise / einsum lines unmodified.  ``_orientation_similarity_map.py``
+needs only a ``CrystalMap`` name from orix for its type annotation.
+"""
+
+from __future__ import annotations
+
+import contextlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = "/root/reference"
+_SRC = os.path.join(REFERENCE_ROOT, "src", "kikuchipy")
+
+
+def available() -> bool:
+    return os.path.isfile(
+        os.path.join(_SRC, "indexing", "similarity_metrics", "_similarity_metric.py")
+    )
+
+
+def _install_stubs() -> None:
+    if "dask" not in sys.modules:
+        dask = types.ModuleType("dask")
+        da = types.ModuleType("dask.array")
+        cfg = types.ModuleType("dask.config")
+
+        class Array:  # placeholder so isinstance(x, da.Array) is False for ndarrays
+            pass
+
+        da.Array = Array
+        da.asarray = np.asarray
+        da.einsum = lambda *a, **k: np.einsum(*a, **k)
+        da.mean, da.sum, da.sqrt, da.square = np.mean, np.sum, np.sqrt, np.square
+        cfg.set = lambda *a, **k: contextlib.nullcontext()
+        dask.array, dask.config = da, cfg
+        sys.modules.update({"dask": dask, "dask.array": da, "dask.config": cfg})
+    if "orix" not in sys.modules:
+        orix = types.ModuleType("orix")
+        cm = types.ModuleType("orix.crystal_map")
+
+        class CrystalMap:  # annotation only
+            pass
+
+        cm.CrystalMap = CrystalMap
+        orix.crystal_map = cm
+        sys.modules.update({"orix": orix, "orix.crystal_map": cm})
+    for name in (
+        "kikuchipy",
+        "kikuchipy.indexing",
+        "kikuchipy.indexing.similarity_metrics",
+    ):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.__path__ = []  # mark as package
+            sys.modules[name] = mod
+
+
+def _load(modname: str, relpath: str):
+    if modname in sys.modules and getattr(sys.modules[modname], "__file__", None):
+        return sys.modules[modname]
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(_SRC, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_metrics():
+    """Return (SimilarityMetric, NCC class, NDP class, ncc_single_numba)."""
+    if not available():
+        raise RuntimeError("reference tree not mounted")
+    _install_stubs()
+    base = "kikuchipy.indexing.similarity_metrics"
+    sm = _load(f"{base}._similarity_metric", "indexing/similarity_metrics/_similarity_metric.py")
+    ncc = _load(
+        f"{base}._normalized_cross_correlation",
+        "indexing/similarity_metrics/_normalized_cross_correlation.py",
+    )
+    ndp = _load(
+        f"{base}._normalized_dot_product",
+        "indexing/similarity_metrics/_normalized_dot_product.py",
+    )
+    return (
+        sm.SimilarityMetric,
+        ncc.NormalizedCrossCorrelationMetric,
+        ndp.NormalizedDotProductMetric,
+        ncc._ncc_single_patterns_1d_float32_exp_centered,
+    )
+
+
+def load_osm():
+    """Return the reference ``orientation_similarity_map`` function."""
+    if not available():
+        raise RuntimeError("reference tree not mounted")
+    _install_stubs()
+    mod = _load(
+        "kikuchipy.indexing._orientation_similarity_map",
+        "indexing/_orientation_similarity_map.py",
+    )
+    return mod.orientation_similarity_map
+
+
+class FakeXmap:
+    """Minimal object with what ``orientation_similarity_map`` reads."""
+
+    def __init__(self, simulation_indices, shape, prop_name="simulation_indices"):
+        self.prop = {prop_name: np.asarray(simulation_indices)}
+        self.shape = tuple(shape)
+
+
+def nickel_ebsd_small() -> np.ndarray:
+    """The nine 60x60 uint8 patterns of ``kp.data.nickel_ebsd_small()`` read from
+    the raw NORDIF file (data/_data.py:97-126)."""
+    raw = np.fromfile(os.path.join(_SRC, "data", "nordif", "Pattern.dat"), dtype=np.uint8)
+    return raw.reshape((3, 3, 60, 60))
