@@ -1,0 +1,184 @@
+/*
+ * kdi.h - C ABI of libkdi, the B200-native dictionary-indexing engine.
+ *
+ * This is the drop-in boundary for ONE hot path of kikuchipy (reference paths
+ * are relative to /root/reference/src/kikuchipy):
+ *
+ *   EBSD.dictionary_indexing            signals/ebsd.py:1827-1984
+ *   _dictionary_indexing / _match_chunk indexing/_dictionary_indexing.py:36-203
+ *   SimilarityMetric (NCC / NDP)        indexing/similarity_metrics/ (all modules)
+ *   orientation_similarity_map          indexing/_orientation_similarity_map.py:30-152
+ *
+ * The reference is pure Python and has no FFI of its own; these are the entry
+ * points a ctypes/cffi binding inside kikuchipy would call (INTEGRATION.md shows
+ * that binding).  Plain pointers and sizes only - no torch / numpy types.
+ *
+ * Conventions
+ *  - every function returns KDI_OK (0) or a negative KDI_E* code; the message
+ *    is available from kdi_last_error().  There is NO CPU fallback: without a
+ *    CUDA device kdi_init() fails.
+ *  - masks use the reference's polarity: nonzero (True) = EXCLUDED
+ *    (similarity_metrics/_similarity_metric.py:51-58).
+ *  - buffers marked host/device are selected by a KDI_HOST / KDI_DEVICE flag;
+ *    the caller owns every buffer it passes in and inputs are never modified
+ *    (reference test tests/test_indexing/test_dictionary_indexing.py:41-43).
+ *  - one kdi_ctx per (process, device); a ctx is not thread-safe.
+ */
+#ifndef KDI_H_
+#define KDI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDI_VERSION 100
+
+/* status codes */
+#define KDI_OK 0
+#define KDI_EINVAL (-1)       /* bad argument                      */
+#define KDI_ECUDA (-2)        /* CUDA runtime / driver error       */
+#define KDI_ENOMEM (-3)       /* device or pinned allocation failed */
+#define KDI_EUNSUPPORTED (-4) /* valid request this build cannot serve */
+#define KDI_EINTERNAL (-5)    /* kernel-side check failed          */
+
+/* source element types accepted by kdi_patterns_create */
+#define KDI_U8 0
+#define KDI_U16 1
+#define KDI_F32 2
+#define KDI_F64 3
+
+/* metrics: which normalisation the prepare step applies */
+#define KDI_NCC 0 /* centre + unit norm  (_normalized_cross_correlation.py:228-233) */
+#define KDI_NDP 1 /* unit norm only      (_normalized_dot_product.py:181-194)       */
+
+/* buffer location */
+#define KDI_HOST 0
+#define KDI_DEVICE 1
+
+/* options for kdi_set_option */
+#define KDI_OPT_COMPUTE_DTYPE 0 /* 0 = fp16 (scaled, default), 1 = bf16: operand type of the tensor-core pass */
+#define KDI_OPT_CERT_SIGMAS 1   /* width of the candidate certificate in sigmas (default 8)              */
+#define KDI_OPT_FORCE_EXACT 2   /* 1 = skip the tensor-core pass, score every pair in fp32/fp64 (validation) */
+#define KDI_OPT_CTA_GROUP 3     /* 1 or 2: tcgen05 cta_group of the GEMM kernel                            */
+#define KDI_OPT_STRIP_TILES 4   /* N tiles per work unit (L2 reuse knob)                                   */
+#define KDI_OPT_SUPERBLOCK 5    /* M tiles per super-block (L2 reuse knob)                                 */
+
+typedef struct kdi_ctx kdi_ctx;
+typedef struct kdi_patterns kdi_patterns;
+
+/* per-stage device timings (ms, CUDA events) of the last kdi_match_topk /
+ * kdi_dictionary_indexing call, plus counters */
+typedef struct kdi_timings {
+  float normalize_exp_ms;
+  float normalize_dict_ms;
+  float gemm_topk_ms;   /* tcgen05 GEMM + fused candidate selection */
+  float rescore_ms;     /* exact fp32 rescoring + sort + certificate */
+  float fallback_ms;    /* exact path for rows whose certificate failed */
+  float merge_ms;       /* running top-k merge across chunks */
+  float total_ms;
+  int64_t gemm_launches;
+  int64_t kernel_launches; /* all kernels of this library in the call */
+  int64_t flagged_rows;    /* rows sent through the exact fallback */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+} kdi_timings;
+
+/* ---- context ----------------------------------------------------------- */
+int kdi_version(void);
+int kdi_init(int device, kdi_ctx** out);
+int kdi_destroy(kdi_ctx* ctx);
+/* message of the last failure on ctx (ctx may be NULL: last kdi_init failure) */
+const char* kdi_last_error(const kdi_ctx* ctx);
+int kdi_set_option(kdi_ctx* ctx, int option, double value);
+int kdi_get_timings(const kdi_ctx* ctx, kdi_timings* out);
+int kdi_device_info(const kdi_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
+                    int64_t* total_mem);
+/* the cudaStream_t every kernel of ctx is launched on (for CUDA-event timing by the caller) */
+int kdi_stream(const kdi_ctx* ctx, void** stream);
+
+/* pinned host memory for fast H2D/D2H (what bench.py's e2e leg stages inputs in) */
+int kdi_host_alloc(kdi_ctx* ctx, int64_t bytes, void** out);
+int kdi_host_free(kdi_ctx* ctx, void* p);
+
+/* ---- signal mask: _mask_patterns, _normalized_cross_correlation.py:185-188 --
+ * mask: S bytes on the host, nonzero = pixel excluded.  NULL clears the mask.
+ * Applies to pattern sets created afterwards. */
+int kdi_set_signal_mask(kdi_ctx* ctx, const uint8_t* mask, int64_t S);
+
+/* ---- prepare_experimental / prepare_dictionary ---------------------------
+ * (_normalized_cross_correlation.py:88-159, _normalized_dot_product.py:80-150)
+ * src: rows x S elements of src_dtype, row-major, host or device.
+ * row_mask: optional `rows` bytes on the host, nonzero = row excluded (the
+ * navigation mask, _normalized_cross_correlation.py:117-118).
+ * Produces, on the device, the normalised fp32 rows (what the reference's
+ * prepare_* returns) and their 16-bit tensor-core operand copy. */
+int kdi_patterns_create(kdi_ctx* ctx, const void* src, int src_loc, int src_dtype,
+                        int64_t rows, int64_t S, int metric, const uint8_t* row_mask,
+                        kdi_patterns** out);
+int kdi_patterns_shape(const kdi_patterns* p, int64_t* rows, int64_t* s_eff);
+/* copy the normalised fp32 rows (rows x s_eff) to the host - parity checks of the prepare step */
+int kdi_patterns_read(kdi_ctx* ctx, const kdi_patterns* p, float* dst_host);
+int kdi_patterns_destroy(kdi_ctx* ctx, kdi_patterns* p);
+
+/* ---- _match_chunk: match + argtopk + topk ---------------------------------
+ * (indexing/_dictionary_indexing.py:172-203)
+ * For every experimental row: the keep_n best dictionary rows, best first.
+ * scores_out: rows x keep_n float32; indices_out: rows x keep_n int64 =
+ * dictionary row + index_offset (the `+= start` of _dictionary_indexing.py:118).
+ * keep_n must be <= number of dictionary rows. */
+int kdi_match_topk(kdi_ctx* ctx, const kdi_patterns* experimental,
+                   const kdi_patterns* dictionary, int keep_n, int64_t index_offset,
+                   float* scores_out, int64_t* indices_out, int out_loc);
+
+/* ---- full similarity block (SimilarityMetric.match / __call__) ------------
+ * out: exp_rows x dict_rows float32, host or device.  Exact fp32 scores; meant
+ * for small blocks (tests, metric(exp, dict) calls), not for indexing. */
+int kdi_match_full(kdi_ctx* ctx, const kdi_patterns* experimental,
+                   const kdi_patterns* dictionary, float* out, int out_loc);
+
+/* validation aid: the raw tensor-core block, out_host[i*dict_rows + j] = sum_k a16[i][k]*b16[j][k]
+ * (16-bit operands = normalised rows * 256, fp32 accumulate), through the same TMA/tcgen05
+ * pipeline as kdi_match_topk but without the fused selection.  Small blocks only. */
+int kdi_debug_gemm16(kdi_ctx* ctx, const kdi_patterns* experimental,
+                     const kdi_patterns* dictionary, float* out_host);
+
+/* ---- running top-k merge across chunks / shards ---------------------------
+ * (indexing/_dictionary_indexing.py:120-128; also the cross-GPU merge)
+ * Merge n_lists ranked lists per row (each rows x k_in, best first, laid out
+ * list-major: list l starts at l*rows*k_in) into the best k_out per row.
+ * All pointers on the device when loc == KDI_DEVICE, else host. */
+int kdi_merge_topk(kdi_ctx* ctx, int64_t rows, int n_lists, int k_in,
+                   const float* scores_in, const int64_t* indices_in, int k_out,
+                   float* scores_out, int64_t* indices_out, int loc);
+
+/* ---- the whole driver on host (or device) buffers --------------------------
+ * (indexing/_dictionary_indexing.py:36-139: prepare once, loop over dictionary
+ * chunks of n_per_iteration rows, per-chunk top-k, running merge)
+ * experimental: exp_rows x S of exp_dtype; dictionary: dict_rows x S of
+ * dict_dtype.  nav_mask: optional exp_rows bytes (nonzero = excluded).
+ * Outputs hold one row per NON-excluded experimental row.  Dictionary chunks
+ * are streamed (H2D of chunk i+1 overlaps compute of chunk i). */
+int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
+                            int exp_dtype, int64_t exp_rows, const void* dictionary,
+                            int dict_loc, int dict_dtype, int64_t dict_rows, int64_t S,
+                            int metric, int keep_n, int64_t n_per_iteration,
+                            const uint8_t* nav_mask, int64_t index_offset,
+                            float* scores_out, int64_t* indices_out, int out_loc);
+
+/* ---- orientation similarity map --------------------------------------------
+ * (indexing/_orientation_similarity_map.py:30-152)
+ * indices: (ny*nx) x keep_n int64 on the host.  footprint: fy x fx bytes
+ * (nonzero = use), center_index = flat index of the centre among the truthy
+ * footprint entries.  out: ny x nx x (n_best - from_n_best + 1) float32 on the
+ * host, layer 0 = n_best (reference ordering, :115-126). */
+int kdi_orientation_similarity_map(kdi_ctx* ctx, const int64_t* indices, int64_t ny,
+                                   int64_t nx, int keep_n, int n_best, int from_n_best,
+                                   int normalize, const uint8_t* footprint, int fy, int fx,
+                                   int center_index, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDI_H_ */

@@ -1,0 +1,32 @@
+"""B200-native EBSD dictionary indexing behind kikuchipy's plugin surface.
+
+Only the dictionary-indexing hot path is implemented: the
+``SimilarityMetric`` classes, ``dictionary_indexing`` and ``orientation_similarity_map``.
+Everything numerical runs in ``libkdi.so`` (hand-written sm_100a CUDA behind the C ABI in
+``include/kdi.h``); importing this package does not need a GPU, calling it does.
+"""
+
+from ._lib import Context, KdiError, default_context
+from .indexing import DictionaryIndexingResult, dictionary_indexing, orientation_similarity_map
+from .similarity_metrics import (
+    NormalizedCrossCorrelationMetric,
+    NormalizedDotProductMetric,
+    SimilarityMetric,
+)
+from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
+
+__all__ = [
+    "Context",
+    "DictionaryIndexingResult",
+    "KdiError",
+    "NormalizedCrossCorrelationMetric",
+    "NormalizedDotProductMetric",
+    "SimilarityMetric",
+    "default_context",
+    "dictionary_indexing",
+    "dictionary_indexing_sharded",
+    "gather_topk",
+    "orientation_similarity_map",
+    "shard_bounds",
+]
+__version__ = "0.1.0"

@@ -1,0 +1,398 @@
+"""ctypes binding of ``libkdi.so`` (the C ABI declared in ``include/kdi.h``).
+
+There is deliberately no fallback: if the shared library has not been built, or no CUDA device
+is present, the calls below raise.  Build with ``python -c "import __graft_entry__ as g;
+g.build()"`` (or ``make -C kikuchipy_b200/csrc``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkdi.so")
+
+KDI_OK = 0
+KDI_EINVAL = -1
+KDI_ECUDA = -2
+KDI_ENOMEM = -3
+KDI_EUNSUPPORTED = -4
+KDI_EINTERNAL = -5
+
+KDI_U8, KDI_U16, KDI_F32, KDI_F64 = 0, 1, 2, 3
+KDI_NCC, KDI_NDP = 0, 1
+KDI_HOST, KDI_DEVICE = 0, 1
+
+OPT_COMPUTE_DTYPE = 0
+OPT_CERT_SIGMAS = 1
+OPT_FORCE_EXACT = 2
+OPT_CTA_GROUP = 3
+OPT_STRIP_TILES = 4
+OPT_SUPERBLOCK = 5
+
+_DTYPES = {
+    np.dtype(np.uint8): KDI_U8,
+    np.dtype(np.uint16): KDI_U16,
+    np.dtype(np.float32): KDI_F32,
+    np.dtype(np.float64): KDI_F64,
+}
+_TORCH_DTYPES = {"torch.uint8": KDI_U8, "torch.float32": KDI_F32, "torch.float64": KDI_F64,
+                 "torch.uint16": KDI_U16}
+
+
+class Timings(C.Structure):
+    _fields_ = [
+        ("normalize_exp_ms", C.c_float),
+        ("normalize_dict_ms", C.c_float),
+        ("gemm_topk_ms", C.c_float),
+        ("rescore_ms", C.c_float),
+        ("fallback_ms", C.c_float),
+        ("merge_ms", C.c_float),
+        ("total_ms", C.c_float),
+        ("gemm_launches", C.c_int64),
+        ("kernel_launches", C.c_int64),
+        ("flagged_rows", C.c_int64),
+        ("h2d_bytes", C.c_int64),
+        ("d2h_bytes", C.c_int64),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# every symbol include/kdi.h declares: name -> (restype, argtypes)
+_vp, _i, _i64, _f32p = C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_float)
+_i64p, _u8p = C.POINTER(C.c_int64), C.POINTER(C.c_uint8)
+SIGNATURES = {
+    "kdi_version": (_i, []),
+    "kdi_init": (_i, [_i, C.POINTER(_vp)]),
+    "kdi_destroy": (_i, [_vp]),
+    "kdi_last_error": (C.c_char_p, [_vp]),
+    "kdi_set_option": (_i, [_vp, _i, C.c_double]),
+    "kdi_get_timings": (_i, [_vp, C.POINTER(Timings)]),
+    "kdi_device_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i64p]),
+    "kdi_stream": (_i, [_vp, C.POINTER(_vp)]),
+    "kdi_host_alloc": (_i, [_vp, _i64, C.POINTER(_vp)]),
+    "kdi_host_free": (_i, [_vp, _vp]),
+    "kdi_set_signal_mask": (_i, [_vp, _vp, _i64]),
+    "kdi_patterns_create": (_i, [_vp, _vp, _i, _i, _i64, _i64, _i, _vp, C.POINTER(_vp)]),
+    "kdi_patterns_shape": (_i, [_vp, _i64p, _i64p]),
+    "kdi_patterns_read": (_i, [_vp, _vp, _vp]),
+    "kdi_patterns_destroy": (_i, [_vp, _vp]),
+    "kdi_match_topk": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _i]),
+    "kdi_match_full": (_i, [_vp, _vp, _vp, _vp, _i]),
+    "kdi_debug_gemm16": (_i, [_vp, _vp, _vp, _vp]),
+    "kdi_merge_topk": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _i]),
+    "kdi_dictionary_indexing": (
+        _i,
+        [_vp, _vp, _i, _i, _i64, _vp, _i, _i, _i64, _i64, _i, _i, _i64, _vp, _i64, _vp, _vp, _i],
+    ),
+    "kdi_orientation_similarity_map": (
+        _i,
+        [_vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
+    ),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load():
+    """Load ``libkdi.so`` and declare its signatures.  Raises if it is missing."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} has not been built; there is no CPU fallback. Build it with "
+                "`make -C kikuchipy_b200/csrc` or `__graft_entry__.build()`."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+class KdiError(RuntimeError):
+    """CUDA / internal failure reported by libkdi."""
+
+
+def _raise(code: int, msg: str):
+    if code == KDI_EINVAL:
+        raise ValueError(msg)
+    if code == KDI_ENOMEM:
+        raise MemoryError(msg)
+    if code == KDI_EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise KdiError(f"libkdi error {code}: {msg}")
+
+
+def _buffer(x):
+    """(pointer, location, dtype code, keep-alive object) of a NumPy array or CUDA torch tensor."""
+    if hasattr(x, "data_ptr") and hasattr(x, "is_cuda"):  # torch tensor
+        if not x.is_contiguous():
+            x = x.contiguous()
+        code = _TORCH_DTYPES.get(str(x.dtype))
+        if code is None:
+            raise ValueError(f"unsupported tensor dtype {x.dtype}")
+        if x.is_cuda:
+            import torch
+
+            torch.cuda.current_stream(x.device).synchronize()
+            return x.data_ptr(), KDI_DEVICE, code, x
+        return x.data_ptr(), KDI_HOST, code, x
+    a = np.asarray(x)
+    if a.dtype not in _DTYPES:
+        a = a.astype(np.float32)  # the reference casts to the metric dtype first anyway
+    a = np.ascontiguousarray(a)
+    return a.ctypes.data, KDI_HOST, _DTYPES[a.dtype], a
+
+
+class Patterns:
+    """Device-resident prepared (normalised) pattern set: what ``prepare_*`` returns."""
+
+    def __init__(self, ctx: "Context", handle: int):
+        self._ctx = ctx
+        self._h = handle
+        rows, s_eff = C.c_int64(), C.c_int64()
+        ctx._lib.kdi_patterns_shape(handle, C.byref(rows), C.byref(s_eff))
+        self.shape = (rows.value, s_eff.value)
+
+    def __array__(self, dtype=None, copy=None):
+        out = np.empty(self.shape, dtype=np.float32)
+        self._ctx._check(self._ctx._lib.kdi_patterns_read(self._ctx._h, self._h, out.ctypes.data))
+        return out if dtype is None else out.astype(dtype)
+
+    def compute(self):
+        return np.asarray(self)
+
+    def close(self):
+        if self._h:
+            self._ctx._lib.kdi_patterns_destroy(self._ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One libkdi context = one (process, device)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = _vp()
+        rc = self._lib.kdi_init(device, C.byref(h))
+        if rc != KDI_OK:
+            _raise(rc, (self._lib.kdi_last_error(None) or b"").decode())
+        self._h = h.value
+        self.device = device
+        self._signal_mask_key = None
+
+    # -- plumbing -------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != KDI_OK:
+            _raise(rc, (self._lib.kdi_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if self._h:
+            self._lib.kdi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, option: int, value: float):
+        self._check(self._lib.kdi_set_option(self._h, option, float(value)))
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self._lib.kdi_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def device_info(self) -> dict:
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        self._check(self._lib.kdi_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    def stream_handle(self) -> int:
+        s = _vp()
+        self._check(self._lib.kdi_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """NumPy array backed by pinned host memory (freed with the context)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = _vp()
+        self._check(self._lib.kdi_host_alloc(self._h, n, C.byref(p)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self.__dict__.setdefault("_pinned", []).append((p.value, buf))
+        return arr
+
+    # -- masks and pattern sets ---------------------------------------------------
+    def set_signal_mask(self, mask):
+        if mask is None:
+            self._check(self._lib.kdi_set_signal_mask(self._h, None, 0))
+            return
+        m = np.ascontiguousarray(np.asarray(mask).ravel().astype(np.uint8))
+        self._check(self._lib.kdi_set_signal_mask(self._h, m.ctypes.data, m.size))
+
+    def patterns(self, data, rows: int, metric: int, row_mask=None) -> Patterns:
+        """cast -> reshape (rows, -1) -> row mask -> signal mask -> normalise, on the device."""
+        ptr, loc, code, keep = _buffer(data)
+        n = int(np.prod(data.shape))
+        if rows < 1 or n % rows:
+            raise ValueError(f"cannot reshape array of size {n} into ({rows}, -1)")
+        S = n // rows
+        rm = None
+        if row_mask is not None:
+            rm = np.ascontiguousarray(np.asarray(row_mask).ravel().astype(np.uint8))
+            if rm.size != rows:
+                raise ValueError("navigation mask size does not match the number of patterns")
+        h = _vp()
+        self._check(
+            self._lib.kdi_patterns_create(
+                self._h, ptr, loc, code, rows, S, metric, rm.ctypes.data if rm is not None else None, C.byref(h)
+            )
+        )
+        del keep
+        return Patterns(self, h.value)
+
+    # -- matching ------------------------------------------------------------------
+    def match_topk(self, exp: Patterns, dic: Patterns, keep_n: int, index_offset: int = 0):
+        m = exp.shape[0]
+        scores = np.empty((m, keep_n), dtype=np.float32)
+        idx = np.empty((m, keep_n), dtype=np.int64)
+        self._check(
+            self._lib.kdi_match_topk(
+                self._h, exp._h, dic._h, keep_n, index_offset, scores.ctypes.data, idx.ctypes.data, KDI_HOST
+            )
+        )
+        return idx, scores
+
+    def match_full(self, exp: Patterns, dic: Patterns) -> np.ndarray:
+        out = np.empty((exp.shape[0], dic.shape[0]), dtype=np.float32)
+        self._check(self._lib.kdi_match_full(self._h, exp._h, dic._h, out.ctypes.data, KDI_HOST))
+        return out
+
+    def debug_gemm16(self, exp: Patterns, dic: Patterns) -> np.ndarray:
+        out = np.empty((exp.shape[0], dic.shape[0]), dtype=np.float32)
+        self._check(self._lib.kdi_debug_gemm16(self._h, exp._h, dic._h, out.ctypes.data))
+        return out
+
+    def merge_topk(self, scores, indices, k_out: int):
+        """Merge ``(n_lists, rows, k_in)`` ranked lists into ``(rows, k_out)``.
+
+        NumPy arrays are staged through the device; CUDA torch tensors are merged in place on
+        the device and CUDA tensors are returned.
+        """
+        if hasattr(scores, "is_cuda") and scores.is_cuda:
+            import torch
+
+            n_lists, rows, k_in = scores.shape
+            scores = scores.contiguous()
+            indices = indices.contiguous()
+            so = torch.empty((rows, k_out), dtype=torch.float32, device=scores.device)
+            io = torch.empty((rows, k_out), dtype=torch.int64, device=scores.device)
+            torch.cuda.current_stream(scores.device).synchronize()
+            self._check(
+                self._lib.kdi_merge_topk(
+                    self._h, rows, n_lists, k_in, scores.data_ptr(), indices.data_ptr(), k_out,
+                    so.data_ptr(), io.data_ptr(), KDI_DEVICE,
+                )
+            )
+            return io, so
+        s = np.ascontiguousarray(scores, dtype=np.float32)
+        i = np.ascontiguousarray(indices, dtype=np.int64)
+        n_lists, rows, k_in = s.shape
+        so = np.empty((rows, k_out), dtype=np.float32)
+        io = np.empty((rows, k_out), dtype=np.int64)
+        self._check(
+            self._lib.kdi_merge_topk(
+                self._h, rows, n_lists, k_in, s.ctypes.data, i.ctypes.data, k_out, so.ctypes.data,
+                io.ctypes.data, KDI_HOST,
+            )
+        )
+        return io, so
+
+    def dictionary_indexing(
+        self, experimental, exp_rows: int, dictionary, dict_rows: int, metric: int, keep_n: int,
+        n_per_iteration: int = 0, nav_mask=None, index_offset: int = 0, out=None,
+    ):
+        """The whole driver on raw buffers (host NumPy / pinned, or CUDA torch tensors)."""
+        eptr, eloc, ecode, ekeep = _buffer(experimental)
+        dptr, dloc, dcode, dkeep = _buffer(dictionary)
+        n_e = int(np.prod(experimental.shape))
+        n_d = int(np.prod(dictionary.shape))
+        if exp_rows < 1 or n_e % exp_rows or dict_rows < 1 or n_d % dict_rows:
+            raise ValueError("pattern arrays cannot be reshaped to (rows, -1)")
+        S = n_e // exp_rows
+        if n_d // dict_rows != S:
+            raise ValueError(f"Experimental ({S}) and dictionary ({n_d // dict_rows}) signal sizes must be identical")
+        rm = None
+        kept = exp_rows
+        if nav_mask is not None:
+            rm = np.ascontiguousarray(np.asarray(nav_mask).ravel().astype(np.uint8))
+            kept = int((rm == 0).sum())
+        if out is None:
+            scores = np.empty((kept, keep_n), dtype=np.float32)
+            idx = np.empty((kept, keep_n), dtype=np.int64)
+            sptr, iptr, oloc = scores.ctypes.data, idx.ctypes.data, KDI_HOST
+        else:
+            idx, scores = out
+            if hasattr(scores, "is_cuda") and scores.is_cuda:
+                sptr, iptr, oloc = scores.data_ptr(), idx.data_ptr(), KDI_DEVICE
+            else:
+                sptr, iptr, oloc = scores.ctypes.data, idx.ctypes.data, KDI_HOST
+        self._check(
+            self._lib.kdi_dictionary_indexing(
+                self._h, eptr, eloc, ecode, exp_rows, dptr, dloc, dcode, dict_rows, S, metric, keep_n,
+                int(n_per_iteration or 0), rm.ctypes.data if rm is not None else None, index_offset,
+                sptr, iptr, oloc,
+            )
+        )
+        del ekeep, dkeep
+        return idx, scores
+
+    def orientation_similarity_map(self, indices, ny, nx, n_best, from_n_best, normalize, footprint, center_index):
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        keep_n = idx.shape[1]
+        fp = np.ascontiguousarray(np.asarray(footprint).astype(bool).astype(np.uint8))
+        out = np.empty((ny, nx, n_best - from_n_best + 1), dtype=np.float32)
+        self._check(
+            self._lib.kdi_orientation_similarity_map(
+                self._h, idx.ctypes.data, ny, nx, keep_n, n_best, from_n_best, int(bool(normalize)),
+                fp.ctypes.data, fp.shape[0], fp.shape[1], center_index, out.ctypes.data,
+            )
+        )
+        return out
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int | None = None) -> Context:
+    """Process-wide context for ``device`` (default: ``LOCAL_RANK`` or 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = _default_ctx.get(device)
+    if ctx is None or ctx._h is None:
+        ctx = Context(device)
+        _default_ctx[device] = ctx
+    return ctx

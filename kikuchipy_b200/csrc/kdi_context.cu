@@ -1,0 +1,360 @@
+// Context, error handling, options, pinned memory, signal mask and pattern-set management
+// of libkdi (see include/kdi.h for the contract of every entry point).
+#include "kdi_internal.cuh"
+
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+namespace {
+std::mutex g_init_mutex;
+std::string g_init_error;
+}  // namespace
+
+void kdi_set_error(kdi_ctx* ctx, const char* msg) {
+  if (ctx) {
+    ctx->err = msg;
+  } else {
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    g_init_error = msg;
+  }
+}
+
+int kdi_fail(kdi_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  kdi_set_error(ctx, buf);
+  return code;
+}
+
+static int reserve(kdi_ctx* ctx, void** p, size_t* have, size_t bytes) {
+  if (bytes <= *have) return KDI_OK;
+  if (*p) {
+    KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KDI_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    KDI_CUDA(ctx, cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+  }
+  // grow geometrically so repeated calls with slowly growing sizes do not thrash
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(p, want);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *p = nullptr;
+    return kdi_fail(ctx, KDI_ENOMEM, "device allocation of %zu bytes failed: %s", bytes,
+                    cudaGetErrorString(e));
+  }
+  *have = want;
+  return KDI_OK;
+}
+
+int kdi_ws_reserve(kdi_ctx* ctx, size_t bytes) { return reserve(ctx, &ctx->ws, &ctx->ws_bytes, bytes); }
+int kdi_ws2_reserve(kdi_ctx* ctx, size_t bytes) {
+  return reserve(ctx, &ctx->ws2, &ctx->ws2_bytes, bytes);
+}
+
+extern "C" {
+
+int kdi_version(void) { return KDI_VERSION; }
+
+int kdi_init(int device, kdi_ctx** out) {
+  if (!out) return kdi_fail(nullptr, KDI_EINVAL, "kdi_init: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return kdi_fail(nullptr, KDI_ECUDA,
+                    "kdi_init: no CUDA device available (%s); libkdi has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= n)
+    return kdi_fail(nullptr, KDI_EINVAL, "kdi_init: device %d out of range [0, %d)", device, n);
+  kdi_ctx* ctx = new kdi_ctx();
+  ctx->device = device;
+#define INIT_CUDA(call)                                                                     \
+  do {                                                                                      \
+    cudaError_t e2 = (call);                                                                \
+    if (e2 != cudaSuccess) {                                                                \
+      int rc = kdi_fail(nullptr, KDI_ECUDA, "kdi_init: %s failed: %s", #call,               \
+                        cudaGetErrorString(e2));                                            \
+      delete ctx;                                                                           \
+      return rc;                                                                            \
+    }                                                                                       \
+  } while (0)
+  INIT_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  INIT_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  ctx->total_mem = prop.totalGlobalMem;
+  INIT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  INIT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : ctx->ev) INIT_CUDA(cudaEventCreate(&ev));
+  for (auto& ev : ctx->copy_ev) INIT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : ctx->free_ev) INIT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+#undef INIT_CUDA
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    ctx->encode_tiled = fn;
+  else
+    cudaGetLastError();
+  *out = ctx;
+  return KDI_OK;
+}
+
+int kdi_destroy(kdi_ctx* ctx) {
+  if (!ctx) return KDI_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->ws2) cudaFree(ctx->ws2);
+  if (ctx->d_cols) cudaFree(ctx->d_cols);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->copy_ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->free_ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return KDI_OK;
+}
+
+const char* kdi_last_error(const kdi_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  return g_init_error.c_str();
+}
+
+int kdi_set_option(kdi_ctx* ctx, int option, double value) {
+  if (!ctx) return KDI_EINVAL;
+  switch (option) {
+    case KDI_OPT_COMPUTE_DTYPE:
+      if (value != 0 && value != 1) return kdi_fail(ctx, KDI_EINVAL, "compute dtype must be 0 (fp16) or 1 (bf16)");
+      ctx->compute_dtype = (int)value;
+      return KDI_OK;
+    case KDI_OPT_CERT_SIGMAS:
+      if (!(value > 0)) return kdi_fail(ctx, KDI_EINVAL, "certificate width must be positive");
+      ctx->cert_sigmas = value;
+      return KDI_OK;
+    case KDI_OPT_FORCE_EXACT:
+      ctx->force_exact = value != 0;
+      return KDI_OK;
+    case KDI_OPT_CTA_GROUP:
+      if (value != 1 && value != 2) return kdi_fail(ctx, KDI_EINVAL, "cta_group must be 1 or 2");
+      ctx->cta_group = (int)value;
+      return KDI_OK;
+    case KDI_OPT_STRIP_TILES:
+      if (value < 0) return kdi_fail(ctx, KDI_EINVAL, "strip_tiles must be >= 0");
+      ctx->strip_tiles = (int)value;
+      return KDI_OK;
+    case KDI_OPT_SUPERBLOCK:
+      if (value < 0) return kdi_fail(ctx, KDI_EINVAL, "superblock must be >= 0");
+      ctx->superblock = (int)value;
+      return KDI_OK;
+    default:
+      return kdi_fail(ctx, KDI_EINVAL, "unknown option %d", option);
+  }
+}
+
+int kdi_get_timings(const kdi_ctx* ctx, kdi_timings* out) {
+  if (!ctx || !out) return KDI_EINVAL;
+  *out = ctx->tm;
+  return KDI_OK;
+}
+
+int kdi_device_info(const kdi_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
+                    int64_t* total_mem) {
+  if (!ctx) return KDI_EINVAL;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (total_mem) *total_mem = (int64_t)ctx->total_mem;
+  return KDI_OK;
+}
+
+int kdi_stream(const kdi_ctx* ctx, void** stream) {
+  if (!ctx || !stream) return KDI_EINVAL;
+  *stream = (void*)ctx->stream;
+  return KDI_OK;
+}
+
+int kdi_host_alloc(kdi_ctx* ctx, int64_t bytes, void** out) {
+  if (!ctx || !out || bytes < 0) return KDI_EINVAL;
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  KDI_CUDA(ctx, cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+  return KDI_OK;
+}
+
+int kdi_host_free(kdi_ctx* ctx, void* p) {
+  if (!ctx) return KDI_EINVAL;
+  if (p) KDI_CUDA(ctx, cudaFreeHost(p));
+  return KDI_OK;
+}
+
+int kdi_set_signal_mask(kdi_ctx* ctx, const uint8_t* mask, int64_t S) {
+  if (!ctx) return KDI_EINVAL;
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->d_cols) {
+    KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KDI_CUDA(ctx, cudaFree(ctx->d_cols));
+    ctx->d_cols = nullptr;
+  }
+  ctx->mask_S = 0;
+  ctx->mask_kept = 0;
+  if (!mask) return KDI_OK;
+  if (S <= 0 || S > 0x7fffffffLL) return kdi_fail(ctx, KDI_EINVAL, "signal mask size %lld invalid", (long long)S);
+  std::vector<int32_t> cols;
+  cols.reserve((size_t)S);
+  for (int64_t j = 0; j < S; ++j)
+    if (!mask[j]) cols.push_back((int32_t)j);  // False = keep (_similarity_metric.py:55-58)
+  if (cols.empty()) return kdi_fail(ctx, KDI_EINVAL, "signal mask excludes every pixel");
+  KDI_CUDA(ctx, cudaMalloc(&ctx->d_cols, cols.size() * sizeof(int32_t)));
+  KDI_CUDA(ctx, cudaMemcpy(ctx->d_cols, cols.data(), cols.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  ctx->mask_S = S;
+  ctx->mask_kept = (int64_t)cols.size();
+  return KDI_OK;
+}
+
+}  // extern "C"
+
+// ---- pattern sets ------------------------------------------------------------------------
+
+int kdi_patterns_alloc(kdi_ctx* ctx, int64_t rows, int64_t S, int metric, kdi_patterns** out) {
+  if (rows < 0 || S <= 0) return kdi_fail(ctx, KDI_EINVAL, "pattern set of %lld x %lld", (long long)rows, (long long)S);
+  if (metric != KDI_NCC && metric != KDI_NDP) return kdi_fail(ctx, KDI_EINVAL, "unknown metric %d", metric);
+  if (ctx->mask_S && ctx->mask_S != S)
+    return kdi_fail(ctx, KDI_EINVAL, "signal mask has %lld pixels but patterns have %lld",
+                    (long long)ctx->mask_S, (long long)S);
+  kdi_patterns* p = new kdi_patterns();
+  p->rows = rows;
+  p->S = S;
+  p->s_eff = ctx->mask_S ? ctx->mask_kept : S;
+  p->s_pitch = kdi_round_up(p->s_eff, 4);
+  p->kp = kdi_round_up(p->s_eff, KDI_TILE_K);
+  p->metric = metric;
+  p->compute_dtype = ctx->compute_dtype;
+  const size_t n32 = (size_t)(rows > 0 ? rows : 1) * p->s_pitch * sizeof(float);
+  const size_t n16 = (size_t)(rows > 0 ? rows : 1) * p->kp * 2;
+  cudaError_t e = cudaMalloc(&p->a32, n32);
+  if (e == cudaSuccess) e = cudaMalloc(&p->a16, n16);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (p->a32) cudaFree(p->a32);
+    delete p;
+    return kdi_fail(ctx, KDI_ENOMEM, "device allocation for %lld patterns failed: %s", (long long)rows,
+                    cudaGetErrorString(e));
+  }
+  *out = p;
+  return KDI_OK;
+}
+
+int kdi_patterns_fill(kdi_ctx* ctx, cudaStream_t stream, kdi_patterns* p, int64_t row_offset,
+                      const void* d_src, int src_dtype, int64_t n_rows, const int64_t* d_rowmap) {
+  if (row_offset < 0 || row_offset + n_rows > p->rows)
+    return kdi_fail(ctx, KDI_EINTERNAL, "pattern fill out of range");
+  return kdi_launch_normalize(ctx, stream, d_src, src_dtype, p->S, d_rowmap,
+                              ctx->mask_S ? ctx->d_cols : nullptr, n_rows, p->s_eff, p->metric,
+                              p->compute_dtype, p->a32 + row_offset * p->s_pitch, p->s_pitch,
+                              reinterpret_cast<uint16_t*>(p->a16) + row_offset * p->kp, p->kp);
+}
+
+extern "C" {
+
+int kdi_patterns_create(kdi_ctx* ctx, const void* src, int src_loc, int src_dtype, int64_t rows,
+                        int64_t S, int metric, const uint8_t* row_mask, kdi_patterns** out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!out || !src) return kdi_fail(ctx, KDI_EINVAL, "kdi_patterns_create: NULL argument");
+  *out = nullptr;
+  const size_t esz = kdi_dtype_size(src_dtype);
+  if (!esz) return kdi_fail(ctx, KDI_EINVAL, "unknown source dtype %d", src_dtype);
+  if (rows < 0 || S <= 0) return kdi_fail(ctx, KDI_EINVAL, "bad shape %lld x %lld", (long long)rows, (long long)S);
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  // navigation mask: rows kept are those with a zero byte (False = keep)
+  std::vector<int64_t> keep;
+  int64_t kept = rows;
+  if (row_mask) {
+    keep.reserve((size_t)rows);
+    for (int64_t i = 0; i < rows; ++i)
+      if (!row_mask[i]) keep.push_back(i);
+    kept = (int64_t)keep.size();
+  }
+  kdi_patterns* p = nullptr;
+  KDI_TRY(kdi_patterns_alloc(ctx, kept, S, metric, &p));
+  int rc = KDI_OK;
+  int64_t* d_rowmap = nullptr;
+  do {
+    if (kept == 0) break;
+    const void* d_src = src;
+    if (src_loc == KDI_HOST) {
+      const size_t bytes = (size_t)rows * S * esz;
+      if ((rc = kdi_ws2_reserve(ctx, bytes)) != KDI_OK) break;
+      cudaError_t e = cudaMemcpyAsync(ctx->ws2, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { rc = kdi_fail(ctx, KDI_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+      ctx->tm.h2d_bytes += (int64_t)bytes;
+      d_src = ctx->ws2;
+    } else if (src_loc != KDI_DEVICE) {
+      rc = kdi_fail(ctx, KDI_EINVAL, "bad buffer location %d", src_loc);
+      break;
+    }
+    if (row_mask) {
+      cudaError_t e = cudaMalloc(&d_rowmap, keep.size() * sizeof(int64_t));
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_rowmap, keep.data(), keep.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { rc = kdi_fail(ctx, KDI_ECUDA, "row map upload failed: %s", cudaGetErrorString(e)); break; }
+    }
+    if ((rc = kdi_patterns_fill(ctx, ctx->stream, p, 0, d_src, src_dtype, kept, d_rowmap)) != KDI_OK) break;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { rc = kdi_fail(ctx, KDI_ECUDA, "normalise failed: %s", cudaGetErrorString(e)); break; }
+  } while (0);
+  if (d_rowmap) cudaFree(d_rowmap);
+  if (rc != KDI_OK) {
+    kdi_patterns_destroy(ctx, p);
+    return rc;
+  }
+  *out = p;
+  return KDI_OK;
+}
+
+int kdi_patterns_shape(const kdi_patterns* p, int64_t* rows, int64_t* s_eff) {
+  if (!p) return KDI_EINVAL;
+  if (rows) *rows = p->rows;
+  if (s_eff) *s_eff = p->s_eff;
+  return KDI_OK;
+}
+
+int kdi_patterns_read(kdi_ctx* ctx, const kdi_patterns* p, float* dst_host) {
+  if (!ctx) return KDI_EINVAL;
+  if (!p || !dst_host) return kdi_fail(ctx, KDI_EINVAL, "kdi_patterns_read: NULL argument");
+  if (p->rows == 0) return KDI_OK;
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  KDI_CUDA(ctx, cudaMemcpy2D(dst_host, (size_t)p->s_eff * sizeof(float), p->a32,
+                             (size_t)p->s_pitch * sizeof(float), (size_t)p->s_eff * sizeof(float),
+                             (size_t)p->rows, cudaMemcpyDeviceToHost));
+  return KDI_OK;
+}
+
+int kdi_patterns_destroy(kdi_ctx* ctx, kdi_patterns* p) {
+  if (!p) return KDI_OK;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (p->a32) cudaFree(p->a32);
+  if (p->a16) cudaFree(p->a16);
+  delete p;
+  return KDI_OK;
+}
+
+}  // extern "C"

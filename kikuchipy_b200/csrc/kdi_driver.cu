@@ -1,0 +1,340 @@
+// Host-side orchestration of the dictionary-indexing path behind the C ABI:
+// _match_chunk (match + top-k), the chunk loop of _dictionary_indexing, the list merge and the
+// orientation similarity map.  Reference: /root/reference/src/kikuchipy/indexing/
+// _dictionary_indexing.py:36-203, _orientation_similarity_map.py:30-152.
+#include "kdi_internal.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// exact path for a set of rows (rows_list on the device, or the range row0..row0+n_rows-1)
+int exact_rows(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict, const int* d_rows_list,
+               int64_t row0, int64_t n_rows, int keep_n, int64_t index_offset, float* d_scores_out,
+               int64_t* d_idx_out) {
+  const int64_t N = dict->rows;
+  // score blocks of at most ~512 MB
+  int64_t batch = (512ll << 20) / (N * (int64_t)sizeof(float));
+  batch = std::max<int64_t>(4, batch / 4 * 4);
+  batch = std::min<int64_t>(batch, n_rows);
+  KDI_TRY(kdi_ws2_reserve(ctx, (size_t)batch * N * sizeof(float)));
+  float* blk = reinterpret_cast<float*>(ctx->ws2);
+  for (int64_t b = 0; b < n_rows; b += batch) {
+    const int nb = (int)std::min<int64_t>(batch, n_rows - b);
+    const int* list = d_rows_list ? d_rows_list + b : nullptr;
+    KDI_TRY(kdi_launch_exact_scores(ctx, ctx->stream, exp, dict, list, row0 + b, nb, blk));
+    KDI_TRY(kdi_launch_extract_topk(ctx, ctx->stream, blk, nb, N, list, row0 + b, keep_n,
+                                    index_offset, d_scores_out, d_idx_out));
+  }
+  return KDI_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+  return ms;
+}
+
+}  // namespace
+
+// match + top-k of device-resident pattern sets; outputs on host or device
+int kdi_match_topk_device(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict,
+                          int keep_n, int64_t index_offset, float* scores_out,
+                          int64_t* indices_out, int out_loc) {
+  if (!exp || !dict || !scores_out || !indices_out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_match_topk: NULL argument");
+  if (out_loc != KDI_HOST && out_loc != KDI_DEVICE) return kdi_fail(ctx, KDI_EINVAL, "bad output location");
+  if (exp->s_eff != dict->s_eff)
+    return kdi_fail(ctx, KDI_EINVAL, "experimental and dictionary signal sizes differ (%lld vs %lld)",
+                    (long long)exp->s_eff, (long long)dict->s_eff);
+  const int64_t M = exp->rows, N = dict->rows;
+  if (keep_n < 1 || keep_n > N)
+    return kdi_fail(ctx, KDI_EINVAL, "keep_n %d must be in [1, %lld]", keep_n, (long long)N);
+  if (N > 0xFFFFFFFELL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "dictionary too large");
+  if (M == 0) return KDI_OK;
+
+  const bool fused = !ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0;
+  kdi_gemm_plan plan;
+  size_t off_cand = 0, off_thr = 0, off_flags = 0, off_nflag = 0, off_sc = 0, off_ix = 0, total = 0;
+  if (fused) {
+    KDI_TRY(kdi_gemm_make_plan(ctx, M, N, exp->kp, keep_n, &plan));
+    off_cand = 0;
+    off_thr = align_up(off_cand + plan.cand_bytes, 256);
+    off_flags = align_up(off_thr + plan.thr_bytes, 256);
+    off_nflag = align_up(off_flags + (size_t)M * sizeof(int), 256);
+    total = off_nflag + 256;
+  }
+  off_sc = align_up(total, 256);
+  off_ix = align_up(off_sc + (size_t)M * keep_n * sizeof(float), 256);
+  total = off_ix + (size_t)M * keep_n * sizeof(int64_t);
+  KDI_TRY(kdi_ws_reserve(ctx, total));
+  uint8_t* ws = reinterpret_cast<uint8_t*>(ctx->ws);
+  float* d_sc = out_loc == KDI_DEVICE ? scores_out : reinterpret_cast<float*>(ws + off_sc);
+  int64_t* d_ix = out_loc == KDI_DEVICE ? indices_out : reinterpret_cast<int64_t*>(ws + off_ix);
+
+  cudaStream_t st = ctx->stream;
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+  int n_flag = 0;
+  if (fused) {
+    uint2* cand = reinterpret_cast<uint2*>(ws + off_cand);
+    uint32_t* thr = reinterpret_cast<uint32_t*>(ws + off_thr);
+    int* flags = reinterpret_cast<int*>(ws + off_flags);
+    int* d_nflag = reinterpret_cast<int*>(ws + off_nflag);
+    KDI_CUDA(ctx, cudaMemsetAsync(d_nflag, 0, sizeof(int), st));
+    KDI_TRY(kdi_launch_cand_init(ctx, st, thr, M));
+    KDI_TRY(kdi_launch_gemm_topk(ctx, st, exp, dict, &plan, cand, thr));
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    const float inv = 1.0f / (KDI_OP_SCALE * KDI_OP_SCALE);
+    KDI_TRY(kdi_launch_select_rescore(ctx, st, exp, dict, &plan, cand, thr, keep_n, index_offset, inv,
+                                      (float)ctx->cert_sigmas, d_sc, d_ix, flags, d_nflag));
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+    KDI_CUDA(ctx, cudaMemcpyAsync(&n_flag, d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KDI_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n_flag > 0)
+      KDI_TRY(exact_rows(ctx, exp, dict, flags, 0, n_flag, keep_n, index_offset, d_sc, d_ix));
+  } else {
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+    KDI_TRY(exact_rows(ctx, exp, dict, nullptr, 0, M, keep_n, index_offset, d_sc, d_ix));
+  }
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+  if (out_loc == KDI_HOST) {
+    KDI_CUDA(ctx, cudaMemcpyAsync(scores_out, d_sc, (size_t)M * keep_n * sizeof(float),
+                                  cudaMemcpyDeviceToHost, st));
+    KDI_CUDA(ctx, cudaMemcpyAsync(indices_out, d_ix, (size_t)M * keep_n * sizeof(int64_t),
+                                  cudaMemcpyDeviceToHost, st));
+    ctx->tm.d2h_bytes += (int64_t)M * keep_n * 12;
+  }
+  KDI_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->tm.gemm_topk_ms += ev_ms(ctx->ev[2], ctx->ev[3]);
+  ctx->tm.rescore_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
+  ctx->tm.fallback_ms += ev_ms(ctx->ev[4], ctx->ev[5]);
+  ctx->tm.flagged_rows += fused ? n_flag : M;
+  return KDI_OK;
+}
+
+extern "C" {
+
+int kdi_match_topk(kdi_ctx* ctx, const kdi_patterns* experimental, const kdi_patterns* dictionary,
+                   int keep_n, int64_t index_offset, float* scores_out, int64_t* indices_out,
+                   int out_loc) {
+  if (!ctx) return KDI_EINVAL;
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  KDI_TRY(kdi_match_topk_device(ctx, experimental, dictionary, keep_n, index_offset, scores_out,
+                                indices_out, out_loc));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+  return KDI_OK;
+}
+
+int kdi_match_full(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict, float* out,
+                   int out_loc) {
+  if (!ctx) return KDI_EINVAL;
+  if (!exp || !dict || !out) return kdi_fail(ctx, KDI_EINVAL, "kdi_match_full: NULL argument");
+  if (exp->s_eff != dict->s_eff)
+    return kdi_fail(ctx, KDI_EINVAL, "experimental and dictionary signal sizes differ (%lld vs %lld)",
+                    (long long)exp->s_eff, (long long)dict->s_eff);
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t M = exp->rows, N = dict->rows;
+  if (M == 0 || N == 0) return KDI_OK;
+  if (out_loc == KDI_DEVICE) {
+    for (int64_t b = 0; b < M; b += 1 << 20) {
+      const int nb = (int)std::min<int64_t>(1 << 20, M - b);
+      KDI_TRY(kdi_launch_exact_scores(ctx, ctx->stream, exp, dict, nullptr, b, nb, out + b * N));
+    }
+  } else {
+    int64_t batch = std::max<int64_t>(4, (256ll << 20) / (N * 4) / 4 * 4);
+    batch = std::min<int64_t>(batch, M);
+    KDI_TRY(kdi_ws2_reserve(ctx, (size_t)batch * N * sizeof(float)));
+    float* blk = reinterpret_cast<float*>(ctx->ws2);
+    for (int64_t b = 0; b < M; b += batch) {
+      const int nb = (int)std::min<int64_t>(batch, M - b);
+      KDI_TRY(kdi_launch_exact_scores(ctx, ctx->stream, exp, dict, nullptr, b, nb, blk));
+      KDI_CUDA(ctx, cudaMemcpyAsync(out + b * N, blk, (size_t)nb * N * sizeof(float),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+      KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KDI_OK;
+}
+
+int kdi_debug_gemm16(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict, float* out_host) {
+  if (!ctx) return KDI_EINVAL;
+  if (!exp || !dict || !out_host) return kdi_fail(ctx, KDI_EINVAL, "kdi_debug_gemm16: NULL argument");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t M = exp->rows, N = dict->rows;
+  if (M == 0 || N == 0) return KDI_OK;
+  KDI_TRY(kdi_ws2_reserve(ctx, (size_t)M * N * sizeof(float)));
+  float* d = reinterpret_cast<float*>(ctx->ws2);
+  KDI_CUDA(ctx, cudaMemsetAsync(d, 0xFF, (size_t)M * N * sizeof(float), ctx->stream));
+  KDI_TRY(kdi_launch_gemm_full(ctx, ctx->stream, exp, dict, d));
+  KDI_CUDA(ctx, cudaMemcpyAsync(out_host, d, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KDI_OK;
+}
+
+int kdi_merge_topk(kdi_ctx* ctx, int64_t rows, int n_lists, int k_in, const float* scores_in,
+                   const int64_t* indices_in, int k_out, float* scores_out, int64_t* indices_out,
+                   int loc) {
+  if (!ctx) return KDI_EINVAL;
+  if (!scores_in || !indices_in || !scores_out || !indices_out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_merge_topk: NULL argument");
+  if (rows < 0 || n_lists < 1 || k_in < 1) return kdi_fail(ctx, KDI_EINVAL, "kdi_merge_topk: bad shape");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (rows == 0) return KDI_OK;
+  cudaStream_t st = ctx->stream;
+  if (loc == KDI_DEVICE) {
+    KDI_TRY(kdi_launch_merge(ctx, st, rows, n_lists, k_in, scores_in, indices_in, k_out, scores_out, indices_out));
+    KDI_CUDA(ctx, cudaStreamSynchronize(st));
+    return KDI_OK;
+  }
+  if (loc != KDI_HOST) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location %d", loc);
+  const size_t n_in = (size_t)rows * n_lists * k_in, n_out = (size_t)rows * k_out;
+  const size_t o_si = 0, o_ii = align_up(o_si + n_in * 4, 256), o_so = align_up(o_ii + n_in * 8, 256),
+               o_io = align_up(o_so + n_out * 4, 256), total = o_io + n_out * 8;
+  KDI_TRY(kdi_ws2_reserve(ctx, total));
+  uint8_t* w = reinterpret_cast<uint8_t*>(ctx->ws2);
+  KDI_CUDA(ctx, cudaMemcpyAsync(w + o_si, scores_in, n_in * 4, cudaMemcpyHostToDevice, st));
+  KDI_CUDA(ctx, cudaMemcpyAsync(w + o_ii, indices_in, n_in * 8, cudaMemcpyHostToDevice, st));
+  KDI_TRY(kdi_launch_merge(ctx, st, rows, n_lists, k_in, reinterpret_cast<float*>(w + o_si),
+                           reinterpret_cast<int64_t*>(w + o_ii), k_out,
+                           reinterpret_cast<float*>(w + o_so), reinterpret_cast<int64_t*>(w + o_io)));
+  KDI_CUDA(ctx, cudaMemcpyAsync(scores_out, w + o_so, n_out * 4, cudaMemcpyDeviceToHost, st));
+  KDI_CUDA(ctx, cudaMemcpyAsync(indices_out, w + o_io, n_out * 8, cudaMemcpyDeviceToHost, st));
+  KDI_CUDA(ctx, cudaStreamSynchronize(st));
+  return KDI_OK;
+}
+
+int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                            int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
+                            int64_t dict_rows, int64_t S, int metric, int keep_n,
+                            int64_t n_per_iteration, const uint8_t* nav_mask, int64_t index_offset,
+                            float* scores_out, int64_t* indices_out, int out_loc) {
+  if (!ctx) return KDI_EINVAL;
+  if (!experimental || !dictionary || !scores_out || !indices_out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_dictionary_indexing: NULL argument");
+  const size_t dsz = kdi_dtype_size(dict_dtype);
+  if (!dsz || !kdi_dtype_size(exp_dtype)) return kdi_fail(ctx, KDI_EINVAL, "unknown dtype");
+  if (dict_rows < 1 || exp_rows < 0 || S < 1) return kdi_fail(ctx, KDI_EINVAL, "bad shape");
+  if (keep_n < 1 || keep_n > dict_rows)
+    return kdi_fail(ctx, KDI_EINVAL, "keep_n %d must be in [1, %lld]", keep_n, (long long)dict_rows);
+  if (dict_loc != KDI_HOST && dict_loc != KDI_DEVICE) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  cudaStream_t st = ctx->stream;
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+
+  // prepare_experimental - once (_dictionary_indexing.py:70)
+  kdi_patterns* exp = nullptr;
+  KDI_TRY(kdi_patterns_create(ctx, experimental, exp_loc, exp_dtype, exp_rows, S, metric, nav_mask, &exp));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+
+  // prepare_dictionary, streamed.  The reference prepares one chunk of n_per_iteration rows per
+  // iteration (_dictionary_indexing.py:102-117); the result does not depend on the chunking, so
+  // the pieces moved here are sized for the copy engine, not by n_per_iteration.
+  (void)n_per_iteration;
+  kdi_patterns* dict = nullptr;
+  int rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict);
+  if (rc == KDI_OK) {
+    if (dict_loc == KDI_DEVICE) {
+      rc = kdi_patterns_fill(ctx, st, dict, 0, dictionary, dict_dtype, dict_rows, nullptr);
+    } else {
+      const size_t row_bytes = (size_t)S * dsz;
+      int64_t piece = (int64_t)std::max<size_t>(1, (64u << 20) / row_bytes);
+      piece = std::min<int64_t>(piece, dict_rows);
+      const size_t slot_bytes = align_up((size_t)piece * row_bytes, 256);
+      rc = kdi_ws2_reserve(ctx, 2 * slot_bytes);
+      uint8_t* stage = reinterpret_cast<uint8_t*>(ctx->ws2);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(dictionary);
+      int it = 0;
+      for (int64_t r0 = 0; rc == KDI_OK && r0 < dict_rows; r0 += piece, ++it) {
+        const int slot = it & 1;
+        const int64_t nr = std::min<int64_t>(piece, dict_rows - r0);
+        cudaError_t e = cudaSuccess;
+        // the slot is free once the normalise that read it two pieces ago has finished
+        if (it >= 2) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->free_ev[slot], 0);
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(stage + slot * slot_bytes, src + (size_t)r0 * row_bytes,
+                              (size_t)nr * row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->copy_ev[slot], 0);
+        if (e != cudaSuccess) {
+          rc = kdi_fail(ctx, KDI_ECUDA, "dictionary upload failed: %s", cudaGetErrorString(e));
+          break;
+        }
+        ctx->tm.h2d_bytes += (int64_t)nr * (int64_t)row_bytes;
+        rc = kdi_patterns_fill(ctx, st, dict, r0, stage + slot * slot_bytes, dict_dtype, nr, nullptr);
+        if (rc == KDI_OK && cudaEventRecord(ctx->free_ev[slot], st) != cudaSuccess)
+          rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+      }
+    }
+  }
+  if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+  // match + top-k + merge
+  if (rc == KDI_OK) {
+    const kdi_timings keep = ctx->tm;
+    (void)keep;
+    rc = kdi_match_topk_device(ctx, exp, dict, keep_n, index_offset, scores_out, indices_out, out_loc);
+  }
+  if (rc == KDI_OK) {
+    cudaEventRecord(ctx->ev[1], st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
+  } else {
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(ctx->copy_stream);
+  }
+  if (rc == KDI_OK) {
+    ctx->tm.normalize_exp_ms = ev_ms(ctx->ev[0], ctx->ev[6]);
+    ctx->tm.normalize_dict_ms = ev_ms(ctx->ev[6], ctx->ev[7]);
+    ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+  }
+  const std::string err = ctx->err;
+  kdi_patterns_destroy(ctx, exp);
+  kdi_patterns_destroy(ctx, dict);
+  if (rc != KDI_OK) ctx->err = err;
+  return rc;
+}
+
+int kdi_orientation_similarity_map(kdi_ctx* ctx, const int64_t* indices, int64_t ny, int64_t nx,
+                                   int keep_n, int n_best, int from_n_best, int normalize,
+                                   const uint8_t* footprint, int fy, int fx, int center_index,
+                                   float* out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!indices || !footprint || !out) return kdi_fail(ctx, KDI_EINVAL, "kdi_orientation_similarity_map: NULL argument");
+  if (ny < 1 || nx < 1 || keep_n < 1 || fy < 1 || fx < 1) return kdi_fail(ctx, KDI_EINVAL, "bad shape");
+  if (n_best > keep_n)  // _orientation_similarity_map.py:99-102
+    return kdi_fail(ctx, KDI_EINVAL, "n_best %d cannot be greater than keep_n %d", n_best, keep_n);
+  if (n_best < 1 || from_n_best < 1 || from_n_best > n_best)
+    return kdi_fail(ctx, KDI_EINVAL, "need 1 <= from_n_best <= n_best");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  // scipy.ndimage centres the footprint at shape // 2; truthy entries in row-major order
+  std::vector<int2> offs;
+  for (int r = 0; r < fy; ++r)
+    for (int c = 0; c < fx; ++c)
+      if (footprint[r * fx + c]) offs.push_back(make_int2(r - fy / 2, c - fx / 2));
+  if (center_index < 0 || center_index >= (int)offs.size())
+    return kdi_fail(ctx, KDI_EINVAL, "center_index %d outside the footprint's %d entries", center_index, (int)offs.size());
+  const int n_layers = n_best - from_n_best + 1;
+  const size_t n_idx = (size_t)ny * nx * keep_n, n_out = (size_t)ny * nx * n_layers;
+  const size_t o_idx = 0, o_off = align_up(n_idx * 8, 256), o_out = align_up(o_off + offs.size() * sizeof(int2), 256);
+  KDI_TRY(kdi_ws2_reserve(ctx, o_out + n_out * 4));
+  uint8_t* w = reinterpret_cast<uint8_t*>(ctx->ws2);
+  cudaStream_t st = ctx->stream;
+  KDI_CUDA(ctx, cudaMemcpyAsync(w + o_idx, indices, n_idx * 8, cudaMemcpyHostToDevice, st));
+  KDI_CUDA(ctx, cudaMemcpyAsync(w + o_off, offs.data(), offs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+  KDI_TRY(kdi_launch_osm(ctx, st, reinterpret_cast<int64_t*>(w + o_idx), ny, nx, keep_n, n_best,
+                         from_n_best, normalize, reinterpret_cast<int2*>(w + o_off), (int)offs.size(),
+                         center_index, reinterpret_cast<float*>(w + o_out)));
+  KDI_CUDA(ctx, cudaMemcpyAsync(out, w + o_out, n_out * 4, cudaMemcpyDeviceToHost, st));
+  KDI_CUDA(ctx, cudaStreamSynchronize(st));
+  return KDI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,533 @@
+// K2: experimental x dictionary similarity block on the 5th-generation tensor cores with the
+// per-row candidate selection fused into the epilogue.
+//
+// Replaces, for one (experimental set, dictionary chunk) pair, the reference's
+//   similarities = metric.match(experimental, simulated)      einsum "ik,mk->im"
+//   similarities.argtopk(keep_n) / similarities.topk(keep_n)
+// (/root/reference/src/kikuchipy/indexing/_dictionary_indexing.py:195-198,
+//  similarity_metrics/_normalized_cross_correlation.py:181-183) without ever
+// materialising the (N_exp x N_dict) block: both operands are K-major already, so
+// D = A * B^T is a TN GEMM fed straight from the normalised 16-bit rows.
+//
+// Structure (sm_100a): persistent CTAs (or CTA pairs), warp-specialised.
+//   warp 0   TMA producer   cp.async.bulk.tensor 2-D tiles (128-byte swizzle) -> smem ring
+//   warp 1   MMA issuer     tcgen05.mma kind::f16, fp32 accumulators in TMEM (2 x 256 columns,
+//                           double-buffered so the epilogue of tile i overlaps the MMAs of i+1)
+//   warps 2-5 epilogue      tcgen05.ld (TMEM lane = experimental row => one thread owns one row),
+//                           threshold filter + per-row candidate list in shared memory
+// A work unit is (block of 128*CG experimental rows) x (strip of `strip_tiles` N tiles); the row
+// block keeps its candidate list in shared memory for the whole strip and publishes its
+// kc-th best score to a global per-row threshold (atomicMax) so later strips of the same rows
+// start with a tight filter.  Units are ordered super-block -> strip -> row block so that
+// concurrently running CTAs stream the same dictionary tiles (L2 reuse) while the
+// super-block's experimental rows stay L2-resident.
+#include "kdi_internal.cuh"
+#include "kdi_ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace {
+
+using namespace kdi;
+
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kABytes = KDI_TILE_M * KDI_TILE_K * 2;  // 16 KB
+
+struct GemmParams {
+  int64_t M, N;
+  int kblocks;      // kp / 64
+  int m_blocks;     // row blocks of 128*CG rows
+  int n_tiles;      // N tiles of 256 rows
+  int strip_tiles;  // N tiles per unit
+  int n_strips;
+  int superblock;  // row blocks per super-block
+  int64_t units;
+  int stages;
+  int fmt;  // 0 fp16, 1 bf16
+  uint2* cand;
+  uint32_t* thr;
+  float* out;  // MODE 1
+};
+
+__device__ __forceinline__ float pick32(const float (&v)[32], int j) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+  float b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+  float c[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+  float d0 = (j & 8) ? c[1] : c[0];
+  float d1 = (j & 8) ? c[3] : c[2];
+  return (j & 16) ? d1 : d0;
+}
+
+// unit u -> (row block, strip); order: super-block -> strip -> row block inside the super-block
+__device__ __forceinline__ void decode_unit(const GemmParams& p, int64_t u, int& mb, int& strip) {
+  const int units_per_sb = p.superblock * p.n_strips;
+  const int sb = (int)(u / units_per_sb);
+  const int rem = (int)(u - (int64_t)sb * units_per_sb);
+  const int sb_blocks = min(p.superblock, p.m_blocks - sb * p.superblock);
+  strip = rem / sb_blocks;
+  mb = sb * p.superblock + rem % sb_blocks;
+}
+
+// MODE 0: candidate selection; MODE 1: write the full block (validation only)
+template <int CG, int KC, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmParams p) {
+  constexpr int kBRows = KDI_TILE_N / CG;  // dictionary rows this CTA stages per tile
+  constexpr int kBBytes = kBRows * KDI_TILE_K * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kListBytes = (MODE == 0) ? KC * KDI_TILE_M * 8 : 0;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle atoms need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = p.stages;
+  float* ls = reinterpret_cast<float*>(smem + (size_t)stages * kStageBytes);
+  uint32_t* li = reinterpret_cast<uint32_t*>(ls + KC * KDI_TILE_M);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * kStageBytes + kListBytes);
+  // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base word
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8u * stages;
+  const uint32_t bar_tfull = bar_empty + 8u * stages;
+  const uint32_t bar_tempty = bar_tfull + 16u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int64_t cluster_id = blockIdx.x / CG;
+  const int64_t n_clusters = gridDim.x / CG;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8u * a, 1);
+      mbar_init(bar_tempty + 8u * a, 4 * CG);  // one arrive per epilogue warp of each CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<CG>(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint64_t pol_a = l2_policy_evict_last();
+      const uint64_t pol_b = l2_policy_evict_normal();
+      // in a CTA pair every load completes on the leader's barrier
+      uint32_t full_dst = bar_full;
+      if constexpr (CG == 2) {
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_dst) : "r"(bar_full));
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = cluster_id; u < p.units; u += n_clusters) {
+        int mb, strip;
+        decode_unit(p, u, mb, strip);
+        const int t0 = strip * p.strip_tiles;
+        const int t1 = min(t0 + p.strip_tiles, p.n_tiles);
+        const int a_row = (mb * CG + (int)rank) * KDI_TILE_M;
+        for (int nt = t0; nt < t1; ++nt) {
+          const int b_row = nt * KDI_TILE_N + (int)rank * kBRows;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+            const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
+            const uint32_t sb_ = sa + kABytes;
+            if constexpr (CG == 1) {
+              mbar_arrive_expect_tx(bar_full + 8u * stage, kStageBytes);
+              tma_load_2d(sa, &tmA, bar_full + 8u * stage, kb * KDI_TILE_K, a_row, pol_a);
+              tma_load_2d(sb_, &tmB, bar_full + 8u * stage, kb * KDI_TILE_K, b_row, pol_b);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(bar_full + 8u * stage, 2 * kStageBytes);
+              tma_load_2d_cg2(sa, &tmA, full_dst + 8u * stage, kb * KDI_TILE_K, a_row, pol_a);
+              tma_load_2d_cg2(sb_, &tmB, full_dst + 8u * stage, kb * KDI_TILE_K, b_row, pol_b);
+            }
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+      // tail: every slot released by the MMA side before this CTA may exit
+      for (int s = 0; s < stages; ++s) {
+        mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only in a pair) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.fmt, KDI_TILE_M * CG, KDI_TILE_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t u = cluster_id; u < p.units; u += n_clusters) {
+        int mb, strip;
+        decode_unit(p, u, mb, strip);
+        const int t0 = strip * p.strip_tiles;
+        const int t1 = min(t0 + p.strip_tiles, p.n_tiles);
+        for (int nt = t0; nt < t1; ++nt) {
+          mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)acc * KDI_TILE_N;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(bar_full + 8u * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
+            const uint64_t da = umma_smem_desc_sw128(sa);
+            const uint64_t db = umma_smem_desc_sw128(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < KDI_TILE_K / 16; ++k) {
+              // advance 16 elements = 32 bytes = 2 descriptor units along K inside the swizzle atom
+              umma_f16<CG>(tmem_d, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+            }
+            if constexpr (CG == 1) umma_commit(bar_empty + 8u * stage);
+            else umma_commit_cg2(bar_empty + 8u * stage, 3);
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+          if constexpr (CG == 1) umma_commit(bar_tfull + 8u * acc);
+          else umma_commit_cg2(bar_tfull + 8u * acc, 3);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, thread = one experimental row =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t u = cluster_id; u < p.units; u += n_clusters) {
+      int mb, strip;
+      decode_unit(p, u, mb, strip);
+      const int t0 = strip * p.strip_tiles;
+      const int t1 = min(t0 + p.strip_tiles, p.n_tiles);
+      const int64_t row = (int64_t)(mb * CG + (int)rank) * KDI_TILE_M + r;
+      const bool valid = row < p.M;
+
+      int cnt = 0, minpos = 0;
+      float lmin = -INFINITY;     // smallest entry of a full list
+      float gthr = -INFINITY;     // last value read from / published to the global threshold
+      float thr = valid ? -INFINITY : INFINITY;
+
+      for (int nt = t0; nt < t1; ++nt) {
+        mbar_wait(bar_tfull + 8u * acc, acc_phase);
+        tc_fence_after();
+        if constexpr (MODE == 0) {
+          if (valid) {
+            gthr = fmaxf(gthr, key_float(__ldcg(p.thr + row)));
+            thr = fmaxf(thr, gthr);
+          }
+        }
+        const int ncols = (int)min((int64_t)KDI_TILE_N, p.N - (int64_t)nt * KDI_TILE_N);
+#pragma unroll 1
+        for (int c = 0; c < KDI_TILE_N / 32; ++c) {
+          float v[32];
+          tmem_ld_32x32(tmem_lane + (uint32_t)(acc * KDI_TILE_N + c * 32), v);
+          if (c == KDI_TILE_N / 32 - 1) {
+            // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CG == 1) mbar_arrive(bar_tempty + 8u * acc);
+              else mbar_arrive_cluster(bar_tempty + 8u * acc, 0);
+            }
+          }
+          const int col0 = c * 32;
+          if (col0 >= ncols) continue;  // warp-uniform
+          if constexpr (MODE == 1) {
+            if (valid) {
+              float* o = p.out + row * p.N + (int64_t)nt * KDI_TILE_N + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ncols) o[j] = v[j];
+            }
+          } else {
+            if (col0 + 32 > ncols) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j >= ncols) v[j] = -INFINITY;
+            }
+            float m = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+            if (m > thr) {
+              uint32_t hits = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) hits |= (v[j] > thr ? 1u : 0u) << j;
+              while (hits) {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const float s = pick32(v, j);
+                if (s > thr) {
+                  const uint32_t idx = (uint32_t)(nt * KDI_TILE_N + col0 + j);
+                  int slot;
+                  if (cnt < KC) slot = cnt++;
+                  else slot = minpos;
+                  ls[slot * KDI_TILE_M + r] = s;
+                  li[slot * KDI_TILE_M + r] = idx;
+                  if (cnt == KC) {
+                    float mn = ls[r];
+                    int mp = 0;
+#pragma unroll 8
+                    for (int i = 1; i < KC; ++i) {
+                      const float x = ls[i * KDI_TILE_M + r];
+                      if (x < mn) { mn = x; mp = i; }
+                    }
+                    lmin = mn;
+                    minpos = mp;
+                    thr = fmaxf(thr, mn);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if constexpr (MODE == 0) {
+          // publish a tighter bound for the other strips of this row
+          if (valid && cnt == KC && lmin > gthr) {
+            atomicMax(p.thr + row, float_key(lmin));
+            gthr = lmin;
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if constexpr (MODE == 0) {
+        if (valid) {
+          uint2* dst = p.cand + ((size_t)row * p.n_strips + strip) * KC;
+#pragma unroll 4
+          for (int i = 0; i < KC; i += 2) {
+            uint4 w;
+            w.x = (i < cnt) ? __float_as_uint(ls[i * KDI_TILE_M + r]) : 0xFF800000u;
+            w.y = (i < cnt) ? li[i * KDI_TILE_M + r] : 0xFFFFFFFFu;
+            w.z = (i + 1 < cnt) ? __float_as_uint(ls[(i + 1) * KDI_TILE_M + r]) : 0xFF800000u;
+            w.w = (i + 1 < cnt) ? li[(i + 1) * KDI_TILE_M + r] : 0xFFFFFFFFu;
+            *reinterpret_cast<uint4*>(dst + i) = w;
+          }
+        }
+      }
+    }
+  }
+
+  // teardown: everyone done with TMEM before it is released
+  tc_fence_before();
+  if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, kTmemCols);
+}
+
+__global__ void kdi_thr_init_kernel(uint32_t* thr, int64_t m) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) thr[i] = 0x007FFFFFu;  // float_key(-inf)
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap(kdi_ctx* ctx, CUtensorMap* out, const void* base, int64_t rows, int64_t kp, int fmt,
+              int box_rows) {
+  if (!ctx->encode_tiled) return kdi_fail(ctx, KDI_ECUDA, "cuTensorMapEncodeTiled unavailable");
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KDI_TILE_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return kdi_fail(ctx, KDI_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld kp=%lld", (int)r,
+                    (long long)rows, (long long)kp);
+  return KDI_OK;
+}
+
+template <int CG, int KC, int MODE>
+int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
+                   const CUtensorMap& tmB, const GemmParams& p) {
+  constexpr int kBBytes = (KDI_TILE_N / CG) * KDI_TILE_K * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kListBytes = (MODE == 0) ? KC * KDI_TILE_M * 8 : 0;
+  const size_t smem = 1024 + (size_t)p.stages * kStageBytes + kListBytes + (2 * p.stages + 4) * 8 + 16;
+  auto kern = kdi_gemm_kernel<CG, KC, MODE>;
+  KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t max_clusters = ctx->sm_count / CG;
+  const int64_t n_clusters = p.units < max_clusters ? p.units : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_clusters * CG));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  KDI_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  ctx->tm.kernel_launches++;
+  ctx->tm.gemm_launches++;
+  return KDI_OK;
+}
+
+int stages_for(int cg, int kc, int mode) {
+  const int stage = kABytes + (KDI_TILE_N / cg) * KDI_TILE_K * 2;
+  const int list = mode == 0 ? kc * KDI_TILE_M * 8 : 0;
+  const int budget = 232448 - 1024 - list - 256;
+  int s = budget / stage;
+  if (s > 8) s = 8;
+  return s;
+}
+
+}  // namespace
+
+int kdi_gemm_kc_for(int keep_n) {
+  if (keep_n <= 24) return 32;
+  if (keep_n <= 52) return 64;
+  return 0;
+}
+
+int kdi_gemm_make_plan(kdi_ctx* ctx, int64_t M, int64_t N, int64_t kp, int keep_n,
+                       kdi_gemm_plan* plan) {
+  kdi_gemm_plan pl;
+  pl.kc = kdi_gemm_kc_for(keep_n);
+  if (pl.kc == 0) return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d too large for the fused path", keep_n);
+  pl.cta_group = ctx->cta_group == 2 ? 2 : 1;
+  pl.stages = stages_for(pl.cta_group, pl.kc, 0);
+  const int64_t rows_per_block = (int64_t)KDI_TILE_M * pl.cta_group;
+  pl.m_blocks = (int)kdi_ceil_div(M, rows_per_block);
+  pl.n_tiles = (int)kdi_ceil_div(N, KDI_TILE_N);
+  const int64_t workers = ctx->sm_count / pl.cta_group;
+  int strip_tiles = ctx->strip_tiles;
+  if (strip_tiles <= 0) {
+    // enough units for a short tail (~24 per worker), but strips of at least 4 tiles so the
+    // threshold warm-up at the start of each unit is amortised
+    int64_t n_strips = kdi_ceil_div(24 * workers, pl.m_blocks);
+    const int64_t max_strips = kdi_ceil_div(pl.n_tiles, 4);
+    if (n_strips > max_strips) n_strips = max_strips;
+    if (n_strips < 1) n_strips = 1;
+    strip_tiles = (int)kdi_ceil_div(pl.n_tiles, n_strips);
+  }
+  if (strip_tiles > pl.n_tiles) strip_tiles = pl.n_tiles;
+  pl.strip_tiles = strip_tiles;
+  pl.n_strips = (int)kdi_ceil_div(pl.n_tiles, strip_tiles);
+  int sb = ctx->superblock;
+  if (sb <= 0) {
+    // keep a super-block of experimental rows (16-bit) within ~48 MB of L2
+    const int64_t block_bytes = (int64_t)KDI_TILE_M * pl.cta_group * kp * 2;
+    int64_t max_sb = (48ll << 20) / block_bytes;
+    if (max_sb < 1) max_sb = 1;
+    const int64_t n_sb = kdi_ceil_div(pl.m_blocks, max_sb);
+    sb = (int)kdi_ceil_div(pl.m_blocks, n_sb);
+  }
+  if (sb > pl.m_blocks) sb = pl.m_blocks;
+  if (sb < 1) sb = 1;
+  pl.superblock = sb;
+  pl.units = (int64_t)pl.m_blocks * pl.n_strips;
+  pl.cand_bytes = (size_t)M * pl.n_strips * pl.kc * sizeof(uint2);
+  pl.thr_bytes = (size_t)M * sizeof(uint32_t);
+  plan[0] = pl;
+  return KDI_OK;
+}
+
+int kdi_launch_cand_init(kdi_ctx* ctx, cudaStream_t stream, uint32_t* thr, int64_t m) {
+  if (m <= 0) return KDI_OK;
+  kdi_thr_init_kernel<<<(unsigned)kdi_ceil_div(m, 256), 256, 0, stream>>>(thr, m);
+  KDI_CUDA(ctx, cudaGetLastError());
+  ctx->tm.kernel_launches++;
+  return KDI_OK;
+}
+
+static int check_operands(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict) {
+  if (!exp || !dict) return kdi_fail(ctx, KDI_EINVAL, "null pattern set");
+  if (exp->s_eff != dict->s_eff || exp->kp != dict->kp)
+    return kdi_fail(ctx, KDI_EINVAL, "experimental and dictionary signal sizes differ (%lld vs %lld)",
+                    (long long)exp->s_eff, (long long)dict->s_eff);
+  if (exp->compute_dtype != dict->compute_dtype)
+    return kdi_fail(ctx, KDI_EINVAL, "pattern sets were prepared with different compute dtypes");
+  if (ctx->cc_major != 10)
+    return kdi_fail(ctx, KDI_EUNSUPPORTED,
+                    "the tensor-core path needs an sm_100 device (found sm_%d%d); there is no fallback",
+                    ctx->cc_major, ctx->cc_minor);
+  return KDI_OK;
+}
+
+int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
+                         const kdi_patterns* dict, const kdi_gemm_plan* plan, uint2* cand,
+                         uint32_t* thr) {
+  KDI_TRY(check_operands(ctx, exp, dict));
+  const int cg = plan->cta_group;
+  CUtensorMap tmA, tmB;
+  KDI_TRY(make_tmap(ctx, &tmA, exp->a16, exp->rows, exp->kp, exp->compute_dtype, KDI_TILE_M));
+  KDI_TRY(make_tmap(ctx, &tmB, dict->a16, dict->rows, dict->kp, dict->compute_dtype, KDI_TILE_N / cg));
+  GemmParams p = {};
+  p.M = exp->rows;
+  p.N = dict->rows;
+  p.kblocks = (int)(exp->kp / KDI_TILE_K);
+  p.m_blocks = plan->m_blocks;
+  p.n_tiles = plan->n_tiles;
+  p.strip_tiles = plan->strip_tiles;
+  p.n_strips = plan->n_strips;
+  p.superblock = plan->superblock;
+  p.units = plan->units;
+  p.stages = plan->stages;
+  p.fmt = exp->compute_dtype;
+  p.cand = cand;
+  p.thr = thr;
+  p.out = nullptr;
+  if (cg == 1 && plan->kc == 32) return launch_variant<1, 32, 0>(ctx, stream, tmA, tmB, p);
+  if (cg == 1 && plan->kc == 64) return launch_variant<1, 64, 0>(ctx, stream, tmA, tmB, p);
+  if (cg == 2 && plan->kc == 32) return launch_variant<2, 32, 0>(ctx, stream, tmA, tmB, p);
+  if (cg == 2 && plan->kc == 64) return launch_variant<2, 64, 0>(ctx, stream, tmA, tmB, p);
+  return kdi_fail(ctx, KDI_EINTERNAL, "no GEMM variant for cta_group=%d kc=%d", cg, plan->kc);
+}
+
+int kdi_launch_gemm_full(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
+                         const kdi_patterns* dict, float* out) {
+  KDI_TRY(check_operands(ctx, exp, dict));
+  const int cg = ctx->cta_group == 2 ? 2 : 1;
+  CUtensorMap tmA, tmB;
+  KDI_TRY(make_tmap(ctx, &tmA, exp->a16, exp->rows, exp->kp, exp->compute_dtype, KDI_TILE_M));
+  KDI_TRY(make_tmap(ctx, &tmB, dict->a16, dict->rows, dict->kp, dict->compute_dtype, KDI_TILE_N / cg));
+  GemmParams p = {};
+  p.M = exp->rows;
+  p.N = dict->rows;
+  p.kblocks = (int)(exp->kp / KDI_TILE_K);
+  p.m_blocks = (int)kdi_ceil_div(p.M, (int64_t)KDI_TILE_M * cg);
+  p.n_tiles = (int)kdi_ceil_div(p.N, KDI_TILE_N);
+  p.strip_tiles = ctx->strip_tiles > 0 ? ctx->strip_tiles : 2;
+  if (p.strip_tiles > p.n_tiles) p.strip_tiles = p.n_tiles;
+  p.n_strips = (int)kdi_ceil_div(p.n_tiles, p.strip_tiles);
+  p.superblock = ctx->superblock > 0 && ctx->superblock < p.m_blocks ? ctx->superblock : p.m_blocks;
+  p.units = (int64_t)p.m_blocks * p.n_strips;
+  p.stages = stages_for(cg, 0, 1);
+  p.fmt = exp->compute_dtype;
+  p.out = out;
+  if (cg == 1) return launch_variant<1, 32, 1>(ctx, stream, tmA, tmB, p);
+  return launch_variant<2, 32, 1>(ctx, stream, tmA, tmB, p);
+}

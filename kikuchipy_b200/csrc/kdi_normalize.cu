@@ -1,0 +1,209 @@
+// K1: prepare_experimental / prepare_dictionary on the device.
+//
+// Per row: cast to float32 -> (optional) row gather by the navigation mask -> (optional)
+// column compaction by the signal mask -> NCC: x = (x - mean(x)) / ||x - mean(x)||,
+// NDP: x = x / ||x|| -> write the float32 row (what the reference's prepare_* returns) and the
+// 16-bit tensor-core operand row (x * KDI_OP_SCALE, K padded with zeros to a multiple of 64).
+//
+// Reference: /root/reference/src/kikuchipy/indexing/similarity_metrics/
+//   _normalized_cross_correlation.py:113-126,151-159,185-188,228-233 (two-pass: exact mean, then
+//   centred sum of squares - mirrored here, no E[x^2]-mean^2 shortcut)
+//   _normalized_dot_product.py:105-118,141-150,176-194 (no centring)
+// HBM-bound: algorithmic bytes per row = S*sizeof(src) + s_pitch*4 + kp*2.
+#include "kdi_internal.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int kNormThreads = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // red may still be read from a previous call
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kNormThreads / 32; ++w) t += red[w];
+  return t;
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint16_t to16(float v) {
+  if constexpr (BF16) {
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v * KDI_OP_SCALE));
+  } else {
+    return __half_as_ushort(__float2half_rn(v * KDI_OP_SCALE));
+  }
+}
+
+// generic path: any source type, optional row / column gathers; the row is re-read from
+// L1/L2 for the second and third pass
+template <typename T, bool BF16>
+__global__ void __launch_bounds__(kNormThreads)
+kdi_normalize_generic(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
+                      const int32_t* __restrict__ cols, int64_t s_eff, int metric,
+                      float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
+                      int64_t kp) {
+  __shared__ double red[kNormThreads / 32];
+  const int64_t row = blockIdx.x;
+  const int64_t srow = rowmap ? rowmap[row] : row;
+  const T* x = src + srow * S;
+  float mean = 0.f;
+  if (metric == KDI_NCC) {
+    double s = 0.0;
+    for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads)
+      s += (double)(float)x[cols ? cols[j] : j];
+    s = block_sum(s, red);
+    mean = (float)(s / (double)s_eff);
+  }
+  double ss = 0.0;
+  for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) {
+    const float c = (float)x[cols ? cols[j] : j] - mean;
+    ss += (double)c * (double)c;
+  }
+  ss = block_sum(ss, red);
+  const float norm = (float)sqrt(ss);
+  float* o32 = a32 + row * s_pitch;
+  uint16_t* o16 = a16 + row * kp;
+  for (int64_t j = threadIdx.x; j < kp; j += kNormThreads) {
+    float v = 0.f;
+    if (j < s_eff) v = ((float)x[cols ? cols[j] : j] - mean) / norm;
+    if (j < s_pitch) o32[j] = v;
+    o16[j] = to16<BF16>(v);
+  }
+  // s_pitch <= kp always (kp is s_eff rounded up to 64, s_pitch to 4)
+}
+
+// fast path: float32 source, no gathers, S % 4 == 0: the row lives in registers (one HBM read)
+template <int V, bool BF16>
+__global__ void __launch_bounds__(kNormThreads)
+kdi_normalize_f32_regs(const float* __restrict__ src, int64_t S, int metric,
+                       float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
+                       int64_t kp) {
+  __shared__ double red[kNormThreads / 32];
+  const int64_t row = blockIdx.x;
+  const float4* x = reinterpret_cast<const float4*>(src + row * S);
+  const int n4 = (int)(S >> 2);
+  float4 r[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int j = threadIdx.x + i * kNormThreads;
+    r[i] = (j < n4) ? __ldg(x + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mean = 0.f;
+  if (metric == KDI_NCC) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += ((double)r[i].x + (double)r[i].y) + ((double)r[i].z + (double)r[i].w);
+    s = block_sum(s, red);
+    mean = (float)(s / (double)S);
+  }
+  double ss = 0.0;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int j = threadIdx.x + i * kNormThreads;
+    if (j < n4) {
+      r[i].x -= mean; r[i].y -= mean; r[i].z -= mean; r[i].w -= mean;
+      ss += ((double)r[i].x * r[i].x + (double)r[i].y * r[i].y) +
+            ((double)r[i].z * r[i].z + (double)r[i].w * r[i].w);
+    }
+  }
+  ss = block_sum(ss, red);
+  const float norm = (float)sqrt(ss);
+  float4* o32 = reinterpret_cast<float4*>(a32 + row * s_pitch);
+  uint2* o16 = reinterpret_cast<uint2*>(a16 + row * kp);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int j = threadIdx.x + i * kNormThreads;
+    if (j < n4) {
+      float4 v;
+      v.x = r[i].x / norm; v.y = r[i].y / norm; v.z = r[i].z / norm; v.w = r[i].w / norm;
+      o32[j] = v;
+      uint2 h;
+      h.x = (uint32_t)to16<BF16>(v.x) | ((uint32_t)to16<BF16>(v.y) << 16);
+      h.y = (uint32_t)to16<BF16>(v.z) | ((uint32_t)to16<BF16>(v.w) << 16);
+      o16[j] = h;
+    }
+  }
+  // zero the K padding of the 16-bit row (s_pitch == S here)
+  for (int64_t j = S + threadIdx.x; j < kp; j += kNormThreads) a16[row * kp + j] = 0;
+}
+
+template <typename T>
+int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_t* rowmap,
+                   const int32_t* cols, int64_t rows, int64_t s_eff, int metric, int bf16,
+                   float* a32, int64_t s_pitch, void* a16, int64_t kp) {
+  const T* s = reinterpret_cast<const T*>(src);
+  uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
+  if (bf16)
+    kdi_normalize_generic<T, true><<<(unsigned)rows, kNormThreads, 0, stream>>>(
+        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp);
+  else
+    kdi_normalize_generic<T, false><<<(unsigned)rows, kNormThreads, 0, stream>>>(
+        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp);
+  return 0;
+}
+
+template <int V>
+void launch_regs(cudaStream_t stream, const float* src, int64_t S, int64_t rows, int metric,
+                 int bf16, float* a32, int64_t s_pitch, void* a16, int64_t kp) {
+  uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
+  if (bf16)
+    kdi_normalize_f32_regs<V, true><<<(unsigned)rows, kNormThreads, 0, stream>>>(
+        src, S, metric, a32, s_pitch, o16, kp);
+  else
+    kdi_normalize_f32_regs<V, false><<<(unsigned)rows, kNormThreads, 0, stream>>>(
+        src, S, metric, a32, s_pitch, o16, kp);
+}
+
+}  // namespace
+
+int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int src_dtype,
+                         int64_t S, const int64_t* d_rowmap, const int32_t* d_cols, int64_t rows,
+                         int64_t s_eff, int metric, int compute_dtype, float* a32, int64_t s_pitch,
+                         void* a16, int64_t kp) {
+  if (rows <= 0) return KDI_OK;
+  if (rows > 0x7fffffffLL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "too many rows in one pattern set");
+  const int bf16 = compute_dtype == 1;
+  const bool plain = !d_rowmap && !d_cols && s_eff == S;
+  if (src_dtype == KDI_F32 && plain && (S % 4) == 0 && s_pitch == S &&
+      (reinterpret_cast<uintptr_t>(src) % 16) == 0 && S <= 16 * 4 * kNormThreads) {
+    const float* s = reinterpret_cast<const float*>(src);
+    const int64_t n4 = S / 4;
+    const int v = (int)kdi_ceil_div(n4, kNormThreads);
+    if (v <= 1) launch_regs<1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
+    else if (v <= 2) launch_regs<2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
+    else if (v <= 4) launch_regs<4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
+    else if (v <= 8) launch_regs<8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
+    else launch_regs<16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
+  } else {
+    switch (src_dtype) {
+      case KDI_U8:
+        launch_generic<uint8_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
+                                s_pitch, a16, kp);
+        break;
+      case KDI_U16:
+        launch_generic<uint16_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
+                                 s_pitch, a16, kp);
+        break;
+      case KDI_F32:
+        launch_generic<float>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
+                              s_pitch, a16, kp);
+        break;
+      case KDI_F64:
+        launch_generic<double>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
+                               s_pitch, a16, kp);
+        break;
+      default:
+        return kdi_fail(ctx, KDI_EINVAL, "unknown source dtype %d", src_dtype);
+    }
+  }
+  KDI_CUDA(ctx, cudaGetLastError());
+  ctx->tm.kernel_launches++;
+  return KDI_OK;
+}

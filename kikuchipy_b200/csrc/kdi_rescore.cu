@@ -1,0 +1,355 @@
+// K3+K4: candidate selection, exact float32 rescoring, ranking and the per-row certificate;
+// plus the exact (no tensor core) path used for rows whose certificate fails, for
+// KDI_OPT_FORCE_EXACT and for kdi_match_full.
+//
+// The tensor-core pass (kdi_gemm_topk.cu) only NOMINATES kc > keep_n candidates per row from
+// 16-bit operands.  The scores and the ranking the caller sees are computed here from the
+// float32 normalised rows, i.e. the same quantity the reference gets from
+//   np.einsum("ik,mk->im", exp, dict)      (_normalized_cross_correlation.py:181-183)
+// followed by argtopk/topk (indexing/_dictionary_indexing.py:197-198): keep_n best, best first.
+// Ties are ordered by ascending dictionary index (the reference inherits an unspecified order
+// from NumPy's partition/sort - SURVEY.md section 7, hard part 1).
+//
+// Certificate: let t be the smallest tensor-core score among the kc retained candidates; every
+// dictionary row that was NOT retained has a tensor-core score <= t.  If the keep_n-th best
+// exact score exceeds t + eps (eps = cert_sigmas x the rms tensor-core error measured on this
+// row's own candidates), no discarded row can belong to the true top keep_n.  Rows that fail
+// are re-done by the exact path, so a missed member of the top-k is impossible, not improbable.
+#include "kdi_internal.cuh"
+#include "kdi_ptx.cuh"
+
+namespace {
+
+using kdi::float_key;
+using kdi::key_float;
+
+constexpr int kSelThreads = 128;
+constexpr int kSelBuf = 1024;  // candidates >= the row's final threshold that fit in smem
+
+// dot product of two zero-padded float32 rows of n4 float4 each, by one warp.  fp32 FMAs in
+// four accumulators per lane, reduction in double.  Every exact score in the library goes
+// through this function, so the fused and the exact path agree bit for bit.
+__device__ __forceinline__ float warp_dot(const float4* __restrict__ a, const float4* __restrict__ b,
+                                          int n4, int lane) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = lane; j < n4; j += 32) {
+    const float4 x = __ldg(a + j);
+    const float4 y = __ldg(b + j);
+    acc.x = fmaf(x.x, y.x, acc.x);
+    acc.y = fmaf(x.y, y.y, acc.y);
+    acc.z = fmaf(x.z, y.z, acc.z);
+    acc.w = fmaf(x.w, y.w, acc.w);
+  }
+  double d = ((double)acc.x + (double)acc.y) + ((double)acc.z + (double)acc.w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  return (float)d;
+}
+
+// descending bitonic sort of n (power of two) 64-bit keys in shared memory
+template <int T>
+__device__ __forceinline__ void block_sort_desc(uint64_t* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += T) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = keys[i], b = keys[ixj];
+          const bool sw = ((i & k) == 0) ? (a < b) : (a > b);
+          if (sw) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint64_t pack_key(float score, uint32_t idx) {
+  return ((uint64_t)float_key(score) << 32) | (uint64_t)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return key_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_index(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
+
+template <int KC>
+__global__ void __launch_bounds__(kSelThreads)
+kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
+                          int64_t s_pitch, int64_t n_dict, const uint2* __restrict__ cand,
+                          const uint32_t* __restrict__ thr, int n_strips, int keep_n,
+                          int64_t index_offset, float inv_scale, float cert_sigmas,
+                          float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+                          int* __restrict__ flag_list, int* __restrict__ n_flag) {
+  __shared__ uint64_t keys[kSelBuf];
+  __shared__ float ex[KC];
+  __shared__ float ap[KC];
+  __shared__ uint32_t ci[KC];
+  __shared__ int s_count;
+  __shared__ float s_red[2];
+
+  const int64_t row = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+
+  // 1. gather candidates at or above the row's final threshold
+  const uint32_t tkey = thr[row];
+  const int64_t total = (int64_t)n_strips * KC;
+  const uint2* c = cand + row * total;
+  bool overflow = false;
+  for (int64_t i = tid; i < total; i += kSelThreads) {
+    const uint2 e = c[i];
+    if (e.y != 0xFFFFFFFFu && float_key(__uint_as_float(e.x)) >= tkey) {
+      const int pos = atomicAdd(&s_count, 1);
+      if (pos < kSelBuf) keys[pos] = pack_key(__uint_as_float(e.x), e.y);
+    }
+  }
+  __syncthreads();
+  int count = s_count;
+  if (count > kSelBuf) { overflow = true; count = kSelBuf; }
+  // 2. order by tensor-core score, keep the kc best
+  int n2 = 64;
+  while (n2 < count) n2 <<= 1;
+  for (int i = count + tid; i < n2; i += kSelThreads) keys[i] = 0;  // below every real key
+  block_sort_desc<kSelThreads>(keys, n2);
+  const int nsel = count < KC ? count : KC;
+  if (tid < KC) {
+    if (tid < nsel) { ap[tid] = key_score(keys[tid]) * inv_scale; ci[tid] = key_index(keys[tid]); }
+    else { ap[tid] = -INFINITY; ci[tid] = 0xFFFFFFFFu; ex[tid] = -INFINITY; }
+  }
+  __syncthreads();
+  // 3. exact scores from the float32 rows
+  const float4* a = reinterpret_cast<const float4*>(exp32 + row * s_pitch);
+  const int n4 = (int)(s_pitch >> 2);
+  for (int i = warp; i < nsel; i += kSelThreads / 32) {
+    const float4* b = reinterpret_cast<const float4*>(dict32 + (int64_t)ci[i] * s_pitch);
+    const float d = warp_dot(a, b, n4, lane);
+    if (lane == 0) ex[i] = d;
+  }
+  __syncthreads();
+  // 4. rank by (exact score desc, index asc); 5. certificate
+  float my_s = 0.f;
+  uint32_t my_i = 0;
+  int rank = KC;
+  float err2 = 0.f;
+  if (tid < nsel) {
+    my_s = ex[tid];
+    my_i = ci[tid];
+    rank = 0;
+    for (int j = 0; j < nsel; ++j) {
+      const float sj = ex[j];
+      rank += (sj > my_s || (sj == my_s && ci[j] < my_i)) ? 1 : 0;
+    }
+    const float d = ap[tid] - my_s;
+    err2 = d * d;
+  }
+  // rms error of the tensor-core scores over this row's candidates (first two warps hold them)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+  if (lane == 0 && warp < 2) s_red[warp] = err2;
+  __syncthreads();
+  if (tid < nsel && rank < keep_n) {
+    out_scores[row * keep_n + rank] = my_s;
+    out_idx[row * keep_n + rank] = (int64_t)my_i + index_offset;
+  }
+  if (tid < nsel && rank == keep_n - 1) {
+    bool ok = true;
+    if (n_dict > (int64_t)nsel) {  // some dictionary rows were discarded
+      const float sigma = sqrtf((s_red[0] + (KC > 32 ? s_red[1] : 0.f)) / (float)nsel);
+      const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 1e-7f;
+      const float t = ap[nsel - 1];  // smallest retained tensor-core score
+      ok = (nsel == KC) && !overflow && (my_s > t + eps);
+    }
+    if (!ok) {
+      const int pos = atomicAdd(n_flag, 1);
+      flag_list[pos] = (int)row;
+    }
+  }
+  if (tid == 0 && nsel < keep_n) {  // fewer candidates than requested (NaN rows): exact path decides
+    const int pos = atomicAdd(n_flag, 1);
+    flag_list[pos] = (int)row;
+  }
+}
+
+// ---- exact path -----------------------------------------------------------------------------
+
+constexpr int kExThreads = 256;
+constexpr int kExRows = 4;  // experimental rows per block (dictionary row read once for all)
+
+// scores[i][n] = <exp[rows[i]], dict[n]>; grid = (dictionary slabs, row groups)
+__global__ void __launch_bounds__(kExThreads)
+kdi_exact_scores_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
+                        int64_t s_pitch, int64_t n_dict, const int* __restrict__ rows_list,
+                        int64_t row0, int n_rows, float* __restrict__ scores, int slab) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g0 = blockIdx.y * kExRows;
+  const int n4 = (int)(s_pitch >> 2);
+  const float4* a[kExRows];
+  int nr = 0;
+#pragma unroll
+  for (int r = 0; r < kExRows; ++r) {
+    const int i = g0 + r;
+    int64_t er = 0;
+    if (i < n_rows) { er = rows_list ? (int64_t)rows_list[i] : row0 + i; nr = r + 1; }
+    a[r] = reinterpret_cast<const float4*>(exp32 + er * s_pitch);
+  }
+  const int64_t n_begin = (int64_t)blockIdx.x * slab;
+  const int64_t n_end = n_begin + slab < n_dict ? n_begin + slab : n_dict;
+  for (int64_t n = n_begin + warp; n < n_end; n += kExThreads / 32) {
+    const float4* b = reinterpret_cast<const float4*>(dict32 + n * s_pitch);
+    float4 acc[kExRows];
+#pragma unroll
+    for (int r = 0; r < kExRows; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = lane; j < n4; j += 32) {
+      const float4 y = __ldg(b + j);
+#pragma unroll
+      for (int r = 0; r < kExRows; ++r) {
+        const float4 x = __ldg(a[r] + j);
+        acc[r].x = fmaf(x.x, y.x, acc[r].x);
+        acc[r].y = fmaf(x.y, y.y, acc[r].y);
+        acc[r].z = fmaf(x.z, y.z, acc[r].z);
+        acc[r].w = fmaf(x.w, y.w, acc[r].w);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kExRows; ++r) {
+      double d = ((double)acc[r].x + (double)acc[r].y) + ((double)acc[r].z + (double)acc[r].w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (lane == 0 && r < nr) scores[(int64_t)(g0 + r) * n_dict + n] = (float)d;
+    }
+  }
+}
+
+constexpr int kTopThreads = 256;
+constexpr int kTopMax = 2048;  // largest keep_n the exact path ranks
+
+__device__ __forceinline__ int block_sum_int(int v, int* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int w = 0; w < kTopThreads / 32; ++w) t += red[w];
+  return t;
+}
+
+// per row: the keep_n largest of n_cols scores, sorted (score desc, index asc)
+__global__ void __launch_bounds__(kTopThreads)
+kdi_extract_topk_kernel(const float* __restrict__ scores, int64_t n_cols,
+                        const int* __restrict__ rows_list, int64_t row0, int keep_n,
+                        int64_t index_offset, float* __restrict__ out_scores,
+                        int64_t* __restrict__ out_idx) {
+  __shared__ uint64_t keys[kTopMax];
+  __shared__ int red[kTopThreads / 32];
+  __shared__ int s_pos;
+  const int i = blockIdx.x;
+  const int64_t out_row = rows_list ? (int64_t)rows_list[i] : row0 + i;
+  const float* s = scores + (int64_t)i * n_cols;
+  const int tid = threadIdx.x;
+
+  // keep_n-th largest key T by bitwise search: largest T with count(key >= T) >= keep_n
+  uint32_t T = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t trial = T | (1u << bit);
+    int c = 0;
+    for (int64_t j = tid; j < n_cols; j += kTopThreads) c += (float_key(s[j]) >= trial) ? 1 : 0;
+    c = block_sum_int(c, red);
+    if (c >= keep_n) T = trial;
+  }
+  if (tid == 0) s_pos = 0;
+  __syncthreads();
+  // everything strictly above T
+  for (int64_t j = tid; j < n_cols; j += kTopThreads) {
+    const float v = s[j];
+    if (float_key(v) > T) keys[atomicAdd(&s_pos, 1)] = pack_key(v, (uint32_t)j);
+  }
+  __syncthreads();
+  // ties at T, lowest indices first (ordered block compaction)
+  int have = s_pos;
+  for (int64_t base = 0; base < n_cols && have < keep_n; base += kTopThreads) {
+    const int64_t j = base + tid;
+    const bool hit = j < n_cols && float_key(s[j]) == T;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    const int lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kTopThreads / 32; ++w) {
+      if (w < warp) before += red[w];
+      tot += red[w];
+    }
+    const int pos = have + before + __popc(bal & ((1u << lane) - 1u));
+    if (hit && pos < keep_n) keys[pos] = pack_key(s[j], (uint32_t)j);
+    have += tot;
+  }
+  __syncthreads();
+  int n2 = 2;
+  while (n2 < keep_n) n2 <<= 1;
+  for (int j = keep_n + tid; j < n2; j += kTopThreads) keys[j] = 0;
+  block_sort_desc<kTopThreads>(keys, n2);
+  for (int j = tid; j < keep_n; j += kTopThreads) {
+    out_scores[out_row * keep_n + j] = key_score(keys[j]);
+    out_idx[out_row * keep_n + j] = (int64_t)key_index(keys[j]) + index_offset;
+  }
+}
+
+}  // namespace
+
+int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
+                              const kdi_patterns* dict, const kdi_gemm_plan* plan,
+                              const uint2* cand, const uint32_t* thr, int keep_n,
+                              int64_t index_offset, float approx_inv_scale, float cert_sigmas,
+                              float* out_scores, int64_t* out_idx, int* flag_list, int* n_flag) {
+  if (exp->rows <= 0) return KDI_OK;
+  const unsigned grid = (unsigned)exp->rows;
+  if (plan->kc == 32)
+    kdi_select_rescore_kernel<32><<<grid, kSelThreads, 0, stream>>>(
+        exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
+        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag);
+  else if (plan->kc == 64)
+    kdi_select_rescore_kernel<64><<<grid, kSelThreads, 0, stream>>>(
+        exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
+        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag);
+  else
+    return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
+  KDI_CUDA(ctx, cudaGetLastError());
+  ctx->tm.kernel_launches++;
+  return KDI_OK;
+}
+
+int kdi_launch_exact_scores(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
+                            const kdi_patterns* dict, const int* rows_list, int64_t row0,
+                            int n_rows, float* scores) {
+  if (n_rows <= 0 || dict->rows <= 0) return KDI_OK;
+  const int groups = (int)kdi_ceil_div(n_rows, kExRows);
+  // enough dictionary slabs to fill the device a few times over
+  int64_t slabs = kdi_ceil_div((int64_t)ctx->sm_count * 8, groups);
+  if (slabs < 1) slabs = 1;
+  int64_t slab = kdi_ceil_div(dict->rows, slabs);
+  if (slab < 8) slab = 8;
+  slabs = kdi_ceil_div(dict->rows, slab);
+  dim3 grid((unsigned)slabs, (unsigned)groups);
+  kdi_exact_scores_kernel<<<grid, kExThreads, 0, stream>>>(exp->a32, dict->a32, exp->s_pitch,
+                                                           dict->rows, rows_list, row0, n_rows,
+                                                           scores, (int)slab);
+  KDI_CUDA(ctx, cudaGetLastError());
+  ctx->tm.kernel_launches++;
+  return KDI_OK;
+}
+
+int kdi_launch_extract_topk(kdi_ctx* ctx, cudaStream_t stream, const float* scores, int n_rows,
+                            int64_t n_cols, const int* rows_list, int64_t row0, int keep_n,
+                            int64_t index_offset, float* out_scores, int64_t* out_idx) {
+  if (n_rows <= 0) return KDI_OK;
+  if (keep_n > kTopMax)
+    return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d exceeds the exact path's limit %d", keep_n, kTopMax);
+  kdi_extract_topk_kernel<<<(unsigned)n_rows, kTopThreads, 0, stream>>>(
+      scores, n_cols, rows_list, row0, keep_n, index_offset, out_scores, out_idx);
+  KDI_CUDA(ctx, cudaGetLastError());
+  ctx->tm.kernel_launches++;
+  return KDI_OK;
+}
