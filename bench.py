@@ -1,0 +1,383 @@
+"""Benchmark of the dictionary-indexing hot path (BASELINE.json metric: EBSD patterns indexed
+per second, 60x60 patterns, 100 000-entry dictionary, NCC, keep_n = 20).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo (CUDA, libkdi)
+  python bench.py --impl reference --gpus N ...          # the reference's CPU arithmetic (oracle port)
+
+One "step" = one full pass of the hot path over one batch of synthetic input:
+normalise experimental + dictionary rows, tensor-core match with fused top-k, exact rescoring,
+(N > 1: all-gather of the per-shard top-k + merge).  N = 1 is BASELINE.json configs[1]
+(10 000 patterns vs 100 000 dictionary entries).  For N > 1 the dictionary (100 000 entries) is
+sharded over the ranks and the pattern count grows with N (10 000 x N), so the work per GPU is
+constant: weak scaling in patterns/s.
+
+`value`   : inputs (raw uint8 patterns, raw float32 dictionary shard) resident in HBM, timed with
+            CUDA events on the library's stream, max over ranks.
+`e2e`     : the same job through the public API with pinned HOST buffers; H2D of both inputs
+            and D2H of the result inside the timed region (wall clock between device syncs).
+`roofline`: the GEMM+top-k kernel; achieved = 2*M*N_shard*S / its CUDA-event duration.
+`cpu_baseline`: the NumPy oracle (the reference's own arithmetic) on the host cores, on a
+            bounded sample, extrapolated linearly in the number of patterns.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SIG = (60, 60)
+S = SIG[0] * SIG[1]
+M_PER_GPU = 10_000
+N_DICT = 100_000
+KEEP_N = 20
+REF_CHUNK = 2083  # the reference's default dictionary chunk: 30 MB of float32 60x60 patterns
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's arithmetic (oracle port), timed on the host cores
+# --------------------------------------------------------------------------------------------
+
+def cpu_sample(exp_u8: np.ndarray, dic_f32: np.ndarray, m_total: int):
+    """Run the reference's chunk loop (prepare chunk -> einsum -> topk -> merge,
+    _dictionary_indexing.py:94-128) for the sample patterns in ``exp_u8`` against the whole
+    dictionary, timing dictionary preparation and matching separately; extrapolate the matching
+    part linearly to ``m_total`` patterns.  Returns (patterns/s at m_total, detail dict)."""
+    from oracle import di_oracle as orc  # the timed CPU arm (allowed use of oracle/)
+
+    m_s = exp_u8.shape[0]
+    n = dic_f32.shape[0]
+    t0 = time.perf_counter()
+    e = orc.prepare_experimental(exp_u8, "ncc", m_s)
+    t_exp = time.perf_counter() - t0
+    dic2 = dic_f32.reshape(n, -1)
+    scores = np.full((m_s, KEEP_N), -1.0, dtype=np.float32)
+    idx = np.zeros((m_s, KEEP_N), dtype=np.int32)
+    t_prep = t_match = 0.0
+    for start in range(0, n, REF_CHUNK):
+        chunk = dic2[start:start + REF_CHUNK]
+        t1 = time.perf_counter()
+        d = orc.prepare_dictionary(chunk, "ncc")
+        t2 = time.perf_counter()
+        sim = orc.match(e, d)
+        k = min(KEEP_N, chunk.shape[0])
+        i_i = orc.argtopk(sim, k) + start
+        s_i = orc.topk(sim, k)
+        all_s = np.hstack((scores, s_i)); all_i = np.hstack((idx, i_i))
+        best = np.argsort(-all_s, axis=1)[:, :KEEP_N]
+        scores = np.take_along_axis(all_s, best, axis=1)
+        idx = np.take_along_axis(all_i, best, axis=1)
+        t3 = time.perf_counter()
+        t_prep += t2 - t1
+        t_match += t3 - t2
+    scale = m_total / m_s
+    t_full = t_prep + (t_exp + t_match) * scale
+    detail = {"sample_patterns": m_s, "dictionary": n, "t_prepare_dictionary_s": round(t_prep, 3),
+              "t_match_sample_s": round(t_match + t_exp, 3), "t_full_extrapolated_s": round(t_full, 3)}
+    return m_total / t_full, detail
+
+
+def host_inputs(m_sample: int, seed_exp=1, seed_dict=2):
+    rng = np.random.default_rng(seed_exp)
+    exp = rng.integers(0, 256, (m_sample,) + SIG, dtype=np.uint8)
+    rng = np.random.default_rng(seed_dict)
+    dic = rng.random((N_DICT,) + SIG, dtype=np.float32)
+    return exp, dic
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    m_total = M_PER_GPU * args.gpus
+    m_s = args.cpu_sample
+    exp, dic = host_inputs(m_s)
+    vals, detail = [], None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        v, detail = cpu_sample(exp, dic, m_total)
+        if i >= args.warmup:
+            vals.append((v, time.perf_counter() - t0))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([t for _, t in vals])) * 1e3
+    cores = os.cpu_count()
+    sample = (f"{m_s} of {m_total} patterns x full {N_DICT}-entry dictionary in {REF_CHUNK}-row chunks per step; "
+              f"matching time scaled by {m_total}/{m_s}, dictionary preparation counted once")
+    line = {
+        "impl": "reference", "metric": "EBSD patterns indexed/sec (60x60, dict=100k, NCC, keep_n=20)",
+        "value": value, "unit": "patterns/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{m_total} uint8 60x60 patterns vs {N_DICT}-entry float32 dictionary, NCC, keep_n={KEEP_N}",
+                   "note": "CPU: NumPy/BLAS restatement of the reference (kikuchipy is pure Python on dask+numpy; dask is not installable here)"},
+        "cpu_baseline": {"value": value, "unit": "patterns/s", "cores": cores, "kind": "port", "sample": sample,
+                         "detail": detail},
+        "e2e": {"value": value, "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import kikuchipy_b200 as kb
+    from kikuchipy_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = kb.default_context(local_rank)
+    if args.cta_group:
+        ctx.set_option(_lib.OPT_CTA_GROUP, args.cta_group)
+    if args.compute_dtype == "bf16":
+        ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 1)
+    if args.strip_tiles:
+        ctx.set_option(_lib.OPT_STRIP_TILES, args.strip_tiles)
+    if args.superblock:
+        ctx.set_option(_lib.OPT_SUPERBLOCK, args.superblock)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+
+    m_total = M_PER_GPU * world
+    start, end = kb.shard_bounds(N_DICT, world, rank)
+    n_shard = end - start
+
+    # synthetic inputs, generated on the device (identical experimental set on every rank)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    exp_dev = torch.randint(0, 256, (m_total,) + SIG, dtype=torch.uint8, device=dev, generator=g)
+    g.manual_seed(2 + rank)
+    dict_dev = torch.rand((n_shard,) + SIG, dtype=torch.float32, device=dev, generator=g)
+    idx_dev = torch.empty((m_total, KEEP_N), dtype=torch.int64, device=dev)
+    sc_dev = torch.empty((m_total, KEEP_N), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        ctx.dictionary_indexing(exp_dev, m_total, dict_dev, n_shard, _lib.KDI_NCC, KEEP_N,
+                                index_offset=start, out=(idx_dev, sc_dev))
+        tm = ctx.timings()
+        if world > 1:
+            s_all, i_all = kb.gather_topk(sc_dev, idx_dev)
+            ctx.merge_topk(s_all, i_all, KEEP_N)
+        return tm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        gemm_ms, launches, tms = [], 0, []
+        for _ in range(args.steps):
+            tm = step_device()
+            gemm_ms.append(tm["gemm_topk_ms"]); launches += tm["kernel_launches"] + (1 if world > 1 else 0)
+            tms.append(tm)
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        dev_ms = e0.elapsed_time(e1)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = m_total / (ms_per_step * 1e-3)
+
+    # ---- end to end: pinned host inputs -> public API -> host result ----------------------
+    exp_host = ctx.pinned_empty((m_total,) + SIG, np.uint8)
+    dict_host = ctx.pinned_empty((n_shard,) + SIG, np.float32)
+    exp_host[...] = exp_dev.cpu().numpy()
+    dict_host[...] = dict_dev.cpu().numpy()
+    h2d = exp_host.nbytes + dict_host.nbytes
+    d2h = m_total * KEEP_N * 12
+
+    def step_e2e():
+        if world == 1:
+            res = kb.dictionary_indexing(exp_host, dict_host, metric="ncc", keep_n=KEEP_N, verbose=False)
+            return res.scores
+        i, s = kb.dictionary_indexing_sharded(exp_host, dict_host, N_DICT, metric="ncc", keep_n=KEEP_N, context=ctx)
+        return s.cpu()
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+
+    if rank != 0:
+        return
+    pk, pk_src = peaks()
+    g_ms = float(np.mean(gemm_ms))
+    flops = 2.0 * m_total * n_shard * S
+    achieved = flops / (g_ms * 1e-3) / 1e12
+    peak = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
+    last = tms[-1]
+    line = {
+        "metric": "EBSD patterns indexed/sec (60x60, dict=100k, NCC, keep_n=20)",
+        "value": value, "unit": "patterns/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16" if args.compute_dtype != "bf16" else "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"{m_total} uint8 60x60 patterns vs {N_DICT}-entry float32 dictionary "
+                        f"({n_shard} rows per GPU), NCC, keep_n={KEEP_N}",
+            "operands": "16-bit tensor-core candidates (fp32 accumulate) + exact fp32 rescoring of every reported score",
+            "l2": "inputs larger than L2 (dictionary shard %.0f MB raw)" % (dict_dev.numel() * 4 / 1e6),
+            "cta_group": args.cta_group or 1,
+            "stage_ms": {k: round(float(np.mean([x[k] for x in tms])), 4)
+                         for k in ("normalize_exp_ms", "normalize_dict_ms", "gemm_topk_ms", "rescore_ms",
+                                   "fallback_ms", "total_ms")},
+            "flagged_rows_last_step": int(last["flagged_rows"]),
+        },
+        "clocks": clocks,
+        "e2e": {"value": m_total / (e2e_ms * 1e-3), "unit": "patterns/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "kdi_gemm_kernel (GEMM + fused top-k)",
+                     "ms_per_launch": g_ms, "peak_source": f"{pk_src} bf16 sustained; burst {pk.get('bf16_tflops')}"},
+    }
+    if world == 1 and not args.no_cpu:
+        exp_s = exp_host[: args.cpu_sample]
+        v, detail = cpu_sample(np.array(exp_s), np.asarray(dict_host), m_total)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "patterns/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{args.cpu_sample} of {m_total} patterns x full dictionary in {REF_CHUNK}-row chunks; matching "
+                      f"time scaled linearly to {m_total} patterns, dictionary preparation counted once",
+            "detail": detail,
+        }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample", type=int, default=500)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--compute-dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--strip-tiles", type=int, default=0)
+    ap.add_argument("--superblock", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

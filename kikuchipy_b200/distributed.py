@@ -34,8 +34,9 @@ def gather_topk(scores, indices, group=None):
     world = dist.get_world_size(group)
     s_all = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
     i_all = torch.empty((world,) + tuple(indices.shape), dtype=indices.dtype, device=indices.device)
-    dist.all_gather_into_tensor(s_all, scores.contiguous(), group=group)
-    dist.all_gather_into_tensor(i_all, indices.contiguous(), group=group)
+    # contiguous slices of one buffer: NCCL takes the flat all-gather path, gloo gathers per slice
+    dist.all_gather(list(s_all.unbind(0)), scores.contiguous(), group=group)
+    dist.all_gather(list(i_all.unbind(0)), indices.contiguous(), group=group)
     return s_all, i_all
 
 

@@ -1,0 +1,352 @@
+"""Parity of the CUDA path (through the C ABI / the Python mirror of the reference surface)
+against the CPU oracle and the committed golden vectors.  Needs a B200.
+
+Gates: scores within 1e-4 of the reference arithmetic (observed ~5e-8);
+index lists identical wherever the reference's own scores are separated by more than ``tie_tol``
+(1e-6; 2e-5 with a signal mask, where the reference's float32 row sums over the NumPy
+fancy-indexed, non-contiguous array are themselves ~1e-5 noisy); strictly identical on the
+reference fixtures and on planted inputs.
+"""
+
+import numpy as np
+import pytest
+
+import kikuchipy_b200 as kb
+from kikuchipy_b200 import _lib
+from oracle import di_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = kb.default_context(0)
+    yield c
+    for opt in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK):
+        c.set_option(opt, 0)
+    c.set_option(_lib.OPT_CTA_GROUP, 1)
+    c.set_signal_mask(None)
+
+
+def _check(ridx, rsc, idx, sc, tie_tol=1e-6, strict=False):
+    assert idx.dtype == np.int64 and sc.dtype == np.float32
+    assert idx.shape == ridx.shape and sc.shape == rsc.shape
+    r = orc.compare_topk(ridx, rsc, idx, sc, tie_tol=tie_tol, score_tol=SCORE_TOL)
+    assert r["scores_ok"], r
+    assert r["tie_ok"], r
+    if strict:
+        assert r["exact_rows"] == 1.0, r
+    # best first
+    assert np.all(np.diff(sc, axis=1) <= 0)
+    return r
+
+
+# ---- prepare_* -------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("metric", ["ncc", "ndp"])
+def test_prepared_rows_match_reference(ctx, golden, metric):
+    g = golden("config1_nickel_x_1000.npz")
+    code = _lib.KDI_NCC if metric == "ncc" else _lib.KDI_NDP
+    ctx.set_signal_mask(None)
+    got = np.asarray(ctx.patterns(g["nickel"], 9, code))
+    assert got.shape == (9, 3600)
+    assert np.max(np.abs(got - g[f"{metric}_prepared_exp"])) < 2e-8
+    # navigation mask drops rows, signal mask compacts columns (False = keep)
+    ctx.set_signal_mask(g["signal_mask"])
+    got = np.asarray(ctx.patterns(g["nickel"], 9, code, row_mask=g["nav_mask"]))
+    ref = orc.prepare_experimental(g["nickel"], metric, 9, g["nav_mask"], g["signal_mask"])
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) < 5e-7
+    ctx.set_signal_mask(None)
+
+
+@pytest.mark.parametrize("metric", ["ncc", "ndp"])
+def test_metric_call_matches_golden_block(golden, metric):
+    """metric(exp, dict) - reference use at tests/test_signals/test_ebsd_master_pattern.py:237-243."""
+    g = golden("config1_nickel_x_1000.npz")
+    dic = orc.synthetic_dictionary(1000, (60, 60), seed=2)
+    cls = kb.NormalizedCrossCorrelationMetric if metric == "ncc" else kb.NormalizedDotProductMetric
+    sim = cls(9, 1000)(g["nickel"], dic)
+    assert sim.shape == (9, 1000) and sim.dtype == np.float32
+    assert np.max(np.abs(sim - g[f"{metric}_sim_f32"])) < 1e-6
+    assert np.max(np.abs(sim - g[f"{metric}_sim_f64"])) < 1e-6
+    m = cls(9, 1000, signal_mask=g["signal_mask"])
+    assert np.max(np.abs(m(g["nickel"], dic) - g[f"{metric}_sim_masked_f32"])) < 2e-5
+    m = cls(9, 9)
+    self_ = m(g["nickel"], g["nickel"].reshape(9, 60, 60))
+    assert np.max(np.abs(self_ - g[f"{metric}_self_f32"])) < 1e-6
+    assert np.allclose(np.diag(self_), 1, atol=1e-6)
+
+
+def test_plugin_hooks_topk(golden):
+    """The three hooks the reference driver calls (_dictionary_indexing.py:70,193-201)."""
+    g = golden("config1_nickel_x_1000.npz")
+    dic = orc.synthetic_dictionary(1000, (60, 60), seed=2)
+    m = kb.NormalizedCrossCorrelationMetric(9, 1000)
+    e = m.prepare_experimental(g["nickel"])
+    d = m.prepare_dictionary(dic.reshape(1000, -1))
+    sim = m.match(e, d)
+    idx = sim.argtopk(5, axis=-1).reshape((-1, 5))
+    sc = sim.topk(5, axis=-1).reshape((-1, 5))
+    ref = g["ncc_sim_f32"]
+    ridx = orc.argtopk(ref, 5)
+    _check(ridx, orc.topk(ref, 5), idx, sc, strict=True)
+    assert np.max(np.abs(np.asarray(sim) - ref)) < 1e-6
+
+
+# ---- BASELINE config 1 and the golden driver vectors ------------------------------------------------
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_config1_nickel(ctx, golden, cta_group):
+    g = golden("config1_nickel_x_1000.npz")
+    dic = orc.synthetic_dictionary(1000, (60, 60), seed=2)
+    ctx.set_option(_lib.OPT_CTA_GROUP, cta_group)
+    res = kb.dictionary_indexing(g["nickel"], dic, metric="ncc", keep_n=5, verbose=False)
+    ridx, rsc = orc.dictionary_indexing(g["nickel"], dic, metric="ncc", keep_n=5)
+    _check(ridx, rsc, res.simulation_indices, res.scores, strict=True)
+    assert res.shape == (3, 3) and res.size == 9 and res.rotations_per_point == 5
+    assert ctx.timings()["gemm_launches"] == 1  # the tensor-core kernel ran
+    ctx.set_option(_lib.OPT_CTA_GROUP, 1)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_golden_driver_vectors(ctx, golden, cta_group):
+    g = golden("driver_64x4096.npz")
+    ctx.set_option(_lib.OPT_CTA_GROUP, cta_group)
+    exp = orc.synthetic_experimental(64, (60, 60), seed=1)
+    dic = orc.synthetic_dictionary(4096, (60, 60), seed=2)
+    idx, sc = ctx.dictionary_indexing(exp, 64, dic, 4096, _lib.KDI_NCC, 20)
+    _check(g["idx"], g["scores"], idx, sc)
+    pexp, j = orc.planted_experimental(dic, 64, seed=3)
+    idx, sc = ctx.dictionary_indexing(pexp, 64, dic, 4096, _lib.KDI_NCC, 20)
+    assert np.array_equal(idx[:, 0], j)
+    _check(g["planted_idx"], orc.dictionary_indexing(pexp, dic, keep_n=20)[1], idx, sc)
+    ctx.set_option(_lib.OPT_CTA_GROUP, 1)
+
+
+# ---- random workloads: metrics, masks, keep_n, operand types, schedules ----------------------------
+
+CASES = [
+    # M, N, sig, keep_n, metric, signal mask, nav mask, options
+    (256, 4096, (60, 60), 20, "ncc", False, False, {}),
+    (256, 4096, (60, 60), 20, "ndp", False, False, {}),
+    (300, 5000, (60, 60), 50, "ncc", False, False, {}),
+    (200, 3000, (60, 60), 1, "ncc", True, True, {}),
+    (130, 2500, (48, 40), 24, "ndp", True, False, {}),
+    (200, 3000, (60, 60), 20, "ncc", False, False, {"bf16": 1}),
+    (300, 5000, (60, 60), 50, "ncc", False, False, {"cg": 2}),
+    (257, 4097, (31, 29), 7, "ncc", False, True, {"cg": 2}),
+    (700, 2100, (20, 20), 20, "ncc", False, False, {"strip": 1, "sb": 1}),
+    (700, 2100, (20, 20), 20, "ncc", False, False, {"strip": 3, "sb": 2, "cg": 2}),
+    (9, 20, (60, 60), 20, "ncc", False, False, {}),          # dictionary smaller than the candidate list
+    (33, 100, (12, 12), 60, "ncc", False, False, {}),        # keep_n beyond the fused path -> exact path
+    (64, 4096, (60, 60), 20, "ncc", False, False, {"exact": 1}),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c[:5]) + str(c[7]) for c in CASES])
+def test_random_workloads(ctx, case):
+    M, N, sig, k, metric, smask, nmask, opt = case
+    ctx.set_option(_lib.OPT_CTA_GROUP, opt.get("cg", 1))
+    ctx.set_option(_lib.OPT_COMPUTE_DTYPE, opt.get("bf16", 0))
+    ctx.set_option(_lib.OPT_FORCE_EXACT, opt.get("exact", 0))
+    ctx.set_option(_lib.OPT_STRIP_TILES, opt.get("strip", 0))
+    ctx.set_option(_lib.OPT_SUPERBLOCK, opt.get("sb", 0))
+    try:
+        exp = orc.synthetic_experimental(M, sig, seed=1)
+        dic = orc.synthetic_dictionary(N, sig, seed=2)
+        before = exp.copy(), dic.copy()
+        sm = orc.circular_signal_mask(sig) if smask else None
+        nm = (np.random.default_rng(5).random(M) < 0.3) if nmask else None
+        ctx.set_signal_mask(sm)
+        idx, sc = ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC if metric == "ncc" else _lib.KDI_NDP,
+                                          k, nav_mask=nm)
+        ridx, rsc = orc.dictionary_indexing(exp, dic, metric=metric, keep_n=k, navigation_mask=nm, signal_mask=sm,
+                                            n_experimental_patterns=M)
+        _check(ridx, rsc, idx, sc, tie_tol=2e-5 if smask else 1e-6)
+        # inputs are never modified (reference tests/test_indexing/test_dictionary_indexing.py:41-43)
+        assert np.array_equal(exp, before[0]) and np.array_equal(dic, before[1])
+    finally:
+        for o in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK):
+            ctx.set_option(o, 0)
+        ctx.set_option(_lib.OPT_CTA_GROUP, 1)
+        ctx.set_signal_mask(None)
+
+
+def test_fused_and_exact_paths_agree_bit_for_bit(ctx):
+    exp = orc.synthetic_experimental(128, (40, 40), seed=1)
+    dic = orc.synthetic_dictionary(6000, (40, 40), seed=2)
+    i1, s1 = ctx.dictionary_indexing(exp, 128, dic, 6000, _lib.KDI_NCC, 20)
+    ctx.set_option(_lib.OPT_FORCE_EXACT, 1)
+    i2, s2 = ctx.dictionary_indexing(exp, 128, dic, 6000, _lib.KDI_NCC, 20)
+    ctx.set_option(_lib.OPT_FORCE_EXACT, 0)
+    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+
+
+def test_duplicate_dictionary_rows_fall_back_to_exact(ctx):
+    """Exact ties across the candidate boundary: the certificate must flag the rows and the exact
+    path must order ties by ascending index."""
+    dic = orc.synthetic_dictionary(400, (20, 20), seed=2)
+    dic[100:180] = dic[7]  # 81 identical rows
+    exp = np.clip(np.rint(dic[[7, 9]] * 255), 0, 255).astype(np.uint8)
+    idx, sc = ctx.dictionary_indexing(exp, 2, dic, 400, _lib.KDI_NCC, 20)
+    assert ctx.timings()["flagged_rows"] >= 1
+    assert list(idx[0]) == [7] + list(range(100, 119))
+    assert np.all(sc[0] == sc[0, 0])
+    assert idx[1, 0] == 9
+
+
+def test_index_offset_and_device_outputs(ctx):
+    import torch
+
+    exp = orc.synthetic_experimental(50, (20, 20), seed=1)
+    dic = orc.synthetic_dictionary(1500, (20, 20), seed=2)
+    ridx, rsc = orc.dictionary_indexing(exp, dic, keep_n=10)
+    idx = torch.empty((50, 10), dtype=torch.int64, device="cuda")
+    sc = torch.empty((50, 10), dtype=torch.float32, device="cuda")
+    ctx.dictionary_indexing(torch.from_numpy(exp).cuda(), 50, torch.from_numpy(dic).cuda(), 1500, _lib.KDI_NCC, 10,
+                            index_offset=1000, out=(idx, sc))
+    _check(ridx + 1000, rsc, idx.cpu().numpy(), sc.cpu().numpy())
+
+
+# ---- reference test-suite semantics (tests/test_indexing/test_dictionary_indexing.py) ---------------
+
+def test_self_dictionary_identity(dummy_array):
+    dic = dummy_array.reshape(-1, 3, 3)
+    before = dummy_array.copy()
+    res = kb.dictionary_indexing(dummy_array, dic, metric="ndp", rechunk=True, verbose=False)  # :27-43
+    assert np.allclose(res.scores[:, 0], 1)
+    assert np.array_equal(res.simulation_indices[:, 0], np.arange(9))
+    assert res.scores.shape == (9, 9)  # keep_n clipped to the dictionary size (:67)
+    assert np.array_equal(dummy_array, before)
+    smask = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 0]], dtype=bool)
+    res = kb.dictionary_indexing(dummy_array, dic, n_per_iteration=2, signal_mask=smask, rechunk=True, verbose=False)
+    assert np.allclose(res.scores[:, 0], 1) and res.simulation_indices.dtype == np.int64  # :45-66
+    ridx, rsc = orc.dictionary_indexing(dummy_array, dic, signal_mask=smask)
+    assert np.max(np.abs(res.scores - rsc)) < 1e-5
+
+
+@pytest.mark.parametrize("nav_slice, nav_shape", [((0, 0), ()), ((0, slice(0, 1)), (1,)), ((0, slice(0, 3)), (3,)),
+                                                   ((slice(0, 3), slice(0, 2)), (3, 2))])
+def test_navigation_shapes(dummy_array, nav_slice, nav_shape):
+    """0-D / 1-D / 2-D navigation (reference :119-145)."""
+    exp = dummy_array[nav_slice]
+    dic = dummy_array.reshape(-1, 3, 3)
+    res = kb.dictionary_indexing(exp, dic, keep_n=3, verbose=False)
+    assert res.shape == nav_shape
+    n = int(np.prod(nav_shape)) if nav_shape else 1
+    assert res.scores.shape == (n, 3) and res.size == n and res.scan_unit == "px"
+    ridx, rsc = orc.dictionary_indexing(exp, dic, keep_n=3)
+    assert np.max(np.abs(res.scores - rsc)) < 1e-5
+    assert np.array_equal(res.simulation_indices[:, 0], ridx[:, 0])
+
+
+def test_navigation_mask_semantics(dummy_array):
+    """reference :166-180 and _dictionary_indexing.py:142-163."""
+    dic = dummy_array.reshape(-1, 3, 3)
+    nav = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 0]], dtype=bool)
+    res = kb.dictionary_indexing(dummy_array, dic, keep_n=1, navigation_mask=nav, verbose=False)
+    assert res.size == 8 and res.rotations_per_point == 1 and res.shape == (3, 3)
+    assert res.prop["scores"].shape == (9,)  # squeezed because keep_n == 1 with a navigation mask
+    assert np.array_equal(res.is_in_data, ~nav.ravel())
+    assert np.allclose(res.scores, 1)
+    res = kb.dictionary_indexing(dummy_array, dic, metric="ndp", navigation_mask=~nav, verbose=False,
+                                 dictionary_rotations=np.tile([1.0, 0, 0, 0], (9, 1)))
+    assert res.size == 1 and res.scores.shape == (1, 9) and res.rotations.shape == (9, 9, 4)
+    res = kb.dictionary_indexing(dummy_array, dic, keep_n=1, verbose=False)
+    assert res.scores.shape == (9, 1)  # no squeeze without a navigation mask (:164-166)
+
+
+def test_info_and_speed_lines(dummy_array, capsys):
+    dic = dummy_array.reshape(-1, 3, 3)
+    kb.dictionary_indexing(dummy_array, dic, phase_name="ni")
+    out = capsys.readouterr().out
+    assert "Dictionary indexing information:\n  Phase name: ni\n  Matching 9 experimental pattern(s) to 9 dictionary pattern(s)\n" in out
+    assert "NormalizedCrossCorrelationMetric: float32, greater is better" in out
+    assert "  Indexing speed: " in out and "comparisons/s" in out
+
+
+# ---- merge and orientation similarity map ------------------------------------------------------------
+
+def test_merge_topk_matches_numpy(ctx):
+    rng = np.random.default_rng(3)
+    L, R, K = 8, 500, 50
+    sc = np.sort(rng.random((L, R, K), dtype=np.float32), axis=2)[:, :, ::-1].copy()
+    idx = rng.permutation(L * R * K).reshape(L, R, K).astype(np.int64)
+    io, so = ctx.merge_topk(sc, idx, 50)
+    alls = np.concatenate(list(sc), axis=1)
+    alli = np.concatenate(list(idx), axis=1)
+    best = np.argsort(-alls, axis=1, kind="stable")[:, :50]
+    assert np.array_equal(so, np.take_along_axis(alls, best, 1))
+    r = orc.compare_topk(np.take_along_axis(alli, best, 1), np.take_along_axis(alls, best, 1), io, so, tie_tol=0)
+    assert r["tie_ok"]
+    # ties are ordered by ascending index
+    sc2 = np.zeros((2, 3, 4), np.float32)
+    idx2 = np.arange(24, dtype=np.int64)[::-1].reshape(2, 3, 4).copy()
+    io, so = ctx.merge_topk(sc2, idx2, 5)
+    for r_ in range(3):
+        pool = np.sort(np.concatenate([idx2[0, r_], idx2[1, r_]]))
+        assert list(io[r_]) == list(pool[:5])
+
+
+def test_osm_goldens(ctx, golden):
+    g = golden("osm.npz")
+
+    class X:
+        def __init__(self, idx, shape):
+            self.prop = {"simulation_indices": idx}
+            self.shape = shape
+
+    assert np.array_equal(kb.orientation_similarity_map(X(g["idx34"], (3, 4))), g["osm34"])
+    assert np.array_equal(kb.orientation_similarity_map(X(g["idx34"], (3, 4)), n_best=2, normalize=True),
+                          g["osm34_norm_n2"])
+    o = kb.orientation_similarity_map(X(g["idx34"], (3, 4)), from_n_best=1)
+    assert o.shape == (3, 4, 3) and np.array_equal(o, g["osm34_from1"])
+    idx = g["idx_17x23"]
+    assert np.array_equal(kb.orientation_similarity_map(X(idx, (17, 23))), g["osm_17x23"])
+    assert np.array_equal(kb.orientation_similarity_map(X(idx, (17, 23)), n_best=7, normalize=True),
+                          g["osm_17x23_n7_norm"])
+    assert np.array_equal(kb.orientation_similarity_map(X(idx, (17, 23)), footprint=g["footprint8"], center_index=4),
+                          g["osm_17x23_fp8"])
+    # reference tests/test_indexing/test_orientation_similarity_map.py:27-64
+    assert np.allclose(kb.orientation_similarity_map(X(g["idx_tiled"], (10, 10))), 5)
+    assert np.allclose(kb.orientation_similarity_map(X(g["idx_tiled"], (10, 10)), normalize=True), 1)
+    with pytest.raises(ValueError, match="n_best 6 cannot be greater than keep_n 5"):
+        kb.orientation_similarity_map(X(g["idx_tiled"], (10, 10)), n_best=6)
+    assert kb.orientation_similarity_map(X(g["idx_tiled"], (10, 10)), n_best=5, from_n_best=2).shape == (10, 10, 4)
+    assert np.isnan(kb.orientation_similarity_map(X(g["idx34"][:1], (1, 1))))
+
+
+# ---- BASELINE sizes through size-independent properties --------------------------------------------
+
+def test_config2_full_size_properties(ctx):
+    """10 000 x 100 000 (BASELINE configs[1]) on device-generated planted data: the planted row
+    must be the best match of every pattern, lists are sorted, indices are valid and unique, and
+    the best score equals an independent exact evaluation of that pair."""
+    import torch
+
+    M, N, sig, k = 10_000, 100_000, (60, 60), 20
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    dic = torch.rand((N,) + sig, device="cuda", generator=g)
+    j = torch.randint(0, N, (M,), device="cuda", generator=g)
+    noise = torch.rand((M,) + sig, device="cuda", generator=g)
+    exp = torch.clamp(torch.round(255.0 * (0.7 * dic[j] + 0.3 * noise)), 0, 255).to(torch.uint8)
+    idx = torch.empty((M, k), dtype=torch.int64, device="cuda")
+    sc = torch.empty((M, k), dtype=torch.float32, device="cuda")
+    for cg in (1, 2):
+        ctx.set_option(_lib.OPT_CTA_GROUP, cg)
+        ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, k, out=(idx, sc))
+        assert ctx.timings()["gemm_launches"] == 1
+        assert torch.equal(idx[:, 0], j)
+        assert bool((sc[:, :-1] >= sc[:, 1:]).all())
+        assert int(idx.min()) >= 0 and int(idx.max()) < N
+        srt = torch.sort(idx, dim=1).values
+        assert bool((srt[:, 1:] != srt[:, :-1]).all())
+        # independent check of the best score on a sample of rows (torch float64)
+        rows = torch.arange(0, M, 97, device="cuda")
+        e = exp[rows].double().flatten(1); e = e - e.mean(1, keepdim=True); e = e / e.norm(dim=1, keepdim=True)
+        d = dic[j[rows]].double().flatten(1); d = d - d.mean(1, keepdim=True); d = d / d.norm(dim=1, keepdim=True)
+        assert float(((e * d).sum(1) - sc[rows, 0].double()).abs().max()) < 1e-5
+    ctx.set_option(_lib.OPT_CTA_GROUP, 1)
