@@ -62,6 +62,55 @@ int kdi_ws2_reserve(kdi_ctx* ctx, size_t bytes) {
   return reserve(ctx, &ctx->ws2, &ctx->ws2_bytes, bytes);
 }
 
+// ---- pooled device allocations for pattern sets -------------------------------------------
+int kdi_dev_alloc(kdi_ctx* ctx, size_t bytes, void** out, size_t* got) {
+  int best = -1;
+  for (int i = 0; i < (int)ctx->pool.size(); ++i) {
+    const size_t b = ctx->pool[i].second;
+    if (b >= bytes && b <= bytes + bytes / 4 + (1u << 20) &&
+        (best < 0 || b < ctx->pool[best].second))
+      best = i;
+  }
+  if (best >= 0) {
+    *out = ctx->pool[best].first;
+    *got = ctx->pool[best].second;
+    ctx->pool_bytes -= *got;
+    ctx->pool.erase(ctx->pool.begin() + best);
+    return KDI_OK;
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    kdi_pool_trim(ctx, 0);  // give cached blocks back and retry once
+    e = cudaMalloc(out, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return kdi_fail(ctx, KDI_ENOMEM, "device allocation of %zu bytes failed: %s", bytes,
+                    cudaGetErrorString(e));
+  }
+  *got = bytes;
+  return KDI_OK;
+}
+
+void kdi_pool_trim(kdi_ctx* ctx, size_t keep_bytes) {
+  while (!ctx->pool.empty() && ctx->pool_bytes > keep_bytes) {
+    cudaFree(ctx->pool.front().first);
+    ctx->pool_bytes -= ctx->pool.front().second;
+    ctx->pool.erase(ctx->pool.begin());
+  }
+}
+
+void kdi_dev_free(kdi_ctx* ctx, void* p, size_t bytes) {
+  if (!p) return;
+  if (!ctx) { cudaFree(p); return; }
+  ctx->pool.emplace_back(p, bytes);
+  ctx->pool_bytes += bytes;
+  // keep at most a quarter of the device memory cached
+  kdi_pool_trim(ctx, ctx->total_mem / 4);
+}
+
 extern "C" {
 
 int kdi_version(void) { return KDI_VERSION; }
@@ -120,6 +169,7 @@ int kdi_destroy(kdi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
+  kdi_pool_trim(ctx, 0);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
   if (ctx->d_cols) cudaFree(ctx->d_cols);
@@ -247,14 +297,12 @@ int kdi_patterns_alloc(kdi_ctx* ctx, int64_t rows, int64_t S, int metric, kdi_pa
   p->compute_dtype = ctx->compute_dtype;
   const size_t n32 = (size_t)(rows > 0 ? rows : 1) * p->s_pitch * sizeof(float);
   const size_t n16 = (size_t)(rows > 0 ? rows : 1) * p->kp * 2;
-  cudaError_t e = cudaMalloc(&p->a32, n32);
-  if (e == cudaSuccess) e = cudaMalloc(&p->a16, n16);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    if (p->a32) cudaFree(p->a32);
+  int rc = kdi_dev_alloc(ctx, n32, reinterpret_cast<void**>(&p->a32), &p->a32_bytes);
+  if (rc == KDI_OK) rc = kdi_dev_alloc(ctx, n16, &p->a16, &p->a16_bytes);
+  if (rc != KDI_OK) {
+    kdi_dev_free(ctx, p->a32, p->a32_bytes);
     delete p;
-    return kdi_fail(ctx, KDI_ENOMEM, "device allocation for %lld patterns failed: %s", (long long)rows,
-                    cudaGetErrorString(e));
+    return rc;
   }
   *out = p;
   return KDI_OK;
@@ -351,8 +399,8 @@ int kdi_patterns_destroy(kdi_ctx* ctx, kdi_patterns* p) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
   }
-  if (p->a32) cudaFree(p->a32);
-  if (p->a16) cudaFree(p->a16);
+  kdi_dev_free(ctx, p->a32, p->a32_bytes);
+  kdi_dev_free(ctx, p->a16, p->a16_bytes);
   delete p;
   return KDI_OK;
 }

@@ -24,7 +24,7 @@ using kdi::float_key;
 using kdi::key_float;
 
 constexpr int kSelThreads = 128;
-constexpr int kSelBuf = 1024;  // candidates >= the row's final threshold that fit in smem
+constexpr int kSelBuf = 2048;  // candidate keys sorted per batch in shared memory
 
 // dot product of two zero-padded float32 rows of n4 float4 each, by one warp.  fp32 FMAs in
 // four accumulators per lane, reduction in double.  Every exact score in the library goes
@@ -88,29 +88,37 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
 
   const int64_t row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-
-  // 1. gather candidates at or above the row's final threshold
-  const uint32_t tkey = thr[row];
+  // 1+2. gather candidates at or above the row's threshold in buffer-sized batches; after each
+  // batch keep the kc best by tensor-core score (and tighten the threshold with the kc-th)
+  uint32_t tkey = thr[row];
   const int64_t total = (int64_t)n_strips * KC;
   const uint2* c = cand + row * total;
-  bool overflow = false;
-  for (int64_t i = tid; i < total; i += kSelThreads) {
-    const uint2 e = c[i];
-    if (e.y != 0xFFFFFFFFu && float_key(__uint_as_float(e.x)) >= tkey) {
-      const int pos = atomicAdd(&s_count, 1);
-      if (pos < kSelBuf) keys[pos] = pack_key(__uint_as_float(e.x), e.y);
+  int kept = 0;  // sorted entries carried over from the previous batch
+  constexpr int kBatch = kSelBuf - KC;
+  for (int64_t base = 0; base < total; base += kBatch) {
+    if (tid == 0) s_count = kept;
+    __syncthreads();
+    const int64_t end = base + kBatch < total ? base + kBatch : total;
+    for (int64_t i = base + tid; i < end; i += kSelThreads) {
+      const uint2 e = c[i];
+      if (e.y != 0xFFFFFFFFu && float_key(__uint_as_float(e.x)) >= tkey)
+        keys[atomicAdd(&s_count, 1)] = pack_key(__uint_as_float(e.x), e.y);
     }
+    __syncthreads();
+    const int cnt = s_count;
+    int n2 = 64;
+    while (n2 < cnt) n2 <<= 1;
+    for (int i = cnt + tid; i < n2; i += kSelThreads) keys[i] = 0;  // below every real key
+    block_sort_desc<kSelThreads>(keys, n2);
+    kept = cnt < KC ? cnt : KC;
+    if (kept == KC) {
+      const uint32_t k32 = (uint32_t)(keys[KC - 1] >> 32);
+      tkey = k32 > tkey ? k32 : tkey;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  int count = s_count;
-  if (count > kSelBuf) { overflow = true; count = kSelBuf; }
-  // 2. order by tensor-core score, keep the kc best
-  int n2 = 64;
-  while (n2 < count) n2 <<= 1;
-  for (int i = count + tid; i < n2; i += kSelThreads) keys[i] = 0;  // below every real key
-  block_sort_desc<kSelThreads>(keys, n2);
+  const int count = kept;
+  const bool overflow = false;
   const int nsel = count < KC ? count : KC;
   if (tid < KC) {
     if (tid < nsel) { ap[tid] = key_score(keys[tid]) * inv_scale; ci[tid] = key_index(keys[tid]); }
