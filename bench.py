@@ -315,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
                         f"({n_shard} rows per GPU), NCC, keep_n={KEEP_N}",
             "operands": "16-bit tensor-core candidates (fp32 accumulate) + exact fp32 rescoring of every reported score",
             "l2": "inputs larger than L2 (dictionary shard %.0f MB raw)" % (dict_dev.numel() * 4 / 1e6),
-            "cta_group": args.cta_group or 1,
+            "cta_group": args.cta_group or 2,
             "stage_ms": {k: round(float(np.mean([x[k] for x in tms])), 4)
                          for k in ("normalize_exp_ms", "normalize_dict_ms", "gemm_topk_ms", "rescore_ms",
                                    "fallback_ms", "total_ms")},

@@ -61,7 +61,7 @@ extern "C" {
 #define KDI_OPT_COMPUTE_DTYPE 0 /* 0 = fp16 (scaled, default), 1 = bf16: operand type of the tensor-core pass */
 #define KDI_OPT_CERT_SIGMAS 1   /* width of the candidate certificate in sigmas (default 8)              */
 #define KDI_OPT_FORCE_EXACT 2   /* 1 = skip the tensor-core pass, score every pair in fp32/fp64 (validation) */
-#define KDI_OPT_CTA_GROUP 3     /* 1 or 2: tcgen05 cta_group of the GEMM kernel                            */
+#define KDI_OPT_CTA_GROUP 3     /* 1 or 2 (default): tcgen05 cta_group of the GEMM kernel                  */
 #define KDI_OPT_STRIP_TILES 4   /* N tiles per work unit (L2 reuse knob)                                   */
 #define KDI_OPT_SUPERBLOCK 5    /* M tiles per super-block (L2 reuse knob)                                 */
 

@@ -40,10 +40,8 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 
 }  // namespace
 
-// match + top-k of device-resident pattern sets; outputs on host or device
-int kdi_match_topk_device(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict,
-                          int keep_n, int64_t index_offset, float* scores_out,
-                          int64_t* indices_out, int out_loc) {
+int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict, int keep_n,
+                    float* scores_out, int64_t* indices_out, int out_loc, kdi_match_job* job) {
   if (!exp || !dict || !scores_out || !indices_out)
     return kdi_fail(ctx, KDI_EINVAL, "kdi_match_topk: NULL argument");
   if (out_loc != KDI_HOST && out_loc != KDI_DEVICE) return kdi_fail(ctx, KDI_EINVAL, "bad output location");
@@ -54,66 +52,104 @@ int kdi_match_topk_device(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patte
   if (keep_n < 1 || keep_n > N)
     return kdi_fail(ctx, KDI_EINVAL, "keep_n %d must be in [1, %lld]", keep_n, (long long)N);
   if (N > 0xFFFFFFFELL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "dictionary too large");
+  *job = kdi_match_job();
+  job->M = M;
+  job->N = N;
+  job->keep_n = keep_n;
+  job->out_loc = out_loc;
+  job->scores_out = scores_out;
+  job->indices_out = indices_out;
   if (M == 0) return KDI_OK;
-
-  const bool fused = !ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0;
-  kdi_gemm_plan plan;
-  size_t off_cand = 0, off_thr = 0, off_flags = 0, off_nflag = 0, off_sc = 0, off_ix = 0, total = 0;
-  if (fused) {
-    KDI_TRY(kdi_gemm_make_plan(ctx, M, N, exp->kp, keep_n, &plan));
-    off_cand = 0;
-    off_thr = align_up(off_cand + plan.cand_bytes, 256);
-    off_flags = align_up(off_thr + plan.thr_bytes, 256);
+  job->fused = !ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0;
+  size_t off_thr = 0, off_flags = 0, off_nflag = 0, total = 0;
+  if (job->fused) {
+    KDI_TRY(kdi_gemm_make_plan(ctx, M, N, exp->kp, keep_n, &job->plan));
+    off_thr = align_up(job->plan.cand_bytes, 256);
+    off_flags = align_up(off_thr + job->plan.thr_bytes, 256);
     off_nflag = align_up(off_flags + (size_t)M * sizeof(int), 256);
     total = off_nflag + 256;
   }
-  off_sc = align_up(total, 256);
-  off_ix = align_up(off_sc + (size_t)M * keep_n * sizeof(float), 256);
+  const size_t off_sc = align_up(total, 256);
+  const size_t off_ix = align_up(off_sc + (size_t)M * keep_n * sizeof(float), 256);
   total = off_ix + (size_t)M * keep_n * sizeof(int64_t);
   KDI_TRY(kdi_ws_reserve(ctx, total));
   uint8_t* ws = reinterpret_cast<uint8_t*>(ctx->ws);
-  float* d_sc = out_loc == KDI_DEVICE ? scores_out : reinterpret_cast<float*>(ws + off_sc);
-  int64_t* d_ix = out_loc == KDI_DEVICE ? indices_out : reinterpret_cast<int64_t*>(ws + off_ix);
+  job->d_sc = out_loc == KDI_DEVICE ? scores_out : reinterpret_cast<float*>(ws + off_sc);
+  job->d_ix = out_loc == KDI_DEVICE ? indices_out : reinterpret_cast<int64_t*>(ws + off_ix);
+  if (job->fused) {
+    job->cand = reinterpret_cast<uint2*>(ws);
+    job->thr = reinterpret_cast<uint32_t*>(ws + off_thr);
+    job->flags = reinterpret_cast<int*>(ws + off_flags);
+    job->d_nflag = reinterpret_cast<int*>(ws + off_nflag);
+    KDI_CUDA(ctx, cudaMemsetAsync(job->d_nflag, 0, sizeof(int), ctx->stream));
+    KDI_TRY(kdi_launch_cand_init(ctx, ctx->stream, job->thr, M));
+  }
+  return KDI_OK;
+}
 
+int kdi_match_advance(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
+                      const kdi_patterns* dict, int64_t rows_ready) {
+  if (!job->fused || job->M == 0) return KDI_OK;
+  const int64_t strip_rows = (int64_t)job->plan.strip_tiles * KDI_TILE_N;
+  int ready = rows_ready >= job->N ? job->plan.n_strips : (int)(rows_ready / strip_rows);
+  if (ready > job->plan.n_strips) ready = job->plan.n_strips;
+  if (ready <= job->strips_done) return KDI_OK;
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
+  KDI_TRY(kdi_launch_gemm_topk(ctx, ctx->stream, exp, dict, &job->plan, job->strips_done,
+                               ready - job->strips_done, job->cand, job->thr));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
+  job->strips_done = ready;
+  return KDI_OK;
+}
+
+int kdi_match_finish(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
+                     const kdi_patterns* dict, int64_t index_offset) {
+  const int64_t M = job->M;
+  const int keep_n = job->keep_n;
+  if (M == 0) return KDI_OK;
   cudaStream_t st = ctx->stream;
-  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
   int n_flag = 0;
-  if (fused) {
-    uint2* cand = reinterpret_cast<uint2*>(ws + off_cand);
-    uint32_t* thr = reinterpret_cast<uint32_t*>(ws + off_thr);
-    int* flags = reinterpret_cast<int*>(ws + off_flags);
-    int* d_nflag = reinterpret_cast<int*>(ws + off_nflag);
-    KDI_CUDA(ctx, cudaMemsetAsync(d_nflag, 0, sizeof(int), st));
-    KDI_TRY(kdi_launch_cand_init(ctx, st, thr, M));
-    KDI_TRY(kdi_launch_gemm_topk(ctx, st, exp, dict, &plan, cand, thr));
-    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+  if (job->fused) {
+    if (job->strips_done != job->plan.n_strips)
+      return kdi_fail(ctx, KDI_EINTERNAL, "match finished before every dictionary strip was processed");
     const float inv = 1.0f / (KDI_OP_SCALE * KDI_OP_SCALE);
-    KDI_TRY(kdi_launch_select_rescore(ctx, st, exp, dict, &plan, cand, thr, keep_n, index_offset, inv,
-                                      (float)ctx->cert_sigmas, d_sc, d_ix, flags, d_nflag));
+    KDI_TRY(kdi_launch_select_rescore(ctx, st, exp, dict, &job->plan, job->cand, job->thr, keep_n,
+                                      index_offset, inv, (float)ctx->cert_sigmas, job->d_sc, job->d_ix,
+                                      job->flags, job->d_nflag));
     KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    KDI_CUDA(ctx, cudaMemcpyAsync(&n_flag, d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KDI_CUDA(ctx, cudaMemcpyAsync(&n_flag, job->d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
     KDI_CUDA(ctx, cudaStreamSynchronize(st));
     if (n_flag > 0)
-      KDI_TRY(exact_rows(ctx, exp, dict, flags, 0, n_flag, keep_n, index_offset, d_sc, d_ix));
+      KDI_TRY(exact_rows(ctx, exp, dict, job->flags, 0, n_flag, keep_n, index_offset, job->d_sc, job->d_ix));
   } else {
-    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    KDI_TRY(exact_rows(ctx, exp, dict, nullptr, 0, M, keep_n, index_offset, d_sc, d_ix));
+    KDI_TRY(exact_rows(ctx, exp, dict, nullptr, 0, M, keep_n, index_offset, job->d_sc, job->d_ix));
   }
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-  if (out_loc == KDI_HOST) {
-    KDI_CUDA(ctx, cudaMemcpyAsync(scores_out, d_sc, (size_t)M * keep_n * sizeof(float),
+  if (job->out_loc == KDI_HOST) {
+    KDI_CUDA(ctx, cudaMemcpyAsync(job->scores_out, job->d_sc, (size_t)M * keep_n * sizeof(float),
                                   cudaMemcpyDeviceToHost, st));
-    KDI_CUDA(ctx, cudaMemcpyAsync(indices_out, d_ix, (size_t)M * keep_n * sizeof(int64_t),
+    KDI_CUDA(ctx, cudaMemcpyAsync(job->indices_out, job->d_ix, (size_t)M * keep_n * sizeof(int64_t),
                                   cudaMemcpyDeviceToHost, st));
     ctx->tm.d2h_bytes += (int64_t)M * keep_n * 12;
   }
   KDI_CUDA(ctx, cudaStreamSynchronize(st));
-  ctx->tm.gemm_topk_ms += ev_ms(ctx->ev[2], ctx->ev[3]);
+  if (job->fused) ctx->tm.gemm_topk_ms += ev_ms(ctx->ev[8], ctx->ev[9]);  // last GEMM launch
   ctx->tm.rescore_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
   ctx->tm.fallback_ms += ev_ms(ctx->ev[4], ctx->ev[5]);
-  ctx->tm.flagged_rows += fused ? n_flag : M;
+  ctx->tm.flagged_rows += job->fused ? n_flag : M;
   return KDI_OK;
+}
+
+// match + top-k of device-resident pattern sets; outputs on host or device
+int kdi_match_topk_device(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict,
+                          int keep_n, int64_t index_offset, float* scores_out,
+                          int64_t* indices_out, int out_loc) {
+  kdi_match_job job;
+  KDI_TRY(kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, &job));
+  KDI_TRY(kdi_match_advance(ctx, &job, exp, dict, dict->rows));
+  return kdi_match_finish(ctx, &job, exp, dict, index_offset);
 }
 
 extern "C" {
@@ -236,15 +272,21 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
   KDI_TRY(kdi_patterns_create(ctx, experimental, exp_loc, exp_dtype, exp_rows, S, metric, nav_mask, &exp));
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
 
-  // prepare_dictionary, streamed.  The reference prepares one chunk of n_per_iteration rows per
-  // iteration (_dictionary_indexing.py:102-117); the result does not depend on the chunking, so
-  // the pieces moved here are sized for the copy engine, not by n_per_iteration.
+  // prepare_dictionary + match, streamed.  The reference prepares and matches one chunk of
+  // n_per_iteration rows per iteration (_dictionary_indexing.py:102-128); the result does not
+  // depend on the chunking, so the pieces moved here are sized for the copy engine (64 MB) and the
+  // tensor-core pass runs over every group of pieces as soon as it has been normalised, while
+  // the next pieces are still in flight on the copy stream.
   (void)n_per_iteration;
   kdi_patterns* dict = nullptr;
+  kdi_match_job job;
   int rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict);
+  if (rc == KDI_OK) rc = kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, &job);
   if (rc == KDI_OK) {
     if (dict_loc == KDI_DEVICE) {
       rc = kdi_patterns_fill(ctx, st, dict, 0, dictionary, dict_dtype, dict_rows, nullptr);
+      if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+      if (rc == KDI_OK) rc = kdi_match_advance(ctx, &job, exp, dict, dict_rows);
     } else {
       const size_t row_bytes = (size_t)S * dsz;
       int64_t piece = (int64_t)std::max<size_t>(1, (64u << 20) / row_bytes);
@@ -253,6 +295,9 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
       rc = kdi_ws2_reserve(ctx, 2 * slot_bytes);
       uint8_t* stage = reinterpret_cast<uint8_t*>(ctx->ws2);
       const uint8_t* src = reinterpret_cast<const uint8_t*>(dictionary);
+      // run the tensor-core pass about 8 times over the upload (launches stay efficient)
+      const int64_t group_rows = std::max<int64_t>(dict_rows / 8, 8192);
+      int64_t next_advance = group_rows;
       int it = 0;
       for (int64_t r0 = 0; rc == KDI_OK && r0 < dict_rows; r0 += piece, ++it) {
         const int slot = it & 1;
@@ -273,16 +318,17 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
         rc = kdi_patterns_fill(ctx, st, dict, r0, stage + slot * slot_bytes, dict_dtype, nr, nullptr);
         if (rc == KDI_OK && cudaEventRecord(ctx->free_ev[slot], st) != cudaSuccess)
           rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+        const int64_t ready = r0 + nr;
+        if (rc == KDI_OK && (ready >= next_advance || ready == dict_rows)) {
+          if (ready == dict_rows && cudaEventRecord(ctx->ev[7], st) != cudaSuccess)
+            rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+          if (rc == KDI_OK) rc = kdi_match_advance(ctx, &job, exp, dict, ready);
+          next_advance = ready + group_rows;
+        }
       }
     }
   }
-  if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
-  // match + top-k + merge
-  if (rc == KDI_OK) {
-    const kdi_timings keep = ctx->tm;
-    (void)keep;
-    rc = kdi_match_topk_device(ctx, exp, dict, keep_n, index_offset, scores_out, indices_out, out_loc);
-  }
+  if (rc == KDI_OK) rc = kdi_match_finish(ctx, &job, exp, dict, index_offset);
   if (rc == KDI_OK) {
     cudaEventRecord(ctx->ev[1], st);
     if (cudaStreamSynchronize(st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");

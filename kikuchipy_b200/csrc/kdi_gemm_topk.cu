@@ -41,9 +41,11 @@ struct GemmParams {
   int m_blocks;     // row blocks of 128*CG rows
   int n_tiles;      // N tiles of 256 rows
   int strip_tiles;  // N tiles per unit
-  int n_strips;
+  int n_strips;     // strips of the whole dictionary (candidate-list layout)
+  int strip0;       // first strip of this launch
+  int launch_strips;  // strips covered by this launch
   int superblock;  // row blocks per super-block
-  int64_t units;
+  int64_t units;    // m_blocks * launch_strips
   int stages;
   int fmt;  // 0 fp16, 1 bf16
   uint2* cand;
@@ -68,11 +70,11 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
 
 // unit u -> (row block, strip); order: super-block -> strip -> row block inside the super-block
 __device__ __forceinline__ void decode_unit(const GemmParams& p, int64_t u, int& mb, int& strip) {
-  const int units_per_sb = p.superblock * p.n_strips;
+  const int units_per_sb = p.superblock * p.launch_strips;
   const int sb = (int)(u / units_per_sb);
   const int rem = (int)(u - (int64_t)sb * units_per_sb);
   const int sb_blocks = min(p.superblock, p.m_blocks - sb * p.superblock);
-  strip = rem / sb_blocks;
+  strip = p.strip0 + rem / sb_blocks;
   mb = sb * p.superblock + rem % sb_blocks;
 }
 
@@ -478,8 +480,10 @@ static int check_operands(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patte
 }
 
 int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
-                         const kdi_patterns* dict, const kdi_gemm_plan* plan, uint2* cand,
-                         uint32_t* thr) {
+                         const kdi_patterns* dict, const kdi_gemm_plan* plan, int strip0,
+                         int strip_count, uint2* cand, uint32_t* thr) {
+  if (strip0 < 0 || strip_count < 1 || strip0 + strip_count > plan->n_strips)
+    return kdi_fail(ctx, KDI_EINTERNAL, "GEMM strip range out of bounds");
   KDI_TRY(check_operands(ctx, exp, dict));
   const int cg = plan->cta_group;
   CUtensorMap tmA, tmB;
@@ -493,8 +497,10 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   p.n_tiles = plan->n_tiles;
   p.strip_tiles = plan->strip_tiles;
   p.n_strips = plan->n_strips;
+  p.strip0 = strip0;
+  p.launch_strips = strip_count;
   p.superblock = plan->superblock;
-  p.units = plan->units;
+  p.units = (int64_t)plan->m_blocks * strip_count;
   p.stages = plan->stages;
   p.fmt = exp->compute_dtype;
   p.cand = cand;
@@ -523,6 +529,8 @@ int kdi_launch_gemm_full(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   p.strip_tiles = ctx->strip_tiles > 0 ? ctx->strip_tiles : 2;
   if (p.strip_tiles > p.n_tiles) p.strip_tiles = p.n_tiles;
   p.n_strips = (int)kdi_ceil_div(p.n_tiles, p.strip_tiles);
+  p.strip0 = 0;
+  p.launch_strips = p.n_strips;
   p.superblock = ctx->superblock > 0 && ctx->superblock < p.m_blocks ? ctx->superblock : p.m_blocks;
   p.units = (int64_t)p.m_blocks * p.n_strips;
   p.stages = stages_for(cg, 0, 1);

@@ -24,7 +24,7 @@ using kdi::float_key;
 using kdi::key_float;
 
 constexpr int kSelThreads = 128;
-constexpr int kSelBuf = 2048;  // candidate keys sorted per batch in shared memory
+constexpr int kSelBuf = 512;  // candidate keys held in shared memory between compactions
 
 // dot product of two zero-padded float32 rows of n4 float4 each, by one warp.  fp32 FMAs in
 // four accumulators per lane, reduction in double.  Every exact score in the library goes
@@ -32,7 +32,21 @@ constexpr int kSelBuf = 2048;  // candidate keys sorted per batch in shared memo
 __device__ __forceinline__ float warp_dot(const float4* __restrict__ a, const float4* __restrict__ b,
                                           int n4, int lane) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = lane; j < n4; j += 32) {
+  int j = lane;
+  // four independent 16-byte loads of the dictionary row in flight per lane
+  for (; j + 96 < n4; j += 128) {
+    const float4 y0 = __ldg(b + j), y1 = __ldg(b + j + 32), y2 = __ldg(b + j + 64), y3 = __ldg(b + j + 96);
+    const float4 x0 = __ldg(a + j), x1 = __ldg(a + j + 32), x2 = __ldg(a + j + 64), x3 = __ldg(a + j + 96);
+    acc.x = fmaf(x0.x, y0.x, acc.x); acc.y = fmaf(x0.y, y0.y, acc.y);
+    acc.z = fmaf(x0.z, y0.z, acc.z); acc.w = fmaf(x0.w, y0.w, acc.w);
+    acc.x = fmaf(x1.x, y1.x, acc.x); acc.y = fmaf(x1.y, y1.y, acc.y);
+    acc.z = fmaf(x1.z, y1.z, acc.z); acc.w = fmaf(x1.w, y1.w, acc.w);
+    acc.x = fmaf(x2.x, y2.x, acc.x); acc.y = fmaf(x2.y, y2.y, acc.y);
+    acc.z = fmaf(x2.z, y2.z, acc.z); acc.w = fmaf(x2.w, y2.w, acc.w);
+    acc.x = fmaf(x3.x, y3.x, acc.x); acc.y = fmaf(x3.y, y3.y, acc.y);
+    acc.z = fmaf(x3.z, y3.z, acc.z); acc.w = fmaf(x3.w, y3.w, acc.w);
+  }
+  for (; j < n4; j += 32) {
     const float4 x = __ldg(a + j);
     const float4 y = __ldg(b + j);
     acc.x = fmaf(x.x, y.x, acc.x);
@@ -85,52 +99,95 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   __shared__ uint32_t ci[KC];
   __shared__ int s_count;
   __shared__ float s_red[2];
+  __shared__ float s_ek;
 
   const int64_t row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // 1+2. gather candidates at or above the row's threshold in buffer-sized batches; after each
-  // batch keep the kc best by tensor-core score (and tighten the threshold with the kc-th)
+  // 1+2. stream the row's candidate lists through a small shared-memory buffer: entries at or
+  // above the running threshold are appended; whenever the buffer could overflow it is sorted,
+  // the kc best are kept and the threshold is raised to the kc-th best (so later entries are
+  // filtered harder and the expected number of survivors stays ~kc*ln(total/buffer))
   uint32_t tkey = thr[row];
   const int64_t total = (int64_t)n_strips * KC;
   const uint2* c = cand + row * total;
-  int kept = 0;  // sorted entries carried over from the previous batch
-  constexpr int kBatch = kSelBuf - KC;
-  for (int64_t base = 0; base < total; base += kBatch) {
-    if (tid == 0) s_count = kept;
-    __syncthreads();
-    const int64_t end = base + kBatch < total ? base + kBatch : total;
-    for (int64_t i = base + tid; i < end; i += kSelThreads) {
+  int kept = 0;      // entries currently in the buffer
+  bool sorted = true;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < total; base += kSelThreads) {
+    const int64_t i = base + tid;
+    if (i < total) {
       const uint2 e = c[i];
       if (e.y != 0xFFFFFFFFu && float_key(__uint_as_float(e.x)) >= tkey)
         keys[atomicAdd(&s_count, 1)] = pack_key(__uint_as_float(e.x), e.y);
     }
     __syncthreads();
-    const int cnt = s_count;
-    int n2 = 64;
-    while (n2 < cnt) n2 <<= 1;
-    for (int i = cnt + tid; i < n2; i += kSelThreads) keys[i] = 0;  // below every real key
-    block_sort_desc<kSelThreads>(keys, n2);
-    kept = cnt < KC ? cnt : KC;
-    if (kept == KC) {
+    kept = s_count;
+    sorted = false;
+    __syncthreads();  // everyone has read the count before the next round appends
+    if (kept > kSelBuf - kSelThreads) {  // the next round might not fit: compact
+      int n2 = 64;
+      while (n2 < kept) n2 <<= 1;
+      for (int j = kept + tid; j < n2; j += kSelThreads) keys[j] = 0;
+      block_sort_desc<kSelThreads>(keys, n2);
+      kept = KC;  // kept > KC here because kSelBuf - kSelThreads >= KC
       const uint32_t k32 = (uint32_t)(keys[KC - 1] >> 32);
       tkey = k32 > tkey ? k32 : tkey;
+      sorted = true;
+      if (tid == 0) s_count = KC;
+      __syncthreads();
     }
-    __syncthreads();
+  }
+  if (!sorted) {
+    int n2 = 64;
+    while (n2 < kept) n2 <<= 1;
+    for (int j = kept + tid; j < n2; j += kSelThreads) keys[j] = 0;  // below every real key
+    block_sort_desc<kSelThreads>(keys, n2);
   }
   const int count = kept;
-  const bool overflow = false;
   const int nsel = count < KC ? count : KC;
   if (tid < KC) {
     if (tid < nsel) { ap[tid] = key_score(keys[tid]) * inv_scale; ci[tid] = key_index(keys[tid]); }
     else { ap[tid] = -INFINITY; ci[tid] = 0xFFFFFFFFu; ex[tid] = -INFINITY; }
   }
   __syncthreads();
-  // 3. exact scores from the float32 rows
+  // 3. exact scores from the float32 rows.  Round A: the keep_n (+ a few) best by tensor-core
+  // score.  Their errors give this row's sigma, their keep_n-th best exact score E gives a
+  // bound: a remaining candidate whose tensor-core score is below E - eps cannot enter the
+  // top keep_n, so round B only reads the dictionary rows that still can.
   const float4* a = reinterpret_cast<const float4*>(exp32 + row * s_pitch);
   const int n4 = (int)(s_pitch >> 2);
-  for (int i = warp; i < nsel; i += kSelThreads / 32) {
+  int n_a = (keep_n + 4 + 3) & ~3;
+  if (n_a > nsel) n_a = nsel;
+  for (int i = warp; i < n_a; i += kSelThreads / 32) {
     const float4* b = reinterpret_cast<const float4*>(dict32 + (int64_t)ci[i] * s_pitch);
     const float d = warp_dot(a, b, n4, lane);
+    if (lane == 0) ex[i] = d;
+  }
+  __syncthreads();
+  float err2 = 0.f;
+  if (tid < n_a) {
+    const float d = ap[tid] - ex[tid];
+    err2 = d * d;
+    int r = 0;
+    const float ms = ex[tid];
+    for (int j = 0; j < n_a; ++j) r += (ex[j] > ms || (ex[j] == ms && j < tid)) ? 1 : 0;
+    if (r == keep_n - 1) s_ek = ms;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+  if (lane == 0 && warp < 2) s_red[warp] = err2;
+  if (tid == 0 && n_a < keep_n) s_ek = -INFINITY;
+  __syncthreads();
+  const float sigma = sqrtf((s_red[0] + s_red[1]) / (float)(n_a > 0 ? n_a : 1));
+  const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 1e-7f;
+  const float e_k = s_ek;
+  for (int i = n_a + warp; i < nsel; i += kSelThreads / 32) {
+    float d = -INFINITY;  // warp-uniform decision
+    if (ap[i] + eps >= e_k) {
+      const float4* b = reinterpret_cast<const float4*>(dict32 + (int64_t)ci[i] * s_pitch);
+      d = warp_dot(a, b, n4, lane);
+    }
     if (lane == 0) ex[i] = d;
   }
   __syncthreads();
@@ -138,7 +195,6 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   float my_s = 0.f;
   uint32_t my_i = 0;
   int rank = KC;
-  float err2 = 0.f;
   if (tid < nsel) {
     my_s = ex[tid];
     my_i = ci[tid];
@@ -147,14 +203,7 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
       const float sj = ex[j];
       rank += (sj > my_s || (sj == my_s && ci[j] < my_i)) ? 1 : 0;
     }
-    const float d = ap[tid] - my_s;
-    err2 = d * d;
   }
-  // rms error of the tensor-core scores over this row's candidates (first two warps hold them)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o);
-  if (lane == 0 && warp < 2) s_red[warp] = err2;
-  __syncthreads();
   if (tid < nsel && rank < keep_n) {
     out_scores[row * keep_n + rank] = my_s;
     out_idx[row * keep_n + rank] = (int64_t)my_i + index_offset;
@@ -162,10 +211,8 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   if (tid < nsel && rank == keep_n - 1) {
     bool ok = true;
     if (n_dict > (int64_t)nsel) {  // some dictionary rows were discarded
-      const float sigma = sqrtf((s_red[0] + (KC > 32 ? s_red[1] : 0.f)) / (float)nsel);
-      const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 1e-7f;
       const float t = ap[nsel - 1];  // smallest retained tensor-core score
-      ok = (nsel == KC) && !overflow && (my_s > t + eps);
+      ok = (nsel == KC) && (my_s > t + eps);
     }
     if (!ok) {
       const int pos = atomicAdd(n_flag, 1);

@@ -26,7 +26,7 @@ def ctx():
     yield c
     for opt in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK):
         c.set_option(opt, 0)
-    c.set_option(_lib.OPT_CTA_GROUP, 1)
+    c.set_option(_lib.OPT_CTA_GROUP, 2)
     c.set_signal_mask(None)
 
 
@@ -108,7 +108,7 @@ def test_config1_nickel(ctx, golden, cta_group):
     _check(ridx, rsc, res.simulation_indices, res.scores, strict=True)
     assert res.shape == (3, 3) and res.size == 9 and res.rotations_per_point == 5
     assert ctx.timings()["gemm_launches"] == 1  # the tensor-core kernel ran
-    ctx.set_option(_lib.OPT_CTA_GROUP, 1)
+    ctx.set_option(_lib.OPT_CTA_GROUP, 2)
 
 
 @pytest.mark.parametrize("cta_group", [1, 2])
@@ -123,7 +123,7 @@ def test_golden_driver_vectors(ctx, golden, cta_group):
     idx, sc = ctx.dictionary_indexing(pexp, 64, dic, 4096, _lib.KDI_NCC, 20)
     assert np.array_equal(idx[:, 0], j)
     _check(g["planted_idx"], orc.dictionary_indexing(pexp, dic, keep_n=20)[1], idx, sc)
-    ctx.set_option(_lib.OPT_CTA_GROUP, 1)
+    ctx.set_option(_lib.OPT_CTA_GROUP, 2)
 
 
 # ---- random workloads: metrics, masks, keep_n, operand types, schedules ----------------------------
@@ -149,7 +149,7 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=[str(c[:5]) + str(c[7]) for c in CASES])
 def test_random_workloads(ctx, case):
     M, N, sig, k, metric, smask, nmask, opt = case
-    ctx.set_option(_lib.OPT_CTA_GROUP, opt.get("cg", 1))
+    ctx.set_option(_lib.OPT_CTA_GROUP, opt.get("cg", 1))  # cases without "cg" exercise the single-CTA kernel
     ctx.set_option(_lib.OPT_COMPUTE_DTYPE, opt.get("bf16", 0))
     ctx.set_option(_lib.OPT_FORCE_EXACT, opt.get("exact", 0))
     ctx.set_option(_lib.OPT_STRIP_TILES, opt.get("strip", 0))
@@ -171,7 +171,7 @@ def test_random_workloads(ctx, case):
     finally:
         for o in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK):
             ctx.set_option(o, 0)
-        ctx.set_option(_lib.OPT_CTA_GROUP, 1)
+        ctx.set_option(_lib.OPT_CTA_GROUP, 2)
         ctx.set_signal_mask(None)
 
 
@@ -349,4 +349,4 @@ def test_config2_full_size_properties(ctx):
         e = exp[rows].double().flatten(1); e = e - e.mean(1, keepdim=True); e = e / e.norm(dim=1, keepdim=True)
         d = dic[j[rows]].double().flatten(1); d = d - d.mean(1, keepdim=True); d = d / d.norm(dim=1, keepdim=True)
         assert float(((e * d).sum(1) - sc[rows, 0].double()).abs().max()) < 1e-5
-    ctx.set_option(_lib.OPT_CTA_GROUP, 1)
+    ctx.set_option(_lib.OPT_CTA_GROUP, 2)

@@ -1,0 +1,56 @@
+"""Dictionary sharded over 2 GPUs (NCCL all-gather of per-shard top-k + device merge) must equal
+the unsharded result.  Skipped with fewer than 2 GPUs."""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+
+    import kikuchipy_b200 as kb
+    from oracle import di_oracle as orc
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        exp = orc.synthetic_experimental(300, (40, 40), seed=1).reshape(15, 20, 40, 40)
+        dic = orc.synthetic_dictionary(7001, (40, 40), seed=2)
+        nav = np.random.default_rng(3).random((15, 20)) < 0.2
+        smask = orc.circular_signal_mask((40, 40))
+        start, end = kb.shard_bounds(7001, world, rank)
+        ctx = kb.default_context(rank)
+        idx, sc = kb.dictionary_indexing_sharded(exp, dic[start:end], 7001, metric="ncc", keep_n=20,
+                                                 navigation_mask=nav, signal_mask=smask, context=ctx)
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), idx=idx.cpu().numpy(), sc=sc.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_shards_equal_unsharded(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    from oracle import di_oracle as orc
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    exp = orc.synthetic_experimental(300, (40, 40), seed=1).reshape(15, 20, 40, 40)
+    dic = orc.synthetic_dictionary(7001, (40, 40), seed=2)
+    nav = np.random.default_rng(3).random((15, 20)) < 0.2
+    smask = orc.circular_signal_mask((40, 40))
+    ridx, rsc = orc.dictionary_indexing(exp, dic, keep_n=20, navigation_mask=nav, signal_mask=smask)
+    z0 = np.load(os.path.join(str(tmp_path), "r0.npz"))
+    z1 = np.load(os.path.join(str(tmp_path), "r1.npz"))
+    assert np.array_equal(z0["idx"], z1["idx"]) and np.array_equal(z0["sc"], z1["sc"])
+    r = orc.compare_topk(ridx, rsc, z0["idx"], z0["sc"], tie_tol=2e-5)
+    assert r["tie_ok"] and r["scores_ok"], r
