@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
@@ -224,13 +224,13 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     def step_device():
-        ctx.dictionary_indexing(exp_dev, m_total, dict_dev, n_shard, _lib.KDI_NCC, KEEP_N,
-                                index_offset=start, out=(idx_dev, sc_dev))
-        tm = ctx.timings()
-        if world > 1:
-            s_all, i_all = kb.gather_topk(sc_dev, idx_dev)
-            ctx.merge_topk(s_all, i_all, KEEP_N)
-        return tm
+        if world == 1:
+            ctx.dictionary_indexing(exp_dev, m_total, dict_dev, n_shard, _lib.KDI_NCC, KEEP_N,
+                                    index_offset=start, out=(idx_dev, sc_dev))
+        else:
+            # candidates per shard -> all-gather + merge -> owner rescoring -> all-reduce -> finalize
+            kb.dictionary_indexing_sharded(exp_dev, dict_dev, N_DICT, metric="ncc", keep_n=KEEP_N, context=ctx)
+        return ctx.timings()
 
     def barrier():
         if world > 1:
@@ -249,7 +249,7 @@ def run_ours(args, rank, world, local_rank):
         gemm_ms, launches, tms = [], 0, []
         for _ in range(args.steps):
             tm = step_device()
-            gemm_ms.append(tm["gemm_topk_ms"]); launches += tm["kernel_launches"] + (1 if world > 1 else 0)
+            gemm_ms.append(tm["gemm_topk_ms"]); launches += tm["kernel_launches"]
             tms.append(tm)
         e1.record(stream)
         barrier()
@@ -344,7 +344,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)

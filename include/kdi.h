@@ -167,6 +167,39 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
                             const uint8_t* nav_mask, int64_t index_offset,
                             float* scores_out, int64_t* indices_out, int out_loc);
 
+/* ---- the same path with the dictionary sharded over GPUs (one process / context per GPU) ------
+ * (no reference equivalent: the reference loops over dictionary chunks serially,
+ * indexing/_dictionary_indexing.py:94-128; this is that reduction spread over ranks)
+ *  1. kdi_shard_candidates   prepare + tensor-core pass over THIS rank's dictionary rows; writes the
+ *                            kc = kdi_candidate_capacity(keep_n) best candidates per experimental
+ *                            row by tensor-core score (approx_out, best first) with GLOBAL indices
+ *                            (row + index_offset; -1 / -inf padding).  Device buffers, rows x kc.
+ *  2. caller: all-gather the (approx, gidx) lists of all ranks, kdi_merge_topk them to rows x kc.
+ *  3. kdi_shard_rescore_owned exact float32 scores of the merged candidates whose dictionary rows
+ *                            this rank holds (-inf for the others).  Device buffers, rows x kc.
+ *  4. caller: all-reduce(MAX) the exact scores over the ranks.
+ *  5. kdi_shard_finalize     rank by exact score, write rows x keep_n results, apply the
+ *                            certificate; flags_out (device, rows ints) / n_flag_out (host) list
+ *                            the rows that need kdi_shard_exact_rows on every rank + a merge.
+ * The kdi_shard handle keeps the prepared pattern sets alive between the steps. */
+typedef struct kdi_shard kdi_shard;
+int kdi_candidate_capacity(int keep_n); /* 32, 64, or 0 when keep_n is too large for this pipeline */
+int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                         int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
+                         int64_t dict_rows, int64_t S, int metric, int keep_n,
+                         const uint8_t* nav_mask, int64_t index_offset, float* approx_out,
+                         int64_t* gidx_out, kdi_shard** out);
+int kdi_shard_rescore_owned(kdi_ctx* ctx, const kdi_shard* shard, const int64_t* gidx,
+                            float* exact_out);
+int kdi_shard_finalize(kdi_ctx* ctx, const kdi_shard* shard, const float* approx,
+                       const int64_t* gidx, const float* exact, int keep_n, int64_t dict_total,
+                       float* scores_out, int64_t* indices_out, int* flags_out, int* n_flag_out);
+/* exact top keep_n of the listed experimental rows (device int list) within this rank's shard;
+ * outputs device, n_rows x keep_n, global indices */
+int kdi_shard_exact_rows(kdi_ctx* ctx, const kdi_shard* shard, const int* rows, int n_rows,
+                         int keep_n, float* scores_out, int64_t* indices_out);
+int kdi_shard_release(kdi_ctx* ctx, kdi_shard* shard);
+
 /* ---- orientation similarity map --------------------------------------------
  * (indexing/_orientation_similarity_map.py:30-152)
  * indices: (ny*nx) x keep_n int64 on the host.  footprint: fy x fx bytes

@@ -91,6 +91,15 @@ SIGNATURES = {
         _i,
         [_vp, _vp, _i, _i, _i64, _vp, _i, _i, _i64, _i64, _i, _i, _i64, _vp, _i64, _vp, _vp, _i],
     ),
+    "kdi_candidate_capacity": (_i, [_i]),
+    "kdi_shard_candidates": (
+        _i,
+        [_vp, _vp, _i, _i, _i64, _vp, _i, _i, _i64, _i64, _i, _i, _vp, _i64, _vp, _vp, C.POINTER(_vp)],
+    ),
+    "kdi_shard_rescore_owned": (_i, [_vp, _vp, _vp, _vp]),
+    "kdi_shard_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, C.POINTER(_i)]),
+    "kdi_shard_exact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "kdi_shard_release": (_i, [_vp, _vp]),
     "kdi_orientation_similarity_map": (
         _i,
         [_vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
@@ -177,6 +186,65 @@ class Patterns:
     def close(self):
         if self._h:
             self._ctx._lib.kdi_patterns_destroy(self._ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+
+class Shard:
+    """This rank's prepared experimental set + dictionary shard between the steps of the
+    sharded pipeline (``kdi_shard_*`` in include/kdi.h)."""
+
+    def __init__(self, ctx: "Context", handle: int, rows: int, kc: int):
+        self._ctx, self._h, self.rows, self.kc = ctx, handle, rows, kc
+
+    def rescore_owned(self, gidx):
+        import torch
+
+        exact = torch.empty((self.rows, self.kc), dtype=torch.float32, device=gidx.device)
+        torch.cuda.current_stream(gidx.device).synchronize()
+        self._ctx._check(self._ctx._lib.kdi_shard_rescore_owned(self._ctx._h, self._h, gidx.data_ptr(), exact.data_ptr()))
+        return exact
+
+    def finalize(self, approx, gidx, exact, keep_n: int, dict_total: int):
+        import torch
+
+        dev = gidx.device
+        scores = torch.empty((self.rows, keep_n), dtype=torch.float32, device=dev)
+        idx = torch.empty((self.rows, keep_n), dtype=torch.int64, device=dev)
+        flags = torch.empty((max(self.rows, 1),), dtype=torch.int32, device=dev)
+        n_flag = C.c_int(0)
+        torch.cuda.current_stream(dev).synchronize()
+        self._ctx._check(
+            self._ctx._lib.kdi_shard_finalize(
+                self._ctx._h, self._h, approx.data_ptr(), gidx.data_ptr(), exact.data_ptr(), int(keep_n),
+                int(dict_total), scores.data_ptr(), idx.data_ptr(), flags.data_ptr(), C.byref(n_flag),
+            )
+        )
+        return idx, scores, flags[: n_flag.value]
+
+    def exact_rows(self, rows, keep_n: int):
+        import torch
+
+        n = int(rows.numel())
+        scores = torch.empty((n, keep_n), dtype=torch.float32, device=rows.device)
+        idx = torch.empty((n, keep_n), dtype=torch.int64, device=rows.device)
+        rows = rows.to(torch.int32).contiguous()
+        torch.cuda.current_stream(rows.device).synchronize()
+        self._ctx._check(
+            self._ctx._lib.kdi_shard_exact_rows(self._ctx._h, self._h, rows.data_ptr(), n, int(keep_n),
+                                                scores.data_ptr(), idx.data_ptr())
+        )
+        return idx, scores
+
+    def close(self):
+        if self._h:
+            self._ctx._lib.kdi_shard_release(self._ctx._h, self._h)
             self._h = None
 
     def __del__(self):
@@ -369,6 +437,46 @@ class Context:
         )
         del ekeep, dkeep
         return idx, scores
+
+    # -- sharded dictionary: candidate pipeline (CUDA torch tensors in and out) -------------------
+    def candidate_capacity(self, keep_n: int) -> int:
+        return int(self._lib.kdi_candidate_capacity(int(keep_n)))
+
+    def shard_candidates(self, experimental, exp_rows, dictionary, dict_rows, metric, keep_n,
+                         nav_mask=None, index_offset=0):
+        """Stage 1 on this rank's dictionary rows.  Returns ``(shard, approx, gidx)``: CUDA tensors
+        ``(rows kept, kc)`` with the best candidates by tensor-core score and global indices."""
+        import torch
+
+        kc = self.candidate_capacity(keep_n)
+        if kc == 0:
+            raise NotImplementedError(f"keep_n {keep_n} too large for the candidate pipeline")
+        eptr, eloc, ecode, ekeep = _buffer(experimental)
+        dptr, dloc, dcode, dkeep = _buffer(dictionary)
+        n_e = int(np.prod(experimental.shape))
+        n_d = int(np.prod(dictionary.shape))
+        if exp_rows < 1 or n_e % exp_rows or dict_rows < 1 or n_d % dict_rows:
+            raise ValueError("pattern arrays cannot be reshaped to (rows, -1)")
+        S = n_e // exp_rows
+        if n_d // dict_rows != S:
+            raise ValueError(f"Experimental ({S}) and dictionary ({n_d // dict_rows}) signal sizes must be identical")
+        rm, kept = None, exp_rows
+        if nav_mask is not None:
+            rm = np.ascontiguousarray(np.asarray(nav_mask).ravel().astype(np.uint8))
+            kept = int((rm == 0).sum())
+        dev = torch.device("cuda", self.device)
+        approx = torch.empty((kept, kc), dtype=torch.float32, device=dev)
+        gidx = torch.empty((kept, kc), dtype=torch.int64, device=dev)
+        h = _vp()
+        self._check(
+            self._lib.kdi_shard_candidates(
+                self._h, eptr, eloc, ecode, exp_rows, dptr, dloc, dcode, dict_rows, S, metric, int(keep_n),
+                rm.ctypes.data if rm is not None else None, int(index_offset), approx.data_ptr(),
+                gidx.data_ptr(), C.byref(h),
+            )
+        )
+        del ekeep, dkeep
+        return Shard(self, h.value, kept, kc), approx, gidx
 
     def orientation_similarity_map(self, indices, ny, nx, n_best, from_n_best, normalize, footprint, center_index):
         idx = np.ascontiguousarray(indices, dtype=np.int64)

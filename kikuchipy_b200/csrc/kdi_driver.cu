@@ -14,7 +14,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // exact path for a set of rows (rows_list on the device, or the range row0..row0+n_rows-1)
 int exact_rows(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict, const int* d_rows_list,
                int64_t row0, int64_t n_rows, int keep_n, int64_t index_offset, float* d_scores_out,
-               int64_t* d_idx_out) {
+               int64_t* d_idx_out, bool compact = false) {
   const int64_t N = dict->rows;
   // score blocks of at most ~512 MB
   int64_t batch = (512ll << 20) / (N * (int64_t)sizeof(float));
@@ -26,8 +26,9 @@ int exact_rows(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict, 
     const int nb = (int)std::min<int64_t>(batch, n_rows - b);
     const int* list = d_rows_list ? d_rows_list + b : nullptr;
     KDI_TRY(kdi_launch_exact_scores(ctx, ctx->stream, exp, dict, list, row0 + b, nb, blk));
-    KDI_TRY(kdi_launch_extract_topk(ctx, ctx->stream, blk, nb, N, list, row0 + b, keep_n,
-                                    index_offset, d_scores_out, d_idx_out));
+    // compact: result row i of the list goes to output row i (not to the experimental row it names)
+    KDI_TRY(kdi_launch_extract_topk(ctx, ctx->stream, blk, nb, N, compact ? nullptr : list,
+                                    compact ? b : row0 + b, keep_n, index_offset, d_scores_out, d_idx_out));
   }
   return KDI_OK;
 }
@@ -41,15 +42,16 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 }  // namespace
 
 int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict, int keep_n,
-                    float* scores_out, int64_t* indices_out, int out_loc, kdi_match_job* job) {
-  if (!exp || !dict || !scores_out || !indices_out)
+                    float* scores_out, int64_t* indices_out, int out_loc, bool candidates_only,
+                    kdi_match_job* job) {
+  if (!exp || !dict || (!candidates_only && (!scores_out || !indices_out)))
     return kdi_fail(ctx, KDI_EINVAL, "kdi_match_topk: NULL argument");
   if (out_loc != KDI_HOST && out_loc != KDI_DEVICE) return kdi_fail(ctx, KDI_EINVAL, "bad output location");
   if (exp->s_eff != dict->s_eff)
     return kdi_fail(ctx, KDI_EINVAL, "experimental and dictionary signal sizes differ (%lld vs %lld)",
                     (long long)exp->s_eff, (long long)dict->s_eff);
   const int64_t M = exp->rows, N = dict->rows;
-  if (keep_n < 1 || keep_n > N)
+  if (keep_n < 1 || (!candidates_only && keep_n > N))
     return kdi_fail(ctx, KDI_EINVAL, "keep_n %d must be in [1, %lld]", keep_n, (long long)N);
   if (N > 0xFFFFFFFELL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "dictionary too large");
   *job = kdi_match_job();
@@ -60,7 +62,7 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
   job->scores_out = scores_out;
   job->indices_out = indices_out;
   if (M == 0) return KDI_OK;
-  job->fused = !ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0;
+  job->fused = candidates_only || (!ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0);
   size_t off_thr = 0, off_flags = 0, off_nflag = 0, total = 0;
   if (job->fused) {
     KDI_TRY(kdi_gemm_make_plan(ctx, M, N, exp->kp, keep_n, &job->plan));
@@ -71,7 +73,7 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
   }
   const size_t off_sc = align_up(total, 256);
   const size_t off_ix = align_up(off_sc + (size_t)M * keep_n * sizeof(float), 256);
-  total = off_ix + (size_t)M * keep_n * sizeof(int64_t);
+  total = candidates_only ? off_sc : off_ix + (size_t)M * keep_n * sizeof(int64_t);
   KDI_TRY(kdi_ws_reserve(ctx, total));
   uint8_t* ws = reinterpret_cast<uint8_t*>(ctx->ws);
   job->d_sc = out_loc == KDI_DEVICE ? scores_out : reinterpret_cast<float*>(ws + off_sc);
@@ -147,7 +149,7 @@ int kdi_match_topk_device(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patte
                           int keep_n, int64_t index_offset, float* scores_out,
                           int64_t* indices_out, int out_loc) {
   kdi_match_job job;
-  KDI_TRY(kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, &job));
+  KDI_TRY(kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, false, &job));
   KDI_TRY(kdi_match_advance(ctx, &job, exp, dict, dict->rows));
   return kdi_match_finish(ctx, &job, exp, dict, index_offset);
 }
@@ -248,22 +250,24 @@ int kdi_merge_topk(kdi_ctx* ctx, int64_t rows, int n_lists, int k_in, const floa
   return KDI_OK;
 }
 
-int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
-                            int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
-                            int64_t dict_rows, int64_t S, int metric, int keep_n,
-                            int64_t n_per_iteration, const uint8_t* nav_mask, int64_t index_offset,
-                            float* scores_out, int64_t* indices_out, int out_loc) {
-  if (!ctx) return KDI_EINVAL;
-  if (!experimental || !dictionary || !scores_out || !indices_out)
-    return kdi_fail(ctx, KDI_EINVAL, "kdi_dictionary_indexing: NULL argument");
+}  // extern "C"
+
+// prepare experimental (once) + dictionary (streamed) and run the tensor-core pass over it.
+// On success *exp_out / *dict_out own the prepared sets and `job` is ready for kdi_match_finish
+// (or, candidates_only, for the selection kernel).
+static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                             int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
+                             int64_t dict_rows, int64_t S, int metric, int keep_n,
+                             const uint8_t* nav_mask, float* scores_out, int64_t* indices_out,
+                             int out_loc, bool candidates_only, kdi_match_job* job,
+                             kdi_patterns** exp_out, kdi_patterns** dict_out) {
   const size_t dsz = kdi_dtype_size(dict_dtype);
   if (!dsz || !kdi_dtype_size(exp_dtype)) return kdi_fail(ctx, KDI_EINVAL, "unknown dtype");
   if (dict_rows < 1 || exp_rows < 0 || S < 1) return kdi_fail(ctx, KDI_EINVAL, "bad shape");
-  if (keep_n < 1 || keep_n > dict_rows)
+  // (a shard may hold fewer rows than keep_n: it then nominates all of them)
+  if (keep_n < 1 || (!candidates_only && keep_n > dict_rows))
     return kdi_fail(ctx, KDI_EINVAL, "keep_n %d must be in [1, %lld]", keep_n, (long long)dict_rows);
   if (dict_loc != KDI_HOST && dict_loc != KDI_DEVICE) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location");
-  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
-  ctx->tm = kdi_timings();
   cudaStream_t st = ctx->stream;
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
 
@@ -277,16 +281,15 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
   // depend on the chunking, so the pieces moved here are sized for the copy engine (64 MB) and the
   // tensor-core pass runs over every group of pieces as soon as it has been normalised, while
   // the next pieces are still in flight on the copy stream.
-  (void)n_per_iteration;
   kdi_patterns* dict = nullptr;
-  kdi_match_job job;
   int rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict);
-  if (rc == KDI_OK) rc = kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, &job);
+  if (rc == KDI_OK)
+    rc = kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, candidates_only, job);
   if (rc == KDI_OK) {
     if (dict_loc == KDI_DEVICE) {
       rc = kdi_patterns_fill(ctx, st, dict, 0, dictionary, dict_dtype, dict_rows, nullptr);
       if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
-      if (rc == KDI_OK) rc = kdi_match_advance(ctx, &job, exp, dict, dict_rows);
+      if (rc == KDI_OK) rc = kdi_match_advance(ctx, job, exp, dict, dict_rows);
     } else {
       const size_t row_bytes = (size_t)S * dsz;
       int64_t piece = (int64_t)std::max<size_t>(1, (64u << 20) / row_bytes);
@@ -322,13 +325,53 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
         if (rc == KDI_OK && (ready >= next_advance || ready == dict_rows)) {
           if (ready == dict_rows && cudaEventRecord(ctx->ev[7], st) != cudaSuccess)
             rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
-          if (rc == KDI_OK) rc = kdi_match_advance(ctx, &job, exp, dict, ready);
+          if (rc == KDI_OK) rc = kdi_match_advance(ctx, job, exp, dict, ready);
           next_advance = ready + group_rows;
         }
       }
     }
   }
-  if (rc == KDI_OK) rc = kdi_match_finish(ctx, &job, exp, dict, index_offset);
+  if (rc != KDI_OK) {
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(ctx->copy_stream);
+    const std::string err = ctx->err;
+    kdi_patterns_destroy(ctx, exp);
+    kdi_patterns_destroy(ctx, dict);
+    ctx->err = err;
+    return rc;
+  }
+  *exp_out = exp;
+  *dict_out = dict;
+  return KDI_OK;
+}
+
+struct kdi_shard {
+  kdi_patterns* exp = nullptr;
+  kdi_patterns* dict = nullptr;
+  int kc = 0;
+  int64_t index_offset = 0;
+};
+
+extern "C" {
+
+int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                            int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
+                            int64_t dict_rows, int64_t S, int metric, int keep_n,
+                            int64_t n_per_iteration, const uint8_t* nav_mask, int64_t index_offset,
+                            float* scores_out, int64_t* indices_out, int out_loc) {
+  if (!ctx) return KDI_EINVAL;
+  if (!experimental || !dictionary || !scores_out || !indices_out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_dictionary_indexing: NULL argument");
+  (void)n_per_iteration;  // accepted for interface parity; transfers are sized internally
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  kdi_patterns *exp = nullptr, *dict = nullptr;
+  kdi_match_job job;
+  KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dictionary, dict_loc,
+                            dict_dtype, dict_rows, S, metric, keep_n, nav_mask, scores_out, indices_out,
+                            out_loc, false, &job, &exp, &dict));
+  cudaStream_t st = ctx->stream;
+  int rc = kdi_match_finish(ctx, &job, exp, dict, index_offset);
   if (rc == KDI_OK) {
     cudaEventRecord(ctx->ev[1], st);
     if (cudaStreamSynchronize(st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
@@ -346,6 +389,109 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
   kdi_patterns_destroy(ctx, dict);
   if (rc != KDI_OK) ctx->err = err;
   return rc;
+}
+
+int kdi_candidate_capacity(int keep_n) { return kdi_gemm_kc_for(keep_n); }
+
+int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                         int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
+                         int64_t dict_rows, int64_t S, int metric, int keep_n,
+                         const uint8_t* nav_mask, int64_t index_offset, float* approx_out,
+                         int64_t* gidx_out, kdi_shard** out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!experimental || !dictionary || !approx_out || !gidx_out || !out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_candidates: NULL argument");
+  const int kc = kdi_gemm_kc_for(keep_n);
+  if (kc == 0) return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d too large for the candidate pipeline", keep_n);
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  kdi_patterns *exp = nullptr, *dict = nullptr;
+  kdi_match_job job;
+  KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dictionary, dict_loc,
+                            dict_dtype, dict_rows, S, metric, keep_n, nav_mask, nullptr, nullptr,
+                            KDI_DEVICE, true, &job, &exp, &dict));
+  cudaStream_t st = ctx->stream;
+  int rc = KDI_OK;
+  if (job.plan.kc != kc) rc = kdi_fail(ctx, KDI_EINTERNAL, "candidate capacity mismatch");
+  cudaEventRecord(ctx->ev[3], st);
+  if (rc == KDI_OK)
+    rc = kdi_launch_select_only(ctx, st, exp->rows, &job.plan, job.cand, job.thr, index_offset,
+                                1.0f / (KDI_OP_SCALE * KDI_OP_SCALE), approx_out, gidx_out);
+  cudaEventRecord(ctx->ev[4], st);
+  cudaEventRecord(ctx->ev[1], st);
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == KDI_OK) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
+  if (rc != KDI_OK) {
+    const std::string err = ctx->err;
+    kdi_patterns_destroy(ctx, exp);
+    kdi_patterns_destroy(ctx, dict);
+    ctx->err = err;
+    return rc;
+  }
+  ctx->tm.normalize_exp_ms = ev_ms(ctx->ev[0], ctx->ev[6]);
+  ctx->tm.normalize_dict_ms = ev_ms(ctx->ev[6], ctx->ev[7]);
+  ctx->tm.gemm_topk_ms = ev_ms(ctx->ev[8], ctx->ev[9]);
+  ctx->tm.rescore_ms = ev_ms(ctx->ev[3], ctx->ev[4]);
+  ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+  kdi_shard* sh = new kdi_shard();
+  sh->exp = exp;
+  sh->dict = dict;
+  sh->kc = kc;
+  sh->index_offset = index_offset;
+  *out = sh;
+  return KDI_OK;
+}
+
+int kdi_shard_rescore_owned(kdi_ctx* ctx, const kdi_shard* shard, const int64_t* gidx, float* exact_out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!shard || !gidx || !exact_out) return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_rescore_owned: NULL argument");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  KDI_TRY(kdi_launch_rescore_owned(ctx, ctx->stream, shard->exp, shard->dict, shard->index_offset,
+                                   shard->kc, gidx, exact_out));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+  KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->tm.rescore_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
+  return KDI_OK;
+}
+
+int kdi_shard_finalize(kdi_ctx* ctx, const kdi_shard* shard, const float* approx, const int64_t* gidx,
+                       const float* exact, int keep_n, int64_t dict_total, float* scores_out,
+                       int64_t* indices_out, int* flags_out, int* n_flag_out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!shard || !approx || !gidx || !exact || !scores_out || !indices_out || !flags_out || !n_flag_out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_finalize: NULL argument");
+  if (keep_n < 1 || keep_n > dict_total) return kdi_fail(ctx, KDI_EINVAL, "keep_n %d must be in [1, %lld]", keep_n, (long long)dict_total);
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  KDI_TRY(kdi_ws2_reserve(ctx, 256));
+  int* d_n = reinterpret_cast<int*>(ctx->ws2);
+  cudaStream_t st = ctx->stream;
+  KDI_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int), st));
+  KDI_TRY(kdi_launch_finalize(ctx, st, shard->exp->rows, shard->kc, approx, exact, gidx, keep_n, dict_total,
+                              (float)ctx->cert_sigmas, scores_out, indices_out, flags_out, d_n));
+  KDI_CUDA(ctx, cudaMemcpyAsync(n_flag_out, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  KDI_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->tm.flagged_rows += *n_flag_out;
+  return KDI_OK;
+}
+
+int kdi_shard_exact_rows(kdi_ctx* ctx, const kdi_shard* shard, const int* rows, int n_rows, int keep_n,
+                         float* scores_out, int64_t* indices_out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!shard || !rows || !scores_out || !indices_out) return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_exact_rows: NULL argument");
+  if (keep_n < 1 || keep_n > shard->dict->rows) return kdi_fail(ctx, KDI_EINVAL, "keep_n %d exceeds the shard size", keep_n);
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  KDI_TRY(exact_rows(ctx, shard->exp, shard->dict, rows, 0, n_rows, keep_n, shard->index_offset,
+                     scores_out, indices_out, true));
+  KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KDI_OK;
+}
+
+int kdi_shard_release(kdi_ctx* ctx, kdi_shard* shard) {
+  if (!shard) return KDI_OK;
+  kdi_patterns_destroy(ctx, shard->exp);
+  kdi_patterns_destroy(ctx, shard->dict);
+  delete shard;
+  return KDI_OK;
 }
 
 int kdi_orientation_similarity_map(kdi_ctx* ctx, const int64_t* indices, int64_t ny, int64_t nx,

@@ -85,6 +85,52 @@ __device__ __forceinline__ uint64_t pack_key(float score, uint32_t idx) {
 __device__ __forceinline__ float key_score(uint64_t k) { return key_float((uint32_t)(k >> 32)); }
 __device__ __forceinline__ uint32_t key_index(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
 
+// Stream one row's candidate lists through a small shared-memory buffer: entries at or above
+// the running threshold are appended; whenever the buffer could overflow it is sorted, the kc best
+// are kept and the threshold is raised to the kc-th best (so later entries are filtered harder and
+// the expected number of survivors stays ~kc*ln(total/buffer)).  On return keys[0..n) holds the
+// n <= KC best candidates, best first.
+template <int KC>
+__device__ __forceinline__ int select_candidates(const uint2* __restrict__ c, int64_t total,
+                                                 uint32_t tkey, uint64_t* keys, int* s_count) {
+  const int tid = threadIdx.x;
+  int kept = 0;  // entries currently in the buffer
+  bool sorted = true;
+  if (tid == 0) *s_count = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < total; base += kSelThreads) {
+    const int64_t i = base + tid;
+    if (i < total) {
+      const uint2 e = c[i];
+      if (e.y != 0xFFFFFFFFu && float_key(__uint_as_float(e.x)) >= tkey)
+        keys[atomicAdd(s_count, 1)] = pack_key(__uint_as_float(e.x), e.y);
+    }
+    __syncthreads();
+    kept = *s_count;
+    sorted = false;
+    __syncthreads();  // everyone has read the count before the next round appends
+    if (kept > kSelBuf - kSelThreads) {  // the next round might not fit: compact
+      int n2 = 64;
+      while (n2 < kept) n2 <<= 1;
+      for (int j = kept + tid; j < n2; j += kSelThreads) keys[j] = 0;
+      block_sort_desc<kSelThreads>(keys, n2);
+      kept = KC;  // kept > KC here because kSelBuf - kSelThreads >= KC
+      const uint32_t k32 = (uint32_t)(keys[KC - 1] >> 32);
+      tkey = k32 > tkey ? k32 : tkey;
+      sorted = true;
+      if (tid == 0) *s_count = KC;
+      __syncthreads();
+    }
+  }
+  if (!sorted) {
+    int n2 = 64;
+    while (n2 < kept) n2 <<= 1;
+    for (int j = kept + tid; j < n2; j += kSelThreads) keys[j] = 0;  // below every real key
+    block_sort_desc<kSelThreads>(keys, n2);
+  }
+  return kept < KC ? kept : KC;
+}
+
 template <int KC>
 __global__ void __launch_bounds__(kSelThreads)
 kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
@@ -103,49 +149,9 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
 
   const int64_t row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // 1+2. stream the row's candidate lists through a small shared-memory buffer: entries at or
-  // above the running threshold are appended; whenever the buffer could overflow it is sorted,
-  // the kc best are kept and the threshold is raised to the kc-th best (so later entries are
-  // filtered harder and the expected number of survivors stays ~kc*ln(total/buffer))
-  uint32_t tkey = thr[row];
+  // 1+2. the kc best candidates by tensor-core score
   const int64_t total = (int64_t)n_strips * KC;
-  const uint2* c = cand + row * total;
-  int kept = 0;      // entries currently in the buffer
-  bool sorted = true;
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-  for (int64_t base = 0; base < total; base += kSelThreads) {
-    const int64_t i = base + tid;
-    if (i < total) {
-      const uint2 e = c[i];
-      if (e.y != 0xFFFFFFFFu && float_key(__uint_as_float(e.x)) >= tkey)
-        keys[atomicAdd(&s_count, 1)] = pack_key(__uint_as_float(e.x), e.y);
-    }
-    __syncthreads();
-    kept = s_count;
-    sorted = false;
-    __syncthreads();  // everyone has read the count before the next round appends
-    if (kept > kSelBuf - kSelThreads) {  // the next round might not fit: compact
-      int n2 = 64;
-      while (n2 < kept) n2 <<= 1;
-      for (int j = kept + tid; j < n2; j += kSelThreads) keys[j] = 0;
-      block_sort_desc<kSelThreads>(keys, n2);
-      kept = KC;  // kept > KC here because kSelBuf - kSelThreads >= KC
-      const uint32_t k32 = (uint32_t)(keys[KC - 1] >> 32);
-      tkey = k32 > tkey ? k32 : tkey;
-      sorted = true;
-      if (tid == 0) s_count = KC;
-      __syncthreads();
-    }
-  }
-  if (!sorted) {
-    int n2 = 64;
-    while (n2 < kept) n2 <<= 1;
-    for (int j = kept + tid; j < n2; j += kSelThreads) keys[j] = 0;  // below every real key
-    block_sort_desc<kSelThreads>(keys, n2);
-  }
-  const int count = kept;
-  const int nsel = count < KC ? count : KC;
+  const int nsel = select_candidates<KC>(cand + row * total, total, thr[row], keys, &s_count);
   if (tid < KC) {
     if (tid < nsel) { ap[tid] = key_score(keys[tid]) * inv_scale; ci[tid] = key_index(keys[tid]); }
     else { ap[tid] = -INFINITY; ci[tid] = 0xFFFFFFFFu; ex[tid] = -INFINITY; }
@@ -223,6 +229,102 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
     const int pos = atomicAdd(n_flag, 1);
     flag_list[pos] = (int)row;
   }
+}
+
+// ---- split pipeline for a sharded dictionary (one process per GPU) -----------------------------
+// select only: the kc best candidates of this shard by tensor-core score, global indices
+template <int KC>
+__global__ void __launch_bounds__(kSelThreads)
+kdi_select_only_kernel(const uint2* __restrict__ cand, const uint32_t* __restrict__ thr, int n_strips,
+                       int64_t index_offset, float inv_scale, float* __restrict__ out_approx,
+                       int64_t* __restrict__ out_gidx) {
+  __shared__ uint64_t keys[kSelBuf];
+  __shared__ int s_count;
+  const int64_t row = blockIdx.x;
+  const int64_t total = (int64_t)n_strips * KC;
+  const int nsel = select_candidates<KC>(cand + row * total, total, thr[row], keys, &s_count);
+  const int tid = threadIdx.x;
+  if (tid < KC) {
+    out_approx[row * KC + tid] = tid < nsel ? key_score(keys[tid]) * inv_scale : -INFINITY;
+    out_gidx[row * KC + tid] = tid < nsel ? (int64_t)key_index(keys[tid]) + index_offset : -1;
+  }
+}
+
+// exact scores of the candidates whose dictionary rows live in this shard; -inf elsewhere
+__global__ void __launch_bounds__(kSelThreads)
+kdi_rescore_owned_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
+                         int64_t s_pitch, int64_t shard_start, int64_t shard_rows, int kc,
+                         const int64_t* __restrict__ gidx, float* __restrict__ exact) {
+  const int64_t row = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4* a = reinterpret_cast<const float4*>(exp32 + row * s_pitch);
+  const int n4 = (int)(s_pitch >> 2);
+  for (int i = warp; i < kc; i += kSelThreads / 32) {
+    const int64_t g = gidx[row * kc + i] - shard_start;  // warp-uniform
+    float d = -INFINITY;
+    if (g >= 0 && g < shard_rows)
+      d = warp_dot(a, reinterpret_cast<const float4*>(dict32 + g * s_pitch), n4, lane);
+    if (lane == 0) exact[row * kc + i] = d;
+  }
+}
+
+// rank by exact score, certificate (same rule as the fused kernel), one 64-thread block per row
+__global__ void __launch_bounds__(64)
+kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __restrict__ exact,
+                    const int64_t* __restrict__ gidx, int keep_n, int64_t n_dict_total,
+                    float cert_sigmas, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+                    int* __restrict__ flag_list, int* __restrict__ n_flag) {
+  __shared__ float ex[64];
+  __shared__ float ap[64];
+  __shared__ int64_t gi[64];
+  __shared__ float s_red[2];
+  __shared__ int s_nsel;
+  const int64_t row = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_nsel = 0;
+  __syncthreads();
+  bool valid = false;
+  if (tid < kc) {
+    gi[tid] = gidx[row * kc + tid];
+    ap[tid] = approx[row * kc + tid];
+    ex[tid] = exact[row * kc + tid];
+    valid = gi[tid] >= 0;
+    if (valid) atomicAdd(&s_nsel, 1);
+  } else {
+    gi[tid] = -1; ap[tid] = -INFINITY; ex[tid] = -INFINITY;
+  }
+  __syncthreads();
+  const int nsel = s_nsel;  // valid entries come first (lists are sorted by approx, padding last)
+  float err2 = 0.f, my_s = 0.f;
+  int rank = 64;
+  if (valid) {
+    my_s = ex[tid];
+    const float d = ap[tid] - my_s;
+    err2 = d * d;
+    rank = 0;
+    for (int j = 0; j < nsel; ++j) {
+      const float sj = ex[j];
+      rank += (sj > my_s || (sj == my_s && gi[j] < gi[tid])) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = err2;
+  __syncthreads();
+  if (valid && rank < keep_n) {
+    out_scores[row * keep_n + rank] = my_s;
+    out_idx[row * keep_n + rank] = gi[tid];
+  }
+  if (valid && rank == keep_n - 1) {
+    bool ok = true;
+    if (n_dict_total > (int64_t)nsel) {
+      const float sigma = sqrtf((s_red[0] + s_red[1]) / (float)nsel);
+      const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 1e-7f;
+      ok = (nsel == kc) && (my_s > ap[nsel - 1] + eps);
+    }
+    if (!ok) flag_list[atomicAdd(n_flag, 1)] = (int)row;
+  }
+  if (tid == 0 && nsel < keep_n) flag_list[atomicAdd(n_flag, 1)] = (int)row;
 }
 
 // ---- exact path -----------------------------------------------------------------------------
@@ -404,6 +506,47 @@ int kdi_launch_extract_topk(kdi_ctx* ctx, cudaStream_t stream, const float* scor
     return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d exceeds the exact path's limit %d", keep_n, kTopMax);
   kdi_extract_topk_kernel<<<(unsigned)n_rows, kTopThreads, 0, stream>>>(
       scores, n_cols, rows_list, row0, keep_n, index_offset, out_scores, out_idx);
+  KDI_CUDA(ctx, cudaGetLastError());
+  ctx->tm.kernel_launches++;
+  return KDI_OK;
+}
+
+int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, const kdi_gemm_plan* plan,
+                           const uint2* cand, const uint32_t* thr, int64_t index_offset,
+                           float approx_inv_scale, float* out_approx, int64_t* out_gidx) {
+  if (rows <= 0) return KDI_OK;
+  if (plan->kc == 32)
+    kdi_select_only_kernel<32><<<(unsigned)rows, kSelThreads, 0, stream>>>(
+        cand, thr, plan->n_strips, index_offset, approx_inv_scale, out_approx, out_gidx);
+  else if (plan->kc == 64)
+    kdi_select_only_kernel<64><<<(unsigned)rows, kSelThreads, 0, stream>>>(
+        cand, thr, plan->n_strips, index_offset, approx_inv_scale, out_approx, out_gidx);
+  else
+    return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
+  KDI_CUDA(ctx, cudaGetLastError());
+  ctx->tm.kernel_launches++;
+  return KDI_OK;
+}
+
+int kdi_launch_rescore_owned(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
+                             const kdi_patterns* dict, int64_t shard_start, int kc,
+                             const int64_t* gidx, float* exact) {
+  if (exp->rows <= 0) return KDI_OK;
+  kdi_rescore_owned_kernel<<<(unsigned)exp->rows, kSelThreads, 0, stream>>>(
+      exp->a32, dict->a32, exp->s_pitch, shard_start, dict->rows, kc, gidx, exact);
+  KDI_CUDA(ctx, cudaGetLastError());
+  ctx->tm.kernel_launches++;
+  return KDI_OK;
+}
+
+int kdi_launch_finalize(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, int kc, const float* approx,
+                        const float* exact, const int64_t* gidx, int keep_n, int64_t n_dict_total,
+                        float cert_sigmas, float* out_scores, int64_t* out_idx, int* flag_list,
+                        int* n_flag) {
+  if (rows <= 0) return KDI_OK;
+  if (kc < 1 || kc > 64 || keep_n > kc) return kdi_fail(ctx, KDI_EINVAL, "finalize: need keep_n <= kc <= 64");
+  kdi_finalize_kernel<<<(unsigned)rows, 64, 0, stream>>>(kc, approx, exact, gidx, keep_n, n_dict_total,
+                                                         cert_sigmas, out_scores, out_idx, flag_list, n_flag);
   KDI_CUDA(ctx, cudaGetLastError());
   ctx->tm.kernel_launches++;
   return KDI_OK;

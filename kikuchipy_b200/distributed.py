@@ -75,16 +75,61 @@ def dictionary_indexing_sharded(
     nav_shape = tuple(experimental.shape[:-2])
     n_exp_all = int(np.prod(nav_shape)) if nav_shape else 1
     kept = n_exp_all if navigation_mask is None else int((~navigation_mask).sum())
-    k_local = min(int(keep_n), n_shard)
+    keep_n = min(int(keep_n), int(dictionary_size))
     dev = torch.device("cuda", ctx.device)
+    if world == 1:
+        scores = torch.empty((kept, keep_n), dtype=torch.float32, device=dev)
+        idx = torch.empty((kept, keep_n), dtype=torch.int64, device=dev)
+        ctx.dictionary_indexing(experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
+                                nav_mask=navigation_mask, index_offset=start, out=(idx, scores))
+        return idx, scores
+    if ctx.candidate_capacity(keep_n) == 0:
+        return _sharded_exact_lists(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
+                                    navigation_mask, start, kept, dictionary_size, group)
+
+    # 1. this shard's candidates by tensor-core score (global indices)
+    shard, approx, gidx = ctx.shard_candidates(experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
+                                               nav_mask=navigation_mask, index_offset=start)
+    try:
+        # 2. the one exchange of the path: all-gather of per-shard top-kc lists, merged per row
+        s_all, i_all = gather_topk(approx, gidx, group)
+        g_idx, g_approx = ctx.merge_topk(s_all, i_all, shard.kc)
+        # 3. every rank rescores exactly the candidates whose dictionary rows it holds ...
+        exact = shard.rescore_owned(g_idx)
+        # 4. ... and the exact scores are combined (each candidate has exactly one owner)
+        dist.all_reduce(exact, op=dist.ReduceOp.MAX, group=group)
+        # 5. rank by exact score + certificate (identical on every rank)
+        idx, scores, flags = shard.finalize(g_approx, g_idx, exact, keep_n, dictionary_size)
+        if flags.numel():
+            # rows whose certificate failed: exact top-k per shard, gathered and merged
+            k_local = min(keep_n, n_shard)
+            fi, fs = shard.exact_rows(flags, k_local)
+            if k_local != keep_n:
+                fs = torch.nn.functional.pad(fs, (0, keep_n - k_local), value=-float("inf"))
+                fi = torch.nn.functional.pad(fi, (0, keep_n - k_local), value=-1)
+            fs_all, fi_all = gather_topk(fs, fi, group)
+            mi, ms = ctx.merge_topk(fs_all, fi_all, keep_n)
+            rows = flags.long()
+            idx[rows] = mi
+            scores[rows] = ms
+        return idx, scores
+    finally:
+        shard.close()
+
+
+def _sharded_exact_lists(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
+                         navigation_mask, start, kept, dictionary_size, group):
+    """keep_n beyond the candidate pipeline: per-shard final top-k lists, gathered and merged."""
+    import torch
+
+    dev = torch.device("cuda", ctx.device)
+    k_local = min(int(keep_n), n_shard)
     scores = torch.empty((kept, k_local), dtype=torch.float32, device=dev)
     idx = torch.empty((kept, k_local), dtype=torch.int64, device=dev)
     ctx.dictionary_indexing(
         experimental, n_exp_all, dictionary_shard, n_shard, code, k_local,
         nav_mask=navigation_mask, index_offset=start, out=(idx, scores),
     )
-    if world == 1:
-        return idx, scores
     if k_local != keep_n:  # ragged shards: pad so every rank contributes the same shape
         pad_s = torch.full((kept, keep_n), -float("inf"), dtype=torch.float32, device=dev)
         pad_i = torch.full((kept, keep_n), -1, dtype=torch.int64, device=dev)
@@ -92,5 +137,4 @@ def dictionary_indexing_sharded(
         pad_i[:, :k_local] = idx
         scores, idx = pad_s, pad_i
     s_all, i_all = gather_topk(scores, idx, group)
-    k_out = min(int(keep_n), int(dictionary_size))
-    return ctx.merge_topk(s_all, i_all, k_out)
+    return ctx.merge_topk(s_all, i_all, min(int(keep_n), int(dictionary_size)))

@@ -29,7 +29,16 @@ def _worker(rank, world, port, tmp):
         ctx = kb.default_context(rank)
         idx, sc = kb.dictionary_indexing_sharded(exp, dic[start:end], 7001, metric="ncc", keep_n=20,
                                                  navigation_mask=nav, signal_mask=smask, context=ctx)
-        np.savez(os.path.join(tmp, f"r{rank}.npz"), idx=idx.cpu().numpy(), sc=sc.cpu().numpy())
+        # exact ties across the candidate boundary and across shards: certificate -> exact rows -> merge
+        dic2 = dic.copy()
+        dic2[100:180] = dic2[7]
+        dic2[5000:5040] = dic2[7]
+        exp2 = np.clip(np.rint(dic2[[7, 9, 6000]] * 255), 0, 255).astype(np.uint8)
+        idx2, sc2 = kb.dictionary_indexing_sharded(exp2, dic2[start:end], 7001, metric="ncc", keep_n=20, context=ctx)
+        # keep_n beyond the candidate pipeline
+        idx3, sc3 = kb.dictionary_indexing_sharded(exp[:2], dic[start:end], 7001, metric="ndp", keep_n=60, context=ctx)
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), idx=idx.cpu().numpy(), sc=sc.cpu().numpy(),
+                 idx2=idx2.cpu().numpy(), sc2=sc2.cpu().numpy(), idx3=idx3.cpu().numpy(), sc3=sc3.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
@@ -53,4 +62,10 @@ def test_two_gpu_shards_equal_unsharded(tmp_path):
     z1 = np.load(os.path.join(str(tmp_path), "r1.npz"))
     assert np.array_equal(z0["idx"], z1["idx"]) and np.array_equal(z0["sc"], z1["sc"])
     r = orc.compare_topk(ridx, rsc, z0["idx"], z0["sc"], tie_tol=2e-5)
+    assert r["tie_ok"] and r["scores_ok"], r
+    assert list(z0["idx2"][0]) == [7] + list(range(100, 119))
+    assert np.all(z0["sc2"][0] == z0["sc2"][0, 0]) and z0["idx2"][1, 0] == 9 and z0["idx2"][2, 0] == 6000
+    assert np.array_equal(z0["idx2"], z1["idx2"])
+    ridx3, rsc3 = orc.dictionary_indexing(exp[:2], dic, metric="ndp", keep_n=60, n_experimental_patterns=40)
+    r = orc.compare_topk(ridx3, rsc3, z0["idx3"], z0["sc3"])
     assert r["tie_ok"] and r["scores_ok"], r
