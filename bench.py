@@ -54,15 +54,16 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled in the background; ``window`` keeps the
+    samples taken inside the timed region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.lines = []
+        self.samples = []  # (host time the line was read, fields)
         self.proc = None
 
     def start(self):
@@ -77,18 +78,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.samples.append((time.time(), [x.strip() for x in line.strip().split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def window(self, t0: float, t1: float) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+        for t, f in self.samples:
+            if len(f) < 9 or not (t0 <= t <= t1 + 0.03):
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
@@ -98,7 +100,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
                 "samples": len(sm), "power_w_max": max(power)}
 
@@ -237,14 +239,15 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a few hundred ms before its first sample: start early
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             step_device()
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        t_start = time.time()
         e0.record(stream)
         gemm_ms, launches, tms = [], 0, []
         for _ in range(args.steps):
@@ -253,7 +256,9 @@ def run_ours(args, rank, world, local_rank):
             tms.append(tm)
         e1.record(stream)
         barrier()
-        clocks = sampler.stop() if rank == 0 else None
+        t_end = time.time()
+        clocks = sampler.window(t_start, t_end) if rank == 0 else None
+        sampler.stop()
         dev_ms = e0.elapsed_time(e1)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -344,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -350,3 +350,104 @@ def test_config2_full_size_properties(ctx):
         d = dic[j[rows]].double().flatten(1); d = d - d.mean(1, keepdim=True); d = d / d.norm(dim=1, keepdim=True)
         assert float(((e * d).sum(1) - sc[rows, 0].double()).abs().max()) < 1e-5
     ctx.set_option(_lib.OPT_CTA_GROUP, 2)
+
+
+# ---- the other BASELINE configurations ---------------------------------------------------------------
+
+def test_config3_shape_small(ctx):
+    """configs[2] at oracle size: 120x120 patterns, circular signal mask (11 287 of 14 400 pixels
+    kept -> K padded to 11 328), NormalizedDotProductMetric, keep_n 20."""
+    sig = (120, 120)
+    sm = orc.circular_signal_mask(sig)
+    assert int((~sm).sum()) == 11287
+    exp = orc.synthetic_experimental(64, sig, seed=1)
+    dic = orc.synthetic_dictionary(3000, sig, seed=2)
+    res = kb.dictionary_indexing(exp, dic, metric="ndp", keep_n=20, signal_mask=sm, verbose=False)
+    ridx, rsc = orc.dictionary_indexing(exp, dic, metric="ndp", keep_n=20, signal_mask=sm)
+    _check(ridx, rsc, res.simulation_indices, res.scores, tie_tol=2e-5)
+    pexp, j = orc.planted_experimental(dic, 64, seed=3)
+    res = kb.dictionary_indexing(pexp, dic, metric="ndp", keep_n=20, signal_mask=sm, verbose=False)
+    assert np.array_equal(res.simulation_indices[:, 0], j)
+
+
+def test_config5_shape_small_with_osm(ctx):
+    """configs[4] at oracle size: 80x80 patterns (K = 6 400, no padding), bf16 operands, a 2-D map
+    and its orientation similarity map."""
+    sig = (80, 80)
+    dic = orc.synthetic_dictionary(5000, sig, seed=2)
+    # a smooth map: neighbouring points are noisy copies of nearby dictionary rows
+    rng = np.random.default_rng(9)
+    base = (np.add.outer(np.arange(20), np.arange(20)) * 7) % 5000
+    noise = rng.random((20, 20) + sig, dtype=np.float32)
+    exp = np.clip(np.rint(255 * (0.6 * dic[base] + 0.4 * noise)), 0, 255).astype(np.uint8)
+    ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 1)
+    try:
+        res = kb.dictionary_indexing(exp, dic, metric="ncc", keep_n=20, verbose=False)
+    finally:
+        ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 0)
+    ridx, rsc = orc.dictionary_indexing(exp, dic, metric="ncc", keep_n=20)
+    r = _check(ridx, rsc, res.simulation_indices, res.scores)
+    assert np.array_equal(res.simulation_indices[:, 0], base.ravel())
+    osm = kb.orientation_similarity_map(res)
+    assert osm.shape == (20, 20) and osm.dtype == np.float32
+    assert np.array_equal(osm, orc.orientation_similarity_map(res.simulation_indices, (20, 20)))
+    if r["exact_rows"] == 1.0:
+        assert np.array_equal(osm, orc.orientation_similarity_map(ridx, (20, 20)))
+    osm_n = kb.orientation_similarity_map(res, n_best=10, normalize=True)
+    assert np.array_equal(osm_n, orc.orientation_similarity_map(res.simulation_indices, (20, 20), n_best=10, normalize=True))
+
+
+def _planted_device(M, N, sig, seed):
+    import torch
+
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    dic = torch.rand((N,) + sig, device="cuda", generator=g)
+    j = torch.randint(0, N, (M,), device="cuda", generator=g)
+    exp = torch.empty((M,) + sig, dtype=torch.uint8, device="cuda")
+    for a in range(0, M, 4096):  # bounded temporaries
+        b = min(a + 4096, M)
+        noise = torch.rand((b - a,) + sig, device="cuda", generator=g)
+        exp[a:b] = torch.clamp(torch.round(255.0 * (0.7 * dic[j[a:b]] + 0.3 * noise)), 0, 255).to(torch.uint8)
+    return exp, dic, j
+
+
+def _full_size_properties(ctx, M, N, sig, k, metric, smask):
+    import torch
+
+    exp, dic, j = _planted_device(M, N, sig, seed=11)
+    idx = torch.empty((M, k), dtype=torch.int64, device="cuda")
+    sc = torch.empty((M, k), dtype=torch.float32, device="cuda")
+    ctx.set_signal_mask(smask)
+    try:
+        ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC if metric == "ncc" else _lib.KDI_NDP, k, out=(idx, sc))
+    finally:
+        ctx.set_signal_mask(None)
+    tm = ctx.timings()
+    assert tm["gemm_launches"] == 1
+    assert torch.equal(idx[:, 0], j)
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all())
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
+    srt = torch.sort(idx, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    rows = torch.arange(0, M, 211, device="cuda")
+    keep = torch.ones(sig[0] * sig[1], dtype=torch.bool, device="cuda") if smask is None else \
+        torch.from_numpy(~smask.ravel()).cuda()
+    e = exp[rows].double().flatten(1)[:, keep]
+    d = dic[j[rows]].double().flatten(1)[:, keep]
+    if metric == "ncc":
+        e = e - e.mean(1, keepdim=True); d = d - d.mean(1, keepdim=True)
+    e = e / e.norm(dim=1, keepdim=True); d = d / d.norm(dim=1, keepdim=True)
+    assert float(((e * d).sum(1) - sc[rows, 0].double()).abs().max()) < 1e-5
+    return tm
+
+
+def test_config3_full_size_properties(ctx):
+    """40 000 x 100 000, 120x120, circular mask, NDP (BASELINE configs[2])."""
+    tm = _full_size_properties(ctx, 40_000, 100_000, (120, 120), 20, "ndp", orc.circular_signal_mask((120, 120)))
+    assert tm["flagged_rows"] < 400
+
+
+def test_config4_shard_full_size_properties(ctx):
+    """One rank's share of BASELINE configs[3]: 100 000 patterns vs a 37 500-row shard, keep_n 50."""
+    tm = _full_size_properties(ctx, 100_000, 37_500, (60, 60), 50, "ncc", None)
+    assert tm["flagged_rows"] < 1000
