@@ -11,10 +11,12 @@
 // from NumPy's partition/sort - SURVEY.md section 7, hard part 1).
 //
 // Certificate: let t be the smallest tensor-core score among the kc retained candidates; every
-// dictionary row that was NOT retained has a tensor-core score <= t.  If the keep_n-th best
-// exact score exceeds t + eps (eps = cert_sigmas x the rms tensor-core error measured on this
-// row's own candidates), no discarded row can belong to the true top keep_n.  Rows that fail
-// are re-done by the exact path, so a missed member of the top-k is impossible, not improbable.
+// dictionary row that was NOT retained has a tensor-core score <= t.  The tensor-core error is
+// modelled per experimental row as exact = approx + bias + noise, both measured on the row's own
+// candidates (bias: common-mode term from the rounding of the experimental row, large for the
+// uncentred NDP metric; noise: per dictionary row).  If the keep_n-th best exact score exceeds
+// t + bias + eps (eps = cert_sigmas x std(noise) + 10 % of |bias|), no discarded row can belong
+// to the true top keep_n.  Rows that fail are re-done by the exact path.
 #include "kdi_internal.cuh"
 #include "kdi_ptx.cuh"
 
@@ -144,7 +146,7 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   __shared__ float ap[KC];
   __shared__ uint32_t ci[KC];
   __shared__ int s_count;
-  __shared__ float s_red[2];
+  __shared__ float s_red[4];
   __shared__ float s_ek;
 
   const int64_t row = blockIdx.x;
@@ -171,9 +173,13 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
     if (lane == 0) ex[i] = d;
   }
   __syncthreads();
-  float err2 = 0.f;
+  // error model of the tensor-core scores on this row: exact = approx + bias + noise.  The bias is
+  // common to the row (rounding of the experimental row times the common mean of the dictionary
+  // rows - large for the uncentred NDP metric, ~0 for NCC), the noise is per dictionary row.
+  float err1 = 0.f, err2 = 0.f;
   if (tid < n_a) {
-    const float d = ap[tid] - ex[tid];
+    const float d = ex[tid] - ap[tid];
+    err1 = d;
     err2 = d * d;
     int r = 0;
     const float ms = ex[tid];
@@ -181,16 +187,21 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
     if (r == keep_n - 1) s_ek = ms;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o);
-  if (lane == 0 && warp < 2) s_red[warp] = err2;
+  for (int o = 16; o > 0; o >>= 1) {
+    err1 += __shfl_xor_sync(0xffffffffu, err1, o);
+    err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+  }
+  if (lane == 0 && warp < 2) { s_red[warp] = err1; s_red[2 + warp] = err2; }
   if (tid == 0 && n_a < keep_n) s_ek = -INFINITY;
   __syncthreads();
-  const float sigma = sqrtf((s_red[0] + s_red[1]) / (float)(n_a > 0 ? n_a : 1));
-  const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 1e-7f;
+  const float inv_na = 1.f / (float)(n_a > 0 ? n_a : 1);
+  const float bias = (s_red[0] + s_red[1]) * inv_na;
+  const float sigma = sqrtf(fmaxf((s_red[2] + s_red[3]) * inv_na - bias * bias, 0.f));
+  const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 0.1f * fabsf(bias) + 1e-7f;
   const float e_k = s_ek;
   for (int i = n_a + warp; i < nsel; i += kSelThreads / 32) {
     float d = -INFINITY;  // warp-uniform decision
-    if (ap[i] + eps >= e_k) {
+    if (ap[i] + bias + eps >= e_k) {
       const float4* b = reinterpret_cast<const float4*>(dict32 + (int64_t)ci[i] * s_pitch);
       d = warp_dot(a, b, n4, lane);
     }
@@ -217,7 +228,7 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   if (tid < nsel && rank == keep_n - 1) {
     bool ok = true;
     if (n_dict > (int64_t)nsel) {  // some dictionary rows were discarded
-      const float t = ap[nsel - 1];  // smallest retained tensor-core score
+      const float t = ap[nsel - 1] + bias;  // smallest retained tensor-core score, debiased
       ok = (nsel == KC) && (my_s > t + eps);
     }
     if (!ok) {
@@ -277,7 +288,7 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
   __shared__ float ex[64];
   __shared__ float ap[64];
   __shared__ int64_t gi[64];
-  __shared__ float s_red[2];
+  __shared__ float s_red[4];
   __shared__ int s_nsel;
   const int64_t row = blockIdx.x;
   const int tid = threadIdx.x;
@@ -295,11 +306,12 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
   }
   __syncthreads();
   const int nsel = s_nsel;  // valid entries come first (lists are sorted by approx, padding last)
-  float err2 = 0.f, my_s = 0.f;
+  float err1 = 0.f, err2 = 0.f, my_s = 0.f;
   int rank = 64;
   if (valid) {
     my_s = ex[tid];
-    const float d = ap[tid] - my_s;
+    const float d = my_s - ap[tid];
+    err1 = d;
     err2 = d * d;
     rank = 0;
     for (int j = 0; j < nsel; ++j) {
@@ -308,8 +320,11 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o);
-  if ((tid & 31) == 0) s_red[tid >> 5] = err2;
+  for (int o = 16; o > 0; o >>= 1) {
+    err1 += __shfl_xor_sync(0xffffffffu, err1, o);
+    err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+  }
+  if ((tid & 31) == 0) { s_red[tid >> 5] = err1; s_red[2 + (tid >> 5)] = err2; }
   __syncthreads();
   if (valid && rank < keep_n) {
     out_scores[row * keep_n + rank] = my_s;
@@ -318,9 +333,10 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
   if (valid && rank == keep_n - 1) {
     bool ok = true;
     if (n_dict_total > (int64_t)nsel) {
-      const float sigma = sqrtf((s_red[0] + s_red[1]) / (float)nsel);
-      const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 1e-7f;
-      ok = (nsel == kc) && (my_s > ap[nsel - 1] + eps);
+      const float bias = (s_red[0] + s_red[1]) / (float)nsel;  // exact = approx + bias + noise
+      const float sigma = sqrtf(fmaxf((s_red[2] + s_red[3]) / (float)nsel - bias * bias, 0.f));
+      const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 0.1f * fabsf(bias) + 1e-7f;
+      ok = (nsel == kc) && (my_s > ap[nsel - 1] + bias + eps);
     }
     if (!ok) flag_list[atomicAdd(n_flag, 1)] = (int)row;
   }
