@@ -451,3 +451,43 @@ def test_config4_shard_full_size_properties(ctx):
     """One rank's share of BASELINE configs[3]: 100 000 patterns vs a 37 500-row shard, keep_n 50."""
     tm = _full_size_properties(ctx, 100_000, 37_500, (60, 60), 50, "ncc", None)
     assert tm["flagged_rows"] < 1000
+
+
+def test_reference_chunk_loop_over_plugin_hooks(ctx):
+    """Level-1 integration: the reference's own chunk loop (_dictionary_indexing.py:94-128),
+    written here exactly as the reference has it, driving the GPU metric through the three plugin
+    hooks + argtopk/topk - what an unmodified kikuchipy does with ``metric=<GPU metric>``."""
+    exp = orc.synthetic_experimental(96, (40, 40), seed=1).reshape(8, 12, 40, 40)
+    dic = orc.synthetic_dictionary(2500, (40, 40), seed=2)
+    nav = np.random.default_rng(2).random((8, 12)) < 0.25
+    sm = orc.circular_signal_mask((40, 40))
+    metric = kb.NormalizedCrossCorrelationMetric(96, 2500, navigation_mask=nav, signal_mask=sm)
+    keep_n, n_per_iteration = 20, 700
+    experimental = metric.prepare_experimental(exp)
+    dictionary = dic.reshape((2500, -1))
+    n_experimental = experimental.shape[0]
+    n_iterations = int(np.ceil(2500 / n_per_iteration))
+    negative_sign = -metric.sign
+    simulation_indices = np.zeros((n_experimental, keep_n), dtype=np.int32)
+    scores = np.full((n_experimental, keep_n), negative_sign, dtype=metric.dtype)
+    chunk_starts = np.cumsum([0] + [n_per_iteration] * (n_iterations - 1))
+    chunk_ends = np.cumsum([n_per_iteration] * n_iterations)
+    chunk_ends[-1] = max(chunk_ends[-1], 2500)
+    for start, end in zip(chunk_starts, chunk_ends):
+        simulated = metric.prepare_dictionary(dictionary[start:end])
+        similarities = metric.match(experimental, simulated)
+        k = min(keep_n, end - start)
+        idx_i = similarities.argtopk(k, axis=-1).reshape((-1, k)) + start
+        sc_i = similarities.topk(k, axis=-1).reshape((-1, k))
+        all_scores = np.hstack((scores, sc_i))
+        all_idx = np.hstack((simulation_indices, idx_i))
+        best = np.argsort(negative_sign * all_scores, axis=1)[:, :keep_n]
+        scores = np.take_along_axis(all_scores, best, axis=1)
+        simulation_indices = np.take_along_axis(all_idx, best, axis=1)
+    ridx, rsc = orc.dictionary_indexing(exp, dic, keep_n=keep_n, n_per_iteration=n_per_iteration,
+                                        navigation_mask=nav, signal_mask=sm)
+    _check(ridx, rsc, simulation_indices.astype(np.int64), scores, tie_tol=2e-5)
+    # and the one-call driver gives the same answer
+    res = kb.dictionary_indexing(exp, dic, keep_n=keep_n, n_per_iteration=n_per_iteration, navigation_mask=nav,
+                                 signal_mask=sm, verbose=False)
+    assert np.array_equal(res.scores, scores) and np.array_equal(res.simulation_indices, simulation_indices)
