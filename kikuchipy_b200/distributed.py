@@ -11,7 +11,38 @@ kernel that serves the chunk loop.
 
 from __future__ import annotations
 
+import os
+import time
+
 import numpy as np
+
+
+class _Trace:
+    """Per-phase wall times of the sharded pipeline (KDI_TRACE=1, rank 0)."""
+
+    def __init__(self, on: bool):
+        self.on, self.t, self.marks = on, None, []
+        if on:
+            import torch
+
+            torch.cuda.synchronize()
+            self.t = time.perf_counter()
+
+    def __call__(self, name: str):
+        if self.on:
+            import torch
+
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.marks.append((name, (now - self.t) * 1e3))
+            self.t = now
+
+    def report(self, ctx):
+        if self.on:
+            tm = ctx.timings()
+            inner = {k: round(tm[k], 3) for k in ("normalize_exp_ms", "normalize_dict_ms", "gemm_topk_ms", "rescore_ms")}
+            print("[kdi trace] " + " ".join(f"{n}={v:.3f}ms" for n, v in self.marks) + f" | inside candidates: {inner}",
+                  flush=True)
 
 
 def shard_bounds(n: int, world_size: int, rank: int) -> tuple[int, int]:
@@ -87,19 +118,27 @@ def dictionary_indexing_sharded(
         return _sharded_exact_lists(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
                                     navigation_mask, start, kept, dictionary_size, group)
 
+    trace = _Trace(os.environ.get("KDI_TRACE") == "1" and rank == 0)
     # 1. this shard's candidates by tensor-core score (global indices)
     shard, approx, gidx = ctx.shard_candidates(experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
                                                nav_mask=navigation_mask, index_offset=start)
+    trace("candidates")
     try:
         # 2. the one exchange of the path: all-gather of per-shard top-kc lists, merged per row
         s_all, i_all = gather_topk(approx, gidx, group)
+        trace("all_gather")
         g_idx, g_approx = ctx.merge_topk(s_all, i_all, shard.kc)
+        trace("merge")
         # 3. every rank rescores exactly the candidates whose dictionary rows it holds ...
         exact = shard.rescore_owned(g_idx)
+        trace("rescore_owned")
         # 4. ... and the exact scores are combined (each candidate has exactly one owner)
         dist.all_reduce(exact, op=dist.ReduceOp.MAX, group=group)
+        trace("all_reduce")
         # 5. rank by exact score + certificate (identical on every rank)
         idx, scores, flags = shard.finalize(g_approx, g_idx, exact, keep_n, dictionary_size)
+        trace("finalize")
+        trace.report(ctx)
         if flags.numel():
             # rows whose certificate failed: exact top-k per shard, gathered and merged
             k_local = min(keep_n, n_shard)
