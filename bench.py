@@ -15,6 +15,8 @@ constant: weak scaling in patterns/s.
             CUDA events on the library's stream, max over ranks.
 `e2e`     : the same job through the public API with pinned HOST buffers; H2D of both inputs
             and D2H of the result inside the timed region (wall clock between device syncs).
+            N > 1: each rank uploads its dictionary shard and 1/N of the experimental rows (the
+            raw rows are all-gathered over NVLink); byte counts are whole-job totals.
 `roofline`: the GEMM+top-k kernel; achieved = 2*M*N_shard*S / its CUDA-event duration.
 `cpu_baseline`: the NumPy oracle (the reference's own arithmetic) on the host cores, on a
             bounded sample, extrapolated linearly in the number of patterns.
@@ -272,15 +274,18 @@ def run_ours(args, rank, world, local_rank):
     dict_host = ctx.pinned_empty((n_shard,) + SIG, np.float32)
     exp_host[...] = exp_dev.cpu().numpy()
     dict_host[...] = dict_dev.cpu().numpy()
-    h2d = exp_host.nbytes + dict_host.nbytes
-    d2h = m_total * KEEP_N * 12
+    # whole-job bytes per step: N = 1 uploads everything over one link; N > 1: every rank uploads
+    # its dictionary shard and 1/N of the experimental rows (all-gathered over NVLink), and every
+    # rank reads the full result back
+    h2d = exp_host.nbytes + N_DICT * S * 4
+    d2h = m_total * KEEP_N * 12 * world
 
     def step_e2e():
         if world == 1:
             res = kb.dictionary_indexing(exp_host, dict_host, metric="ncc", keep_n=KEEP_N, verbose=False)
             return res.scores
         i, s = kb.dictionary_indexing_sharded(exp_host, dict_host, N_DICT, metric="ncc", keep_n=KEEP_N, context=ctx)
-        return s.cpu()
+        return i.cpu(), s.cpu()
 
     with torch.cuda.stream(stream):
         for _ in range(max(1, args.warmup // 2)):

@@ -64,6 +64,10 @@ extern "C" {
 #define KDI_OPT_CTA_GROUP 3     /* 1 or 2 (default): tcgen05 cta_group of the GEMM kernel                  */
 #define KDI_OPT_STRIP_TILES 4   /* N tiles per work unit (L2 reuse knob)                                   */
 #define KDI_OPT_SUPERBLOCK 5    /* M tiles per super-block (L2 reuse knob)                                 */
+#define KDI_OPT_L2_POLICY 6     /* L2 cache hints of the GEMM tile loads: 0 = experimental evict_last +
+                                   dictionary normal (default), 1 = both normal, 2 = evict_last +
+                                   evict_first, 3 = normal + evict_first                               */
+#define KDI_OPT_TILE_ROTATE 7   /* 1 = each row block starts its strip at a different tile            */
 
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;
@@ -181,6 +185,11 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
  *  5. kdi_shard_finalize     rank by exact score, write rows x keep_n results, apply the
  *                            certificate; flags_out (device, rows ints) / n_flag_out (host) list
  *                            the rows that need kdi_shard_exact_rows on every rank + a merge.
+ *                            It works on the experimental rows [row0, row0 + rows): the list
+ *                            pointers and outputs address that slice (rows x kc / rows x keep_n),
+ *                            the flags are row numbers of the whole set - so the ranks can split
+ *                            steps 2 and 5 by rows (all-to-all instead of all-gather, reduce-scatter
+ *                            instead of all-reduce) and gather the finished slices.
  * The kdi_shard handle keeps the prepared pattern sets alive between the steps. */
 typedef struct kdi_shard kdi_shard;
 int kdi_candidate_capacity(int keep_n); /* 32, 64, or 0 when keep_n is too large for this pipeline */
@@ -191,9 +200,10 @@ int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, in
                          int64_t* gidx_out, kdi_shard** out);
 int kdi_shard_rescore_owned(kdi_ctx* ctx, const kdi_shard* shard, const int64_t* gidx,
                             float* exact_out);
-int kdi_shard_finalize(kdi_ctx* ctx, const kdi_shard* shard, const float* approx,
-                       const int64_t* gidx, const float* exact, int keep_n, int64_t dict_total,
-                       float* scores_out, int64_t* indices_out, int* flags_out, int* n_flag_out);
+int kdi_shard_finalize(kdi_ctx* ctx, const kdi_shard* shard, int64_t row0, int64_t rows,
+                       const float* approx, const int64_t* gidx, const float* exact, int keep_n,
+                       int64_t dict_total, float* scores_out, int64_t* indices_out, int* flags_out,
+                       int* n_flag_out);
 /* exact top keep_n of the listed experimental rows (device int list) within this rank's shard;
  * outputs device, n_rows x keep_n, global indices */
 int kdi_shard_exact_rows(kdi_ctx* ctx, const kdi_shard* shard, const int* rows, int n_rows,

@@ -33,6 +33,8 @@ OPT_FORCE_EXACT = 2
 OPT_CTA_GROUP = 3
 OPT_STRIP_TILES = 4
 OPT_SUPERBLOCK = 5
+OPT_L2_POLICY = 6
+OPT_TILE_ROTATE = 7
 
 _DTYPES = {
     np.dtype(np.uint8): KDI_U8,
@@ -97,7 +99,7 @@ SIGNATURES = {
         [_vp, _vp, _i, _i, _i64, _vp, _i, _i, _i64, _i64, _i, _i, _vp, _i64, _vp, _vp, C.POINTER(_vp)],
     ),
     "kdi_shard_rescore_owned": (_i, [_vp, _vp, _vp, _vp]),
-    "kdi_shard_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, C.POINTER(_i)]),
+    "kdi_shard_finalize": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, C.POINTER(_i)]),
     "kdi_shard_exact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "kdi_shard_release": (_i, [_vp, _vp]),
     "kdi_orientation_similarity_map": (
@@ -144,7 +146,7 @@ def _raise(code: int, msg: str):
     raise KdiError(f"libkdi error {code}: {msg}")
 
 
-def _buffer(x):
+def _buffer(x, ctx=None):
     """(pointer, location, dtype code, keep-alive object) of a NumPy array or CUDA torch tensor."""
     if hasattr(x, "data_ptr") and hasattr(x, "is_cuda"):  # torch tensor
         if not x.is_contiguous():
@@ -153,9 +155,12 @@ def _buffer(x):
         if code is None:
             raise ValueError(f"unsupported tensor dtype {x.dtype}")
         if x.is_cuda:
-            import torch
+            if ctx is not None:
+                ctx._stream_sync(x.device)
+            else:
+                import torch
 
-            torch.cuda.current_stream(x.device).synchronize()
+                torch.cuda.current_stream(x.device).synchronize()
             return x.data_ptr(), KDI_DEVICE, code, x
         return x.data_ptr(), KDI_HOST, code, x
     a = np.asarray(x)
@@ -204,26 +209,38 @@ class Shard:
         self._ctx, self._h, self.rows, self.kc = ctx, handle, rows, kc
 
     def rescore_owned(self, gidx):
+        """Exact scores of the candidates in ``gidx`` (at least ``rows`` x kc) whose dictionary rows
+        this rank holds; -inf elsewhere (also in rows past ``rows``: padding of the row split)."""
         import torch
 
-        exact = torch.empty((self.rows, self.kc), dtype=torch.float32, device=gidx.device)
-        torch.cuda.current_stream(gidx.device).synchronize()
+        n = max(int(gidx.shape[0]), self.rows)
+        exact = torch.empty((n, self.kc), dtype=torch.float32, device=gidx.device)
+        if n > self.rows:
+            exact[self.rows:].fill_(-float("inf"))
+        self._ctx._stream_sync(gidx.device)
         self._ctx._check(self._ctx._lib.kdi_shard_rescore_owned(self._ctx._h, self._h, gidx.data_ptr(), exact.data_ptr()))
         return exact
 
-    def finalize(self, approx, gidx, exact, keep_n: int, dict_total: int):
+    def finalize(self, approx, gidx, exact, keep_n: int, dict_total: int, row0: int = 0, rows: int | None = None):
+        """Rank + certificate for the experimental rows ``[row0, row0 + rows)``; the three list
+        tensors address that slice.  Returns ``(indices, scores, flagged row numbers)``."""
         import torch
 
         dev = gidx.device
-        scores = torch.empty((self.rows, keep_n), dtype=torch.float32, device=dev)
-        idx = torch.empty((self.rows, keep_n), dtype=torch.int64, device=dev)
-        flags = torch.empty((max(self.rows, 1),), dtype=torch.int32, device=dev)
+        rows = self.rows - row0 if rows is None else int(rows)
+        n_out = max(rows, int(gidx.shape[0]))  # callers may pass a padded slice
+        scores = torch.empty((n_out, keep_n), dtype=torch.float32, device=dev)
+        idx = torch.empty((n_out, keep_n), dtype=torch.int64, device=dev)
+        if n_out > rows:
+            scores[rows:].fill_(-float("inf"))
+            idx[rows:].fill_(-1)
+        flags = torch.empty((max(rows, 1),), dtype=torch.int32, device=dev)
         n_flag = C.c_int(0)
-        torch.cuda.current_stream(dev).synchronize()
+        self._ctx._stream_sync(dev)
         self._ctx._check(
             self._ctx._lib.kdi_shard_finalize(
-                self._ctx._h, self._h, approx.data_ptr(), gidx.data_ptr(), exact.data_ptr(), int(keep_n),
-                int(dict_total), scores.data_ptr(), idx.data_ptr(), flags.data_ptr(), C.byref(n_flag),
+                self._ctx._h, self._h, int(row0), int(rows), approx.data_ptr(), gidx.data_ptr(), exact.data_ptr(),
+                int(keep_n), int(dict_total), scores.data_ptr(), idx.data_ptr(), flags.data_ptr(), C.byref(n_flag),
             )
         )
         return idx, scores, flags[: n_flag.value]
@@ -235,7 +252,7 @@ class Shard:
         scores = torch.empty((n, keep_n), dtype=torch.float32, device=rows.device)
         idx = torch.empty((n, keep_n), dtype=torch.int64, device=rows.device)
         rows = rows.to(torch.int32).contiguous()
-        torch.cuda.current_stream(rows.device).synchronize()
+        self._ctx._stream_sync(rows.device)
         self._ctx._check(
             self._ctx._lib.kdi_shard_exact_rows(self._ctx._h, self._h, rows.data_ptr(), n, int(keep_n),
                                                 scores.data_ptr(), idx.data_ptr())
@@ -284,6 +301,22 @@ class Context:
         except Exception:
             pass
 
+    def _stream_sync(self, device):
+        """Order work queued on torch's current stream before library calls (which run on the
+        context's own stream).  Nothing to do when the current stream IS the context's stream."""
+        import torch
+
+        cur = torch.cuda.current_stream(device)
+        if cur.cuda_stream != self.stream_handle():
+            cur.synchronize()
+
+    def torch_stream(self):
+        """The context's stream as a ``torch.cuda.ExternalStream`` (make it current to avoid
+        host synchronisation between torch ops / NCCL collectives and library calls)."""
+        import torch
+
+        return torch.cuda.ExternalStream(self.stream_handle(), device=torch.device("cuda", self.device))
+
     def set_option(self, option: int, value: float):
         self._check(self._lib.kdi_set_option(self._h, option, float(value)))
 
@@ -323,7 +356,7 @@ class Context:
 
     def patterns(self, data, rows: int, metric: int, row_mask=None) -> Patterns:
         """cast -> reshape (rows, -1) -> row mask -> signal mask -> normalise, on the device."""
-        ptr, loc, code, keep = _buffer(data)
+        ptr, loc, code, keep = _buffer(data, self)
         n = int(np.prod(data.shape))
         if rows < 1 or n % rows:
             raise ValueError(f"cannot reshape array of size {n} into ({rows}, -1)")
@@ -378,7 +411,7 @@ class Context:
             indices = indices.contiguous()
             so = torch.empty((rows, k_out), dtype=torch.float32, device=scores.device)
             io = torch.empty((rows, k_out), dtype=torch.int64, device=scores.device)
-            torch.cuda.current_stream(scores.device).synchronize()
+            self._stream_sync(scores.device)
             self._check(
                 self._lib.kdi_merge_topk(
                     self._h, rows, n_lists, k_in, scores.data_ptr(), indices.data_ptr(), k_out,
@@ -404,8 +437,8 @@ class Context:
         n_per_iteration: int = 0, nav_mask=None, index_offset: int = 0, out=None,
     ):
         """The whole driver on raw buffers (host NumPy / pinned, or CUDA torch tensors)."""
-        eptr, eloc, ecode, ekeep = _buffer(experimental)
-        dptr, dloc, dcode, dkeep = _buffer(dictionary)
+        eptr, eloc, ecode, ekeep = _buffer(experimental, self)
+        dptr, dloc, dcode, dkeep = _buffer(dictionary, self)
         n_e = int(np.prod(experimental.shape))
         n_d = int(np.prod(dictionary.shape))
         if exp_rows < 1 or n_e % exp_rows or dict_rows < 1 or n_d % dict_rows:
@@ -443,16 +476,17 @@ class Context:
         return int(self._lib.kdi_candidate_capacity(int(keep_n)))
 
     def shard_candidates(self, experimental, exp_rows, dictionary, dict_rows, metric, keep_n,
-                         nav_mask=None, index_offset=0):
+                         nav_mask=None, index_offset=0, pad_rows=0):
         """Stage 1 on this rank's dictionary rows.  Returns ``(shard, approx, gidx)``: CUDA tensors
-        ``(rows kept, kc)`` with the best candidates by tensor-core score and global indices."""
+        ``(max(rows kept, pad_rows), kc)`` with the best candidates by tensor-core score and global
+        indices; rows past the kept ones are padding (-inf / -1)."""
         import torch
 
         kc = self.candidate_capacity(keep_n)
         if kc == 0:
             raise NotImplementedError(f"keep_n {keep_n} too large for the candidate pipeline")
-        eptr, eloc, ecode, ekeep = _buffer(experimental)
-        dptr, dloc, dcode, dkeep = _buffer(dictionary)
+        eptr, eloc, ecode, ekeep = _buffer(experimental, self)
+        dptr, dloc, dcode, dkeep = _buffer(dictionary, self)
         n_e = int(np.prod(experimental.shape))
         n_d = int(np.prod(dictionary.shape))
         if exp_rows < 1 or n_e % exp_rows or dict_rows < 1 or n_d % dict_rows:
@@ -465,8 +499,13 @@ class Context:
             rm = np.ascontiguousarray(np.asarray(nav_mask).ravel().astype(np.uint8))
             kept = int((rm == 0).sum())
         dev = torch.device("cuda", self.device)
-        approx = torch.empty((kept, kc), dtype=torch.float32, device=dev)
-        gidx = torch.empty((kept, kc), dtype=torch.int64, device=dev)
+        n_out = max(kept, int(pad_rows))
+        approx = torch.empty((n_out, kc), dtype=torch.float32, device=dev)
+        gidx = torch.empty((n_out, kc), dtype=torch.int64, device=dev)
+        if n_out > kept:
+            approx[kept:].fill_(-float("inf"))
+            gidx[kept:].fill_(-1)
+            self._stream_sync(dev)
         h = _vp()
         self._check(
             self._lib.kdi_shard_candidates(

@@ -213,6 +213,13 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
       if (value < 0) return kdi_fail(ctx, KDI_EINVAL, "superblock must be >= 0");
       ctx->superblock = (int)value;
       return KDI_OK;
+    case KDI_OPT_L2_POLICY:
+      if (value < 0 || value > 3) return kdi_fail(ctx, KDI_EINVAL, "l2 policy must be 0..3");
+      ctx->l2_policy = (int)value;
+      return KDI_OK;
+    case KDI_OPT_TILE_ROTATE:
+      ctx->tile_rotate = value != 0;
+      return KDI_OK;
     default:
       return kdi_fail(ctx, KDI_EINVAL, "unknown option %d", option);
   }

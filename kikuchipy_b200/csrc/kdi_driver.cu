@@ -454,20 +454,26 @@ int kdi_shard_rescore_owned(kdi_ctx* ctx, const kdi_shard* shard, const int64_t*
   return KDI_OK;
 }
 
-int kdi_shard_finalize(kdi_ctx* ctx, const kdi_shard* shard, const float* approx, const int64_t* gidx,
-                       const float* exact, int keep_n, int64_t dict_total, float* scores_out,
-                       int64_t* indices_out, int* flags_out, int* n_flag_out) {
+int kdi_shard_finalize(kdi_ctx* ctx, const kdi_shard* shard, int64_t row0, int64_t rows,
+                       const float* approx, const int64_t* gidx, const float* exact, int keep_n,
+                       int64_t dict_total, float* scores_out, int64_t* indices_out, int* flags_out,
+                       int* n_flag_out) {
   if (!ctx) return KDI_EINVAL;
   if (!shard || !approx || !gidx || !exact || !scores_out || !indices_out || !flags_out || !n_flag_out)
     return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_finalize: NULL argument");
   if (keep_n < 1 || keep_n > dict_total) return kdi_fail(ctx, KDI_EINVAL, "keep_n %d must be in [1, %lld]", keep_n, (long long)dict_total);
+  if (row0 < 0 || rows < 0 || row0 + rows > shard->exp->rows)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_finalize: rows [%lld, %lld) outside the %lld experimental rows",
+                    (long long)row0, (long long)(row0 + rows), (long long)shard->exp->rows);
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  *n_flag_out = 0;
+  if (rows == 0) return KDI_OK;
   KDI_TRY(kdi_ws2_reserve(ctx, 256));
   int* d_n = reinterpret_cast<int*>(ctx->ws2);
   cudaStream_t st = ctx->stream;
   KDI_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int), st));
-  KDI_TRY(kdi_launch_finalize(ctx, st, shard->exp->rows, shard->kc, approx, exact, gidx, keep_n, dict_total,
-                              (float)ctx->cert_sigmas, scores_out, indices_out, flags_out, d_n));
+  KDI_TRY(kdi_launch_finalize(ctx, st, rows, shard->kc, approx, exact, gidx, keep_n, dict_total,
+                              (float)ctx->cert_sigmas, row0, scores_out, indices_out, flags_out, d_n));
   KDI_CUDA(ctx, cudaMemcpyAsync(n_flag_out, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
   KDI_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->tm.flagged_rows += *n_flag_out;

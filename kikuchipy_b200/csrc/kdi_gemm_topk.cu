@@ -48,6 +48,9 @@ struct GemmParams {
   int64_t units;    // m_blocks * launch_strips
   int stages;
   int fmt;  // 0 fp16, 1 bf16
+  int rotate;     // 1: row block mb starts its strip at tile (mb mod strip length) - de-synchronises the
+                  // CTAs that share a strip so that they do not all miss on the same tile at once
+  int l2_policy;  // cache hints of the A / B tile loads (KDI_OPT_L2_POLICY)
   uint2* cand;
   uint32_t* thr;
   float* out;  // MODE 1
@@ -134,8 +137,10 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint64_t pol_a = l2_policy_evict_last();
-      const uint64_t pol_b = l2_policy_evict_normal();
+      // 0: A evict_last, B normal (default) | 1: both normal | 2: A evict_last, B evict_first |
+      // 3: A normal, B evict_first
+      const uint64_t pol_a = (p.l2_policy == 1 || p.l2_policy == 3) ? l2_policy_evict_normal() : l2_policy_evict_last();
+      const uint64_t pol_b = (p.l2_policy >= 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
       // in a CTA pair every load completes on the leader's barrier
       uint32_t full_dst = bar_full;
       if constexpr (CG == 2) {
@@ -149,7 +154,9 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int t0 = strip * p.strip_tiles;
         const int t1 = min(t0 + p.strip_tiles, p.n_tiles);
         const int a_row = (mb * CG + (int)rank) * KDI_TILE_M;
-        for (int nt = t0; nt < t1; ++nt) {
+        const int rot = p.rotate ? mb % (t1 - t0) : 0;
+        for (int ti = 0; ti < t1 - t0; ++ti) {
+          const int nt = t0 + (ti + rot) % (t1 - t0);
           const int b_row = nt * KDI_TILE_N + (int)rank * kBRows;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
@@ -187,7 +194,7 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         decode_unit(p, u, mb, strip);
         const int t0 = strip * p.strip_tiles;
         const int t1 = min(t0 + p.strip_tiles, p.n_tiles);
-        for (int nt = t0; nt < t1; ++nt) {
+        for (int ti = 0; ti < t1 - t0; ++ti) {  // (tile order is irrelevant to the issuer)
           mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)acc * KDI_TILE_N;
@@ -233,7 +240,9 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float gthr = -INFINITY;     // last value read from / published to the global threshold
       float thr = valid ? -INFINITY : INFINITY;
 
-      for (int nt = t0; nt < t1; ++nt) {
+      const int rot = p.rotate ? mb % (t1 - t0) : 0;
+      for (int ti = 0; ti < t1 - t0; ++ti) {
+        const int nt = t0 + (ti + rot) % (t1 - t0);
         mbar_wait(bar_tfull + 8u * acc, acc_phase);
         tc_fence_after();
         if constexpr (MODE == 0) {
@@ -503,6 +512,8 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   p.units = (int64_t)plan->m_blocks * strip_count;
   p.stages = plan->stages;
   p.fmt = exp->compute_dtype;
+  p.l2_policy = ctx->l2_policy;
+  p.rotate = ctx->tile_rotate;
   p.cand = cand;
   p.thr = thr;
   p.out = nullptr;

@@ -283,8 +283,8 @@ kdi_rescore_owned_kernel(const float* __restrict__ exp32, const float* __restric
 __global__ void __launch_bounds__(64)
 kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __restrict__ exact,
                     const int64_t* __restrict__ gidx, int keep_n, int64_t n_dict_total,
-                    float cert_sigmas, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
-                    int* __restrict__ flag_list, int* __restrict__ n_flag) {
+                    float cert_sigmas, int64_t row0, float* __restrict__ out_scores,
+                    int64_t* __restrict__ out_idx, int* __restrict__ flag_list, int* __restrict__ n_flag) {
   __shared__ float ex[64];
   __shared__ float ap[64];
   __shared__ int64_t gi[64];
@@ -338,9 +338,9 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
       const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 0.1f * fabsf(bias) + 1e-7f;
       ok = (nsel == kc) && (my_s > ap[nsel - 1] + bias + eps);
     }
-    if (!ok) flag_list[atomicAdd(n_flag, 1)] = (int)row;
+    if (!ok) flag_list[atomicAdd(n_flag, 1)] = (int)(row0 + row);
   }
-  if (tid == 0 && nsel < keep_n) flag_list[atomicAdd(n_flag, 1)] = (int)row;
+  if (tid == 0 && nsel < keep_n) flag_list[atomicAdd(n_flag, 1)] = (int)(row0 + row);
 }
 
 // ---- exact path -----------------------------------------------------------------------------
@@ -557,12 +557,13 @@ int kdi_launch_rescore_owned(kdi_ctx* ctx, cudaStream_t stream, const kdi_patter
 
 int kdi_launch_finalize(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, int kc, const float* approx,
                         const float* exact, const int64_t* gidx, int keep_n, int64_t n_dict_total,
-                        float cert_sigmas, float* out_scores, int64_t* out_idx, int* flag_list,
-                        int* n_flag) {
+                        float cert_sigmas, int64_t row0, float* out_scores, int64_t* out_idx,
+                        int* flag_list, int* n_flag) {
   if (rows <= 0) return KDI_OK;
   if (kc < 1 || kc > 64 || keep_n > kc) return kdi_fail(ctx, KDI_EINVAL, "finalize: need keep_n <= kc <= 64");
   kdi_finalize_kernel<<<(unsigned)rows, 64, 0, stream>>>(kc, approx, exact, gidx, keep_n, n_dict_total,
-                                                         cert_sigmas, out_scores, out_idx, flag_list, n_flag);
+                                                         cert_sigmas, row0, out_scores, out_idx, flag_list,
+                                                         n_flag);
   KDI_CUDA(ctx, cudaGetLastError());
   ctx->tm.kernel_launches++;
   return KDI_OK;

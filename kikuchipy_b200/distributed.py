@@ -1,12 +1,27 @@
-"""Dictionary sharding across GPUs: one process per GPU, one all-gather of per-shard top-k.
+"""Dictionary sharding across GPUs: one process per GPU, rank ``r`` holds
+dictionary rows ``shard_bounds(N, world, r)`` and every experimental row.
 
-The reference has no multi-device code; its serial loop over dictionary chunks with a running
-top-k (/root/reference/src/kikuchipy/indexing/_dictionary_indexing.py:94-128) is the same
-reduction this module spreads over ranks: every rank matches ALL experimental patterns against
-its contiguous dictionary shard (global indices via ``index_offset``, the ``+= start`` of
-``:118``), the per-shard ``(M, keep_n)`` scores + indices are all-gathered (NCCL over NVLink on
-GPUs, gloo in the CPU tests) and every rank merges the ``world_size`` lists with the same merge
-kernel that serves the chunk loop.
+The reduction is the one the reference runs serially over dictionary chunks
+(/root/reference/src/kikuchipy/indexing/_dictionary_indexing.py:94-128: per-chunk top-k, chunk
+offset added to the indices, running merge), spread over ranks.  The tensor-core pass (the
+expensive part) runs on every rank against its own shard; everything that is per experimental
+row afterwards is split by rows so that no rank repeats another rank's work:
+
+  0. host input only: every rank uploads 1/world of the raw experimental rows over its own PCIe
+     link and the raw bytes are all-gathered over NVLink
+  1. candidates: this shard's ``kc`` best per row by tensor-core score, global indices
+  2. the exchange of the path: all-to-all of the candidate lists by row slice, per-row merge
+     of the ``world`` lists of this rank's slice
+  3. all-gather of the merged candidate indices (every rank needs to know which of its
+     dictionary rows were nominated)
+  4. every rank rescores, in exact float32, the candidates whose dictionary rows it holds
+  5. reduce-scatter(MAX) of the exact scores by row slice (each candidate has one owner)
+  6. rank + certificate for this rank's slice
+  7. all-gather of the finished slices (identical result on every rank)
+  8. rows whose certificate failed anywhere: exact top-k per shard, gathered and merged
+
+The exchange logic is written against a small ``stages`` interface so that it runs under
+``gloo`` on CPU tensors in the tests (with the oracle standing in for the GPU stages).
 """
 
 from __future__ import annotations
@@ -55,6 +70,17 @@ def shard_bounds(n: int, world_size: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def row_slice(n_rows: int, world_size: int, rank: int) -> tuple[int, int, int]:
+    """``(rows per slice, start, end)`` of the experimental rows rank ``rank`` post-processes:
+    equal slices of ``ceil(n_rows / world_size)`` rows (the last ones may be short or empty), so
+    the collectives exchange equal-sized blocks."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank / world size")
+    per = -(-int(n_rows) // world_size) if n_rows > 0 else 0
+    start = min(rank * per, n_rows)
+    return per, start, min(start + per, n_rows)
+
+
 def gather_topk(scores, indices, group=None):
     """All-gather per-rank ``(M, k)`` score / index tensors into ``(world, M, k)`` tensors
     (list-major: what ``kdi_merge_topk`` expects).  Works on CUDA tensors (NCCL) and CPU
@@ -63,12 +89,130 @@ def gather_topk(scores, indices, group=None):
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
+    scores, indices = scores.contiguous(), indices.contiguous()
     s_all = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
     i_all = torch.empty((world,) + tuple(indices.shape), dtype=indices.dtype, device=indices.device)
-    # contiguous slices of one buffer: NCCL takes the flat all-gather path, gloo gathers per slice
-    dist.all_gather(list(s_all.unbind(0)), scores.contiguous(), group=group)
-    dist.all_gather(list(i_all.unbind(0)), indices.contiguous(), group=group)
+    # (concatenation form along dim 0: the one form both NCCL and gloo accept)
+    dist.all_gather_into_tensor(s_all.view((-1,) + tuple(scores.shape[1:])), scores, group=group)
+    dist.all_gather_into_tensor(i_all.view((-1,) + tuple(indices.shape[1:])), indices, group=group)
     return s_all, i_all
+
+
+def gather_experimental(experimental_host: np.ndarray, n_rows: int, device, group=None):
+    """Step 0: upload rows ``row_slice(n_rows, world, rank)`` of a raw host pattern array and
+    all-gather the raw bytes, so each PCIe link carries 1/world of the experimental set.
+    Returns a ``(n_rows, S)`` device tensor of the input dtype."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    flat = np.ascontiguousarray(experimental_host).reshape(n_rows, -1)
+    per, start, end = row_slice(n_rows, world, rank)
+    mine = torch.zeros((per, flat.shape[1]), dtype=torch.from_numpy(flat[:0]).dtype, device=device)
+    if end > start:
+        mine[: end - start].copy_(torch.from_numpy(flat[start:end]), non_blocking=True)
+    full = torch.empty((per * world, flat.shape[1]), dtype=mine.dtype, device=device)
+    dist.all_gather_into_tensor(full.view(torch.uint8), mine.view(torch.uint8), group=group)
+    return full[:n_rows]
+
+
+class _KdiStages:
+    """The GPU stages of the pipeline: thin calls into libkdi (``kdi_shard_*``)."""
+
+    def __init__(self, ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n, navigation_mask,
+                 start):
+        self.ctx, self.args = ctx, (experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n)
+        self.nav, self.start, self.shard = navigation_mask, start, None
+
+    def candidates(self, pad_rows):
+        self.shard, approx, gidx = self.ctx.shard_candidates(*self.args, nav_mask=self.nav, index_offset=self.start,
+                                                             pad_rows=pad_rows)
+        return approx, gidx, self.shard.kc
+
+    def merge(self, s_all, i_all, k):
+        return self.ctx.merge_topk(s_all, i_all, k)
+
+    def rescore_owned(self, gidx):
+        return self.shard.rescore_owned(gidx)
+
+    def finalize(self, approx, gidx, exact, keep_n, dict_total, row0, rows):
+        return self.shard.finalize(approx, gidx, exact, keep_n, dict_total, row0=row0, rows=rows)
+
+    def exact_rows(self, rows, k_local):
+        return self.shard.exact_rows(rows, k_local)
+
+    def close(self):
+        if self.shard is not None:
+            self.shard.close()
+
+
+def run_sharded_pipeline(stages, n_rows: int, keep_n: int, dictionary_size: int, n_shard: int, group=None,
+                         trace=None):
+    """Steps 1-8 of the module docstring over ``stages`` (see ``_KdiStages``).  Returns
+    ``(indices, scores)`` tensors ``(n_rows, keep_n)``, identical on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    trace = trace or (lambda name: None)
+    per, r0, r1 = row_slice(n_rows, world, rank)
+    padded = per * world
+    # 1. this shard's candidates by tensor-core score (global indices), padded to equal slices
+    approx, gidx, kc = stages.candidates(padded)
+    trace("candidates")
+    # 2. all-to-all by row slice: block j of the send buffer (rows of slice j) goes to rank j;
+    #    the receive buffer is list-major (list l = rank l's candidates for MY rows)
+    s_in = torch.empty((world, per, kc), dtype=approx.dtype, device=approx.device)
+    i_in = torch.empty((world, per, kc), dtype=gidx.dtype, device=gidx.device)
+    dist.all_to_all_single(s_in, approx.contiguous(), group=group)
+    dist.all_to_all_single(i_in, gidx.contiguous(), group=group)
+    trace("all_to_all")
+    my_idx, my_approx = stages.merge(s_in, i_in, kc)
+    trace("merge")
+    # 3. everyone learns every row's merged candidates
+    g_idx = torch.empty((padded, kc), dtype=my_idx.dtype, device=my_idx.device)
+    dist.all_gather_into_tensor(g_idx, my_idx.contiguous(), group=group)
+    trace("all_gather_idx")
+    # 4. exact scores of the candidates whose dictionary rows this rank holds (-inf elsewhere)
+    exact = stages.rescore_owned(g_idx)
+    trace("rescore_owned")
+    # 5. each candidate has exactly one owner: MAX combines, scattered back by row slice
+    my_exact = torch.empty((per, kc), dtype=exact.dtype, device=exact.device)
+    dist.reduce_scatter_tensor(my_exact, exact.contiguous(), op=dist.ReduceOp.MAX, group=group)
+    trace("reduce_scatter")
+    # 6. rank by exact score + certificate for this rank's rows
+    idx_s, sc_s, flags = stages.finalize(my_approx, my_idx, my_exact, keep_n, dictionary_size, r0, r1 - r0)
+    trace("finalize")
+    # 7. finished slices to everyone (+ how many rows each rank flagged)
+    idx = torch.empty((padded, keep_n), dtype=idx_s.dtype, device=idx_s.device)
+    scores = torch.empty((padded, keep_n), dtype=sc_s.dtype, device=sc_s.device)
+    dist.all_gather_into_tensor(idx, idx_s.contiguous(), group=group)
+    dist.all_gather_into_tensor(scores, sc_s.contiguous(), group=group)
+    counts = torch.zeros((world,), dtype=torch.int64, device=idx_s.device)
+    dist.all_gather_into_tensor(counts, torch.tensor([int(flags.numel())], dtype=torch.int64, device=idx_s.device),
+                                group=group)
+    counts = counts.cpu()
+    idx, scores = idx[:n_rows], scores[:n_rows]
+    trace("all_gather_results")
+    # 8. rows whose certificate failed on any rank: exact top-k per shard, gathered and merged
+    n_max = int(counts.max())
+    if n_max > 0:
+        mine = torch.full((n_max,), -1, dtype=torch.int32, device=idx_s.device)
+        mine[: flags.numel()] = flags.to(torch.int32)
+        rows = torch.empty((world * n_max,), dtype=torch.int32, device=idx_s.device)
+        dist.all_gather_into_tensor(rows, mine, group=group)
+        rows = torch.sort(rows[rows >= 0]).values  # same order on every rank
+        k_local = min(keep_n, n_shard)
+        fi, fs = stages.exact_rows(rows, k_local)
+        if k_local != keep_n:  # a shard smaller than keep_n contributes what it has
+            fs = torch.nn.functional.pad(fs, (0, keep_n - k_local), value=-float("inf"))
+            fi = torch.nn.functional.pad(fi, (0, keep_n - k_local), value=-1)
+        fs_all, fi_all = gather_topk(fs, fi, group)
+        mi, ms = stages.merge(fs_all, fi_all, keep_n)
+        idx[rows.long()] = mi
+        scores[rows.long()] = ms
+        trace("flagged_rows")
+    return idx, scores
 
 
 def dictionary_indexing_sharded(
@@ -86,9 +230,10 @@ def dictionary_indexing_sharded(
     """Index ``experimental`` against a dictionary whose rows ``shard_bounds(dictionary_size,
     world, rank)`` this rank holds in ``dictionary_shard``.
 
-    Returns ``(simulation_indices, scores)`` as CUDA tensors ``(M, keep_n)`` (global dictionary
-    indices, identical on every rank).  Needs an initialised ``torch.distributed`` process group
-    with the NCCL backend.
+    ``experimental`` (the same array on every rank) and ``dictionary_shard`` may be host arrays
+    or CUDA tensors.  Returns ``(simulation_indices, scores)`` as CUDA tensors ``(M, keep_n)``
+    (global dictionary indices, identical on every rank).  Needs an initialised
+    ``torch.distributed`` process group with the NCCL backend.
     """
     import torch
     import torch.distributed as dist
@@ -114,46 +259,27 @@ def dictionary_indexing_sharded(
         ctx.dictionary_indexing(experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
                                 nav_mask=navigation_mask, index_offset=start, out=(idx, scores))
         return idx, scores
-    if ctx.candidate_capacity(keep_n) == 0:
-        return _sharded_exact_lists(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
-                                    navigation_mask, start, kept, dictionary_size, group)
 
-    trace = _Trace(os.environ.get("KDI_TRACE") == "1" and rank == 0)
-    # 1. this shard's candidates by tensor-core score (global indices)
-    shard, approx, gidx = ctx.shard_candidates(experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
-                                               nav_mask=navigation_mask, index_offset=start)
-    trace("candidates")
-    try:
-        # 2. the one exchange of the path: all-gather of per-shard top-kc lists, merged per row
-        s_all, i_all = gather_topk(approx, gidx, group)
-        trace("all_gather")
-        g_idx, g_approx = ctx.merge_topk(s_all, i_all, shard.kc)
-        trace("merge")
-        # 3. every rank rescores exactly the candidates whose dictionary rows it holds ...
-        exact = shard.rescore_owned(g_idx)
-        trace("rescore_owned")
-        # 4. ... and the exact scores are combined (each candidate has exactly one owner)
-        dist.all_reduce(exact, op=dist.ReduceOp.MAX, group=group)
-        trace("all_reduce")
-        # 5. rank by exact score + certificate (identical on every rank)
-        idx, scores, flags = shard.finalize(g_approx, g_idx, exact, keep_n, dictionary_size)
-        trace("finalize")
-        trace.report(ctx)
-        if flags.numel():
-            # rows whose certificate failed: exact top-k per shard, gathered and merged
-            k_local = min(keep_n, n_shard)
-            fi, fs = shard.exact_rows(flags, k_local)
-            if k_local != keep_n:
-                fs = torch.nn.functional.pad(fs, (0, keep_n - k_local), value=-float("inf"))
-                fi = torch.nn.functional.pad(fi, (0, keep_n - k_local), value=-1)
-            fs_all, fi_all = gather_topk(fs, fi, group)
-            mi, ms = ctx.merge_topk(fs_all, fi_all, keep_n)
-            rows = flags.long()
-            idx[rows] = mi
-            scores[rows] = ms
-        return idx, scores
-    finally:
-        shard.close()
+    # torch ops, NCCL collectives and library kernels all on the context's stream: no host syncs
+    with torch.cuda.stream(ctx.torch_stream()):
+        trace = _Trace(os.environ.get("KDI_TRACE") == "1" and rank == 0)
+        if not (hasattr(experimental, "is_cuda") and experimental.is_cuda):
+            experimental = np.asarray(experimental)
+            if experimental.dtype in (np.uint8, np.uint16, np.float32, np.float64):
+                experimental = gather_experimental(experimental, n_exp_all, dev, group)
+                trace("upload_gather_experimental")
+        if ctx.candidate_capacity(keep_n) == 0:
+            return _sharded_exact_lists(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
+                                        navigation_mask, start, kept, dictionary_size, group)
+        stages = _KdiStages(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n, navigation_mask,
+                            start)
+        try:
+            idx, scores = run_sharded_pipeline(stages, kept, keep_n, dictionary_size, n_shard, group, trace)
+            trace.report(ctx)
+            torch.cuda.current_stream().synchronize()
+            return idx, scores
+        finally:
+            stages.close()
 
 
 def _sharded_exact_lists(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
@@ -176,4 +302,6 @@ def _sharded_exact_lists(ctx, experimental, n_exp_all, dictionary_shard, n_shard
         pad_i[:, :k_local] = idx
         scores, idx = pad_s, pad_i
     s_all, i_all = gather_topk(scores, idx, group)
-    return ctx.merge_topk(s_all, i_all, min(int(keep_n), int(dictionary_size)))
+    idx, scores = ctx.merge_topk(s_all, i_all, min(int(keep_n), int(dictionary_size)))
+    torch.cuda.current_stream().synchronize()
+    return idx, scores

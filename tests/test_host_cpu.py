@@ -94,46 +94,127 @@ def test_shard_bounds_cover_dictionary():
         kb.shard_bounds(10, 2, 2)
 
 
+class _OracleStages:
+    """CPU stand-in for the GPU stages of ``run_sharded_pipeline`` (the oracle is the checker here):
+    same interface as ``kikuchipy_b200.distributed._KdiStages`` on CPU torch tensors."""
+
+    KC = 8
+
+    def __init__(self, exp, dic_shard, start, flag_every=0):
+        import torch
+
+        self.t = torch
+        e = orc.prepare_experimental(exp, "ncc", exp.shape[0])
+        d = orc.prepare_dictionary(dic_shard.reshape(dic_shard.shape[0], -1), "ncc")
+        self.sim = orc.match(e, d)  # (rows, shard rows) exact scores
+        self.start, self.flag_every = start, flag_every
+
+    @staticmethod
+    def _rank(scores, idx, k):
+        order = np.lexsort((idx, -scores), axis=1)[:, :k]  # score desc, index asc
+        return np.take_along_axis(idx, order, 1), np.take_along_axis(scores, order, 1)
+
+    def candidates(self, pad_rows):
+        rows, n = self.sim.shape
+        kc = self.KC
+        # "tensor-core" scores: the exact ones plus a small deterministic perturbation
+        approx = self.sim + 1e-6 * np.cos(np.arange(rows * n, dtype=np.float32)).reshape(rows, n)
+        gidx = np.broadcast_to(np.arange(n, dtype=np.int64) + self.start, (rows, n))
+        i, s = self._rank(approx, gidx, min(kc, n))
+        a = np.full((max(rows, pad_rows), kc), -np.inf, np.float32)
+        g = np.full((max(rows, pad_rows), kc), -1, np.int64)
+        a[:rows, : s.shape[1]] = s
+        g[:rows, : i.shape[1]] = i
+        return self.t.from_numpy(a), self.t.from_numpy(g), kc
+
+    def merge(self, s_all, i_all, k):
+        s = np.concatenate(list(s_all.numpy()), axis=1)
+        i = np.concatenate(list(i_all.numpy()), axis=1)
+        mi, ms = self._rank(s, i, k)
+        return self.t.from_numpy(mi.copy()), self.t.from_numpy(ms.copy())
+
+    def rescore_owned(self, gidx):
+        g = gidx.numpy()
+        rows, n = self.sim.shape
+        out = np.full((max(rows, g.shape[0]), g.shape[1]), -np.inf, np.float32)
+        loc = g[:rows] - self.start
+        own = (loc >= 0) & (loc < n)
+        r = np.nonzero(own)
+        out[r[0], r[1]] = self.sim[r[0], loc[own]]
+        return self.t.from_numpy(out)
+
+    def finalize(self, approx, gidx, exact, keep_n, dict_total, row0, rows):
+        i, s = self._rank(exact.numpy(), gidx.numpy(), keep_n)
+        i[rows:], s[rows:] = -1, -np.inf
+        flags = [r for r in range(row0, row0 + rows) if self.flag_every and r % self.flag_every == 0]
+        for r in flags:  # a flagged row's provisional result must not survive
+            i[r - row0], s[r - row0] = -7, np.nan
+        return self.t.from_numpy(i.copy()), self.t.from_numpy(s.copy()), self.t.tensor(flags, dtype=self.t.int32)
+
+    def exact_rows(self, rows, k_local):
+        r = rows.numpy().astype(np.int64)
+        n = self.sim.shape[1]
+        gidx = np.broadcast_to(np.arange(n, dtype=np.int64) + self.start, (r.size, n))
+        i, s = self._rank(self.sim[r], gidx, k_local)
+        return self.t.from_numpy(i.copy()), self.t.from_numpy(s.copy())
+
+
 def _gloo_worker(rank, world, port, tmp):
     import torch
     import torch.distributed as dist
 
+    from kikuchipy_b200.distributed import run_sharded_pipeline
+
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        exp = orc.synthetic_experimental(24, (12, 12), seed=1)
+        exp = orc.synthetic_experimental(25, (12, 12), seed=1)
         dic = orc.synthetic_dictionary(301, (12, 12), seed=2)
         start, end = kb.shard_bounds(301, world, rank)
-        # per-shard stage: the oracle stands in for the GPU call (checker), global indices via the offset
-        idx, sc = orc.dictionary_indexing(exp, dic[start:end], keep_n=7)
-        idx = idx + start
-        s_all, i_all = kb.gather_topk(torch.from_numpy(sc.copy()), torch.from_numpy(idx.copy()))
-        assert tuple(s_all.shape) == (world, 24, 7)
-        # list-major layout: list r must be rank r's result
-        assert np.array_equal(s_all[rank].numpy(), sc) and np.array_equal(i_all[rank].numpy(), idx)
-        alls = np.concatenate(list(s_all.numpy()), axis=1)
-        alli = np.concatenate(list(i_all.numpy()), axis=1)
-        best = np.argsort(-alls, axis=1, kind="stable")[:, :7]
-        np.savez(os.path.join(tmp, f"r{rank}.npz"), idx=np.take_along_axis(alli, best, 1),
-                 sc=np.take_along_axis(alls, best, 1))
+        out = {}
+        for name, flag_every in (("plain", 0), ("flagged", 4)):
+            st = _OracleStages(exp, dic[start:end], start, flag_every)
+            idx, sc = run_sharded_pipeline(st, 25, 5, 301, end - start)
+            out[f"idx_{name}"], out[f"sc_{name}"] = idx.numpy(), sc.numpy()
+        # layout of the plain all-gather helper: list r is rank r's tensor
+        s_all, i_all = kb.gather_topk(torch.full((3, 2), float(rank)), torch.full((3, 2), rank, dtype=torch.int64))
+        assert tuple(s_all.shape) == (world, 3, 2) and all(float(s_all[r, 0, 0]) == r for r in range(world))
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), **out)
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_gather_matches_unsharded_gloo(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_pipeline_matches_unsharded_gloo(tmp_path, world):
+    """all-to-all by row slice -> merge -> all-gather -> owner rescoring -> reduce-scatter ->
+    finalize -> all-gather (+ flagged rows), with ragged row slices (25 rows over 2 / 3 ranks)."""
     import torch.multiprocessing as mp
 
-    world = 2
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + world
     mp.spawn(_gloo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
-    exp = orc.synthetic_experimental(24, (12, 12), seed=1)
+    exp = orc.synthetic_experimental(25, (12, 12), seed=1)
     dic = orc.synthetic_dictionary(301, (12, 12), seed=2)
-    ridx, rsc = orc.dictionary_indexing(exp, dic, keep_n=7)
+    ridx, rsc = orc.dictionary_indexing(exp, dic, keep_n=5)
+    z0 = np.load(os.path.join(str(tmp_path), "r0.npz"))
     for r in range(world):
         z = np.load(os.path.join(str(tmp_path), f"r{r}.npz"))
-        c = orc.compare_topk(ridx, rsc, z["idx"], z["sc"])
-        assert c["tie_ok"] and c["max_dscore"] < 1e-6
-        assert c["exact_rows"] == 1.0
+        for name in ("plain", "flagged"):
+            assert z[f"idx_{name}"].shape == (25, 5)
+            c = orc.compare_topk(ridx, rsc, z[f"idx_{name}"], z[f"sc_{name}"])
+            assert c["tie_ok"] and c["max_dscore"] < 1e-6 and c["exact_rows"] == 1.0, (name, c)
+            assert np.array_equal(z[f"idx_{name}"], z0[f"idx_{name}"])  # identical on every rank
+
+
+def test_row_slices_cover_rows():
+    from kikuchipy_b200.distributed import row_slice
+
+    for n in (1, 7, 25, 80_000):
+        for world in (1, 2, 3, 8):
+            sl = [row_slice(n, world, r) for r in range(world)]
+            per = sl[0][0]
+            assert all(s[0] == per for s in sl) and per * world >= n
+            assert sl[0][1] == 0 and sl[-1][2] == n
+            assert all(sl[i][2] == sl[i + 1][1] for i in range(world - 1))
 
 
 def test_bench_cpu_arm_runs_small(monkeypatch):
