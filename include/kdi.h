@@ -68,6 +68,7 @@ extern "C" {
                                    dictionary normal (default), 1 = both normal, 2 = evict_last +
                                    evict_first, 3 = normal + evict_first                               */
 #define KDI_OPT_TILE_ROTATE 7   /* 1 = each row block starts its strip at a different tile            */
+#define KDI_OPT_MAX_STAGES 8    /* cap on the GEMM kernel's shared-memory ring depth (0 = as many as fit) */
 
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;

@@ -35,6 +35,7 @@ OPT_STRIP_TILES = 4
 OPT_SUPERBLOCK = 5
 OPT_L2_POLICY = 6
 OPT_TILE_ROTATE = 7
+OPT_MAX_STAGES = 8
 
 _DTYPES = {
     np.dtype(np.uint8): KDI_U8,

@@ -217,6 +217,10 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
       if (value < 0 || value > 3) return kdi_fail(ctx, KDI_EINVAL, "l2 policy must be 0..3");
       ctx->l2_policy = (int)value;
       return KDI_OK;
+    case KDI_OPT_MAX_STAGES:
+      if (value != 0 && value < 2) return kdi_fail(ctx, KDI_EINVAL, "max_stages must be 0 or >= 2");
+      ctx->max_stages = (int)value;
+      return KDI_OK;
     case KDI_OPT_TILE_ROTATE:
       ctx->tile_rotate = value != 0;
       return KDI_OK;

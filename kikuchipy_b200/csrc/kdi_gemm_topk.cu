@@ -430,6 +430,7 @@ int kdi_gemm_make_plan(kdi_ctx* ctx, int64_t M, int64_t N, int64_t kp, int keep_
   if (pl.kc == 0) return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d too large for the fused path", keep_n);
   pl.cta_group = ctx->cta_group == 2 ? 2 : 1;
   pl.stages = stages_for(pl.cta_group, pl.kc, 0);
+  if (ctx->max_stages > 1 && pl.stages > ctx->max_stages) pl.stages = ctx->max_stages;
   const int64_t rows_per_block = (int64_t)KDI_TILE_M * pl.cta_group;
   pl.m_blocks = (int)kdi_ceil_div(M, rows_per_block);
   pl.n_tiles = (int)kdi_ceil_div(N, KDI_TILE_N);

@@ -27,6 +27,7 @@ using kdi::key_float;
 
 constexpr int kSelThreads = 128;
 constexpr int kSelBuf = 512;  // candidate keys held in shared memory between compactions
+constexpr int kSelBatch = 8;  // candidate loads in flight per thread
 
 // dot product of two zero-padded float32 rows of n4 float4 each, by one warp.  fp32 FMAs in
 // four accumulators per lane, reduction in double.  Every exact score in the library goes
@@ -100,28 +101,37 @@ __device__ __forceinline__ int select_candidates(const uint2* __restrict__ c, in
   bool sorted = true;
   if (tid == 0) *s_count = 0;
   __syncthreads();
-  for (int64_t base = 0; base < total; base += kSelThreads) {
-    const int64_t i = base + tid;
-    if (i < total) {
-      const uint2 e = c[i];
-      if (e.y != 0xFFFFFFFFu && float_key(__uint_as_float(e.x)) >= tkey)
-        keys[atomicAdd(s_count, 1)] = pack_key(__uint_as_float(e.x), e.y);
+  // kSelBatch independent loads per thread are issued before any of them is consumed: the kernel
+  // shares the device with the HBM-saturating rescoring gathers of other rows, so a chain of
+  // dependent load -> barrier rounds would pay the loaded memory latency once per round.
+  for (int64_t base = 0; base < total; base += kSelThreads * kSelBatch) {
+    uint2 e[kSelBatch];
+#pragma unroll
+    for (int b = 0; b < kSelBatch; ++b) {
+      const int64_t i = base + b * kSelThreads + tid;
+      e[b] = i < total ? __ldg(c + i) : make_uint2(0u, 0xFFFFFFFFu);
     }
-    __syncthreads();
-    kept = *s_count;
-    sorted = false;
-    __syncthreads();  // everyone has read the count before the next round appends
-    if (kept > kSelBuf - kSelThreads) {  // the next round might not fit: compact
-      int n2 = 64;
-      while (n2 < kept) n2 <<= 1;
-      for (int j = kept + tid; j < n2; j += kSelThreads) keys[j] = 0;
-      block_sort_desc<kSelThreads>(keys, n2);
-      kept = KC;  // kept > KC here because kSelBuf - kSelThreads >= KC
-      const uint32_t k32 = (uint32_t)(keys[KC - 1] >> 32);
-      tkey = k32 > tkey ? k32 : tkey;
-      sorted = true;
-      if (tid == 0) *s_count = KC;
+#pragma unroll
+    for (int b = 0; b < kSelBatch; ++b) {
+      if (base + b * kSelThreads >= total) break;  // uniform
+      if (e[b].y != 0xFFFFFFFFu && float_key(__uint_as_float(e[b].x)) >= tkey)
+        keys[atomicAdd(s_count, 1)] = pack_key(__uint_as_float(e[b].x), e[b].y);
       __syncthreads();
+      kept = *s_count;
+      sorted = false;
+      __syncthreads();  // everyone has read the count before the next round appends
+      if (kept > kSelBuf - kSelThreads) {  // the next round might not fit: compact
+        int n2 = 64;
+        while (n2 < kept) n2 <<= 1;
+        for (int j = kept + tid; j < n2; j += kSelThreads) keys[j] = 0;
+        block_sort_desc<kSelThreads>(keys, n2);
+        kept = KC;  // kept > KC here because kSelBuf - kSelThreads >= KC
+        const uint32_t k32 = (uint32_t)(keys[KC - 1] >> 32);
+        tkey = k32 > tkey ? k32 : tkey;
+        sorted = true;
+        if (tid == 0) *s_count = KC;
+        __syncthreads();
+      }
     }
   }
   if (!sorted) {

@@ -21,23 +21,35 @@ idx = torch.empty((M, 20), dtype=torch.int64, device=dev)
 sc = torch.empty((M, 20), dtype=torch.float32, device=dev)
 torch.cuda.synchronize()
 
-# (superblock, strip_tiles, l2_policy, rotate)
+# (superblock, strip_tiles, l2_policy, rotate[, max_stages])
 SETTINGS = [(0, 0, 0, 0), (0, 0, 1, 0), (0, 0, 2, 0), (0, 0, 3, 0), (0, 0, 0, 1), (0, 0, 1, 1),
             (0, 4, 0, 0), (0, 4, 0, 1), (0, 16, 0, 1), (10, 0, 0, 0), (10, 4, 0, 1), (5, 4, 0, 0),
             (40, 0, 0, 0), (40, 4, 0, 0), (40, 4, 0, 1), (40, 4, 1, 1), (40, 9, 1, 1), (40, 16, 0, 0)]
 if os.environ.get("SETTINGS"):
     SETTINGS = [tuple(int(x) for x in s.split(",")) for s in os.environ["SETTINGS"].split(";")]
+ROUNDS = int(os.environ.get("ROUNDS", "1"))  # > 1: settings interleaved (A B C A B C ...) so that clock / power drift
+                                            # over the run does not favour whichever setting happens to run first
 ref = None
-for sb, st, pol, rot in SETTINGS:
-    ctx.set_option(_lib.OPT_SUPERBLOCK, sb); ctx.set_option(_lib.OPT_STRIP_TILES, st)
-    ctx.set_option(_lib.OPT_L2_POLICY, pol); ctx.set_option(_lib.OPT_TILE_ROTATE, rot)
-    ms, tot = [], []
-    for _ in range(REPS):
-        ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, 20, out=(idx, sc))
-        t = ctx.timings(); ms.append(t["gemm_topk_ms"]); tot.append(t["total_ms"])
-    if ref is None:
-        ref = idx.clone()
-    same = bool(torch.equal(ref, idx))
+acc = {s: {"gemm": [], "total": [], "rescore": [], "flagged": 0, "same": True} for s in SETTINGS}
+for rnd in range(ROUNDS):
+    for setting in SETTINGS:
+        sb, st, pol, rot = setting[:4]
+        ctx.set_option(_lib.OPT_MAX_STAGES, setting[4] if len(setting) > 4 else 0)
+        ctx.set_option(_lib.OPT_SUPERBLOCK, sb); ctx.set_option(_lib.OPT_STRIP_TILES, st)
+        ctx.set_option(_lib.OPT_L2_POLICY, pol); ctx.set_option(_lib.OPT_TILE_ROTATE, rot)
+        a = acc[setting]
+        for _ in range(REPS):
+            ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, 20, out=(idx, sc))
+            t = ctx.timings()
+            a["gemm"].append(t["gemm_topk_ms"]); a["total"].append(t["total_ms"]); a["rescore"].append(t["rescore_ms"])
+            a["flagged"] = t["flagged_rows"]
+        if ref is None:
+            ref = idx.clone()
+        a["same"] = a["same"] and bool(torch.equal(ref, idx))
+for setting, a in acc.items():
+    sb, st, pol, rot = setting[:4]
     print(json.dumps({"superblock": sb, "strip_tiles": st, "l2_policy": pol, "rotate": rot,
-                      "gemm_ms": [round(x, 3) for x in ms], "total_ms": round(min(tot), 3),
-                      "rescore_ms": round(t["rescore_ms"], 3), "flagged": t["flagged_rows"], "same_idx": same}), flush=True)
+                      "max_stages": setting[4] if len(setting) > 4 else 0,
+                      "gemm_ms_mean": round(float(np.mean(a["gemm"])), 3), "gemm_ms_min": round(min(a["gemm"]), 3),
+                      "total_ms_mean": round(float(np.mean(a["total"])), 3), "rescore_ms_mean": round(float(np.mean(a["rescore"])), 3),
+                      "flagged": a["flagged"], "same_idx": a["same"], "n": len(a["gemm"])}), flush=True)
