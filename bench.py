@@ -212,6 +212,8 @@ def run_ours(args, rank, world, local_rank):
         ctx.set_option(_lib.OPT_STRIP_TILES, args.strip_tiles)
     if args.superblock:
         ctx.set_option(_lib.OPT_SUPERBLOCK, args.superblock)
+    if args.overlap is not None:
+        ctx.set_option(_lib.OPT_OVERLAP, args.overlap)
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
 
     m_total = M_PER_GPU * world
@@ -364,6 +366,7 @@ def main():
     ap.add_argument("--compute-dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--strip-tiles", type=int, default=0)
     ap.add_argument("--superblock", type=int, default=0)
+    ap.add_argument("--overlap", type=int, default=None, help="0: one kernel at a time; 1 (default): overlapped schedule")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -69,6 +69,10 @@ extern "C" {
                                    evict_first, 3 = normal + evict_first                               */
 #define KDI_OPT_TILE_ROTATE 7   /* 1 = each row block starts its strip at a different tile            */
 #define KDI_OPT_MAX_STAGES 8    /* cap on the GEMM kernel's shared-memory ring depth (0 = as many as fit) */
+#define KDI_OPT_OVERLAP 9       /* 1 (default) = device-resident jobs run the dictionary normalisation and the
+                                   rescoring of finished row blocks beside the tensor-core launches (separate
+                                   streams); 0 = one kernel at a time (per-kernel profiling); 2 = overlapped
+                                   schedule even for small jobs (tests)                                 */
 
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;

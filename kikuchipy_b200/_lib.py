@@ -36,6 +36,7 @@ OPT_SUPERBLOCK = 5
 OPT_L2_POLICY = 6
 OPT_TILE_ROTATE = 7
 OPT_MAX_STAGES = 8
+OPT_OVERLAP = 9
 
 _DTYPES = {
     np.dtype(np.uint8): KDI_U8,

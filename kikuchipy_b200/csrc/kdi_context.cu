@@ -3,6 +3,7 @@
 #include "kdi_internal.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -111,6 +112,61 @@ void kdi_dev_free(kdi_ctx* ctx, void* p, size_t bytes) {
   kdi_pool_trim(ctx, ctx->total_mem / 4);
 }
 
+int kdi_carveout_pref() {
+  static const int v = [] {
+    const char* e = getenv("KDI_CARVEOUT");
+    return e ? atoi(e) : -1;
+  }();
+  return v;
+}
+
+int kdi_gemm_carveout_pref() {
+  static const int v = [] {
+    const char* e = getenv("KDI_GEMM_CARVEOUT");
+    return e ? atoi(e) : -1;
+  }();
+  return v;
+}
+
+// ---- KDI_TIMELINE=1 diagnostics -----------------------------------------------------------------
+static cudaEvent_t span_event(kdi_ctx* ctx) {
+  if (ctx->span_next == ctx->span_events.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    ctx->span_events.push_back(e);
+  }
+  return ctx->span_events[ctx->span_next++];
+}
+
+kdi_span::kdi_span(kdi_ctx* c, cudaStream_t s, const char* name) : ctx(c), stream(s) {
+  if (!c->timeline) return;
+  cudaEvent_t a = span_event(c);
+  b = span_event(c);
+  cudaEventRecord(a, s);
+  const int sid = s == c->stream ? 0 : s == c->gemm_stream2 ? 1 : s == c->aux_stream ? 2 : 3;
+  c->spans.push_back({name, sid, a, b});
+}
+kdi_span::~kdi_span() {
+  if (b) cudaEventRecord(b, stream);
+}
+void kdi_timeline_reset(kdi_ctx* ctx) {
+  ctx->spans.clear();
+  ctx->span_next = 0;
+}
+void kdi_timeline_print(kdi_ctx* ctx) {
+  if (!ctx->timeline || ctx->spans.empty()) return;
+  static const char* names[] = {"main", "gemm2", "aux", "copy"};
+  cudaDeviceSynchronize();
+  fprintf(stderr, "[kdi timeline] (ms from the first launch; start = stream reached the launch, end = kernel done)\n");
+  for (const auto& sp : ctx->spans) {
+    float t0 = 0.f, t1 = 0.f;
+    cudaEventElapsedTime(&t0, ctx->spans[0].a, sp.a);
+    cudaEventElapsedTime(&t1, ctx->spans[0].a, sp.b);
+    fprintf(stderr, "  %-6s %-28s %8.3f -> %8.3f  (%.3f)\n", names[sp.stream_id], sp.name, t0, t1, t1 - t0);
+  }
+  cudaGetLastError();
+}
+
 extern "C" {
 
 int kdi_version(void) { return KDI_VERSION; }
@@ -147,12 +203,18 @@ int kdi_init(int device, kdi_ctx** out) {
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   ctx->total_mem = prop.totalGlobalMem;
-  INIT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
+  INIT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  INIT_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+  INIT_CUDA(cudaStreamCreateWithPriority(&ctx->gemm_stream2, cudaStreamNonBlocking, prio_hi));
+  INIT_CUDA(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_lo));
   INIT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : ctx->dep_ev) INIT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : ctx->ev) INIT_CUDA(cudaEventCreate(&ev));
   for (auto& ev : ctx->copy_ev) INIT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : ctx->free_ev) INIT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 #undef INIT_CUDA
+  if (const char* tl = getenv("KDI_TIMELINE")) ctx->timeline = atoi(tl);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
@@ -169,6 +231,8 @@ int kdi_destroy(kdi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->gemm_stream2) cudaStreamSynchronize(ctx->gemm_stream2);
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   kdi_pool_trim(ctx, 0);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
@@ -178,6 +242,10 @@ int kdi_destroy(kdi_ctx* ctx) {
   for (auto& ev : ctx->free_ev) if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->gemm_stream2) cudaStreamDestroy(ctx->gemm_stream2);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  for (auto& ev : ctx->dep_ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->span_events) if (ev) cudaEventDestroy(ev);
   delete ctx;
   return KDI_OK;
 }
@@ -220,6 +288,10 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
     case KDI_OPT_MAX_STAGES:
       if (value != 0 && value < 2) return kdi_fail(ctx, KDI_EINVAL, "max_stages must be 0 or >= 2");
       ctx->max_stages = (int)value;
+      return KDI_OK;
+    case KDI_OPT_OVERLAP:
+      if (value != 0 && value != 1 && value != 2) return kdi_fail(ctx, KDI_EINVAL, "overlap must be 0, 1 or 2");
+      ctx->overlap = (int)value;
       return KDI_OK;
     case KDI_OPT_TILE_ROTATE:
       ctx->tile_rotate = value != 0;
@@ -320,13 +392,14 @@ int kdi_patterns_alloc(kdi_ctx* ctx, int64_t rows, int64_t S, int metric, kdi_pa
 }
 
 int kdi_patterns_fill(kdi_ctx* ctx, cudaStream_t stream, kdi_patterns* p, int64_t row_offset,
-                      const void* d_src, int src_dtype, int64_t n_rows, const int64_t* d_rowmap) {
+                      const void* d_src, int src_dtype, int64_t n_rows, const int64_t* d_rowmap,
+                      int max_ctas) {
   if (row_offset < 0 || row_offset + n_rows > p->rows)
     return kdi_fail(ctx, KDI_EINTERNAL, "pattern fill out of range");
   return kdi_launch_normalize(ctx, stream, d_src, src_dtype, p->S, d_rowmap,
                               ctx->mask_S ? ctx->d_cols : nullptr, n_rows, p->s_eff, p->metric,
                               p->compute_dtype, p->a32 + row_offset * p->s_pitch, p->s_pitch,
-                              reinterpret_cast<uint16_t*>(p->a16) + row_offset * p->kp, p->kp);
+                              reinterpret_cast<uint16_t*>(p->a16) + row_offset * p->kp, p->kp, max_ctas);
 }
 
 extern "C" {

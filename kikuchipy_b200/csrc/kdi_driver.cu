@@ -104,27 +104,129 @@ int kdi_match_advance(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
   return KDI_OK;
 }
 
-int kdi_match_finish(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
-                     const kdi_patterns* dict, int64_t index_offset) {
+// what runs on a range of experimental rows once every dictionary strip has been matched
+// against them: the full selection + exact rescoring + certificate, or (sharded pipeline) the
+// selection alone
+struct kdi_post {
+  bool candidates_only = false;
+  int64_t index_offset = 0;
+  float* approx_out = nullptr;   // candidates_only
+  int64_t* gidx_out = nullptr;   // candidates_only
+};
+
+static int launch_post(kdi_ctx* ctx, cudaStream_t st, kdi_match_job* job, const kdi_patterns* exp,
+                       const kdi_patterns* dict, const kdi_post& post, int64_t row0, int64_t n_rows) {
+  const float inv = 1.0f / (KDI_OP_SCALE * KDI_OP_SCALE);
+  if (post.candidates_only)
+    return kdi_launch_select_only(ctx, st, exp->rows, &job->plan, job->cand, job->thr, post.index_offset, inv,
+                                  post.approx_out, post.gidx_out, row0, n_rows);
+  return kdi_launch_select_rescore(ctx, st, exp, dict, &job->plan, job->cand, job->thr, job->keep_n,
+                                   post.index_offset, inv, (float)ctx->cert_sigmas, job->d_sc, job->d_ix,
+                                   job->flags, job->d_nflag, row0, n_rows);
+}
+
+static void sync_all_streams(kdi_ctx* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamSynchronize(ctx->gemm_stream2);
+  cudaStreamSynchronize(ctx->aux_stream);
+}
+
+// Overlapped schedule of a device-resident job (fused path).  The tensor-core launches go to the
+// two high-priority streams, the HBM-bound kernels to the low-priority stream and run beside them
+// (the GEMM kernel leaves ~30 KB of shared memory per SM free for that):
+//   aux : normalise dictionary rows [g1_rows, N)  (small resident grid; queued by the caller)
+//   main: normalise rows [0, g1_rows) -> GEMM(all row blocks, strips below g1_rows)
+//   main/gemm2 alternating, after the aux normalise: GEMM(row-block group i, remaining strips)
+//   aux : post-processing (selection + exact rescoring) of group i as soon as its GEMM is done
+// Only the first slice of the normalisation and the last group's rescoring are exposed.
+// `strips_lo` strips have already been launched on the main stream for every row block;
+// `e_fill` (may be NULL) is the event the remaining strips have to wait for.
+static int run_overlapped(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
+                          const kdi_patterns* dict, const kdi_post& post, int strips_lo,
+                          cudaEvent_t e_fill) {
+  const kdi_gemm_plan& pl = job->plan;
+  cudaStream_t sm = ctx->stream, s2 = ctx->gemm_stream2, sa = ctx->aux_stream;
+  const int64_t rows_per_mb = (int64_t)KDI_TILE_M * pl.cta_group;
+  const int n_sb = (int)kdi_ceil_div(pl.m_blocks, pl.superblock);
+  const int max_groups = 48;  // bounded by the event pool
+  const int sb_per_group = (int)kdi_ceil_div(n_sb, max_groups);
+  const int n_groups = (int)kdi_ceil_div(n_sb, sb_per_group);
+  int ev_i = 0;
+  // everything queued on the main stream so far (experimental rows, thresholds, the first
+  // dictionary slice and its strips) precedes the work on the other streams
+  cudaEvent_t e_start = ctx->dep_ev[ev_i++];
+  KDI_CUDA(ctx, cudaEventRecord(e_start, sm));
+  KDI_CUDA(ctx, cudaStreamWaitEvent(s2, e_start, 0));
+  KDI_CUDA(ctx, cudaStreamWaitEvent(sa, e_start, 0));
+  if (e_fill) {
+    KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_fill, 0));
+    KDI_CUDA(ctx, cudaStreamWaitEvent(s2, e_fill, 0));
+  }
+  for (int g = 0; g < n_groups; ++g) {
+    cudaStream_t sg = (g & 1) ? s2 : sm;
+    const int mb0 = g * sb_per_group * pl.superblock;
+    const int mbn = std::min(pl.m_blocks - mb0, sb_per_group * pl.superblock);
+    if (strips_lo < pl.n_strips)
+      KDI_TRY(kdi_launch_gemm_topk(ctx, sg, exp, dict, &pl, strips_lo, pl.n_strips - strips_lo, job->cand,
+                                   job->thr, mb0, mbn));
+    cudaEvent_t e_g = ctx->dep_ev[ev_i++];
+    KDI_CUDA(ctx, cudaEventRecord(e_g, sg));
+    KDI_CUDA(ctx, cudaStreamWaitEvent(sa, e_g, 0));
+    const int64_t row0 = (int64_t)mb0 * rows_per_mb;
+    const int64_t n_rows = std::min<int64_t>(job->M - row0, (int64_t)mbn * rows_per_mb);
+    KDI_TRY(launch_post(ctx, sa, job, exp, dict, post, row0, n_rows));
+  }
+  job->strips_done = pl.n_strips;
+  // join: GEMM span ends when both GEMM streams are done; the job when the aux stream is
+  cudaEvent_t e_s2 = ctx->dep_ev[ev_i++];
+  KDI_CUDA(ctx, cudaEventRecord(e_s2, s2));
+  KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_s2, 0));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[9], sm));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], sm));
+  cudaEvent_t e_aux = ctx->dep_ev[ev_i++];
+  KDI_CUDA(ctx, cudaEventRecord(e_aux, sa));
+  KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_aux, 0));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], sm));
+  return KDI_OK;
+}
+
+// is the overlapped schedule worth it for this job?  (needs the fused path and enough work that
+// the extra launches do not matter)
+static bool want_overlap(const kdi_ctx* ctx, const kdi_match_job* job) {
+  if (!ctx->overlap || !job->fused || job->M <= 0) return false;
+  if (ctx->overlap == 2) return true;  // forced (tests)
+  return job->plan.units >= 4 * (ctx->sm_count / job->plan.cta_group);
+}
+
+// selection + rescoring of every row on the main stream (non-overlapped schedule)
+static int kdi_match_select(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
+                            const kdi_patterns* dict, const kdi_post& post) {
+  if (job->M == 0 || !job->fused) return KDI_OK;
+  if (job->strips_done != job->plan.n_strips)
+    return kdi_fail(ctx, KDI_EINTERNAL, "match finished before every dictionary strip was processed");
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  KDI_TRY(launch_post(ctx, ctx->stream, job, exp, dict, post, 0, job->M));
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+  return KDI_OK;
+}
+
+// after the post-processing of every row has been queued (ev[3] / ev[4] recorded): rows whose
+// certificate failed go through the exact path, results go to the caller
+int kdi_match_complete(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
+                       const kdi_patterns* dict, int64_t index_offset) {
   const int64_t M = job->M;
   const int keep_n = job->keep_n;
   if (M == 0) return KDI_OK;
   cudaStream_t st = ctx->stream;
   int n_flag = 0;
-  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
   if (job->fused) {
-    if (job->strips_done != job->plan.n_strips)
-      return kdi_fail(ctx, KDI_EINTERNAL, "match finished before every dictionary strip was processed");
-    const float inv = 1.0f / (KDI_OP_SCALE * KDI_OP_SCALE);
-    KDI_TRY(kdi_launch_select_rescore(ctx, st, exp, dict, &job->plan, job->cand, job->thr, keep_n,
-                                      index_offset, inv, (float)ctx->cert_sigmas, job->d_sc, job->d_ix,
-                                      job->flags, job->d_nflag));
-    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     KDI_CUDA(ctx, cudaMemcpyAsync(&n_flag, job->d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
     KDI_CUDA(ctx, cudaStreamSynchronize(st));
     if (n_flag > 0)
       KDI_TRY(exact_rows(ctx, exp, dict, job->flags, 0, n_flag, keep_n, index_offset, job->d_sc, job->d_ix));
   } else {
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     KDI_TRY(exact_rows(ctx, exp, dict, nullptr, 0, M, keep_n, index_offset, job->d_sc, job->d_ix));
   }
@@ -137,11 +239,19 @@ int kdi_match_finish(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
     ctx->tm.d2h_bytes += (int64_t)M * keep_n * 12;
   }
   KDI_CUDA(ctx, cudaStreamSynchronize(st));
-  if (job->fused) ctx->tm.gemm_topk_ms += ev_ms(ctx->ev[8], ctx->ev[9]);  // last GEMM launch
+  if (job->fused) ctx->tm.gemm_topk_ms += ev_ms(ctx->ev[8], ctx->ev[9]);  // last GEMM launch / GEMM span
   ctx->tm.rescore_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
   ctx->tm.fallback_ms += ev_ms(ctx->ev[4], ctx->ev[5]);
   ctx->tm.flagged_rows += job->fused ? n_flag : M;
   return KDI_OK;
+}
+
+int kdi_match_finish(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
+                     const kdi_patterns* dict, int64_t index_offset) {
+  kdi_post post;
+  post.index_offset = index_offset;
+  KDI_TRY(kdi_match_select(ctx, job, exp, dict, post));
+  return kdi_match_complete(ctx, job, exp, dict, index_offset);
 }
 
 // match + top-k of device-resident pattern sets; outputs on host or device
@@ -150,6 +260,14 @@ int kdi_match_topk_device(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patte
                           int64_t* indices_out, int out_loc) {
   kdi_match_job job;
   KDI_TRY(kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, false, &job));
+  if (want_overlap(ctx, &job)) {
+    kdi_post post;
+    post.index_offset = index_offset;
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
+    int rc = run_overlapped(ctx, &job, exp, dict, post, 0, nullptr);
+    if (rc != KDI_OK) { sync_all_streams(ctx); return rc; }
+    return kdi_match_complete(ctx, &job, exp, dict, index_offset);
+  }
   KDI_TRY(kdi_match_advance(ctx, &job, exp, dict, dict->rows));
   return kdi_match_finish(ctx, &job, exp, dict, index_offset);
 }
@@ -252,15 +370,18 @@ int kdi_merge_topk(kdi_ctx* ctx, int64_t rows, int n_lists, int k_in, const floa
 
 }  // extern "C"
 
-// prepare experimental (once) + dictionary (streamed) and run the tensor-core pass over it.
-// On success *exp_out / *dict_out own the prepared sets and `job` is ready for kdi_match_finish
-// (or, candidates_only, for the selection kernel).
+// prepare experimental (once) + dictionary (streamed) and run the tensor-core pass and the
+// per-row post-processing (`post`: selection + rescoring, or the selection alone).  On success
+// *exp_out / *dict_out own the prepared sets, everything has been queued and the main stream
+// is ordered after all of it (ev[3] / ev[4] bracket the exposed post-processing); the caller
+// continues with kdi_match_complete (or, candidates_only, just synchronises).
 static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
                              int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
                              int64_t dict_rows, int64_t S, int metric, int keep_n,
                              const uint8_t* nav_mask, float* scores_out, int64_t* indices_out,
-                             int out_loc, bool candidates_only, kdi_match_job* job,
+                             int out_loc, kdi_post post, kdi_match_job* job,
                              kdi_patterns** exp_out, kdi_patterns** dict_out) {
+  const bool candidates_only = post.candidates_only;
   const size_t dsz = kdi_dtype_size(dict_dtype);
   if (!dsz || !kdi_dtype_size(exp_dtype)) return kdi_fail(ctx, KDI_EINVAL, "unknown dtype");
   if (dict_rows < 1 || exp_rows < 0 || S < 1) return kdi_fail(ctx, KDI_EINVAL, "bad shape");
@@ -270,28 +391,70 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   if (dict_loc != KDI_HOST && dict_loc != KDI_DEVICE) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location");
   cudaStream_t st = ctx->stream;
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+  const size_t row_bytes = (size_t)S * dsz;
+
+  kdi_patterns* dict = nullptr;
+  KDI_TRY(kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict));
+  // Device-resident dictionary, overlapped schedule: all but the first quarter of the dictionary
+  // is normalised on the low-priority stream by a small resident grid, starting now - beside the
+  // experimental normalisation, the first quarter and the tensor-core pass over that quarter.
+  int64_t g1_rows = dict_rows;
+  cudaEvent_t e_fill = nullptr;
+  const bool early = ctx->overlap && dict_loc == KDI_DEVICE && !ctx->force_exact &&
+                     kdi_gemm_kc_for(keep_n) != 0 &&
+                     (ctx->overlap == 2 ? dict_rows >= 4 * KDI_TILE_N : (dict_rows >= 16384 && exp_rows >= 2048));
+  if (early) {
+    g1_rows = dict_rows / 4 / KDI_TILE_N * KDI_TILE_N;
+    cudaEvent_t e0 = ctx->dep_ev[63];
+    e_fill = ctx->dep_ev[62];
+    cudaError_t e = cudaEventRecord(e0, st);  // the caller's buffers may have been produced on this stream
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, e0, 0);
+    int rc = e == cudaSuccess ? KDI_OK : kdi_fail(ctx, KDI_ECUDA, "stream setup failed: %s", cudaGetErrorString(e));
+    if (rc == KDI_OK)
+      rc = kdi_patterns_fill(ctx, ctx->aux_stream, dict, g1_rows,
+                             reinterpret_cast<const uint8_t*>(dictionary) + (size_t)g1_rows * row_bytes,
+                             dict_dtype, dict_rows - g1_rows, nullptr, 4 * ctx->sm_count);
+    if (rc == KDI_OK && cudaEventRecord(e_fill, ctx->aux_stream) != cudaSuccess)
+      rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+    if (rc != KDI_OK) {
+      sync_all_streams(ctx);
+      const std::string err = ctx->err;
+      kdi_patterns_destroy(ctx, dict);
+      ctx->err = err;
+      return rc;
+    }
+  }
 
   // prepare_experimental - once (_dictionary_indexing.py:70)
   kdi_patterns* exp = nullptr;
-  KDI_TRY(kdi_patterns_create(ctx, experimental, exp_loc, exp_dtype, exp_rows, S, metric, nav_mask, &exp));
-  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+  int rc = kdi_patterns_create(ctx, experimental, exp_loc, exp_dtype, exp_rows, S, metric, nav_mask, &exp);
+  if (rc == KDI_OK && cudaEventRecord(ctx->ev[6], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
 
   // prepare_dictionary + match, streamed.  The reference prepares and matches one chunk of
   // n_per_iteration rows per iteration (_dictionary_indexing.py:102-128); the result does not
   // depend on the chunking, so the pieces moved here are sized for the copy engine (64 MB) and the
   // tensor-core pass runs over every group of pieces as soon as it has been normalised, while
   // the next pieces are still in flight on the copy stream.
-  kdi_patterns* dict = nullptr;
-  int rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict);
   if (rc == KDI_OK)
     rc = kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, candidates_only, job);
   if (rc == KDI_OK) {
     if (dict_loc == KDI_DEVICE) {
-      rc = kdi_patterns_fill(ctx, st, dict, 0, dictionary, dict_dtype, dict_rows, nullptr);
+      rc = kdi_patterns_fill(ctx, st, dict, 0, dictionary, dict_dtype, g1_rows, nullptr);
       if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
-      if (rc == KDI_OK) rc = kdi_match_advance(ctx, job, exp, dict, dict_rows);
+      if (rc == KDI_OK && job->M > 0 && job->fused && want_overlap(ctx, job)) {
+        // first quarter against every row block, then the row-block groups over the rest
+        if (cudaEventRecord(ctx->ev[8], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+        const int64_t strip_rows = (int64_t)job->plan.strip_tiles * KDI_TILE_N;
+        int strips_lo = g1_rows >= dict_rows ? 0 : (int)(g1_rows / strip_rows);
+        if (rc == KDI_OK && strips_lo > 0)
+          rc = kdi_launch_gemm_topk(ctx, st, exp, dict, &job->plan, 0, strips_lo, job->cand, job->thr);
+        if (rc == KDI_OK) rc = run_overlapped(ctx, job, exp, dict, post, strips_lo, e_fill);
+      } else if (rc == KDI_OK) {
+        if (e_fill && cudaStreamWaitEvent(st, e_fill, 0) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream wait failed");
+        if (rc == KDI_OK) rc = kdi_match_advance(ctx, job, exp, dict, dict_rows);
+        if (rc == KDI_OK) rc = kdi_match_select(ctx, job, exp, dict, post);
+      }
     } else {
-      const size_t row_bytes = (size_t)S * dsz;
       int64_t piece = (int64_t)std::max<size_t>(1, (64u << 20) / row_bytes);
       piece = std::min<int64_t>(piece, dict_rows);
       const size_t slot_bytes = align_up((size_t)piece * row_bytes, 256);
@@ -329,11 +492,11 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
           next_advance = ready + group_rows;
         }
       }
+      if (rc == KDI_OK) rc = kdi_match_select(ctx, job, exp, dict, post);
     }
   }
   if (rc != KDI_OK) {
-    cudaStreamSynchronize(st);
-    cudaStreamSynchronize(ctx->copy_stream);
+    sync_all_streams(ctx);
     const std::string err = ctx->err;
     kdi_patterns_destroy(ctx, exp);
     kdi_patterns_destroy(ctx, dict);
@@ -365,24 +528,27 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
   (void)n_per_iteration;  // accepted for interface parity; transfers are sized internally
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
   ctx->tm = kdi_timings();
+  kdi_timeline_reset(ctx);
   kdi_patterns *exp = nullptr, *dict = nullptr;
   kdi_match_job job;
+  kdi_post post;
+  post.index_offset = index_offset;
   KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dictionary, dict_loc,
                             dict_dtype, dict_rows, S, metric, keep_n, nav_mask, scores_out, indices_out,
-                            out_loc, false, &job, &exp, &dict));
+                            out_loc, post, &job, &exp, &dict));
   cudaStream_t st = ctx->stream;
-  int rc = kdi_match_finish(ctx, &job, exp, dict, index_offset);
+  int rc = kdi_match_complete(ctx, &job, exp, dict, index_offset);
   if (rc == KDI_OK) {
     cudaEventRecord(ctx->ev[1], st);
     if (cudaStreamSynchronize(st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
   } else {
-    cudaStreamSynchronize(st);
-    cudaStreamSynchronize(ctx->copy_stream);
+    sync_all_streams(ctx);
   }
   if (rc == KDI_OK) {
     ctx->tm.normalize_exp_ms = ev_ms(ctx->ev[0], ctx->ev[6]);
     ctx->tm.normalize_dict_ms = ev_ms(ctx->ev[6], ctx->ev[7]);
     ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+    kdi_timeline_print(ctx);
   }
   const std::string err = ctx->err;
   kdi_patterns_destroy(ctx, exp);
@@ -407,17 +573,17 @@ int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, in
   ctx->tm = kdi_timings();
   kdi_patterns *exp = nullptr, *dict = nullptr;
   kdi_match_job job;
+  kdi_post post;
+  post.candidates_only = true;
+  post.index_offset = index_offset;
+  post.approx_out = approx_out;
+  post.gidx_out = gidx_out;
   KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dictionary, dict_loc,
                             dict_dtype, dict_rows, S, metric, keep_n, nav_mask, nullptr, nullptr,
-                            KDI_DEVICE, true, &job, &exp, &dict));
+                            KDI_DEVICE, post, &job, &exp, &dict));
   cudaStream_t st = ctx->stream;
   int rc = KDI_OK;
-  if (job.plan.kc != kc) rc = kdi_fail(ctx, KDI_EINTERNAL, "candidate capacity mismatch");
-  cudaEventRecord(ctx->ev[3], st);
-  if (rc == KDI_OK)
-    rc = kdi_launch_select_only(ctx, st, exp->rows, &job.plan, job.cand, job.thr, index_offset,
-                                1.0f / (KDI_OP_SCALE * KDI_OP_SCALE), approx_out, gidx_out);
-  cudaEventRecord(ctx->ev[4], st);
+  if (job.M > 0 && job.plan.kc != kc) rc = kdi_fail(ctx, KDI_EINTERNAL, "candidate capacity mismatch");
   cudaEventRecord(ctx->ev[1], st);
   if (cudaStreamSynchronize(st) != cudaSuccess && rc == KDI_OK) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
   if (rc != KDI_OK) {

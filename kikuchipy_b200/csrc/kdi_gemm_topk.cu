@@ -38,7 +38,8 @@ constexpr int kABytes = KDI_TILE_M * KDI_TILE_K * 2;  // 16 KB
 struct GemmParams {
   int64_t M, N;
   int kblocks;      // kp / 64
-  int m_blocks;     // row blocks of 128*CG rows
+  int m_blocks;     // row blocks of 128*CG rows covered by this launch
+  int mb0;          // first row block of this launch
   int n_tiles;      // N tiles of 256 rows
   int strip_tiles;  // N tiles per unit
   int n_strips;     // strips of the whole dictionary (candidate-list layout)
@@ -78,7 +79,7 @@ __device__ __forceinline__ void decode_unit(const GemmParams& p, int64_t u, int&
   const int rem = (int)(u - (int64_t)sb * units_per_sb);
   const int sb_blocks = min(p.superblock, p.m_blocks - sb * p.superblock);
   strip = p.strip0 + rem / sb_blocks;
-  mb = sb * p.superblock + rem % sb_blocks;
+  mb = p.mb0 + sb * p.superblock + rem % sb_blocks;
 }
 
 // MODE 0: candidate selection; MODE 1: write the full block (validation only)
@@ -386,6 +387,9 @@ int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
   const size_t smem = 1024 + (size_t)p.stages * kStageBytes + kListBytes + (2 * p.stages + 4) * 8 + 16;
   auto kern = kdi_gemm_kernel<CG, KC, MODE>;
   KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (experiments with SM sharing: see kdi_gemm_carveout_pref)
+  if (kdi_gemm_carveout_pref() >= 0)
+    KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_gemm_carveout_pref()));
   const int64_t max_clusters = ctx->sm_count / CG;
   const int64_t n_clusters = p.units < max_clusters ? p.units : max_clusters;
   cudaLaunchConfig_t cfg = {};
@@ -400,7 +404,10 @@ int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  KDI_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  {
+    kdi_span span(ctx, stream, "gemm_topk");
+    KDI_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  }
   ctx->tm.kernel_launches++;
   ctx->tm.gemm_launches++;
   return KDI_OK;
@@ -491,9 +498,12 @@ static int check_operands(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patte
 
 int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
                          const kdi_patterns* dict, const kdi_gemm_plan* plan, int strip0,
-                         int strip_count, uint2* cand, uint32_t* thr) {
+                         int strip_count, uint2* cand, uint32_t* thr, int mb0, int mb_count) {
   if (strip0 < 0 || strip_count < 1 || strip0 + strip_count > plan->n_strips)
     return kdi_fail(ctx, KDI_EINTERNAL, "GEMM strip range out of bounds");
+  if (mb_count < 0) mb_count = plan->m_blocks - mb0;
+  if (mb0 < 0 || mb_count < 1 || mb0 + mb_count > plan->m_blocks)
+    return kdi_fail(ctx, KDI_EINTERNAL, "GEMM row-block range out of bounds");
   KDI_TRY(check_operands(ctx, exp, dict));
   const int cg = plan->cta_group;
   CUtensorMap tmA, tmB;
@@ -503,14 +513,15 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   p.M = exp->rows;
   p.N = dict->rows;
   p.kblocks = (int)(exp->kp / KDI_TILE_K);
-  p.m_blocks = plan->m_blocks;
+  p.m_blocks = mb_count;
+  p.mb0 = mb0;
   p.n_tiles = plan->n_tiles;
   p.strip_tiles = plan->strip_tiles;
   p.n_strips = plan->n_strips;
   p.strip0 = strip0;
   p.launch_strips = strip_count;
-  p.superblock = plan->superblock;
-  p.units = (int64_t)plan->m_blocks * strip_count;
+  p.superblock = plan->superblock < mb_count ? plan->superblock : mb_count;
+  p.units = (int64_t)mb_count * strip_count;
   p.stages = plan->stages;
   p.fmt = exp->compute_dtype;
   p.l2_policy = ctx->l2_policy;

@@ -48,9 +48,9 @@ __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_generic(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
                       const int32_t* __restrict__ cols, int64_t s_eff, int metric,
                       float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
-                      int64_t kp) {
+                      int64_t kp, int64_t n_rows) {
   __shared__ double red[kNormThreads / 32];
-  const int64_t row = blockIdx.x;
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
   const int64_t srow = rowmap ? rowmap[row] : row;
   const T* x = src + srow * S;
   float mean = 0.f;
@@ -77,6 +77,7 @@ kdi_normalize_generic(const T* __restrict__ src, int64_t S, const int64_t* __res
     o16[j] = to16<BF16>(v);
   }
   // s_pitch <= kp always (kp is s_eff rounded up to 64, s_pitch to 4)
+  }
 }
 
 // fast path: float32 source, no gathers, S % 4 == 0: the row lives in registers (one HBM read)
@@ -84,9 +85,9 @@ template <int V, bool BF16>
 __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_f32_regs(const float* __restrict__ src, int64_t S, int metric,
                        float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
-                       int64_t kp) {
+                       int64_t kp, int64_t n_rows) {
   __shared__ double red[kNormThreads / 32];
-  const int64_t row = blockIdx.x;
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
   const float4* x = reinterpret_cast<const float4*>(src + row * S);
   const int n4 = (int)(S >> 2);
   float4 r[V];
@@ -132,33 +133,46 @@ kdi_normalize_f32_regs(const float* __restrict__ src, int64_t S, int metric,
   }
   // zero the K padding of the 16-bit row (s_pitch == S here)
   for (int64_t j = S + threadIdx.x; j < kp; j += kNormThreads) a16[row * kp + j] = 0;
+  }
+}
+
+// The SM's L1 / shared-memory split is reconfigured only when the SM is idle, so a kernel can run
+// beside the GEMM kernel only if both ask for the same split (see kdi_carveout_pref; off by
+// default because sharing SMs with the GEMM kernel did not pay).
+template <typename K>
+void prefer_max_shared(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_carveout_pref());
 }
 
 template <typename T>
 int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_t* rowmap,
                    const int32_t* cols, int64_t rows, int64_t s_eff, int metric, int bf16,
-                   float* a32, int64_t s_pitch, void* a16, int64_t kp) {
+                   float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid) {
   const T* s = reinterpret_cast<const T*>(src);
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
+  static bool once = (prefer_max_shared(kdi_normalize_generic<T, true>), prefer_max_shared(kdi_normalize_generic<T, false>), true);
+  (void)once;
   if (bf16)
-    kdi_normalize_generic<T, true><<<(unsigned)rows, kNormThreads, 0, stream>>>(
-        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp);
+    kdi_normalize_generic<T, true><<<grid, kNormThreads, 0, stream>>>(
+        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
   else
-    kdi_normalize_generic<T, false><<<(unsigned)rows, kNormThreads, 0, stream>>>(
-        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp);
+    kdi_normalize_generic<T, false><<<grid, kNormThreads, 0, stream>>>(
+        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
   return 0;
 }
 
 template <int V>
 void launch_regs(cudaStream_t stream, const float* src, int64_t S, int64_t rows, int metric,
-                 int bf16, float* a32, int64_t s_pitch, void* a16, int64_t kp) {
+                 int bf16, float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid) {
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
+  static bool once = (prefer_max_shared(kdi_normalize_f32_regs<V, true>), prefer_max_shared(kdi_normalize_f32_regs<V, false>), true);
+  (void)once;
   if (bf16)
-    kdi_normalize_f32_regs<V, true><<<(unsigned)rows, kNormThreads, 0, stream>>>(
-        src, S, metric, a32, s_pitch, o16, kp);
+    kdi_normalize_f32_regs<V, true><<<grid, kNormThreads, 0, stream>>>(
+        src, S, metric, a32, s_pitch, o16, kp, rows);
   else
-    kdi_normalize_f32_regs<V, false><<<(unsigned)rows, kNormThreads, 0, stream>>>(
-        src, S, metric, a32, s_pitch, o16, kp);
+    kdi_normalize_f32_regs<V, false><<<grid, kNormThreads, 0, stream>>>(
+        src, S, metric, a32, s_pitch, o16, kp, rows);
 }
 
 }  // namespace
@@ -166,38 +180,41 @@ void launch_regs(cudaStream_t stream, const float* src, int64_t S, int64_t rows,
 int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int src_dtype,
                          int64_t S, const int64_t* d_rowmap, const int32_t* d_cols, int64_t rows,
                          int64_t s_eff, int metric, int compute_dtype, float* a32, int64_t s_pitch,
-                         void* a16, int64_t kp) {
+                         void* a16, int64_t kp, int max_ctas) {
   if (rows <= 0) return KDI_OK;
   if (rows > 0x7fffffffLL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "too many rows in one pattern set");
+  // max_ctas > 0: a small resident grid that loops over the rows (runs beside the GEMM kernel)
+  const unsigned grid = (unsigned)((max_ctas > 0 && rows > max_ctas) ? max_ctas : rows);
   const int bf16 = compute_dtype == 1;
   const bool plain = !d_rowmap && !d_cols && s_eff == S;
+  kdi_span span(ctx, stream, max_ctas > 0 ? "normalize (resident grid)" : "normalize");
   if (src_dtype == KDI_F32 && plain && (S % 4) == 0 && s_pitch == S &&
       (reinterpret_cast<uintptr_t>(src) % 16) == 0 && S <= 16 * 4 * kNormThreads) {
     const float* s = reinterpret_cast<const float*>(src);
     const int64_t n4 = S / 4;
     const int v = (int)kdi_ceil_div(n4, kNormThreads);
-    if (v <= 1) launch_regs<1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
-    else if (v <= 2) launch_regs<2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
-    else if (v <= 4) launch_regs<4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
-    else if (v <= 8) launch_regs<8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
-    else launch_regs<16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp);
+    if (v <= 1) launch_regs<1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+    else if (v <= 2) launch_regs<2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+    else if (v <= 4) launch_regs<4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+    else if (v <= 8) launch_regs<8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+    else launch_regs<16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
   } else {
     switch (src_dtype) {
       case KDI_U8:
         launch_generic<uint8_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                s_pitch, a16, kp);
+                                s_pitch, a16, kp, grid);
         break;
       case KDI_U16:
         launch_generic<uint16_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                 s_pitch, a16, kp);
+                                 s_pitch, a16, kp, grid);
         break;
       case KDI_F32:
         launch_generic<float>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                              s_pitch, a16, kp);
+                              s_pitch, a16, kp, grid);
         break;
       case KDI_F64:
         launch_generic<double>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                               s_pitch, a16, kp);
+                               s_pitch, a16, kp, grid);
         break;
       default:
         return kdi_fail(ctx, KDI_EINVAL, "unknown source dtype %d", src_dtype);

@@ -150,7 +150,7 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
                           const uint32_t* __restrict__ thr, int n_strips, int keep_n,
                           int64_t index_offset, float inv_scale, float cert_sigmas,
                           float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
-                          int* __restrict__ flag_list, int* __restrict__ n_flag) {
+                          int* __restrict__ flag_list, int* __restrict__ n_flag, int64_t row0) {
   __shared__ uint64_t keys[kSelBuf];
   __shared__ float ex[KC];
   __shared__ float ap[KC];
@@ -159,7 +159,7 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   __shared__ float s_red[4];
   __shared__ float s_ek;
 
-  const int64_t row = blockIdx.x;
+  const int64_t row = row0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // 1+2. the kc best candidates by tensor-core score
   const int64_t total = (int64_t)n_strips * KC;
@@ -258,10 +258,10 @@ template <int KC>
 __global__ void __launch_bounds__(kSelThreads)
 kdi_select_only_kernel(const uint2* __restrict__ cand, const uint32_t* __restrict__ thr, int n_strips,
                        int64_t index_offset, float inv_scale, float* __restrict__ out_approx,
-                       int64_t* __restrict__ out_gidx) {
+                       int64_t* __restrict__ out_gidx, int64_t row0) {
   __shared__ uint64_t keys[kSelBuf];
   __shared__ int s_count;
-  const int64_t row = blockIdx.x;
+  const int64_t row = row0 + blockIdx.x;
   const int64_t total = (int64_t)n_strips * KC;
   const int nsel = select_candidates<KC>(cand + row * total, total, thr[row], keys, &s_count);
   const int tid = threadIdx.x;
@@ -486,17 +486,24 @@ int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patte
                               const kdi_patterns* dict, const kdi_gemm_plan* plan,
                               const uint2* cand, const uint32_t* thr, int keep_n,
                               int64_t index_offset, float approx_inv_scale, float cert_sigmas,
-                              float* out_scores, int64_t* out_idx, int* flag_list, int* n_flag) {
-  if (exp->rows <= 0) return KDI_OK;
-  const unsigned grid = (unsigned)exp->rows;
+                              float* out_scores, int64_t* out_idx, int* flag_list, int* n_flag,
+                              int64_t row0, int64_t n_rows) {
+  if (n_rows < 0) n_rows = exp->rows - row0;
+  if (n_rows <= 0) return KDI_OK;
+  const unsigned grid = (unsigned)n_rows;
+  // (carveout preference: experiments with SM sharing, see kdi_carveout_pref)
+  static bool once = (cudaFuncSetAttribute(kdi_select_rescore_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_carveout_pref()),
+                      cudaFuncSetAttribute(kdi_select_rescore_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_carveout_pref()), true);
+  (void)once;
+  kdi_span span(ctx, stream, "select_rescore");
   if (plan->kc == 32)
     kdi_select_rescore_kernel<32><<<grid, kSelThreads, 0, stream>>>(
         exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
-        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag);
+        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0);
   else if (plan->kc == 64)
     kdi_select_rescore_kernel<64><<<grid, kSelThreads, 0, stream>>>(
         exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
-        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag);
+        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0);
   else
     return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
   KDI_CUDA(ctx, cudaGetLastError());
@@ -539,14 +546,20 @@ int kdi_launch_extract_topk(kdi_ctx* ctx, cudaStream_t stream, const float* scor
 
 int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, const kdi_gemm_plan* plan,
                            const uint2* cand, const uint32_t* thr, int64_t index_offset,
-                           float approx_inv_scale, float* out_approx, int64_t* out_gidx) {
-  if (rows <= 0) return KDI_OK;
+                           float approx_inv_scale, float* out_approx, int64_t* out_gidx,
+                           int64_t row0, int64_t n_rows) {
+  if (n_rows < 0) n_rows = rows - row0;
+  if (n_rows <= 0) return KDI_OK;
+  static bool once = (cudaFuncSetAttribute(kdi_select_only_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_carveout_pref()),
+                      cudaFuncSetAttribute(kdi_select_only_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_carveout_pref()), true);
+  (void)once;
+  kdi_span span(ctx, stream, "select_only");
   if (plan->kc == 32)
-    kdi_select_only_kernel<32><<<(unsigned)rows, kSelThreads, 0, stream>>>(
-        cand, thr, plan->n_strips, index_offset, approx_inv_scale, out_approx, out_gidx);
+    kdi_select_only_kernel<32><<<(unsigned)n_rows, kSelThreads, 0, stream>>>(
+        cand, thr, plan->n_strips, index_offset, approx_inv_scale, out_approx, out_gidx, row0);
   else if (plan->kc == 64)
-    kdi_select_only_kernel<64><<<(unsigned)rows, kSelThreads, 0, stream>>>(
-        cand, thr, plan->n_strips, index_offset, approx_inv_scale, out_approx, out_gidx);
+    kdi_select_only_kernel<64><<<(unsigned)n_rows, kSelThreads, 0, stream>>>(
+        cand, thr, plan->n_strips, index_offset, approx_inv_scale, out_approx, out_gidx, row0);
   else
     return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
   KDI_CUDA(ctx, cudaGetLastError());

@@ -24,9 +24,11 @@ SCORE_TOL = 1e-4
 def ctx():
     c = kb.default_context(0)
     yield c
-    for opt in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK):
+    for opt in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK,
+                _lib.OPT_MAX_STAGES):
         c.set_option(opt, 0)
     c.set_option(_lib.OPT_CTA_GROUP, 2)
+    c.set_option(_lib.OPT_OVERLAP, 1)
     c.set_signal_mask(None)
 
 
@@ -185,6 +187,51 @@ def test_fused_and_exact_paths_agree_bit_for_bit(ctx):
     assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
 
 
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_overlapped_schedule_equals_serial(ctx, cta_group):
+    """The overlapped schedule (dictionary normalisation on the auxiliary stream, one tensor-core
+    launch per row-block group on alternating streams, rescoring of finished groups beside the
+    next launch) must give bit-identical results to one-kernel-at-a-time execution - for the full
+    pipeline, for pre-normalised pattern sets (kdi_match_topk) and for the candidate stage of the
+    sharded pipeline."""
+    import torch
+
+    M, N, sig, k = 1500, 7000, (30, 30), 20
+    exp = torch.from_numpy(orc.synthetic_experimental(M, sig, seed=5)).cuda()
+    dic = torch.from_numpy(orc.synthetic_dictionary(N, sig, seed=6)).cuda()
+    ctx.set_option(_lib.OPT_CTA_GROUP, cta_group)
+    ctx.set_option(_lib.OPT_SUPERBLOCK, 2)
+    ctx.set_option(_lib.OPT_STRIP_TILES, 3)
+    out = {}
+    try:
+        for mode in (0, 2):
+            ctx.set_option(_lib.OPT_OVERLAP, mode)
+            idx = torch.empty((M, k), dtype=torch.int64, device="cuda")
+            sc = torch.empty((M, k), dtype=torch.float32, device="cuda")
+            ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, k, out=(idx, sc))
+            launches = ctx.timings()["gemm_launches"]
+            e = ctx.patterns(exp, M, _lib.KDI_NCC)
+            d = ctx.patterns(dic, N, _lib.KDI_NCC)
+            i2, s2 = ctx.match_topk(e, d, k)
+            shard, approx, gidx = ctx.shard_candidates(exp, M, dic, N, _lib.KDI_NCC, k, index_offset=100)
+            out[mode] = (idx.cpu().numpy(), sc.cpu().numpy(), i2, s2, approx.cpu().numpy(), gidx.cpu().numpy(), launches)
+            shard.close(); e.close(); d.close()
+    finally:
+        ctx.set_option(_lib.OPT_OVERLAP, 1)
+        ctx.set_option(_lib.OPT_SUPERBLOCK, 0)
+        ctx.set_option(_lib.OPT_STRIP_TILES, 0)
+        ctx.set_option(_lib.OPT_CTA_GROUP, 2)
+    assert out[0][6] == 1 and out[2][6] >= 3  # one launch vs first slice + one per row-block group
+    for a, b in zip(out[0][:4], out[2][:4]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out[0][0], out[0][2]) and np.array_equal(out[0][1], out[0][3])
+    # candidate lists: the tensor-core scores do not depend on the schedule (an exact tie at the
+    # kc-th place may keep either index)
+    assert np.array_equal(out[0][4], out[2][4]) and np.mean(out[0][5] == out[2][5]) > 0.999
+    ridx, rsc = orc.dictionary_indexing(exp.cpu().numpy(), dic.cpu().numpy(), keep_n=k)
+    _check(ridx, rsc, out[2][0], out[2][1])
+
+
 def test_duplicate_dictionary_rows_fall_back_to_exact(ctx):
     """Exact ties across the candidate boundary: the certificate must flag the rows and the exact
     path must order ties by ascending index."""
@@ -338,7 +385,7 @@ def test_config2_full_size_properties(ctx):
     for cg in (1, 2):
         ctx.set_option(_lib.OPT_CTA_GROUP, cg)
         ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, k, out=(idx, sc))
-        assert ctx.timings()["gemm_launches"] == 1
+        assert ctx.timings()["gemm_launches"] >= 1
         assert torch.equal(idx[:, 0], j)
         assert bool((sc[:, :-1] >= sc[:, 1:]).all())
         assert int(idx.min()) >= 0 and int(idx.max()) < N
@@ -423,7 +470,7 @@ def _full_size_properties(ctx, M, N, sig, k, metric, smask):
     finally:
         ctx.set_signal_mask(None)
     tm = ctx.timings()
-    assert tm["gemm_launches"] == 1
+    assert tm["gemm_launches"] >= 1
     assert torch.equal(idx[:, 0], j)
     assert bool((sc[:, :-1] >= sc[:, 1:]).all())
     assert int(idx.min()) >= 0 and int(idx.max()) < N
