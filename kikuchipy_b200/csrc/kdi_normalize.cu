@@ -80,6 +80,55 @@ kdi_normalize_generic(const T* __restrict__ src, int64_t S, const int64_t* __res
   }
 }
 
+// staged path: any source type, optional gathers, the (compacted, float32) row is staged in
+// shared memory by ONE pass over global memory; the two reduction passes and the output pass
+// read shared memory.  Same per-thread summation order as the generic kernel (bit-identical
+// results); used whenever the compacted row fits in shared memory.
+template <typename T, bool BF16>
+__global__ void __launch_bounds__(kNormThreads)
+kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
+                     const int32_t* __restrict__ cols, int64_t s_eff, int metric,
+                     float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
+                     int64_t kp, int64_t n_rows) {
+  extern __shared__ float v[];  // s_eff floats
+  __shared__ double red[kNormThreads / 32];
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int64_t srow = rowmap ? rowmap[row] : row;
+    const T* x = src + srow * S;
+    __syncthreads();  // the previous row's output pass has finished reading v
+    for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) v[j] = (float)x[cols ? cols[j] : j];
+    __syncthreads();
+    float mean = 0.f;
+    if (metric == KDI_NCC) {
+      double s = 0.0;
+      for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) s += (double)v[j];
+      s = block_sum(s, red);
+      mean = (float)(s / (double)s_eff);
+    }
+    double ss = 0.0;
+    for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) {
+      const float c = v[j] - mean;
+      ss += (double)c * (double)c;
+    }
+    ss = block_sum(ss, red);
+    const float norm = (float)sqrt(ss);
+    float* o32 = a32 + row * s_pitch;
+    uint16_t* o16 = a16 + row * kp;
+    // four outputs per thread and step: 16-byte fp32 stores, 8-byte 16-bit stores (pitches are
+    // multiples of 4 and the buffers 256-byte aligned)
+    for (int64_t j = 4 * (int64_t)threadIdx.x; j < kp; j += 4 * kNormThreads) {
+      float o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? (v[j + q] - mean) / norm : 0.f;
+      if (j < s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+      uint2 h;
+      h.x = (uint32_t)to16<BF16>(o[0]) | ((uint32_t)to16<BF16>(o[1]) << 16);
+      h.y = (uint32_t)to16<BF16>(o[2]) | ((uint32_t)to16<BF16>(o[3]) << 16);
+      *reinterpret_cast<uint2*>(o16 + j) = h;
+    }
+  }
+}
+
 // fast path: float32 source, no gathers, S % 4 == 0: the row lives in registers (one HBM read)
 template <int V, bool BF16>
 __global__ void __launch_bounds__(kNormThreads)
@@ -150,6 +199,20 @@ int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_
                    float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid) {
   const T* s = reinterpret_cast<const T*>(src);
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
+  const size_t stage_bytes = (size_t)s_eff * sizeof(float);
+  if (stage_bytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(a32) % 16) == 0 &&
+      (reinterpret_cast<uintptr_t>(a16) % 8) == 0) {
+    static bool once_s = (cudaFuncSetAttribute(kdi_normalize_staged<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                          cudaFuncSetAttribute(kdi_normalize_staged<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
+    (void)once_s;
+    if (bf16)
+      kdi_normalize_staged<T, true><<<grid, kNormThreads, stage_bytes, stream>>>(
+          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
+    else
+      kdi_normalize_staged<T, false><<<grid, kNormThreads, stage_bytes, stream>>>(
+          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
+    return 0;
+  }
   static bool once = (prefer_max_shared(kdi_normalize_generic<T, true>), prefer_max_shared(kdi_normalize_generic<T, false>), true);
   (void)once;
   if (bf16)
