@@ -1,0 +1,429 @@
+// K6: dictionary GENERATION on the device - project a square-Lambert master pattern onto the
+// detector for a set of crystal rotations - optionally fused with K1 (the dictionary-side
+// prepare step), so that a generated dictionary never exists in HBM as raw float32 patterns.
+//
+// Replaces /root/reference/src/kikuchipy/signals/util/_master_pattern.py
+//   :299-370  _project_patterns_from_master_pattern_with_fixed_pc
+//   :449-527  _project_single_pattern_from_master_pattern (rotate, Lambert, bilinear, rescale)
+//   :531-568  _vector2lambert, :580-678 _get_lambert_interpolation_parameters,
+//   :682-708  _get_pixel_from_master_pattern
+// and _utils/numba.py:62-81 rotate_vector, pattern/_pattern.py:97-111 _rescale_with_min_max -
+// the work `dictionary_chunk.compute()` does inside the reference's DI loop for a lazy
+// dictionary (indexing/_dictionary_indexing.py:106-108).  All coordinate arithmetic is float64
+// like the reference's; the pattern is cast to float32 (dtype_out) before normalisation, which
+// is the order the reference uses (get_patterns -> float32 dictionary -> prepare_dictionary).
+//
+// One CTA per rotation (grid-stride): direction cosines (S x 3 doubles, L2-resident) are rotated,
+// projected, the four master-pattern neighbours are gathered from L1/L2 (the master pattern is a
+// few MB), the pattern is staged in shared memory, then either written out as float32 or
+// normalised exactly as kdi_normalize_staged does.  Bound: fp64 pipe (about 300 double operations
+// per pixel), not HBM.
+#include "kdi_internal.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int kProjThreads = 256;
+constexpr double kSqrtPi = 1.7724538509055160273;         // sqrt(pi)
+constexpr double kSqrtPiHalf = 1.2533141373155002512;     // sqrt(pi / 2)
+constexpr double kSqrtPiOver2 = 0.88622692545275801365;   // sqrt(pi) / 2
+constexpr double kTwoOverSqrtPi = 1.1283791670955125739;  // 2 / sqrt(pi)
+
+struct ProjParams {
+  const double* rot;  // n x 4 (a, b, c, d)
+  const double* dc;   // S x 3
+  const void* upper;  // npy x npx, MT
+  const void* lower;
+  int npx, npy;       // as the reference passes them (npx bounds the row index, npy the column index)
+  int ld;             // row pitch of the master pattern arrays (elements)
+  double scale;
+  int rescale;
+  double out_min, out_max;
+  int64_t S;
+  int64_t n_rows;
+  // raw output
+  float* out;  // n x S (or NULL)
+  // fused normalisation (or a32 == NULL)
+  const int32_t* cols;
+  int64_t s_eff;
+  int metric;
+  float* a32;
+  int64_t s_pitch;
+  uint16_t* a16;
+  int64_t kp;
+};
+
+__device__ __forceinline__ double block_reduce_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kProjThreads / 32; ++w) t += red[w];
+  return t;
+}
+
+__device__ __forceinline__ void block_reduce_minmax(double& lo, double& hi, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { red[warp] = lo; red[8 + warp] = hi; }
+  __syncthreads();
+  lo = red[0]; hi = red[8];
+#pragma unroll
+  for (int w = 1; w < kProjThreads / 32; ++w) { lo = fmin(lo, red[w]); hi = fmax(hi, red[8 + w]); }
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint16_t op16(float v) {
+  if constexpr (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v * KDI_OP_SCALE));
+  else return __half_as_ushort(__float2half_rn(v * KDI_OP_SCALE));
+}
+
+// intensity of one detector pixel for one rotation (float64, as the reference computes it)
+template <typename MT>
+__device__ __forceinline__ double project_pixel(const ProjParams& p, const double (&m)[9], double vx,
+                                                double vy, double vz) {
+  // rotate_vector (_utils/numba.py:78-80) with the products precomputed per rotation
+  const double x = m[0] * vx + 2.0 * (m[1] * vz + m[2] * vy);
+  const double y = m[3] * vy + 2.0 * (m[4] * vx + m[5] * vz);
+  const double z = m[6] * vz + 2.0 * (m[7] * vy + m[8] * vx);
+  // _vector2lambert (:541-566)
+  const double inv = 1.0 / sqrt(x * x + y * y + z * z);
+  const double wx = x * inv, wy = y * inv, wz = z * inv;
+  const double abs_z = fabs(wz);
+  const double sqrt_z = sqrt(2.0 * (1.0 - abs_z));
+  double lx = 0.0, ly = 0.0;
+  if (abs_z != 1.0) {
+    if (fabs(wy) <= fabs(wx)) {
+      const double s = (wx > 0.0) ? 1.0 : ((wx < 0.0) ? -1.0 : 0.0);
+      lx = s * sqrt_z * kSqrtPiOver2;
+      ly = s * sqrt_z * kTwoOverSqrtPi * atan(wy / wx);
+    } else {
+      const double s = (wy > 0.0) ? 1.0 : ((wy < 0.0) ? -1.0 : 0.0);
+      lx = s * sqrt_z * kTwoOverSqrtPi * atan(wx / wy);
+      ly = s * sqrt_z * kSqrtPiOver2;
+    }
+  }
+  // _get_lambert_interpolation_parameters (:638-676)
+  const double i_this = p.scale * ly / kSqrtPiHalf;
+  const double j_this = p.scale * lx / kSqrtPiHalf;
+  int nii = (int)(i_this + p.scale);  // truncation towards zero, like np.int32(float)
+  int nij = (int)(j_this + p.scale);
+  int niip = nii + 1, nijp = nij + 1;
+  if (niip >= p.npx) niip = nii;
+  if (nijp >= p.npy) nijp = nij;
+  if (nii < 0) nii = niip;
+  if (nij < 0) nij = nijp;
+  const double di = i_this - (double)nii + p.scale;
+  const double dj = j_this - (double)nij + p.scale;
+  const double dim = 1.0 - di, djm = 1.0 - dj;
+  // _get_pixel_from_master_pattern (:703-708), hemisphere by the sign of the ROTATED z (:506)
+  const MT* mp = reinterpret_cast<const MT*>(z >= 0.0 ? p.upper : p.lower);
+  const double v00 = (double)__ldg(mp + (int64_t)nii * p.ld + nij);
+  const double v10 = (double)__ldg(mp + (int64_t)niip * p.ld + nij);
+  const double v01 = (double)__ldg(mp + (int64_t)nii * p.ld + nijp);
+  const double v11 = (double)__ldg(mp + (int64_t)niip * p.ld + nijp);
+  return v00 * dim * djm + v10 * di * djm + v01 * dim * dj + v11 * di * dj;
+}
+
+template <typename MT, bool BF16>
+__global__ void __launch_bounds__(kProjThreads)
+kdi_project_kernel(const ProjParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  // [S floats: pattern as float32] [S doubles: only when rescaling]
+  float* v = reinterpret_cast<float*>(smem_raw);
+  double* vd = reinterpret_cast<double*>(smem_raw + ((p.S * sizeof(float) + 15) / 16) * 16);
+  __shared__ double red[16];
+  for (int64_t row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
+    const double a = p.rot[row * 4 + 0], b = p.rot[row * 4 + 1], c = p.rot[row * 4 + 2], d = p.rot[row * 4 + 3];
+    const double aa = a * a, bb = b * b, cc = c * c, dd = d * d;
+    const double m[9] = {aa + bb - cc - dd, a * c + b * d, b * c - a * d,
+                         aa - bb + cc - dd, a * d + b * c, c * d - a * b,
+                         aa - bb - cc + dd, a * b + c * d, b * d - a * c};
+    __syncthreads();  // previous row's readers are done with v / vd
+    double lo = INFINITY, hi = -INFINITY;
+    for (int64_t j = threadIdx.x; j < p.S; j += kProjThreads) {
+      const double val = project_pixel<MT>(p, m, __ldg(p.dc + 3 * j), __ldg(p.dc + 3 * j + 1), __ldg(p.dc + 3 * j + 2));
+      if (p.rescale) {
+        vd[j] = val;
+        lo = fmin(lo, val);
+        hi = fmax(hi, val);
+      } else {
+        v[j] = (float)val;
+      }
+    }
+    if (p.rescale) {  // _rescale_with_min_max (pattern/_pattern.py:110-111), then the cast
+      block_reduce_minmax(lo, hi, red);
+      const double range = hi - lo, orange = p.out_max - p.out_min;
+      for (int64_t j = threadIdx.x; j < p.S; j += kProjThreads)
+        v[j] = (float)((vd[j] - lo) / range * orange + p.out_min);
+    }
+    __syncthreads();
+    if (p.out) {
+      float* o = p.out + row * p.S;
+      for (int64_t j = threadIdx.x; j < p.S; j += kProjThreads) o[j] = v[j];
+    }
+    if (p.a32) {
+      // the dictionary-side prepare step on the staged row: same arithmetic and summation order
+      // as kdi_normalize_staged (kdi_normalize.cu)
+      const int32_t* cols = p.cols;
+      float mean = 0.f;
+      if (p.metric == KDI_NCC) {
+        double s = 0.0;
+        for (int64_t j = threadIdx.x; j < p.s_eff; j += kProjThreads) s += (double)v[cols ? cols[j] : j];
+        s = block_reduce_sum(s, red);
+        mean = (float)(s / (double)p.s_eff);
+      }
+      double ss = 0.0;
+      for (int64_t j = threadIdx.x; j < p.s_eff; j += kProjThreads) {
+        const float cv = v[cols ? cols[j] : j] - mean;
+        ss += (double)cv * (double)cv;
+      }
+      ss = block_reduce_sum(ss, red);
+      const float norm = (float)sqrt(ss);
+      float* o32 = p.a32 + row * p.s_pitch;
+      uint16_t* o16 = p.a16 + row * p.kp;
+      for (int64_t j = 4 * (int64_t)threadIdx.x; j < p.kp; j += 4 * kProjThreads) {
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = (j + q < p.s_eff) ? (v[cols ? cols[j + q] : j + q] - mean) / norm : 0.f;
+        if (j < p.s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        uint2 h;
+        h.x = (uint32_t)op16<BF16>(o[0]) | ((uint32_t)op16<BF16>(o[1]) << 16);
+        h.y = (uint32_t)op16<BF16>(o[2]) | ((uint32_t)op16<BF16>(o[3]) << 16);
+        *reinterpret_cast<uint2*>(o16 + j) = h;
+      }
+    }
+  }
+}
+
+template <typename MT>
+int launch_typed(kdi_ctx* ctx, cudaStream_t stream, const ProjParams& p, int bf16, int max_ctas) {
+  size_t smem = ((size_t)p.S * sizeof(float) + 15) / 16 * 16;
+  if (p.rescale) smem += (size_t)p.S * sizeof(double);
+  if (smem > 200 * 1024)
+    return kdi_fail(ctx, KDI_EUNSUPPORTED, "detector of %lld pixels is too large for the projection kernel's shared-memory staging",
+                    (long long)p.S);
+  static bool once = (cudaFuncSetAttribute(kdi_project_kernel<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                      cudaFuncSetAttribute(kdi_project_kernel<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
+  (void)once;
+  const unsigned grid = (unsigned)((max_ctas > 0 && p.n_rows > max_ctas) ? max_ctas : p.n_rows);
+  kdi_span span(ctx, stream, "project (+normalize)");
+  if (bf16) kdi_project_kernel<MT, true><<<grid, kProjThreads, smem, stream>>>(p);
+  else kdi_project_kernel<MT, false><<<grid, kProjThreads, smem, stream>>>(p);
+  KDI_CUDA(ctx, cudaGetLastError());
+  ctx->tm.kernel_launches++;
+  return KDI_OK;
+}
+
+}  // namespace
+
+struct kdi_master_pattern {
+  int mp_dtype = KDI_F32;  // storage type on the device: KDI_F32 (f32/u8/u16 sources, exact) or KDI_F64
+  int npx = 0, npy = 0;    // columns, rows of the master pattern arrays
+  void* upper = nullptr;
+  void* lower = nullptr;
+  double* dc = nullptr;  // S x 3
+  int64_t S = 0;
+  double scale = 0.0;
+  int rescale = 0;
+  double out_min = 0.0, out_max = 1.0;
+};
+
+int kdi_launch_project(kdi_ctx* ctx, cudaStream_t stream, const kdi_master_pattern* mp, const double* d_rot,
+                       int64_t n, float* d_out, kdi_patterns* dst, int64_t row_offset, int max_ctas) {
+  if (n <= 0) return KDI_OK;
+  if (n > 0x7fffffffLL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "too many rotations in one call");
+  ProjParams p = {};
+  p.rot = d_rot;
+  p.dc = mp->dc;
+  p.upper = mp->upper;
+  p.lower = mp->lower;
+  // EBSDMasterPattern.get_patterns passes npx, npy = axes_manager.signal_shape = (columns, rows)
+  // and the kernels bound the ROW index by npx and the COLUMN index by npy (_master_pattern.py
+  // :650-653); kept as is (master patterns are square)
+  p.npx = mp->npx;
+  p.npy = mp->npy;
+  p.ld = mp->npx;
+  p.scale = mp->scale;
+  p.rescale = mp->rescale;
+  p.out_min = mp->out_min;
+  p.out_max = mp->out_max;
+  p.S = mp->S;
+  p.n_rows = n;
+  p.out = d_out;
+  int bf16 = 0;
+  if (dst) {
+    if (dst->S != mp->S) return kdi_fail(ctx, KDI_EINVAL, "pattern set has %lld pixels, detector %lld", (long long)dst->S, (long long)mp->S);
+    if (row_offset < 0 || row_offset + n > dst->rows) return kdi_fail(ctx, KDI_EINTERNAL, "projection out of range");
+    p.cols = ctx->mask_S ? ctx->d_cols : nullptr;
+    p.s_eff = dst->s_eff;
+    p.metric = dst->metric;
+    p.a32 = dst->a32 + row_offset * dst->s_pitch;
+    p.s_pitch = dst->s_pitch;
+    p.a16 = reinterpret_cast<uint16_t*>(dst->a16) + row_offset * dst->kp;
+    p.kp = dst->kp;
+    bf16 = dst->compute_dtype == 1;
+  }
+  if (mp->mp_dtype == KDI_F64) return launch_typed<double>(ctx, stream, p, bf16, max_ctas);
+  return launch_typed<float>(ctx, stream, p, bf16, max_ctas);
+}
+
+extern "C" {
+
+int kdi_master_pattern_create(kdi_ctx* ctx, const void* upper, const void* lower, int mp_dtype, int64_t rows,
+                              int64_t cols, const double* direction_cosines, int64_t S, double scale, int rescale,
+                              double out_min, double out_max, kdi_master_pattern** out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!upper || !lower || !direction_cosines || !out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_master_pattern_create: NULL argument");
+  const size_t esz = kdi_dtype_size(mp_dtype);
+  if (!esz) return kdi_fail(ctx, KDI_EINVAL, "unknown master pattern dtype %d", mp_dtype);
+  if (rows < 2 || cols < 2 || rows > 32768 || cols > 32768 || S < 1)
+    return kdi_fail(ctx, KDI_EINVAL, "bad master pattern / detector shape");
+  if (rescale && !(out_max > out_min)) return kdi_fail(ctx, KDI_EINVAL, "rescale needs out_max > out_min");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  kdi_master_pattern* mp = new kdi_master_pattern();
+  mp->npx = (int)cols;
+  mp->npy = (int)rows;
+  mp->S = S;
+  mp->scale = scale;
+  mp->rescale = rescale != 0;
+  mp->out_min = out_min;
+  mp->out_max = out_max;
+  mp->mp_dtype = mp_dtype == KDI_F64 ? KDI_F64 : KDI_F32;
+  const size_t n = (size_t)rows * cols;
+  const size_t dsz = mp->mp_dtype == KDI_F64 ? 8 : 4;
+  // integer and float32 master patterns are stored as float32 (exact); float64 stays float64
+  std::vector<float> tmp;
+  const void* hu = upper;
+  const void* hl = lower;
+  std::vector<float> tu, tl;
+  if (mp_dtype == KDI_U8 || mp_dtype == KDI_U16) {
+    tu.resize(n); tl.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      tu[i] = mp_dtype == KDI_U8 ? (float)reinterpret_cast<const uint8_t*>(upper)[i] : (float)reinterpret_cast<const uint16_t*>(upper)[i];
+      tl[i] = mp_dtype == KDI_U8 ? (float)reinterpret_cast<const uint8_t*>(lower)[i] : (float)reinterpret_cast<const uint16_t*>(lower)[i];
+    }
+    hu = tu.data(); hl = tl.data();
+  }
+  cudaError_t e = cudaMalloc(&mp->upper, n * dsz);
+  if (e == cudaSuccess) e = cudaMalloc(&mp->lower, n * dsz);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&mp->dc), (size_t)S * 3 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(mp->upper, hu, n * dsz, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(mp->lower, hl, n * dsz, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(mp->dc, direction_cosines, (size_t)S * 3 * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (mp->upper) cudaFree(mp->upper);
+    if (mp->lower) cudaFree(mp->lower);
+    if (mp->dc) cudaFree(mp->dc);
+    delete mp;
+    return kdi_fail(ctx, e == cudaErrorMemoryAllocation ? KDI_ENOMEM : KDI_ECUDA, "master pattern upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = mp;
+  return KDI_OK;
+}
+
+int kdi_master_pattern_destroy(kdi_ctx* ctx, kdi_master_pattern* mp) {
+  if (!mp) return KDI_OK;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+  }
+  cudaFree(mp->upper);
+  cudaFree(mp->lower);
+  cudaFree(mp->dc);
+  delete mp;
+  return KDI_OK;
+}
+
+// upload rotations (n x 4 doubles) if they live on the host; returns the device pointer
+static int rotations_on_device(kdi_ctx* ctx, const double* rot, int loc, int64_t n, const double** d_rot, void** owned) {
+  *owned = nullptr;
+  if (loc == KDI_DEVICE) { *d_rot = rot; return KDI_OK; }
+  if (loc != KDI_HOST) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location %d", loc);
+  void* d = nullptr;
+  KDI_CUDA(ctx, cudaMalloc(&d, (size_t)n * 4 * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(d, rot, (size_t)n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) { cudaFree(d); return kdi_fail(ctx, KDI_ECUDA, "rotation upload failed: %s", cudaGetErrorString(e)); }
+  ctx->tm.h2d_bytes += n * 32;
+  *d_rot = reinterpret_cast<const double*>(d);
+  *owned = d;
+  return KDI_OK;
+}
+
+int kdi_project_patterns(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations, int rot_loc,
+                         int64_t n, float* out, int out_loc) {
+  if (!ctx) return KDI_EINVAL;
+  if (!mp || !rotations || !out) return kdi_fail(ctx, KDI_EINVAL, "kdi_project_patterns: NULL argument");
+  if (n < 0) return kdi_fail(ctx, KDI_EINVAL, "bad rotation count");
+  if (n == 0) return KDI_OK;
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  const double* d_rot = nullptr;
+  void* owned = nullptr;
+  KDI_TRY(rotations_on_device(ctx, rotations, rot_loc, n, &d_rot, &owned));
+  int rc = KDI_OK;
+  if (out_loc == KDI_DEVICE) {
+    rc = kdi_launch_project(ctx, ctx->stream, mp, d_rot, n, out, nullptr, 0, 0);
+  } else {
+    // bounded staging: ~256 MB of patterns at a time
+    int64_t batch = std::max<int64_t>(1, (256ll << 20) / (mp->S * 4));
+    batch = std::min<int64_t>(batch, n);
+    rc = kdi_ws2_reserve(ctx, (size_t)batch * mp->S * sizeof(float));
+    float* stage = reinterpret_cast<float*>(ctx->ws2);
+    for (int64_t r0 = 0; rc == KDI_OK && r0 < n; r0 += batch) {
+      const int64_t nb = std::min<int64_t>(batch, n - r0);
+      rc = kdi_launch_project(ctx, ctx->stream, mp, d_rot + r0 * 4, nb, stage, nullptr, 0, 0);
+      if (rc == KDI_OK && cudaMemcpyAsync(out + r0 * mp->S, stage, (size_t)nb * mp->S * sizeof(float),
+                                          cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        rc = kdi_fail(ctx, KDI_ECUDA, "D2H copy failed");
+      if (rc == KDI_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (owned) cudaFree(owned);
+  if (rc == KDI_OK && e != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "projection failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+int kdi_patterns_create_projected(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations,
+                                  int rot_loc, int64_t n, int metric, kdi_patterns** out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!mp || !rotations || !out) return kdi_fail(ctx, KDI_EINVAL, "kdi_patterns_create_projected: NULL argument");
+  *out = nullptr;
+  if (n < 0) return kdi_fail(ctx, KDI_EINVAL, "bad rotation count");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  kdi_patterns* p = nullptr;
+  KDI_TRY(kdi_patterns_alloc(ctx, n, mp->S, metric, &p));
+  int rc = KDI_OK;
+  if (n > 0) {
+    const double* d_rot = nullptr;
+    void* owned = nullptr;
+    rc = rotations_on_device(ctx, rotations, rot_loc, n, &d_rot, &owned);
+    if (rc == KDI_OK) rc = kdi_launch_project(ctx, ctx->stream, mp, d_rot, n, nullptr, p, 0, 0);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (owned) cudaFree(owned);
+    if (rc == KDI_OK && e != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "projection failed: %s", cudaGetErrorString(e));
+  }
+  if (rc != KDI_OK) {
+    const std::string err = ctx->err;
+    kdi_patterns_destroy(ctx, p);
+    ctx->err = err;
+    return rc;
+  }
+  *out = p;
+  return KDI_OK;
+}
+
+}  // extern "C"

@@ -129,3 +129,38 @@ def nickel_ebsd_small() -> np.ndarray:
     the raw NORDIF file (data/_data.py:97-126)."""
     raw = np.fromfile(os.path.join(_SRC, "data", "nordif", "Pattern.dat"), dtype=np.uint8)
     return raw.reshape((3, 3, 60, 60))
+
+
+def load_master_pattern():
+    """Return the reference's ``signals/util/_master_pattern.py`` module, executed in place.
+
+    It imports two helpers from modules that cannot be imported here
+    (``kikuchipy/pattern/_pattern.py`` needs scikit-image): ``_rescale_with_min_max`` is taken
+    from that file by executing only that function's own source lines (AST extraction, nothing
+    is copied into this repository); ``kikuchipy/_utils/numba.py`` loads as is.  Needs numba.
+    """
+    if not available():
+        raise RuntimeError("reference tree not mounted")
+    import ast
+
+    _install_stubs()
+    for name in ("kikuchipy._utils", "kikuchipy.pattern", "kikuchipy.signals", "kikuchipy.signals.util",
+                 "kikuchipy.detectors"):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.__path__ = []
+            sys.modules[name] = mod
+    _load("kikuchipy._utils.numba", "_utils/numba.py")
+    if "kikuchipy.pattern._pattern" not in sys.modules:
+        path = os.path.join(_SRC, "pattern", "_pattern.py")
+        tree = ast.parse(open(path).read())
+        fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "_rescale_with_min_max"]
+        stub = types.ModuleType("kikuchipy.pattern._pattern")
+        stub.__file__ = path
+        from numba import njit
+
+        ns = {"njit": njit, "np": np}
+        exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+        stub._rescale_with_min_max = ns["_rescale_with_min_max"]
+        sys.modules["kikuchipy.pattern._pattern"] = stub
+    return _load("kikuchipy.signals.util._master_pattern", "signals/util/_master_pattern.py")
