@@ -215,6 +215,49 @@ int kdi_shard_exact_rows(kdi_ctx* ctx, const kdi_shard* shard, const int* rows, 
                          int keep_n, float* scores_out, int64_t* indices_out);
 int kdi_shard_release(kdi_ctx* ctx, kdi_shard* shard);
 
+/* ---- dictionary generation on the device (next row of the path: SURVEY.md section 8f.1) ---------
+ * (signals/ebsd_master_pattern.py:97-329 EBSDMasterPattern.get_patterns with a fixed projection
+ *  centre; signals/util/_master_pattern.py:299-370 _project_patterns_from_master_pattern_with_
+ *  fixed_pc, :449-708 its helpers; _utils/numba.py:62-81 rotate_vector)
+ * In the reference a lazy dictionary is generated chunk by chunk INSIDE the indexing loop
+ * (indexing/_dictionary_indexing.py:106-108); here the same projection runs on the device and
+ * feeds the prepare step directly, so the dictionary never crosses PCIe.
+ *
+ * kdi_master_pattern_create: upper / lower hemisphere arrays (rows x cols of mp_dtype - KDI_U8,
+ * KDI_U16, KDI_F32 or KDI_F64, host, row-major), the detector's direction cosines (S x 3 float64,
+ * host: what _get_direction_cosines_from_detector returns, :83-124), `scale` = (cols - 1) / 2
+ * (ebsd_master_pattern.py:256), and the rescale rule of get_patterns (:222-233: rescale to
+ * [out_min, out_max] per pattern when dtype_out differs from the master pattern's dtype).
+ * Patterns are produced as float32 (get_patterns' default dtype_out). */
+typedef struct kdi_master_pattern kdi_master_pattern;
+int kdi_master_pattern_create(kdi_ctx* ctx, const void* upper, const void* lower, int mp_dtype,
+                              int64_t rows, int64_t cols, const double* direction_cosines, int64_t S,
+                              double scale, int rescale, double out_min, double out_max,
+                              kdi_master_pattern** out);
+int kdi_master_pattern_destroy(kdi_ctx* ctx, kdi_master_pattern* mp);
+/* _project_patterns_from_master_pattern_with_fixed_pc: rotations n x 4 float64 unit quaternions
+ * (a, b, c, d), host or device; out: n x S float32, host or device. */
+int kdi_project_patterns(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations,
+                         int rot_loc, int64_t n, float* out, int out_loc);
+/* get_patterns + prepare_dictionary fused: a prepared (normalised) pattern set straight from
+ * rotations (the current signal mask applies, as in kdi_patterns_create). */
+int kdi_patterns_create_projected(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations,
+                                  int rot_loc, int64_t n, int metric, kdi_patterns** out);
+/* kdi_dictionary_indexing / kdi_shard_candidates with the dictionary given as rotations of a
+ * master pattern: dictionary row i = pattern of rotation i (index_offset as usual). */
+int kdi_dictionary_indexing_projected(kdi_ctx* ctx, const void* experimental, int exp_loc,
+                                      int exp_dtype, int64_t exp_rows, int64_t S,
+                                      const kdi_master_pattern* mp, const double* rotations,
+                                      int rot_loc, int64_t n_rotations, int metric, int keep_n,
+                                      const uint8_t* nav_mask, int64_t index_offset,
+                                      float* scores_out, int64_t* indices_out, int out_loc);
+int kdi_shard_candidates_projected(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                                   int64_t exp_rows, int64_t S, const kdi_master_pattern* mp,
+                                   const double* rotations, int rot_loc, int64_t n_rotations,
+                                   int metric, int keep_n, const uint8_t* nav_mask,
+                                   int64_t index_offset, float* approx_out, int64_t* gidx_out,
+                                   kdi_shard** out);
+
 /* ---- orientation similarity map --------------------------------------------
  * (indexing/_orientation_similarity_map.py:30-152)
  * indices: (ny*nx) x keep_n int64 on the host.  footprint: fy x fx bytes

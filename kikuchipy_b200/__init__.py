@@ -14,10 +14,12 @@ from .similarity_metrics import (
     SimilarityMetric,
 )
 from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
+from .master_pattern import GeneratedDictionary, direction_cosines, get_patterns
 
 __all__ = [
     "Context",
     "DictionaryIndexingResult",
+    "GeneratedDictionary",
     "KdiError",
     "NormalizedCrossCorrelationMetric",
     "NormalizedDotProductMetric",
@@ -25,6 +27,8 @@ __all__ = [
     "default_context",
     "dictionary_indexing",
     "dictionary_indexing_sharded",
+    "direction_cosines",
+    "get_patterns",
     "gather_topk",
     "orientation_similarity_map",
     "shard_bounds",

@@ -104,6 +104,15 @@ SIGNATURES = {
     "kdi_shard_finalize": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, C.POINTER(_i)]),
     "kdi_shard_exact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "kdi_shard_release": (_i, [_vp, _vp]),
+    "kdi_master_pattern_create": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _i64, C.c_double, _i, C.c_double,
+                                       C.c_double, C.POINTER(_vp)]),
+    "kdi_master_pattern_destroy": (_i, [_vp, _vp]),
+    "kdi_project_patterns": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _i]),
+    "kdi_patterns_create_projected": (_i, [_vp, _vp, _vp, _i, _i64, _i, C.POINTER(_vp)]),
+    "kdi_dictionary_indexing_projected": (
+        _i, [_vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _i, _i64, _i, _i, _vp, _i64, _vp, _vp, _i]),
+    "kdi_shard_candidates_projected": (
+        _i, [_vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _i, _i64, _i, _i, _vp, _i64, _vp, _vp, C.POINTER(_vp)]),
     "kdi_orientation_similarity_map": (
         _i,
         [_vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
@@ -272,6 +281,37 @@ class Shard:
                 self.close()
         except Exception:
             pass
+
+
+class MasterPattern:
+    """Device-resident master pattern + detector direction cosines (``kdi_master_pattern``)."""
+
+    def __init__(self, ctx: "Context", handle: int, n_pixels: int):
+        self._ctx, self._h, self.n_pixels = ctx, handle, n_pixels
+
+    def close(self):
+        if self._h:
+            self._ctx._lib.kdi_master_pattern_destroy(self._ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+
+def _rotations(rot):
+    """(pointer, location, keep-alive, n) of (n, 4) float64 quaternions (NumPy or CUDA tensor)."""
+    if hasattr(rot, "is_cuda") and rot.is_cuda:
+        import torch
+
+        if rot.dtype != torch.float64 or not rot.is_contiguous():
+            rot = rot.to(torch.float64).contiguous()
+        return rot.data_ptr(), KDI_DEVICE, rot, int(rot.shape[0])
+    r = np.ascontiguousarray(np.asarray(rot, dtype=np.float64).reshape(-1, 4))
+    return r.ctypes.data, KDI_HOST, r, int(r.shape[0])
 
 
 class Context:
@@ -517,6 +557,128 @@ class Context:
             )
         )
         del ekeep, dkeep
+        return Shard(self, h.value, kept, kc), approx, gidx
+
+    # -- dictionary generation -------------------------------------------------------------------
+    def master_pattern(self, upper, lower, direction_cosines, scale=None, rescale=False, out_min=-1.0,
+                       out_max=1.0) -> MasterPattern:
+        up = np.ascontiguousarray(upper)
+        lo = np.ascontiguousarray(lower)
+        if up.dtype not in _DTYPES:
+            up, lo = up.astype(np.float64), lo.astype(np.float64)
+        if lo.dtype != up.dtype or lo.shape != up.shape or up.ndim != 2:
+            raise ValueError("master pattern hemispheres must be 2-D arrays of the same shape and dtype")
+        dc = np.ascontiguousarray(np.asarray(direction_cosines, dtype=np.float64).reshape(-1, 3))
+        if scale is None:
+            scale = (up.shape[1] - 1) / 2  # ebsd_master_pattern.py:255-256
+        h = _vp()
+        self._check(
+            self._lib.kdi_master_pattern_create(
+                self._h, up.ctypes.data, lo.ctypes.data, _DTYPES[up.dtype], up.shape[0], up.shape[1],
+                dc.ctypes.data, dc.shape[0], float(scale), int(bool(rescale)), float(out_min), float(out_max),
+                C.byref(h),
+            )
+        )
+        return MasterPattern(self, h.value, dc.shape[0])
+
+    def project_patterns(self, mp: MasterPattern, rotations, out=None):
+        """``(n, S)`` float32 patterns (NumPy, or the CUDA tensor ``out``)."""
+        rptr, rloc, keep, n = _rotations(rotations)
+        if out is None:
+            res = np.empty((n, mp.n_pixels), dtype=np.float32)
+            optr, oloc = res.ctypes.data, KDI_HOST
+        else:
+            res = out
+            self._stream_sync(out.device)
+            optr, oloc = out.data_ptr(), KDI_DEVICE
+        if rloc == KDI_DEVICE:
+            self._stream_sync(keep.device)
+        self._check(self._lib.kdi_project_patterns(self._h, mp._h, rptr, rloc, n, optr, oloc))
+        del keep
+        return res
+
+    def patterns_projected(self, mp: MasterPattern, rotations, metric: int) -> Patterns:
+        rptr, rloc, keep, n = _rotations(rotations)
+        if rloc == KDI_DEVICE:
+            self._stream_sync(keep.device)
+        h = _vp()
+        self._check(self._lib.kdi_patterns_create_projected(self._h, mp._h, rptr, rloc, n, metric, C.byref(h)))
+        del keep
+        return Patterns(self, h.value)
+
+    def dictionary_indexing_projected(self, experimental, exp_rows: int, mp: MasterPattern, rotations, metric: int,
+                                      keep_n: int, nav_mask=None, index_offset: int = 0, out=None):
+        """The whole driver with the dictionary generated on the device from ``rotations``."""
+        eptr, eloc, ecode, ekeep = _buffer(experimental, self)
+        rptr, rloc, rkeep, n = _rotations(rotations)
+        if rloc == KDI_DEVICE:
+            self._stream_sync(rkeep.device)
+        n_e = int(np.prod(experimental.shape))
+        if exp_rows < 1 or n_e % exp_rows:
+            raise ValueError("pattern array cannot be reshaped to (rows, -1)")
+        S = n_e // exp_rows
+        if S != mp.n_pixels:
+            raise ValueError(f"Experimental ({S}) and dictionary ({mp.n_pixels}) signal sizes must be identical")
+        rm, kept = None, exp_rows
+        if nav_mask is not None:
+            rm = np.ascontiguousarray(np.asarray(nav_mask).ravel().astype(np.uint8))
+            kept = int((rm == 0).sum())
+        if out is None:
+            scores = np.empty((kept, keep_n), dtype=np.float32)
+            idx = np.empty((kept, keep_n), dtype=np.int64)
+            sptr, iptr, oloc = scores.ctypes.data, idx.ctypes.data, KDI_HOST
+        else:
+            idx, scores = out
+            if hasattr(scores, "is_cuda") and scores.is_cuda:
+                sptr, iptr, oloc = scores.data_ptr(), idx.data_ptr(), KDI_DEVICE
+            else:
+                sptr, iptr, oloc = scores.ctypes.data, idx.ctypes.data, KDI_HOST
+        self._check(
+            self._lib.kdi_dictionary_indexing_projected(
+                self._h, eptr, eloc, ecode, exp_rows, S, mp._h, rptr, rloc, n, metric, keep_n,
+                rm.ctypes.data if rm is not None else None, index_offset, sptr, iptr, oloc,
+            )
+        )
+        del ekeep, rkeep
+        return idx, scores
+
+    def shard_candidates_projected(self, experimental, exp_rows, mp: MasterPattern, rotations, metric, keep_n,
+                                   nav_mask=None, index_offset=0, pad_rows=0):
+        """``shard_candidates`` with this rank's dictionary rows generated from its rotations."""
+        import torch
+
+        kc = self.candidate_capacity(keep_n)
+        if kc == 0:
+            raise NotImplementedError(f"keep_n {keep_n} too large for the candidate pipeline")
+        eptr, eloc, ecode, ekeep = _buffer(experimental, self)
+        rptr, rloc, rkeep, n = _rotations(rotations)
+        if rloc == KDI_DEVICE:
+            self._stream_sync(rkeep.device)
+        n_e = int(np.prod(experimental.shape))
+        if exp_rows < 1 or n_e % exp_rows:
+            raise ValueError("pattern array cannot be reshaped to (rows, -1)")
+        S = n_e // exp_rows
+        rm, kept = None, exp_rows
+        if nav_mask is not None:
+            rm = np.ascontiguousarray(np.asarray(nav_mask).ravel().astype(np.uint8))
+            kept = int((rm == 0).sum())
+        dev = torch.device("cuda", self.device)
+        n_out = max(kept, int(pad_rows))
+        approx = torch.empty((n_out, kc), dtype=torch.float32, device=dev)
+        gidx = torch.empty((n_out, kc), dtype=torch.int64, device=dev)
+        if n_out > kept:
+            approx[kept:].fill_(-float("inf"))
+            gidx[kept:].fill_(-1)
+            self._stream_sync(dev)
+        h = _vp()
+        self._check(
+            self._lib.kdi_shard_candidates_projected(
+                self._h, eptr, eloc, ecode, exp_rows, S, mp._h, rptr, rloc, n, metric, int(keep_n),
+                rm.ctypes.data if rm is not None else None, int(index_offset), approx.data_ptr(),
+                gidx.data_ptr(), C.byref(h),
+            )
+        )
+        del ekeep, rkeep
         return Shard(self, h.value, kept, kc), approx, gidx
 
     def orientation_similarity_map(self, indices, ny, nx, n_best, from_n_best, normalize, footprint, center_index):

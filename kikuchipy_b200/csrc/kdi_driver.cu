@@ -370,20 +370,45 @@ int kdi_merge_topk(kdi_ctx* ctx, int64_t rows, int n_lists, int k_in, const floa
 
 }  // extern "C"
 
+// where the dictionary rows come from: raw patterns (host or device, any supported dtype) or a
+// master pattern + rotations projected on the device (kdi_project.cu)
+struct kdi_dict_source {
+  const void* data = nullptr;
+  int loc = KDI_DEVICE;
+  int dtype = KDI_F32;
+  const kdi_master_pattern* mp = nullptr;
+  const double* d_rot = nullptr;  // device, rows x 4
+};
+
+// normalised rows [row0, row0 + n) of `dict` from a device-resident source
+static int fill_dict(kdi_ctx* ctx, cudaStream_t st, kdi_patterns* dict, int64_t row0, int64_t n,
+                     const kdi_dict_source& src, int64_t S, int max_ctas) {
+  if (src.mp) return kdi_launch_project(ctx, st, src.mp, src.d_rot + row0 * 4, n, nullptr, dict, row0, max_ctas);
+  const size_t row_bytes = (size_t)S * kdi_dtype_size(src.dtype);
+  return kdi_patterns_fill(ctx, st, dict, row0, reinterpret_cast<const uint8_t*>(src.data) + (size_t)row0 * row_bytes,
+                           src.dtype, n, nullptr, max_ctas);
+}
+
 // prepare experimental (once) + dictionary (streamed) and run the tensor-core pass and the
 // per-row post-processing (`post`: selection + rescoring, or the selection alone).  On success
 // *exp_out / *dict_out own the prepared sets, everything has been queued and the main stream
 // is ordered after all of it (ev[3] / ev[4] bracket the exposed post-processing); the caller
 // continues with kdi_match_complete (or, candidates_only, just synchronises).
 static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
-                             int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
+                             int64_t exp_rows, const kdi_dict_source& dsrc,
                              int64_t dict_rows, int64_t S, int metric, int keep_n,
                              const uint8_t* nav_mask, float* scores_out, int64_t* indices_out,
                              int out_loc, kdi_post post, kdi_match_job* job,
                              kdi_patterns** exp_out, kdi_patterns** dict_out) {
   const bool candidates_only = post.candidates_only;
+  const void* dictionary = dsrc.data;
+  const int dict_loc = dsrc.mp ? KDI_DEVICE : dsrc.loc;
+  const int dict_dtype = dsrc.mp ? KDI_F32 : dsrc.dtype;
   const size_t dsz = kdi_dtype_size(dict_dtype);
   if (!dsz || !kdi_dtype_size(exp_dtype)) return kdi_fail(ctx, KDI_EINVAL, "unknown dtype");
+  if (dsrc.mp && kdi_master_pattern_pixels(dsrc.mp) != S)
+    return kdi_fail(ctx, KDI_EINVAL, "Experimental (%lld) and dictionary (%lld) signal sizes must be identical",
+                    (long long)S, (long long)kdi_master_pattern_pixels(dsrc.mp));
   if (dict_rows < 1 || exp_rows < 0 || S < 1) return kdi_fail(ctx, KDI_EINVAL, "bad shape");
   // (a shard may hold fewer rows than keep_n: it then nominates all of them)
   if (keep_n < 1 || (!candidates_only && keep_n > dict_rows))
@@ -411,9 +436,7 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, e0, 0);
     int rc = e == cudaSuccess ? KDI_OK : kdi_fail(ctx, KDI_ECUDA, "stream setup failed: %s", cudaGetErrorString(e));
     if (rc == KDI_OK)
-      rc = kdi_patterns_fill(ctx, ctx->aux_stream, dict, g1_rows,
-                             reinterpret_cast<const uint8_t*>(dictionary) + (size_t)g1_rows * row_bytes,
-                             dict_dtype, dict_rows - g1_rows, nullptr, 4 * ctx->sm_count);
+      rc = fill_dict(ctx, ctx->aux_stream, dict, g1_rows, dict_rows - g1_rows, dsrc, S, 4 * ctx->sm_count);
     if (rc == KDI_OK && cudaEventRecord(e_fill, ctx->aux_stream) != cudaSuccess)
       rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
     if (rc != KDI_OK) {
@@ -439,7 +462,7 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
     rc = kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, candidates_only, job);
   if (rc == KDI_OK) {
     if (dict_loc == KDI_DEVICE) {
-      rc = kdi_patterns_fill(ctx, st, dict, 0, dictionary, dict_dtype, g1_rows, nullptr);
+      rc = fill_dict(ctx, st, dict, 0, g1_rows, dsrc, S, 0);
       if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
       if (rc == KDI_OK && job->M > 0 && job->fused && want_overlap(ctx, job)) {
         // first quarter against every row block, then the row-block groups over the rest
@@ -515,27 +538,17 @@ struct kdi_shard {
   int64_t index_offset = 0;
 };
 
-extern "C" {
-
-int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
-                            int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
-                            int64_t dict_rows, int64_t S, int metric, int keep_n,
-                            int64_t n_per_iteration, const uint8_t* nav_mask, int64_t index_offset,
-                            float* scores_out, int64_t* indices_out, int out_loc) {
-  if (!ctx) return KDI_EINVAL;
-  if (!experimental || !dictionary || !scores_out || !indices_out)
-    return kdi_fail(ctx, KDI_EINVAL, "kdi_dictionary_indexing: NULL argument");
-  (void)n_per_iteration;  // accepted for interface parity; transfers are sized internally
-  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
-  ctx->tm = kdi_timings();
-  kdi_timeline_reset(ctx);
+// the whole driver for any dictionary source
+static int run_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                                   int64_t exp_rows, const kdi_dict_source& dsrc, int64_t dict_rows, int64_t S,
+                                   int metric, int keep_n, const uint8_t* nav_mask, int64_t index_offset,
+                                   float* scores_out, int64_t* indices_out, int out_loc) {
   kdi_patterns *exp = nullptr, *dict = nullptr;
   kdi_match_job job;
   kdi_post post;
   post.index_offset = index_offset;
-  KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dictionary, dict_loc,
-                            dict_dtype, dict_rows, S, metric, keep_n, nav_mask, scores_out, indices_out,
-                            out_loc, post, &job, &exp, &dict));
+  KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric, keep_n,
+                            nav_mask, scores_out, indices_out, out_loc, post, &job, &exp, &dict));
   cudaStream_t st = ctx->stream;
   int rc = kdi_match_complete(ctx, &job, exp, dict, index_offset);
   if (rc == KDI_OK) {
@@ -557,20 +570,13 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
   return rc;
 }
 
-int kdi_candidate_capacity(int keep_n) { return kdi_gemm_kc_for(keep_n); }
-
-int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
-                         int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
-                         int64_t dict_rows, int64_t S, int metric, int keep_n,
-                         const uint8_t* nav_mask, int64_t index_offset, float* approx_out,
-                         int64_t* gidx_out, kdi_shard** out) {
-  if (!ctx) return KDI_EINVAL;
-  if (!experimental || !dictionary || !approx_out || !gidx_out || !out)
-    return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_candidates: NULL argument");
+// stage 1 of the sharded pipeline for any dictionary source
+static int run_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                                int64_t exp_rows, const kdi_dict_source& dsrc, int64_t dict_rows, int64_t S,
+                                int metric, int keep_n, const uint8_t* nav_mask, int64_t index_offset,
+                                float* approx_out, int64_t* gidx_out, kdi_shard** out) {
   const int kc = kdi_gemm_kc_for(keep_n);
   if (kc == 0) return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d too large for the candidate pipeline", keep_n);
-  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
-  ctx->tm = kdi_timings();
   kdi_patterns *exp = nullptr, *dict = nullptr;
   kdi_match_job job;
   kdi_post post;
@@ -578,9 +584,8 @@ int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, in
   post.index_offset = index_offset;
   post.approx_out = approx_out;
   post.gidx_out = gidx_out;
-  KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dictionary, dict_loc,
-                            dict_dtype, dict_rows, S, metric, keep_n, nav_mask, nullptr, nullptr,
-                            KDI_DEVICE, post, &job, &exp, &dict));
+  KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric, keep_n,
+                            nav_mask, nullptr, nullptr, KDI_DEVICE, post, &job, &exp, &dict));
   cudaStream_t st = ctx->stream;
   int rc = KDI_OK;
   if (job.M > 0 && job.plan.kc != kc) rc = kdi_fail(ctx, KDI_EINTERNAL, "candidate capacity mismatch");
@@ -598,6 +603,7 @@ int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, in
   ctx->tm.gemm_topk_ms = ev_ms(ctx->ev[8], ctx->ev[9]);
   ctx->tm.rescore_ms = ev_ms(ctx->ev[3], ctx->ev[4]);
   ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+  kdi_timeline_print(ctx);
   kdi_shard* sh = new kdi_shard();
   sh->exp = exp;
   sh->dict = dict;
@@ -605,6 +611,100 @@ int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, in
   sh->index_offset = index_offset;
   *out = sh;
   return KDI_OK;
+}
+
+// rotations (rows x 4 doubles) to the device if they are on the host
+static int upload_rotations(kdi_ctx* ctx, const double* rot, int loc, int64_t n, const double** d_rot,
+                            kdi_rot_buffer* owned) {
+  *owned = kdi_rot_buffer();
+  if (loc == KDI_DEVICE) { *d_rot = rot; return KDI_OK; }
+  if (loc != KDI_HOST) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location %d", loc);
+  return kdi_upload_rotations(ctx, rot, n, d_rot, owned);
+}
+
+extern "C" {
+
+int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                            int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
+                            int64_t dict_rows, int64_t S, int metric, int keep_n,
+                            int64_t n_per_iteration, const uint8_t* nav_mask, int64_t index_offset,
+                            float* scores_out, int64_t* indices_out, int out_loc) {
+  if (!ctx) return KDI_EINVAL;
+  if (!experimental || !dictionary || !scores_out || !indices_out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_dictionary_indexing: NULL argument");
+  (void)n_per_iteration;  // accepted for interface parity; transfers are sized internally
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  kdi_timeline_reset(ctx);
+  kdi_dict_source dsrc;
+  dsrc.data = dictionary;
+  dsrc.loc = dict_loc;
+  dsrc.dtype = dict_dtype;
+  return run_dictionary_indexing(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric,
+                                 keep_n, nav_mask, index_offset, scores_out, indices_out, out_loc);
+}
+
+int kdi_dictionary_indexing_projected(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                                      int64_t exp_rows, int64_t S, const kdi_master_pattern* mp,
+                                      const double* rotations, int rot_loc, int64_t n_rotations, int metric,
+                                      int keep_n, const uint8_t* nav_mask, int64_t index_offset,
+                                      float* scores_out, int64_t* indices_out, int out_loc) {
+  if (!ctx) return KDI_EINVAL;
+  if (!experimental || !mp || !rotations || !scores_out || !indices_out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_dictionary_indexing_projected: NULL argument");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  kdi_timeline_reset(ctx);
+  kdi_dict_source dsrc;
+  dsrc.mp = mp;
+  kdi_rot_buffer owned;
+  KDI_TRY(upload_rotations(ctx, rotations, rot_loc, n_rotations, &dsrc.d_rot, &owned));
+  const int rc = run_dictionary_indexing(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, n_rotations, S,
+                                         metric, keep_n, nav_mask, index_offset, scores_out, indices_out, out_loc);
+  kdi_dev_free(ctx, owned.p, owned.bytes);
+  return rc;
+}
+
+int kdi_candidate_capacity(int keep_n) { return kdi_gemm_kc_for(keep_n); }
+
+int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                         int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
+                         int64_t dict_rows, int64_t S, int metric, int keep_n,
+                         const uint8_t* nav_mask, int64_t index_offset, float* approx_out,
+                         int64_t* gidx_out, kdi_shard** out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!experimental || !dictionary || !approx_out || !gidx_out || !out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_candidates: NULL argument");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  kdi_timeline_reset(ctx);
+  kdi_dict_source dsrc;
+  dsrc.data = dictionary;
+  dsrc.loc = dict_loc;
+  dsrc.dtype = dict_dtype;
+  return run_shard_candidates(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric, keep_n,
+                              nav_mask, index_offset, approx_out, gidx_out, out);
+}
+
+int kdi_shard_candidates_projected(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
+                                   int64_t exp_rows, int64_t S, const kdi_master_pattern* mp,
+                                   const double* rotations, int rot_loc, int64_t n_rotations, int metric,
+                                   int keep_n, const uint8_t* nav_mask, int64_t index_offset, float* approx_out,
+                                   int64_t* gidx_out, kdi_shard** out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!experimental || !mp || !rotations || !approx_out || !gidx_out || !out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_candidates_projected: NULL argument");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  kdi_timeline_reset(ctx);
+  kdi_dict_source dsrc;
+  dsrc.mp = mp;
+  kdi_rot_buffer owned;
+  KDI_TRY(upload_rotations(ctx, rotations, rot_loc, n_rotations, &dsrc.d_rot, &owned));
+  const int rc = run_shard_candidates(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, n_rotations, S, metric,
+                                      keep_n, nav_mask, index_offset, approx_out, gidx_out, out);
+  kdi_dev_free(ctx, owned.p, owned.bytes);
+  return rc;
 }
 
 int kdi_shard_rescore_owned(kdi_ctx* ctx, const kdi_shard* shard, const int64_t* gidx, float* exact_out) {

@@ -26,7 +26,6 @@
 namespace {
 
 constexpr int kProjThreads = 256;
-constexpr double kSqrtPi = 1.7724538509055160273;         // sqrt(pi)
 constexpr double kSqrtPiHalf = 1.2533141373155002512;     // sqrt(pi / 2)
 constexpr double kSqrtPiOver2 = 0.88622692545275801365;   // sqrt(pi) / 2
 constexpr double kTwoOverSqrtPi = 1.1283791670955125739;  // 2 / sqrt(pi)
@@ -93,17 +92,22 @@ __device__ __forceinline__ uint16_t op16(float v) {
 template <typename MT>
 __device__ __forceinline__ double project_pixel(const ProjParams& p, const double (&m)[9], double vx,
                                                 double vy, double vz) {
-  // rotate_vector (_utils/numba.py:78-80) with the products precomputed per rotation
-  const double x = m[0] * vx + 2.0 * (m[1] * vz + m[2] * vy);
-  const double y = m[3] * vy + 2.0 * (m[4] * vx + m[5] * vz);
-  const double z = m[6] * vz + 2.0 * (m[7] * vy + m[8] * vx);
+  // rotate_vector (_utils/numba.py:78-80) with the products precomputed per rotation.  Plain
+  // IEEE multiplies and adds (no FMA contraction): for symmetric rotations the reference's terms
+  // cancel EXACTLY (e.g. a rotated z of exactly 0 selects the upper hemisphere, :506); a fused
+  // multiply-add would leave the rounding error of one product and could flip that choice
+  const double x = __dadd_rn(__dmul_rn(m[0], vx), __dmul_rn(2.0, __dadd_rn(__dmul_rn(m[1], vz), __dmul_rn(m[2], vy))));
+  const double y = __dadd_rn(__dmul_rn(m[3], vy), __dmul_rn(2.0, __dadd_rn(__dmul_rn(m[4], vx), __dmul_rn(m[5], vz))));
+  const double z = __dadd_rn(__dmul_rn(m[6], vz), __dmul_rn(2.0, __dadd_rn(__dmul_rn(m[7], vy), __dmul_rn(m[8], vx))));
   // _vector2lambert (:541-566)
+  // (one reciprocal instead of the reference's three divisions: at most one ulp of float64 apart;
+  // an exact pole, x = y = 0, is recognised below whatever |wz| rounds to)
   const double inv = 1.0 / sqrt(x * x + y * y + z * z);
   const double wx = x * inv, wy = y * inv, wz = z * inv;
   const double abs_z = fabs(wz);
   const double sqrt_z = sqrt(2.0 * (1.0 - abs_z));
   double lx = 0.0, ly = 0.0;
-  if (abs_z != 1.0) {
+  if (abs_z != 1.0 && (wx != 0.0 || wy != 0.0)) {
     if (fabs(wy) <= fabs(wx)) {
       const double s = (wx > 0.0) ? 1.0 : ((wx < 0.0) ? -1.0 : 0.0);
       lx = s * sqrt_z * kSqrtPiOver2;
@@ -146,10 +150,12 @@ kdi_project_kernel(const ProjParams p) {
   __shared__ double red[16];
   for (int64_t row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
     const double a = p.rot[row * 4 + 0], b = p.rot[row * 4 + 1], c = p.rot[row * 4 + 2], d = p.rot[row * 4 + 3];
-    const double aa = a * a, bb = b * b, cc = c * c, dd = d * d;
-    const double m[9] = {aa + bb - cc - dd, a * c + b * d, b * c - a * d,
-                         aa - bb + cc - dd, a * d + b * c, c * d - a * b,
-                         aa - bb - cc + dd, a * b + c * d, b * d - a * c};
+    const double aa = __dmul_rn(a, a), bb = __dmul_rn(b, b), cc = __dmul_rn(c, c), dd = __dmul_rn(d, d);
+    const double ac = __dmul_rn(a, c), ab = __dmul_rn(a, b), ad = __dmul_rn(a, d);
+    const double bc = __dmul_rn(b, c), bd = __dmul_rn(b, d), cd = __dmul_rn(c, d);
+    const double m[9] = {__dadd_rn(__dadd_rn(__dadd_rn(aa, bb), -cc), -dd), __dadd_rn(ac, bd), __dadd_rn(bc, -ad),
+                         __dadd_rn(__dadd_rn(__dadd_rn(aa, -bb), cc), -dd), __dadd_rn(ad, bc), __dadd_rn(cd, -ab),
+                         __dadd_rn(__dadd_rn(__dadd_rn(aa, -bb), -cc), dd), __dadd_rn(ab, cd), __dadd_rn(bd, -ac)};
     __syncthreads();  // previous row's readers are done with v / vd
     double lo = INFINITY, hi = -INFINITY;
     for (int64_t j = threadIdx.x; j < p.S; j += kProjThreads) {
@@ -240,6 +246,8 @@ struct kdi_master_pattern {
   double out_min = 0.0, out_max = 1.0;
 };
 
+int64_t kdi_master_pattern_pixels(const kdi_master_pattern* mp) { return mp->S; }
+
 int kdi_launch_project(kdi_ctx* ctx, cudaStream_t stream, const kdi_master_pattern* mp, const double* d_rot,
                        int64_t n, float* d_out, kdi_patterns* dst, int64_t row_offset, int max_ctas) {
   if (n <= 0) return KDI_OK;
@@ -277,6 +285,23 @@ int kdi_launch_project(kdi_ctx* ctx, cudaStream_t stream, const kdi_master_patte
   }
   if (mp->mp_dtype == KDI_F64) return launch_typed<double>(ctx, stream, p, bf16, max_ctas);
   return launch_typed<float>(ctx, stream, p, bf16, max_ctas);
+}
+
+// host rotations (n x 4 doubles) into a pooled device buffer, asynchronously on the main stream
+int kdi_upload_rotations(kdi_ctx* ctx, const double* rot, int64_t n, const double** d_rot, kdi_rot_buffer* owned) {
+  void* d = nullptr;
+  size_t got = 0;
+  KDI_TRY(kdi_dev_alloc(ctx, (size_t)(n > 0 ? n : 1) * 4 * sizeof(double), &d, &got));
+  cudaError_t e = cudaMemcpyAsync(d, rot, (size_t)n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    kdi_dev_free(ctx, d, got);
+    return kdi_fail(ctx, KDI_ECUDA, "rotation upload failed: %s", cudaGetErrorString(e));
+  }
+  ctx->tm.h2d_bytes += n * 32;
+  *d_rot = reinterpret_cast<const double*>(d);
+  owned->p = d;
+  owned->bytes = got;
+  return KDI_OK;
 }
 
 extern "C" {
@@ -349,18 +374,11 @@ int kdi_master_pattern_destroy(kdi_ctx* ctx, kdi_master_pattern* mp) {
 }
 
 // upload rotations (n x 4 doubles) if they live on the host; returns the device pointer
-static int rotations_on_device(kdi_ctx* ctx, const double* rot, int loc, int64_t n, const double** d_rot, void** owned) {
-  *owned = nullptr;
+static int rotations_on_device(kdi_ctx* ctx, const double* rot, int loc, int64_t n, const double** d_rot, kdi_rot_buffer* owned) {
+  *owned = kdi_rot_buffer();
   if (loc == KDI_DEVICE) { *d_rot = rot; return KDI_OK; }
   if (loc != KDI_HOST) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location %d", loc);
-  void* d = nullptr;
-  KDI_CUDA(ctx, cudaMalloc(&d, (size_t)n * 4 * sizeof(double)));
-  cudaError_t e = cudaMemcpyAsync(d, rot, (size_t)n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-  if (e != cudaSuccess) { cudaFree(d); return kdi_fail(ctx, KDI_ECUDA, "rotation upload failed: %s", cudaGetErrorString(e)); }
-  ctx->tm.h2d_bytes += n * 32;
-  *d_rot = reinterpret_cast<const double*>(d);
-  *owned = d;
-  return KDI_OK;
+  return kdi_upload_rotations(ctx, rot, n, d_rot, owned);
 }
 
 int kdi_project_patterns(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations, int rot_loc,
@@ -371,7 +389,7 @@ int kdi_project_patterns(kdi_ctx* ctx, const kdi_master_pattern* mp, const doubl
   if (n == 0) return KDI_OK;
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
   const double* d_rot = nullptr;
-  void* owned = nullptr;
+  kdi_rot_buffer owned;
   KDI_TRY(rotations_on_device(ctx, rotations, rot_loc, n, &d_rot, &owned));
   int rc = KDI_OK;
   if (out_loc == KDI_DEVICE) {
@@ -392,7 +410,7 @@ int kdi_project_patterns(kdi_ctx* ctx, const kdi_master_pattern* mp, const doubl
     }
   }
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  if (owned) cudaFree(owned);
+  kdi_dev_free(ctx, owned.p, owned.bytes);
   if (rc == KDI_OK && e != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "projection failed: %s", cudaGetErrorString(e));
   return rc;
 }
@@ -409,11 +427,11 @@ int kdi_patterns_create_projected(kdi_ctx* ctx, const kdi_master_pattern* mp, co
   int rc = KDI_OK;
   if (n > 0) {
     const double* d_rot = nullptr;
-    void* owned = nullptr;
+    kdi_rot_buffer owned;
     rc = rotations_on_device(ctx, rotations, rot_loc, n, &d_rot, &owned);
     if (rc == KDI_OK) rc = kdi_launch_project(ctx, ctx->stream, mp, d_rot, n, nullptr, p, 0, 0);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (owned) cudaFree(owned);
+    kdi_dev_free(ctx, owned.p, owned.bytes);
     if (rc == KDI_OK && e != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "projection failed: %s", cudaGetErrorString(e));
   }
   if (rc != KDI_OK) {

@@ -125,8 +125,16 @@ class _KdiStages:
         self.nav, self.start, self.shard = navigation_mask, start, None
 
     def candidates(self, pad_rows):
-        self.shard, approx, gidx = self.ctx.shard_candidates(*self.args, nav_mask=self.nav, index_offset=self.start,
-                                                             pad_rows=pad_rows)
+        from .master_pattern import GeneratedDictionary
+
+        experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n = self.args
+        if isinstance(dictionary_shard, GeneratedDictionary):  # this rank's rows are generated from its rotations
+            self.shard, approx, gidx = self.ctx.shard_candidates_projected(
+                experimental, n_exp_all, dictionary_shard.master_pattern, dictionary_shard.rotations, code, keep_n,
+                nav_mask=self.nav, index_offset=self.start, pad_rows=pad_rows)
+        else:
+            self.shard, approx, gidx = self.ctx.shard_candidates(*self.args, nav_mask=self.nav,
+                                                                 index_offset=self.start, pad_rows=pad_rows)
         return approx, gidx, self.shard.kc
 
     def merge(self, s_all, i_all, k):
@@ -231,7 +239,8 @@ def dictionary_indexing_sharded(
     world, rank)`` this rank holds in ``dictionary_shard``.
 
     ``experimental`` (the same array on every rank) and ``dictionary_shard`` may be host arrays
-    or CUDA tensors.  Returns ``(simulation_indices, scores)`` as CUDA tensors ``(M, keep_n)``
+    or CUDA tensors; ``dictionary_shard`` may also be a :class:`GeneratedDictionary` holding this
+    rank's rotations (the shard is then generated on the device).  Returns ``(simulation_indices, scores)`` as CUDA tensors ``(M, keep_n)``
     (global dictionary indices, identical on every rank).  Needs an initialised
     ``torch.distributed`` process group with the NCCL backend.
     """
@@ -253,11 +262,19 @@ def dictionary_indexing_sharded(
     kept = n_exp_all if navigation_mask is None else int((~navigation_mask).sum())
     keep_n = min(int(keep_n), int(dictionary_size))
     dev = torch.device("cuda", ctx.device)
+    from .master_pattern import GeneratedDictionary
+
+    generated = isinstance(dictionary_shard, GeneratedDictionary)
     if world == 1:
         scores = torch.empty((kept, keep_n), dtype=torch.float32, device=dev)
         idx = torch.empty((kept, keep_n), dtype=torch.int64, device=dev)
-        ctx.dictionary_indexing(experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
-                                nav_mask=navigation_mask, index_offset=start, out=(idx, scores))
+        if generated:
+            ctx.dictionary_indexing_projected(experimental, n_exp_all, dictionary_shard.master_pattern,
+                                              dictionary_shard.rotations, code, keep_n, nav_mask=navigation_mask,
+                                              index_offset=start, out=(idx, scores))
+        else:
+            ctx.dictionary_indexing(experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
+                                    nav_mask=navigation_mask, index_offset=start, out=(idx, scores))
         return idx, scores
 
     # torch ops, NCCL collectives and library kernels all on the context's stream: no host syncs
@@ -269,6 +286,8 @@ def dictionary_indexing_sharded(
                 experimental = gather_experimental(experimental, n_exp_all, dev, group)
                 trace("upload_gather_experimental")
         if ctx.candidate_capacity(keep_n) == 0:
+            if generated:
+                raise NotImplementedError(f"keep_n {keep_n} is too large for a generated, sharded dictionary")
             return _sharded_exact_lists(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
                                         navigation_mask, start, kept, dictionary_size, group)
         stages = _KdiStages(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n, navigation_mask,

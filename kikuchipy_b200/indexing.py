@@ -15,6 +15,7 @@ import time
 import numpy as np
 
 from . import _lib
+from .master_pattern import GeneratedDictionary
 from .similarity_metrics import (
     NormalizedCrossCorrelationMetric,
     NormalizedDotProductMetric,
@@ -103,6 +104,8 @@ def _unwrap(signal):
             pass
         return signal.data, nav_shape, sig_shape, steps, unit, getattr(signal, "xmap", None)
     data = signal
+    if isinstance(data, GeneratedDictionary):
+        return data, (data.shape[0],), data.sig_shape if len(data.sig_shape) == 2 else (1,) + data.sig_shape, None, "px", None
     if len(data.shape) < 2:
         raise ValueError("pattern arrays need at least the two detector axes")
     return data, tuple(data.shape[:-2]), tuple(data.shape[-2:]), None, "px", None
@@ -198,7 +201,8 @@ def dictionary_indexing(
     metric = _prepare_metric(
         metric, navigation_mask, signal_mask, dtype, rechunk, n_exp_all, dict_size, context
     )
-    if hasattr(dict_data, "compute"):  # lazy dictionary: materialise (chunks are streamed to the GPU below)
+    generated = isinstance(dict_data, GeneratedDictionary)
+    if hasattr(dict_data, "compute") and not generated:  # lazy (Dask) dictionary: materialise
         dict_data = dict_data.compute()
     if hasattr(exp_data, "compute"):
         exp_data = exp_data.compute()
@@ -214,7 +218,20 @@ def dictionary_indexing(
         print(_info_message(metric, n_exp_all, dict_size, phase_name, n_exp))
 
     t0 = time.time()
-    if isinstance(metric, _GpuMetric):
+    if generated and dictionary_rotations is None:
+        dictionary_rotations = dict_data.rotations
+    if isinstance(metric, _GpuMetric) and generated:
+        # dictionary generated on the device from rotations of a master pattern: the reference's
+        # `dictionary_chunk.compute()` (_dictionary_indexing.py:106-108) fused with the prepare step
+        ctx = metric.context
+        if dict_data.context is not ctx:
+            raise ValueError("the generated dictionary lives on a different device context than the metric")
+        ctx.set_signal_mask(metric.signal_mask)
+        simulation_indices, scores = ctx.dictionary_indexing_projected(
+            exp_data, n_exp_all, dict_data.master_pattern, dict_data.rotations, metric._kdi_metric, keep_n,
+            nav_mask=metric.navigation_mask, index_offset=index_offset,
+        )
+    elif isinstance(metric, _GpuMetric):
         ctx = metric.context
         ctx.set_signal_mask(metric.signal_mask)
         simulation_indices, scores = ctx.dictionary_indexing(
@@ -224,6 +241,8 @@ def dictionary_indexing(
     else:
         # custom SimilarityMetric subclass: the reference's generic driver over its three hooks
         # (_dictionary_indexing.py:70, 193-201); selection is whatever match() returns
+        if generated:
+            dict_data = dict_data.compute()
         simulation_indices, scores = _generic_driver(exp_data, dict_data, metric, keep_n, n_per_iteration)
     total_time = max(time.time() - t0, 1e-12)
     if verbose:
@@ -246,7 +265,7 @@ def dictionary_indexing(
         if rot_src is not None and not _is_orix(rot_src):
             rot = np.zeros((n_exp_all, keep_n, 4))
             rot[..., 0] = 1.0  # identity elsewhere
-            rot[nav] = np.asarray(rot_src)[simulation_indices - index_offset]
+            rot[nav] = np.take(np.asarray(rot_src), simulation_indices - index_offset, axis=0)
             rotations = rot
         if keep_n == 1:
             scores_all = scores_all.squeeze()
@@ -257,7 +276,7 @@ def dictionary_indexing(
     else:
         out_scores, out_idx, is_in_data = scores, simulation_indices, np.ones(n_exp_all, dtype=bool)
         if rot_src is not None and not _is_orix(rot_src):
-            rotations = np.asarray(rot_src)[simulation_indices - index_offset]
+            rotations = np.take(np.asarray(rot_src), simulation_indices - index_offset, axis=0)
 
     if _is_orix(rot_src):  # pragma: no cover - orix is not installed in the build container
         return _to_crystal_map(out_scores, out_idx, simulation_indices, rot_src, dict_xmap, nav_shape,

@@ -182,3 +182,36 @@ def test_live_reference_modules_agree():
         ref_osm(ref_loader.FakeXmap(idx, (6, 7)), from_n_best=4, normalize=True),
         orc.orientation_similarity_map(idx, (6, 7), from_n_best=4, normalize=True),
     )
+
+
+# ---- dictionary generation (master-pattern projection) ------------------------------------------
+
+def test_projection_oracle_matches_reference_golden(golden):
+    """oracle/projection_oracle.py against the outputs of the reference's own Numba kernels
+    (tests/golden/make_golden_projection.py)."""
+    from oracle import projection_oracle as po
+
+    z = golden("projection.npz")
+    nrows, ncols = int(z["nrows"]), int(z["ncols"])
+    d = po.direction_cosines_fixed_pc(z["gnomonic_bounds"], float(z["pcz"]), nrows, ncols, z["om"])
+    assert np.abs(d - z["dc"]).max() < 1e-14
+    dm = po.direction_cosines_fixed_pc(z["gnomonic_bounds"], float(z["pcz"]), nrows, ncols, z["om"], z["dc_mask"])
+    assert dm.shape == z["dc_masked"].shape and np.abs(dm - z["dc_masked"]).max() < 1e-14
+    o1 = po.project_patterns(z["rotations"], z["dc_all"], z["mu32"], z["ml32"])
+    o2 = po.project_patterns(z["rotations"], z["dc_all"], z["mu8"], z["ml8"], rescale=True, out_min=-1.0, out_max=1.0)
+    for got, ref in ((o1, z["out_f32"]), (o2, z["out_u8"])):
+        assert got.dtype == np.float32 and got.shape == ref.shape
+        ulp = np.spacing(np.maximum(np.abs(got), np.abs(ref)))
+        assert np.all(np.abs(got - ref) <= ulp) and np.mean(got == ref) > 0.999
+    # the rescaled patterns span exactly [-1, 1]; both hemispheres are used
+    assert o2.min() == -1.0 and o2.max() == 1.0
+    assert 0.1 < np.mean([(po.rotate_vector(r, z["dc_all"])[:, 2] < 0).mean() for r in z["rotations"]]) < 0.9
+
+
+def test_host_direction_cosines_match_reference_golden(golden):
+    import kikuchipy_b200 as kb
+
+    z = golden("projection.npz")
+    d = kb.direction_cosines(z["gnomonic_bounds"], z["pcz"], int(z["nrows"]), int(z["ncols"]), z["om"])
+    assert np.abs(d - z["dc"]).max() < 1e-14
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-14)

@@ -1,0 +1,25 @@
+"""Time the projection kernel (raw output and fused with the prepare step) for 100 000 rotations."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import kikuchipy_b200 as kb
+from kikuchipy_b200 import _lib
+from oracle import projection_oracle as po
+ctx = kb.default_context(0)
+N = int(os.environ.get("N", "100000"))
+for size in (401, 1001):
+    mu, ml = po.synthetic_master_pattern(size, seed=5)
+    dc = kb.direction_cosines([-0.9, 0.85, -0.7, 0.95], 0.5, 60, 60, po.tilted_detector_matrix(70.0))
+    rot = torch.from_numpy(po.random_rotations(N, seed=4)).cuda()
+    mp = ctx.master_pattern(mu, ml, dc)
+    out = torch.empty((N, 3600), dtype=torch.float32, device="cuda")
+    for name, fn in (("raw float32 out", lambda: ctx.project_patterns(mp, rot, out=out)),
+                     ("fused with prepare", lambda: ctx.patterns_projected(mp, rot, _lib.KDI_NCC).close())):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / 5 * 1e3
+        print(f"master {size}x{size}: {name}: {ms:.3f} ms for {N} patterns ({N * 3600 / ms / 1e6:.1f} Gpixel/s)")
+    mp.close()

@@ -15,10 +15,20 @@ exp = torch.randint(0, 256, (M,) + SIG, dtype=torch.uint8, device=dev, generator
 dic = torch.rand((N,) + SIG, dtype=torch.float32, device=dev, generator=g)
 idx = torch.empty((M, 20), dtype=torch.int64, device=dev); sc = torch.empty((M, 20), dtype=torch.float32, device=dev)
 torch.cuda.synchronize()
+gen = None
+if os.environ.get("GEN"):
+    from oracle import projection_oracle as po
+    mu, ml = po.synthetic_master_pattern(1001, seed=5)
+    dcs = kb.direction_cosines([-0.9, 0.85, -0.7, 0.95], 0.5, 60, 60, po.tilted_detector_matrix(70.0))
+    rot = torch.from_numpy(po.random_rotations(N, seed=4)).cuda()
+    gen = ctx.master_pattern(mu, ml, dcs)
 for i in range(4):
     if i == 3:
-        sys.stderr.write("==== %s\n" % {k: os.environ.get(k) for k in ("OVERLAP", "KDI_CARVEOUT", "SUPERBLOCK", "MAX_STAGES")})
+        sys.stderr.write("==== %s\n" % {k: os.environ.get(k) for k in ("OVERLAP", "KDI_CARVEOUT", "KDI_GEMM_CARVEOUT", "SUPERBLOCK", "MAX_STAGES", "GEN")})
     else:
         sys.stderr.flush()
-    ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, 20, out=(idx, sc))
+    if gen is not None:
+        ctx.dictionary_indexing_projected(exp, M, gen, rot, _lib.KDI_NCC, 20, out=(idx, sc))
+    else:
+        ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, 20, out=(idx, sc))
 print({k: round(v, 3) if isinstance(v, float) else v for k, v in ctx.timings().items()})
