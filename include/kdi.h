@@ -73,6 +73,8 @@ extern "C" {
                                    rescoring of finished row blocks beside the tensor-core launches (separate
                                    streams); 0 = one kernel at a time (per-kernel profiling); 2 = overlapped
                                    schedule even for small jobs (tests)                                 */
+#define KDI_OPT_SPLIT_SELECT 10 /* 1 (default) = candidate selection in its own warp-per-row kernel, 0 = inside
+                                   the rescoring kernel (one 128-thread CTA per row)                      */
 
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;

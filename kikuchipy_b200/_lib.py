@@ -37,6 +37,7 @@ OPT_L2_POLICY = 6
 OPT_TILE_ROTATE = 7
 OPT_MAX_STAGES = 8
 OPT_OVERLAP = 9
+OPT_SPLIT_SELECT = 10
 
 _DTYPES = {
     np.dtype(np.uint8): KDI_U8,

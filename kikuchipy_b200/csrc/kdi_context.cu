@@ -293,6 +293,9 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
       if (value != 0 && value != 1 && value != 2) return kdi_fail(ctx, KDI_EINVAL, "overlap must be 0, 1 or 2");
       ctx->overlap = (int)value;
       return KDI_OK;
+    case KDI_OPT_SPLIT_SELECT:
+      ctx->split_select = value != 0;
+      return KDI_OK;
     case KDI_OPT_TILE_ROTATE:
       ctx->tile_rotate = value != 0;
       return KDI_OK;

@@ -63,13 +63,18 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
   job->indices_out = indices_out;
   if (M == 0) return KDI_OK;
   job->fused = candidates_only || (!ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0);
-  size_t off_thr = 0, off_flags = 0, off_nflag = 0, total = 0;
+  size_t off_thr = 0, off_flags = 0, off_nflag = 0, off_sela = 0, off_seli = 0, total = 0;
   if (job->fused) {
     KDI_TRY(kdi_gemm_make_plan(ctx, M, N, exp->kp, keep_n, &job->plan));
     off_thr = align_up(job->plan.cand_bytes, 256);
     off_flags = align_up(off_thr + job->plan.thr_bytes, 256);
     off_nflag = align_up(off_flags + (size_t)M * sizeof(int), 256);
     total = off_nflag + 256;
+    if (!candidates_only) {  // selected lists between the selection and the rescoring kernel
+      off_sela = align_up(total, 256);
+      off_seli = align_up(off_sela + (size_t)M * job->plan.kc * sizeof(float), 256);
+      total = off_seli + (size_t)M * job->plan.kc * sizeof(int64_t);
+    }
   }
   const size_t off_sc = align_up(total, 256);
   const size_t off_ix = align_up(off_sc + (size_t)M * keep_n * sizeof(float), 256);
@@ -83,6 +88,10 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
     job->thr = reinterpret_cast<uint32_t*>(ws + off_thr);
     job->flags = reinterpret_cast<int*>(ws + off_flags);
     job->d_nflag = reinterpret_cast<int*>(ws + off_nflag);
+    if (!candidates_only) {
+      job->sel_approx = reinterpret_cast<float*>(ws + off_sela);
+      job->sel_idx = reinterpret_cast<int64_t*>(ws + off_seli);
+    }
     KDI_CUDA(ctx, cudaMemsetAsync(job->d_nflag, 0, sizeof(int), ctx->stream));
     KDI_TRY(kdi_launch_cand_init(ctx, ctx->stream, job->thr, M));
   }
@@ -120,6 +129,14 @@ static int launch_post(kdi_ctx* ctx, cudaStream_t st, kdi_match_job* job, const 
   if (post.candidates_only)
     return kdi_launch_select_only(ctx, st, exp->rows, &job->plan, job->cand, job->thr, post.index_offset, inv,
                                   post.approx_out, post.gidx_out, row0, n_rows);
+  // selection (warp per row, local indices) -> lists -> exact rescoring + ranking + certificate
+  if (ctx->split_select) {
+    KDI_TRY(kdi_launch_select_only(ctx, st, exp->rows, &job->plan, job->cand, job->thr, 0, inv, job->sel_approx,
+                                   job->sel_idx, row0, n_rows));
+    return kdi_launch_select_rescore(ctx, st, exp, dict, &job->plan, job->cand, job->thr, job->keep_n,
+                                     post.index_offset, inv, (float)ctx->cert_sigmas, job->d_sc, job->d_ix,
+                                     job->flags, job->d_nflag, row0, n_rows, job->sel_approx, job->sel_idx);
+  }
   return kdi_launch_select_rescore(ctx, st, exp, dict, &job->plan, job->cand, job->thr, job->keep_n,
                                    post.index_offset, inv, (float)ctx->cert_sigmas, job->d_sc, job->d_ix,
                                    job->flags, job->d_nflag, row0, n_rows);

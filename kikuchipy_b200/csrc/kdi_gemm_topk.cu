@@ -445,9 +445,13 @@ int kdi_gemm_make_plan(kdi_ctx* ctx, int64_t M, int64_t N, int64_t kp, int keep_
   int strip_tiles = ctx->strip_tiles;
   if (strip_tiles <= 0) {
     // enough units for a short tail (~24 per worker), but strips of at least 4 tiles so the
-    // threshold warm-up at the start of each unit is amortised
+    // threshold warm-up at the start of each unit is amortised, and of at most 16 tiles: the CTAs
+    // that share a strip drift apart over a long unit and stop sharing the dictionary tiles in L2
+    // (100 000 x 37 500: 30-tile strips 26.8 GB of DRAM reads, 15-tile strips 22.7 GB and 7 % faster)
     int64_t n_strips = kdi_ceil_div(24 * workers, pl.m_blocks);
     const int64_t max_strips = kdi_ceil_div(pl.n_tiles, 4);
+    const int64_t min_strips = kdi_ceil_div(pl.n_tiles, 16);
+    if (n_strips < min_strips) n_strips = min_strips;
     if (n_strips > max_strips) n_strips = max_strips;
     if (n_strips < 1) n_strips = 1;
     strip_tiles = (int)kdi_ceil_div(pl.n_tiles, n_strips);

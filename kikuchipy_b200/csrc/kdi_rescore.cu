@@ -143,6 +143,87 @@ __device__ __forceinline__ int select_candidates(const uint2* __restrict__ c, in
   return kept < KC ? kept : KC;
 }
 
+// ---- warp-per-row selection --------------------------------------------------------------------
+// The same streaming selection as select_candidates, at warp scope: no block barriers, four rows
+// per CTA.  Survivors of the threshold filter are compacted into a 256-key shared-memory buffer
+// with ballots; when the buffer could overflow it is sorted by the warp, the kc best are kept
+// and the threshold is raised.  One row costs a few thousand warp instructions.
+constexpr int kWarpBuf = 256;
+constexpr int kWarpSelRows = 4;  // rows (warps) per CTA
+
+__device__ __forceinline__ void warp_sort_desc(uint64_t* keys, int n, int lane) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = keys[i], b = keys[ixj];
+          const bool sw = ((i & k) == 0) ? (a < b) : (a > b);
+          if (sw) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int KC>
+__global__ void __launch_bounds__(32 * kWarpSelRows)
+kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restrict__ thr, int n_strips,
+                       int64_t row0, int64_t row_end, int64_t index_offset, float inv_scale,
+                       float* __restrict__ out_approx, int64_t* __restrict__ out_gidx) {
+  __shared__ uint64_t s_keys[kWarpSelRows][kWarpBuf];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = row0 + (int64_t)blockIdx.x * kWarpSelRows + warp;
+  if (row >= row_end) return;  // whole warp
+  uint64_t* keys = s_keys[warp];
+  const int64_t total = (int64_t)n_strips * KC;
+  const uint2* c = cand + row * total;
+  uint32_t tkey = thr[row];
+  int count = 0;  // warp-uniform
+  bool sorted = true;
+  constexpr int kBatch = 4;
+  for (int64_t base = 0; base < total; base += 32 * kBatch) {
+    uint2 e[kBatch];
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int64_t i = base + b * 32 + lane;
+      e[b] = i < total ? __ldg(c + i) : make_uint2(0u, 0xFFFFFFFFu);
+    }
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const bool pass = e[b].y != 0xFFFFFFFFu && float_key(__uint_as_float(e[b].x)) >= tkey;
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      if (bal) {
+        if (pass) keys[count + __popc(bal & ((1u << lane) - 1u))] = pack_key(__uint_as_float(e[b].x), e[b].y);
+        count += __popc(bal);
+        sorted = false;
+        if (count > kWarpBuf - 32) {  // the next ballot might not fit: keep the KC best
+          for (int j = count + lane; j < kWarpBuf; j += 32) keys[j] = 0;
+          warp_sort_desc(keys, kWarpBuf, lane);
+          count = KC;
+          const uint32_t k32 = (uint32_t)(keys[KC - 1] >> 32);
+          tkey = k32 > tkey ? k32 : tkey;
+          sorted = true;
+        }
+      }
+    }
+  }
+  if (!sorted) {
+    int n2 = 64;
+    while (n2 < count) n2 <<= 1;
+    for (int j = count + lane; j < n2; j += 32) keys[j] = 0;  // below every real key
+    warp_sort_desc(keys, n2, lane);
+  }
+  __syncwarp();
+  const int nsel = count < KC ? count : KC;
+  for (int i = lane; i < KC; i += 32) {
+    out_approx[row * KC + i] = i < nsel ? key_score(keys[i]) * inv_scale : -INFINITY;
+    out_gidx[row * KC + i] = i < nsel ? (int64_t)key_index(keys[i]) + index_offset : -1;
+  }
+}
+
 template <int KC>
 __global__ void __launch_bounds__(kSelThreads)
 kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
@@ -150,7 +231,8 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
                           const uint32_t* __restrict__ thr, int n_strips, int keep_n,
                           int64_t index_offset, float inv_scale, float cert_sigmas,
                           float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
-                          int* __restrict__ flag_list, int* __restrict__ n_flag, int64_t row0) {
+                          int* __restrict__ flag_list, int* __restrict__ n_flag, int64_t row0,
+                          const float* __restrict__ pre_approx, const int64_t* __restrict__ pre_idx) {
   __shared__ uint64_t keys[kSelBuf];
   __shared__ float ex[KC];
   __shared__ float ap[KC];
@@ -161,14 +243,28 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
 
   const int64_t row = row0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // 1+2. the kc best candidates by tensor-core score
-  const int64_t total = (int64_t)n_strips * KC;
-  const int nsel = select_candidates<KC>(cand + row * total, total, thr[row], keys, &s_count);
-  if (tid < KC) {
-    if (tid < nsel) { ap[tid] = key_score(keys[tid]) * inv_scale; ci[tid] = key_index(keys[tid]); }
-    else { ap[tid] = -INFINITY; ci[tid] = 0xFFFFFFFFu; ex[tid] = -INFINITY; }
+  // 1+2. the kc best candidates by tensor-core score: selected here, or already selected by
+  // kdi_select_warp_kernel (lists sorted best first, -1 padding last, local indices)
+  int nsel;
+  if (pre_idx) {
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    if (tid < KC) {
+      const int64_t g = pre_idx[row * KC + tid];
+      if (g >= 0) { ap[tid] = pre_approx[row * KC + tid]; ci[tid] = (uint32_t)g; atomicAdd(&s_count, 1); }
+      else { ap[tid] = -INFINITY; ci[tid] = 0xFFFFFFFFu; ex[tid] = -INFINITY; }
+    }
+    __syncthreads();
+    nsel = s_count;
+  } else {
+    const int64_t total = (int64_t)n_strips * KC;
+    nsel = select_candidates<KC>(cand + row * total, total, thr[row], keys, &s_count);
+    if (tid < KC) {
+      if (tid < nsel) { ap[tid] = key_score(keys[tid]) * inv_scale; ci[tid] = key_index(keys[tid]); }
+      else { ap[tid] = -INFINITY; ci[tid] = 0xFFFFFFFFu; ex[tid] = -INFINITY; }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // 3. exact scores from the float32 rows.  Round A: the keep_n (+ a few) best by tensor-core
   // score.  Their errors give this row's sigma, their keep_n-th best exact score E gives a
   // bound: a remaining candidate whose tensor-core score is below E - eps cannot enter the
@@ -487,7 +583,7 @@ int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patte
                               const uint2* cand, const uint32_t* thr, int keep_n,
                               int64_t index_offset, float approx_inv_scale, float cert_sigmas,
                               float* out_scores, int64_t* out_idx, int* flag_list, int* n_flag,
-                              int64_t row0, int64_t n_rows) {
+                              int64_t row0, int64_t n_rows, const float* pre_approx, const int64_t* pre_idx) {
   if (n_rows < 0) n_rows = exp->rows - row0;
   if (n_rows <= 0) return KDI_OK;
   const unsigned grid = (unsigned)n_rows;
@@ -499,11 +595,11 @@ int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patte
   if (plan->kc == 32)
     kdi_select_rescore_kernel<32><<<grid, kSelThreads, 0, stream>>>(
         exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
-        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0);
+        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
   else if (plan->kc == 64)
     kdi_select_rescore_kernel<64><<<grid, kSelThreads, 0, stream>>>(
         exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
-        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0);
+        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
   else
     return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
   KDI_CUDA(ctx, cudaGetLastError());
@@ -550,16 +646,14 @@ int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, cons
                            int64_t row0, int64_t n_rows) {
   if (n_rows < 0) n_rows = rows - row0;
   if (n_rows <= 0) return KDI_OK;
-  static bool once = (cudaFuncSetAttribute(kdi_select_only_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_carveout_pref()),
-                      cudaFuncSetAttribute(kdi_select_only_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_carveout_pref()), true);
-  (void)once;
-  kdi_span span(ctx, stream, "select_only");
+  const unsigned grid = (unsigned)kdi_ceil_div(n_rows, kWarpSelRows);
+  kdi_span span(ctx, stream, "select (warp per row)");
   if (plan->kc == 32)
-    kdi_select_only_kernel<32><<<(unsigned)n_rows, kSelThreads, 0, stream>>>(
-        cand, thr, plan->n_strips, index_offset, approx_inv_scale, out_approx, out_gidx, row0);
+    kdi_select_warp_kernel<32><<<grid, 32 * kWarpSelRows, 0, stream>>>(
+        cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx);
   else if (plan->kc == 64)
-    kdi_select_only_kernel<64><<<(unsigned)n_rows, kSelThreads, 0, stream>>>(
-        cand, thr, plan->n_strips, index_offset, approx_inv_scale, out_approx, out_gidx, row0);
+    kdi_select_warp_kernel<64><<<grid, 32 * kWarpSelRows, 0, stream>>>(
+        cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx);
   else
     return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
   KDI_CUDA(ctx, cudaGetLastError());

@@ -5,6 +5,7 @@ import torch
 import kikuchipy_b200 as kb
 from kikuchipy_b200 import _lib
 M, N, SIG = int(os.environ.get("M", "10000")), int(os.environ.get("N", "100000")), (60, 60)
+KEEP = int(os.environ.get("KEEP", "20"))
 ctx = kb.default_context(0)
 for name, opt in (("OVERLAP", _lib.OPT_OVERLAP), ("SUPERBLOCK", _lib.OPT_SUPERBLOCK), ("MAX_STAGES", _lib.OPT_MAX_STAGES)):
     if os.environ.get(name):
@@ -13,7 +14,7 @@ dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(1)
 exp = torch.randint(0, 256, (M,) + SIG, dtype=torch.uint8, device=dev, generator=g)
 dic = torch.rand((N,) + SIG, dtype=torch.float32, device=dev, generator=g)
-idx = torch.empty((M, 20), dtype=torch.int64, device=dev); sc = torch.empty((M, 20), dtype=torch.float32, device=dev)
+idx = torch.empty((M, KEEP), dtype=torch.int64, device=dev); sc = torch.empty((M, KEEP), dtype=torch.float32, device=dev)
 torch.cuda.synchronize()
 gen = None
 if os.environ.get("GEN"):
@@ -28,7 +29,7 @@ for i in range(4):
     else:
         sys.stderr.flush()
     if gen is not None:
-        ctx.dictionary_indexing_projected(exp, M, gen, rot, _lib.KDI_NCC, 20, out=(idx, sc))
+        ctx.dictionary_indexing_projected(exp, M, gen, rot, _lib.KDI_NCC, KEEP, out=(idx, sc))
     else:
-        ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, 20, out=(idx, sc))
+        ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, KEEP, out=(idx, sc))
 print({k: round(v, 3) if isinstance(v, float) else v for k, v in ctx.timings().items()})
