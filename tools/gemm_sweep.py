@@ -27,6 +27,8 @@ SETTINGS = [(0, 0, 0, 0), (0, 0, 1, 0), (0, 0, 2, 0), (0, 0, 3, 0), (0, 0, 0, 1)
             (40, 0, 0, 0), (40, 4, 0, 0), (40, 4, 0, 1), (40, 4, 1, 1), (40, 9, 1, 1), (40, 16, 0, 0)]
 if os.environ.get("SETTINGS"):
     SETTINGS = [tuple(int(x) for x in s.split(",")) for s in os.environ["SETTINGS"].split(";")]
+if os.environ.get("OVERLAP"):
+    ctx.set_option(_lib.OPT_OVERLAP, int(os.environ["OVERLAP"]))
 ROUNDS = int(os.environ.get("ROUNDS", "1"))  # > 1: settings interleaved (A B C A B C ...) so that clock / power drift
                                             # over the run does not favour whichever setting happens to run first
 ref = None
