@@ -188,6 +188,10 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
  *  2. caller: all-gather the (approx, gidx) lists of all ranks, kdi_merge_topk them to rows x kc.
  *  3. kdi_shard_rescore_owned exact float32 scores of the merged candidates whose dictionary rows
  *                            this rank holds (-inf for the others).  Device buffers, rows x kc.
+ *                            approx (optional, the merged tensor-core scores, same on every
+ *                            rank): candidates past the first keep_n + 4 that lie far below the
+ *                            keep_n-th tensor-core score are not read (-inf); step 5 verifies
+ *                            that none of them could matter, else the row is flagged.
  *  4. caller: all-reduce(MAX) the exact scores over the ranks.
  *  5. kdi_shard_finalize     rank by exact score, write rows x keep_n results, apply the
  *                            certificate; flags_out (device, rows ints) / n_flag_out (host) list
@@ -206,7 +210,7 @@ int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, in
                          const uint8_t* nav_mask, int64_t index_offset, float* approx_out,
                          int64_t* gidx_out, kdi_shard** out);
 int kdi_shard_rescore_owned(kdi_ctx* ctx, const kdi_shard* shard, const int64_t* gidx,
-                            float* exact_out);
+                            const float* approx, int keep_n, float* exact_out);
 int kdi_shard_finalize(kdi_ctx* ctx, const kdi_shard* shard, int64_t row0, int64_t rows,
                        const float* approx, const int64_t* gidx, const float* exact, int keep_n,
                        int64_t dict_total, float* scores_out, int64_t* indices_out, int* flags_out,

@@ -101,7 +101,7 @@ SIGNATURES = {
         _i,
         [_vp, _vp, _i, _i, _i64, _vp, _i, _i, _i64, _i64, _i, _i, _vp, _i64, _vp, _vp, C.POINTER(_vp)],
     ),
-    "kdi_shard_rescore_owned": (_i, [_vp, _vp, _vp, _vp]),
+    "kdi_shard_rescore_owned": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "kdi_shard_finalize": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, C.POINTER(_i)]),
     "kdi_shard_exact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "kdi_shard_release": (_i, [_vp, _vp]),
@@ -220,9 +220,11 @@ class Shard:
     def __init__(self, ctx: "Context", handle: int, rows: int, kc: int):
         self._ctx, self._h, self.rows, self.kc = ctx, handle, rows, kc
 
-    def rescore_owned(self, gidx):
+    def rescore_owned(self, gidx, approx=None, keep_n: int = 0):
         """Exact scores of the candidates in ``gidx`` (at least ``rows`` x kc) whose dictionary rows
-        this rank holds; -inf elsewhere (also in rows past ``rows``: padding of the row split)."""
+        this rank holds; -inf elsewhere (also in rows past ``rows``: padding of the row split).
+        With ``approx`` (the merged tensor-core scores) and ``keep_n``, candidates that cannot
+        reach the top ``keep_n`` are not read (``finalize`` verifies that)."""
         import torch
 
         n = max(int(gidx.shape[0]), self.rows)
@@ -230,7 +232,9 @@ class Shard:
         if n > self.rows:
             exact[self.rows:].fill_(-float("inf"))
         self._ctx._stream_sync(gidx.device)
-        self._ctx._check(self._ctx._lib.kdi_shard_rescore_owned(self._ctx._h, self._h, gidx.data_ptr(), exact.data_ptr()))
+        self._ctx._check(self._ctx._lib.kdi_shard_rescore_owned(
+            self._ctx._h, self._h, gidx.data_ptr(), approx.data_ptr() if approx is not None else None,
+            int(keep_n), exact.data_ptr()))
         return exact
 
     def finalize(self, approx, gidx, exact, keep_n: int, dict_total: int, row0: int = 0, rows: int | None = None):

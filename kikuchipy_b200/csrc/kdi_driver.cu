@@ -724,13 +724,17 @@ int kdi_shard_candidates_projected(kdi_ctx* ctx, const void* experimental, int e
   return rc;
 }
 
-int kdi_shard_rescore_owned(kdi_ctx* ctx, const kdi_shard* shard, const int64_t* gidx, float* exact_out) {
+int kdi_shard_rescore_owned(kdi_ctx* ctx, const kdi_shard* shard, const int64_t* gidx, const float* approx,
+                            int keep_n, float* exact_out) {
   if (!ctx) return KDI_EINVAL;
   if (!shard || !gidx || !exact_out) return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_rescore_owned: NULL argument");
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  // pruning margin: twice the certificate width at the noise level measured for each operand type
+  // (std of tensor-core minus exact score: 4.5e-6 with fp16 operands, 3.6e-5 with bf16)
+  const float margin = 2.0f * (float)ctx->cert_sigmas * (shard->exp->compute_dtype == 1 ? 3.6e-5f : 4.5e-6f) + 2e-5f;
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
   KDI_TRY(kdi_launch_rescore_owned(ctx, ctx->stream, shard->exp, shard->dict, shard->index_offset,
-                                   shard->kc, gidx, exact_out));
+                                   shard->kc, gidx, approx, keep_n, margin, exact_out));
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
   KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->tm.rescore_ms += ev_ms(ctx->ev[3], ctx->ev[4]);

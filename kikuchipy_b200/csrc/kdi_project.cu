@@ -26,7 +26,6 @@
 namespace {
 
 constexpr int kProjThreads = 256;
-constexpr double kSqrtPiHalf = 1.2533141373155002512;     // sqrt(pi / 2)
 constexpr double kSqrtPiOver2 = 0.88622692545275801365;   // sqrt(pi) / 2
 constexpr double kTwoOverSqrtPi = 1.1283791670955125739;  // 2 / sqrt(pi)
 
@@ -38,6 +37,7 @@ struct ProjParams {
   int npx, npy;       // as the reference passes them (npx bounds the row index, npy the column index)
   int ld;             // row pitch of the master pattern arrays (elements)
   double scale;
+  double scale_over_sqrt_pi_half;
   int rescale;
   double out_min, out_max;
   int64_t S;
@@ -102,7 +102,7 @@ __device__ __forceinline__ double project_pixel(const ProjParams& p, const doubl
   // _vector2lambert (:541-566)
   // (one reciprocal instead of the reference's three divisions: at most one ulp of float64 apart;
   // an exact pole, x = y = 0, is recognised below whatever |wz| rounds to)
-  const double inv = 1.0 / sqrt(x * x + y * y + z * z);
+  const double inv = rsqrt(x * x + y * y + z * z);
   const double wx = x * inv, wy = y * inv, wz = z * inv;
   const double abs_z = fabs(wz);
   const double sqrt_z = sqrt(2.0 * (1.0 - abs_z));
@@ -119,8 +119,9 @@ __device__ __forceinline__ double project_pixel(const ProjParams& p, const doubl
     }
   }
   // _get_lambert_interpolation_parameters (:638-676)
-  const double i_this = p.scale * ly / kSqrtPiHalf;
-  const double j_this = p.scale * lx / kSqrtPiHalf;
+  // scale * l / sqrt(pi / 2) with the constant folded: within one ulp of float64 of the reference
+  const double i_this = ly * p.scale_over_sqrt_pi_half;
+  const double j_this = lx * p.scale_over_sqrt_pi_half;
   int nii = (int)(i_this + p.scale);  // truncation towards zero, like np.int32(float)
   int nij = (int)(j_this + p.scale);
   int niip = nii + 1, nijp = nij + 1;
@@ -264,6 +265,7 @@ int kdi_launch_project(kdi_ctx* ctx, cudaStream_t stream, const kdi_master_patte
   p.npy = mp->npy;
   p.ld = mp->npx;
   p.scale = mp->scale;
+  p.scale_over_sqrt_pi_half = mp->scale / 1.2533141373155002512;
   p.rescale = mp->rescale;
   p.out_min = mp->out_min;
   p.out_max = mp->out_max;

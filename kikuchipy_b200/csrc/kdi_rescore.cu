@@ -368,18 +368,25 @@ kdi_select_only_kernel(const uint2* __restrict__ cand, const uint32_t* __restric
 }
 
 // exact scores of the candidates whose dictionary rows live in this shard; -inf elsewhere
+// Pruning (approx != NULL; lists sorted by tensor-core score): beyond the first keep_n + 4
+// candidates, one whose tensor-core score lies more than `margin` below the keep_n-th best
+// tensor-core score is not read at all (every rank takes the same decision from the same lists);
+// the finalize step verifies, with the error model measured on the rescored candidates, that none
+// of the skipped ones could have entered the top keep_n - otherwise the row is flagged.
 __global__ void __launch_bounds__(kSelThreads)
 kdi_rescore_owned_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
                          int64_t s_pitch, int64_t shard_start, int64_t shard_rows, int kc,
-                         const int64_t* __restrict__ gidx, float* __restrict__ exact) {
+                         const int64_t* __restrict__ gidx, const float* __restrict__ approx, int keep_n,
+                         float margin, float* __restrict__ exact) {
   const int64_t row = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4* a = reinterpret_cast<const float4*>(exp32 + row * s_pitch);
   const int n4 = (int)(s_pitch >> 2);
+  const float floor_score = (approx && keep_n <= kc) ? approx[row * kc + keep_n - 1] - margin : -INFINITY;
   for (int i = warp; i < kc; i += kSelThreads / 32) {
     const int64_t g = gidx[row * kc + i] - shard_start;  // warp-uniform
     float d = -INFINITY;
-    if (g >= 0 && g < shard_rows)
+    if (g >= 0 && g < shard_rows && (i < keep_n + 4 || !approx || approx[row * kc + i] >= floor_score))
       d = warp_dot(a, reinterpret_cast<const float4*>(dict32 + g * s_pitch), n4, lane);
     if (lane == 0) exact[row * kc + i] = d;
   }
@@ -395,6 +402,7 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
   __shared__ float ap[64];
   __shared__ int64_t gi[64];
   __shared__ float s_red[4];
+  __shared__ float s_red2[4];
   __shared__ int s_nsel;
   const int64_t row = blockIdx.x;
   const int tid = threadIdx.x;
@@ -412,9 +420,13 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
   }
   __syncthreads();
   const int nsel = s_nsel;  // valid entries come first (lists are sorted by approx, padding last)
-  float err1 = 0.f, err2 = 0.f, my_s = 0.f;
+  // candidates the owner did not rescore (pruned: exact == -inf) take no part in the ranking or
+  // the error statistics; the best tensor-core score among them is checked by the certificate
+  const bool scored = valid && ex[tid] != -INFINITY;
+  float err1 = 0.f, err2 = 0.f, my_s = 0.f, cnt1 = scored ? 1.f : 0.f;
+  float skipped_ap = (valid && !scored) ? ap[tid] : -INFINITY;
   int rank = 64;
-  if (valid) {
+  if (scored) {
     my_s = ex[tid];
     const float d = my_s - ap[tid];
     err1 = d;
@@ -429,24 +441,33 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
   for (int o = 16; o > 0; o >>= 1) {
     err1 += __shfl_xor_sync(0xffffffffu, err1, o);
     err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+    cnt1 += __shfl_xor_sync(0xffffffffu, cnt1, o);
+    skipped_ap = fmaxf(skipped_ap, __shfl_xor_sync(0xffffffffu, skipped_ap, o));
   }
-  if ((tid & 31) == 0) { s_red[tid >> 5] = err1; s_red[2 + (tid >> 5)] = err2; }
+  if ((tid & 31) == 0) {
+    s_red[tid >> 5] = err1; s_red[2 + (tid >> 5)] = err2; s_red2[tid >> 5] = cnt1; s_red2[2 + (tid >> 5)] = skipped_ap;
+  }
   __syncthreads();
-  if (valid && rank < keep_n) {
+  const float n_scored = s_red2[0] + s_red2[1];
+  if (scored && rank < keep_n) {
     out_scores[row * keep_n + rank] = my_s;
     out_idx[row * keep_n + rank] = gi[tid];
   }
-  if (valid && rank == keep_n - 1) {
+  if (scored && rank == keep_n - 1) {
     bool ok = true;
-    if (n_dict_total > (int64_t)nsel) {
-      const float bias = (s_red[0] + s_red[1]) / (float)nsel;  // exact = approx + bias + noise
-      const float sigma = sqrtf(fmaxf((s_red[2] + s_red[3]) / (float)nsel - bias * bias, 0.f));
+    const bool any_skipped = n_scored < (float)nsel;
+    if (n_dict_total > (int64_t)nsel || any_skipped) {
+      const float bias = (s_red[0] + s_red[1]) / n_scored;  // exact = approx + bias + noise
+      const float sigma = sqrtf(fmaxf((s_red[2] + s_red[3]) / n_scored - bias * bias, 0.f));
       const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 0.1f * fabsf(bias) + 1e-7f;
-      ok = (nsel == kc) && (my_s > ap[nsel - 1] + bias + eps);
+      // nothing outside the rescored set may reach the keep_n-th exact score: neither a row the
+      // tensor-core pass discarded (score <= the smallest retained one) nor a pruned candidate
+      if (n_dict_total > (int64_t)nsel) ok = (nsel == kc) && (my_s > ap[nsel - 1] + bias + eps);
+      if (any_skipped) ok = ok && (my_s > fmaxf(s_red2[2], s_red2[3]) + bias + eps);
     }
     if (!ok) flag_list[atomicAdd(n_flag, 1)] = (int)(row0 + row);
   }
-  if (tid == 0 && nsel < keep_n) flag_list[atomicAdd(n_flag, 1)] = (int)(row0 + row);
+  if (tid == 0 && n_scored < (float)keep_n) flag_list[atomicAdd(n_flag, 1)] = (int)(row0 + row);
 }
 
 // ---- exact path -----------------------------------------------------------------------------
@@ -663,10 +684,12 @@ int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, cons
 
 int kdi_launch_rescore_owned(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
                              const kdi_patterns* dict, int64_t shard_start, int kc,
-                             const int64_t* gidx, float* exact) {
+                             const int64_t* gidx, const float* approx, int keep_n, float margin,
+                             float* exact) {
   if (exp->rows <= 0) return KDI_OK;
+  kdi_span span(ctx, stream, "rescore (owned candidates)");
   kdi_rescore_owned_kernel<<<(unsigned)exp->rows, kSelThreads, 0, stream>>>(
-      exp->a32, dict->a32, exp->s_pitch, shard_start, dict->rows, kc, gidx, exact);
+      exp->a32, dict->a32, exp->s_pitch, shard_start, dict->rows, kc, gidx, approx, keep_n, margin, exact);
   KDI_CUDA(ctx, cudaGetLastError());
   ctx->tm.kernel_launches++;
   return KDI_OK;

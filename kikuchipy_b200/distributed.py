@@ -116,6 +116,24 @@ def gather_experimental(experimental_host: np.ndarray, n_rows: int, device, grou
     return full[:n_rows]
 
 
+def _pack(scores, indices):
+    """(float32 scores, int64 indices) of equal shape -> one byte tensor ``(..., 12)`` so that both
+    travel in ONE collective (one concatenation kernel; NCCL launch latency dominates here)."""
+    import torch
+
+    s = scores.contiguous()
+    i = indices.contiguous()
+    return torch.cat([s.view(torch.uint8).view(s.shape + (4,)), i.view(torch.uint8).view(i.shape + (8,))], dim=-1)
+
+
+def _unpack(packed):
+    import torch
+
+    scores = packed[..., :4].contiguous().view(torch.float32).squeeze(-1)
+    indices = packed[..., 4:].contiguous().view(torch.int64).squeeze(-1)
+    return scores, indices
+
+
 class _KdiStages:
     """The GPU stages of the pipeline: thin calls into libkdi (``kdi_shard_*``)."""
 
@@ -140,8 +158,8 @@ class _KdiStages:
     def merge(self, s_all, i_all, k):
         return self.ctx.merge_topk(s_all, i_all, k)
 
-    def rescore_owned(self, gidx):
-        return self.shard.rescore_owned(gidx)
+    def rescore_owned(self, gidx, approx, keep_n):
+        return self.shard.rescore_owned(gidx, approx, keep_n)
 
     def finalize(self, approx, gidx, exact, keep_n, dict_total, row0, rows):
         return self.shard.finalize(approx, gidx, exact, keep_n, dict_total, row0=row0, rows=rows)
@@ -169,20 +187,22 @@ def run_sharded_pipeline(stages, n_rows: int, keep_n: int, dictionary_size: int,
     approx, gidx, kc = stages.candidates(padded)
     trace("candidates")
     # 2. all-to-all by row slice: block j of the send buffer (rows of slice j) goes to rank j;
-    #    the receive buffer is list-major (list l = rank l's candidates for MY rows)
-    s_in = torch.empty((world, per, kc), dtype=approx.dtype, device=approx.device)
-    i_in = torch.empty((world, per, kc), dtype=gidx.dtype, device=gidx.device)
-    dist.all_to_all_single(s_in, approx.contiguous(), group=group)
-    dist.all_to_all_single(i_in, gidx.contiguous(), group=group)
+    #    the receive buffer is list-major (list l = rank l's candidates for MY rows).  Scores and
+    #    indices travel as one 12-byte record per candidate (one collective instead of two).
+    packed_in = torch.empty((world, per, kc, 12), dtype=torch.uint8, device=approx.device)
+    dist.all_to_all_single(packed_in, _pack(approx, gidx), group=group)
+    s_in, i_in = _unpack(packed_in)
     trace("all_to_all")
     my_idx, my_approx = stages.merge(s_in, i_in, kc)
     trace("merge")
-    # 3. everyone learns every row's merged candidates
-    g_idx = torch.empty((padded, kc), dtype=my_idx.dtype, device=my_idx.device)
-    dist.all_gather_into_tensor(g_idx, my_idx.contiguous(), group=group)
+    # 3. everyone learns every row's merged candidates (indices + tensor-core scores)
+    g_packed = torch.empty((padded, kc, 12), dtype=torch.uint8, device=my_idx.device)
+    dist.all_gather_into_tensor(g_packed, _pack(my_approx, my_idx), group=group)
+    g_approx, g_idx = _unpack(g_packed)
     trace("all_gather_idx")
-    # 4. exact scores of the candidates whose dictionary rows this rank holds (-inf elsewhere)
-    exact = stages.rescore_owned(g_idx)
+    # 4. exact scores of the candidates whose dictionary rows this rank holds (-inf elsewhere, and
+    #    for candidates too far below the keep_n-th tensor-core score to matter)
+    exact = stages.rescore_owned(g_idx, g_approx, keep_n)
     trace("rescore_owned")
     # 5. each candidate has exactly one owner: MAX combines, scattered back by row slice
     my_exact = torch.empty((per, kc), dtype=exact.dtype, device=exact.device)

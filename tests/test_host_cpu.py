@@ -133,7 +133,7 @@ class _OracleStages:
         mi, ms = self._rank(s, i, k)
         return self.t.from_numpy(mi.copy()), self.t.from_numpy(ms.copy())
 
-    def rescore_owned(self, gidx):
+    def rescore_owned(self, gidx, approx, keep_n):
         g = gidx.numpy()
         rows, n = self.sim.shape
         out = np.full((max(rows, g.shape[0]), g.shape[1]), -np.inf, np.float32)
