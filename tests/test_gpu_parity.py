@@ -27,6 +27,7 @@ def ctx():
     for opt in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK,
                 _lib.OPT_MAX_STAGES):
         c.set_option(opt, 0)
+    c.set_option(_lib.OPT_SPLIT_SELECT, 1)
     c.set_option(_lib.OPT_CTA_GROUP, 2)
     c.set_option(_lib.OPT_OVERLAP, 1)
     c.set_signal_mask(None)
@@ -145,6 +146,10 @@ CASES = [
     (9, 20, (60, 60), 20, "ncc", False, False, {}),          # dictionary smaller than the candidate list
     (33, 100, (12, 12), 60, "ncc", False, False, {}),        # keep_n beyond the fused path -> exact path
     (64, 4096, (60, 60), 20, "ncc", False, False, {"exact": 1}),
+    (1, 1, (3, 3), 1, "ncc", False, False, {}),               # one pattern, one dictionary entry
+    (3, 2, (5, 7), 2, "ndp", False, False, {}),               # keep_n equal to the dictionary size
+    (7, 300, (240, 240), 10, "ncc", True, False, {"cg": 2}),  # 57 600-pixel detector, masked (generic normalise path)
+    (300, 5000, (60, 60), 20, "ncc", True, True, {"cg": 2, "split": 0}),  # selection inside the rescoring kernel
 ]
 
 
@@ -156,6 +161,7 @@ def test_random_workloads(ctx, case):
     ctx.set_option(_lib.OPT_FORCE_EXACT, opt.get("exact", 0))
     ctx.set_option(_lib.OPT_STRIP_TILES, opt.get("strip", 0))
     ctx.set_option(_lib.OPT_SUPERBLOCK, opt.get("sb", 0))
+    ctx.set_option(_lib.OPT_SPLIT_SELECT, opt.get("split", 1))
     try:
         exp = orc.synthetic_experimental(M, sig, seed=1)
         dic = orc.synthetic_dictionary(N, sig, seed=2)
@@ -174,7 +180,42 @@ def test_random_workloads(ctx, case):
         for o in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK):
             ctx.set_option(o, 0)
         ctx.set_option(_lib.OPT_CTA_GROUP, 2)
+        ctx.set_option(_lib.OPT_SPLIT_SELECT, 1)
         ctx.set_signal_mask(None)
+
+
+@pytest.mark.parametrize("src_dtype", [np.uint16, np.float32, np.float64])
+def test_source_dtypes_host_and_device(ctx, src_dtype):
+    """Experimental patterns of every accepted source type, from host and from device memory, give
+    the result of the reference's cast-to-float32-first arithmetic."""
+    import torch
+
+    rng = np.random.default_rng(8)
+    exp = (rng.random((70, 24, 24)) * 1000).astype(src_dtype)
+    dic = orc.synthetic_dictionary(1500, (24, 24), seed=2)
+    ridx, rsc = orc.dictionary_indexing(exp.astype(np.float32), dic, keep_n=12, n_experimental_patterns=70)
+    idx, sc = ctx.dictionary_indexing(exp, 70, dic, 1500, _lib.KDI_NCC, 12)
+    _check(ridx, rsc, idx, sc)
+    if src_dtype != np.uint16:
+        i2 = torch.empty((70, 12), dtype=torch.int64, device="cuda"); s2 = torch.empty((70, 12), dtype=torch.float32, device="cuda")
+        ctx.dictionary_indexing(torch.from_numpy(exp).cuda(), 70, torch.from_numpy(dic).cuda(), 1500, _lib.KDI_NCC, 12, out=(i2, s2))
+        assert np.array_equal(i2.cpu().numpy(), idx) and np.array_equal(s2.cpu().numpy(), sc)
+
+
+def test_constant_pattern_gives_nan_row_without_disturbing_others(ctx):
+    """A constant experimental pattern has zero variance: the reference divides 0 by 0 and that
+    row's scores are NaN (its index order is then arbitrary).  The other rows must be unaffected
+    and the call must not hang."""
+    exp = orc.synthetic_experimental(40, (20, 20), seed=1)
+    exp[7] = 128
+    dic = orc.synthetic_dictionary(900, (20, 20), seed=2)
+    idx, sc = ctx.dictionary_indexing(exp, 40, dic, 900, _lib.KDI_NCC, 10)
+    assert np.all(np.isnan(sc[7]))
+    keep = np.arange(40) != 7
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ridx, rsc = orc.dictionary_indexing(exp, dic, keep_n=10, n_experimental_patterns=40)
+    _check(ridx[keep], rsc[keep], idx[keep], sc[keep])
+    assert idx.min() >= 0 and idx.max() < 900
 
 
 def test_fused_and_exact_paths_agree_bit_for_bit(ctx):
