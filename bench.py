@@ -203,6 +203,9 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: keep this rank's pinned buffers on the GPU's own NUMA node (N = 1 keeps
+    # all cores for the CPU baseline)
+    numa_cpus = kb.bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else None
     ctx = kb.default_context(local_rank)
     if args.cta_group:
         ctx.set_option(_lib.OPT_CTA_GROUP, args.cta_group)
@@ -309,7 +312,7 @@ def run_ours(args, rank, world, local_rank):
     # pinned host patterns and this rank's rotations, no float32 dictionary crosses PCIe
     gen_ms = None
     if not args.no_generated:
-        from oracle import projection_oracle as po  # synthetic master pattern / rotations only
+        from kikuchipy_b200 import synthetic as po  # synthetic master pattern / rotations
 
         mu, ml = po.synthetic_master_pattern(args.master_pattern_size, seed=5)
         dc = kb.direction_cosines([-0.9, 0.85, -0.7, 0.95], 0.5, SIG[0], SIG[1], po.tilted_detector_matrix(70.0))
@@ -368,6 +371,7 @@ def run_ours(args, rank, world, local_rank):
             "operands": "16-bit tensor-core candidates (fp32 accumulate) + exact fp32 rescoring of every reported score",
             "l2": "inputs larger than L2 (dictionary shard %.0f MB raw)" % (dict_dev.numel() * 4 / 1e6),
             "cta_group": args.cta_group or 2,
+            "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None),
             "stage_ms": {k: round(float(np.mean([x[k] for x in tms])), 4)
                          for k in ("normalize_exp_ms", "normalize_dict_ms", "gemm_topk_ms", "rescore_ms",
                                    "fallback_ms", "total_ms")},
@@ -417,6 +421,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=500)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-generated", action="store_true", help="skip the generated-dictionary end-to-end leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--master-pattern-size", type=int, default=1001)
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--compute-dtype", default="fp16", choices=["fp16", "bf16"])

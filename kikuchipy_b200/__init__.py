@@ -6,7 +6,7 @@ Everything numerical runs in ``libkdi.so`` (hand-written sm_100a CUDA behind the
 ``include/kdi.h``); importing this package does not need a GPU, calling it does.
 """
 
-from ._lib import Context, KdiError, default_context
+from ._lib import Context, KdiError, bind_to_gpu_numa_node, default_context
 from .indexing import DictionaryIndexingResult, dictionary_indexing, orientation_similarity_map
 from .similarity_metrics import (
     NormalizedCrossCorrelationMetric,
@@ -24,6 +24,7 @@ __all__ = [
     "NormalizedCrossCorrelationMetric",
     "NormalizedDotProductMetric",
     "SimilarityMetric",
+    "bind_to_gpu_numa_node",
     "default_context",
     "dictionary_indexing",
     "dictionary_indexing_sharded",

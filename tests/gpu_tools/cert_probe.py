@@ -2,7 +2,7 @@
 import os, sys
 import numpy as np
 import torch
-ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, ROOT)
 import kikuchipy_b200 as kb
 from kikuchipy_b200 import _lib

@@ -4,7 +4,7 @@ master pattern, experimental patterns = projections at slightly perturbed dictio
 random dictionaries), which is what real EBSD dictionaries look like.  Reports the rows the
 certificate sends to the exact path and compares a sample against the forced-exact path."""
 import os, sys, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import kikuchipy_b200 as kb
 from kikuchipy_b200 import _lib

@@ -1,7 +1,7 @@
 """Run one BASELINE.json configuration at FULL size on the GPU(s), verify it, print one JSON line.
 
-  python tools/run_config.py --config 2|3                                   (one GPU)
-  python -m torch.distributed.run --nproc-per-node 8 ... tools/run_config.py --config 4|5
+  python tests/gpu_tools/run_config.py --config 2|3                                   (one GPU)
+  python -m torch.distributed.run --nproc-per-node 8 ... tests/gpu_tools/run_config.py --config 4|5
 
   2: 10 000 x 100 000, 60x60, NCC, keep_n 20            (1 GPU)
   3: 40 000 x 100 000, 120x120, circular mask, NDP      (1 GPU)
@@ -32,7 +32,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {

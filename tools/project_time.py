@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import kikuchipy_b200 as kb
 from kikuchipy_b200 import _lib
-from oracle import projection_oracle as po
+from kikuchipy_b200 import synthetic as po
 ctx = kb.default_context(0)
 N = int(os.environ.get("N", "100000"))
 for size in (401, 1001):

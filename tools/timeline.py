@@ -18,7 +18,7 @@ idx = torch.empty((M, KEEP), dtype=torch.int64, device=dev); sc = torch.empty((M
 torch.cuda.synchronize()
 gen = None
 if os.environ.get("GEN"):
-    from oracle import projection_oracle as po
+    from kikuchipy_b200 import synthetic as po
     mu, ml = po.synthetic_master_pattern(1001, seed=5)
     dcs = kb.direction_cosines([-0.9, 0.85, -0.7, 0.95], 0.5, 60, 60, po.tilted_detector_matrix(70.0))
     rot = torch.from_numpy(po.random_rotations(N, seed=4)).cuda()
