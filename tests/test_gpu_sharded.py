@@ -37,8 +37,18 @@ def _worker(rank, world, port, tmp):
         idx2, sc2 = kb.dictionary_indexing_sharded(exp2, dic2[start:end], 7001, metric="ncc", keep_n=20, context=ctx)
         # keep_n beyond the candidate pipeline
         idx3, sc3 = kb.dictionary_indexing_sharded(exp[:2], dic[start:end], 7001, metric="ndp", keep_n=60, context=ctx)
+        # dictionary generated on the device: every rank projects its own slice of the rotations
+        from oracle import projection_oracle as po
+
+        mu, ml = po.synthetic_master_pattern(201, seed=3)
+        dc = po.direction_cosines_fixed_pc([-0.9, 0.85, -0.7, 0.95], 0.5, 40, 40, po.tilted_detector_matrix(70.0))
+        rot = po.random_rotations(7001, seed=2)
+        gen = kb.get_patterns(mu, ml, rot[start:end], direction_cosines=dc, detector_shape=(40, 40), context=ctx)
+        idx4, sc4 = kb.dictionary_indexing_sharded(exp, gen, 7001, metric="ncc", keep_n=20, navigation_mask=nav,
+                                                   signal_mask=smask, context=ctx)
         np.savez(os.path.join(tmp, f"r{rank}.npz"), idx=idx.cpu().numpy(), sc=sc.cpu().numpy(),
-                 idx2=idx2.cpu().numpy(), sc2=sc2.cpu().numpy(), idx3=idx3.cpu().numpy(), sc3=sc3.cpu().numpy())
+                 idx2=idx2.cpu().numpy(), sc2=sc2.cpu().numpy(), idx3=idx3.cpu().numpy(), sc3=sc3.cpu().numpy(),
+                 idx4=idx4.cpu().numpy(), sc4=sc4.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
@@ -68,4 +78,14 @@ def test_two_gpu_shards_equal_unsharded(tmp_path):
     assert np.array_equal(z0["idx2"], z1["idx2"])
     ridx3, rsc3 = orc.dictionary_indexing(exp[:2], dic, metric="ndp", keep_n=60, n_experimental_patterns=40)
     r = orc.compare_topk(ridx3, rsc3, z0["idx3"], z0["sc3"])
+    assert r["tie_ok"] and r["scores_ok"], r
+    # generated, sharded dictionary == the oracle on the oracle's projection of all rotations
+    from oracle import projection_oracle as po
+
+    mu, ml = po.synthetic_master_pattern(201, seed=3)
+    dc = po.direction_cosines_fixed_pc([-0.9, 0.85, -0.7, 0.95], 0.5, 40, 40, po.tilted_detector_matrix(70.0))
+    patterns = po.project_patterns(po.random_rotations(7001, seed=2), dc, mu, ml).reshape(7001, 40, 40)
+    ridx4, rsc4 = orc.dictionary_indexing(exp, patterns, keep_n=20, navigation_mask=nav, signal_mask=smask)
+    assert np.array_equal(z0["idx4"], z1["idx4"]) and np.array_equal(z0["sc4"], z1["sc4"])
+    r = orc.compare_topk(ridx4, rsc4, z0["idx4"], z0["sc4"], tie_tol=2e-5)
     assert r["tie_ok"] and r["scores_ok"], r
