@@ -205,7 +205,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     # one process per GPU: keep this rank's pinned buffers on the GPU's own NUMA node (N = 1 keeps
     # all cores for the CPU baseline)
-    numa_cpus = kb.bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else None
+    numa_cpus = kb.bind_to_gpu_numa_node(local_rank) if world > 1 and args.numa_bind else None
     ctx = kb.default_context(local_rank)
     if args.cta_group:
         ctx.set_option(_lib.OPT_CTA_GROUP, args.cta_group)
@@ -421,7 +421,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=500)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-generated", action="store_true", help="skip the generated-dictionary end-to-end leg")
-    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind ranks to their GPU's NUMA node")
+    ap.add_argument("--numa-bind", action="store_true",
+                    help="bind each rank to its GPU's NUMA node (no effect on single-node-affinity boxes like this pool's)")
     ap.add_argument("--master-pattern-size", type=int, default=1001)
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--compute-dtype", default="fp16", choices=["fp16", "bf16"])

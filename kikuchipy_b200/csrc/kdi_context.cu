@@ -215,6 +215,7 @@ int kdi_init(int device, kdi_ctx** out) {
   for (auto& ev : ctx->free_ev) INIT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 #undef INIT_CUDA
   if (const char* tl = getenv("KDI_TIMELINE")) ctx->timeline = atoi(tl);
+  if (const char* pg = getenv("KDI_POST_PER_GROUP")) ctx->post_per_group = atoi(pg);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&

@@ -155,8 +155,10 @@ static void sync_all_streams(kdi_ctx* ctx) {
 //   aux : normalise dictionary rows [g1_rows, N)  (small resident grid; queued by the caller)
 //   main: normalise rows [0, g1_rows) -> GEMM(all row blocks, strips below g1_rows)
 //   main/gemm2 alternating, after the aux normalise: GEMM(row-block group i, remaining strips)
-//   aux : post-processing (selection + exact rescoring) of group i as soon as its GEMM is done
-// Only the first slice of the normalisation and the last group's rescoring are exposed.
+//   main: post-processing (selection + exact rescoring) of all rows once the GEMM launches are done
+// One GEMM launch per row-block group keeps the CTAs inside one L2 super-block (a single launch
+// striding over all groups reads 2-4x more from DRAM), and alternating the
+// streams lets the next launch fill the tail of the previous one.
 // `strips_lo` strips have already been launched on the main stream for every row block;
 // `e_fill` (may be NULL) is the event the remaining strips have to wait for.
 static int run_overlapped(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
@@ -187,23 +189,33 @@ static int run_overlapped(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* 
     if (strips_lo < pl.n_strips)
       KDI_TRY(kdi_launch_gemm_topk(ctx, sg, exp, dict, &pl, strips_lo, pl.n_strips - strips_lo, job->cand,
                                    job->thr, mb0, mbn));
-    cudaEvent_t e_g = ctx->dep_ev[ev_i++];
-    KDI_CUDA(ctx, cudaEventRecord(e_g, sg));
-    KDI_CUDA(ctx, cudaStreamWaitEvent(sa, e_g, 0));
-    const int64_t row0 = (int64_t)mb0 * rows_per_mb;
-    const int64_t n_rows = std::min<int64_t>(job->M - row0, (int64_t)mbn * rows_per_mb);
-    KDI_TRY(launch_post(ctx, sa, job, exp, dict, post, row0, n_rows));
+    if (ctx->post_per_group) {
+      // (only useful when the post-processing kernels may share SMs with the GEMM kernel - see
+      // kdi_gemm_carveout_pref; otherwise they would just queue up behind the GEMM launches as
+      // many small latency-bound kernels)
+      cudaEvent_t e_g = ctx->dep_ev[ev_i++];
+      KDI_CUDA(ctx, cudaEventRecord(e_g, sg));
+      KDI_CUDA(ctx, cudaStreamWaitEvent(sa, e_g, 0));
+      const int64_t row0 = (int64_t)mb0 * rows_per_mb;
+      const int64_t n_rows = std::min<int64_t>(job->M - row0, (int64_t)mbn * rows_per_mb);
+      KDI_TRY(launch_post(ctx, sa, job, exp, dict, post, row0, n_rows));
+    }
   }
   job->strips_done = pl.n_strips;
-  // join: GEMM span ends when both GEMM streams are done; the job when the aux stream is
+  // join: the GEMM span ends when both GEMM streams are done
   cudaEvent_t e_s2 = ctx->dep_ev[ev_i++];
   KDI_CUDA(ctx, cudaEventRecord(e_s2, s2));
   KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_s2, 0));
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[9], sm));
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], sm));
-  cudaEvent_t e_aux = ctx->dep_ev[ev_i++];
-  KDI_CUDA(ctx, cudaEventRecord(e_aux, sa));
-  KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_aux, 0));
+  if (ctx->post_per_group) {
+    cudaEvent_t e_aux = ctx->dep_ev[ev_i++];
+    KDI_CUDA(ctx, cudaEventRecord(e_aux, sa));
+    KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_aux, 0));
+  } else {
+    // selection + rescoring of every row in one launch each (HBM-bound; full-size grids)
+    KDI_TRY(launch_post(ctx, sm, job, exp, dict, post, 0, job->M));
+  }
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], sm));
   return KDI_OK;
 }

@@ -48,6 +48,27 @@ def _check(ridx, rsc, idx, sc, tie_tol=1e-6, strict=False):
 
 # ---- prepare_* -------------------------------------------------------------------------------
 
+@pytest.mark.parametrize("src_dtype", [np.uint8, np.uint16, np.float32, np.float64])
+def test_masked_prepare_large_row_count_matches_small(ctx, src_dtype):
+    """With a signal mask and >= 1024 rows the normalise kernel keeps the column list (and 8-bit raw
+    rows) in shared memory and loops over rows with a resident grid: same bits as the per-row
+    path used for small sets, and the reference's values."""
+    rng = np.random.default_rng(3)
+    sig = (40, 40)
+    data = (rng.random((1500,) + sig) * 250).astype(src_dtype)
+    smask = orc.circular_signal_mask(sig)
+    ctx.set_signal_mask(smask)
+    try:
+        for code, name in ((_lib.KDI_NCC, "ncc"), (_lib.KDI_NDP, "ndp")):
+            big = np.asarray(ctx.patterns(data, 1500, code))
+            small = np.concatenate([np.asarray(ctx.patterns(data[a:a + 500], 500, code)) for a in (0, 500, 1000)])
+            assert np.array_equal(big, small)
+            ref = orc.prepare_dictionary(data.reshape(1500, -1).astype(np.float32), name, smask)
+            assert big.shape == ref.shape and np.abs(big - ref).max() < 3e-7
+    finally:
+        ctx.set_signal_mask(None)
+
+
 @pytest.mark.parametrize("metric", ["ncc", "ndp"])
 def test_prepared_rows_match_reference(ctx, golden, metric):
     g = golden("config1_nickel_x_1000.npz")
