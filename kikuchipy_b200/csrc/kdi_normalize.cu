@@ -89,24 +89,16 @@ __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
                      const int32_t* __restrict__ cols, int64_t s_eff, int metric,
                      float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
-                     int64_t kp, int64_t n_rows, int cols_in_smem) {
-  extern __shared__ float v[];  // s_eff floats [+ s_eff column indices [+ S raw bytes]]
+                     int64_t kp, int64_t n_rows) {
+  extern __shared__ float v[];  // s_eff floats
   __shared__ double red[kNormThreads / 32];
-  // Signal mask: the kept-column list is copied to shared memory once per CTA (the grid is small and
-  // loops over rows), so the gather below has no dependent global index load; 8-bit rows are
-  // first staged whole with 16-byte loads and gathered from shared memory.
-  int32_t* cols_s = reinterpret_cast<int32_t*>(v + s_eff);
-  uint8_t* raw_s = reinterpret_cast<uint8_t*>(v) + ((size_t)s_eff * 8 + 15) / 16 * 16;  // 16-byte aligned
-  const bool stage_raw = cols_in_smem && sizeof(T) == 1 && (S & 15) == 0;
-  if (cols_in_smem)
-    for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) cols_s[j] = cols[j];
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
     const int64_t srow = rowmap ? rowmap[row] : row;
     const T* x = src + srow * S;
-    __syncthreads();  // the previous row's output pass has finished reading v (and cols_s is filled)
+    __syncthreads();  // the previous row's output pass has finished reading v
     if constexpr (sizeof(T) == 1) {
+      // unmasked 8-bit rows: 16 pixels per load instead of one
       if (!cols && (S & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-        // unmasked 8-bit rows: 16 pixels per load instead of one
         const uint4* x16 = reinterpret_cast<const uint4*>(x);
         for (int64_t j = threadIdx.x; j < (S >> 4); j += kNormThreads) {
           const uint4 w = __ldg(x16 + j);
@@ -119,19 +111,11 @@ kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __rest
             *reinterpret_cast<float4*>(v + 16 * j + 4 * q) = f;
           }
         }
-      } else if (stage_raw && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-        const uint4* x16 = reinterpret_cast<const uint4*>(x);
-        for (int64_t j = threadIdx.x; j < (S >> 4); j += kNormThreads)
-          reinterpret_cast<uint4*>(raw_s)[j] = __ldg(x16 + j);
-        __syncthreads();
-        for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) v[j] = (float)raw_s[cols_s[j]];
       } else {
-        for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads)
-          v[j] = (float)x[cols ? (cols_in_smem ? cols_s[j] : cols[j]) : j];
+        for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) v[j] = (float)x[cols ? cols[j] : j];
       }
     } else {
-      for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads)
-        v[j] = (float)x[cols ? (cols_in_smem ? cols_s[j] : cols[j]) : j];
+      for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) v[j] = (float)x[cols ? cols[j] : j];
     }
     __syncthreads();
     float mean = 0.f;
@@ -232,7 +216,7 @@ void prefer_max_shared(K kernel) {
 template <typename T>
 int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_t* rowmap,
                    const int32_t* cols, int64_t rows, int64_t s_eff, int metric, int bf16,
-                   float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid, int sm_count) {
+                   float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid) {
   const T* s = reinterpret_cast<const T*>(src);
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
   const size_t stage_bytes = (size_t)s_eff * sizeof(float);
@@ -241,26 +225,12 @@ int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_
     static bool once_s = (cudaFuncSetAttribute(kdi_normalize_staged<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                           cudaFuncSetAttribute(kdi_normalize_staged<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
     (void)once_s;
-    // with a signal mask: column list (and 8-bit raw row) in shared memory too when it fits, and a
-    // resident grid that loops over the rows so the list is loaded once per CTA
-    size_t smem = stage_bytes;
-    int cols_in_smem = 0;
-    unsigned g = grid;
-    if (cols) {
-      const size_t with_cols = (stage_bytes * 2 + 15) / 16 * 16 + (sizeof(T) == 1 ? ((size_t)S + 15) / 16 * 16 : 0);
-      if (with_cols <= 100 * 1024 && rows >= 1024) {
-        cols_in_smem = 1;
-        smem = with_cols;
-        const unsigned resident = (unsigned)(sm_count * (200 * 1024 / with_cols));
-        if (g > resident) g = resident;
-      }
-    }
     if (bf16)
-      kdi_normalize_staged<T, true><<<g, kNormThreads, smem, stream>>>(
-          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, cols_in_smem);
+      kdi_normalize_staged<T, true><<<grid, kNormThreads, stage_bytes, stream>>>(
+          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
     else
-      kdi_normalize_staged<T, false><<<g, kNormThreads, smem, stream>>>(
-          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, cols_in_smem);
+      kdi_normalize_staged<T, false><<<grid, kNormThreads, stage_bytes, stream>>>(
+          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
     return 0;
   }
   static bool once = (prefer_max_shared(kdi_normalize_generic<T, true>), prefer_max_shared(kdi_normalize_generic<T, false>), true);
@@ -315,19 +285,19 @@ int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int
     switch (src_dtype) {
       case KDI_U8:
         launch_generic<uint8_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                s_pitch, a16, kp, grid, ctx->sm_count);
+                                s_pitch, a16, kp, grid);
         break;
       case KDI_U16:
         launch_generic<uint16_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                 s_pitch, a16, kp, grid, ctx->sm_count);
+                                 s_pitch, a16, kp, grid);
         break;
       case KDI_F32:
         launch_generic<float>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                              s_pitch, a16, kp, grid, ctx->sm_count);
+                              s_pitch, a16, kp, grid);
         break;
       case KDI_F64:
         launch_generic<double>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                               s_pitch, a16, kp, grid, ctx->sm_count);
+                               s_pitch, a16, kp, grid);
         break;
       default:
         return kdi_fail(ctx, KDI_EINVAL, "unknown source dtype %d", src_dtype);

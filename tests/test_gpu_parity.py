@@ -50,9 +50,8 @@ def _check(ridx, rsc, idx, sc, tie_tol=1e-6, strict=False):
 
 @pytest.mark.parametrize("src_dtype", [np.uint8, np.uint16, np.float32, np.float64])
 def test_masked_prepare_large_row_count_matches_small(ctx, src_dtype):
-    """With a signal mask and >= 1024 rows the normalise kernel keeps the column list (and 8-bit raw
-    rows) in shared memory and loops over rows with a resident grid: same bits as the per-row
-    path used for small sets, and the reference's values."""
+    """Masked prepare of a larger set, every source type: same bits whatever the number of rows
+    per call, and the reference's values."""
     rng = np.random.default_rng(3)
     sig = (40, 40)
     data = (rng.random((1500,) + sig) * 250).astype(src_dtype)
