@@ -149,21 +149,31 @@ kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __rest
   }
 }
 
-// fast path: float32 source, no gathers, S % 4 == 0: the row lives in registers (one HBM read)
-template <int V, bool BF16>
+// four consecutive elements of a float32 / uint8 row as float4
+__device__ __forceinline__ float4 load4(const float* row, int j) {
+  return __ldg(reinterpret_cast<const float4*>(row) + j);
+}
+__device__ __forceinline__ float4 load4(const uint8_t* row, int j) {
+  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(row) + j);
+  return make_float4((float)(w & 0xFFu), (float)((w >> 8) & 0xFFu), (float)((w >> 16) & 0xFFu), (float)(w >> 24));
+}
+
+// fast path: float32 or uint8 source, no gathers, S % 4 == 0: the row lives in registers (one HBM
+// read, no shared-memory staging)
+template <typename T, int V, bool BF16>
 __global__ void __launch_bounds__(kNormThreads)
-kdi_normalize_f32_regs(const float* __restrict__ src, int64_t S, int metric,
+kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
                        float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
                        int64_t kp, int64_t n_rows) {
   __shared__ double red[kNormThreads / 32];
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
-  const float4* x = reinterpret_cast<const float4*>(src + row * S);
+  const T* x = src + row * S;
   const int n4 = (int)(S >> 2);
   float4 r[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int j = threadIdx.x + i * kNormThreads;
-    r[i] = (j < n4) ? __ldg(x + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    r[i] = (j < n4) ? load4(x, j) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float mean = 0.f;
   if (metric == KDI_NCC) {
@@ -244,18 +254,29 @@ int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_
   return 0;
 }
 
-template <int V>
-void launch_regs(cudaStream_t stream, const float* src, int64_t S, int64_t rows, int metric,
+template <typename T, int V>
+void launch_regs(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int metric,
                  int bf16, float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid) {
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
-  static bool once = (prefer_max_shared(kdi_normalize_f32_regs<V, true>), prefer_max_shared(kdi_normalize_f32_regs<V, false>), true);
+  static bool once = (prefer_max_shared(kdi_normalize_f32_regs<T, V, true>), prefer_max_shared(kdi_normalize_f32_regs<T, V, false>), true);
   (void)once;
   if (bf16)
-    kdi_normalize_f32_regs<V, true><<<grid, kNormThreads, 0, stream>>>(
+    kdi_normalize_f32_regs<T, V, true><<<grid, kNormThreads, 0, stream>>>(
         src, S, metric, a32, s_pitch, o16, kp, rows);
   else
-    kdi_normalize_f32_regs<V, false><<<grid, kNormThreads, 0, stream>>>(
+    kdi_normalize_f32_regs<T, V, false><<<grid, kNormThreads, 0, stream>>>(
         src, S, metric, a32, s_pitch, o16, kp, rows);
+}
+
+template <typename T>
+void launch_regs_any(cudaStream_t stream, const T* s, int64_t S, int64_t rows, int metric, int bf16,
+                     float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid) {
+  const int v = (int)kdi_ceil_div(S / 4, kNormThreads);
+  if (v <= 1) launch_regs<T, 1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+  else if (v <= 2) launch_regs<T, 2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+  else if (v <= 4) launch_regs<T, 4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+  else if (v <= 8) launch_regs<T, 8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+  else launch_regs<T, 16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
 }
 
 }  // namespace
@@ -271,16 +292,11 @@ int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int
   const int bf16 = compute_dtype == 1;
   const bool plain = !d_rowmap && !d_cols && s_eff == S;
   kdi_span span(ctx, stream, max_ctas > 0 ? "normalize (resident grid)" : "normalize");
-  if (src_dtype == KDI_F32 && plain && (S % 4) == 0 && s_pitch == S &&
-      (reinterpret_cast<uintptr_t>(src) % 16) == 0 && S <= 16 * 4 * kNormThreads) {
-    const float* s = reinterpret_cast<const float*>(src);
-    const int64_t n4 = S / 4;
-    const int v = (int)kdi_ceil_div(n4, kNormThreads);
-    if (v <= 1) launch_regs<1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
-    else if (v <= 2) launch_regs<2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
-    else if (v <= 4) launch_regs<4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
-    else if (v <= 8) launch_regs<8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
-    else launch_regs<16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+  const bool reg_path = plain && (S % 4) == 0 && s_pitch == S && S <= 16 * 4 * kNormThreads;
+  if (src_dtype == KDI_F32 && reg_path && (reinterpret_cast<uintptr_t>(src) % 16) == 0) {
+    launch_regs_any<float>(stream, reinterpret_cast<const float*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+  } else if (src_dtype == KDI_U8 && reg_path && (reinterpret_cast<uintptr_t>(src) % 4) == 0) {
+    launch_regs_any<uint8_t>(stream, reinterpret_cast<const uint8_t*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
   } else {
     switch (src_dtype) {
       case KDI_U8:

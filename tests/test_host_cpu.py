@@ -217,6 +217,39 @@ def test_row_slices_cover_rows():
             assert all(sl[i][2] == sl[i + 1][1] for i in range(world - 1))
 
 
+def test_get_patterns_argument_checks_without_gpu():
+    """Argument handling of the get_patterns mirror that happens before any device call
+    (signals/ebsd_master_pattern.py:97-233)."""
+    mp = np.zeros((11, 11), np.float32)
+    rot = np.tile([1.0, 0, 0, 0], (3, 1))
+    with pytest.raises(NotImplementedError, match="float32"):
+        kb.get_patterns(mp, mp, rot, direction_cosines=np.ones((4, 3)), dtype_out="uint8")
+    with pytest.raises(ValueError, match="either a detector or direction cosines"):
+        kb.get_patterns(mp, mp, rot)
+    with pytest.raises(ValueError, match="quaternions"):
+        kb.get_patterns(mp, mp, np.zeros((3, 3)), direction_cosines=np.ones((4, 3)))
+    with pytest.raises(NotImplementedError, match="one navigation dimension"):
+        kb.get_patterns(mp, mp, np.zeros((2, 3, 4)), direction_cosines=np.ones((4, 3)))
+    with pytest.raises(ValueError, match="detector shape"):
+        kb.get_patterns(mp, mp, rot, direction_cosines=np.ones((4, 3)), detector_shape=(3, 3))
+
+    class _Det:  # an EBSDDetector with several projection centres is not supported
+        navigation_shape = (2, 2)
+
+    with pytest.raises(NotImplementedError, match="one projection centre"):
+        kb.get_patterns(mp, mp, rot, _Det())
+
+
+def test_synthetic_inputs_match_oracle_copies():
+    from kikuchipy_b200 import synthetic as syn
+    from oracle import projection_oracle as po
+
+    for a, b in zip(syn.synthetic_master_pattern(51, 5), po.synthetic_master_pattern(51, 5)):
+        assert np.array_equal(a, b)
+    assert np.array_equal(syn.random_rotations(7, 4), po.random_rotations(7, 4))
+    assert np.array_equal(syn.tilted_detector_matrix(70.0), po.tilted_detector_matrix(70.0))
+
+
 def test_bench_cpu_arm_runs_small(monkeypatch):
     sys.path.insert(0, ROOT)
     import bench
