@@ -331,6 +331,7 @@ class Context:
         self._h = h.value
         self.device = device
         self._signal_mask_key = None
+        self._signal_mask_set = False
 
     # -- plumbing -------------------------------------------------------------
     def _check(self, rc: int):
@@ -395,11 +396,17 @@ class Context:
 
     # -- masks and pattern sets ---------------------------------------------------
     def set_signal_mask(self, mask):
+        """Signal mask for pattern sets created afterwards (True = pixel excluded).  A mask equal to
+        the current one is not uploaded again."""
+        key = None if mask is None else np.ascontiguousarray(np.asarray(mask).ravel().astype(np.uint8)).tobytes()
+        if key == self._signal_mask_key and (key is not None or self._signal_mask_set):
+            return
         if mask is None:
             self._check(self._lib.kdi_set_signal_mask(self._h, None, 0))
-            return
-        m = np.ascontiguousarray(np.asarray(mask).ravel().astype(np.uint8))
-        self._check(self._lib.kdi_set_signal_mask(self._h, m.ctypes.data, m.size))
+        else:
+            m = np.frombuffer(key, dtype=np.uint8)
+            self._check(self._lib.kdi_set_signal_mask(self._h, m.ctypes.data, m.size))
+        self._signal_mask_key, self._signal_mask_set = key, True
 
     def patterns(self, data, rows: int, metric: int, row_mask=None) -> Patterns:
         """cast -> reshape (rows, -1) -> row mask -> signal mask -> normalise, on the device."""

@@ -232,9 +232,9 @@ int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_
   const size_t stage_bytes = (size_t)s_eff * sizeof(float);
   if (stage_bytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(a32) % 16) == 0 &&
       (reinterpret_cast<uintptr_t>(a16) % 8) == 0) {
-    static bool once_s = (cudaFuncSetAttribute(kdi_normalize_staged<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                          cudaFuncSetAttribute(kdi_normalize_staged<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
-    (void)once_s;
+    // (per launch, not once per process: the attribute is per device)
+    if (bf16) cudaFuncSetAttribute(kdi_normalize_staged<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    else cudaFuncSetAttribute(kdi_normalize_staged<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (bf16)
       kdi_normalize_staged<T, true><<<grid, kNormThreads, stage_bytes, stream>>>(
           s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);

@@ -221,9 +221,9 @@ int launch_typed(kdi_ctx* ctx, cudaStream_t stream, const ProjParams& p, int bf1
   if (smem > 200 * 1024)
     return kdi_fail(ctx, KDI_EUNSUPPORTED, "detector of %lld pixels is too large for the projection kernel's shared-memory staging",
                     (long long)p.S);
-  static bool once = (cudaFuncSetAttribute(kdi_project_kernel<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                      cudaFuncSetAttribute(kdi_project_kernel<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
-  (void)once;
+  // (per launch, not once per process: the attribute is per device)
+  if (bf16) cudaFuncSetAttribute(kdi_project_kernel<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  else cudaFuncSetAttribute(kdi_project_kernel<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const unsigned grid = (unsigned)((max_ctas > 0 && p.n_rows > max_ctas) ? max_ctas : p.n_rows);
   kdi_span span(ctx, stream, "project (+normalize)");
   if (bf16) kdi_project_kernel<MT, true><<<grid, kProjThreads, smem, stream>>>(p);

@@ -125,9 +125,12 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    per_step = []
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         idx, sc = step()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        per_step.append(round((time.perf_counter() - t_s) * 1e3, 3))
     if world > 1:
         dist.barrier()
     ms = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -236,7 +239,7 @@ def main():
         line = {
             "config": args.config, "n_gpus": world, "M": M, "N": N, "signal": list(sig), "s_eff": s_eff, "metric": cfg["metric"],
             "keep_n": k, "compute_dtype": "bf16" if cfg["bf16"] else "fp16", "dictionary": "host (streamed)" if cfg["host_dict"] else "device",
-            "ms_per_step": round(ms, 3), "patterns_per_s": round(M / (ms * 1e-3)), "comparisons_per_s": float(M) * N / (ms * 1e-3),
+            "ms_per_step": round(ms, 3), "rank0_ms_each_step": per_step, "patterns_per_s": round(M / (ms * 1e-3)), "comparisons_per_s": float(M) * N / (ms * 1e-3),
             "rank0_stage_ms": {kk: round(v, 3) for kk, v in tm.items() if kk.endswith("_ms")},
             "rank0_gemm_tflops_algorithmic": None if gemm_tflops is None else round(gemm_tflops, 1),
             "flagged_rows": int(tm["flagged_rows"]), "checks": checks, "osm": osm_info,
