@@ -16,7 +16,8 @@ constant: weak scaling in patterns/s.
 `e2e`     : the same job through the public API with pinned HOST buffers; H2D of both inputs
             and D2H of the result inside the timed region (wall clock between device syncs).
             N > 1: each rank uploads its dictionary shard and 1/N of the experimental rows (the
-            raw rows are all-gathered over NVLink); byte counts are whole-job totals.
+            raw rows are all-gathered over NVLink) and rank 0 reads the result back; byte counts
+            are whole-job totals.
 `roofline`: the GEMM+top-k kernel; achieved = 2*M*N_shard*S / its CUDA-event duration.
 `cpu_baseline`: the NumPy oracle (the reference's own arithmetic) on the host cores, on a
             bounded sample, extrapolated linearly in the number of patterns.
@@ -280,17 +281,17 @@ def run_ours(args, rank, world, local_rank):
     exp_host[...] = exp_dev.cpu().numpy()
     dict_host[...] = dict_dev.cpu().numpy()
     # whole-job bytes per step: N = 1 uploads everything over one link; N > 1: every rank uploads
-    # its dictionary shard and 1/N of the experimental rows (all-gathered over NVLink), and every
-    # rank reads the full result back
+    # its dictionary shard and 1/N of the experimental rows (all-gathered over NVLink), and rank 0
+    # reads the result back
     h2d = exp_host.nbytes + N_DICT * S * 4
-    d2h = m_total * KEEP_N * 12 * world
+    d2h = m_total * KEEP_N * 12  # the result (identical on every rank) is read back by rank 0
 
     def step_e2e():
         if world == 1:
             res = kb.dictionary_indexing(exp_host, dict_host, metric="ncc", keep_n=KEEP_N, verbose=False)
             return res.scores
         i, s = kb.dictionary_indexing_sharded(exp_host, dict_host, N_DICT, metric="ncc", keep_n=KEEP_N, context=ctx)
-        return i.cpu(), s.cpu()
+        return (i.cpu(), s.cpu()) if rank == 0 else (i, s)
 
     with torch.cuda.stream(stream):
         for _ in range(max(1, args.warmup // 2)):
@@ -324,7 +325,7 @@ def run_ours(args, rank, world, local_rank):
                 res = kb.dictionary_indexing(exp_host, gen, metric="ncc", keep_n=KEEP_N, verbose=False, context=ctx)
                 return res.scores
             i, s = kb.dictionary_indexing_sharded(exp_host, gen, N_DICT, metric="ncc", keep_n=KEEP_N, context=ctx)
-            return i.cpu(), s.cpu()
+            return (i.cpu(), s.cpu()) if rank == 0 else (i, s)
 
         with torch.cuda.stream(stream):
             for _ in range(2):
