@@ -275,6 +275,32 @@ int kdi_orientation_similarity_map(kdi_ctx* ctx, const int64_t* indices, int64_t
                                    int normalize, const uint8_t* footprint, int fy, int fx,
                                    int center_index, float* out);
 
+/* ---- merge_crystal_maps (next row of the path: SURVEY.md section 8f.2) -------------------------
+ * (indexing/_merge_crystal_maps.py:28-354, the array arithmetic: combined scores :199-214, phase
+ *  of the best nanmean of the first mean_n_best scores :216-225, not-indexed points :227-237,
+ *  values of the winning map :239-296, stable best-first ordering of all scores of a point
+ *  :298-308, simulation indices made unique across maps :313-347)
+ * All pointers on the host.  Map k holds n_points[k] points; scores[k]: n_points[k] x n_scores of
+ * score_dtype (KDI_F32 / KDI_F64); rotations[k]: n_points[k] x n_scores x 4 float64;
+ * simulation_indices: NULL, or per map n_points[k] x n_scores int64.  point_rows: NULL, or per map
+ * NULL (the map holds every point, in order) or map_size int32 = row of the point in map k, -1 =
+ * the map does not hold it (the navigation masks of :154-165).  not_indexed: NULL, or per map NULL
+ * or map_size bytes, nonzero = the map's phase_id is -1 there.  sign: +1 greater is better, -1
+ * lower is better.  Outputs: phase_id (map_size int64: index of the winning map, -1 = not
+ * indexed), scores / rotations / simulation_indices (int32) of the winning map (map_size x
+ * n_scores [x 4]), merged_scores (map_size x n_scores*n_maps of score_dtype, NaN for missing
+ * points, last) and merged_indices (same shape; int64, or float64 with NaN when idx_as_double -
+ * what the reference produces when navigation masks are used).  A point that no map holds gives
+ * KDI_EINVAL "All-NaN slice encountered" (np.nanargmax, :225). */
+#define KDI_MERGE_MAX_MAPS 32
+int kdi_merge_crystal_maps(kdi_ctx* ctx, int n_maps, int64_t map_size, int n_scores, int score_dtype,
+                           const int64_t* n_points, const void* const* scores,
+                           const double* const* rotations, const int64_t* const* simulation_indices,
+                           const int32_t* const* point_rows, const uint8_t* const* not_indexed,
+                           int mean_n_best, int sign, int idx_as_double, int64_t* phase_id_out,
+                           void* scores_out, double* rotations_out, int32_t* simulation_indices_out,
+                           void* merged_scores_out, void* merged_indices_out);
+
 #ifdef __cplusplus
 }
 #endif

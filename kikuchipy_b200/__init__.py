@@ -1,7 +1,8 @@
 """B200-native EBSD dictionary indexing behind kikuchipy's plugin surface.
 
 Only the dictionary-indexing hot path is implemented: the
-``SimilarityMetric`` classes, ``dictionary_indexing`` and ``orientation_similarity_map``.
+``SimilarityMetric`` classes, ``dictionary_indexing`` and ``orientation_similarity_map``, plus
+the rows section 8f marks next: dictionary generation (``get_patterns``) and ``merge_crystal_maps``.
 Everything numerical runs in ``libkdi.so`` (hand-written sm_100a CUDA behind the C ABI in
 ``include/kdi.h``); importing this package does not need a GPU, calling it does.
 """
@@ -15,12 +16,14 @@ from .similarity_metrics import (
 )
 from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
 from .master_pattern import GeneratedDictionary, direction_cosines, get_patterns
+from .merge_maps import MergedCrystalMap, merge_crystal_maps
 
 __all__ = [
     "Context",
     "DictionaryIndexingResult",
     "GeneratedDictionary",
     "KdiError",
+    "MergedCrystalMap",
     "NormalizedCrossCorrelationMetric",
     "NormalizedDotProductMetric",
     "SimilarityMetric",
@@ -31,6 +34,7 @@ __all__ = [
     "direction_cosines",
     "get_patterns",
     "gather_topk",
+    "merge_crystal_maps",
     "orientation_similarity_map",
     "shard_bounds",
 ]

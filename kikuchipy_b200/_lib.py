@@ -118,6 +118,10 @@ SIGNATURES = {
         _i,
         [_vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
     ),
+    "kdi_merge_crystal_maps": (
+        _i,
+        [_vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    ),
 }
 
 _lib = None
@@ -702,6 +706,51 @@ class Context:
             self._lib.kdi_orientation_similarity_map(
                 self._h, idx.ctypes.data, ny, nx, keep_n, n_best, from_n_best, int(bool(normalize)),
                 fp.ctypes.data, fp.shape[0], fp.shape[1], center_index, out.ctypes.data,
+            )
+        )
+        return out
+
+    def merge_crystal_maps(self, scores, rotations, simulation_indices, point_rows, not_indexed,
+                           map_size, mean_n_best, sign, idx_as_double):
+        """``kdi_merge_crystal_maps``: per-map lists of ``(n_i, N)`` scores (float32 or float64),
+        ``(n_i, N, 4)`` rotations, optional ``(n_i, N)`` simulation indices, optional int32 row
+        maps and not-indexed flags.  Returns a dict of the merged arrays."""
+        n_maps = len(scores)
+        dt = np.dtype(scores[0].dtype)
+        if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError(f"scores must be float32 or float64, not {dt}")
+        sc = [np.ascontiguousarray(s, dtype=dt) for s in scores]
+        n_scores = sc[0].shape[1]
+        rot = [np.ascontiguousarray(r, dtype=np.float64) for r in rotations]
+        idx = None if simulation_indices is None else [np.ascontiguousarray(i, dtype=np.int64) for i in simulation_indices]
+        rows = [None if r is None else np.ascontiguousarray(r, dtype=np.int32) for r in point_rows]
+        ni = [None if f is None else np.ascontiguousarray(f, dtype=np.uint8) for f in not_indexed]
+
+        def ptrs(arrs):
+            return (C.c_void_p * n_maps)(*[None if a is None else a.ctypes.data for a in arrs])
+
+        n_pts = (C.c_int64 * n_maps)(*[a.shape[0] for a in sc])
+        total = n_scores * n_maps
+        out = {
+            "phase_id": np.empty(map_size, dtype=np.int64),
+            "scores": np.empty((map_size, n_scores), dtype=dt),
+            "rotations": np.empty((map_size, n_scores, 4), dtype=np.float64),
+            "merged_scores": np.empty((map_size, total), dtype=dt),
+        }
+        if idx is not None:
+            out["simulation_indices"] = np.empty((map_size, n_scores), dtype=np.int32)
+            out["merged_simulation_indices"] = np.empty((map_size, total), dtype=np.float64 if idx_as_double else np.int64)
+        self._check(
+            self._lib.kdi_merge_crystal_maps(
+                self._h, n_maps, int(map_size), int(n_scores), _DTYPES[dt], n_pts, ptrs(sc), ptrs(rot),
+                None if idx is None else ptrs(idx),
+                ptrs(rows) if any(r is not None for r in rows) else None,
+                ptrs(ni) if any(f is not None for f in ni) else None,
+                int(mean_n_best), int(sign), int(bool(idx_as_double)), out["phase_id"].ctypes.data,
+                out["scores"].ctypes.data, out["rotations"].ctypes.data,
+                out["simulation_indices"].ctypes.data if idx is not None else None,
+                out["merged_scores"].ctypes.data,
+                out["merged_simulation_indices"].ctypes.data if idx is not None else None,
             )
         )
         return out
