@@ -301,6 +301,44 @@ int kdi_merge_crystal_maps(kdi_ctx* ctx, int n_maps, int64_t map_size, int n_sco
                            void* scores_out, double* rotations_out, int32_t* simulation_indices_out,
                            void* merged_scores_out, void* merged_indices_out);
 
+/* ---- refinement of orientations / projection centres (next row: SURVEY.md section 8f.3) ---------
+ * (indexing/_refinement/_solvers.py:50-470 the three *_solver_scipy functions with their default
+ *  optimiser, scipy.optimize.minimize(method="Nelder-Mead"); _objective_functions.py:36-190;
+ *  EBSD.refine_orientation / refine_projection_center / refine_orientation_projection_center,
+ *  signals/ebsd.py:1986-2560, call them per pattern through _refinement.py:340-870)
+ * For every pattern: centre it (rescale float32 input to [-1, 1] first when `rescale`), then
+ * minimise 1 - NCC(pattern, projection of the master pattern) over the control variables with a
+ * Nelder-Mead simplex search that follows SciPy's step for step, from each of n_starts start
+ * points (pseudo-symmetry variants); the start with the best score is reported.
+ *   mode KDI_REFINE_ORI     x = (phi1, Phi, phi2) Bunge-Euler angles in radians.  Direction cosines:
+ *                           those of mp (whole detector, nrows*ncols x 3) when pcs == NULL, else
+ *                           computed from the pattern's own projection centre pcs[i] (PCx, PCy, PCz,
+ *                           Bruker convention) and om_detector_to_sample.
+ *   mode KDI_REFINE_PC      x = (PCx, PCy, PCz); rotations: n_patterns x 4 unit quaternions; n_starts 1.
+ *   mode KDI_REFINE_ORI_PC  x = (phi1, Phi, phi2, PCx, PCy, PCz).
+ * patterns: n_patterns x (nrows*ncols) of pat_dtype, host or device; the current signal mask
+ * (kdi_set_signal_mask) selects the pixels that are matched.  x0 / lower / upper: n_patterns x
+ * n_starts x n_var float64 on the host (lower == upper == NULL: unbounded, i.e. no trust region).
+ * om_detector_to_sample: 3 x 3 row-major float64.  results_out (host): n_patterns rows of
+ * [score, number of objective evaluations, x..., (index of the best start when n_starts > 1)]
+ * as float64 - the layout of the reference's result arrays (_refinement.py:437-470).
+ * The master pattern must be float32 on the device (u8/u16/f32 sources). */
+#define KDI_REFINE_ORI 0
+#define KDI_REFINE_PC 1
+#define KDI_REFINE_ORI_PC 2
+typedef struct kdi_refine_options {
+  double xatol;      /* Nelder-Mead: absolute tolerance on the simplex size (SciPy default 1e-4)   */
+  double fatol;      /* ... and on the spread of the objective values (SciPy default 1e-4)        */
+  int64_t maxiter;   /* < 0: not given (SciPy: n_var * 200 when maxfev is not given either);       */
+  int64_t maxfev;    /*      INT64_MAX: unlimited                                                  */
+  int adaptive;      /* SciPy's `adaptive` option (dimension-dependent coefficients)               */
+} kdi_refine_options;
+int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, const void* patterns, int pat_loc,
+               int pat_dtype, int64_t n_patterns, int nrows, int ncols, int rescale, const double* x0,
+               int n_starts, const double* lower, const double* upper, const double* rotations,
+               const double* pcs, const double* om_detector_to_sample, const kdi_refine_options* opt,
+               double* results_out);
+
 #ifdef __cplusplus
 }
 #endif

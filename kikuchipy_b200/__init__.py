@@ -17,15 +17,24 @@ from .similarity_metrics import (
 from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
 from .master_pattern import GeneratedDictionary, direction_cosines, get_patterns
 from .merge_maps import MergedCrystalMap, merge_crystal_maps
+from .refinement import (
+    Detector,
+    RefinementResult,
+    refine_orientation,
+    refine_orientation_projection_center,
+    refine_projection_center,
+)
 
 __all__ = [
     "Context",
+    "Detector",
     "DictionaryIndexingResult",
     "GeneratedDictionary",
     "KdiError",
     "MergedCrystalMap",
     "NormalizedCrossCorrelationMetric",
     "NormalizedDotProductMetric",
+    "RefinementResult",
     "SimilarityMetric",
     "bind_to_gpu_numa_node",
     "default_context",
@@ -36,6 +45,9 @@ __all__ = [
     "gather_topk",
     "merge_crystal_maps",
     "orientation_similarity_map",
+    "refine_orientation",
+    "refine_orientation_projection_center",
+    "refine_projection_center",
     "shard_bounds",
 ]
 __version__ = "0.1.0"

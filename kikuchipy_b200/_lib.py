@@ -39,6 +39,8 @@ OPT_MAX_STAGES = 8
 OPT_OVERLAP = 9
 OPT_SPLIT_SELECT = 10
 
+REFINE_ORI, REFINE_PC, REFINE_ORI_PC = 0, 1, 2
+
 _DTYPES = {
     np.dtype(np.uint8): KDI_U8,
     np.dtype(np.uint16): KDI_U16,
@@ -47,6 +49,18 @@ _DTYPES = {
 }
 _TORCH_DTYPES = {"torch.uint8": KDI_U8, "torch.float32": KDI_F32, "torch.float64": KDI_F64,
                  "torch.uint16": KDI_U16}
+
+
+class RefineOptions(C.Structure):
+    """``kdi_refine_options`` (include/kdi.h)."""
+
+    _fields_ = [
+        ("xatol", C.c_double),
+        ("fatol", C.c_double),
+        ("maxiter", C.c_int64),
+        ("maxfev", C.c_int64),
+        ("adaptive", C.c_int),
+    ]
 
 
 class Timings(C.Structure):
@@ -117,6 +131,11 @@ SIGNATURES = {
     "kdi_orientation_similarity_map": (
         _i,
         [_vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
+    ),
+    "kdi_refine": (
+        _i,
+        [_vp, _vp, _i, _vp, _i, _i, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp,
+         C.POINTER(RefineOptions), _vp],
     ),
     "kdi_merge_crystal_maps": (
         _i,
@@ -708,6 +727,42 @@ class Context:
                 fp.ctypes.data, fp.shape[0], fp.shape[1], center_index, out.ctypes.data,
             )
         )
+        return out
+
+    def refine(self, mp: "MasterPattern", mode: int, patterns, nrows: int, ncols: int, rescale: bool, x0,
+               lower=None, upper=None, rotations=None, pcs=None, om_detector_to_sample=None, xatol=1e-4,
+               fatol=1e-4, maxiter=-1, maxfev=-1, adaptive=False) -> np.ndarray:
+        """``kdi_refine``: Nelder-Mead refinement of ``x0`` ``(n, starts, 3 | 6)`` for ``patterns``
+        ``(n, nrows * ncols)`` (NumPy array or CUDA tensor).  Returns the reference's result rows
+        ``(n, 2 + n_var [+ 1])``: score, evaluations, variables[, best start]."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        n, n_starts, nv = x0.shape
+        ptr, loc, code, keep = _buffer(patterns, self)
+
+        def opt(a, shape):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != shape:
+                raise ValueError(f"expected an array of shape {shape}, got {a.shape}")
+            return a
+
+        lo, hi = opt(lower, x0.shape), opt(upper, x0.shape)
+        rot, pc = opt(rotations, (n, 4)), opt(pcs, (n, 3))
+        om = opt(om_detector_to_sample, (3, 3))
+        o = RefineOptions(float(xatol), float(fatol), int(maxiter), int(maxfev), int(bool(adaptive)))
+        out = np.empty((n, 2 + nv + (1 if n_starts > 1 else 0)), dtype=np.float64)
+
+        def p(a):
+            return None if a is None else a.ctypes.data
+
+        self._check(
+            self._lib.kdi_refine(
+                self._h, mp._h, int(mode), ptr, loc, code, n, int(nrows), int(ncols), int(bool(rescale)),
+                x0.ctypes.data, n_starts, p(lo), p(hi), p(rot), p(pc), p(om), C.byref(o), out.ctypes.data,
+            )
+        )
+        del keep
         return out
 
     def merge_crystal_maps(self, scores, rotations, simulation_indices, point_rows, not_indexed,

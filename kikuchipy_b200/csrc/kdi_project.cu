@@ -19,6 +19,7 @@
 // normalised exactly as kdi_normalize_staged does.  Bound: fp64 pipe (about 300 double operations
 // per pixel), not HBM.
 #include "kdi_internal.cuh"
+#include "kdi_project_dev.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -26,9 +27,6 @@
 namespace {
 
 constexpr int kProjThreads = 256;
-constexpr double kSqrtPiOver2 = 0.88622692545275801365;   // sqrt(pi) / 2
-constexpr double kTwoOverSqrtPi = 1.1283791670955125739;  // 2 / sqrt(pi)
-
 struct ProjParams {
   const double* rot;  // n x 4 (a, b, c, d)
   const double* dc;   // S x 3
@@ -86,59 +84,6 @@ template <bool BF16>
 __device__ __forceinline__ uint16_t op16(float v) {
   if constexpr (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v * KDI_OP_SCALE));
   else return __half_as_ushort(__float2half_rn(v * KDI_OP_SCALE));
-}
-
-// intensity of one detector pixel for one rotation (float64, as the reference computes it)
-template <typename MT>
-__device__ __forceinline__ double project_pixel(const ProjParams& p, const double (&m)[9], double vx,
-                                                double vy, double vz) {
-  // rotate_vector (_utils/numba.py:78-80) with the products precomputed per rotation.  Plain
-  // IEEE multiplies and adds (no FMA contraction): for symmetric rotations the reference's terms
-  // cancel EXACTLY (e.g. a rotated z of exactly 0 selects the upper hemisphere, :506); a fused
-  // multiply-add would leave the rounding error of one product and could flip that choice
-  const double x = __dadd_rn(__dmul_rn(m[0], vx), __dmul_rn(2.0, __dadd_rn(__dmul_rn(m[1], vz), __dmul_rn(m[2], vy))));
-  const double y = __dadd_rn(__dmul_rn(m[3], vy), __dmul_rn(2.0, __dadd_rn(__dmul_rn(m[4], vx), __dmul_rn(m[5], vz))));
-  const double z = __dadd_rn(__dmul_rn(m[6], vz), __dmul_rn(2.0, __dadd_rn(__dmul_rn(m[7], vy), __dmul_rn(m[8], vx))));
-  // _vector2lambert (:541-566)
-  // (one reciprocal instead of the reference's three divisions: at most one ulp of float64 apart;
-  // an exact pole, x = y = 0, is recognised below whatever |wz| rounds to)
-  const double inv = rsqrt(x * x + y * y + z * z);
-  const double wx = x * inv, wy = y * inv, wz = z * inv;
-  const double abs_z = fabs(wz);
-  const double sqrt_z = sqrt(2.0 * (1.0 - abs_z));
-  double lx = 0.0, ly = 0.0;
-  if (abs_z != 1.0 && (wx != 0.0 || wy != 0.0)) {
-    if (fabs(wy) <= fabs(wx)) {
-      const double s = (wx > 0.0) ? 1.0 : ((wx < 0.0) ? -1.0 : 0.0);
-      lx = s * sqrt_z * kSqrtPiOver2;
-      ly = s * sqrt_z * kTwoOverSqrtPi * atan(wy / wx);
-    } else {
-      const double s = (wy > 0.0) ? 1.0 : ((wy < 0.0) ? -1.0 : 0.0);
-      lx = s * sqrt_z * kTwoOverSqrtPi * atan(wx / wy);
-      ly = s * sqrt_z * kSqrtPiOver2;
-    }
-  }
-  // _get_lambert_interpolation_parameters (:638-676)
-  // scale * l / sqrt(pi / 2) with the constant folded: within one ulp of float64 of the reference
-  const double i_this = ly * p.scale_over_sqrt_pi_half;
-  const double j_this = lx * p.scale_over_sqrt_pi_half;
-  int nii = (int)(i_this + p.scale);  // truncation towards zero, like np.int32(float)
-  int nij = (int)(j_this + p.scale);
-  int niip = nii + 1, nijp = nij + 1;
-  if (niip >= p.npx) niip = nii;
-  if (nijp >= p.npy) nijp = nij;
-  if (nii < 0) nii = niip;
-  if (nij < 0) nij = nijp;
-  const double di = i_this - (double)nii + p.scale;
-  const double dj = j_this - (double)nij + p.scale;
-  const double dim = 1.0 - di, djm = 1.0 - dj;
-  // _get_pixel_from_master_pattern (:703-708), hemisphere by the sign of the ROTATED z (:506)
-  const MT* mp = reinterpret_cast<const MT*>(z >= 0.0 ? p.upper : p.lower);
-  const double v00 = (double)__ldg(mp + (int64_t)nii * p.ld + nij);
-  const double v10 = (double)__ldg(mp + (int64_t)niip * p.ld + nij);
-  const double v01 = (double)__ldg(mp + (int64_t)nii * p.ld + nijp);
-  const double v11 = (double)__ldg(mp + (int64_t)niip * p.ld + nijp);
-  return v00 * dim * djm + v10 * di * djm + v01 * dim * dj + v11 * di * dj;
 }
 
 template <typename MT, bool BF16>
@@ -235,18 +180,6 @@ int launch_typed(kdi_ctx* ctx, cudaStream_t stream, const ProjParams& p, int bf1
 
 }  // namespace
 
-struct kdi_master_pattern {
-  int mp_dtype = KDI_F32;  // storage type on the device: KDI_F32 (f32/u8/u16 sources, exact) or KDI_F64
-  int npx = 0, npy = 0;    // columns, rows of the master pattern arrays
-  void* upper = nullptr;
-  void* lower = nullptr;
-  double* dc = nullptr;  // S x 3
-  int64_t S = 0;
-  double scale = 0.0;
-  int rescale = 0;
-  double out_min = 0.0, out_max = 1.0;
-};
-
 int64_t kdi_master_pattern_pixels(const kdi_master_pattern* mp) { return mp->S; }
 
 int kdi_launch_project(kdi_ctx* ctx, cudaStream_t stream, const kdi_master_pattern* mp, const double* d_rot,
@@ -265,7 +198,7 @@ int kdi_launch_project(kdi_ctx* ctx, cudaStream_t stream, const kdi_master_patte
   p.npy = mp->npy;
   p.ld = mp->npx;
   p.scale = mp->scale;
-  p.scale_over_sqrt_pi_half = mp->scale / 1.2533141373155002512;
+  p.scale_over_sqrt_pi_half = mp->scale / kdi_proj::kSqrtPiHalf;
   p.rescale = mp->rescale;
   p.out_min = mp->out_min;
   p.out_max = mp->out_max;

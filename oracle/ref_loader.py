@@ -24,6 +24,10 @@ import types
 
 import numpy as np
 
+# Numba's on-disk cache (the reference's kernels are declared cache=True) defaults to a __pycache__
+# directory NEXT TO THE SOURCE FILE when that directory is writable: keep it out of /root/reference
+os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(os.environ.get("TMPDIR", "/tmp"), "kdi_numba_cache"))
+
 REFERENCE_ROOT = "/root/reference"
 _SRC = os.path.join(REFERENCE_ROOT, "src", "kikuchipy")
 
@@ -164,3 +168,35 @@ def load_master_pattern():
         stub._rescale_with_min_max = ns["_rescale_with_min_max"]
         sys.modules["kikuchipy.pattern._pattern"] = stub
     return _load("kikuchipy.signals.util._master_pattern", "signals/util/_master_pattern.py")
+
+
+def load_refinement():
+    """Return the reference's ``indexing/_refinement/_solvers.py`` module, executed in place
+    (with ``_objective_functions.py`` and everything they import).  ``kikuchipy/pattern/_pattern.py``
+    cannot be imported here (scikit-image), so the three small Numba helpers the solvers take from
+    it are compiled from their own source lines (AST extraction, nothing copied into this
+    repository).  Needs numba and scipy."""
+    import ast
+
+    mp = load_master_pattern()
+    load_metrics()
+    from numba import njit
+
+    path = os.path.join(_SRC, "pattern", "_pattern.py")
+    stub = sys.modules["kikuchipy.pattern._pattern"]
+    if not hasattr(stub, "_zero_mean_sum_square_1d_float32"):
+        tree = ast.parse(open(path).read())
+        want = ("_rescale_without_min_max_1d_float32", "_zero_mean_sum_square_1d_float32")
+        fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+        # executed inside the stub module itself: Numba's on-disk cache (cache=True) re-imports
+        # the defining module by name
+        stub.njit, stub.np = njit, np
+        exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), stub.__dict__)
+    if "kikuchipy.indexing._refinement" not in sys.modules or not getattr(
+            sys.modules["kikuchipy.indexing._refinement"], "__file__", None):
+        pkg = _load("kikuchipy.indexing._refinement", "indexing/_refinement/__init__.py")
+        pkg.__path__ = []
+    _load("kikuchipy._utils._gnonomic_bounds", "_utils/_gnonomic_bounds.py")
+    _load("kikuchipy.indexing._refinement._objective_functions", "indexing/_refinement/_objective_functions.py")
+    solvers = _load("kikuchipy.indexing._refinement._solvers", "indexing/_refinement/_solvers.py")
+    return solvers, mp

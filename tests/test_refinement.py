@@ -1,0 +1,350 @@
+"""Refinement.  CPU: the oracle's Nelder-Mead against the installed SciPy, the
+oracle against golden vectors produced by the reference's own solvers
+(tests/golden/make_golden_refinement.py), the host mirror's argument handling.  ``gpu``: the CUDA
+path (through the C ABI) against the oracle and the goldens."""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refinement_oracle as ro
+
+import kikuchipy_b200 as kb
+from kikuchipy_b200 import _lib
+from kikuchipy_b200 import refinement as rf
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "refinement.npz"))
+# Agreement with the reference: its Numba kernels sum in float32 with fastmath=True, so objective
+# values differ from any other evaluation order by float32 rounding (~1e-7) and the simplex
+# searches, which stop at xatol = fatol = 1e-4, end within those tolerances of each other.
+SCORE_TOL = 1e-4   # the north star's bound on scores; observed differences are ~1e-6
+ANGLE_TOL = 2e-3   # radians (flat synthetic optimum; the search itself stops at 1e-4)
+PC_TOL = 2e-3
+
+
+def _case(name):
+    if name == "A":
+        c = ro.synthetic_case(n=8, seed=1, circular_mask=True)
+    elif name == "B":
+        c = ro.synthetic_case(n=4, seed=2, pc_spread=0.01, nrows=20, ncols=20)
+    else:
+        c = ro.synthetic_case(n=4, seed=3, dtype=np.float32, nrows=18, ncols=26)
+    assert np.array_equal(c["patterns"], GOLD[f"{name}_patterns"]), "synthetic generator drifted from the goldens"
+    return c
+
+
+# ---- CPU: Nelder-Mead restatement == SciPy ------------------------------------------------------
+
+def _rosen3(x):
+    return float(100 * (x[1] - x[0] ** 2) ** 2 + (1 - x[0]) ** 2 + 100 * (x[2] - x[1] ** 2) ** 2 + (1 - x[1]) ** 2)
+
+
+@pytest.mark.parametrize("kw", [
+    {}, {"xatol": 1e-8, "fatol": 1e-8}, {"maxfev": 37}, {"maxiter": 11}, {"adaptive": True},
+    {"bounds": [(-0.5, 0.8), (0.0, 2.0), (-3.0, 0.3)]}, {"bounds": [(-2.0, -1.19), (0.9, 1.0), (0.0, 5.0)], "maxfev": 50},
+    {"maxfev": 3},
+])
+@pytest.mark.parametrize("x0", [[-1.2, 1.0, 0.7], [0.0, 0.0, 0.0], [2.0, -1.0, 0.0]])
+def test_oracle_nelder_mead_equals_scipy(kw, x0):
+    import warnings
+
+    import scipy.optimize as so
+
+    kw = dict(kw)
+    bounds = kw.pop("bounds", None)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = so.minimize(_rosen3, x0, method="Nelder-Mead", bounds=bounds, options=dict(kw))
+    x, f, nfev, nit = ro.nelder_mead(_rosen3, x0, bounds=None if bounds is None else np.array(bounds), **kw)
+    assert nfev == ref.nfev and nit == ref.nit
+    assert np.array_equal(x, ref.x) and f == ref.fun
+
+
+def test_oracle_nelder_mead_six_variables():
+    import scipy.optimize as so
+
+    def f(x):
+        return float(np.sum((x - np.arange(6)) ** 2 * (1 + np.arange(6))) + 0.1 * np.sum(np.cos(3 * x)))
+
+    x0 = np.array([0.3, 0.0, 2.5, 2.0, 5.0, 4.0])
+    ref = so.minimize(f, x0, method="Nelder-Mead")
+    x, fv, nfev, nit = ro.nelder_mead(f, x0)
+    assert (nfev, nit) == (ref.nfev, ref.nit) and np.array_equal(x, ref.x) and fv == ref.fun
+
+
+# ---- CPU: oracle vs the reference's own outputs -------------------------------------------------
+
+def test_oracle_prepare_pattern_vs_reference():
+    a = _case("A")
+    for i in range(8):
+        e, sq = ro.prepare_pattern(a["patterns"][i][a["keep"]], False)
+        assert np.allclose(e, GOLD["A_prepared"][i], rtol=0, atol=2e-5)  # one float32 ulp of values ~200
+        assert abs(float(sq) - float(GOLD["A_sqnorm"][i])) <= 2e-6 * float(sq)
+    c = _case("C")
+    for i in range(4):
+        e, sq = ro.prepare_pattern(c["patterns"][i], True)
+        assert np.allclose(e, GOLD["C_prepared"][i], rtol=0, atol=3e-7)
+        assert abs(float(sq) - float(GOLD["C_sqnorm"][i])) <= 2e-6 * float(sq)
+
+
+def test_oracle_objectives_vs_reference():
+    a = _case("A")
+    p = a["problem"]
+    for i in range(8):
+        e, sq = ro.prepare_pattern(a["patterns"][i][a["keep"]], False)
+        assert abs(p.objective_ori(a["start_eulers"][i], e, sq, p.dc) - GOLD["A_objective_start"][i]) < 5e-7
+    b = _case("B")
+    p = b["problem"]
+    for i in range(4):
+        e, sq = ro.prepare_pattern(b["patterns"][i], False)
+        assert abs(p.objective_pc(GOLD["B_pc_start"][i], e, sq, GOLD["B_quats"][i]) - GOLD["B_objective_pc_start"][i]) < 5e-7
+        x6 = np.concatenate([b["start_eulers"][i], GOLD["B_pc_start"][i]])
+        assert abs(p.objective_ori_pc(x6, e, sq) - GOLD["B_objective_ori_pc_start"][i]) < 5e-7
+
+
+def _close(res, gold, var_tol):
+    res, gold = np.asarray(res), np.asarray(gold)
+    assert res.shape == gold.shape
+    assert np.max(np.abs(res[:, 0] - gold[:, 0])) < SCORE_TOL
+    nv = 6 if res.shape[1] >= 8 else 3
+    assert np.max(np.abs(res[:, 2:2 + nv] - gold[:, 2:2 + nv])) < var_tol
+    if res.shape[1] in (6, 9):
+        # which start wins is decided by score differences of ~1e-7 when several starts reach
+        # the same optimum (they do here), so the index itself is not comparable
+        assert np.all((res[:, -1] >= 0) & (res[:, -1] <= 2))
+
+
+def _solve_all(run):
+    """The golden scenarios through ``run(kind, case, **kw)`` (oracle or GPU)."""
+    a, b, c = _case("A"), _case("B"), _case("C")
+    out = {}
+    x0 = a["start_eulers"][:, None, :]
+    out["A_result"] = run("ori", a, x0=x0)
+    tr = np.deg2rad(GOLD["A_trust_region_deg"])
+    out["A_result_bounded"] = run("ori", a, x0=x0, lower=x0 - tr, upper=x0 + tr)
+    out["A_result_ps"] = run("ori", a, x0=GOLD["A_ps_starts"])
+    xb = b["start_eulers"][:, None, :]
+    out["B_result_varying_pc"] = run("ori", b, x0=xb, pcs=b["pcs"])
+    pc0 = GOLD["B_pc_start"][:, None, :]
+    out["B_result_pc"] = run("pc", b, x0=pc0, rotations=GOLD["B_quats"])
+    trp = GOLD["B_pc_trust_region"]
+    out["B_result_pc_bounded"] = run("pc", b, x0=pc0, rotations=GOLD["B_quats"], lower=pc0 - trp, upper=pc0 + trp)
+    out["B_result_ori_pc"] = run("ori_pc", b, x0=np.concatenate([xb, pc0], axis=2))
+    out["C_result"] = run("ori", c, x0=c["start_eulers"][:, None, :], rescale=True, xatol=1e-5, fatol=1e-6, maxfev=150)
+    return out
+
+
+def _oracle_run(kind, case, x0, lower=None, upper=None, rotations=None, pcs=None, rescale=False, **nm):
+    p = case["problem"]
+    pats = case["patterns"][:, case["keep"]]
+    bounds = None if lower is None else np.stack([lower, upper], axis=-1)
+    if kind == "ori":
+        return ro.refine_orientation(p, pats, x0, rescale, bounds=bounds, pcs=pcs, **nm)
+    if kind == "pc":
+        return ro.refine_pc(p, pats, rotations, x0[:, 0], rescale, bounds=None if bounds is None else bounds[:, 0], **nm)
+    return ro.refine_orientation_pc(p, pats, x0, rescale, bounds=bounds, **nm)
+
+
+_TOL = {"A_result": ANGLE_TOL, "A_result_bounded": ANGLE_TOL, "A_result_ps": ANGLE_TOL, "B_result_varying_pc": ANGLE_TOL,
+        "B_result_pc": PC_TOL, "B_result_pc_bounded": PC_TOL, "B_result_ori_pc": 2e-2, "C_result": ANGLE_TOL}
+
+
+def test_oracle_solvers_vs_reference():
+    got = _solve_all(_oracle_run)
+    for name, res in got.items():
+        _close(res, GOLD[name], _TOL[name])
+    # nothing ran away: the searches end where the reference's do, with a similar effort
+    for name in ("A_result", "B_result_pc"):
+        assert np.all(np.abs(got[name][:, 1] - GOLD[name][:, 1]) <= 0.5 * GOLD[name][:, 1])
+
+
+def test_detector_matrix_vs_reference():
+    for ang, m in zip(GOLD["det_angles_deg"], GOLD["det_matrices"]):
+        assert np.allclose(rf.sample_to_detector_matrix(*ang), m, rtol=0, atol=5e-16)  # the reference's is Numba-compiled
+    det = kb.Detector((20, 24), pc=(0.4, 0.2, 0.5), sample_tilt=70, tilt=5)
+    assert np.allclose(det.om_detector_to_sample @ det.om_detector_to_sample.T, np.eye(3), atol=1e-15)
+
+
+# ---- CPU: host mirror ---------------------------------------------------------------------------
+
+class _RecordingContext:
+    """Captures what the mirror hands to the device call."""
+
+    def __init__(self):
+        self.calls = []
+
+    def set_signal_mask(self, mask):
+        self.masks = getattr(self, "masks", []) + [mask]
+
+    def master_pattern(self, mu, ml, dc, **kw):
+        self.dc = dc
+        return "mp"
+
+    def refine(self, mp, mode, patterns, nrows, ncols, rescale, x0, lower, upper, rotations, pcs, om, **opts):
+        self.calls.append(dict(mode=mode, patterns=patterns, rescale=rescale, x0=x0, lower=lower, upper=upper,
+                               rotations=rotations, pcs=pcs, om=om, opts=opts))
+        nv = x0.shape[2]
+        out = np.zeros((x0.shape[0], 2 + nv + (1 if x0.shape[1] > 1 else 0)))
+        out[:, 2:2 + nv] = x0[:, 0]
+        return out
+
+
+def test_host_mirror_arguments():
+    a = _case("A")
+    ctx = _RecordingContext()
+    pats = a["patterns"].reshape(2, 4, 24, 32)
+    quats = rf.euler_to_quaternion(a["start_eulers"])
+    det = kb.Detector((24, 32), pc=a["pc"])
+    mask = ~a["keep"].reshape(24, 32)
+    nav_mask = np.zeros((2, 4), dtype=bool)
+    nav_mask[0, 1] = True
+    res = kb.refine_orientation(pats, quats, det, (a["mu"], a["ml"]), navigation_mask=nav_mask, signal_mask=mask,
+                                trust_region=[1, 2, 3], context=ctx, verbose=False)
+    call = ctx.calls[0]
+    assert call["mode"] == _lib.REFINE_ORI and call["patterns"].shape == (7, 768) and call["rescale"] is False
+    assert call["pcs"] is None and call["opts"] == dict(xatol=1e-4, fatol=1e-4, maxiter=-1, maxfev=-1, adaptive=False)
+    eu = rf.quaternion_to_euler(quats)[np.arange(8) != 1]
+    assert np.allclose(call["x0"][:, 0], eu)
+    assert np.allclose(call["upper"][:, 0] - call["x0"][:, 0], np.deg2rad([1, 2, 3]))
+    assert np.array_equal(ctx.masks[0], mask) and ctx.masks[1] is None and ctx.dc.shape == (768, 3)
+    assert res.size == 7 and res.rotations.shape == (7, 4) and res.scores.shape == (7,) and res.num_evals.dtype == np.int32
+    # trust region clipped to the Euler ranges (+- 5 degrees), _refinement.py:1213-1245
+    kb.refine_orientation(pats, quats, det, (a["mu"], a["ml"]), trust_region=[400, 400, 400], context=ctx, verbose=False)
+    assert np.allclose(ctx.calls[-1]["lower"], -np.deg2rad(5)) and np.allclose(ctx.calls[-1]["upper"][..., 1], np.pi + np.deg2rad(5))
+    # one PC per pattern -> direction cosines on the device; SciPy options are passed through
+    det8 = kb.Detector((24, 32), pc=np.tile(a["pc"], (2, 4, 1)))
+    kb.refine_orientation(pats, quats, det8, (a["mu"], a["ml"]), context=ctx, verbose=False,
+                          method_kwargs=dict(method="Nelder-Mead", tol=1e-3, options=dict(maxfev=50, fatol=1e-6)))
+    assert ctx.calls[-1]["pcs"].shape == (8, 3)
+    assert ctx.calls[-1]["opts"] == dict(xatol=1e-3, fatol=1e-6, maxiter=-1, maxfev=50, adaptive=False)
+    # pseudo-symmetry operators add starts
+    ops = rf.euler_to_quaternion(np.array([[0.1, 0.2, 0.3], [1.0, 0.5, 0.2]]))
+    r = kb.refine_orientation(pats, quats, det, (a["mu"], a["ml"]), pseudo_symmetry_ops=ops, context=ctx, verbose=False)
+    assert ctx.calls[-1]["x0"].shape == (8, 3, 3) and "pseudo_symmetry_index" in r.prop
+    # the other two entry points
+    scores, det2, nev = kb.refine_projection_center(pats, quats, det, (a["mu"], a["ml"]), trust_region=[0.1, 0.1, 0.1],
+                                                    context=ctx, verbose=False)
+    assert ctx.calls[-1]["mode"] == _lib.REFINE_PC and ctx.calls[-1]["rotations"].shape == (8, 4)
+    assert det2.pc.shape == (2, 4, 3) and scores.shape == (8,) and nev.shape == (8,)
+    r, det3 = kb.refine_orientation_projection_center(pats, quats, det, (a["mu"], a["ml"]), trust_region=[1, 1, 1, 0.1, 0.1, 0.1],
+                                                      context=ctx, verbose=False)
+    assert ctx.calls[-1]["mode"] == _lib.REFINE_ORI_PC and ctx.calls[-1]["x0"].shape == (8, 1, 6)
+    assert np.allclose(ctx.calls[-1]["upper"][0, 0] - ctx.calls[-1]["x0"][0, 0], [np.deg2rad(1)] * 3 + [0.1] * 3)
+    # float32 patterns are rescaled by the prepare step (_refinement.py:956)
+    kb.refine_orientation(pats.astype(np.float32), quats, det, (a["mu"], a["ml"]), context=ctx, verbose=False)
+    assert ctx.calls[-1]["rescale"] is True
+
+
+def test_host_mirror_errors(capsys):
+    a = _case("A")
+    pats = a["patterns"].reshape(8, 24, 32)
+    quats = rf.euler_to_quaternion(a["start_eulers"])
+    det = kb.Detector((24, 32), pc=a["pc"])
+    mp = (a["mu"], a["ml"])
+    ctx = _RecordingContext()
+    for method, kwargs in [("differential_evolution", None), ("ln_neldermead", None), ("minimize", dict(method="Powell"))]:
+        with pytest.raises(NotImplementedError):
+            kb.refine_orientation(pats, quats, det, mp, method=method, method_kwargs=kwargs, context=ctx)
+    with pytest.raises(ValueError, match="Detector shape"):
+        kb.refine_orientation(pats, quats, kb.Detector((32, 24)), mp, context=ctx)
+    with pytest.raises(ValueError, match="Signal mask shape"):
+        kb.refine_orientation(pats, quats, det, mp, signal_mask=np.zeros((3, 3), bool), context=ctx)
+    with pytest.raises(ValueError, match="Navigation mask shape"):
+        kb.refine_orientation(pats, quats, det, mp, navigation_mask=np.zeros((2, 4), bool), context=ctx)
+    with pytest.raises(ValueError, match="one projection center"):
+        kb.refine_orientation(pats, quats, kb.Detector((24, 32), pc=np.zeros((3, 3)) + 0.5), mp, context=ctx)
+    kb.refine_orientation(pats, quats, det, mp, trust_region=[1, 1, 1], context=ctx)
+    text = capsys.readouterr().out
+    assert "Refinement information:\n  Method: Nelder-Mead (local) from SciPy" in text
+    assert "Trust region (+/-): [1 1 1]" in text and "Refining 8 orientation(s):" in text and "Refinement speed:" in text
+
+
+# ---- GPU ----------------------------------------------------------------------------------------
+
+def _gpu_run(kind, case, x0, lower=None, upper=None, rotations=None, pcs=None, rescale=False, **nm):
+    ctx = kb.default_context()
+    p = case["problem"]
+    keep = case["keep"]
+    ctx.set_signal_mask(None if keep.all() else ~keep)
+    try:
+        dc = np.zeros((p.nrows * p.ncols, 3))
+        if kind == "ori" and pcs is None:  # direction cosines of the whole detector
+            dc = ro.Problem(p.mu, p.ml, p.nrows, p.ncols, om_detector_to_sample=p.om).dc_from_pc(*case["pc"])
+        mp = ctx.master_pattern(p.mu, p.ml, dc)
+        mode = {"ori": _lib.REFINE_ORI, "pc": _lib.REFINE_PC, "ori_pc": _lib.REFINE_ORI_PC}[kind]
+        return ctx.refine(mp, mode, case["patterns"], p.nrows, p.ncols, rescale, x0, lower, upper, rotations, pcs, p.om, **nm)
+    finally:
+        ctx.set_signal_mask(None)
+
+
+@pytest.mark.gpu
+def test_gpu_vs_oracle_and_reference():
+    """Every golden scenario: against the reference's outputs with the tolerances of the oracle
+    test, and against the oracle itself - same arithmetic, so the searches follow each other
+    step for step (identical evaluation counts) except where a float32 rounding falls differently."""
+    got = _solve_all(_gpu_run)
+    want = _solve_all(_oracle_run)
+    same = total = 0
+    for name, res in got.items():
+        _close(res, GOLD[name], _TOL[name])
+        assert np.max(np.abs(res[:, 0] - want[name][:, 0])) < 2e-5, name
+        ident = (res[:, 1] == want[name][:, 1]) & (np.max(np.abs(res[:, 2:] - want[name][:, 2:]), axis=1) < 1e-9)
+        same += int(ident.sum())
+        total += len(ident)
+    assert same >= 0.9 * total, f"only {same} of {total} searches identical to the oracle's"
+
+
+@pytest.mark.gpu
+def test_gpu_refinement_recovers_orientations_after_indexing():
+    """Dictionary indexing -> refine_orientation through the public API, both on the device."""
+    c = ro.synthetic_case(n=64, seed=7, nrows=30, ncols=30, mp_size=301, noise=0.02, perturb_deg=1.5)
+    det = kb.Detector((30, 30), pc=c["pc"], sample_tilt=70.0)
+    # the synthetic case uses a plain 70 degree tilt about x as its detector matrix
+    det_om = c["om"]
+
+    class Det:
+        shape = (30, 30)
+        pc = c["pc"][None]
+        om_detector_to_sample = det_om
+        gnomonic_bounds = det.gnomonic_bounds
+
+    pats = c["patterns"].reshape(8, 8, 30, 30)
+    start = rf.euler_to_quaternion(c["start_eulers"])
+    res = kb.refine_orientation(pats, start, Det, (c["mu"], c["ml"]), verbose=False)
+    truth = rf.euler_to_quaternion(c["true_eulers"])
+    mis0 = 2 * np.arccos(np.clip(np.abs(np.sum(start * truth, axis=1)), 0, 1))
+    mis1 = 2 * np.arccos(np.clip(np.abs(np.sum(res.rotations * truth, axis=1)), 0, 1))
+    assert np.median(mis1) < 0.25 * np.median(mis0)
+    assert np.all(res.scores > 0.98) and np.all(res.num_evals > 20)
+    want = ro.refine_orientation(c["problem"], c["patterns"], c["start_eulers"][:, None, :], False)
+    assert np.max(np.abs(res.scores - want[:, 0])) < 2e-5
+    assert np.mean(res.num_evals == want[:, 1]) >= 0.9
+
+
+@pytest.mark.gpu
+def test_gpu_refine_edge_cases():
+    a = _case("A")
+    p = a["problem"]
+    x0 = a["start_eulers"][:, None, :]
+    # maxfev smaller than the simplex: SciPy evaluates what it may and returns the best of those
+    got = _gpu_run("ori", a, x0=x0, maxfev=2)
+    want = _oracle_run("ori", a, x0=x0, maxfev=2)
+    assert np.array_equal(got[:, 1], want[:, 1]) and np.all(got[:, 1] == 2)
+    assert np.max(np.abs(got[:, 0] - want[:, 0])) < 1e-6 and np.allclose(got[:, 2:], want[:, 2:], atol=1e-12)
+    # adaptive coefficients, maxiter
+    got = _gpu_run("ori", a, x0=x0, adaptive=True, maxiter=25)
+    want = _oracle_run("ori", a, x0=x0, adaptive=True, maxiter=25)
+    assert np.mean(got[:, 1] == want[:, 1]) >= 0.75 and np.max(np.abs(got[:, 0] - want[:, 0])) < 2e-5
+    # a zero Euler angle starts the simplex with the absolute step (zdelt)
+    x0z = x0.copy()
+    x0z[:, 0, 2] = 0.0
+    got = _gpu_run("ori", a, x0=x0z, maxfev=4)
+    want = _oracle_run("ori", a, x0=x0z, maxfev=4)
+    assert np.max(np.abs(got[:, 0] - want[:, 0])) < 1e-6 and np.allclose(got[:, 2:], want[:, 2:], atol=1e-12)
+    # uint16 / float64 pattern sources give what their float32 cast gives
+    a16 = dict(a, patterns=a["patterns"].astype(np.uint16) * 200)
+    assert np.allclose(_gpu_run("ori", a16, x0=x0, maxfev=30)[:, 0], _oracle_run("ori", a16, x0=x0, maxfev=30)[:, 0], atol=2e-5)
+    with pytest.raises(ValueError):
+        kb.default_context().refine(kb.default_context().master_pattern(p.mu, p.ml, np.zeros((5, 3))), _lib.REFINE_ORI,
+                                    a["patterns"], 24, 32, False, x0)
