@@ -272,6 +272,8 @@ extern "C" int kdi_merge_crystal_maps(kdi_ctx* ctx, int n_maps, int64_t map_size
   int* d_err = reinterpret_cast<int*>(w + o_err);
   KDI_CUDA(ctx, cudaMemsetAsync(d_err, 0, 4, st));
   KDI_CUDA(ctx, cudaMemsetAsync(d_off, 0, (size_t)n_maps * 8, st));
+  ctx->tm = kdi_timings();
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
   if (with_idx) {
     KDI_CUDA(ctx, cudaMemcpyAsync(d_mm, mm_init.data(), mm_init.size() * 8, cudaMemcpyHostToDevice, st));
     int64_t biggest = 1;
@@ -303,6 +305,7 @@ extern "C" int kdi_merge_crystal_maps(kdi_ctx* ctx, int n_maps, int64_t map_size
         reinterpret_cast<double*>(w + o_ms), w + o_mi, d_err);
   }
   KDI_CUDA(ctx, cudaGetLastError());
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
   ctx->tm.kernel_launches++;
   int h_err = 0;
   KDI_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
@@ -315,6 +318,10 @@ extern "C" int kdi_merge_crystal_maps(kdi_ctx* ctx, int n_maps, int64_t map_size
     KDI_CUDA(ctx, cudaMemcpyAsync(merged_indices_out, w + o_mi, n_mer * 8, cudaMemcpyDeviceToHost, st));
   }
   KDI_CUDA(ctx, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  KDI_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  ctx->tm.merge_ms = ms;  // the kernels alone (min/max + offsets + merge), without the copies around them
+  ctx->tm.total_ms = ms;
   if (h_err) return kdi_fail(ctx, KDI_EINVAL, "All-NaN slice encountered");
   return KDI_OK;
 }

@@ -26,6 +26,7 @@
 // Bound: fp64 pipe (about 300 double operations per pixel and evaluation).
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 
 #include "kdi_internal.cuh"
 #include "kdi_project_dev.cuh"
@@ -194,8 +195,8 @@ __device__ double evaluate(const RefineParams& p, const double* x, const double*
 __device__ __forceinline__ bool f_less(double a, double b) { return (a < b) || (b != b && a == a); }
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 
-template <int MODE, int NV>
-__global__ void __launch_bounds__(kRefThreads) kdi_refine_kernel(const RefineParams p) {
+template <int MODE, int NV, int MINB>
+__global__ void __launch_bounds__(kRefThreads, MINB) kdi_refine_kernel(const RefineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int64_t pitch = (p.s_eff + 3) & ~(int64_t)3;
   float* e = reinterpret_cast<float*>(smem_raw);
@@ -488,9 +489,18 @@ extern "C" int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, 
     KDI_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     return KDI_OK;
   };
-  if (mode == KDI_REFINE_ORI) KDI_TRY(launch(kdi_refine_kernel<0, 3>));
-  else if (mode == KDI_REFINE_PC) KDI_TRY(launch(kdi_refine_kernel<1, 3>));
-  else KDI_TRY(launch(kdi_refine_kernel<2, 6>));
+  // resident CTAs per SM the register allocation aims for (KDI_REFINE_MINB = 2, 3 or 4: tuning aid)
+  static const int minb = [] { const char* e = getenv("KDI_REFINE_MINB"); return e ? atoi(e) : 4; }();
+#define KDI_REFINE_LAUNCH(MB)                                                   \
+  do {                                                                          \
+    if (mode == KDI_REFINE_ORI) KDI_TRY(launch(kdi_refine_kernel<0, 3, MB>));   \
+    else if (mode == KDI_REFINE_PC) KDI_TRY(launch(kdi_refine_kernel<1, 3, MB>)); \
+    else KDI_TRY(launch(kdi_refine_kernel<2, 6, MB>));                          \
+  } while (0)
+  if (minb <= 2) KDI_REFINE_LAUNCH(2);
+  else if (minb == 3) KDI_REFINE_LAUNCH(3);
+  else KDI_REFINE_LAUNCH(4);
+#undef KDI_REFINE_LAUNCH
   ctx->tm.kernel_launches++;
   KDI_CUDA(ctx, cudaMemcpyAsync(results_out, w + o_out, (size_t)n_patterns * out_stride * 8, cudaMemcpyDeviceToHost, st));
   ctx->tm.d2h_bytes += n_patterns * out_stride * 8;
