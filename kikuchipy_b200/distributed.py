@@ -116,6 +116,29 @@ def gather_experimental(experimental_host: np.ndarray, n_rows: int, device, grou
     return full[:n_rows]
 
 
+def gather_rows(local: np.ndarray, counts, group=None) -> np.ndarray:
+    """All-gather of per-rank row blocks of a float64 result array (``counts[r]`` rows from rank
+    ``r``, concatenated in rank order on every rank).  Used where the path partitions into
+    independent units with no exchange step (refinement: one pattern = one unit): each rank works
+    on its own slice and only the finished rows travel.  NCCL moves device tensors, gloo (the CPU
+    tests) host tensors."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if len(counts) != world:
+        raise ValueError("one row count per rank is needed")
+    width = int(local.shape[1])
+    per = max(int(c) for c in counts)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.zeros((per, width), dtype=torch.float64, device=dev)
+    mine[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(dev)
+    out = torch.empty((world * per, width), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    out = out.cpu().numpy().reshape(world, per, width)
+    return np.concatenate([out[r, : int(counts[r])] for r in range(world)], axis=0)
+
+
 def _pack(scores, indices):
     """(float32 scores, int64 indices) of equal shape -> one byte tensor ``(..., 12)`` so that both
     travel in ONE collective (one concatenation kernel; NCCL launch latency dominates here)."""

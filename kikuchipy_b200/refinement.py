@@ -253,7 +253,13 @@ def _info_message(method_name, trust_region, method_kwargs, n_ps):
 class _Setup:
     """Everything the three entry points share: points to refine, patterns, masks, geometry."""
 
-    def __init__(self, signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context):
+    def __init__(self, signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context,
+                 sharded=False, group=None):
+        self.sharded, self.group = False, group
+        if sharded:
+            import torch.distributed as dist
+
+            self.sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         data, nav_shape, sig_shape, _, _, _ = _unwrap(signal)
         self.nav_shape = tuple(nav_shape)
         self.nav_size = int(np.prod(nav_shape)) if len(nav_shape) else 1
@@ -293,7 +299,31 @@ class _Setup:
         self.detector = detector
 
     def run(self, mode, x0, lower, upper, rotations, pcs, opts, fixed_dc):
+        """One device call for this process's patterns.  With ``sharded`` (one process per GPU,
+        ``torch.distributed`` initialised) the patterns are split into contiguous balanced slices,
+        every rank refines its own and the finished rows are all-gathered: the path partitions by
+        pattern, there is no exchange step."""
+        if self.sharded:
+            import torch.distributed as dist
+
+            from .distributed import gather_rows, shard_bounds
+
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            bounds = [shard_bounds(self.n, world, r) for r in range(world)]
+            a, b = bounds[rank]
+
+            def cut(arr):
+                return None if arr is None else arr[a:b]
+
+            local = self._run_local(mode, x0[a:b], cut(lower), cut(upper), cut(rotations), cut(pcs), opts, fixed_dc,
+                                    self.patterns[a:b])
+            return gather_rows(local, [e - s for s, e in bounds], self.group)
+        return self._run_local(mode, x0, lower, upper, rotations, pcs, opts, fixed_dc, self.patterns)
+
+    def _run_local(self, mode, x0, lower, upper, rotations, pcs, opts, fixed_dc, patterns):
         ctx = self.ctx
+        if x0.shape[0] == 0:
+            return np.zeros((0, 2 + x0.shape[2] + (1 if x0.shape[1] > 1 else 0)))
         ctx.set_signal_mask(self.signal_mask)
         try:
             if fixed_dc:
@@ -306,7 +336,7 @@ class _Setup:
             else:
                 dc = np.zeros((self.nrows * self.ncols, 3))  # unused: computed per pattern on the device
             mp = ctx.master_pattern(self.mpu, self.mpl, dc)
-            return ctx.refine(mp, mode, self.patterns, self.nrows, self.ncols, self.rescale, x0, lower, upper,
+            return ctx.refine(mp, mode, patterns, self.nrows, self.ncols, self.rescale, x0, lower, upper,
                               rotations, pcs, self.om, **opts)
         finally:
             ctx.set_signal_mask(None)
@@ -334,14 +364,14 @@ def _finish(setup, res, what, verbose, t0):
 def refine_orientation(signal, xmap, detector, master_pattern, energy=None, navigation_mask=None,
                        signal_mask=None, pseudo_symmetry_ops=None, method="minimize", method_kwargs=None,
                        trust_region=None, initial_step=None, rtol=1e-4, maxeval=None, compute=True,
-                       rechunk=True, chunk_kwargs=None, *, context=None, verbose=True):
+                       rechunk=True, chunk_kwargs=None, *, context=None, verbose=True, sharded=False, group=None):
     """Refine orientations with fixed projection centres (``signals/ebsd.py:1986-2177``).
 
     Returns a :class:`RefinementResult` (an orix ``CrystalMap`` needs orix), or with
     ``compute=False`` the raw ``(n, 5 | 6)`` array of the reference (score, evaluations, Euler
     angles[, pseudo-symmetry index]) - already computed, the GPU call is not lazy."""
     opts, name = _nelder_mead_options(method, method_kwargs)
-    setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context)
+    setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context, sharded, group)
     x0, n_ps = _starts(setup, pseudo_symmetry_ops)
     lower, upper = _bounds(x0, trust_region, "ori")
     if verbose:
@@ -373,12 +403,12 @@ def _orientation_result(setup, res, n_eu, with_ps):
 def refine_projection_center(signal, xmap, detector, master_pattern, energy=None, navigation_mask=None,
                              signal_mask=None, method="minimize", method_kwargs=None, trust_region=None,
                              initial_step=None, rtol=1e-4, maxeval=None, compute=True, rechunk=True,
-                             chunk_kwargs=None, *, context=None, verbose=True):
+                             chunk_kwargs=None, *, context=None, verbose=True, sharded=False, group=None):
     """Refine projection centres with fixed orientations (``signals/ebsd.py:2179-2356``).  Returns
     ``(scores, detector with the refined PCs, num_evals)`` like the reference
     (``_refinement.py:133-200``), or the raw ``(n, 5)`` array with ``compute=False``."""
     opts, name = _nelder_mead_options(method, method_kwargs)
-    setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context)
+    setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context, sharded, group)
     x0 = setup.pcs[:, None, :].copy()
     lower, upper = _bounds(x0, trust_region, "pc")
     if verbose:
@@ -398,12 +428,12 @@ def refine_orientation_projection_center(signal, xmap, detector, master_pattern,
                                          navigation_mask=None, signal_mask=None, pseudo_symmetry_ops=None,
                                          method="minimize", method_kwargs=None, trust_region=None,
                                          initial_step=None, rtol=1e-4, maxeval=None, compute=True, rechunk=True,
-                                         chunk_kwargs=None, *, context=None, verbose=True):
+                                         chunk_kwargs=None, *, context=None, verbose=True, sharded=False, group=None):
     """Refine orientations and projection centres together (``signals/ebsd.py:2358-2560``).
     Returns ``(RefinementResult, detector with the refined PCs)``, or the raw ``(n, 8 | 9)``
     array with ``compute=False``."""
     opts, name = _nelder_mead_options(method, method_kwargs)
-    setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context)
+    setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context, sharded, group)
     eu, n_ps = _starts(setup, pseudo_symmetry_ops)
     x0 = np.concatenate([eu, np.repeat(setup.pcs[:, None, :], eu.shape[1], axis=1)], axis=2)
     lower, upper = _bounds(x0, trust_region, "ori_pc")

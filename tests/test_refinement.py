@@ -348,3 +348,55 @@ def test_gpu_refine_edge_cases():
     with pytest.raises(ValueError):
         kb.default_context().refine(kb.default_context().master_pattern(p.mu, p.ml, np.zeros((5, 3))), _lib.REFINE_ORI,
                                     a["patterns"], 24, 32, False, x0)
+
+
+# ---- multi-GPU: partition by pattern, gather the finished rows (gloo, CPU) ----------------------
+
+class _OracleRefineContext(_RecordingContext):
+    """The oracle standing in for ``kdi_refine`` (orientation mode, fixed direction cosines)."""
+
+    def __init__(self, problem):
+        super().__init__()
+        self.problem = problem
+
+    def refine(self, mp, mode, patterns, nrows, ncols, rescale, x0, lower, upper, rotations, pcs, om, **opts):
+        self.calls.append(x0.shape[0])
+        nm = {k: v for k, v in opts.items() if k in ("xatol", "fatol")}
+        return ro.refine_orientation(self.problem, patterns, x0, rescale, maxfev=12, **nm).reshape(x0.shape[0], -1)
+
+
+def _gloo_refine_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = ro.synthetic_case(n=7, seed=4, nrows=12, ncols=14, mp_size=101)
+        ctx = _OracleRefineContext(c["problem"])
+        det = kb.Detector((12, 14), pc=c["pc"])
+        res = kb.refine_orientation(c["patterns"].reshape(7, 12, 14), rf.euler_to_quaternion(c["start_eulers"]), det,
+                                    (c["mu"], c["ml"]), compute=False, context=ctx, verbose=False, sharded=True)
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), res=res, rows=np.array(ctx.calls))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_refinement_gloo(tmp_path, world):
+    """7 patterns over 2 / 3 ranks (ragged slices): every rank refines its slice only and ends up
+    with the same full result as an unsharded run."""
+    import torch.multiprocessing as mp
+
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_gloo_refine_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    c = ro.synthetic_case(n=7, seed=4, nrows=12, ncols=14, mp_size=101)
+    x0 = rf.quaternion_to_euler(rf.euler_to_quaternion(c["start_eulers"]))[:, None, :]
+    want = ro.refine_orientation(c["problem"], c["patterns"], x0, False, maxfev=12)
+    done = 0
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), f"r{r}.npz"))
+        assert np.array_equal(z["res"], want)
+        a, b = kb.shard_bounds(7, world, r)
+        assert list(z["rows"]) == [b - a]
+        done += b - a
+    assert done == 7
