@@ -339,6 +339,33 @@ int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, const void*
                const double* pcs, const double* om_detector_to_sample, const kdi_refine_options* opt,
                double* results_out);
 
+/* ---- experimental-side preprocessing (next row of the path: SURVEY.md section 8f.4) -------------
+ * (EBSD.remove_static_background / remove_dynamic_background / average_neighbour_patterns,
+ *  signals/ebsd.py:442-697, :943-1112; pattern/_pattern.py:96-111, :393-517; filters/fft_barnes.py
+ *  :119-195; pattern/chunk.py:130-164; scipy.ndimage.gaussian_filter / correlate underneath)
+ * patterns: n x (nrows*ncols) of dtype KDI_U8, KDI_U16 or KDI_F32, host or device; out: same shape
+ * and dtype (each step ends with the reference's rescale to the dtype's range and a truncating cast).
+ * kdi_preprocess_patterns runs, in ONE launch and in this order,
+ *   static_op  (0 none, 1 subtract, 2 divide) with static_bg (nrows*ncols float32, host; scale_bg:
+ *              rescaled to each pattern's own intensity range first, _pattern.py:407-414), then
+ *   dynamic_op (0 none, 1 subtract, 2 divide) with the pattern's own Gaussian blur:
+ *              dynamic_domain 1 = "spatial": weights_y / weights_x = the odd-length normalised
+ *              kernel of scipy.ndimage.gaussian_filter, 'reflect' boundary, SciPy's summation order
+ *              (bit-identical); 0 = "frequency": weights = the 1-D factors of the reference's
+ *              normalised Gaussian window (filters/fft_barnes.py convolves with it by FFT, the image
+ *              continued by its edge values; here the same linear convolution is summed directly,
+ *              so results agree to the float32 rounding of the reference's FFT).
+ * kdi_average_neighbour_patterns: patterns of a ny x nx map; window wy x wx float64 over the map
+ * axes (zero entries are outside the footprint); window_sums: ny*nx int32 = what the reference
+ * gets from correlate(ones, window, mode="constant") (signals/ebsd.py:1029-1033). */
+int kdi_preprocess_patterns(kdi_ctx* ctx, const void* patterns, int loc, int dtype, int64_t n, int nrows,
+                            int ncols, int static_op, const float* static_bg, int scale_bg,
+                            int dynamic_op, int dynamic_domain, const double* weights_y, int n_wy,
+                            const double* weights_x, int n_wx, void* out, int out_loc);
+int kdi_average_neighbour_patterns(kdi_ctx* ctx, const void* patterns, int loc, int dtype, int64_t ny,
+                                   int64_t nx, int64_t S, const double* window, int wy, int wx,
+                                   const int32_t* window_sums, void* out, int out_loc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,12 @@ from .similarity_metrics import (
 from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
 from .master_pattern import GeneratedDictionary, direction_cosines, get_patterns
 from .merge_maps import MergedCrystalMap, merge_crystal_maps
+from .preprocessing import (
+    average_neighbour_patterns,
+    preprocess,
+    remove_dynamic_background,
+    remove_static_background,
+)
 from .refinement import (
     Detector,
     RefinementResult,
@@ -36,6 +42,7 @@ __all__ = [
     "NormalizedDotProductMetric",
     "RefinementResult",
     "SimilarityMetric",
+    "average_neighbour_patterns",
     "bind_to_gpu_numa_node",
     "default_context",
     "dictionary_indexing",
@@ -45,9 +52,12 @@ __all__ = [
     "gather_topk",
     "merge_crystal_maps",
     "orientation_similarity_map",
+    "preprocess",
     "refine_orientation",
     "refine_orientation_projection_center",
     "refine_projection_center",
+    "remove_dynamic_background",
+    "remove_static_background",
     "shard_bounds",
 ]
 __version__ = "0.1.0"

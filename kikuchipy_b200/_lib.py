@@ -132,6 +132,10 @@ SIGNATURES = {
         _i,
         [_vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
     ),
+    "kdi_preprocess_patterns": (
+        _i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i]),
+    "kdi_average_neighbour_patterns": (
+        _i, [_vp, _vp, _i, _i, _i64, _i64, _i64, _vp, _i, _i, _vp, _vp, _i]),
     "kdi_refine": (
         _i,
         [_vp, _vp, _i, _vp, _i, _i, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp,
@@ -727,6 +731,55 @@ class Context:
                 fp.ctypes.data, fp.shape[0], fp.shape[1], center_index, out.ctypes.data,
             )
         )
+        return out
+
+    def _pattern_io(self, patterns, device_output):
+        """(pointer, location, dtype code, keep-alive, output array/tensor, its pointer, its location)."""
+        ptr, loc, code, keep = _buffer(patterns, self)
+        if code not in (KDI_U8, KDI_U16, KDI_F32):
+            raise NotImplementedError("patterns must be uint8, uint16 or float32")
+        if loc == KDI_DEVICE or device_output:
+            import torch
+
+            dev = keep.device if loc == KDI_DEVICE else torch.device("cuda", self.device)
+            tdt = {KDI_U8: torch.uint8, KDI_U16: torch.uint16, KDI_F32: torch.float32}[code]
+            out = torch.empty(tuple(keep.shape), dtype=tdt, device=dev)
+            self._stream_sync(dev)
+            return ptr, loc, code, keep, out, out.data_ptr(), KDI_DEVICE
+        out = np.empty(keep.shape, dtype=keep.dtype)
+        return ptr, loc, code, keep, out, out.ctypes.data, KDI_HOST
+
+    def preprocess_patterns(self, patterns, nrows, ncols, static_op=0, static_bg=None, scale_bg=False, dynamic_op=0,
+                            dynamic_domain=0, weights_y=None, weights_x=None, device_output=False):
+        """``kdi_preprocess_patterns`` on ``(n, nrows * ncols)`` patterns (NumPy or CUDA tensor)."""
+        ptr, loc, code, keep, out, optr, oloc = self._pattern_io(patterns, device_output)
+        n = int(np.prod(keep.shape)) // (nrows * ncols)
+        bg = None if static_bg is None else np.ascontiguousarray(static_bg, dtype=np.float32).reshape(-1)
+        wy = None if weights_y is None else np.ascontiguousarray(weights_y, dtype=np.float64)
+        wx = None if weights_x is None else np.ascontiguousarray(weights_x, dtype=np.float64)
+        self._check(
+            self._lib.kdi_preprocess_patterns(
+                self._h, ptr, loc, code, n, int(nrows), int(ncols), int(static_op),
+                None if bg is None else bg.ctypes.data, int(bool(scale_bg)), int(dynamic_op), int(dynamic_domain),
+                None if wy is None else wy.ctypes.data, 0 if wy is None else wy.size,
+                None if wx is None else wx.ctypes.data, 0 if wx is None else wx.size, optr, oloc,
+            )
+        )
+        del keep
+        return out
+
+    def average_neighbour_patterns(self, patterns, ny, nx, n_pixels, window, window_sums, device_output=False):
+        """``kdi_average_neighbour_patterns`` on the ``(ny * nx, n_pixels)`` patterns of a map."""
+        ptr, loc, code, keep, out, optr, oloc = self._pattern_io(patterns, device_output)
+        w = np.ascontiguousarray(window, dtype=np.float64)
+        sums = np.ascontiguousarray(window_sums, dtype=np.int32)
+        self._check(
+            self._lib.kdi_average_neighbour_patterns(
+                self._h, ptr, loc, code, int(ny), int(nx), int(n_pixels), w.ctypes.data, w.shape[0], w.shape[1],
+                sums.ctypes.data, optr, oloc,
+            )
+        )
+        del keep
         return out
 
     def refine(self, mp: "MasterPattern", mode: int, patterns, nrows: int, ncols: int, rescale: bool, x0,

@@ -163,10 +163,11 @@ def load_master_pattern():
         stub.__file__ = path
         from numba import njit
 
-        ns = {"njit": njit, "np": np}
-        exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
-        stub._rescale_with_min_max = ns["_rescale_with_min_max"]
+        # executed inside the stub module itself (it has a __name__): Numba's on-disk cache
+        # (cache=True) re-imports the defining module by name when it loads an entry
+        stub.njit, stub.np = njit, np
         sys.modules["kikuchipy.pattern._pattern"] = stub
+        exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), stub.__dict__)
     return _load("kikuchipy.signals.util._master_pattern", "signals/util/_master_pattern.py")
 
 
@@ -200,3 +201,52 @@ def load_refinement():
     _load("kikuchipy.indexing._refinement._objective_functions", "indexing/_refinement/_objective_functions.py")
     solvers = _load("kikuchipy.indexing._refinement._solvers", "indexing/_refinement/_solvers.py")
     return solvers, mp
+
+
+def load_preprocessing():
+    """Return a namespace with the reference's background-removal / neighbour-averaging functions,
+    executed in place: ``filters/window.py`` and ``filters/fft_barnes.py`` load as they are (with a
+    stub for matplotlib, which ``window.py`` imports for its plot method only); from
+    ``pattern/_pattern.py`` (scikit-image) and ``pattern/chunk.py`` (dask) the needed functions are
+    compiled from their own source lines (AST extraction, nothing copied into this repository)."""
+    import ast
+
+    load_master_pattern()  # stubs + kikuchipy.pattern._pattern with _rescale_with_min_max
+    for name in ("matplotlib", "matplotlib.figure", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.Figure = object
+            m.subplots = None
+            sys.modules[name] = m
+    sys.modules["matplotlib"].figure = sys.modules["matplotlib.figure"]
+    if "kikuchipy.filters" not in sys.modules:
+        pkg = types.ModuleType("kikuchipy.filters")
+        pkg.__path__ = []
+        sys.modules["kikuchipy.filters"] = pkg
+    window = _load("kikuchipy.filters.window", "filters/window.py")
+    barnes = _load("kikuchipy.filters.fft_barnes", "filters/fft_barnes.py")
+    from numba import njit
+    from scipy.ndimage import correlate, gaussian_filter
+
+    stub = sys.modules["kikuchipy.pattern._pattern"]
+    if not hasattr(stub, "_remove_dynamic_background"):
+        path = os.path.join(_SRC, "pattern", "_pattern.py")
+        want = ("_remove_static_background_subtract", "_remove_static_background_divide", "_remove_dynamic_background",
+                "_remove_background_subtract", "_remove_background_divide", "_dynamic_background_frequency_space_setup")
+        fns = [n for n in ast.parse(open(path).read()).body if isinstance(n, ast.FunctionDef) and n.name in want]
+        stub.njit, stub.np, stub.Callable = njit, np, __import__("typing").Callable
+        stub.Window, stub._fft_filter, stub._fft_filter_setup = window.Window, barnes._fft_filter, barnes._fft_filter_setup
+        stub.gaussian_filter = gaussian_filter
+        exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), stub.__dict__)
+    if "kikuchipy.pattern.chunk" not in sys.modules:
+        path = os.path.join(_SRC, "pattern", "chunk.py")
+        chunk = types.ModuleType("kikuchipy.pattern.chunk")
+        chunk.__file__ = path
+        sys.modules["kikuchipy.pattern.chunk"] = chunk
+        chunk.njit, chunk.np, chunk.correlate, chunk.Window = njit, np, correlate, window.Window
+        chunk._rescale_with_min_max = stub._rescale_with_min_max
+        want = ("_average_neighbour_patterns", "_rescale_neighbour_averaged_patterns")
+        fns = [n for n in ast.parse(open(path).read()).body if isinstance(n, ast.FunctionDef) and n.name in want]
+        exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), chunk.__dict__)
+    ns = types.SimpleNamespace(Window=window.Window, fft_barnes=barnes, pattern=stub, chunk=sys.modules["kikuchipy.pattern.chunk"])
+    return ns
