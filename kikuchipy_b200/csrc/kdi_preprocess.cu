@@ -28,6 +28,8 @@ namespace {
 
 constexpr int kPreThreads = 256;
 constexpr int kPreWarps = kPreThreads / 32;
+constexpr int kMaxTaps = 128;  // frequency-domain window length the parameter block holds
+constexpr int kRows = 4;       // outputs per thread of the sliding-window convolution
 
 struct PreParams {
   const void* src;
@@ -45,6 +47,10 @@ struct PreParams {
   const double* wy;     // weights along axis 0 (rows)
   const double* wx;     // weights along axis 1 (columns)
   int nwy, nwx;
+  // frequency domain: the same weights as float32 in the parameter block (constant bank: a
+  // uniform-indexed operand costs no shared-memory or L1 traffic)
+  float wyf[kMaxTaps];
+  float wxf[kMaxTaps];
 };
 
 __device__ __forceinline__ void block_minmax(float& lo, float& hi, float (*red)[kPreWarps]) {
@@ -103,10 +109,43 @@ __device__ __forceinline__ void rescale_cast(float* p, int S, float omin, float 
 }
 
 __device__ __forceinline__ int reflect_index(int i, int n) {  // (d c b a | a b c d | d c b a)
+  if (i >= 0 && i < n) return i;
+  if (i < 0 && i >= -n) return -i - 1;
+  if (i >= n && i < 2 * n) return 2 * n - 1 - i;
   const int period = 2 * n;
   i %= period;
   if (i < 0) i += period;
   return i < n ? i : period - 1 - i;
+}
+
+// One pass of the frequency-domain blur: out[(c) * n_lines + l] (TRANSPOSED) = sum_a w[a] *
+// in[clamp(l + half - a) * n_cols + c] for the n_lines x n_cols array `in` - a convolution along
+// the first axis with the line continued by its edge values.  Each thread produces kRows
+// consecutive outputs of one column from a sliding window (one shared-memory read per source
+// element instead of one per tap); consecutive threads take consecutive columns, so the reads
+// are conflict-free.  Writing the result transposed makes the second pass the same routine.
+__device__ __forceinline__ void conv_first_axis_transposed(const float* __restrict__ in, float* __restrict__ out,
+                                                           int n_lines, int n_cols, const float* w, int nw) {
+  const int half = (nw - 1) / 2;
+  const int blocks = (n_lines + kRows - 1) / kRows;
+  for (int item = threadIdx.x; item < blocks * n_cols; item += kPreThreads) {
+    const int lb = item / n_cols, c = item - lb * n_cols;
+    const int l0 = lb * kRows;
+    float acc[kRows];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) acc[i] = 0.f;
+    for (int s = half - (nw - 1); s <= half + kRows - 1; ++s) {
+      const float v = in[min(max(l0 + s, 0), n_lines - 1) * n_cols + c];
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) {
+        const int a = half + i - s;
+        if (a >= 0 && a < nw) acc[i] = fmaf(v, w[a], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kRows; ++i)
+      if (l0 + i < n_lines) out[c * n_lines + l0 + i] = acc[i];
+  }
 }
 
 __global__ void __launch_bounds__(kPreThreads) kdi_preprocess_kernel(const PreParams q) {
@@ -118,7 +157,16 @@ __global__ void __launch_bounds__(kPreThreads) kdi_preprocess_kernel(const PrePa
   __shared__ float red[2][kPreWarps];
   for (int64_t row = blockIdx.x; row < q.n; row += gridDim.x) {
     __syncthreads();
-    for (int j = threadIdx.x; j < S; j += kPreThreads) p[j] = load_px(q.src, q.dtype, row * S + j);
+    if (q.dtype == KDI_U8 && (S & 3) == 0) {
+      const uint32_t* src4 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(q.src) + row * S);
+      for (int j = threadIdx.x; j < S / 4; j += kPreThreads) {
+        const uint32_t v = __ldg(src4 + j);
+        *reinterpret_cast<float4*>(p + 4 * j) =
+            make_float4((float)(v & 0xffu), (float)((v >> 8) & 0xffu), (float)((v >> 16) & 0xffu), (float)(v >> 24));
+      }
+    } else {
+      for (int j = threadIdx.x; j < S; j += kPreThreads) p[j] = load_px(q.src, q.dtype, row * S + j);
+    }
     __syncthreads();
     if (q.static_op) {
       float k = 0.f, o = 0.f;
@@ -140,58 +188,57 @@ __global__ void __launch_bounds__(kPreThreads) kdi_preprocess_kernel(const PrePa
       __syncthreads();
       rescale_cast(p, S, q.omin, q.orange, q.dtype, red);
     }
-    if (q.dynamic_op) {
-      // pass 1 along axis 0 (rows) into tmp, pass 2 along axis 1 (columns) into bg
+    if (q.dynamic_op && q.domain == 0) {
+      // frequency domain: linear convolution with the separable window, float32 like the
+      // reference's FFT; rows first (result transposed), then columns (transposed back)
+      conv_first_axis_transposed(p, tmp, q.nrows, q.ncols, q.wyf, q.nwy);
+      __syncthreads();
+      conv_first_axis_transposed(tmp, bg, q.ncols, q.nrows, q.wxf, q.nwx);
+      __syncthreads();
+    }
+    if (q.dynamic_op && q.domain == 1) {
+      // spatial domain: pass 1 along axis 0 (rows) into tmp, pass 2 along axis 1 (columns) into bg
       for (int j = threadIdx.x; j < S; j += kPreThreads) {
         const int y = j / q.ncols, x = j - y * q.ncols;
-        double acc;
-        if (q.domain == 1) {
-          const int lw = q.nwy / 2;
-          acc = __dmul_rn((double)p[j], q.wy[lw]);
-          for (int jj = -lw; jj < 0; ++jj) {
-            const double a = (double)p[reflect_index(y + jj, q.nrows) * q.ncols + x];
-            const double b = (double)p[reflect_index(y - jj, q.nrows) * q.ncols + x];
-            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), q.wy[lw + jj]));
-          }
-        } else {
-          const int ay = (q.nwy - 1) / 2;
-          acc = 0.0;
-          for (int a = 0; a < q.nwy; ++a) {
-            const int r = min(max(y + ay - a, 0), q.nrows - 1);
-            acc += (double)p[r * q.ncols + x] * q.wy[a];
-          }
+        const int lw = q.nwy / 2;
+        double acc = __dmul_rn((double)p[j], q.wy[lw]);
+        for (int jj = -lw; jj < 0; ++jj) {
+          const double a = (double)p[reflect_index(y + jj, q.nrows) * q.ncols + x];
+          const double b = (double)p[reflect_index(y - jj, q.nrows) * q.ncols + x];
+          acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), q.wy[lw + jj]));
         }
         tmp[j] = (float)acc;
       }
       __syncthreads();
       for (int j = threadIdx.x; j < S; j += kPreThreads) {
         const int y = j / q.ncols, x = j - y * q.ncols;
-        double acc;
-        if (q.domain == 1) {
-          const int lw = q.nwx / 2;
-          acc = __dmul_rn((double)tmp[j], q.wx[lw]);
-          for (int jj = -lw; jj < 0; ++jj) {
-            const double a = (double)tmp[y * q.ncols + reflect_index(x + jj, q.ncols)];
-            const double b = (double)tmp[y * q.ncols + reflect_index(x - jj, q.ncols)];
-            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), q.wx[lw + jj]));
-          }
-        } else {
-          const int ax = (q.nwx - 1) / 2;
-          acc = 0.0;
-          for (int b = 0; b < q.nwx; ++b) {
-            const int c = min(max(x + ax - b, 0), q.ncols - 1);
-            acc += (double)tmp[y * q.ncols + c] * q.wx[b];
-          }
+        const int lw = q.nwx / 2;
+        double acc = __dmul_rn((double)tmp[j], q.wx[lw]);
+        for (int jj = -lw; jj < 0; ++jj) {
+          const double a = (double)tmp[y * q.ncols + reflect_index(x + jj, q.ncols)];
+          const double b = (double)tmp[y * q.ncols + reflect_index(x - jj, q.ncols)];
+          acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), q.wx[lw + jj]));
         }
         bg[j] = (float)acc;
       }
       __syncthreads();
+    }
+    if (q.dynamic_op) {
       for (int j = threadIdx.x; j < S; j += kPreThreads)
         p[j] = q.dynamic_op == 1 ? __fsub_rn(p[j], bg[j]) : __fdiv_rn(p[j], bg[j]);
       __syncthreads();
       rescale_cast(p, S, q.omin, q.orange, q.dtype, red);
     }
-    for (int j = threadIdx.x; j < S; j += kPreThreads) store_px(q.dst, q.dtype, row * S + j, p[j]);
+    if (q.dtype == KDI_U8 && (S & 3) == 0) {
+      uint32_t* dst4 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(q.dst) + row * S);
+      for (int j = threadIdx.x; j < S / 4; j += kPreThreads) {
+        const float4 v = *reinterpret_cast<const float4*>(p + 4 * j);
+        dst4[j] = (uint32_t)(uint8_t)v.x | ((uint32_t)(uint8_t)v.y << 8) | ((uint32_t)(uint8_t)v.z << 16) |
+                  ((uint32_t)(uint8_t)v.w << 24);
+      }
+    } else {
+      for (int j = threadIdx.x; j < S; j += kPreThreads) store_px(q.dst, q.dtype, row * S + j, p[j]);
+    }
   }
 }
 
@@ -270,9 +317,11 @@ extern "C" int kdi_preprocess_patterns(kdi_ctx* ctx, const void* patterns, int l
     return kdi_fail(ctx, KDI_EINVAL, "kdi_preprocess_patterns: the spatial filter needs an odd number of weights");
   if (n == 0) return KDI_OK;
   const int64_t S = (int64_t)nrows * ncols;
-  const size_t smem = (size_t)S * 3 * sizeof(float);
+  const size_t smem = (size_t)S * (dynamic_op ? 3 : 1) * sizeof(float);
   if (smem > 200 * 1024)
     return kdi_fail(ctx, KDI_EUNSUPPORTED, "kdi_preprocess_patterns: a %d x %d detector does not fit the kernel's shared-memory staging", nrows, ncols);
+  if (dynamic_op && dynamic_domain == 0 && (n_wy > kMaxTaps || n_wx > kMaxTaps))
+    return kdi_fail(ctx, KDI_EUNSUPPORTED, "kdi_preprocess_patterns: frequency-domain windows of more than %d pixels are not supported", kMaxTaps);
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const size_t esz = kdi_dtype_size(dtype);
@@ -315,6 +364,10 @@ extern "C" int kdi_preprocess_patterns(kdi_ctx* ctx, const void* patterns, int l
   q.wx = reinterpret_cast<const double*>(w + o_wx);
   q.nwy = n_wy;
   q.nwx = n_wx;
+  if (dynamic_op && dynamic_domain == 0) {
+    for (int a = 0; a < n_wy; ++a) q.wyf[a] = (float)weights_y[a];
+    for (int a = 0; a < n_wx; ++a) q.wxf[a] = (float)weights_x[a];
+  }
   KDI_CUDA(ctx, cudaFuncSetAttribute(kdi_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const unsigned grid = (unsigned)std::min<int64_t>(n, (int64_t)ctx->sm_count * 16);
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
