@@ -409,7 +409,53 @@ def run_ours(args, rank, world, local_rank):
                       f"time scaled linearly to {m_total} patterns, dictionary preparation counted once",
             "detail": detail,
         }
+    if world == 1 and not args.no_extras:
+        try:
+            line["neighbouring_rows"] = neighbouring_rows(ctx)
+        except Exception as e:  # noqa: BLE001 - never lose the main line to an extra
+            line["neighbouring_rows"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
+
+
+def neighbouring_rows(ctx):
+    """Device timings (CUDA events inside the library) of the rows either side of the path
+    (SURVEY.md section 8f): preprocessing of the measured patterns and orientation refinement of
+    the indexed ones, on synthetic inputs of the benchmark's pattern size.  Not part of `value`."""
+    import torch
+
+    import kikuchipy_b200 as kb
+    from kikuchipy_b200 import _lib
+    from kikuchipy_b200 import synthetic as syn
+
+    out = {}
+    rng = np.random.default_rng(7)
+    pats = rng.integers(0, 256, (M_PER_GPU, SIG[0], SIG[1]), dtype=np.uint8)
+    bg = pats[:16].mean(axis=0).astype(np.uint8)
+    dev = torch.from_numpy(pats).cuda()
+    for _ in range(2):
+        kb.preprocess(dev, static_bg=bg)
+    ms = ctx.timings()["total_ms"]
+    out["preprocess_static+dynamic"] = {"patterns": M_PER_GPU, "kernel_ms": round(ms, 3),
+                                        "patterns_per_s": round(M_PER_GPU / ms * 1e3)}
+    n_ref, mp_n = 4096, 501
+    mu, ml = syn.synthetic_master_pattern(mp_n, seed=5)
+    dc = kb.direction_cosines([-0.9, 0.85, -0.7, 0.95], 0.5, SIG[0], SIG[1], syn.tilted_detector_matrix(70.0))
+    eu = np.stack([rng.uniform(0.2, 6.0, n_ref), rng.uniform(0.2, 2.9, n_ref), rng.uniform(0.2, 6.0, n_ref)], axis=1)
+    quat = kb.refinement.euler_to_quaternion(eu)
+    mp = ctx.master_pattern(mu, ml, dc)
+    sim = ctx.project_patterns(mp, quat)
+    lo, hi = sim.min(axis=1, keepdims=True), sim.max(axis=1, keepdims=True)
+    pats8 = np.round((sim - lo) / (hi - lo) * 255).astype(np.uint8)
+    x0 = (eu + np.deg2rad(rng.uniform(-1, 1, eu.shape)))[:, None, :]
+    for _ in range(2):
+        res = ctx.refine(mp, _lib.REFINE_ORI, pats8, SIG[0], SIG[1], False, x0)
+    ms = ctx.timings()["total_ms"]
+    out["refine_orientation"] = {"patterns": n_ref, "kernel_ms": round(ms, 3), "patterns_per_s": round(n_ref / ms * 1e3),
+                                 "mean_evaluations": round(float(res[:, 1].mean()), 1),
+                                 "mean_score": round(float(res[:, 0].mean()), 5),
+                                 "median_misorientation_to_truth_deg": round(float(np.degrees(np.median(
+                                     2 * np.arccos(np.clip(np.abs(np.sum(kb.refinement.euler_to_quaternion(res[:, 2:5]) * quat, axis=1)), 0, 1))))), 4)}
+    return out
 
 
 def main():
@@ -421,6 +467,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=500)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the preprocessing / refinement timings")
     ap.add_argument("--no-generated", action="store_true", help="skip the generated-dictionary end-to-end leg")
     ap.add_argument("--numa-bind", action="store_true",
                     help="bind each rank to its GPU's NUMA node (no effect on single-node-affinity boxes like this pool's)")
