@@ -245,6 +245,14 @@ int kdi_master_pattern_destroy(kdi_ctx* ctx, kdi_master_pattern* mp);
  * (a, b, c, d), host or device; out: n x S float32, host or device. */
 int kdi_project_patterns(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations,
                          int rot_loc, int64_t n, float* out, int out_loc);
+/* _project_patterns_from_master_pattern_with_varying_pc (:374-445) with the direction cosines of
+ * _get_direction_cosines_for_varying_pc (:207-296) computed on the device: rotation i is projected
+ * for its own projection centre pcs[i] = (PCx, PCy, PCz) (Bruker convention).  rotations, pcs and
+ * om_detector_to_sample (3 x 3 row-major) on the host; out: n x nrows*ncols float32 on the host.
+ * The direction cosines stored in mp are not used; nrows*ncols must equal its pixel count. */
+int kdi_project_patterns_varying_pc(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations,
+                                    int64_t n, const double* pcs, int nrows, int ncols,
+                                    const double* om_detector_to_sample, float* out);
 /* get_patterns + prepare_dictionary fused: a prepared (normalised) pattern set straight from
  * rotations (the current signal mask applies, as in kdi_patterns_create). */
 int kdi_patterns_create_projected(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations,

@@ -123,6 +123,7 @@ SIGNATURES = {
                                        C.c_double, C.POINTER(_vp)]),
     "kdi_master_pattern_destroy": (_i, [_vp, _vp]),
     "kdi_project_patterns": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _i]),
+    "kdi_project_patterns_varying_pc": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp]),
     "kdi_patterns_create_projected": (_i, [_vp, _vp, _vp, _i, _i64, _i, C.POINTER(_vp)]),
     "kdi_dictionary_indexing_projected": (
         _i, [_vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _i, _i64, _i, _i, _vp, _i64, _vp, _vp, _i]),
@@ -634,6 +635,19 @@ class Context:
             self._stream_sync(keep.device)
         self._check(self._lib.kdi_project_patterns(self._h, mp._h, rptr, rloc, n, optr, oloc))
         del keep
+        return res
+
+    def project_patterns_varying_pc(self, mp: MasterPattern, rotations, pcs, nrows, ncols, om_detector_to_sample):
+        """``(n, nrows * ncols)`` float32 patterns, rotation ``i`` seen from projection centre ``pcs[i]``."""
+        rot = np.ascontiguousarray(rotations, dtype=np.float64).reshape(-1, 4)
+        pc = np.ascontiguousarray(pcs, dtype=np.float64).reshape(-1, 3)
+        if pc.shape[0] != rot.shape[0]:
+            raise ValueError("one projection centre per rotation is needed")
+        om = np.ascontiguousarray(om_detector_to_sample, dtype=np.float64).reshape(3, 3)
+        res = np.empty((rot.shape[0], mp.n_pixels), dtype=np.float32)
+        self._check(self._lib.kdi_project_patterns_varying_pc(
+            self._h, mp._h, rot.ctypes.data, rot.shape[0], pc.ctypes.data, int(nrows), int(ncols), om.ctypes.data,
+            res.ctypes.data))
         return res
 
     def patterns_projected(self, mp: MasterPattern, rotations, metric: int) -> Patterns:

@@ -71,7 +71,46 @@ __device__ __forceinline__ bool ranks_before(T ka, int pa, T kb, int pb) {
   return pa < pb;
 }
 
-template <typename T>
+// Bitonic sort of 32 * E (key, position) pairs held E per lane (element i = e * 32 + lane): partners
+// closer than 32 are exchanged by shuffle, farther ones sit in the same lane.  Fully unrolled, so
+// the slots stay in registers.
+template <typename T, int E>
+__device__ __forceinline__ void warp_sort_registers(T (&key)[E], int (&pos)[E], int lane) {
+  constexpr int L = 32 * E;
+#pragma unroll
+  for (int k = 2; k <= L; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int pe = e ^ (j >> 5);
+          if (pe > e) {
+            const bool up = (((e * 32 + lane) & k) == 0);
+            const bool a_first = ranks_before<T>(key[e], pos[e], key[pe], pos[pe]);
+            if (up ? !a_first : a_first) {
+              const T tk = key[e]; key[e] = key[pe]; key[pe] = tk;
+              const int tp = pos[e]; pos[e] = pos[pe]; pos[pe] = tp;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const T ok = __shfl_xor_sync(0xffffffffu, key[e], j);
+          const int op = __shfl_xor_sync(0xffffffffu, pos[e], j);
+          const bool up = (((e * 32 + lane) & k) == 0);
+          const bool lower = (lane & j) == 0;
+          const bool mine_first = ranks_before<T>(key[e], pos[e], ok, op);
+          const bool keep = (lower == up) ? mine_first : !mine_first;
+          if (!keep) { key[e] = ok; pos[e] = op; }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int E>
 __global__ void __launch_bounds__(256)
 kdi_merge_maps_kernel(MapArgs a, int n_maps, int64_t map_size, int n_scores, int n_best, int sign,
                       int with_idx, int idx_as_double, int l_pad, const long long* __restrict__ off,
@@ -83,7 +122,7 @@ kdi_merge_maps_kernel(MapArgs a, int n_maps, int64_t map_size, int n_scores, int
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t p = (int64_t)blockIdx.x * warps + warp;
   if (p >= map_size) return;
-  T* keys = reinterpret_cast<T*>(smem_raw) + (size_t)warp * l_pad;
+  T* keys = reinterpret_cast<T*>(smem_raw) + (size_t)warp * l_pad;  // (E == 0 only)
   int* pos = reinterpret_cast<int*>(smem_raw + (size_t)warps * l_pad * sizeof(T)) + (size_t)warp * l_pad;
   const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
   auto row_of = [&](int k) -> int64_t { return a.rows[k] ? (int64_t)a.rows[k][p] : p; };
@@ -139,6 +178,41 @@ kdi_merge_maps_kernel(MapArgs a, int n_maps, int64_t map_size, int n_scores, int
 
   // --- all N*K scores of the point in stable best-first order (:298-308) ---
   const int total = n_scores * n_maps;
+  if constexpr (E > 0) {  // up to 32 * E values: sorted in registers
+    T rk[E];
+    int rp[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+      const int e = s * 32 + lane;
+      T v = nan;
+      rp[s] = INT_MAX;
+      if (e < total) {
+        const int n = e / n_maps, k = e - n * n_maps;
+        const int64_t r = row_of(k);
+        if (r >= 0) v = reinterpret_cast<const T*>(a.scores[k])[r * n_scores + n];
+        rp[s] = e;
+      }
+      rk[s] = (T)(-sign) * v;
+    }
+    warp_sort_registers<T, E>(rk, rp, lane);
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+      const int e = s * 32 + lane;
+      if (e >= total) continue;
+      const int ps = rp[s];
+      const int n = ps / n_maps, k = ps - n * n_maps;
+      const int64_t r = row_of(k);
+      const int64_t o = p * total + e;
+      merged_scores[o] = r >= 0 ? reinterpret_cast<const T*>(a.scores[k])[r * n_scores + n] : nan;
+      if (with_idx) {
+        if (idx_as_double)
+          reinterpret_cast<double*>(merged_idx)[o] =
+              r >= 0 ? (double)(a.idx[k][r * n_scores + n] + off[k]) : __longlong_as_double(0x7ff8000000000000LL);
+        else
+          reinterpret_cast<long long*>(merged_idx)[o] = r >= 0 ? a.idx[k][r * n_scores + n] + off[k] : LLONG_MIN;
+      }
+    }
+  } else {
   for (int e = lane; e < l_pad; e += 32) {
     T v = nan;
     int ps = INT_MAX;
@@ -181,6 +255,7 @@ kdi_merge_maps_kernel(MapArgs a, int n_maps, int64_t map_size, int n_scores, int
         reinterpret_cast<long long*>(merged_idx)[o] = r >= 0 ? a.idx[k][r * n_scores + n] + off[k] : LLONG_MIN;
     }
   }
+  }  // shared-memory path
 }
 
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -285,25 +360,30 @@ extern "C" int kdi_merge_crystal_maps(kdi_ctx* ctx, int n_maps, int64_t map_size
     KDI_CUDA(ctx, cudaGetLastError());
     ctx->tm.kernel_launches += 2;
   }
-  int l_pad = 2;
+  int l_pad = 32;
   while (l_pad < total) l_pad <<= 1;
-  const size_t per_warp = (size_t)l_pad * (es + 4);
-  const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / per_warp));
+  const int e_reg = l_pad <= 128 ? l_pad / 32 : 0;  // values per lane of the register sort (0: shared memory)
+  const size_t per_warp = e_reg ? 0 : (size_t)l_pad * (es + 4);
+  const int warps = e_reg ? 8 : (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / per_warp));
   const size_t smem = per_warp * warps;
   const unsigned blocks = (unsigned)kdi_ceil_div(map_size, (int64_t)warps);
+#define KDI_MERGE_LAUNCH(T, E)                                                                          \
+  kdi_merge_maps_kernel<T, E><<<blocks, warps * 32, smem, st>>>(                                        \
+      a, n_maps, map_size, n_scores, mean_n_best, sign, with_idx, idx_as_double, l_pad, d_off,          \
+      reinterpret_cast<long long*>(w + o_ph), reinterpret_cast<T*>(w + o_ns), reinterpret_cast<double*>(w + o_nr), \
+      reinterpret_cast<int32_t*>(w + o_nx), reinterpret_cast<T*>(w + o_ms), w + o_mi, d_err)
   if (score_dtype == KDI_F32) {
-    kdi_merge_maps_kernel<float><<<blocks, warps * 32, smem, st>>>(
-        a, n_maps, map_size, n_scores, mean_n_best, sign, with_idx, idx_as_double, l_pad, d_off,
-        reinterpret_cast<long long*>(w + o_ph), reinterpret_cast<float*>(w + o_ns),
-        reinterpret_cast<double*>(w + o_nr), reinterpret_cast<int32_t*>(w + o_nx),
-        reinterpret_cast<float*>(w + o_ms), w + o_mi, d_err);
+    if (e_reg == 1) KDI_MERGE_LAUNCH(float, 1);
+    else if (e_reg == 2) KDI_MERGE_LAUNCH(float, 2);
+    else if (e_reg == 4) KDI_MERGE_LAUNCH(float, 4);
+    else KDI_MERGE_LAUNCH(float, 0);
   } else {
-    kdi_merge_maps_kernel<double><<<blocks, warps * 32, smem, st>>>(
-        a, n_maps, map_size, n_scores, mean_n_best, sign, with_idx, idx_as_double, l_pad, d_off,
-        reinterpret_cast<long long*>(w + o_ph), reinterpret_cast<double*>(w + o_ns),
-        reinterpret_cast<double*>(w + o_nr), reinterpret_cast<int32_t*>(w + o_nx),
-        reinterpret_cast<double*>(w + o_ms), w + o_mi, d_err);
+    if (e_reg == 1) KDI_MERGE_LAUNCH(double, 1);
+    else if (e_reg == 2) KDI_MERGE_LAUNCH(double, 2);
+    else if (e_reg == 4) KDI_MERGE_LAUNCH(double, 4);
+    else KDI_MERGE_LAUNCH(double, 0);
   }
+#undef KDI_MERGE_LAUNCH
   KDI_CUDA(ctx, cudaGetLastError());
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
   ctx->tm.kernel_launches++;

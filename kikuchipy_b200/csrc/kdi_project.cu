@@ -30,6 +30,12 @@ constexpr int kProjThreads = 256;
 struct ProjParams {
   const double* rot;  // n x 4 (a, b, c, d)
   const double* dc;   // S x 3
+  // one projection centre per rotation (or null): direction cosines are then computed per pixel
+  // from (PCx, PCy, PCz) - get_gnomonic_bounds + _get_direction_cosines_for_varying_pc
+  // (signals/util/_master_pattern.py:207-296)
+  const double* pcs;  // n x 3
+  int nrows, ncols;
+  double om[9];       // detector -> sample, row-major
   const void* upper;  // npy x npx, MT
   const void* lower;
   int npx, npy;       // as the reference passes them (npx bounds the row index, npy the column index)
@@ -104,8 +110,32 @@ kdi_project_kernel(const ProjParams p) {
                          __dadd_rn(__dadd_rn(__dadd_rn(aa, -bb), -cc), dd), __dadd_rn(ab, cd), __dadd_rn(bd, -ac)};
     __syncthreads();  // previous row's readers are done with v / vd
     double lo = INFINITY, hi = -INFINITY;
+    double gx0 = 0, gy0 = 0, xs = 0, ys = 0, xh = 0, yh = 0, pcz = 0;
+    if (p.pcs) {
+      const double pcx = p.pcs[row * 3], pcy = p.pcs[row * 3 + 1];
+      pcz = p.pcs[row * 3 + 2];
+      const double aspect = (double)p.ncols / (double)p.nrows;
+      const double x_min = -aspect * (pcx / pcz), x_max = aspect * (1.0 - pcx) / pcz;
+      const double y_min = -(1.0 - pcy) / pcz, y_max = pcy / pcz;
+      xs = (x_max - x_min) / (double)p.ncols;
+      ys = (y_max - y_min) / (double)p.nrows;
+      gx0 = x_min; gy0 = y_max; xh = xs / 2.0; yh = ys / 2.0;
+    }
     for (int64_t j = threadIdx.x; j < p.S; j += kProjThreads) {
-      const double val = project_pixel<MT>(p, m, __ldg(p.dc + 3 * j), __ldg(p.dc + 3 * j + 1), __ldg(p.dc + 3 * j + 2));
+      double vx, vy, vz;
+      if (p.pcs) {
+        const int64_t r = j / p.ncols, c = j - r * p.ncols;
+        const double gx = (gx0 + (double)c * xs + xh) * pcz;
+        const double gy = (gy0 + (double)r * (-ys) - yh) * pcz;
+        vx = gx * p.om[0] + gy * p.om[1] + pcz * p.om[2];
+        vy = gx * p.om[3] + gy * p.om[4] + pcz * p.om[5];
+        vz = gx * p.om[6] + gy * p.om[7] + pcz * p.om[8];
+        const double inv = 1.0 / sqrt(vx * vx + vy * vy + vz * vz);
+        vx *= inv; vy *= inv; vz *= inv;
+      } else {
+        vx = __ldg(p.dc + 3 * j); vy = __ldg(p.dc + 3 * j + 1); vz = __ldg(p.dc + 3 * j + 2);
+      }
+      const double val = project_pixel<MT>(p, m, vx, vy, vz);
       if (p.rescale) {
         vd[j] = val;
         lo = fmin(lo, val);
@@ -184,11 +214,21 @@ int64_t kdi_master_pattern_pixels(const kdi_master_pattern* mp) { return mp->S; 
 
 int kdi_launch_project(kdi_ctx* ctx, cudaStream_t stream, const kdi_master_pattern* mp, const double* d_rot,
                        int64_t n, float* d_out, kdi_patterns* dst, int64_t row_offset, int max_ctas) {
+  return kdi_launch_project_pcs(ctx, stream, mp, d_rot, n, d_out, dst, row_offset, max_ctas, nullptr, 0, 0, nullptr);
+}
+
+int kdi_launch_project_pcs(kdi_ctx* ctx, cudaStream_t stream, const kdi_master_pattern* mp, const double* d_rot,
+                           int64_t n, float* d_out, kdi_patterns* dst, int64_t row_offset, int max_ctas,
+                           const double* d_pcs, int nrows, int ncols, const double* om) {
   if (n <= 0) return KDI_OK;
   if (n > 0x7fffffffLL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "too many rotations in one call");
   ProjParams p = {};
   p.rot = d_rot;
   p.dc = mp->dc;
+  p.pcs = d_pcs;
+  p.nrows = nrows;
+  p.ncols = ncols;
+  if (d_pcs) for (int i = 0; i < 9; ++i) p.om[i] = om[i];
   p.upper = mp->upper;
   p.lower = mp->lower;
   // EBSDMasterPattern.get_patterns passes npx, npy = axes_manager.signal_shape = (columns, rows)
@@ -348,6 +388,36 @@ int kdi_project_patterns(kdi_ctx* ctx, const kdi_master_pattern* mp, const doubl
   kdi_dev_free(ctx, owned.p, owned.bytes);
   if (rc == KDI_OK && e != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "projection failed: %s", cudaGetErrorString(e));
   return rc;
+}
+
+int kdi_project_patterns_varying_pc(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations,
+                                    int64_t n, const double* pcs, int nrows, int ncols,
+                                    const double* om_detector_to_sample, float* out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!mp || !rotations || !pcs || !om_detector_to_sample || !out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_project_patterns_varying_pc: NULL argument");
+  if (n < 0 || nrows < 1 || ncols < 1 || (int64_t)nrows * ncols != mp->S)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_project_patterns_varying_pc: detector shape does not match the master pattern handle");
+  if (n == 0) return KDI_OK;
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  // bounded staging: ~256 MB of patterns at a time; rotations and PCs of the batch beside them
+  int64_t batch = std::max<int64_t>(1, (256ll << 20) / (mp->S * 4));
+  batch = std::min<int64_t>(batch, n);
+  const size_t o_rot = (((size_t)batch * mp->S * 4) + 255) & ~(size_t)255;
+  const size_t o_pc = (o_rot + (size_t)batch * 32 + 255) & ~(size_t)255;
+  KDI_TRY(kdi_ws2_reserve(ctx, o_pc + (size_t)batch * 24));
+  uint8_t* w = reinterpret_cast<uint8_t*>(ctx->ws2);
+  for (int64_t r0 = 0; r0 < n; r0 += batch) {
+    const int64_t nb = std::min<int64_t>(batch, n - r0);
+    KDI_CUDA(ctx, cudaMemcpyAsync(w + o_rot, rotations + r0 * 4, (size_t)nb * 32, cudaMemcpyHostToDevice, ctx->stream));
+    KDI_CUDA(ctx, cudaMemcpyAsync(w + o_pc, pcs + r0 * 3, (size_t)nb * 24, cudaMemcpyHostToDevice, ctx->stream));
+    KDI_TRY(kdi_launch_project_pcs(ctx, ctx->stream, mp, reinterpret_cast<const double*>(w + o_rot), nb,
+                                   reinterpret_cast<float*>(w), nullptr, 0, 0, reinterpret_cast<const double*>(w + o_pc),
+                                   nrows, ncols, om_detector_to_sample));
+    KDI_CUDA(ctx, cudaMemcpyAsync(out + r0 * mp->S, w, (size_t)nb * mp->S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return KDI_OK;
 }
 
 int kdi_patterns_create_projected(kdi_ctx* ctx, const kdi_master_pattern* mp, const double* rotations,

@@ -52,9 +52,10 @@ def direction_cosines(gnomonic_bounds, pcz, nrows, ncols, om_detector_to_sample,
 
 def _detector_direction_cosines(detector):
     """Direction cosines of a kikuchipy ``EBSDDetector`` (duck-typed) with one PC."""
-    if tuple(detector.navigation_shape) != (1,):
-        raise NotImplementedError("only detectors with one projection centre are supported")
-    om = (~detector.sample_to_detector).to_matrix().squeeze()
+    if int(np.prod(tuple(detector.navigation_shape))) != 1:
+        raise ValueError("`detector.navigation_shape` is not (1,) or equal to `rotations.shape`")
+    om = (detector.om_detector_to_sample if hasattr(detector, "om_detector_to_sample")
+          else (~detector.sample_to_detector).to_matrix().squeeze())
     return direction_cosines(np.asarray(detector.gnomonic_bounds).squeeze(), detector.pcz, detector.nrows,
                              detector.ncols, om), (int(detector.nrows), int(detector.ncols))
 
@@ -85,8 +86,31 @@ class GeneratedDictionary:
         return out if dtype is None else out.astype(dtype)
 
 
+def _varying_pc_geometry(detector, pcs, om_detector_to_sample, detector_shape, n_rot):
+    """``(pcs (n, 3), om (3, 3), (nrows, ncols))`` when one projection centre per rotation is
+    asked for (``detector.navigation_shape == rotations.shape``, signals/ebsd_master_pattern.py
+    :236-254), else ``None``."""
+    if pcs is None and detector is not None and hasattr(detector, "pc"):
+        pc = np.asarray(getattr(detector, "pc_flattened", detector.pc), dtype=np.float64).reshape(-1, 3)
+        if pc.shape[0] > 1:
+            pcs = pc
+            detector_shape = tuple(int(s) for s in detector.shape)
+            if om_detector_to_sample is None:
+                om_detector_to_sample = (detector.om_detector_to_sample if hasattr(detector, "om_detector_to_sample")
+                                         else (~detector.sample_to_detector).to_matrix().squeeze())
+    if pcs is None:
+        return None
+    pcs = np.asarray(pcs, dtype=np.float64).reshape(-1, 3)
+    if pcs.shape[0] != n_rot:
+        raise ValueError("`detector.navigation_shape` is not (1,) or equal to `rotations.shape`")
+    if om_detector_to_sample is None or detector_shape is None or len(detector_shape) != 2:
+        raise ValueError("projection centres per pattern need the detector shape and the detector-to-sample matrix")
+    return pcs, np.asarray(om_detector_to_sample, dtype=np.float64).reshape(3, 3), tuple(detector_shape)
+
+
 def get_patterns(master_upper, master_lower, rotations, detector=None, *, direction_cosines=None,
-                 detector_shape=None, dtype_out="float32", compute=False, context=None):
+                 detector_shape=None, dtype_out="float32", compute=False, context=None, pcs=None,
+                 om_detector_to_sample=None):
     """Patterns projected onto a detector from a square-Lambert master pattern for the given
     rotations - ``EBSDMasterPattern.get_patterns`` (signals/ebsd_master_pattern.py:97-329).
 
@@ -105,8 +129,20 @@ def get_patterns(master_upper, master_lower, rotations, detector=None, *, direct
     rot = np.asarray(getattr(rotations, "data", rotations), dtype=np.float64)
     if rot.ndim > 3 or rot.shape[-1] != 4:
         raise ValueError("`rotations` must be an array of quaternions with at most two navigation dimensions")
-    if rot.ndim == 3:
+    if rot.ndim == 3 and pcs is None and not (detector is not None and np.asarray(getattr(detector, "pc", [[0]])).reshape(-1, 3).shape[0] > 1):
         raise NotImplementedError("a dictionary has one navigation dimension; flatten the rotations first")
+    varying = _varying_pc_geometry(detector, pcs, om_detector_to_sample, detector_shape, rot.reshape(-1, 4).shape[0])
+    if varying is not None:
+        # one projection centre per rotation (_project_patterns_from_master_pattern_with_varying_pc):
+        # the patterns belong to map points, not to a dictionary, and are returned computed
+        pc, om, shape = varying
+        up = np.asarray(master_upper)
+        ctx = context if context is not None else _lib.default_context()
+        out_min, out_max = _DTYPE_RANGE[np.dtype(dtype_out)]
+        handle = ctx.master_pattern(up, np.asarray(master_lower), np.zeros((shape[0] * shape[1], 3)),
+                                    rescale=up.dtype != np.dtype(dtype_out), out_min=out_min, out_max=out_max)
+        out = ctx.project_patterns_varying_pc(handle, rot.reshape(-1, 4), pc, shape[0], shape[1], om)
+        return out.reshape((rot.reshape(-1, 4).shape[0],) + shape)
     if direction_cosines is None:
         if detector is None:
             raise ValueError("either a detector or direction cosines are needed")

@@ -65,6 +65,18 @@ class Detector:
         return self.pc.reshape(-1, 3)
 
     @property
+    def pcx(self):
+        return self.pc[..., 0]
+
+    @property
+    def pcy(self):
+        return self.pc[..., 1]
+
+    @property
+    def pcz(self):
+        return self.pc[..., 2]
+
+    @property
     def om_detector_to_sample(self):
         return sample_to_detector_matrix(self.sample_tilt, self.tilt, self.azimuthal, self.twist).T
 

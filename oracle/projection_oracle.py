@@ -175,3 +175,25 @@ def tilted_detector_matrix(tilt_deg: float = 70.0) -> np.ndarray:
     (the real one comes from ``EBSDDetector.sample_to_detector``, out of scope here)."""
     t = np.deg2rad(tilt_deg)
     return np.array([[1, 0, 0], [0, np.cos(t), -np.sin(t)], [0, np.sin(t), np.cos(t)]], dtype=np.float64)
+
+
+def gnomonic_bounds(nrows, ncols, pcx, pcy, pcz):
+    """``EBSDDetector.gnomonic_bounds`` / ``get_gnomonic_bounds`` (detectors/_ebsd_detector.py:731-818,
+    _utils/_gnonomic_bounds.py:23-62): ``(x_min, x_max, y_min, y_max)``."""
+    aspect = ncols / nrows
+    return np.array([-aspect * (pcx / pcz), aspect * (1 - pcx) / pcz, -(1 - pcy) / pcz, pcy / pcz])
+
+
+def project_patterns_varying_pc(rotations, pcs, nrows, ncols, om_detector_to_sample, master_upper, master_lower,
+                                rescale=False, out_min=1, out_max=2, dtype_out=np.float32):
+    """``_get_direction_cosines_for_varying_pc`` + ``_project_patterns_from_master_pattern_with_
+    varying_pc`` (_master_pattern.py:207-296, :374-445): rotation ``i`` seen from ``pcs[i]``."""
+    rotations = np.asarray(rotations, dtype=np.float64).reshape(-1, 4)
+    pcs = np.asarray(pcs, dtype=np.float64).reshape(-1, 3)
+    npy, npx = np.asarray(master_upper).shape
+    out = np.zeros((rotations.shape[0], nrows * ncols), dtype=dtype_out)
+    for i, (r, pc) in enumerate(zip(rotations, pcs)):
+        dc = direction_cosines_fixed_pc(gnomonic_bounds(nrows, ncols, *pc), pc[2], nrows, ncols, om_detector_to_sample)
+        out[i] = project_single_pattern(r, dc, master_upper, master_lower, int(npx), int(npy), (npx - 1) / 2, rescale,
+                                        out_min, out_max, dtype_out)
+    return out

@@ -150,3 +150,32 @@ def test_generated_dictionary_overlapped_schedule_and_errors(ctx):
     with pytest.raises(ValueError, match="either a detector or direction cosines"):
         kb.get_patterns(mu, ml, rot)
     mp.close()
+
+
+def test_projection_with_one_pc_per_rotation(ctx, golden):
+    """_project_patterns_from_master_pattern_with_varying_pc: direction cosines computed on the
+    device from each rotation's own projection centre, against the reference's golden outputs."""
+    z = golden("projection_varying_pc.npz")
+    nrows, ncols = int(z["nrows"]), int(z["ncols"])
+    mu32, ml32 = po.synthetic_master_pattern(101, seed=5, dtype=np.float32)
+    mu8, ml8 = po.synthetic_master_pattern(101, seed=6, dtype=np.uint8)
+    got = kb.get_patterns(mu32, ml32, z["rotations"], pcs=z["pcs"], om_detector_to_sample=z["om"], detector_shape=(nrows, ncols))
+    assert got.shape == (7, nrows, ncols)
+    _close(got.reshape(7, -1), z["out_f32"])
+    got8 = kb.get_patterns(mu8, ml8, z["rotations"], pcs=z["pcs"], om_detector_to_sample=z["om"], detector_shape=(nrows, ncols))
+    _close(got8.reshape(7, -1), z["out_u8"])
+    # a detector object with one PC per rotation takes the same path; a mismatch is refused
+    det = kb.Detector((nrows, ncols), pc=z["pcs"])
+    det_om = z["om"]
+
+    class Det:
+        shape, pc, om_detector_to_sample = det.shape, det.pc, det_om
+
+    assert np.array_equal(kb.get_patterns(mu32, ml32, z["rotations"], Det), got)
+    with pytest.raises(ValueError, match="navigation_shape"):
+        kb.get_patterns(mu32, ml32, z["rotations"][:3], Det)
+    # many rotations: batches, every pattern equal to its single-PC projection
+    rot = po.random_rotations(300, seed=3)
+    pcs = np.array([0.5, 0.3, 0.6]) + np.random.default_rng(1).normal(scale=0.03, size=(300, 3))
+    many = kb.get_patterns(mu32, ml32, rot, pcs=pcs, om_detector_to_sample=z["om"], detector_shape=(nrows, ncols))
+    _close(many.reshape(300, -1), po.project_patterns_varying_pc(rot, pcs, nrows, ncols, z["om"], mu32, ml32))

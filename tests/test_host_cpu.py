@@ -233,10 +233,13 @@ def test_get_patterns_argument_checks_without_gpu():
     with pytest.raises(ValueError, match="detector shape"):
         kb.get_patterns(mp, mp, rot, direction_cosines=np.ones((4, 3)), detector_shape=(3, 3))
 
-    class _Det:  # an EBSDDetector with several projection centres is not supported
+    class _Det:  # several projection centres: their number must equal the number of rotations
         navigation_shape = (2, 2)
+        shape = (2, 2)
+        pc = np.full((2, 2, 3), 0.5)
+        om_detector_to_sample = np.eye(3)
 
-    with pytest.raises(NotImplementedError, match="one projection centre"):
+    with pytest.raises(ValueError, match="is not \\(1,\\) or equal to `rotations.shape`"):
         kb.get_patterns(mp, mp, rot, _Det())
 
 
