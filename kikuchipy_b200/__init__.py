@@ -15,6 +15,7 @@ from .similarity_metrics import (
     SimilarityMetric,
 )
 from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
+from .io_nordif import NordifScan, load_nordif
 from .master_pattern import GeneratedDictionary, direction_cosines, get_patterns
 from .merge_maps import MergedCrystalMap, merge_crystal_maps
 from .preprocessing import (
@@ -38,6 +39,7 @@ __all__ = [
     "GeneratedDictionary",
     "KdiError",
     "MergedCrystalMap",
+    "NordifScan",
     "NormalizedCrossCorrelationMetric",
     "NormalizedDotProductMetric",
     "RefinementResult",
@@ -49,6 +51,7 @@ __all__ = [
     "dictionary_indexing_sharded",
     "direction_cosines",
     "get_patterns",
+    "load_nordif",
     "gather_topk",
     "merge_crystal_maps",
     "orientation_similarity_map",

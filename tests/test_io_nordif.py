@@ -1,0 +1,94 @@
+"""NORDIF reader (kikuchipy_b200/io_nordif.py) against a NORDIF directory written by the test and,
+when the reference tree is mounted (build container), against its sample data set
+(/root/reference/src/kikuchipy/data/nordif: the nine nickel patterns)."""
+
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import kikuchipy_b200 as kb
+from kikuchipy_b200 import io_nordif
+from oracle import ref_loader
+
+SETTING = "\r\n".join([
+    "[NORDIF]\t\t", "Software version\t3.1.2\t", "\t\t", "[Microscope]\t\t", "Manufacturer\tHitachi\t", "Model\tSU-6600\t",
+    "Magnification\t200\t#", "Scan direction\tDirect\t", "Accelerating voltage\t20\tkV", "Working distance\t24.7\tmm",
+    "Tilt angle\t70\t\xb0", "\t\t", "[Detector angles]\t\t", "Euler 1\t0\t\xb0", "Euler 2\t0\t\xb0", "Euler 3\t0\t\xb0",
+    "Azimuthal\t2\t\xb0", "Elevation\t-3.5\t\xb0", "\t\t", "[Acquisition settings]\t\t", "Frame rate\t202\tfps",
+    "Resolution\t6x4\tpx", "\t\t", "[Area]\t\t", "Top\t89.200 (223)\t\xb5m (px)", "Left\t60.384 (152)\t\xb5m (px)",
+    "Width\t4.500 (11)\t\xb5m (px)", "Height\t4.500 (11)\t\xb5m (px)", "Step size\t1.500\t\xb5m", "Number of samples\t2x3\t#", ""])
+
+
+def _write_bmp(path, img):
+    h, w = img.shape
+    stride = (w + 3) & ~3
+    rows = np.zeros((h, stride), np.uint8)
+    rows[:, :w] = img[::-1]
+    palette = np.repeat(np.arange(256, dtype=np.uint8)[:, None], 4, axis=1)
+    palette[:, 3] = 0
+    with open(path, "wb") as f:
+        f.write(b"BM" + struct.pack("<IHHI", 54 + 1024 + rows.size, 0, 0, 54 + 1024))
+        f.write(struct.pack("<IiiHHIIiiII", 40, w, h, 1, 8, 0, rows.size, 2835, 2835, 256, 0))
+        f.write(palette.tobytes() + rows.tobytes())
+
+
+def test_load_nordif_directory(tmp_path):
+    rng = np.random.default_rng(0)
+    pats = rng.integers(0, 256, (2, 3, 4, 6), dtype=np.uint8)  # ny = 2, nx = 3, sy = 4, sx = 6
+    bg = rng.integers(0, 256, (4, 6), dtype=np.uint8)
+    pats.tofile(tmp_path / "Pattern.dat")
+    (tmp_path / "Setting.txt").write_text(SETTING, encoding="latin-1")
+    _write_bmp(tmp_path / "Background acquisition pattern.bmp", bg)
+    scan = kb.load_nordif(str(tmp_path / "Pattern.dat"))
+    assert np.array_equal(scan.data, pats) and np.array_equal(scan.static_background, bg)
+    assert scan.step_sizes == (1.5, 1.5) and scan.detector.shape == (4, 6)
+    assert (scan.detector.sample_tilt, scan.detector.tilt, scan.detector.azimuthal) == (70.0, 3.5, 2.0)
+    sem = scan.metadata["Acquisition_instrument"]["SEM"]
+    assert sem == {"beam_energy": 20.0, "magnification": 200, "microscope": "Hitachi SU-6600", "working_distance": 24.7}
+    # explicit sizes, a line scan, a short file (zero padded with a warning), no setting file
+    line = kb.load_nordif(str(tmp_path / "Pattern.dat"), scan_size=6, pattern_size=(6, 4))
+    assert line.data.shape == (6, 4, 6) and np.array_equal(line.data, pats.reshape(6, 4, 6))
+    with pytest.warns(UserWarning, match="zero padding"):
+        big = kb.load_nordif(str(tmp_path / "Pattern.dat"), scan_size=(3, 3), pattern_size=(6, 4))
+    assert big.data.shape == (3, 3, 4, 6) and not big.data[2].any()
+    os.remove(tmp_path / "Setting.txt")
+    os.remove(tmp_path / "Background acquisition pattern.bmp")
+    with pytest.raises(ValueError, match="No setting file found"):
+        kb.load_nordif(str(tmp_path / "Pattern.dat"))
+    with pytest.warns(UserWarning):
+        bare = kb.load_nordif(str(tmp_path / "Pattern.dat"), scan_size=(3, 2), pattern_size=(6, 4))
+    assert bare.static_background is None and bare.detector is None and np.array_equal(bare.data, pats)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_load_reference_sample():
+    folder = os.path.join(ref_loader.REFERENCE_ROOT, "src", "kikuchipy", "data", "nordif")
+    scan = kb.load_nordif(os.path.join(folder, "Pattern.dat"))
+    assert np.array_equal(scan.data, ref_loader.nickel_ebsd_small())
+    assert scan.static_background.shape == (60, 60) and scan.static_background.dtype == np.uint8
+    assert 50 < scan.static_background.mean() < 200 and scan.step_sizes == (1.5, 1.5)
+    assert (scan.detector.sample_tilt, scan.detector.tilt, scan.detector.azimuthal) == (70.0, 0.0, 0.0)
+    md, header, sizes, det = io_nordif.read_settings(os.path.join(folder, "Setting.txt"))
+    assert sizes == {"ny": 3, "nx": 3, "sy": 60, "sx": 60, "step_y": 1.5, "step_x": 1.5}
+
+
+@pytest.mark.gpu
+def test_load_to_device_and_index(tmp_path):
+    """File -> pinned upload -> preprocessing -> indexing without the patterns returning to the host."""
+    from oracle import di_oracle as orc
+    from oracle import preprocess_oracle as pp
+
+    pats = orc.synthetic_experimental(12, (60, 60), seed=1).reshape(3, 4, 60, 60)
+    pats.tofile(tmp_path / "Pattern.dat")
+    with pytest.warns(UserWarning):
+        scan = kb.load_nordif(str(tmp_path / "Pattern.dat"), scan_size=(4, 3), pattern_size=(60, 60), device=True)
+    assert scan.data.is_cuda and tuple(scan.data.shape) == (3, 4, 60, 60)
+    clean = kb.remove_dynamic_background(scan.data, "subtract", "spatial")
+    assert clean.is_cuda and np.array_equal(clean.cpu().numpy(), pp.remove_dynamic_background(pats, "subtract", "spatial"))
+    dic = orc.synthetic_dictionary(400, (60, 60), seed=2)
+    res = kb.dictionary_indexing(clean, dic, keep_n=5, verbose=False)
+    ridx, rsc = orc.dictionary_indexing(clean.cpu().numpy(), dic, keep_n=5)
+    c = orc.compare_topk(ridx, rsc, res.simulation_indices, res.scores)
+    assert c["tie_ok"] and c["scores_ok"], c

@@ -1,0 +1,40 @@
+"""Turn an `ncu --set full` report into the short summary kept under profiles/ (one metric per
+line: name, unit, value of the first captured launch).
+
+  python tools/ncu_summary.py gpurun_out/prof_<kernel>.ncu-rep profiles/r1_<kernel>_ncu_summary.csv
+"""
+import csv
+import subprocess
+import sys
+
+KEEP = [
+    "Kernel Name", "gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
+    "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg",
+    "smsp__average_warp_latency_per_inst_issued.ratio",
+]
+
+
+def main(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], check=True, capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    col = {h: i for i, h in enumerate(hdr)}
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f, quoting=csv.QUOTE_ALL)
+        f.write("metric,unit,value\n")
+        for k in KEEP:
+            if k in col:
+                w.writerow([k, units[col[k]], vals[col[k]]])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])
