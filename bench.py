@@ -417,6 +417,25 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def cpu_preprocess_sample(pats, bg):
+    """patterns/s of the oracle port (SciPy / NumPy, one core) for static + dynamic background removal."""
+    from oracle import preprocess_oracle as pp  # checker / CPU baseline only
+
+    t0 = time.perf_counter()
+    pp.remove_dynamic_background(pp.remove_static_background(pats, bg))
+    return round(len(pats) / (time.perf_counter() - t0), 1)
+
+
+def cpu_refine_sample(mu, ml, dc, pats, x0):
+    """patterns/s of the oracle port (NumPy + the restated Nelder-Mead, one core) for orientation refinement."""
+    from oracle import refinement_oracle as ro  # checker / CPU baseline only
+
+    prob = ro.Problem(mu, ml, SIG[0], SIG[1], direction_cosines=dc)
+    t0 = time.perf_counter()
+    ro.refine_orientation(prob, pats.reshape(len(pats), -1), x0, False)
+    return round(len(pats) / (time.perf_counter() - t0), 2)
+
+
 def neighbouring_rows(ctx):
     """Device timings (CUDA events inside the library) of the rows either side of the path
     (SURVEY.md section 8f): preprocessing of the measured patterns and orientation refinement of
@@ -436,7 +455,8 @@ def neighbouring_rows(ctx):
         kb.preprocess(dev, static_bg=bg)
     ms = ctx.timings()["total_ms"]
     out["preprocess_static+dynamic"] = {"patterns": M_PER_GPU, "kernel_ms": round(ms, 3),
-                                        "patterns_per_s": round(M_PER_GPU / ms * 1e3)}
+                                        "patterns_per_s": round(M_PER_GPU / ms * 1e3),
+                                        "cpu_port_patterns_per_s_1core": cpu_preprocess_sample(pats[:200], bg)}
     n_ref, mp_n = 4096, 501
     mu, ml = syn.synthetic_master_pattern(mp_n, seed=5)
     dc = kb.direction_cosines([-0.9, 0.85, -0.7, 0.95], 0.5, SIG[0], SIG[1], syn.tilted_detector_matrix(70.0))
@@ -451,6 +471,7 @@ def neighbouring_rows(ctx):
         res = ctx.refine(mp, _lib.REFINE_ORI, pats8, SIG[0], SIG[1], False, x0)
     ms = ctx.timings()["total_ms"]
     out["refine_orientation"] = {"patterns": n_ref, "kernel_ms": round(ms, 3), "patterns_per_s": round(n_ref / ms * 1e3),
+                                 "cpu_port_patterns_per_s_1core": cpu_refine_sample(mu, ml, dc, pats8[:8], x0[:8]),
                                  "mean_evaluations": round(float(res[:, 1].mean()), 1),
                                  "mean_score": round(float(res[:, 0].mean()), 5),
                                  "median_misorientation_to_truth_deg": round(float(np.degrees(np.median(
