@@ -104,6 +104,12 @@ def _unwrap(signal):
             pass
         return signal.data, nav_shape, sig_shape, steps, unit, getattr(signal, "xmap", None)
     data = signal
+    if hasattr(signal, "step_sizes") and hasattr(signal, "data") and not hasattr(signal, "ndim"):
+        # a scan container of this package's readers (io_nordif.NordifScan): patterns + step sizes in um
+        data = signal.data
+        if len(data.shape) < 2:
+            raise ValueError("pattern arrays need at least the two detector axes")
+        return data, tuple(data.shape[:-2]), tuple(data.shape[-2:]), tuple(signal.step_sizes), "um", None
     if isinstance(data, GeneratedDictionary):
         return data, (data.shape[0],), data.sig_shape if len(data.sig_shape) == 2 else (1,) + data.sig_shape, None, "px", None
     if len(data.shape) < 2:

@@ -103,6 +103,13 @@ def _prop(xmap, name):
 
 
 def _rotation_data(xmap):
+    if getattr(xmap, "rotations", None) is None:
+        # an indexing result of a dictionary given without rotations: identity rotations, so that
+        # scores and simulation indices can still be merged
+        shape = _prop(xmap, next(iter(xmap.prop))).shape
+        r = np.zeros(tuple(shape) + (4,))
+        r[..., 0] = 1.0
+        return r
     r = xmap.rotations
     r = np.asarray(r.data if hasattr(r, "data") and not isinstance(r, np.ndarray) else r, dtype=np.float64)
     iid = _is_in_data(xmap)

@@ -175,6 +175,8 @@ def _detector_geometry(detector):
 def _xmap_rotations(xmap, points_in_data):
     """Quaternions ``(n, 4)`` of the best match of the points to refine (``_refinement.py:966-970``)."""
     r = xmap.rotations if hasattr(xmap, "rotations") else xmap
+    if r is None:
+        raise ValueError("The crystal map has no rotations to refine (index against a dictionary with rotations)")
     r = np.asarray(r.data if hasattr(r, "data") and not isinstance(r, np.ndarray) else r, dtype=np.float64)
     if r.ndim == 3:
         r = r[:, 0]

@@ -261,3 +261,21 @@ def test_bench_cpu_arm_runs_small(monkeypatch):
     exp, dic = bench.host_inputs(8)
     v, detail = bench.cpu_sample(exp, dic, 100)
     assert v > 0 and detail["sample_patterns"] == 8 and detail["dictionary"] == 3000
+
+
+def test_inputs_of_neighbouring_rows_without_gpu():
+    """Host-side input handling that needs no device: a NORDIF scan container is unwrapped like a
+    signal; refinement refuses a map without rotations; merge_crystal_maps substitutes identity
+    rotations for indexing results that carry none."""
+    from kikuchipy_b200 import indexing, merge_maps
+    from kikuchipy_b200.io_nordif import NordifScan
+
+    scan = NordifScan(np.zeros((3, 4, 6, 5), np.uint8), None, None, (1.5, 1.5), {}, {})
+    data, nav, sig, steps, unit, xmap = indexing._unwrap(scan)
+    assert data is scan.data and nav == (3, 4) and sig == (6, 5) and steps == (1.5, 1.5) and unit == "um" and xmap is None
+    res = kb.DictionaryIndexingResult(np.ones((12, 2), np.float32), np.zeros((12, 2), np.int64), None, (3, 4), None,
+                                      np.ones(12, bool), 2, "ni")
+    with pytest.raises(ValueError, match="no rotations to refine"):
+        kb.refine_orientation(scan.data, res, kb.Detector((6, 5)), (np.zeros((5, 5), np.float32),) * 2)
+    r = merge_maps._rotation_data(res)
+    assert r.shape == (12, 2, 4) and np.all(r[..., 0] == 1) and not r[..., 1:].any()
