@@ -400,3 +400,45 @@ def test_sharded_refinement_gloo(tmp_path, world):
         assert list(z["rows"]) == [b - a]
         done += b - a
     assert done == 7
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_oracle_nelder_mead_equals_scipy_random_problems(seed):
+    """Random smooth objectives in 3 and 6 variables, random starts (some components exactly 0, some
+    on a bound), random bounds and limits: the restatement follows SciPy step for step."""
+    import warnings
+
+    import scipy.optimize as so
+
+    rng = np.random.default_rng(100 + seed)
+    n = 3 if seed % 2 == 0 else 6
+    a = rng.normal(size=(n, n))
+    q = a @ a.T + 0.5 * np.eye(n)
+    c = rng.normal(size=n)
+    w = rng.uniform(0.0, 0.3)
+
+    def f(x):
+        d = x - c
+        return float(d @ q @ d + w * np.sum(np.sin(5 * x)))
+
+    x0 = c + rng.normal(scale=0.5, size=n)
+    if seed % 3 == 0:
+        x0[rng.integers(n)] = 0.0
+    bounds = None
+    if seed % 4 in (1, 2):
+        lo = c - rng.uniform(0.05, 1.0, n)
+        hi = c + rng.uniform(0.05, 1.0, n)
+        if seed % 4 == 2:
+            x0[0] = hi[0]  # start on a bound: the initial simplex is reflected into the interior
+        bounds = np.stack([lo, hi], axis=1)
+    opts = {}
+    if seed % 5 == 0:
+        opts["maxfev"] = int(rng.integers(5, 60))
+    if seed % 7 == 0:
+        opts["adaptive"] = True
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = so.minimize(f, x0, method="Nelder-Mead", bounds=None if bounds is None else list(map(tuple, bounds)), options=dict(opts))
+    x, fv, nfev, nit = ro.nelder_mead(f, x0, bounds=bounds, **opts)
+    assert (nfev, nit) == (ref.nfev, ref.nit)
+    assert np.array_equal(x, ref.x) and fv == ref.fun
