@@ -15,6 +15,7 @@ from .similarity_metrics import (
     SimilarityMetric,
 )
 from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
+from .io_edax import load_edax_binary
 from .io_nordif import NordifScan, load_nordif
 from .master_pattern import GeneratedDictionary, direction_cosines, get_patterns
 from .merge_maps import MergedCrystalMap, merge_crystal_maps
@@ -51,6 +52,7 @@ __all__ = [
     "dictionary_indexing_sharded",
     "direction_cosines",
     "get_patterns",
+    "load_edax_binary",
     "load_nordif",
     "gather_topk",
     "merge_crystal_maps",

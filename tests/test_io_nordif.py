@@ -92,3 +92,54 @@ def test_load_to_device_and_index(tmp_path):
     ridx, rsc = orc.dictionary_indexing(clean.cpu().numpy(), dic, keep_n=5)
     c = orc.compare_topk(ridx, rsc, res.simulation_indices, res.scores)
     assert c["tie_ok"] and c["scores_ok"], c
+
+
+def _write_edax(path, version, pats, nav=None, is_hex=False, steps=(0.5, 0.25), extra=0):
+    sy, sx = pats.shape[-2:]
+    with open(path, "wb") as f:
+        np.array([version], "uint32").tofile(f)
+        if version == 1:
+            np.array([sx, sy, 16], "uint32").tofile(f)
+        else:
+            np.array([sx, sy, 42], "uint32").tofile(f)
+            np.array([1], "uint8").tofile(f)
+            np.array([nav[1], nav[0]], "uint32").tofile(f)
+            np.array([int(is_hex)], "uint8").tofile(f)
+            np.array(steps, "float64").tofile(f)
+        pats.ravel().tofile(f)
+        if extra:
+            np.zeros(extra * sy * sx, pats.dtype).tofile(f)
+
+
+def test_load_edax_binary(tmp_path):
+    rng = np.random.default_rng(1)
+    p8 = rng.integers(0, 256, (6, 5, 7), dtype=np.uint8)
+    p16 = rng.integers(0, 65536, (2, 3, 5, 7)).astype(np.uint16)
+    _write_edax(tmp_path / "a.up1", 1, p8)
+    a = kb.load_edax_binary(str(tmp_path / "a.up1"))
+    assert a.data.dtype == np.uint8 and np.array_equal(a.data, p8) and a.step_sizes == (1, 1)
+    assert np.array_equal(kb.load_edax_binary(str(tmp_path / "a.up1"), nav_shape=(2, 3)).data, p8.reshape(2, 3, 5, 7))
+    with pytest.raises(ValueError, match="does not match the number of patterns"):
+        kb.load_edax_binary(str(tmp_path / "a.up1"), nav_shape=(2, 2))
+    _write_edax(tmp_path / "b.up2", 3, p16, nav=(2, 3))
+    b = kb.load_edax_binary(str(tmp_path / "b.up2"))
+    assert b.data.dtype == np.uint16 and np.array_equal(b.data, p16) and b.step_sizes == (0.25, 0.5)
+    _write_edax(tmp_path / "c.up2", 3, p16, nav=(2, 3), is_hex=True, extra=1)
+    with pytest.warns(UserWarning, match="hexagonal grid"):
+        c = kb.load_edax_binary(str(tmp_path / "c.up2"))
+    assert c.data.shape == (7, 5, 7) and np.array_equal(c.data[:6], p16.reshape(6, 5, 7)) and not c.data[6].any()
+    _write_edax(tmp_path / "d.up1", 2, p8, nav=(1, 6))
+    with pytest.raises(ValueError, match="not 2, can be read"):
+        kb.load_edax_binary(str(tmp_path / "d.up1"))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_load_reference_edax_samples():
+    folder = os.path.join(ref_loader.REFERENCE_ROOT, "src", "kikuchipy", "data", "edax_binary")
+    ni = ref_loader.nickel_ebsd_small().reshape(9, 60, 60)
+    up1 = kb.load_edax_binary(os.path.join(folder, "edax_binary.up1"))
+    assert np.array_equal(up1.data, ni)
+    with pytest.warns(UserWarning, match="hexagonal grid"):
+        up2 = kb.load_edax_binary(os.path.join(folder, "edax_binary.up2"))
+    assert up2.data.dtype == np.uint16 and up2.data.shape == (10, 60, 60) and np.array_equal(up2.data[:9], ni)
+    assert np.allclose(up2.step_sizes, (np.pi / 2, np.pi))
