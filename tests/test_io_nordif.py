@@ -143,3 +143,17 @@ def test_load_reference_edax_samples():
         up2 = kb.load_edax_binary(os.path.join(folder, "edax_binary.up2"))
     assert up2.data.dtype == np.uint16 and up2.data.shape == (10, 60, 60) and np.array_equal(up2.data[:9], ni)
     assert np.allclose(up2.step_sizes, (np.pi / 2, np.pi))
+
+
+@pytest.mark.gpu
+def test_load_edax_to_device(tmp_path):
+    rng = np.random.default_rng(2)
+    p16 = rng.integers(0, 65536, (2, 3, 20, 24)).astype(np.uint16)
+    _write_edax(tmp_path / "b.up2", 3, p16, nav=(2, 3))
+    scan = kb.load_edax_binary(str(tmp_path / "b.up2"), device=True)
+    assert scan.data.is_cuda and tuple(scan.data.shape) == (2, 3, 20, 24)
+    assert np.array_equal(scan.data.cpu().numpy(), p16)
+    from oracle import preprocess_oracle as pp
+
+    out = kb.remove_dynamic_background(scan.data, "subtract", "spatial", std=2.5)
+    assert np.array_equal(out.cpu().numpy(), pp.remove_dynamic_background(p16, "subtract", "spatial", 2.5))
