@@ -17,6 +17,7 @@ from .similarity_metrics import (
 from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
 from .io_edax import load_edax_binary
 from .io_nordif import NordifScan, load_nordif
+from .io_oxford import load_oxford_binary
 from .master_pattern import GeneratedDictionary, direction_cosines, get_patterns
 from .merge_maps import MergedCrystalMap, merge_crystal_maps
 from .preprocessing import (
@@ -54,6 +55,7 @@ __all__ = [
     "get_patterns",
     "load_edax_binary",
     "load_nordif",
+    "load_oxford_binary",
     "gather_topk",
     "merge_crystal_maps",
     "orientation_similarity_map",

@@ -157,3 +157,80 @@ def test_load_edax_to_device(tmp_path):
 
     out = kb.remove_dynamic_background(scan.data, "subtract", "spatial", std=2.5)
     assert np.array_equal(out.cpu().numpy(), pp.remove_dynamic_background(p16, "subtract", "spatial", 2.5))
+
+
+def _write_oxford(path, pats, version, compressed=False, all_present=True, shuffle=True):
+    """An .ebsp file like the reference's test fixture writes (/root/reference/conftest.py,
+    ``oxford_binary_file``): pattern records stored in a rolled order, beam positions in um."""
+    nr, nc, sr, sc = pats.shape
+    n = nr * nc
+    item = pats.dtype.itemsize
+    header = 16 if version < 5 else 24
+    footer = {0: 0, 1: 16}.get(version, 18)
+    step = 1.0
+    with open(path, "wb") as f:
+        if version != 0:
+            np.array(-version, dtype="<i8").tofile(f)
+        start0 = (0 if version == 0 else 8) + (1 if version > 3 else 0)
+        if version > 3:
+            np.array(1, dtype="u1").tofile(f)
+        starts = np.arange(n, dtype="<i8") * (header + sr * sc * item + footer) + start0 + n * 8
+        order = np.arange(n)
+        if shuffle:
+            starts = np.roll(starts, 1)
+            order = np.roll(order, -1)
+        if not all_present:  # like the reference's fixture: the first listed point has no pattern
+            starts[0] = 0
+            order = order[1:]
+        starts.tofile(f)
+        for i in order:
+            r, c = np.unravel_index(i, (nr, nc))
+            if version >= 5:
+                np.array([c, r], dtype="<i4").tofile(f)
+            np.array([int(compressed), sr, sc, sr * sc * item], dtype="<i4").tofile(f)
+            pats[r, c].tofile(f)
+            if version == 1:
+                np.array([c * step, r * step], dtype="<f8").tofile(f)
+            elif version > 1:
+                np.array(1, dtype=bool).tofile(f)
+                np.array(c * step, dtype="<f8").tofile(f)
+                np.array(1, dtype=bool).tofile(f)
+                np.array(r * step, dtype="<f8").tofile(f)
+
+
+@pytest.mark.parametrize("version, dtype, nav", [(2, np.uint8, (2, 3)), (1, np.uint16, (2, 3)), (0, np.uint8, (6,)),
+                                                 (4, np.uint8, (2, 3)), (5, np.uint16, (2, 3)), (6, np.uint8, (2, 3))])
+def test_load_oxford_binary_versions(tmp_path, version, dtype, nav):
+    """tests/test_io/test_oxford_binary.py:59-101: versions 0, 1, > 1; uint8 and uint16."""
+    rng = np.random.default_rng(version)
+    pats = rng.integers(0, np.iinfo(dtype).max, (2, 3, 60, 60)).astype(dtype)
+    _write_oxford(tmp_path / "p.ebsp", pats, version, shuffle=version != 0)
+    scan = kb.load_oxford_binary(str(tmp_path / "p.ebsp"))
+    assert scan.version == version and scan.data.dtype == dtype and scan.data.shape == nav + (60, 60)
+    assert np.array_equal(scan.data.reshape(2, 3, 60, 60), pats)
+    if version > 0:
+        assert np.allclose(scan.original_metadata["beam_x"], [0, 1, 2, 0, 1, 2])
+        assert np.allclose(scan.original_metadata["beam_y"], [0, 0, 0, 1, 1, 1])
+    if version >= 5:
+        assert np.array_equal(scan.original_metadata["map_x"], [0, 1, 2, 0, 1, 2])
+
+
+def test_load_oxford_binary_missing_and_compressed(tmp_path):
+    """tests/test_io/test_oxford_binary.py:47-57, :72-83."""
+    pats = np.random.default_rng(0).integers(0, 256, (2, 3, 60, 60), dtype=np.uint8)
+    _write_oxford(tmp_path / "c.ebsp", pats, 2, compressed=True)
+    with pytest.raises(NotImplementedError, match="Cannot read compressed"):
+        kb.load_oxford_binary(str(tmp_path / "c.ebsp"))
+    _write_oxford(tmp_path / "m.ebsp", pats, 2, all_present=False)
+    scan = kb.load_oxford_binary(str(tmp_path / "m.ebsp"))
+    assert scan.data.shape == (5, 60, 60)  # one pattern is missing: a line of the present ones
+    assert np.allclose(scan.original_metadata["beam_y"], [0, 1, 1, 1, 0])
+    assert np.allclose(scan.original_metadata["beam_x"], [2, 0, 1, 2, 0])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_load_reference_oxford_sample():
+    path = os.path.join(ref_loader.REFERENCE_ROOT, "src", "kikuchipy", "data", "oxford_binary", "patterns.ebsp")
+    scan = kb.load_oxford_binary(path)
+    assert scan.version == 2 and scan.step_sizes == (1.5, 1.5)
+    assert np.array_equal(scan.data, ref_loader.nickel_ebsd_small())
