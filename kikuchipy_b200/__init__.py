@@ -16,7 +16,7 @@ from .similarity_metrics import (
 )
 from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
 from .io_edax import load_edax_binary
-from .io_nordif import NordifScan, load_nordif
+from .io_nordif import NordifScan, load, load_nordif
 from .io_oxford import load_oxford_binary
 from .master_pattern import GeneratedDictionary, direction_cosines, get_patterns
 from .merge_maps import MergedCrystalMap, merge_crystal_maps
@@ -53,6 +53,7 @@ __all__ = [
     "dictionary_indexing_sharded",
     "direction_cosines",
     "get_patterns",
+    "load",
     "load_edax_binary",
     "load_nordif",
     "load_oxford_binary",

@@ -169,3 +169,22 @@ def load_nordif(filename, scan_size=None, pattern_size=None, setting_file=None, 
         else:
             data = data.reshape(ny, nx, sy, sx).squeeze()
     return NordifScan(data, static_bg, detector, step, md, omd)
+
+
+def load(filename, device=False, context=None, **kwargs):
+    """Read a pattern file by its extension, like ``kikuchipy.load`` does for the binary formats
+    this package reads: ``.dat`` (NORDIF), ``.up1`` / ``.up2`` (EDAX), ``.ebsp`` (Oxford Instruments)."""
+    ext = os.path.splitext(filename)[1].lower()
+    if not os.path.isfile(filename):
+        raise IOError(f"No filename matches {filename!r}")
+    if ext == ".dat":
+        return load_nordif(filename, device=device, context=context, **kwargs)
+    if ext in (".up1", ".up2"):
+        from .io_edax import load_edax_binary
+
+        return load_edax_binary(filename, device=device, context=context, **kwargs)
+    if ext == ".ebsp":
+        from .io_oxford import load_oxford_binary
+
+        return load_oxford_binary(filename, device=device, context=context, **kwargs)
+    raise IOError(f"Could not read {filename!r}: only .dat, .up1, .up2 and .ebsp files are read (the HDF5 formats need h5py)")

@@ -234,3 +234,19 @@ def test_load_reference_oxford_sample():
     scan = kb.load_oxford_binary(path)
     assert scan.version == 2 and scan.step_sizes == (1.5, 1.5)
     assert np.array_equal(scan.data, ref_loader.nickel_ebsd_small())
+
+
+def test_load_dispatches_on_extension(tmp_path):
+    pats = np.random.default_rng(3).integers(0, 256, (2, 3, 60, 60), dtype=np.uint8)
+    _write_oxford(tmp_path / "p.ebsp", pats, 2)
+    _write_edax(tmp_path / "p.up1", 1, pats.reshape(6, 60, 60))
+    pats.tofile(tmp_path / "p.dat")
+    assert np.array_equal(kb.load(str(tmp_path / "p.ebsp")).data, pats)
+    assert np.array_equal(kb.load(str(tmp_path / "p.up1"), nav_shape=(2, 3)).data, pats)
+    with pytest.warns(UserWarning):
+        assert np.array_equal(kb.load(str(tmp_path / "p.dat"), scan_size=(3, 2), pattern_size=(60, 60)).data, pats)
+    with pytest.raises(IOError, match="No filename matches"):
+        kb.load(str(tmp_path / "missing.dat"))
+    (tmp_path / "p.h5").write_bytes(b"x")
+    with pytest.raises(IOError, match="need h5py"):
+        kb.load(str(tmp_path / "p.h5"))
