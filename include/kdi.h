@@ -8,6 +8,13 @@
  *   _dictionary_indexing / _match_chunk indexing/_dictionary_indexing.py:36-203
  *   SimilarityMetric (NCC / NDP)        indexing/similarity_metrics/ (all modules)
  *   orientation_similarity_map          indexing/_orientation_similarity_map.py:30-152
+ * and the rows either side of it:
+ *   EBSDMasterPattern.get_patterns      signals/ebsd_master_pattern.py:97-329 (dictionary generation)
+ *   merge_crystal_maps                  indexing/_merge_crystal_maps.py:28-354
+ *   EBSD.refine_orientation / _projection_center / _orientation_projection_center
+ *                                       signals/ebsd.py:1986-2560, indexing/_refinement/ (Nelder-Mead)
+ *   EBSD.remove_static_background / remove_dynamic_background / average_neighbour_patterns
+ *                                       signals/ebsd.py:442-697, :943-1112
  *
  * The reference is pure Python and has no FFI of its own; these are the entry
  * points a ctypes/cffi binding inside kikuchipy would call (INTEGRATION.md shows
