@@ -83,6 +83,23 @@ extern "C" {
 #define KDI_OPT_SPLIT_SELECT 10 /* 1 (default) = candidate selection in its own warp-per-row kernel, 0 = inside
                                    the rescoring kernel (one 128-thread CTA per row)                      */
 
+#define KDI_OPT_GEMM_SMS 11     /* SMs the tensor-core kernel may occupy (0 = all, default): the rest stay free
+                                   for the HBM-bound kernels queued beside it                              */
+#define KDI_OPT_DEP_FLAGS 12    /* 1 (default) = device-resident float32 / uint8 dictionaries are normalised beside
+                                   the tensor-core launches, which wait per 256-row tile on device-side
+                                   readiness counters; 0 = stream events only (first quarter, then the rest)  */
+#define KDI_OPT_MIN_GROUPS 13   /* at least this many row-block groups (= tensor-core launches) per job; 0 = one
+                                   per L2 super-block of experimental rows                                 */
+#define KDI_OPT_POST_PER_GROUP 14 /* 1 = selection + rescoring of a finished row-block group is queued on the
+                                   post-processing stream beside the next groups' launches; 0 (default) = all
+                                   rows after the last launch                                              */
+#define KDI_OPT_GEMM_SERIAL 15  /* 1 = every tensor-core launch on one stream (no tail filling by the next
+                                   launch; with KDI_OPT_GEMM_SMS the spare SMs then really stay free)       */
+#define KDI_OPT_SM_PARTITION 16 /* n > 0: split the device with CUDA green contexts into n SMs for the
+                                   post-processing stream and the rest for the tensor-core launches (n is
+                                   rounded up by the driver's granularity); 0 (default) = no partition.
+                                   KDI_EUNSUPPORTED when the driver cannot do it                           */
+
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;
 

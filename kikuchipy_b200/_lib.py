@@ -38,6 +38,12 @@ OPT_TILE_ROTATE = 7
 OPT_MAX_STAGES = 8
 OPT_OVERLAP = 9
 OPT_SPLIT_SELECT = 10
+OPT_GEMM_SMS = 11
+OPT_DEP_FLAGS = 12
+OPT_MIN_GROUPS = 13
+OPT_POST_PER_GROUP = 14
+OPT_GEMM_SERIAL = 15
+OPT_SM_PARTITION = 16
 
 REFINE_ORI, REFINE_PC, REFINE_ORI_PC = 0, 1, 2
 
@@ -368,6 +374,7 @@ class Context:
 
     def close(self):
         if self._h:
+            self.__dict__.pop("_pinned", None)  # kdi_destroy frees every pinned block still alive
             self._lib.kdi_destroy(self._h)
             self._h = None
 
@@ -412,15 +419,55 @@ class Context:
         return s.value or 0
 
     def pinned_empty(self, shape, dtype) -> np.ndarray:
-        """NumPy array backed by pinned host memory (freed with the context)."""
+        """NumPy array backed by pinned host memory.  Release it with :meth:`pinned_free` as soon as
+        it is no longer needed (page-locked memory is not swappable); whatever is still alive is
+        freed with the context (``kdi_destroy``)."""
         dtype = np.dtype(dtype)
         n = int(np.prod(shape)) * dtype.itemsize
         p = _vp()
         self._check(self._lib.kdi_host_alloc(self._h, n, C.byref(p)))
         buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        self.__dict__.setdefault("_pinned", []).append((p.value, buf))
+        self.__dict__.setdefault("_pinned", {})[p.value] = buf
         return arr
+
+    def pinned_free(self, arr: np.ndarray) -> None:
+        """Free the pinned block behind an array returned by :meth:`pinned_empty` (the array must
+        not be used afterwards)."""
+        addr = arr.__array_interface__["data"][0] if arr.size else None
+        pinned = self.__dict__.get("_pinned", {})
+        if addr is None or addr not in pinned:
+            raise ValueError("not the start of a block returned by pinned_empty() of this context")
+        del pinned[addr]
+        self._check(self._lib.kdi_host_free(self._h, addr))
+
+    def to_device(self, array: np.ndarray):
+        """Upload a host array to a CUDA tensor through a small reusable pinned ring (two 32 MB
+        blocks owned by the context) instead of one dataset-sized page-locked allocation: the host
+        copy into one block overlaps the DMA out of the other."""
+        import torch
+
+        a = np.ascontiguousarray(array)
+        dev = torch.device("cuda", self.device)
+        out = torch.empty(a.shape, dtype=torch.from_numpy(a.reshape(-1)[:0]).dtype, device=dev)
+        src = a.reshape(-1).view(np.uint8)
+        dst = out.reshape(-1).view(torch.uint8)
+        ring = self.__dict__.get("_ring")
+        if ring is None:
+            blk = 32 << 20
+            ring = self.__dict__["_ring"] = [(self.pinned_empty((blk,), np.uint8), torch.cuda.Event()) for _ in range(2)]
+        blk = ring[0][0].size
+        stream = torch.cuda.current_stream(dev)
+        for i, a0 in enumerate(range(0, src.size, blk)):
+            buf, ev = ring[i & 1]
+            if i >= 2:
+                ev.synchronize()  # the DMA that last read this block has finished
+            n = min(blk, src.size - a0)
+            buf[:n] = src[a0:a0 + n]
+            dst[a0:a0 + n].copy_(torch.from_numpy(buf[:n]), non_blocking=True)
+            ev.record(stream)
+        stream.synchronize()
+        return out
 
     # -- masks and pattern sets ---------------------------------------------------
     def set_signal_mask(self, mask):

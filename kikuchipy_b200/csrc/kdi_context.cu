@@ -31,6 +31,13 @@ int kdi_fail(kdi_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
+static void sync_ctx_streams(kdi_ctx* ctx) {
+  cudaStream_t all[] = {ctx->stream, ctx->copy_stream, ctx->gemm_stream2, ctx->aux_stream, ctx->post_stream,
+                        ctx->part_gemm[0], ctx->part_gemm[1]};
+  for (cudaStream_t s : all)
+    if (s) cudaStreamSynchronize(s);
+}
+
 static int reserve(kdi_ctx* ctx, void** p, size_t* have, size_t bytes) {
   if (bytes <= *have) return KDI_OK;
   if (*p) {
@@ -167,6 +174,89 @@ void kdi_timeline_print(kdi_ctx* ctx) {
   cudaGetLastError();
 }
 
+// ---- SM partition (CUDA green contexts) ----------------------------------------------------------
+// The post-processing kernels (selection, exact rescoring: HBM-bound gathers) of a finished row-block
+// group are meant to run WHILE the tensor-core kernel works on the next groups.  The tensor-core
+// kernel is persistent with one CTA per SM and ~225 KB of shared memory, so nothing else fits on its
+// SMs, and a queued launch of it grabs every SM that becomes free.  A green context pins a stream to
+// a subset of the SMs: the tensor-core launches get the large partition, the post stream the small one.
+namespace {
+template <typename F>
+bool driver_fn(const char* name, F* out) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  *out = reinterpret_cast<F>(fn);
+  return true;
+}
+}  // namespace
+
+static void kdi_drop_sm_partition(kdi_ctx* ctx) {
+  typedef CUresult (*DestroyFn)(CUgreenCtx);
+  DestroyFn destroy = nullptr;
+  driver_fn("cuGreenCtxDestroy", &destroy);
+  cudaStream_t* streams[3] = {&ctx->post_stream, &ctx->part_gemm[0], &ctx->part_gemm[1]};
+  for (auto sp : streams)
+    if (*sp) { cudaStreamSynchronize(*sp); cudaStreamDestroy(*sp); *sp = nullptr; }
+  for (auto& g : ctx->green)
+    if (g) { if (destroy) destroy(reinterpret_cast<CUgreenCtx>(g)); g = nullptr; }
+  ctx->sm_partition = 0;
+}
+
+int kdi_setup_sm_partition(kdi_ctx* ctx, int n_small) {
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  sync_ctx_streams(ctx);
+  kdi_drop_sm_partition(ctx);
+  if (n_small <= 0) return KDI_OK;
+  typedef CUresult (*GetDevFn)(CUdevice*, int);
+  typedef CUresult (*GetResFn)(CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*SplitFn)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*DescFn)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*CreateFn)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*StreamFn)(CUstream*, CUgreenCtx, unsigned int, int);
+  GetDevFn get_dev = nullptr; GetResFn get_res = nullptr; SplitFn split = nullptr; DescFn gen_desc = nullptr;
+  CreateFn create = nullptr; StreamFn stream_create = nullptr;
+  if (!driver_fn("cuDeviceGet", &get_dev) || !driver_fn("cuDeviceGetDevResource", &get_res) ||
+      !driver_fn("cuDevSmResourceSplitByCount", &split) || !driver_fn("cuDevResourceGenerateDesc", &gen_desc) ||
+      !driver_fn("cuGreenCtxCreate", &create) || !driver_fn("cuGreenCtxStreamCreate", &stream_create))
+    return kdi_fail(ctx, KDI_EUNSUPPORTED, "this driver has no green-context API");
+  CUdevice dev;
+  CUdevResource all, small_res, rest;
+  unsigned int n_groups = 1;
+  CUresult r = get_dev(&dev, ctx->device);
+  if (r == CUDA_SUCCESS) r = get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM);
+  if (r == CUDA_SUCCESS) r = split(&small_res, &n_groups, &all, &rest, 0, (unsigned int)n_small);
+  if (r != CUDA_SUCCESS || n_groups != 1 || rest.sm.smCount < 2)
+    return kdi_fail(ctx, KDI_EUNSUPPORTED, "cannot split %d SMs off the device (driver result %d)", n_small, (int)r);
+  CUdevResourceDesc d_small, d_rest;
+  CUgreenCtx g_small = nullptr, g_rest = nullptr;
+  r = gen_desc(&d_small, &small_res, 1);
+  if (r == CUDA_SUCCESS) r = gen_desc(&d_rest, &rest, 1);
+  if (r == CUDA_SUCCESS) r = create(&g_small, d_small, dev, CU_GREEN_CTX_DEFAULT_STREAM);
+  if (r == CUDA_SUCCESS) r = create(&g_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM);
+  ctx->green[0] = g_small;
+  ctx->green[1] = g_rest;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  CUstream s_post = nullptr, s_g0 = nullptr, s_g1 = nullptr;
+  if (r == CUDA_SUCCESS) r = stream_create(&s_post, g_small, CU_STREAM_NON_BLOCKING, prio_hi);
+  if (r == CUDA_SUCCESS) r = stream_create(&s_g0, g_rest, CU_STREAM_NON_BLOCKING, prio_hi);
+  if (r == CUDA_SUCCESS) r = stream_create(&s_g1, g_rest, CU_STREAM_NON_BLOCKING, prio_hi);
+  ctx->post_stream = reinterpret_cast<cudaStream_t>(s_post);
+  ctx->part_gemm[0] = reinterpret_cast<cudaStream_t>(s_g0);
+  ctx->part_gemm[1] = reinterpret_cast<cudaStream_t>(s_g1);
+  if (r != CUDA_SUCCESS) {
+    kdi_drop_sm_partition(ctx);
+    return kdi_fail(ctx, KDI_EUNSUPPORTED, "green-context setup failed (driver result %d)", (int)r);
+  }
+  ctx->sm_partition = (int)small_res.sm.smCount;
+  ctx->part_gemm_sms = (int)rest.sm.smCount;
+  return KDI_OK;
+}
+
 extern "C" {
 
 int kdi_version(void) { return KDI_VERSION; }
@@ -234,6 +324,10 @@ int kdi_destroy(kdi_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->gemm_stream2) cudaStreamSynchronize(ctx->gemm_stream2);
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+  kdi_drop_sm_partition(ctx);
+  if (ctx->h_nflag) cudaFreeHost(ctx->h_nflag);
+  for (void* q : ctx->pinned) cudaFreeHost(q);
+  ctx->pinned.clear();
   kdi_pool_trim(ctx, 0);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
@@ -300,6 +394,26 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
     case KDI_OPT_TILE_ROTATE:
       ctx->tile_rotate = value != 0;
       return KDI_OK;
+    case KDI_OPT_GEMM_SMS:
+      if (value < 0 || (value != 0 && value < 2)) return kdi_fail(ctx, KDI_EINVAL, "gemm_sms must be 0 or >= 2");
+      ctx->gemm_sms = (int)value;
+      return KDI_OK;
+    case KDI_OPT_DEP_FLAGS:
+      ctx->dep_flags = value != 0;
+      return KDI_OK;
+    case KDI_OPT_MIN_GROUPS:
+      if (value < 0) return kdi_fail(ctx, KDI_EINVAL, "min_groups must be >= 0");
+      ctx->min_groups = (int)value;
+      return KDI_OK;
+    case KDI_OPT_POST_PER_GROUP:
+      ctx->post_per_group = value != 0;
+      return KDI_OK;
+    case KDI_OPT_GEMM_SERIAL:
+      ctx->gemm_serial = value != 0;
+      return KDI_OK;
+    case KDI_OPT_SM_PARTITION:
+      if (value < 0) return kdi_fail(ctx, KDI_EINVAL, "sm_partition must be >= 0");
+      return kdi_setup_sm_partition(ctx, (int)value);
     default:
       return kdi_fail(ctx, KDI_EINVAL, "unknown option %d", option);
   }
@@ -331,13 +445,20 @@ int kdi_host_alloc(kdi_ctx* ctx, int64_t bytes, void** out) {
   if (!ctx || !out || bytes < 0) return KDI_EINVAL;
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
   KDI_CUDA(ctx, cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+  ctx->pinned.push_back(*out);  // freed by kdi_host_free, or with the context at the latest
   return KDI_OK;
 }
 
 int kdi_host_free(kdi_ctx* ctx, void* p) {
   if (!ctx) return KDI_EINVAL;
-  if (p) KDI_CUDA(ctx, cudaFreeHost(p));
-  return KDI_OK;
+  if (!p) return KDI_OK;
+  for (size_t i = 0; i < ctx->pinned.size(); ++i)
+    if (ctx->pinned[i] == p) {
+      ctx->pinned.erase(ctx->pinned.begin() + i);
+      KDI_CUDA(ctx, cudaFreeHost(p));
+      return KDI_OK;
+    }
+  return kdi_fail(ctx, KDI_EINVAL, "kdi_host_free: pointer was not allocated by kdi_host_alloc on this context");
 }
 
 int kdi_set_signal_mask(kdi_ctx* ctx, const uint8_t* mask, int64_t S) {
@@ -397,13 +518,62 @@ int kdi_patterns_alloc(kdi_ctx* ctx, int64_t rows, int64_t S, int metric, kdi_pa
 
 int kdi_patterns_fill(kdi_ctx* ctx, cudaStream_t stream, kdi_patterns* p, int64_t row_offset,
                       const void* d_src, int src_dtype, int64_t n_rows, const int64_t* d_rowmap,
-                      int max_ctas) {
+                      int max_ctas, uint32_t* ready) {
   if (row_offset < 0 || row_offset + n_rows > p->rows)
     return kdi_fail(ctx, KDI_EINTERNAL, "pattern fill out of range");
   return kdi_launch_normalize(ctx, stream, d_src, src_dtype, p->S, d_rowmap,
                               ctx->mask_S ? ctx->d_cols : nullptr, n_rows, p->s_eff, p->metric,
                               p->compute_dtype, p->a32 + row_offset * p->s_pitch, p->s_pitch,
-                              reinterpret_cast<uint16_t*>(p->a16) + row_offset * p->kp, p->kp, max_ctas);
+                              reinterpret_cast<uint16_t*>(p->a16) + row_offset * p->kp, p->kp, max_ctas,
+                              ready, row_offset);
+}
+
+int kdi_patterns_plan(kdi_ctx* ctx, const void* src, int src_loc, int src_dtype, int64_t rows, int64_t S,
+                      int metric, const uint8_t* row_mask, kdi_patterns** out, kdi_fill_plan* plan) {
+  *out = nullptr;
+  if (!src) return kdi_fail(ctx, KDI_EINVAL, "pattern source is NULL");
+  if (!kdi_dtype_size(src_dtype)) return kdi_fail(ctx, KDI_EINVAL, "unknown source dtype %d", src_dtype);
+  if (rows < 0 || S <= 0) return kdi_fail(ctx, KDI_EINVAL, "bad shape %lld x %lld", (long long)rows, (long long)S);
+  if (src_loc != KDI_HOST && src_loc != KDI_DEVICE) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location %d", src_loc);
+  *plan = kdi_fill_plan();
+  plan->src = src;
+  plan->loc = src_loc;
+  plan->dtype = src_dtype;
+  plan->rows = rows;
+  plan->S = S;
+  // navigation mask: rows kept are those with a zero byte (False = keep)
+  int64_t kept = rows;
+  if (row_mask) {
+    plan->masked = true;
+    plan->keep.reserve((size_t)rows);
+    for (int64_t i = 0; i < rows; ++i)
+      if (!row_mask[i]) plan->keep.push_back(i);
+    kept = (int64_t)plan->keep.size();
+  }
+  return kdi_patterns_alloc(ctx, kept, S, metric, out);
+}
+
+int kdi_patterns_run_plan(kdi_ctx* ctx, cudaStream_t stream, kdi_patterns* p, const kdi_fill_plan* plan) {
+  if (p->rows == 0) return KDI_OK;
+  const void* d_src = plan->src;
+  if (plan->loc == KDI_HOST) {
+    const size_t bytes = (size_t)plan->rows * plan->S * kdi_dtype_size(plan->dtype);
+    KDI_TRY(kdi_ws2_reserve(ctx, bytes));
+    cudaError_t e = cudaMemcpyAsync(ctx->ws2, plan->src, bytes, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return kdi_fail(ctx, KDI_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+    ctx->tm.h2d_bytes += (int64_t)bytes;
+    d_src = ctx->ws2;
+  }
+  if (plan->masked) {
+    void* q = nullptr;
+    KDI_TRY(kdi_dev_alloc(ctx, plan->keep.size() * sizeof(int64_t), &q, &p->rowmap_bytes));
+    p->d_rowmap = reinterpret_cast<int64_t*>(q);
+    // (pageable source: the copy is staged by the driver before the call returns)
+    cudaError_t e = cudaMemcpyAsync(p->d_rowmap, plan->keep.data(), plan->keep.size() * sizeof(int64_t),
+                                    cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return kdi_fail(ctx, KDI_ECUDA, "row map upload failed: %s", cudaGetErrorString(e));
+  }
+  return kdi_patterns_fill(ctx, stream, p, 0, d_src, plan->dtype, p->rows, p->d_rowmap);
 }
 
 extern "C" {
@@ -413,50 +583,20 @@ int kdi_patterns_create(kdi_ctx* ctx, const void* src, int src_loc, int src_dtyp
   if (!ctx) return KDI_EINVAL;
   if (!out || !src) return kdi_fail(ctx, KDI_EINVAL, "kdi_patterns_create: NULL argument");
   *out = nullptr;
-  const size_t esz = kdi_dtype_size(src_dtype);
-  if (!esz) return kdi_fail(ctx, KDI_EINVAL, "unknown source dtype %d", src_dtype);
-  if (rows < 0 || S <= 0) return kdi_fail(ctx, KDI_EINVAL, "bad shape %lld x %lld", (long long)rows, (long long)S);
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
-  // navigation mask: rows kept are those with a zero byte (False = keep)
-  std::vector<int64_t> keep;
-  int64_t kept = rows;
-  if (row_mask) {
-    keep.reserve((size_t)rows);
-    for (int64_t i = 0; i < rows; ++i)
-      if (!row_mask[i]) keep.push_back(i);
-    kept = (int64_t)keep.size();
-  }
   kdi_patterns* p = nullptr;
-  KDI_TRY(kdi_patterns_alloc(ctx, kept, S, metric, &p));
-  int rc = KDI_OK;
-  int64_t* d_rowmap = nullptr;
-  do {
-    if (kept == 0) break;
-    const void* d_src = src;
-    if (src_loc == KDI_HOST) {
-      const size_t bytes = (size_t)rows * S * esz;
-      if ((rc = kdi_ws2_reserve(ctx, bytes)) != KDI_OK) break;
-      cudaError_t e = cudaMemcpyAsync(ctx->ws2, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
-      if (e != cudaSuccess) { rc = kdi_fail(ctx, KDI_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
-      ctx->tm.h2d_bytes += (int64_t)bytes;
-      d_src = ctx->ws2;
-    } else if (src_loc != KDI_DEVICE) {
-      rc = kdi_fail(ctx, KDI_EINVAL, "bad buffer location %d", src_loc);
-      break;
-    }
-    if (row_mask) {
-      cudaError_t e = cudaMalloc(&d_rowmap, keep.size() * sizeof(int64_t));
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d_rowmap, keep.data(), keep.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
-      if (e != cudaSuccess) { rc = kdi_fail(ctx, KDI_ECUDA, "row map upload failed: %s", cudaGetErrorString(e)); break; }
-    }
-    if ((rc = kdi_patterns_fill(ctx, ctx->stream, p, 0, d_src, src_dtype, kept, d_rowmap)) != KDI_OK) break;
+  kdi_fill_plan plan;
+  KDI_TRY(kdi_patterns_plan(ctx, src, src_loc, src_dtype, rows, S, metric, row_mask, &p, &plan));
+  int rc = kdi_patterns_run_plan(ctx, ctx->stream, p, &plan);
+  if (rc == KDI_OK) {
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { rc = kdi_fail(ctx, KDI_ECUDA, "normalise failed: %s", cudaGetErrorString(e)); break; }
-  } while (0);
-  if (d_rowmap) cudaFree(d_rowmap);
+    if (e != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "normalise failed: %s", cudaGetErrorString(e));
+  }
   if (rc != KDI_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    const std::string err = ctx->err;
     kdi_patterns_destroy(ctx, p);
+    ctx->err = err;
     return rc;
   }
   *out = p;
@@ -489,6 +629,7 @@ int kdi_patterns_destroy(kdi_ctx* ctx, kdi_patterns* p) {
   }
   kdi_dev_free(ctx, p->a32, p->a32_bytes);
   kdi_dev_free(ctx, p->a16, p->a16_bytes);
+  kdi_dev_free(ctx, p->d_rowmap, p->rowmap_bytes);
   delete p;
   return KDI_OK;
 }

@@ -63,13 +63,14 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
   job->indices_out = indices_out;
   if (M == 0) return KDI_OK;
   job->fused = candidates_only || (!ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0);
-  size_t off_thr = 0, off_flags = 0, off_nflag = 0, off_sela = 0, off_seli = 0, total = 0;
+  size_t off_thr = 0, off_flags = 0, off_nflag = 0, off_sela = 0, off_seli = 0, off_ready = 0, total = 0;
   if (job->fused) {
     KDI_TRY(kdi_gemm_make_plan(ctx, M, N, exp->kp, keep_n, &job->plan));
     off_thr = align_up(job->plan.cand_bytes, 256);
     off_flags = align_up(off_thr + job->plan.thr_bytes, 256);
     off_nflag = align_up(off_flags + (size_t)M * sizeof(int), 256);
-    total = off_nflag + 256;
+    off_ready = off_nflag + 256;
+    total = align_up(off_ready + ((size_t)job->plan.n_tiles + 1) * sizeof(uint32_t), 256);
     if (!candidates_only) {  // selected lists between the selection and the rescoring kernel
       off_sela = align_up(total, 256);
       off_seli = align_up(off_sela + (size_t)M * job->plan.kc * sizeof(float), 256);
@@ -88,11 +89,14 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
     job->thr = reinterpret_cast<uint32_t*>(ws + off_thr);
     job->flags = reinterpret_cast<int*>(ws + off_flags);
     job->d_nflag = reinterpret_cast<int*>(ws + off_nflag);
+    job->tile_ready = reinterpret_cast<uint32_t*>(ws + off_ready);
     if (!candidates_only) {
       job->sel_approx = reinterpret_cast<float*>(ws + off_sela);
       job->sel_idx = reinterpret_cast<int64_t*>(ws + off_seli);
     }
-    KDI_CUDA(ctx, cudaMemsetAsync(job->d_nflag, 0, sizeof(int), ctx->stream));
+    // (the flagged-row counter and the readiness counters are adjacent: one memset)
+    KDI_CUDA(ctx, cudaMemsetAsync(job->d_nflag, 0, 256 + ((size_t)job->plan.n_tiles + 1) * sizeof(uint32_t),
+                                  ctx->stream));
     KDI_TRY(kdi_launch_cand_init(ctx, ctx->stream, job->thr, M));
   }
   return KDI_OK;
@@ -163,36 +167,52 @@ static void sync_all_streams(kdi_ctx* ctx) {
 // `e_fill` (may be NULL) is the event the remaining strips have to wait for.
 static int run_overlapped(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
                           const kdi_patterns* dict, const kdi_post& post, int strips_lo,
-                          cudaEvent_t e_fill) {
+                          cudaEvent_t e_fill, const uint32_t* ready = nullptr,
+                          cudaEvent_t e_dict_done = nullptr) {
   const kdi_gemm_plan& pl = job->plan;
-  cudaStream_t sm = ctx->stream, s2 = ctx->gemm_stream2, sa = ctx->aux_stream;
+  cudaStream_t sm = ctx->stream, sa = ctx->post_stream ? ctx->post_stream : ctx->aux_stream;
+  // GEMM streams: the context's two high-priority streams, or (SM partition) the two streams of the
+  // large partition; gemm_serial keeps every launch on one stream
+  cudaStream_t g0 = ctx->part_gemm[0] ? ctx->part_gemm[0] : sm;
+  cudaStream_t g1 = ctx->gemm_serial ? g0 : (ctx->part_gemm[1] ? ctx->part_gemm[1] : ctx->gemm_stream2);
   const int64_t rows_per_mb = (int64_t)KDI_TILE_M * pl.cta_group;
   const int n_sb = (int)kdi_ceil_div(pl.m_blocks, pl.superblock);
-  const int max_groups = 48;  // bounded by the event pool
-  const int sb_per_group = (int)kdi_ceil_div(n_sb, max_groups);
-  const int n_groups = (int)kdi_ceil_div(n_sb, sb_per_group);
+  const int max_groups = 24;  // bounded by the event pool
+  // one launch per L2 super-block of experimental rows, or more (smaller) groups when the
+  // post-processing of a finished group is to run beside the following launches
+  int n_groups = std::min(n_sb, max_groups);
+  if (ctx->min_groups > n_groups) n_groups = std::min(std::min(ctx->min_groups, max_groups), pl.m_blocks);
+  const int mb_per_group = (int)kdi_ceil_div(pl.m_blocks, n_groups);
+  n_groups = (int)kdi_ceil_div(pl.m_blocks, mb_per_group);
   int ev_i = 0;
   // everything queued on the main stream so far (experimental rows, thresholds, the first
   // dictionary slice and its strips) precedes the work on the other streams
   cudaEvent_t e_start = ctx->dep_ev[ev_i++];
   KDI_CUDA(ctx, cudaEventRecord(e_start, sm));
-  KDI_CUDA(ctx, cudaStreamWaitEvent(s2, e_start, 0));
+  if (g0 != sm) KDI_CUDA(ctx, cudaStreamWaitEvent(g0, e_start, 0));
+  if (g1 != sm && g1 != g0) KDI_CUDA(ctx, cudaStreamWaitEvent(g1, e_start, 0));
   KDI_CUDA(ctx, cudaStreamWaitEvent(sa, e_start, 0));
   if (e_fill) {
-    KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_fill, 0));
-    KDI_CUDA(ctx, cudaStreamWaitEvent(s2, e_fill, 0));
+    KDI_CUDA(ctx, cudaStreamWaitEvent(g0, e_fill, 0));
+    if (g1 != g0) KDI_CUDA(ctx, cudaStreamWaitEvent(g1, e_fill, 0));
   }
+  // `ready` mode: the GEMM launches do not wait for the dictionary (their TMA producers poll the
+  // readiness counters), but the post-processing reads the float32 dictionary rows with ordinary
+  // loads and is ordered after the kernel that writes them
+  if (e_dict_done) KDI_CUDA(ctx, cudaStreamWaitEvent(sa, e_dict_done, 0));
+  const bool post_groups = ctx->post_per_group && n_groups > 1;
+  int first_post_group = n_groups;  // groups >= this one are post-processed on the main stream at the end
+  if (post_groups) first_post_group = n_groups - 1;
   for (int g = 0; g < n_groups; ++g) {
-    cudaStream_t sg = (g & 1) ? s2 : sm;
-    const int mb0 = g * sb_per_group * pl.superblock;
-    const int mbn = std::min(pl.m_blocks - mb0, sb_per_group * pl.superblock);
+    cudaStream_t sg = (g & 1) ? g1 : g0;
+    const int mb0 = g * mb_per_group;
+    const int mbn = std::min(pl.m_blocks - mb0, mb_per_group);
     if (strips_lo < pl.n_strips)
       KDI_TRY(kdi_launch_gemm_topk(ctx, sg, exp, dict, &pl, strips_lo, pl.n_strips - strips_lo, job->cand,
-                                   job->thr, mb0, mbn));
-    if (ctx->post_per_group) {
-      // (only useful when the post-processing kernels may share SMs with the GEMM kernel - see
-      // kdi_gemm_carveout_pref; otherwise they would just queue up behind the GEMM launches as
-      // many small latency-bound kernels)
+                                   job->thr, mb0, mbn, ready));
+    if (post_groups && g < first_post_group) {
+      // the finished group's rows are selected / rescored on the post stream while the next groups'
+      // launches run (useful when that stream has SMs of its own: KDI_OPT_GEMM_SMS / SM partition)
       cudaEvent_t e_g = ctx->dep_ev[ev_i++];
       KDI_CUDA(ctx, cudaEventRecord(e_g, sg));
       KDI_CUDA(ctx, cudaStreamWaitEvent(sa, e_g, 0));
@@ -203,18 +223,28 @@ static int run_overlapped(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* 
   }
   job->strips_done = pl.n_strips;
   // join: the GEMM span ends when both GEMM streams are done
-  cudaEvent_t e_s2 = ctx->dep_ev[ev_i++];
-  KDI_CUDA(ctx, cudaEventRecord(e_s2, s2));
-  KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_s2, 0));
+  if (g0 != sm) {
+    cudaEvent_t e_a = ctx->dep_ev[ev_i++];
+    KDI_CUDA(ctx, cudaEventRecord(e_a, g0));
+    KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_a, 0));
+  }
+  if (g1 != sm && g1 != g0) {
+    cudaEvent_t e_b = ctx->dep_ev[ev_i++];
+    KDI_CUDA(ctx, cudaEventRecord(e_b, g1));
+    KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_b, 0));
+  }
+  if (e_dict_done) KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_dict_done, 0));
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[9], sm));
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], sm));
-  if (ctx->post_per_group) {
+  // the rest (every row, or the last group) right behind the last launch on the main stream
+  {
+    const int64_t row0 = post_groups ? (int64_t)first_post_group * mb_per_group * rows_per_mb : 0;
+    KDI_TRY(launch_post(ctx, sm, job, exp, dict, post, row0, job->M - row0));
+  }
+  if (post_groups) {
     cudaEvent_t e_aux = ctx->dep_ev[ev_i++];
     KDI_CUDA(ctx, cudaEventRecord(e_aux, sa));
     KDI_CUDA(ctx, cudaStreamWaitEvent(sm, e_aux, 0));
-  } else {
-    // selection + rescoring of every row in one launch each (HBM-bound; full-size grids)
-    KDI_TRY(launch_post(ctx, sm, job, exp, dict, post, 0, job->M));
   }
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], sm));
   return KDI_OK;
@@ -248,29 +278,43 @@ int kdi_match_complete(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp
   const int keep_n = job->keep_n;
   if (M == 0) return KDI_OK;
   cudaStream_t st = ctx->stream;
-  int n_flag = 0;
-  if (job->fused) {
-    KDI_CUDA(ctx, cudaMemcpyAsync(&n_flag, job->d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    KDI_CUDA(ctx, cudaStreamSynchronize(st));
-    if (n_flag > 0)
-      KDI_TRY(exact_rows(ctx, exp, dict, job->flags, 0, n_flag, keep_n, index_offset, job->d_sc, job->d_ix));
-  } else {
-    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    KDI_TRY(exact_rows(ctx, exp, dict, nullptr, 0, M, keep_n, index_offset, job->d_sc, job->d_ix));
-  }
-  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-  if (job->out_loc == KDI_HOST) {
+  auto copy_out = [&]() -> int {
+    if (job->out_loc != KDI_HOST) return KDI_OK;
     KDI_CUDA(ctx, cudaMemcpyAsync(job->scores_out, job->d_sc, (size_t)M * keep_n * sizeof(float),
                                   cudaMemcpyDeviceToHost, st));
     KDI_CUDA(ctx, cudaMemcpyAsync(job->indices_out, job->d_ix, (size_t)M * keep_n * sizeof(int64_t),
                                   cudaMemcpyDeviceToHost, st));
-    ctx->tm.d2h_bytes += (int64_t)M * keep_n * 12;
+    return KDI_OK;
+  };
+  int n_flag = 0;
+  if (job->fused) {
+    // the flagged-row count travels with the results: one synchronisation when no row was flagged
+    // (the common case), a second round only for the rows the exact path has to redo
+    if (!ctx->h_nflag) KDI_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_nflag), 64, cudaHostAllocDefault));
+    KDI_CUDA(ctx, cudaMemcpyAsync(ctx->h_nflag, job->d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    KDI_TRY(copy_out());
+    KDI_CUDA(ctx, cudaStreamSynchronize(st));
+    n_flag = *ctx->h_nflag;
+    if (n_flag > 0) {
+      KDI_CUDA(ctx, cudaEventRecord(ctx->ev[10], st));
+      KDI_TRY(exact_rows(ctx, exp, dict, job->flags, 0, n_flag, keep_n, index_offset, job->d_sc, job->d_ix));
+      KDI_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+      KDI_TRY(copy_out());
+      KDI_CUDA(ctx, cudaStreamSynchronize(st));
+      ctx->tm.fallback_ms += ev_ms(ctx->ev[10], ctx->ev[5]);
+    }
+  } else {
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[10], st));
+    KDI_TRY(exact_rows(ctx, exp, dict, nullptr, 0, M, keep_n, index_offset, job->d_sc, job->d_ix));
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    KDI_TRY(copy_out());
+    KDI_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->tm.fallback_ms += ev_ms(ctx->ev[10], ctx->ev[5]);
   }
-  KDI_CUDA(ctx, cudaStreamSynchronize(st));
+  if (job->out_loc == KDI_HOST) ctx->tm.d2h_bytes += (int64_t)M * keep_n * 12;
   if (job->fused) ctx->tm.gemm_topk_ms += ev_ms(ctx->ev[8], ctx->ev[9]);  // last GEMM launch / GEMM span
-  ctx->tm.rescore_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
-  ctx->tm.fallback_ms += ev_ms(ctx->ev[4], ctx->ev[5]);
+  if (job->fused) ctx->tm.rescore_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
   ctx->tm.flagged_rows += job->fused ? n_flag : M;
   return KDI_OK;
 }
@@ -411,11 +455,12 @@ struct kdi_dict_source {
 
 // normalised rows [row0, row0 + n) of `dict` from a device-resident source
 static int fill_dict(kdi_ctx* ctx, cudaStream_t st, kdi_patterns* dict, int64_t row0, int64_t n,
-                     const kdi_dict_source& src, int64_t S, int max_ctas) {
+                     const kdi_dict_source& src, int64_t S, int max_ctas, uint32_t* ready) {
+  if (n <= 0) return KDI_OK;
   if (src.mp) return kdi_launch_project(ctx, st, src.mp, src.d_rot + row0 * 4, n, nullptr, dict, row0, max_ctas);
   const size_t row_bytes = (size_t)S * kdi_dtype_size(src.dtype);
   return kdi_patterns_fill(ctx, st, dict, row0, reinterpret_cast<const uint8_t*>(src.data) + (size_t)row0 * row_bytes,
-                           src.dtype, n, nullptr, max_ctas);
+                           src.dtype, n, nullptr, max_ctas, ready);
 }
 
 // prepare experimental (once) + dictionary (streamed) and run the tensor-core pass and the
@@ -447,64 +492,95 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
   const size_t row_bytes = (size_t)S * dsz;
 
+  // allocate both pattern sets first (nothing queued yet), so that every piece of work can be
+  // queued where the schedule wants it
+  kdi_patterns* exp = nullptr;
+  kdi_fill_plan exp_plan;
+  KDI_TRY(kdi_patterns_plan(ctx, experimental, exp_loc, exp_dtype, exp_rows, S, metric, nav_mask, &exp, &exp_plan));
   kdi_patterns* dict = nullptr;
-  KDI_TRY(kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict));
-  // Device-resident dictionary, overlapped schedule: all but the first quarter of the dictionary
-  // is normalised on the low-priority stream by a small resident grid, starting now - beside the
-  // experimental normalisation, the first quarter and the tensor-core pass over that quarter.
+  int rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict);
+  if (rc != KDI_OK) {
+    const std::string err = ctx->err;
+    kdi_patterns_destroy(ctx, exp);
+    ctx->err = err;
+    return rc;
+  }
+  // prepare_dictionary + match, streamed.  The reference prepares and matches one chunk of
+  // n_per_iteration rows per iteration (_dictionary_indexing.py:102-128); the result does not
+  // depend on the chunking.
+  rc = kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, candidates_only, job);
+
+  // Device-resident dictionary, overlapped schedule: the dictionary is prepared on the low-priority
+  // stream by a small resident grid, beside the experimental normalisation and the tensor-core pass.
+  //  * flag mode (register-resident normalise kernel, which fits on an SM next to a GEMM CTA): the
+  //    whole dictionary goes to that stream and publishes per-tile readiness counters; the GEMM
+  //    launches start right after the experimental rows are ready and their TMA producers wait on
+  //    the counters of the tiles they are about to load;
+  //  * event mode (kernels that need shared memory: masks, other dtypes, generated dictionaries):
+  //    the first quarter is prepared on the main stream and matched against every row block while
+  //    the rest is prepared on the other stream; the remaining launches wait for its event.
+  const bool overlap_ok = rc == KDI_OK && ctx->overlap && dict_loc == KDI_DEVICE && job->fused && job->M > 0 &&
+                          want_overlap(ctx, job);
+  const int64_t s_eff = ctx->mask_S ? ctx->mask_kept : S;
+  const bool flag_mode = overlap_ok && ctx->dep_flags && !dsrc.mp &&
+                         kdi_normalize_is_light(S, s_eff, false, ctx->mask_S != 0) &&
+                         (dict_dtype == KDI_F32 || dict_dtype == KDI_U8) &&
+                         (reinterpret_cast<uintptr_t>(dictionary) % 16) == 0;
+  const bool early = overlap_ok && !flag_mode &&
+                     (ctx->overlap == 2 ? dict_rows >= 4 * KDI_TILE_N : (dict_rows >= 16384 && exp_rows >= 2048));
   int64_t g1_rows = dict_rows;
   cudaEvent_t e_fill = nullptr;
-  const bool early = ctx->overlap && dict_loc == KDI_DEVICE && !ctx->force_exact &&
-                     kdi_gemm_kc_for(keep_n) != 0 &&
-                     (ctx->overlap == 2 ? dict_rows >= 4 * KDI_TILE_N : (dict_rows >= 16384 && exp_rows >= 2048));
-  if (early) {
-    g1_rows = dict_rows / 4 / KDI_TILE_N * KDI_TILE_N;
+  if (rc == KDI_OK && (flag_mode || early)) {
+    if (early) g1_rows = dict_rows / 4 / KDI_TILE_N * KDI_TILE_N;
+    else g1_rows = 0;
     cudaEvent_t e0 = ctx->dep_ev[63];
     e_fill = ctx->dep_ev[62];
-    cudaError_t e = cudaEventRecord(e0, st);  // the caller's buffers may have been produced on this stream
+    // the caller's buffers may have been produced on the main stream; the counters were reset on it
+    cudaError_t e = cudaEventRecord(e0, st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, e0, 0);
-    int rc = e == cudaSuccess ? KDI_OK : kdi_fail(ctx, KDI_ECUDA, "stream setup failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream setup failed: %s", cudaGetErrorString(e));
     if (rc == KDI_OK)
-      rc = fill_dict(ctx, ctx->aux_stream, dict, g1_rows, dict_rows - g1_rows, dsrc, S, 4 * ctx->sm_count);
+      rc = fill_dict(ctx, ctx->aux_stream, dict, g1_rows, dict_rows - g1_rows, dsrc, S, 4 * ctx->sm_count,
+                     flag_mode ? job->tile_ready : nullptr);
+    if (rc == KDI_OK && flag_mode) {
+      // "everything is ready": the producers stop polling once they have seen this word
+      if (cudaMemsetAsync(job->tile_ready + job->plan.n_tiles, 0x01, sizeof(uint32_t), ctx->aux_stream) != cudaSuccess)
+        rc = kdi_fail(ctx, KDI_ECUDA, "memset failed");
+      if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], ctx->aux_stream) != cudaSuccess)
+        rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+    }
     if (rc == KDI_OK && cudaEventRecord(e_fill, ctx->aux_stream) != cudaSuccess)
       rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
-    if (rc != KDI_OK) {
-      sync_all_streams(ctx);
-      const std::string err = ctx->err;
-      kdi_patterns_destroy(ctx, dict);
-      ctx->err = err;
-      return rc;
-    }
   }
 
   // prepare_experimental - once (_dictionary_indexing.py:70)
-  kdi_patterns* exp = nullptr;
-  int rc = kdi_patterns_create(ctx, experimental, exp_loc, exp_dtype, exp_rows, S, metric, nav_mask, &exp);
+  if (rc == KDI_OK) rc = kdi_patterns_run_plan(ctx, st, exp, &exp_plan);
   if (rc == KDI_OK && cudaEventRecord(ctx->ev[6], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+  // a host dictionary is staged through the same workspace the experimental upload used
+  if (rc == KDI_OK && dict_loc == KDI_HOST && exp_loc == KDI_HOST && cudaStreamSynchronize(st) != cudaSuccess)
+    rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
 
-  // prepare_dictionary + match, streamed.  The reference prepares and matches one chunk of
-  // n_per_iteration rows per iteration (_dictionary_indexing.py:102-128); the result does not
-  // depend on the chunking, so the pieces moved here are sized for the copy engine (64 MB) and the
-  // tensor-core pass runs over every group of pieces as soon as it has been normalised, while
-  // the next pieces are still in flight on the copy stream.
-  if (rc == KDI_OK)
-    rc = kdi_match_begin(ctx, exp, dict, keep_n, scores_out, indices_out, out_loc, candidates_only, job);
   if (rc == KDI_OK) {
     if (dict_loc == KDI_DEVICE) {
-      rc = fill_dict(ctx, st, dict, 0, g1_rows, dsrc, S, 0);
-      if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
-      if (rc == KDI_OK && job->M > 0 && job->fused && want_overlap(ctx, job)) {
-        // first quarter against every row block, then the row-block groups over the rest
+      if (flag_mode) {
         if (cudaEventRecord(ctx->ev[8], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
-        const int64_t strip_rows = (int64_t)job->plan.strip_tiles * KDI_TILE_N;
-        int strips_lo = g1_rows >= dict_rows ? 0 : (int)(g1_rows / strip_rows);
-        if (rc == KDI_OK && strips_lo > 0)
-          rc = kdi_launch_gemm_topk(ctx, st, exp, dict, &job->plan, 0, strips_lo, job->cand, job->thr);
-        if (rc == KDI_OK) rc = run_overlapped(ctx, job, exp, dict, post, strips_lo, e_fill);
-      } else if (rc == KDI_OK) {
-        if (e_fill && cudaStreamWaitEvent(st, e_fill, 0) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream wait failed");
-        if (rc == KDI_OK) rc = kdi_match_advance(ctx, job, exp, dict, dict_rows);
-        if (rc == KDI_OK) rc = kdi_match_select(ctx, job, exp, dict, post);
+        if (rc == KDI_OK) rc = run_overlapped(ctx, job, exp, dict, post, 0, nullptr, job->tile_ready, e_fill);
+      } else {
+        rc = fill_dict(ctx, st, dict, 0, g1_rows, dsrc, S, 0, nullptr);
+        if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+        if (rc == KDI_OK && overlap_ok) {
+          // first quarter against every row block, then the row-block groups over the rest
+          if (cudaEventRecord(ctx->ev[8], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+          const int64_t strip_rows = (int64_t)job->plan.strip_tiles * KDI_TILE_N;
+          int strips_lo = g1_rows >= dict_rows ? 0 : (int)(g1_rows / strip_rows);
+          if (rc == KDI_OK && strips_lo > 0)
+            rc = kdi_launch_gemm_topk(ctx, st, exp, dict, &job->plan, 0, strips_lo, job->cand, job->thr);
+          if (rc == KDI_OK) rc = run_overlapped(ctx, job, exp, dict, post, strips_lo, e_fill, nullptr, e_fill);
+        } else if (rc == KDI_OK) {
+          if (e_fill && cudaStreamWaitEvent(st, e_fill, 0) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream wait failed");
+          if (rc == KDI_OK) rc = kdi_match_advance(ctx, job, exp, dict, dict_rows);
+          if (rc == KDI_OK) rc = kdi_match_select(ctx, job, exp, dict, post);
+        }
       }
     } else {
       int64_t piece = (int64_t)std::max<size_t>(1, (64u << 20) / row_bytes);

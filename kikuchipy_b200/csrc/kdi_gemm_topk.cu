@@ -55,6 +55,7 @@ struct GemmParams {
   uint2* cand;
   uint32_t* thr;
   float* out;  // MODE 1
+  const uint32_t* ready;  // optional per-tile readiness counters of the dictionary (+ "all ready" word)
 };
 
 __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
@@ -149,6 +150,7 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       int stage = 0;
       uint32_t phase = 0;
+      bool all_ready = p.ready == nullptr;
       for (int64_t u = cluster_id; u < p.units; u += n_clusters) {
         int mb, strip;
         decode_unit(p, u, mb, strip);
@@ -159,6 +161,16 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int ti = 0; ti < t1 - t0; ++ti) {
           const int nt = t0 + (ti + rot) % (t1 - t0);
           const int b_row = nt * KDI_TILE_N + (int)rank * kBRows;
+          if (!all_ready) {
+            // the dictionary is being prepared by a kernel running beside this one: wait for the
+            // rows of this tile (or for the "everything is ready" word, after which nothing is polled)
+            all_ready = ld_acquire_gpu(p.ready + p.n_tiles) != 0u;
+            if (!all_ready) {
+              const int64_t left = p.N - (int64_t)nt * KDI_TILE_N;
+              wait_counter_ge(p.ready + nt, (uint32_t)(left < KDI_TILE_N ? left : KDI_TILE_N));
+            }
+            fence_proxy_async_global();
+          }
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
             const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
@@ -390,7 +402,11 @@ int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
   // (experiments with SM sharing: see kdi_gemm_carveout_pref)
   if (kdi_gemm_carveout_pref() >= 0)
     KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_gemm_carveout_pref()));
-  const int64_t max_clusters = ctx->sm_count / CG;
+  // (KDI_OPT_GEMM_SMS: leave some SMs to the HBM-bound kernels of the overlapped schedule)
+  int sms = (ctx->gemm_sms > 0 && ctx->gemm_sms < ctx->sm_count) ? ctx->gemm_sms : ctx->sm_count;
+  if ((stream == ctx->part_gemm[0] || stream == ctx->part_gemm[1]) && stream != nullptr && ctx->part_gemm_sms < sms)
+    sms = ctx->part_gemm_sms;  // launched into the large SM partition
+  const int64_t max_clusters = sms / CG;
   const int64_t n_clusters = p.units < max_clusters ? p.units : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_clusters * CG));
@@ -502,7 +518,8 @@ static int check_operands(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patte
 
 int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
                          const kdi_patterns* dict, const kdi_gemm_plan* plan, int strip0,
-                         int strip_count, uint2* cand, uint32_t* thr, int mb0, int mb_count) {
+                         int strip_count, uint2* cand, uint32_t* thr, int mb0, int mb_count,
+                         const uint32_t* ready) {
   if (strip0 < 0 || strip_count < 1 || strip0 + strip_count > plan->n_strips)
     return kdi_fail(ctx, KDI_EINTERNAL, "GEMM strip range out of bounds");
   if (mb_count < 0) mb_count = plan->m_blocks - mb0;
@@ -533,6 +550,7 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   p.cand = cand;
   p.thr = thr;
   p.out = nullptr;
+  p.ready = ready;
   if (cg == 1 && plan->kc == 32) return launch_variant<1, 32, 0>(ctx, stream, tmA, tmB, p);
   if (cg == 1 && plan->kc == 64) return launch_variant<1, 64, 0>(ctx, stream, tmA, tmB, p);
   if (cg == 2 && plan->kc == 32) return launch_variant<2, 32, 0>(ctx, stream, tmA, tmB, p);

@@ -32,6 +32,19 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
+// Readiness signal for a consumer that runs CONCURRENTLY with this kernel (the tensor-core kernel
+// of the overlapped schedule, kdi_gemm_topk.cu): once every thread of the block has stored its part
+// of dictionary row `grow`, one thread makes the stores visible device-wide and bumps the counter of
+// the 256-row tile the row belongs to.  The consumer acquires the counter before its TMA loads.
+__device__ __forceinline__ void publish_row(uint32_t* ready, int64_t grow) {
+  if (ready == nullptr) return;  // uniform
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ready + grow / KDI_TILE_N, 1u);
+  }
+}
+
 template <bool BF16>
 __device__ __forceinline__ uint16_t to16(float v) {
   if constexpr (BF16) {
@@ -48,7 +61,7 @@ __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_generic(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
                       const int32_t* __restrict__ cols, int64_t s_eff, int metric,
                       float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
-                      int64_t kp, int64_t n_rows) {
+                      int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0) {
   __shared__ double red[kNormThreads / 32];
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
   const int64_t srow = rowmap ? rowmap[row] : row;
@@ -77,6 +90,7 @@ kdi_normalize_generic(const T* __restrict__ src, int64_t S, const int64_t* __res
     o16[j] = to16<BF16>(v);
   }
   // s_pitch <= kp always (kp is s_eff rounded up to 64, s_pitch to 4)
+  publish_row(ready, ready_row0 + row);
   }
 }
 
@@ -89,7 +103,7 @@ __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
                      const int32_t* __restrict__ cols, int64_t s_eff, int metric,
                      float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
-                     int64_t kp, int64_t n_rows) {
+                     int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0) {
   extern __shared__ float v[];  // s_eff floats
   __shared__ double red[kNormThreads / 32];
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
@@ -146,6 +160,7 @@ kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __rest
       h.y = (uint32_t)to16<BF16>(o[2]) | ((uint32_t)to16<BF16>(o[3]) << 16);
       *reinterpret_cast<uint2*>(o16 + j) = h;
     }
+    publish_row(ready, ready_row0 + row);
   }
 }
 
@@ -164,7 +179,7 @@ template <typename T, int V, bool BF16>
 __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
                        float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
-                       int64_t kp, int64_t n_rows) {
+                       int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0) {
   __shared__ double red[kNormThreads / 32];
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
   const T* x = src + row * S;
@@ -212,6 +227,7 @@ kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
   }
   // zero the K padding of the 16-bit row (s_pitch == S here)
   for (int64_t j = S + threadIdx.x; j < kp; j += kNormThreads) a16[row * kp + j] = 0;
+  publish_row(ready, ready_row0 + row);
   }
 }
 
@@ -226,7 +242,8 @@ void prefer_max_shared(K kernel) {
 template <typename T>
 int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_t* rowmap,
                    const int32_t* cols, int64_t rows, int64_t s_eff, int metric, int bf16,
-                   float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid) {
+                   float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
+                   uint32_t* ready, int64_t ready_row0) {
   const T* s = reinterpret_cast<const T*>(src);
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
   const size_t stage_bytes = (size_t)s_eff * sizeof(float);
@@ -237,54 +254,62 @@ int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_
     else cudaFuncSetAttribute(kdi_normalize_staged<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (bf16)
       kdi_normalize_staged<T, true><<<grid, kNormThreads, stage_bytes, stream>>>(
-          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
+          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
     else
       kdi_normalize_staged<T, false><<<grid, kNormThreads, stage_bytes, stream>>>(
-          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
+          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
     return 0;
   }
   static bool once = (prefer_max_shared(kdi_normalize_generic<T, true>), prefer_max_shared(kdi_normalize_generic<T, false>), true);
   (void)once;
   if (bf16)
     kdi_normalize_generic<T, true><<<grid, kNormThreads, 0, stream>>>(
-        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
+        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
   else
     kdi_normalize_generic<T, false><<<grid, kNormThreads, 0, stream>>>(
-        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows);
+        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
   return 0;
 }
 
 template <typename T, int V>
 void launch_regs(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int metric,
-                 int bf16, float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid) {
+                 int bf16, float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
+                 uint32_t* ready, int64_t ready_row0) {
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
   static bool once = (prefer_max_shared(kdi_normalize_f32_regs<T, V, true>), prefer_max_shared(kdi_normalize_f32_regs<T, V, false>), true);
   (void)once;
   if (bf16)
     kdi_normalize_f32_regs<T, V, true><<<grid, kNormThreads, 0, stream>>>(
-        src, S, metric, a32, s_pitch, o16, kp, rows);
+        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
   else
     kdi_normalize_f32_regs<T, V, false><<<grid, kNormThreads, 0, stream>>>(
-        src, S, metric, a32, s_pitch, o16, kp, rows);
+        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
 }
 
 template <typename T>
 void launch_regs_any(cudaStream_t stream, const T* s, int64_t S, int64_t rows, int metric, int bf16,
-                     float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid) {
+                     float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
+                     uint32_t* ready, int64_t ready_row0) {
   const int v = (int)kdi_ceil_div(S / 4, kNormThreads);
-  if (v <= 1) launch_regs<T, 1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
-  else if (v <= 2) launch_regs<T, 2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
-  else if (v <= 4) launch_regs<T, 4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
-  else if (v <= 8) launch_regs<T, 8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
-  else launch_regs<T, 16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+  if (v <= 1) launch_regs<T, 1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
+  else if (v <= 2) launch_regs<T, 2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
+  else if (v <= 4) launch_regs<T, 4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
+  else if (v <= 8) launch_regs<T, 8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
+  else launch_regs<T, 16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
 }
 
 }  // namespace
 
+// Does this shape take the register-resident kernel (no dynamic shared memory)?  Only that kernel
+// may run beside the tensor-core kernel, whose CTAs leave no shared memory free on their SMs.
+bool kdi_normalize_is_light(int64_t S, int64_t s_eff, bool row_gather, bool col_gather) {
+  return !row_gather && !col_gather && s_eff == S && (S % 4) == 0 && S <= 16 * 4 * kNormThreads;
+}
+
 int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int src_dtype,
                          int64_t S, const int64_t* d_rowmap, const int32_t* d_cols, int64_t rows,
                          int64_t s_eff, int metric, int compute_dtype, float* a32, int64_t s_pitch,
-                         void* a16, int64_t kp, int max_ctas) {
+                         void* a16, int64_t kp, int max_ctas, uint32_t* ready, int64_t ready_row0) {
   if (rows <= 0) return KDI_OK;
   if (rows > 0x7fffffffLL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "too many rows in one pattern set");
   // max_ctas > 0: a small resident grid that loops over the rows (runs beside the GEMM kernel)
@@ -292,28 +317,29 @@ int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int
   const int bf16 = compute_dtype == 1;
   const bool plain = !d_rowmap && !d_cols && s_eff == S;
   kdi_span span(ctx, stream, max_ctas > 0 ? "normalize (resident grid)" : "normalize");
-  const bool reg_path = plain && (S % 4) == 0 && s_pitch == S && S <= 16 * 4 * kNormThreads;
+  const bool reg_path = kdi_normalize_is_light(S, s_eff, d_rowmap != nullptr, d_cols != nullptr) && s_pitch == S;
+  (void)plain;
   if (src_dtype == KDI_F32 && reg_path && (reinterpret_cast<uintptr_t>(src) % 16) == 0) {
-    launch_regs_any<float>(stream, reinterpret_cast<const float*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+    launch_regs_any<float>(stream, reinterpret_cast<const float*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
   } else if (src_dtype == KDI_U8 && reg_path && (reinterpret_cast<uintptr_t>(src) % 4) == 0) {
-    launch_regs_any<uint8_t>(stream, reinterpret_cast<const uint8_t*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid);
+    launch_regs_any<uint8_t>(stream, reinterpret_cast<const uint8_t*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
   } else {
     switch (src_dtype) {
       case KDI_U8:
         launch_generic<uint8_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                s_pitch, a16, kp, grid);
+                                s_pitch, a16, kp, grid, ready, ready_row0);
         break;
       case KDI_U16:
         launch_generic<uint16_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                 s_pitch, a16, kp, grid);
+                                 s_pitch, a16, kp, grid, ready, ready_row0);
         break;
       case KDI_F32:
         launch_generic<float>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                              s_pitch, a16, kp, grid);
+                              s_pitch, a16, kp, grid, ready, ready_row0);
         break;
       case KDI_F64:
         launch_generic<double>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                               s_pitch, a16, kp, grid);
+                               s_pitch, a16, kp, grid, ready, ready_row0);
         break;
       default:
         return kdi_fail(ctx, KDI_EINVAL, "unknown source dtype %d", src_dtype);

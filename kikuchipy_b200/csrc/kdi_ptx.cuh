@@ -74,6 +74,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ---- device-side dependencies between concurrently running kernels ---------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// orders the generic-proxy view of global memory (the acquire above) before subsequent
+// async-proxy reads (TMA loads) of data another kernel wrote with ordinary stores
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+// Bounded wait until *p >= need (see mbar_wait: a protocol bug traps instead of hanging)
+__device__ __forceinline__ void wait_counter_ge(const uint32_t* p, uint32_t need) {
+  if (ld_acquire_gpu(p) >= need) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(p) < need) {
+    __nanosleep(100);
+    if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s
+  }
+}
+
 // ---- TMA ----------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

@@ -62,14 +62,10 @@ def load_edax_binary(filename, nav_shape=None, device=False, context=None):
     with open(filename, "rb") as f:
         f.seek(h["pattern_offset"])
         if device:
-            import torch
-
             from . import _lib
 
             ctx = context if context is not None else _lib.default_context()
-            staged = ctx.pinned_empty((count,), h["dtype"])
-            staged[:] = np.fromfile(f, dtype=h["dtype"], count=count)
-            data = torch.from_numpy(staged).to(torch.device("cuda", ctx.device)).reshape(shape)
+            data = ctx.to_device(np.fromfile(f, dtype=h["dtype"], count=count)).reshape(shape)
         else:
             data = np.fromfile(f, dtype=h["dtype"], count=count).reshape(shape)
     md = {"General": {"original_filename": filename, "title": os.path.splitext(os.path.basename(filename))[0]},

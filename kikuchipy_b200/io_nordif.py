@@ -148,18 +148,13 @@ def load_nordif(filename, scan_size=None, pattern_size=None, setting_file=None, 
         from . import _lib
 
         ctx = context if context is not None else _lib.default_context()
-        import torch
-
-        staged = ctx.pinned_empty((count,), np.uint8)
         got = np.fromfile(filename, dtype=np.uint8, count=count)
-        staged[: got.size] = got
-        staged[got.size:] = 0
         if got.size < count:
             warnings.warn("Pattern size and scan size larger than file size! Will attempt to load by zero padding "
                           "incomplete frames.")
-        data = torch.from_numpy(staged).to(torch.device("cuda", ctx.device), non_blocking=False).reshape(ny, nx, sy, sx)
-        if data.shape[0] == 1:
-            data = data.squeeze(0)
+            got = np.pad(got, [(0, count - got.size)])
+        # (same squeeze as the host branch and the reference, io/plugins/nordif/_api.py)
+        data = ctx.to_device(got).reshape(ny, nx, sy, sx).squeeze()
     else:
         data = np.fromfile(filename, dtype=np.uint8, count=count)
         if data.size < count:

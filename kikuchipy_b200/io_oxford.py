@@ -105,14 +105,10 @@ def load_oxford_binary(filename, device=False, context=None):
         if key in names:
             om[key] = records[key][sel]
     if device:
-        import torch
-
         from . import _lib
 
         ctx = context if context is not None else _lib.default_context()
-        staged = ctx.pinned_empty(data.shape, data.dtype)
-        staged[...] = data
-        data = torch.from_numpy(staged).to(torch.device("cuda", ctx.device))
+        data = ctx.to_device(data)
     md = {"General": {"original_filename": filename, "title": os.path.splitext(os.path.basename(filename))[0]},
           "Signal": {"signal_type": "EBSD", "record_by": "image"}}
     scan = NordifScan(data, None, None, steps if len(steps) == 2 else (1.0, steps[0]), md, om)
