@@ -99,6 +99,10 @@ extern "C" {
                                    post-processing stream and the rest for the tensor-core launches (n is
                                    rounded up by the driver's granularity); 0 (default) = no partition.
                                    KDI_EUNSUPPORTED when the driver cannot do it                           */
+#define KDI_OPT_POST_CORESIDENT 17 /* n > 0 (with KDI_OPT_POST_PER_GROUP): the tensor-core kernel gives up one
+                                   pipeline stage of shared memory and the post-processing kernels of a
+                                   finished group are sized so that n of their CTAs fit into that hole on
+                                   every SM - they then run BESIDE the next groups' launches; 0 = off     */
 
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;

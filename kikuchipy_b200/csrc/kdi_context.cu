@@ -119,6 +119,16 @@ void kdi_dev_free(kdi_ctx* ctx, void* p, size_t bytes) {
   kdi_pool_trim(ctx, ctx->total_mem / 4);
 }
 
+size_t kdi_post_pad_bytes(const kdi_ctx* ctx, size_t static_bytes) {
+  if (ctx->post_coresident <= 0) return 0;
+  // one 32 KB pipeline stage of the GEMM kernel (+ what it leaves anyway), minus the 1 KB the
+  // hardware reserves per CTA
+  const size_t hole = 32768 + 1536;
+  const size_t per_cta = hole / (size_t)ctx->post_coresident;
+  const size_t own = static_bytes + 1024;
+  return per_cta > own + 256 ? per_cta - own - 128 : 0;
+}
+
 int kdi_carveout_pref() {
   static const int v = [] {
     const char* e = getenv("KDI_CARVEOUT");
@@ -410,6 +420,10 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
       return KDI_OK;
     case KDI_OPT_GEMM_SERIAL:
       ctx->gemm_serial = value != 0;
+      return KDI_OK;
+    case KDI_OPT_POST_CORESIDENT:
+      if (value < 0 || value > 8) return kdi_fail(ctx, KDI_EINVAL, "post_coresident must be 0..8");
+      ctx->post_coresident = (int)value;
       return KDI_OK;
     case KDI_OPT_SM_PARTITION:
       if (value < 0) return kdi_fail(ctx, KDI_EINVAL, "sm_partition must be >= 0");

@@ -530,27 +530,28 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
                      (ctx->overlap == 2 ? dict_rows >= 4 * KDI_TILE_N : (dict_rows >= 16384 && exp_rows >= 2048));
   int64_t g1_rows = dict_rows;
   cudaEvent_t e_fill = nullptr;
-  if (rc == KDI_OK && (flag_mode || early)) {
-    if (early) g1_rows = dict_rows / 4 / KDI_TILE_N * KDI_TILE_N;
-    else g1_rows = 0;
+  // queue the dictionary rows [g1_rows, N) on the low-priority stream
+  auto start_aux_fill = [&]() -> int {
     cudaEvent_t e0 = ctx->dep_ev[63];
     e_fill = ctx->dep_ev[62];
     // the caller's buffers may have been produced on the main stream; the counters were reset on it
     cudaError_t e = cudaEventRecord(e0, st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, e0, 0);
-    if (e != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream setup failed: %s", cudaGetErrorString(e));
-    if (rc == KDI_OK)
-      rc = fill_dict(ctx, ctx->aux_stream, dict, g1_rows, dict_rows - g1_rows, dsrc, S, 4 * ctx->sm_count,
-                     flag_mode ? job->tile_ready : nullptr);
-    if (rc == KDI_OK && flag_mode) {
+    if (e != cudaSuccess) return kdi_fail(ctx, KDI_ECUDA, "stream setup failed: %s", cudaGetErrorString(e));
+    KDI_TRY(fill_dict(ctx, ctx->aux_stream, dict, g1_rows, dict_rows - g1_rows, dsrc, S, 4 * ctx->sm_count,
+                      flag_mode ? job->tile_ready : nullptr));
+    if (flag_mode) {
       // "everything is ready": the producers stop polling once they have seen this word
-      if (cudaMemsetAsync(job->tile_ready + job->plan.n_tiles, 0x01, sizeof(uint32_t), ctx->aux_stream) != cudaSuccess)
-        rc = kdi_fail(ctx, KDI_ECUDA, "memset failed");
-      if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], ctx->aux_stream) != cudaSuccess)
-        rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+      KDI_CUDA(ctx, cudaMemsetAsync(job->tile_ready + job->plan.n_tiles, 0x01, sizeof(uint32_t), ctx->aux_stream));
+      KDI_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
     }
-    if (rc == KDI_OK && cudaEventRecord(e_fill, ctx->aux_stream) != cudaSuccess)
-      rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+    KDI_CUDA(ctx, cudaEventRecord(e_fill, ctx->aux_stream));
+    return KDI_OK;
+  };
+  // event mode: the rest of the dictionary starts now, beside the experimental rows and the first quarter
+  if (rc == KDI_OK && early) {
+    g1_rows = dict_rows / 4 / KDI_TILE_N * KDI_TILE_N;
+    rc = start_aux_fill();
   }
 
   // prepare_experimental - once (_dictionary_indexing.py:70)
@@ -559,6 +560,13 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   // a host dictionary is staged through the same workspace the experimental upload used
   if (rc == KDI_OK && dict_loc == KDI_HOST && exp_loc == KDI_HOST && cudaStreamSynchronize(st) != cudaSuccess)
     rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
+  // flag mode: the experimental rows (a fraction of a millisecond on their own) go first and get the
+  // whole device; the dictionary follows on the other stream, and the tensor-core launches - queued
+  // right behind the experimental rows - consume its tiles as they become ready
+  if (rc == KDI_OK && flag_mode) {
+    g1_rows = 0;
+    rc = start_aux_fill();
+  }
 
   if (rc == KDI_OK) {
     if (dict_loc == KDI_DEVICE) {

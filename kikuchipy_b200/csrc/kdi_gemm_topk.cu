@@ -400,8 +400,9 @@ int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
   auto kern = kdi_gemm_kernel<CG, KC, MODE>;
   KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // (experiments with SM sharing: see kdi_gemm_carveout_pref)
-  if (kdi_gemm_carveout_pref() >= 0)
-    KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_gemm_carveout_pref()));
+  if (kdi_gemm_carveout_pref() >= 0 || ctx->post_coresident > 0)
+    KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       ctx->post_coresident > 0 ? 100 : kdi_gemm_carveout_pref()));
   // (KDI_OPT_GEMM_SMS: leave some SMs to the HBM-bound kernels of the overlapped schedule)
   int sms = (ctx->gemm_sms > 0 && ctx->gemm_sms < ctx->sm_count) ? ctx->gemm_sms : ctx->sm_count;
   if ((stream == ctx->part_gemm[0] || stream == ctx->part_gemm[1]) && stream != nullptr && ctx->part_gemm_sms < sms)
@@ -454,6 +455,7 @@ int kdi_gemm_make_plan(kdi_ctx* ctx, int64_t M, int64_t N, int64_t kp, int keep_
   pl.cta_group = ctx->cta_group == 2 ? 2 : 1;
   pl.stages = stages_for(pl.cta_group, pl.kc, 0);
   if (ctx->max_stages > 1 && pl.stages > ctx->max_stages) pl.stages = ctx->max_stages;
+  if (ctx->post_coresident > 0 && pl.stages > 3) pl.stages -= 1;  // room for post-processing CTAs beside this kernel
   const int64_t rows_per_block = (int64_t)KDI_TILE_M * pl.cta_group;
   pl.m_blocks = (int)kdi_ceil_div(M, rows_per_block);
   pl.n_tiles = (int)kdi_ceil_div(N, KDI_TILE_N);

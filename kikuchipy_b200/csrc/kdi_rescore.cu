@@ -184,6 +184,42 @@ kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restric
   int count = 0;  // warp-uniform
   bool sorted = true;
   constexpr int kBatch = 4;
+  // Pre-pass: a lower bound on the row's KC-th best score that is much tighter than the threshold the
+  // GEMM kernel published (which only bounds the KC-th best of the best STRIP, so ~all n_strips x KC
+  // entries pass it).  Each lane keeps the KC/32 best keys of the entries it sees; the smallest of
+  // those over the lanes has at least KC entries at or above it.  With it ~4 KC entries survive the
+  // filter below instead of ~n_strips x KC, and the shared-memory buffer is sorted once.
+  {
+    constexpr int R = KC / 32;
+    uint32_t best[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) best[r] = 0u;
+    for (int64_t base = 0; base < total; base += 32 * kBatch) {
+      uint2 e[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int64_t i = base + b * 32 + lane;
+        e[b] = i < total ? __ldg(c + i) : make_uint2(0u, 0xFFFFFFFFu);
+      }
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        uint32_t k = e[b].y != 0xFFFFFFFFu ? float_key(__uint_as_float(e[b].x)) : 0u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {  // insert into the descending list
+          const uint32_t hi = k > best[r] ? k : best[r];
+          k = k > best[r] ? best[r] : k;
+          best[r] = hi;
+        }
+      }
+    }
+    uint32_t lo = best[R - 1];  // 0 when the lane saw fewer than R valid entries: no tightening then
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, lo, o);
+      lo = other < lo ? other : lo;
+    }
+    tkey = lo > tkey ? lo : tkey;
+  }
   for (int64_t base = 0; base < total; base += 32 * kBatch) {
     uint2 e[kBatch];
 #pragma unroll
@@ -608,17 +644,20 @@ int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patte
   if (n_rows < 0) n_rows = exp->rows - row0;
   if (n_rows <= 0) return KDI_OK;
   const unsigned grid = (unsigned)n_rows;
-  // (carveout preference: experiments with SM sharing, see kdi_carveout_pref)
-  static bool once = (cudaFuncSetAttribute(kdi_select_rescore_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_carveout_pref()),
-                      cudaFuncSetAttribute(kdi_select_rescore_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, kdi_carveout_pref()), true);
-  (void)once;
+  // SM sharing with the GEMM kernel (KDI_OPT_POST_CORESIDENT): same shared-memory carveout as that
+  // kernel (the split is only changed on an idle SM) and a padded footprint so that a fixed number of
+  // these CTAs fits into the stage the GEMM kernel gave up
+  const int carve = ctx->post_coresident > 0 ? 100 : kdi_carveout_pref();
+  cudaFuncSetAttribute(kdi_select_rescore_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_rescore_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  const size_t pad = kdi_post_pad_bytes(ctx, kSelBuf * 8 + 3 * plan->kc * 4 + 64);
   kdi_span span(ctx, stream, "select_rescore");
   if (plan->kc == 32)
-    kdi_select_rescore_kernel<32><<<grid, kSelThreads, 0, stream>>>(
+    kdi_select_rescore_kernel<32><<<grid, kSelThreads, pad, stream>>>(
         exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
         index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
   else if (plan->kc == 64)
-    kdi_select_rescore_kernel<64><<<grid, kSelThreads, 0, stream>>>(
+    kdi_select_rescore_kernel<64><<<grid, kSelThreads, pad, stream>>>(
         exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
         index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
   else
@@ -668,12 +707,16 @@ int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, cons
   if (n_rows < 0) n_rows = rows - row0;
   if (n_rows <= 0) return KDI_OK;
   const unsigned grid = (unsigned)kdi_ceil_div(n_rows, kWarpSelRows);
+  const int carve = ctx->post_coresident > 0 ? 100 : kdi_carveout_pref();
+  cudaFuncSetAttribute(kdi_select_warp_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_warp_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  const size_t pad = kdi_post_pad_bytes(ctx, (size_t)kWarpSelRows * kWarpBuf * 8);
   kdi_span span(ctx, stream, "select (warp per row)");
   if (plan->kc == 32)
-    kdi_select_warp_kernel<32><<<grid, 32 * kWarpSelRows, 0, stream>>>(
+    kdi_select_warp_kernel<32><<<grid, 32 * kWarpSelRows, pad, stream>>>(
         cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx);
   else if (plan->kc == 64)
-    kdi_select_warp_kernel<64><<<grid, 32 * kWarpSelRows, 0, stream>>>(
+    kdi_select_warp_kernel<64><<<grid, 32 * kWarpSelRows, pad, stream>>>(
         cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx);
   else
     return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
