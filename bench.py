@@ -18,7 +18,14 @@ constant: weak scaling in patterns/s.
             N > 1: each rank uploads its dictionary shard and 1/N of the experimental rows (the
             raw rows are all-gathered over NVLink) and rank 0 reads the result back; byte counts
             are whole-job totals.
-`roofline`: the GEMM+top-k kernel; achieved = 2*M*N_shard*S / its CUDA-event duration.
+`e2e_pageable`: the same with ordinary (pageable) NumPy arrays, what a kikuchipy user passes.
+`roofline`: the GEMM+top-k kernel; achieved = 2*M*N_shard*S / its CUDA-event duration; `frac` is
+            against the measured BURST bf16 peak, `frac_of_sustained` against the sustained one.
+`parity`  : checks of the objects the timed steps produced (structure, a 256-row sample against a
+            float64 evaluation of the whole dictionary) and the planted-best hit rate of one extra
+            step on planted patterns.
+`extra`   : the other BASELINE.json configurations that fit this run (N = 1: configs[2];
+            N = 8: configs[3] and configs[4]), timed and verified the same way on planted inputs.
 `cpu_baseline`: the NumPy oracle (the reference's own arithmetic) on the host cores, on a
             bounded sample, extrapolated linearly in the number of patterns.
 """
@@ -45,6 +52,38 @@ M_PER_GPU = 10_000
 N_DICT = 100_000
 KEEP_N = 20
 REF_CHUNK = 2083  # the reference's default dictionary chunk: 30 MB of float32 60x60 patterns
+
+
+def workload_config(m_total: int) -> dict:
+    """`config` of BOTH arms (identical strings: the driver compares them)."""
+    return {
+        "workload": f"{m_total} uint8 60x60 patterns vs {N_DICT}-entry float32 dictionary, NCC, keep_n={KEEP_N}",
+        "l2": "inputs larger than L2 (raw dictionary %.0f MB; L2 126 MB)" % (N_DICT * S * 4 / 1e6),
+    }
+
+
+_BLAS_LIMIT = None
+
+
+def blas_setup() -> dict:
+    """Give the BLAS behind NumPy every core this process may use - torchrun exports
+    OMP_NUM_THREADS=1 for nproc > 1, which would silently make the CPU arm single-threaded - and
+    report what is in effect."""
+    global _BLAS_LIMIT
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    info = {"numpy": np.__version__, "cores_available": cores,
+            "env": {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}}
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        _BLAS_LIMIT = threadpool_limits(limits=cores)  # kept alive for the life of the process
+        info["blas"] = [{k: lib.get(k) for k in ("internal_api", "version", "num_threads", "threading_layer", "architecture")}
+                        for lib in threadpool_info() if lib.get("user_api") == "blas"]
+        info["threads"] = max([lib.get("num_threads", 1) for lib in threadpool_info() if lib.get("user_api") == "blas"] or [1])
+    except Exception as e:  # noqa: BLE001
+        info["blas"] = f"threadpoolctl unavailable ({type(e).__name__}); BLAS thread count as inherited"
+        info["threads"] = cores
+    return info
 
 
 def peaks():
@@ -162,8 +201,9 @@ def host_inputs(m_sample: int, seed_exp=1, seed_dict=2):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    blas = blas_setup()
     m_total = M_PER_GPU * args.gpus
-    m_s = args.cpu_sample
+    m_s = min(args.cpu_sample, m_total)
     exp, dic = host_inputs(m_s)
     vals, detail = [], None
     for i in range(args.warmup + args.steps):
@@ -173,7 +213,6 @@ def run_reference(args, rank, world):
             vals.append((v, time.perf_counter() - t0))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([t for _, t in vals])) * 1e3
-    cores = os.cpu_count()
     sample = (f"{m_s} of {m_total} patterns x full {N_DICT}-entry dictionary in {REF_CHUNK}-row chunks per step; "
               f"matching time scaled by {m_total}/{m_s}, dictionary preparation counted once")
     line = {
@@ -181,10 +220,10 @@ def run_reference(args, rank, world):
         "value": value, "unit": "patterns/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{m_total} uint8 60x60 patterns vs {N_DICT}-entry float32 dictionary, NCC, keep_n={KEEP_N}",
-                   "note": "CPU: NumPy/BLAS restatement of the reference (kikuchipy is pure Python on dask+numpy; dask is not installable here)"},
-        "cpu_baseline": {"value": value, "unit": "patterns/s", "cores": cores, "kind": "port", "sample": sample,
-                         "detail": detail},
+        "config": workload_config(m_total),
+        "note": "CPU: NumPy/BLAS restatement of the reference (kikuchipy is pure Python on dask+numpy; dask is not installable here)",
+        "cpu_baseline": {"value": value, "unit": "patterns/s", "cores": blas["threads"], "kind": "port", "sample": sample,
+                         "detail": detail, "blas": blas},
         "e2e": {"value": value, "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -233,13 +272,18 @@ def run_ours(args, rank, world, local_rank):
     sc_dev = torch.empty((m_total, KEEP_N), dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
 
-    def step_device():
+    result = {}
+
+    def step_device(exp=None):
+        exp = exp_dev if exp is None else exp
         if world == 1:
-            ctx.dictionary_indexing(exp_dev, m_total, dict_dev, n_shard, _lib.KDI_NCC, KEEP_N,
+            ctx.dictionary_indexing(exp, m_total, dict_dev, n_shard, _lib.KDI_NCC, KEEP_N,
                                     index_offset=start, out=(idx_dev, sc_dev))
+            result["idx"], result["sc"] = idx_dev, sc_dev
         else:
-            # candidates per shard -> all-gather + merge -> owner rescoring -> all-reduce -> finalize
-            kb.dictionary_indexing_sharded(exp_dev, dict_dev, N_DICT, metric="ncc", keep_n=KEEP_N, context=ctx)
+            # candidates per shard -> exchange by row slice -> owner rescoring -> finalize -> gather
+            result["idx"], result["sc"] = kb.dictionary_indexing_sharded(exp, dict_dev, N_DICT, metric="ncc",
+                                                                     keep_n=KEEP_N, context=ctx)
         return ctx.timings()
 
     def barrier():
@@ -275,6 +319,24 @@ def run_ours(args, rank, world, local_rank):
     ms_per_step = dev_ms / args.steps
     value = m_total / (ms_per_step * 1e-3)
 
+    # ---- parity of the TIMED objects (outside the timed region) ----------------------------------
+    from tools import di_configs as dc
+
+    dictionary = dc.ShardedDictionary(N_DICT, S, world, dev, seed=2, shard_bounds=kb.shard_bounds)
+    parity = dc.structural_checks(result["idx"], result["sc"], N_DICT)
+    if rank == 0:
+        rows = torch.linspace(0, m_total - 1, 256, device=dev).long().unique()
+        parity.update(dc.float64_check(exp_dev, rows, dictionary, "ncc", KEEP_N, None, result["idx"], result["sc"]))
+    parity["flagged_rows_last_step"] = int(tms[-1]["flagged_rows"])
+    # one extra (untimed) step on PLANTED patterns of the same shape: the planted dictionary row must
+    # be the best match of every pattern
+    with torch.cuda.stream(stream):
+        planted, j = dc.planted_patterns(dictionary, dict_dev, rank, m_total)
+        step_device(planted.reshape((m_total,) + SIG))
+        torch.cuda.synchronize()
+        parity["planted_hit_rate"] = float((result["idx"][:, 0] == j).double().mean())
+        del planted
+
     # ---- end to end: pinned host inputs -> public API -> host result ----------------------
     exp_host = ctx.pinned_empty((m_total,) + SIG, np.uint8)
     dict_host = ctx.pinned_empty((n_shard,) + SIG, np.float32)
@@ -306,6 +368,29 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
+
+    # the same from ordinary (pageable) NumPy arrays - what a kikuchipy user passes
+    exp_page, dict_page = np.array(exp_host), np.array(dict_host)
+
+    def step_pageable():
+        if world == 1:
+            return kb.dictionary_indexing(exp_page, dict_page, metric="ncc", keep_n=KEEP_N, verbose=False).scores
+        i, s_ = kb.dictionary_indexing_sharded(exp_page, dict_page, N_DICT, metric="ncc", keep_n=KEEP_N, context=ctx)
+        return (i.cpu(), s_.cpu()) if rank == 0 else (i, s_)
+
+    with torch.cuda.stream(stream):
+        step_pageable()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_pageable()
+        barrier()
+        page_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
+    t = torch.tensor([page_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    page_ms = float(t.item())
+    del exp_page, dict_page
 
     # ---- end to end with the dictionary GENERATED on the device: the
     # workflow the reference runs with a lazy dictionary (get_patterns(compute=False) ->
@@ -342,6 +427,16 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gen_ms = float(t.item())
 
+    # ---- the other BASELINE.json configurations that fit this run (every rank takes part) --------
+    extra = {}
+    if not args.no_extras:
+        for number in ({1: [3], 8: [4, 5]}.get(world, [])):
+            try:
+                r = dc.run_config(number, ctx, rank, world, dev, steps=3, warmup=2, sample64=256)
+                extra[f"config{number}"] = r
+            except Exception as e:  # noqa: BLE001 - never lose the main line to an extra
+                extra[f"config{number}"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
     if rank != 0:
         return
     pk, pk_src = peaks()
@@ -353,7 +448,8 @@ def run_ours(args, rank, world, local_rank):
     g_launches = float(np.mean([x["gemm_launches"] for x in tms]))
     flops = 2.0 * m_total * n_shard * S
     achieved = flops / (g_ms * 1e-3) / 1e12
-    peak = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
+    peak = float(pk["bf16_tflops"])  # burst: the kernel runs for a few ms inside a short step
+    peak_sustained = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
@@ -366,11 +462,10 @@ def run_ours(args, rank, world, local_rank):
         "value": value, "unit": "patterns/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16" if args.compute_dtype != "bf16" else "bf16", "data": "synthetic",
-        "config": {
-            "workload": f"{m_total} uint8 60x60 patterns vs {N_DICT}-entry float32 dictionary "
-                        f"({n_shard} rows per GPU), NCC, keep_n={KEEP_N}",
+        "config": workload_config(m_total),
+        "detail": {
+            "dictionary_rows_per_gpu": n_shard,
             "operands": "16-bit tensor-core candidates (fp32 accumulate) + exact fp32 rescoring of every reported score",
-            "l2": "inputs larger than L2 (dictionary shard %.0f MB raw)" % (dict_dev.numel() * 4 / 1e6),
             "cta_group": args.cta_group or 2,
             "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None),
             "stage_ms": {k: round(float(np.mean([x[k] for x in tms])), 4)
@@ -379,15 +474,20 @@ def run_ours(args, rank, world, local_rank):
             "flagged_rows_last_step": int(last["flagged_rows"]),
         },
         "clocks": clocks,
+        "parity": parity,
         "e2e": {"value": m_total / (e2e_ms * 1e-3), "unit": "patterns/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps},
+        "e2e_pageable": {"value": m_total / (page_ms * 1e-3), "unit": "patterns/s", "ms_per_step": page_ms,
+                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+                         "note": "inputs are ordinary NumPy arrays; the library stages them through its own pinned buffers"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel": "kdi_gemm_kernel (GEMM + fused top-k)",
+                     "frac": achieved / peak, "frac_of_sustained": achieved / peak_sustained, "peak_sustained": peak_sustained,
+                     "traffic": traffic, "kernel": "kdi_gemm_kernel (GEMM + fused top-k)",
                      "ms_per_launch": g_ms / max(g_launches, 1.0), "launches_per_step": g_launches,
                      "ms_per_step": g_ms, "flops_per_step": flops,
                      "traffic_note": "DRAM bytes of the step's GEMM launches at N=1 (ncu, profiles/gemm_traffic.json)",
-                     "peak_source": f"{pk_src} bf16 sustained; burst {pk.get('bf16_tflops')}"},
+                     "peak_source": f"{pk_src}: burst bf16 peak (cuBLAS, best of 10) as the denominator of frac; sustained alongside"},
     }
     if gen_ms is not None:
         line["e2e_generated"] = {
@@ -400,14 +500,17 @@ def run_ours(args, rank, world, local_rank):
             "rank0_stage_ms": {k: round(float(gen_tm[k]), 4) for k in ("normalize_exp_ms", "normalize_dict_ms",
                                                                         "gemm_topk_ms", "rescore_ms", "total_ms")},
         }
+    if extra:
+        line["extra"] = extra
     if world == 1 and not args.no_cpu:
+        blas = blas_setup()
         exp_s = exp_host[: args.cpu_sample]
         v, detail = cpu_sample(np.array(exp_s), np.asarray(dict_host), m_total)
         line["cpu_baseline"] = {
-            "value": v, "unit": "patterns/s", "cores": os.cpu_count(), "kind": "port",
+            "value": v, "unit": "patterns/s", "cores": blas["threads"], "kind": "port",
             "sample": f"{args.cpu_sample} of {m_total} patterns x full dictionary in {REF_CHUNK}-row chunks; matching "
                       f"time scaled linearly to {m_total} patterns, dictionary preparation counted once",
-            "detail": detail,
+            "detail": detail, "blas": blas,
         }
     if world == 1 and not args.no_extras:
         try:
@@ -486,9 +589,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-sample", type=int, default=500)
+    ap.add_argument("--cpu-sample", type=int, default=2000)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the preprocessing / refinement timings")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the other BASELINE configurations and the preprocessing / refinement timings")
     ap.add_argument("--no-generated", action="store_true", help="skip the generated-dictionary end-to-end leg")
     ap.add_argument("--numa-bind", action="store_true",
                     help="bind each rank to its GPU's NUMA node (no effect on single-node-affinity boxes like this pool's)")

@@ -276,8 +276,13 @@ void launch_regs(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int
                  int bf16, float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
                  uint32_t* ready, int64_t ready_row0) {
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
-  static bool once = (prefer_max_shared(kdi_normalize_f32_regs<T, V, true>), prefer_max_shared(kdi_normalize_f32_regs<T, V, false>), true);
-  (void)once;
+  // This kernel is the one that runs BESIDE the tensor-core kernel in the flag-mode schedule.  An SM's
+  // L1 / shared-memory split is only changed while the SM is idle, and the tensor-core kernel needs
+  // the maximum shared-memory carveout: a kernel that prefers another split is not scheduled onto an
+  // SM that runs a GEMM CTA (observed on B200: the GEMM CTAs then wait for dictionary tiles that no
+  // resident CTA will ever produce).  It stages nothing in L1, so it simply asks for the same split.
+  cudaFuncSetAttribute(kdi_normalize_f32_regs<T, V, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(kdi_normalize_f32_regs<T, V, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (bf16)
     kdi_normalize_f32_regs<T, V, true><<<grid, kNormThreads, 0, stream>>>(
         src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
