@@ -206,6 +206,29 @@ int kdi_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int exp_loc,
                             const uint8_t* nav_mask, int64_t index_offset,
                             float* scores_out, int64_t* indices_out, int out_loc);
 
+/* ---- the same driver with the CALLER in charge of the dictionary chunks ----------------------------
+ * (indexing/_dictionary_indexing.py:94-128: the reference takes one chunk of n_per_iteration rows per
+ *  iteration - `dictionary[start:end]`, computed on the spot when the dictionary is lazy (:105-108) -
+ *  prepares it, matches it and merges the chunk's top-k into the running one)
+ * kdi_job_begin    prepares the experimental rows (once, :70) and allocates the resident dictionary
+ *                  of dict_rows x S; the experimental buffer is free again when the call returns.
+ * kdi_job_append   the next `rows` dictionary rows, in order (host: pinned or pageable - pageable rows
+ *                  are staged through the context's pinned ring by a few host threads; or device).
+ *                  Upload, normalise and the tensor-core pass over the completed part run behind the
+ *                  call; the chunk buffer is free again when the call returns, so the caller can
+ *                  compute / load the next chunk into it while the device works on this one.
+ * kdi_job_finish   after the last chunk: selection, exact rescoring, certificate; writes
+ *                  rows x keep_n results (indices = dictionary row + index_offset) and frees the job.
+ * The result is identical to kdi_dictionary_indexing on the concatenated chunks (the reduction does
+ * not depend on the chunking).  kdi_job_abort frees a job that will not be finished. */
+typedef struct kdi_job kdi_job;
+int kdi_job_begin(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype, int64_t exp_rows,
+                  int64_t dict_rows, int64_t S, int metric, int keep_n, const uint8_t* nav_mask,
+                  int64_t index_offset, kdi_job** out);
+int kdi_job_append(kdi_ctx* ctx, kdi_job* job, const void* chunk, int loc, int dtype, int64_t rows);
+int kdi_job_finish(kdi_ctx* ctx, kdi_job* job, float* scores_out, int64_t* indices_out, int out_loc);
+int kdi_job_abort(kdi_ctx* ctx, kdi_job* job);
+
 /* ---- the same path with the dictionary sharded over GPUs (one process / context per GPU) ------
  * (no reference equivalent: the reference loops over dictionary chunks serially,
  * indexing/_dictionary_indexing.py:94-128; this is that reduction spread over ranks)

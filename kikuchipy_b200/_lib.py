@@ -117,6 +117,10 @@ SIGNATURES = {
         _i,
         [_vp, _vp, _i, _i, _i64, _vp, _i, _i, _i64, _i64, _i, _i, _i64, _vp, _i64, _vp, _vp, _i],
     ),
+    "kdi_job_begin": (_i, [_vp, _vp, _i, _i, _i64, _i64, _i64, _i, _i, _vp, _i64, C.POINTER(_vp)]),
+    "kdi_job_append": (_i, [_vp, _vp, _vp, _i, _i, _i64]),
+    "kdi_job_finish": (_i, [_vp, _vp, _vp, _vp, _i]),
+    "kdi_job_abort": (_i, [_vp, _vp]),
     "kdi_candidate_capacity": (_i, [_i]),
     "kdi_shard_candidates": (
         _i,
@@ -319,6 +323,57 @@ class Shard:
         try:
             if self._ctx._h:
                 self.close()
+        except Exception:
+            pass
+
+
+class IndexingJob:
+    """An appendable dictionary-indexing job (``kdi_job_*`` in include/kdi.h)."""
+
+    def __init__(self, ctx: "Context", handle: int, rows: int, keep_n: int, S: int, dict_rows: int):
+        self._ctx, self._h, self.rows, self.keep_n, self.S, self.dict_rows = ctx, handle, rows, keep_n, S, dict_rows
+        self.appended = 0
+
+    def append(self, chunk):
+        """The next dictionary rows (NumPy array or CUDA tensor, ``(n, ...)`` with ``S`` values per
+        row).  The buffer may be reused as soon as the call returns."""
+        ptr, loc, code, keep = _buffer(chunk, self._ctx)
+        n = int(np.prod(chunk.shape))
+        if n % self.S:
+            raise ValueError(f"chunk of {n} values is not a whole number of {self.S}-pixel patterns")
+        try:
+            self._ctx._check(self._ctx._lib.kdi_job_append(self._ctx._h, self._h, ptr, loc, code, n // self.S))
+        except Exception:
+            self.abort()
+            raise
+        self.appended += n // self.S
+        del keep
+
+    def finish(self, out=None):
+        """``(indices, scores)``: NumPy arrays, or the CUDA tensors given in ``out``."""
+        if out is None:
+            scores = np.empty((self.rows, self.keep_n), dtype=np.float32)
+            idx = np.empty((self.rows, self.keep_n), dtype=np.int64)
+            sptr, iptr, oloc = scores.ctypes.data, idx.ctypes.data, KDI_HOST
+        else:
+            idx, scores = out
+            if hasattr(scores, "is_cuda") and scores.is_cuda:
+                sptr, iptr, oloc = scores.data_ptr(), idx.data_ptr(), KDI_DEVICE
+            else:
+                sptr, iptr, oloc = scores.ctypes.data, idx.ctypes.data, KDI_HOST
+        h, self._h = self._h, None  # the library frees the job whatever happens
+        self._ctx._check(self._ctx._lib.kdi_job_finish(self._ctx._h, h, sptr, iptr, oloc))
+        return idx, scores
+
+    def abort(self):
+        if self._h:
+            self._ctx._lib.kdi_job_abort(self._ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._ctx._h:
+                self.abort()
         except Exception:
             pass
 
@@ -600,6 +655,27 @@ class Context:
         )
         del ekeep, dkeep
         return idx, scores
+
+    def indexing_job(self, experimental, exp_rows: int, dict_rows: int, metric: int, keep_n: int,
+                     nav_mask=None, index_offset: int = 0) -> "IndexingJob":
+        """Start an appendable job (``kdi_job_begin``): the dictionary follows chunk by chunk through
+        :meth:`IndexingJob.append` - the reference's loop over ``dictionary[start:end]``
+        (``_dictionary_indexing.py:102-128``) with the device working behind the caller."""
+        eptr, eloc, ecode, ekeep = _buffer(experimental, self)
+        n_e = int(np.prod(experimental.shape))
+        if exp_rows < 1 or n_e % exp_rows:
+            raise ValueError("pattern array cannot be reshaped to (rows, -1)")
+        S = n_e // exp_rows
+        rm, kept = None, exp_rows
+        if nav_mask is not None:
+            rm = np.ascontiguousarray(np.asarray(nav_mask).ravel().astype(np.uint8))
+            kept = int((rm == 0).sum())
+        h = _vp()
+        self._check(self._lib.kdi_job_begin(
+            self._h, eptr, eloc, ecode, exp_rows, int(dict_rows), S, metric, int(keep_n),
+            rm.ctypes.data if rm is not None else None, int(index_offset), C.byref(h)))
+        del ekeep
+        return IndexingJob(self, h.value, kept, int(keep_n), S, int(dict_rows))
 
     # -- sharded dictionary: candidate pipeline (CUDA torch tensors in and out) -------------------
     def candidate_capacity(self, keep_n: int) -> int:

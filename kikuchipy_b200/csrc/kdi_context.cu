@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 namespace {
 std::mutex g_init_mutex;
@@ -68,6 +69,27 @@ static int reserve(kdi_ctx* ctx, void** p, size_t* have, size_t bytes) {
 int kdi_ws_reserve(kdi_ctx* ctx, size_t bytes) { return reserve(ctx, &ctx->ws, &ctx->ws_bytes, bytes); }
 int kdi_ws2_reserve(kdi_ctx* ctx, size_t bytes) {
   return reserve(ctx, &ctx->ws2, &ctx->ws2_bytes, bytes);
+}
+
+int kdi_ring_reserve(kdi_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ring_bytes) return KDI_OK;
+  sync_ctx_streams(ctx);
+  for (int i = 0; i < KDI_RING_SLOTS; ++i) {
+    if (ctx->ring[i]) cudaFreeHost(ctx->ring[i]);
+    ctx->ring[i] = nullptr;
+    ctx->ring_used[i] = 0;
+    if (!ctx->ring_ev[i]) KDI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+  }
+  ctx->ring_bytes = 0;
+  for (int i = 0; i < KDI_RING_SLOTS; ++i) {
+    cudaError_t e = cudaHostAlloc(&ctx->ring[i], bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return kdi_fail(ctx, KDI_ENOMEM, "pinned staging block of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+  }
+  ctx->ring_bytes = bytes;
+  return KDI_OK;
 }
 
 // ---- pooled device allocations for pattern sets -------------------------------------------
@@ -303,6 +325,7 @@ int kdi_init(int device, kdi_ctx** out) {
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   ctx->total_mem = prop.totalGlobalMem;
+  ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
   int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
   INIT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   INIT_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
@@ -315,6 +338,13 @@ int kdi_init(int device, kdi_ctx** out) {
   for (auto& ev : ctx->free_ev) INIT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 #undef INIT_CUDA
   if (const char* tl = getenv("KDI_TIMELINE")) ctx->timeline = atoi(tl);
+  {
+    // host threads for staging pageable inputs: a few are enough to outrun one PCIe link
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = hw >= 16 ? 6 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
+    if (const char* ct = getenv("KDI_COPY_THREADS")) n = atoi(ct);
+    ctx->copy_threads = n < 1 ? 1 : (n > 32 ? 32 : n);
+  }
   if (const char* pg = getenv("KDI_POST_PER_GROUP")) ctx->post_per_group = atoi(pg);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -336,6 +366,10 @@ int kdi_destroy(kdi_ctx* ctx) {
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   kdi_drop_sm_partition(ctx);
   if (ctx->h_nflag) cudaFreeHost(ctx->h_nflag);
+  for (int i = 0; i < KDI_RING_SLOTS; ++i) {
+    if (ctx->ring[i]) cudaFreeHost(ctx->ring[i]);
+    if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
+  }
   for (void* q : ctx->pinned) cudaFreeHost(q);
   ctx->pinned.clear();
   kdi_pool_trim(ctx, 0);

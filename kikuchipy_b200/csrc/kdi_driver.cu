@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <thread>
 
 namespace {
 
@@ -44,7 +45,8 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict, int keep_n,
                     float* scores_out, int64_t* indices_out, int out_loc, bool candidates_only,
                     kdi_match_job* job) {
-  if (!exp || !dict || (!candidates_only && (!scores_out || !indices_out)))
+  // (host outputs may be named later - kdi_job_finish: the results wait in the workspace)
+  if (!exp || !dict || (!candidates_only && out_loc == KDI_DEVICE && (!scores_out || !indices_out)))
     return kdi_fail(ctx, KDI_EINVAL, "kdi_match_topk: NULL argument");
   if (out_loc != KDI_HOST && out_loc != KDI_DEVICE) return kdi_fail(ctx, KDI_EINVAL, "bad output location");
   if (exp->s_eff != dict->s_eff)
@@ -279,11 +281,11 @@ int kdi_match_complete(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp
   if (M == 0) return KDI_OK;
   cudaStream_t st = ctx->stream;
   auto copy_out = [&]() -> int {
-    if (job->out_loc != KDI_HOST) return KDI_OK;
-    KDI_CUDA(ctx, cudaMemcpyAsync(job->scores_out, job->d_sc, (size_t)M * keep_n * sizeof(float),
-                                  cudaMemcpyDeviceToHost, st));
-    KDI_CUDA(ctx, cudaMemcpyAsync(job->indices_out, job->d_ix, (size_t)M * keep_n * sizeof(int64_t),
-                                  cudaMemcpyDeviceToHost, st));
+    if (job->out_loc != KDI_HOST && job->d_sc == job->scores_out) return KDI_OK;  // written in place
+    if (!job->scores_out || !job->indices_out) return kdi_fail(ctx, KDI_EINVAL, "output buffers are NULL");
+    const cudaMemcpyKind kind = job->out_loc == KDI_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    KDI_CUDA(ctx, cudaMemcpyAsync(job->scores_out, job->d_sc, (size_t)M * keep_n * sizeof(float), kind, st));
+    KDI_CUDA(ctx, cudaMemcpyAsync(job->indices_out, job->d_ix, (size_t)M * keep_n * sizeof(int64_t), kind, st));
     return KDI_OK;
   };
   int n_flag = 0;
@@ -463,6 +465,108 @@ static int fill_dict(kdi_ctx* ctx, cudaStream_t st, kdi_patterns* dict, int64_t 
                            src.dtype, n, nullptr, max_ctas, ready);
 }
 
+// ---- streaming of dictionary rows into a resident prepared set ---------------------------------
+// (the reference's loop body, _dictionary_indexing.py:105-118: take the next chunk, prepare it, match
+// it).  Host rows travel in pieces of ~64 MB through a device double buffer on the copy stream; a
+// piece is normalised as soon as it has landed and the tensor-core pass runs over the strips that
+// are complete every `group_rows` rows, while the next pieces are in flight.  Pageable host memory
+// (an ordinary NumPy array) is first copied by a few host threads into the context's pinned ring, so
+// that the DMA engine never waits for the driver's own staging of unpinned pages.
+struct kdi_stream_state {
+  int64_t rows_done = 0;
+  int64_t group_rows = 0, next_advance = 0;
+  int it = 0;       // pieces sent so far (device double buffer slot = it & 1)
+  int ring_it = 0;  // pinned-ring blocks used so far
+};
+
+static void parallel_copy(void* dst, const void* src, size_t bytes, int n_threads) {
+  if (n_threads <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t part = (bytes / n_threads + 4095) & ~(size_t)4095;
+  for (int t = 0; t < n_threads; ++t) {
+    const size_t a = (size_t)t * part;
+    if (a >= bytes) break;
+    const size_t n = std::min(part, bytes - a);
+    th.emplace_back([=] { memcpy(static_cast<uint8_t*>(dst) + a, static_cast<const uint8_t*>(src) + a, n); });
+  }
+  for (auto& t : th) t.join();
+}
+
+static int append_rows(kdi_ctx* ctx, kdi_stream_state* ss, kdi_patterns* dict, kdi_match_job* job,
+                       const kdi_patterns* exp, const void* rows_src, int loc, int dtype, int64_t n_rows) {
+  cudaStream_t st = ctx->stream;
+  const size_t row_bytes = (size_t)dict->S * kdi_dtype_size(dtype);
+  if (!row_bytes) return kdi_fail(ctx, KDI_EINVAL, "unknown dtype");
+  if (n_rows < 0 || ss->rows_done + n_rows > dict->rows)
+    return kdi_fail(ctx, KDI_EINVAL, "more dictionary rows appended (%lld) than announced (%lld)",
+                    (long long)(ss->rows_done + n_rows), (long long)dict->rows);
+  auto advance = [&]() -> int {
+    if (ss->rows_done >= ss->next_advance || ss->rows_done == dict->rows) {
+      if (ss->rows_done == dict->rows) KDI_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+      KDI_TRY(kdi_match_advance(ctx, job, exp, dict, ss->rows_done));
+      ss->next_advance = ss->rows_done + ss->group_rows;
+    }
+    return KDI_OK;
+  };
+  if (loc == KDI_DEVICE) {
+    KDI_TRY(kdi_patterns_fill(ctx, st, dict, ss->rows_done, rows_src, dtype, n_rows, nullptr));
+    KDI_CUDA(ctx, cudaEventRecord(ctx->dep_ev[61], st));  // the source buffer has been read once this has passed
+    ss->rows_done += n_rows;
+    return advance();
+  }
+  if (loc != KDI_HOST) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location %d", loc);
+  // pageable or pinned?
+  cudaPointerAttributes attr;
+  bool pageable = true;
+  if (cudaPointerGetAttributes(&attr, rows_src) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+  else cudaGetLastError();
+  int64_t piece = (int64_t)std::max<size_t>(1, (64u << 20) / row_bytes);
+  piece = std::min<int64_t>(piece, std::max<int64_t>(n_rows, 1));
+  const size_t slot_bytes = align_up((size_t)piece * row_bytes, 256);
+  if (2 * slot_bytes > ctx->ws2_bytes) {
+    // growing the staging buffer frees the old one: nothing may still be reading it
+    sync_all_streams(ctx);
+    KDI_TRY(kdi_ws2_reserve(ctx, 2 * slot_bytes));
+  }
+  if (pageable) KDI_TRY(kdi_ring_reserve(ctx, slot_bytes));
+  uint8_t* stage = reinterpret_cast<uint8_t*>(ctx->ws2);
+  const size_t stage_slot = ctx->ws2_bytes / 2 / 256 * 256;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(rows_src);
+  for (int64_t r0 = 0; r0 < n_rows; r0 += piece, ++ss->it) {
+    const int slot = ss->it & 1;
+    const int64_t nr = std::min<int64_t>(piece, n_rows - r0);
+    const size_t bytes = (size_t)nr * row_bytes;
+    const uint8_t* from = src + (size_t)r0 * row_bytes;
+    if (pageable) {
+      const int rs = ss->ring_it % KDI_RING_SLOTS;
+      // the DMA that last read this pinned block must have finished before the host overwrites it
+      if (ss->ring_it >= KDI_RING_SLOTS || ctx->ring_used[rs]) KDI_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[rs]));
+      parallel_copy(ctx->ring[rs], from, bytes, ctx->copy_threads);
+      from = static_cast<const uint8_t*>(ctx->ring[rs]);
+    }
+    // the device slot is free once the normalise that read it two pieces ago has finished
+    if (ss->it >= 2) KDI_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->free_ev[slot], 0));
+    KDI_CUDA(ctx, cudaMemcpyAsync(stage + slot * stage_slot, from, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (pageable) {
+      const int rs = ss->ring_it % KDI_RING_SLOTS;
+      KDI_CUDA(ctx, cudaEventRecord(ctx->ring_ev[rs], ctx->copy_stream));
+      ctx->ring_used[rs] = 1;
+      ++ss->ring_it;
+    }
+    KDI_CUDA(ctx, cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream));
+    KDI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->copy_ev[slot], 0));
+    ctx->tm.h2d_bytes += (int64_t)bytes;
+    KDI_TRY(kdi_patterns_fill(ctx, st, dict, ss->rows_done, stage + slot * stage_slot, dtype, nr, nullptr));
+    KDI_CUDA(ctx, cudaEventRecord(ctx->free_ev[slot], st));
+    ss->rows_done += nr;
+    KDI_TRY(advance());
+  }
+  // a pinned source is read by the DMA engine directly: the caller gets its buffer back when the
+  // last copy has left it (pageable rows were copied by the host already)
+  if (!pageable) KDI_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  return KDI_OK;
+}
+
 // prepare experimental (once) + dictionary (streamed) and run the tensor-core pass and the
 // per-row post-processing (`post`: selection + rescoring, or the selection alone).  On success
 // *exp_out / *dict_out own the prepared sets, everything has been queued and the main stream
@@ -490,8 +594,6 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   if (dict_loc != KDI_HOST && dict_loc != KDI_DEVICE) return kdi_fail(ctx, KDI_EINVAL, "bad buffer location");
   cudaStream_t st = ctx->stream;
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-  const size_t row_bytes = (size_t)S * dsz;
-
   // allocate both pattern sets first (nothing queued yet), so that every piece of work can be
   // queued where the schedule wants it
   kdi_patterns* exp = nullptr;
@@ -522,10 +624,15 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   const bool overlap_ok = rc == KDI_OK && ctx->overlap && dict_loc == KDI_DEVICE && job->fused && job->M > 0 &&
                           want_overlap(ctx, job);
   const int64_t s_eff = ctx->mask_S ? ctx->mask_kept : S;
-  const bool flag_mode = overlap_ok && ctx->dep_flags && !dsrc.mp &&
+  bool flag_mode = overlap_ok && ctx->dep_flags && !dsrc.mp &&
                          kdi_normalize_is_light(S, s_eff, false, ctx->mask_S != 0) &&
                          (dict_dtype == KDI_F32 || dict_dtype == KDI_U8) &&
                          (reinterpret_cast<uintptr_t>(dictionary) % 16) == 0;
+  if (flag_mode) {
+    // the normalise CTAs have to fit on the SMs BESIDE the GEMM CTAs (which wait for them): give up
+    // pipeline stages until a few KB of shared memory per SM are left over
+    while (job->plan.stages > 3 && kdi_gemm_free_smem(ctx, &job->plan) < 8192) job->plan.stages -= 1;
+  }
   const bool early = overlap_ok && !flag_mode &&
                      (ctx->overlap == 2 ? dict_rows >= 4 * KDI_TILE_N : (dict_rows >= 16384 && exp_rows >= 2048));
   int64_t g1_rows = dict_rows;
@@ -591,43 +698,10 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
         }
       }
     } else {
-      int64_t piece = (int64_t)std::max<size_t>(1, (64u << 20) / row_bytes);
-      piece = std::min<int64_t>(piece, dict_rows);
-      const size_t slot_bytes = align_up((size_t)piece * row_bytes, 256);
-      rc = kdi_ws2_reserve(ctx, 2 * slot_bytes);
-      uint8_t* stage = reinterpret_cast<uint8_t*>(ctx->ws2);
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(dictionary);
-      // run the tensor-core pass about 8 times over the upload (launches stay efficient)
-      const int64_t group_rows = std::max<int64_t>(dict_rows / 8, 8192);
-      int64_t next_advance = group_rows;
-      int it = 0;
-      for (int64_t r0 = 0; rc == KDI_OK && r0 < dict_rows; r0 += piece, ++it) {
-        const int slot = it & 1;
-        const int64_t nr = std::min<int64_t>(piece, dict_rows - r0);
-        cudaError_t e = cudaSuccess;
-        // the slot is free once the normalise that read it two pieces ago has finished
-        if (it >= 2) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->free_ev[slot], 0);
-        if (e == cudaSuccess)
-          e = cudaMemcpyAsync(stage + slot * slot_bytes, src + (size_t)r0 * row_bytes,
-                              (size_t)nr * row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->copy_ev[slot], 0);
-        if (e != cudaSuccess) {
-          rc = kdi_fail(ctx, KDI_ECUDA, "dictionary upload failed: %s", cudaGetErrorString(e));
-          break;
-        }
-        ctx->tm.h2d_bytes += (int64_t)nr * (int64_t)row_bytes;
-        rc = kdi_patterns_fill(ctx, st, dict, r0, stage + slot * slot_bytes, dict_dtype, nr, nullptr);
-        if (rc == KDI_OK && cudaEventRecord(ctx->free_ev[slot], st) != cudaSuccess)
-          rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
-        const int64_t ready = r0 + nr;
-        if (rc == KDI_OK && (ready >= next_advance || ready == dict_rows)) {
-          if (ready == dict_rows && cudaEventRecord(ctx->ev[7], st) != cudaSuccess)
-            rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
-          if (rc == KDI_OK) rc = kdi_match_advance(ctx, job, exp, dict, ready);
-          next_advance = ready + group_rows;
-        }
-      }
+      kdi_stream_state ss;
+      ss.group_rows = std::max<int64_t>(dict_rows / 8, 8192);  // ~8 tensor-core launches over the upload
+      ss.next_advance = ss.group_rows;
+      rc = append_rows(ctx, &ss, dict, job, exp, dictionary, KDI_HOST, dict_dtype, dict_rows);
       if (rc == KDI_OK) rc = kdi_match_select(ctx, job, exp, dict, post);
     }
   }
@@ -915,6 +989,110 @@ int kdi_orientation_similarity_map(kdi_ctx* ctx, const int64_t* indices, int64_t
                          center_index, reinterpret_cast<float*>(w + o_out)));
   KDI_CUDA(ctx, cudaMemcpyAsync(out, w + o_out, n_out * 4, cudaMemcpyDeviceToHost, st));
   KDI_CUDA(ctx, cudaStreamSynchronize(st));
+  return KDI_OK;
+}
+
+
+/* ---- appendable job: the reference's chunk loop with the caller in charge of the chunks ------------ */
+
+struct kdi_job {
+  kdi_patterns* exp = nullptr;
+  kdi_patterns* dict = nullptr;
+  kdi_match_job mj;
+  kdi_stream_state ss;
+  int64_t index_offset = 0;
+};
+
+static void job_free(kdi_ctx* ctx, kdi_job* job) {
+  if (!job) return;
+  sync_all_streams(ctx);
+  const std::string err = ctx->err;
+  kdi_patterns_destroy(ctx, job->exp);
+  kdi_patterns_destroy(ctx, job->dict);
+  ctx->err = err;
+  delete job;
+}
+
+int kdi_job_begin(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype, int64_t exp_rows,
+                  int64_t dict_rows, int64_t S, int metric, int keep_n, const uint8_t* nav_mask,
+                  int64_t index_offset, kdi_job** out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!experimental || !out) return kdi_fail(ctx, KDI_EINVAL, "kdi_job_begin: NULL argument");
+  *out = nullptr;
+  if (dict_rows < 1 || exp_rows < 0 || S < 1) return kdi_fail(ctx, KDI_EINVAL, "bad shape");
+  if (keep_n < 1 || keep_n > dict_rows)
+    return kdi_fail(ctx, KDI_EINVAL, "keep_n %d must be in [1, %lld]", keep_n, (long long)dict_rows);
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  kdi_timeline_reset(ctx);
+  cudaStream_t st = ctx->stream;
+  KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+  kdi_job* job = new kdi_job();
+  job->index_offset = index_offset;
+  kdi_fill_plan plan;
+  int rc = kdi_patterns_plan(ctx, experimental, exp_loc, exp_dtype, exp_rows, S, metric, nav_mask, &job->exp, &plan);
+  if (rc == KDI_OK) rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &job->dict);
+  if (rc == KDI_OK) rc = kdi_match_begin(ctx, job->exp, job->dict, keep_n, nullptr, nullptr, KDI_HOST, false, &job->mj);
+  if (rc == KDI_OK) rc = kdi_patterns_run_plan(ctx, st, job->exp, &plan);
+  if (rc == KDI_OK && cudaEventRecord(ctx->ev[6], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+  // the caller's experimental buffer is free again, and the staging workspace may be reused by the chunks
+  if (rc == KDI_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "experimental rows: stream sync failed");
+  if (rc != KDI_OK) { job_free(ctx, job); return rc; }
+  job->ss.group_rows = std::max<int64_t>(dict_rows / 8, 8192);
+  job->ss.next_advance = job->ss.group_rows;
+  *out = job;
+  return KDI_OK;
+}
+
+int kdi_job_append(kdi_ctx* ctx, kdi_job* job, const void* chunk, int loc, int dtype, int64_t rows) {
+  if (!ctx) return KDI_EINVAL;
+  if (!job || !chunk) return kdi_fail(ctx, KDI_EINVAL, "kdi_job_append: NULL argument");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = append_rows(ctx, &job->ss, job->dict, &job->mj, job->exp, chunk, loc, dtype, rows);
+  // a device chunk is read by the normalise kernel only: the caller may reuse it once that has run
+  // (the tensor-core pass over the completed strips keeps running)
+  if (rc == KDI_OK && loc == KDI_DEVICE && rows > 0) KDI_CUDA(ctx, cudaEventSynchronize(ctx->dep_ev[61]));
+  if (rc != KDI_OK) sync_all_streams(ctx);
+  return rc;
+}
+
+int kdi_job_finish(kdi_ctx* ctx, kdi_job* job, float* scores_out, int64_t* indices_out, int out_loc) {
+  if (!ctx) return KDI_EINVAL;
+  if (!job) return kdi_fail(ctx, KDI_EINVAL, "kdi_job_finish: NULL job");
+  int rc = KDI_OK;
+  if (!scores_out || !indices_out) rc = kdi_fail(ctx, KDI_EINVAL, "kdi_job_finish: NULL output");
+  else if (out_loc != KDI_HOST && out_loc != KDI_DEVICE) rc = kdi_fail(ctx, KDI_EINVAL, "bad output location");
+  else if (job->ss.rows_done != job->dict->rows)
+    rc = kdi_fail(ctx, KDI_EINVAL, "only %lld of the %lld announced dictionary rows were appended",
+                  (long long)job->ss.rows_done, (long long)job->dict->rows);
+  if (rc == KDI_OK) {
+    cudaSetDevice(ctx->device);
+    job->mj.scores_out = scores_out;
+    job->mj.indices_out = indices_out;
+    job->mj.out_loc = out_loc;
+    kdi_post post;
+    post.index_offset = job->index_offset;
+    rc = kdi_match_select(ctx, &job->mj, job->exp, job->dict, post);
+    if (rc == KDI_OK) rc = kdi_match_complete(ctx, &job->mj, job->exp, job->dict, job->index_offset);
+    if (rc == KDI_OK) {
+      cudaEventRecord(ctx->ev[1], ctx->stream);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
+    }
+    if (rc == KDI_OK) {
+      ctx->tm.normalize_exp_ms = ev_ms(ctx->ev[0], ctx->ev[6]);
+      ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+      kdi_timeline_print(ctx);
+    }
+  }
+  const std::string err = ctx->err;
+  job_free(ctx, job);
+  if (rc != KDI_OK) ctx->err = err;
+  return rc;
+}
+
+int kdi_job_abort(kdi_ctx* ctx, kdi_job* job) {
+  if (!ctx) return KDI_EINVAL;
+  job_free(ctx, job);
   return KDI_OK;
 }
 

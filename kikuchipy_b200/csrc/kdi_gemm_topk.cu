@@ -447,6 +447,13 @@ int kdi_gemm_kc_for(int keep_n) {
   return 0;
 }
 
+// shared memory per SM that a launch with this plan leaves to other kernels' CTAs
+int64_t kdi_gemm_free_smem(const kdi_ctx* ctx, const kdi_gemm_plan* plan) {
+  const int64_t stage = kABytes + (KDI_TILE_N / plan->cta_group) * KDI_TILE_K * 2;
+  const int64_t used = 1024 + (int64_t)plan->stages * stage + (int64_t)plan->kc * KDI_TILE_M * 8 + (2 * plan->stages + 4) * 8 + 16;
+  return (int64_t)ctx->smem_per_sm - (used + 1024);  // 1 KB per CTA is reserved by the system
+}
+
 int kdi_gemm_make_plan(kdi_ctx* ctx, int64_t M, int64_t N, int64_t kp, int keep_n,
                        kdi_gemm_plan* plan) {
   kdi_gemm_plan pl;

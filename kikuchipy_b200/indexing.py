@@ -208,8 +208,9 @@ def dictionary_indexing(
         metric, navigation_mask, signal_mask, dtype, rechunk, n_exp_all, dict_size, context
     )
     generated = isinstance(dict_data, GeneratedDictionary)
-    if hasattr(dict_data, "compute") and not generated:  # lazy (Dask) dictionary: materialise
-        dict_data = dict_data.compute()
+    # a lazy (Dask-like) dictionary is NOT materialised: it is computed chunk by chunk inside the
+    # loop, like the reference does (_dictionary_indexing.py:105-108)
+    lazy_dictionary = hasattr(dict_data, "compute") and not generated
     if hasattr(exp_data, "compute"):
         exp_data = exp_data.compute()
 
@@ -237,6 +238,24 @@ def dictionary_indexing(
             exp_data, n_exp_all, dict_data.master_pattern, dict_data.rotations, metric._kdi_metric, keep_n,
             nav_mask=metric.navigation_mask, index_offset=index_offset,
         )
+    elif isinstance(metric, _GpuMetric) and lazy_dictionary:
+        # the reference's chunk loop with the device working behind it: chunk i is uploaded, prepared
+        # and matched while the host computes chunk i + 1 (kdi_job_begin / _append / _finish)
+        ctx = metric.context
+        ctx.set_signal_mask(metric.signal_mask)
+        n_per_iteration = max(1, int(n_per_iteration))
+        job = ctx.indexing_job(exp_data, n_exp_all, dict_size, metric._kdi_metric, keep_n,
+                               nav_mask=metric.navigation_mask, index_offset=index_offset)
+        try:
+            for start in range(0, dict_size, n_per_iteration):
+                chunk = dict_data[start:start + n_per_iteration]
+                if hasattr(chunk, "compute"):
+                    chunk = chunk.compute()
+                chunk = np.asarray(chunk)
+                job.append(chunk.reshape((chunk.shape[0], -1)))
+            simulation_indices, scores = job.finish()
+        finally:
+            job.abort()  # no-op after finish()
     elif isinstance(metric, _GpuMetric):
         ctx = metric.context
         ctx.set_signal_mask(metric.signal_mask)
@@ -250,6 +269,7 @@ def dictionary_indexing(
         if generated:
             dict_data = dict_data.compute()
         simulation_indices, scores = _generic_driver(exp_data, dict_data, metric, keep_n, n_per_iteration)
+        simulation_indices = simulation_indices + index_offset if index_offset else simulation_indices
     total_time = max(time.time() - t0, 1e-12)
     if verbose:
         print(
@@ -284,7 +304,7 @@ def dictionary_indexing(
         if rot_src is not None and not _is_orix(rot_src):
             rotations = np.take(np.asarray(rot_src), simulation_indices - index_offset, axis=0)
 
-    if _is_orix(rot_src):  # pragma: no cover - orix is not installed in the build container
+    if _is_orix(rot_src):
         return _to_crystal_map(out_scores, out_idx, simulation_indices, rot_src, dict_xmap, nav_shape,
                                steps, navigation_mask, keep_n, scan_unit, index_offset)
     return DictionaryIndexingResult(out_scores, out_idx, rotations, nav_shape, steps, is_in_data,
@@ -292,14 +312,44 @@ def dictionary_indexing(
 
 
 def _generic_driver(exp_data, dict_data, metric, keep_n, n_per_iteration):
+    """The reference's driver over the three hooks of a custom ``SimilarityMetric``
+    (``_dictionary_indexing.py:66-71, 88-128, 193-201``): experimental rows prepared once, the
+    dictionary taken in chunks of ``n_per_iteration`` rows (computed on the spot when lazy), per
+    chunk ``keep_n`` clamped to the chunk length and the chunk start added to the indices, running
+    merge by ``argsort(-sign * scores)`` - so lower-is-better metrics work like in the reference."""
     dict_size = metric.n_dictionary_patterns
+    keep_n = min(int(keep_n), dict_size)
     experimental = metric.prepare_experimental(exp_data)
-    dictionary = np.asarray(dict_data).reshape((dict_size, -1))
-    simulated = metric.prepare_dictionary(dictionary)
-    sim = metric.match(experimental, simulated)
-    idx = np.asarray(sim.argtopk(keep_n, axis=-1)).reshape((-1, keep_n))
-    sc = np.asarray(sim.topk(keep_n, axis=-1)).reshape((-1, keep_n))
-    return idx, sc
+    lazy = hasattr(dict_data, "compute")
+    dictionary = dict_data if lazy else np.asarray(dict_data)
+    dictionary = dictionary.reshape((dict_size, -1))
+
+    def match_chunk(simulated, k):
+        sim = metric.match(experimental, metric.prepare_dictionary(simulated))
+        idx, sc = sim.argtopk(k, axis=-1), sim.topk(k, axis=-1)
+        idx = idx.compute() if hasattr(idx, "compute") else idx
+        sc = sc.compute() if hasattr(sc, "compute") else sc
+        return np.asarray(idx).reshape((-1, k)), np.asarray(sc).reshape((-1, k))
+
+    n_per_iteration = max(1, int(n_per_iteration))
+    if dict_size == n_per_iteration and not lazy:
+        return match_chunk(dictionary, keep_n)
+    negative_sign = -metric.sign
+    n_exp = int(experimental.shape[0])
+    indices = np.zeros((n_exp, keep_n), dtype=np.int32)
+    scores = np.full((n_exp, keep_n), negative_sign, dtype=metric.dtype)
+    for start in range(0, dict_size, n_per_iteration):
+        end = min(start + n_per_iteration, dict_size)
+        chunk = dictionary[start:end]
+        if hasattr(chunk, "compute"):
+            chunk = chunk.compute()
+        idx_i, sc_i = match_chunk(chunk, min(keep_n, end - start))
+        all_scores = np.hstack((scores, sc_i))
+        all_indices = np.hstack((indices, idx_i + start))
+        best = np.argsort(negative_sign * all_scores, axis=1)[:, :keep_n]
+        scores = np.take_along_axis(all_scores, best, axis=1)
+        indices = np.take_along_axis(all_indices, best, axis=1)
+    return indices, scores
 
 
 def _is_orix(rot) -> bool:
@@ -307,7 +357,8 @@ def _is_orix(rot) -> bool:
 
 
 def _to_crystal_map(scores, idx, idx_matched, rotations, dict_xmap, nav_shape, steps, navigation_mask,
-                    keep_n, scan_unit, index_offset):  # pragma: no cover
+                    keep_n, scan_unit, index_offset):
+    """Result assembly as an orix ``CrystalMap`` (``_dictionary_indexing.py:141-167``)."""
     from orix.crystal_map import CrystalMap, create_coordinate_arrays
     from orix.quaternion import Rotation
 

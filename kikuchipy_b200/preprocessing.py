@@ -170,18 +170,20 @@ def window_sums(nav_shape, window):
     order, truncated to integers like SciPy's integer output."""
     ny, nx = nav_shape
     wy, wx = window.shape
-    out = np.zeros(nav_shape, dtype=np.int32)
-    for y in range(ny):
-        for x in range(nx):
-            s = 0.0
-            for a in range(wy):
-                yy = y + a - wy // 2
-                if 0 <= yy < ny:
-                    for b in range(wx):
-                        if 0 <= x + b - wx // 2 < nx:
-                            s += window[a, b]
-            out[y, x] = int(s)
-    return out
+    # loop over the window taps only (C order, like SciPy's accumulation): tap (a, b) contributes to
+    # the map points whose neighbour (y + a - wy // 2, x + b - wx // 2) lies inside the map
+    acc = np.zeros((ny, nx), dtype=np.float64)
+    for a in range(wy):
+        dy = a - wy // 2
+        y0, y1 = max(0, -dy), min(ny, ny - dy)
+        if y0 >= y1:
+            continue
+        for b in range(wx):
+            dx = b - wx // 2
+            x0, x1 = max(0, -dx), min(nx, nx - dx)
+            if x0 < x1:
+                acc[y0:y1, x0:x1] += window[a, b]
+    return acc.astype(np.int32)  # truncation, like SciPy's integer output
 
 
 def average_neighbour_patterns(signal, window="circular", window_shape=(3, 3), show_progressbar=None, inplace=True,

@@ -383,7 +383,11 @@ def refine_orientation(signal, xmap, detector, master_pattern, energy=None, navi
 
     Returns a :class:`RefinementResult` (an orix ``CrystalMap`` needs orix), or with
     ``compute=False`` the raw ``(n, 5 | 6)`` array of the reference (score, evaluations, Euler
-    angles[, pseudo-symmetry index]) - already computed, the GPU call is not lazy."""
+    angles[, pseudo-symmetry index]) - already computed, the GPU call is not lazy.
+
+    Limit (all three ``refine_*`` functions): the kernel keeps the pattern and its simulation in
+    shared memory, so at most 25 600 matched pixels (e.g. 160x160 unmasked); larger patterns raise
+    ``NotImplementedError`` (``KDI_EUNSUPPORTED``) - bin them or use a signal mask."""
     opts, name = _nelder_mead_options(method, method_kwargs)
     setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context, sharded, group)
     x0, n_ps = _starts(setup, pseudo_symmetry_ops)

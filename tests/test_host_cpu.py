@@ -279,3 +279,238 @@ def test_inputs_of_neighbouring_rows_without_gpu():
         kb.refine_orientation(scan.data, res, kb.Detector((6, 5)), (np.zeros((5, 5), np.float32),) * 2)
     r = merge_maps._rotation_data(res)
     assert r.shape == (12, 2, 4) and np.all(r[..., 0] == 1) and not r[..., 1:].any()
+
+
+# ---- the reference's generic driver over custom SimilarityMetric subclasses -------------------------
+
+class _LazyArray:
+    """Minimal Dask-like array: slicing and reshape stay lazy, ``compute()`` materialises."""
+
+    def __init__(self, a, log=None):
+        self._a, self.log = a, log if log is not None else []
+        self.shape, self.chunksize = a.shape, (7,) + a.shape[1:]
+
+    def __getitem__(self, key):
+        return _LazyArray(self._a[key], self.log)
+
+    def reshape(self, shape):
+        return _LazyArray(self._a.reshape(shape), self.log)
+
+    def compute(self):
+        self.log.append(self._a.shape[0])
+        return self._a
+
+
+class _NegEuclid(kb.SimilarityMetric):
+    """Toy lower-is-better metric (mean squared difference) with NumPy hooks.  Scores stay below 1:
+    the reference initialises the running list with -sign = +1 as "worse than anything"
+    (_dictionary_indexing.py:96-99), which only holds for metrics bounded by 1."""
+
+    _allowed_dtypes = [np.float32, np.float64]
+    _sign = -1
+
+    def prepare_experimental(self, p):
+        p = np.asarray(p, self.dtype).reshape((self.n_experimental_patterns, -1))
+        return p if self.navigation_mask is None else p[~self.navigation_mask.ravel()]
+
+    def prepare_dictionary(self, p):
+        return np.asarray(p, self.dtype)
+
+    def match(self, e, d):
+        class Block:
+            def __init__(self, s):
+                self.s = s
+
+            def argtopk(self, k, axis=-1):  # Dask: negative k = the k smallest
+                return np.argsort(self.s, axis=1, kind="stable")[:, : abs(k)]
+
+            def topk(self, k, axis=-1):
+                return np.sort(self.s, axis=1, kind="stable")[:, : abs(k)]
+
+        return Block(((e[:, None, :] - d[None, :, :]) ** 2).mean(-1))
+
+
+@pytest.mark.parametrize("lazy", [False, True])
+@pytest.mark.parametrize("n_per_iteration", [None, 7, 50])
+def test_generic_driver_chunks_sign_and_lazy_dictionaries(lazy, n_per_iteration):
+    """the path for custom metrics must follow the reference loop
+    (_dictionary_indexing.py:94-128): chunking by n_per_iteration, keep_n clamped per chunk, chunk
+    offset added, merge by argsort(-sign * scores) - checked with a lower-is-better metric - and a
+    lazy dictionary computed one chunk at a time."""
+    rng = np.random.default_rng(0)
+    exp = rng.random((2, 3, 4, 5)).astype(np.float32)
+    dic = rng.random((23, 4, 5)).astype(np.float32)
+    log = []
+    d_in = _LazyArray(dic, log) if lazy else dic
+    res = kb.dictionary_indexing(exp, d_in, metric=_NegEuclid(), keep_n=9, n_per_iteration=n_per_iteration,
+                                 verbose=False)
+    ssd = ((exp.reshape(6, 1, -1) - dic.reshape(1, 23, -1)) ** 2).mean(-1)
+    want = np.argsort(ssd, axis=1, kind="stable")[:, :9]
+    assert np.array_equal(res.simulation_indices, want)
+    assert np.allclose(res.scores, np.take_along_axis(ssd, want, 1))
+    if lazy:
+        per = 7 if n_per_iteration in (None, 7) else 23  # default: the dictionary's own chunk size
+        assert log and max(log) <= per and sum(log) == 23  # never materialised in one piece
+
+
+# ---- orix / kikuchipy branches, driven through stand-in modules -------------------------------------
+
+def _install_orix_stub(monkeypatch):
+    import types
+
+    orix = types.ModuleType("orix")
+    cm = types.ModuleType("orix.crystal_map")
+    quat = types.ModuleType("orix.quaternion")
+
+    class Rotation:
+        def __init__(self, data):
+            self.data = np.array(data, dtype=float)
+
+        @classmethod
+        def identity(cls, shape):
+            d = np.zeros(tuple(np.atleast_1d(shape)) + (4,))
+            d[..., 0] = 1
+            return cls(d)
+
+        @property
+        def shape(self):
+            return self.data.shape[:-1]
+
+        def __getitem__(self, key):
+            return Rotation(self.data[key])
+
+        def __setitem__(self, key, value):
+            self.data[key] = value.data if isinstance(value, Rotation) else value
+
+        def flatten(self):
+            return Rotation(self.data.reshape(-1, 4))
+
+    Rotation.__module__ = "orix.quaternion"
+
+    class CrystalMap:
+        def __init__(self, rotations=None, phase_list=None, x=None, y=None, prop=None, is_in_data=None, **kw):
+            self.rotations, self.phases, self.x, self.y, self.prop = rotations, phase_list, x, y, prop
+            self.is_in_data = np.ones(len(x), bool) if is_in_data is None else is_in_data
+            self.scan_unit = "px"
+
+    CrystalMap.__module__ = "orix.crystal_map"
+
+    def create_coordinate_arrays(shape, step_sizes=None):
+        shape = tuple(shape) if len(shape) else (1,)
+        steps = (1,) * len(shape) if step_sizes is None else step_sizes
+        if len(shape) == 1:
+            return {"x": np.arange(shape[0]) * steps[0]}, shape[0]
+        ny, nx = shape
+        return {"x": np.tile(np.arange(nx) * steps[1], ny), "y": np.repeat(np.arange(ny) * steps[0], nx)}, ny * nx
+
+    cm.CrystalMap, cm.create_coordinate_arrays, quat.Rotation = CrystalMap, create_coordinate_arrays, Rotation
+    orix.crystal_map, orix.quaternion = cm, quat
+    for name, mod in (("orix", orix), ("orix.crystal_map", cm), ("orix.quaternion", quat)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    return Rotation, CrystalMap
+
+
+class _Axis:
+    def __init__(self, scale, units="um"):
+        self.scale, self.units = scale, units
+
+
+class _AxesManager:
+    def __init__(self, nav_shape, sig_shape, scales):
+        self.navigation_shape, self.signal_shape = tuple(nav_shape[::-1]), tuple(sig_shape[::-1])
+        self.navigation_axes = [_Axis(s) for s in scales[::-1]]
+
+
+class _Signal:
+    """What dictionary_indexing touches of a kikuchipy EBSD signal."""
+
+    def __init__(self, data, nav_dims, scales, xmap=None):
+        self.data, self.xmap = data, xmap
+        self.axes_manager = _AxesManager(data.shape[:nav_dims], data.shape[nav_dims:], scales)
+
+
+@pytest.mark.parametrize("keep_n, masked", [(3, False), (3, True), (1, True), (1, False)])
+def test_crystal_map_branch_with_orix_stand_in(monkeypatch, keep_n, masked):
+    """the CrystalMap return path (_dictionary_indexing.py:141-167) had never run.
+    With stand-in orix modules the whole branch executes: coordinate arrays, rotations gathered from
+    the dictionary's crystal map, navigation-mask scatter with identity rotations elsewhere, the
+    keep_n == 1 squeeze inside the mask branch only, phase list and scan unit."""
+    Rotation, CrystalMap = _install_orix_stub(monkeypatch)
+    rng = np.random.default_rng(1)
+    exp = rng.random((2, 3, 4, 5)).astype(np.float32)
+    dic = rng.random((11, 4, 5)).astype(np.float32)
+    q = rng.normal(size=(11, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+
+    class _Phases:
+        names = ["ni"]
+
+    class _DictMap:
+        rotations, phases, phases_in_data, shape = Rotation(q), _Phases(), "phase list of the dictionary", (11,)
+
+    nav = None
+    if masked:
+        nav = np.zeros((2, 3), bool); nav[0, 1] = nav[1, 2] = True
+    res = kb.dictionary_indexing(_Signal(exp, 2, (1.5, 0.5)), _Signal(dic, 1, (1,), _DictMap()), metric=_NegEuclid(),
+                                 keep_n=keep_n, navigation_mask=nav, verbose=False)
+    assert isinstance(res, CrystalMap) and res.phases == "phase list of the dictionary" and res.scan_unit == "um"
+    assert np.allclose(res.x, np.tile(np.arange(3) * 0.5, 2)) and np.allclose(res.y, np.repeat(np.arange(2) * 1.5, 3))
+    ssd = ((exp.reshape(6, 1, -1) - dic.reshape(1, 11, -1)) ** 2).mean(-1)
+    want = np.argsort(ssd, axis=1, kind="stable")[:, :keep_n]
+    idx = res.prop["simulation_indices"]
+    if masked:
+        keep = ~nav.ravel()
+        assert np.array_equal(res.is_in_data, keep)
+        if keep_n == 1:  # squeezed to 1-D only in this branch (:155-158)
+            assert idx.shape == (6,) and res.rotations.data.shape == (6, 4)
+            assert np.array_equal(idx[keep], want[keep, 0])
+            assert np.allclose(res.rotations.data[keep], q[want[keep, 0]])
+            assert np.allclose(res.rotations.data[~keep], [1, 0, 0, 0])
+        else:
+            assert idx.shape == (6, keep_n) and np.array_equal(idx[keep], want[keep])
+            assert np.allclose(res.rotations.data[keep], q[want[keep]])
+            assert np.allclose(res.rotations.data[~keep], [1, 0, 0, 0])
+    else:
+        assert idx.shape == (6, keep_n) and np.array_equal(idx, want)  # (M, 1) stays 2-D without a mask (:164-166)
+        assert np.allclose(res.rotations.data, q[want])
+
+
+def test_gpu_metrics_subclass_the_reference_abc(monkeypatch):
+    """Level-1 drop-in: an unmodified kikuchipy only accepts ``metric=`` instances of ITS
+    SimilarityMetric (signals/ebsd.py:3067) and then assigns sizes, masks and dtype onto them
+    (:3071-3086).  With ``kikuchipy.indexing.SimilarityMetric`` importable - the reference's own class
+    when /root/reference is mounted, else a stand-in with the same surface - the GPU metric classes must
+    be its subclasses and survive that treatment."""
+    import importlib
+    import types
+
+    from oracle import ref_loader
+
+    if ref_loader.available():
+        ref_abc = ref_loader.load_metrics()[0]
+    else:
+        ref_abc = type("SimilarityMetric", (kb.similarity_metrics._SimilarityMetricReplica,), {})
+    pkg = types.ModuleType("kikuchipy"); pkg.__path__ = []
+    indexing = types.ModuleType("kikuchipy.indexing"); indexing.__path__ = []
+    indexing.SimilarityMetric = ref_abc
+    monkeypatch.setitem(sys.modules, "kikuchipy", pkg)
+    monkeypatch.setitem(sys.modules, "kikuchipy.indexing", indexing)
+    sm = importlib.reload(kb.similarity_metrics)
+    try:
+        assert sm.SimilarityMetric is ref_abc
+        for cls in (sm.NormalizedCrossCorrelationMetric, sm.NormalizedDotProductMetric):
+            metric = cls()
+            assert isinstance(metric, ref_abc)
+            # what EBSD._prepare_metric does with a metric instance it accepted
+            metric.n_experimental_patterns, metric.n_dictionary_patterns = 6, 11
+            metric.navigation_mask = np.zeros((2, 3), bool)
+            metric.signal_mask = np.zeros((4, 5), bool)
+            metric.dtype = np.float32
+            metric.raise_error_if_invalid()
+            assert repr(metric) == (f"{cls.__name__}: float32, greater is better, rechunk: False, "
+                                    "navigation mask: True, signal mask: True")
+            metric.dtype = np.float64  # the reference allows it; the GPU classes advertise float32 only
+            with pytest.raises(ValueError, match="Data type float64 not among supported data types"):
+                metric.raise_error_if_invalid()
+    finally:
+        monkeypatch.undo()
+        importlib.reload(kb.similarity_metrics)
