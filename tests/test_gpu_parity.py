@@ -704,3 +704,86 @@ def test_reference_chunk_loop_over_plugin_hooks(ctx):
     res = kb.dictionary_indexing(exp, dic, keep_n=keep_n, n_per_iteration=n_per_iteration, navigation_mask=nav,
                                  signal_mask=sm, verbose=False)
     assert np.array_equal(res.scores, scores) and np.array_equal(res.simulation_indices, simulation_indices)
+
+
+class _LazyDictionary:
+    """Dask-like stand-in: slices stay lazy, ``compute()`` materialises and logs the chunk length."""
+
+    def __init__(self, a, log):
+        self._a, self.log = a, log
+        self.shape, self.chunksize = a.shape, (1000,) + a.shape[1:]
+
+    def __getitem__(self, key):
+        return _LazyDictionary(self._a[key], self.log)
+
+    def compute(self):
+        self.log.append(self._a.shape[0])
+        return self._a
+
+
+@pytest.mark.parametrize("n_per_iteration", [None, 700, 4096])
+def test_lazy_dictionary_is_streamed_chunk_by_chunk(ctx, n_per_iteration):
+    """A lazy dictionary is computed one chunk at a time inside the loop (the reference:
+    _dictionary_indexing.py:105-108) and fed to the appendable job (kdi_job_*); it is never
+    materialised as a whole, and the result equals the one-call driver's on the full array."""
+    exp = orc.synthetic_experimental(300, (24, 24), seed=3)
+    dic = orc.synthetic_dictionary(5000, (24, 24), seed=4)
+    log = []
+    res = kb.dictionary_indexing(exp.reshape(15, 20, 24, 24), _LazyDictionary(dic, log), keep_n=12,
+                                 n_per_iteration=n_per_iteration, verbose=False)
+    per = 1000 if n_per_iteration is None else n_per_iteration
+    assert sum(log) == 5000 and max(log) <= per and len(log) == -(-5000 // per)
+    idx, sc = ctx.dictionary_indexing(exp, 300, dic, 5000, _lib.KDI_NCC, 12)
+    assert np.array_equal(res.simulation_indices, idx) and np.array_equal(res.scores, sc)
+    ridx, rsc = orc.dictionary_indexing(exp, dic, keep_n=12, n_per_iteration=per)
+    _check(ridx, rsc, res.simulation_indices, res.scores)
+
+
+def test_job_api_chunks_devices_and_errors(ctx):
+    """kdi_job_begin / _append / _finish: ragged chunks from host (pageable and pinned) and device
+    memory, device outputs, and the error paths (too many rows, finish before the last chunk)."""
+    import torch
+
+    exp = orc.synthetic_experimental(200, (20, 20), seed=5)
+    dic = orc.synthetic_dictionary(3000, (20, 20), seed=6)
+    want_i, want_s = ctx.dictionary_indexing(exp, 200, dic, 3000, _lib.KDI_NCC, 20, index_offset=7)
+    pinned = ctx.pinned_empty((900, 20, 20), np.float32)
+    pinned[...] = dic[1100:2000]
+    job = ctx.indexing_job(exp, 200, 3000, _lib.KDI_NCC, 20, index_offset=7)
+    job.append(dic[:100])                               # pageable
+    job.append(torch.from_numpy(dic[100:1100]).cuda())  # device
+    job.append(pinned)                                  # pinned
+    job.append(dic[2000:])
+    io = torch.empty((200, 20), dtype=torch.int64, device="cuda")
+    so = torch.empty((200, 20), dtype=torch.float32, device="cuda")
+    job.finish(out=(io, so))
+    ctx.pinned_free(pinned)
+    assert np.array_equal(io.cpu().numpy(), want_i) and np.array_equal(so.cpu().numpy(), want_s)
+    job = ctx.indexing_job(exp, 200, 3000, _lib.KDI_NCC, 20)
+    job.append(dic[:2000])
+    with pytest.raises(ValueError, match="more dictionary rows appended"):
+        job.append(dic[:2000])
+    job = ctx.indexing_job(exp, 200, 3000, _lib.KDI_NCC, 20)
+    job.append(dic[:2000])
+    with pytest.raises(ValueError, match="only 2000 of the 3000 announced"):
+        job.finish()
+    # the context is still healthy
+    i2, s2 = ctx.dictionary_indexing(exp, 200, dic, 3000, _lib.KDI_NCC, 20, index_offset=7)
+    assert np.array_equal(i2, want_i) and np.array_equal(s2, want_s)
+
+
+def test_pageable_and_pinned_host_dictionaries_agree(ctx):
+    """Pageable host rows go through the library's pinned ring (host threads + DMA), pinned rows
+    straight to the DMA engine; several pieces per call (> 64 MB) and identical results."""
+    M, N, sig = 64, 12_000, (40, 40)
+    exp = orc.synthetic_experimental(M, sig, seed=7)
+    dic = orc.synthetic_dictionary(N, sig, seed=8)  # 77 MB: two pieces
+    pinned = ctx.pinned_empty(dic.shape, np.float32)
+    pinned[...] = dic
+    a = ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NDP, 5)
+    b = ctx.dictionary_indexing(exp, M, pinned, N, _lib.KDI_NDP, 5)
+    ctx.pinned_free(pinned)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert ctx.timings()["h2d_bytes"] >= dic.nbytes
+    ridx, rsc = orc.dictionary_indexing(exp, dic, metric="ndp", keep_n=5)
+    _check(ridx, rsc, a[0], a[1])
