@@ -72,7 +72,7 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
     off_flags = align_up(off_thr + job->plan.thr_bytes, 256);
     off_nflag = align_up(off_flags + (size_t)M * sizeof(int), 256);
     off_ready = off_nflag + 256;
-    total = align_up(off_ready + ((size_t)job->plan.n_tiles + 1) * sizeof(uint32_t), 256);
+    total = align_up(off_ready + ((size_t)job->plan.n_tiles + 8) * sizeof(uint32_t), 256);
     if (!candidates_only) {  // selected lists between the selection and the rescoring kernel
       off_sela = align_up(total, 256);
       off_seli = align_up(off_sela + (size_t)M * job->plan.kc * sizeof(float), 256);
@@ -97,7 +97,7 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
       job->sel_idx = reinterpret_cast<int64_t*>(ws + off_seli);
     }
     // (the flagged-row counter and the readiness counters are adjacent: one memset)
-    KDI_CUDA(ctx, cudaMemsetAsync(job->d_nflag, 0, 256 + ((size_t)job->plan.n_tiles + 1) * sizeof(uint32_t),
+    KDI_CUDA(ctx, cudaMemsetAsync(job->d_nflag, 0, 256 + ((size_t)job->plan.n_tiles + 8) * sizeof(uint32_t),
                                   ctx->stream));
     KDI_TRY(kdi_launch_cand_init(ctx, ctx->stream, job->thr, M));
   }
@@ -169,8 +169,9 @@ static void sync_all_streams(kdi_ctx* ctx) {
 // `e_fill` (may be NULL) is the event the remaining strips have to wait for.
 static int run_overlapped(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp,
                           const kdi_patterns* dict, const kdi_post& post, int strips_lo,
-                          cudaEvent_t e_fill, const uint32_t* ready = nullptr,
+                          cudaEvent_t e_fill, uint32_t* ready = nullptr,
                           cudaEvent_t e_dict_done = nullptr) {
+  job->uses_ready = ready != nullptr;
   const kdi_gemm_plan& pl = job->plan;
   cudaStream_t sm = ctx->stream, sa = ctx->post_stream ? ctx->post_stream : ctx->aux_stream;
   // GEMM streams: the context's two high-priority streams, or (SM partition) the two streams of the
@@ -294,9 +295,17 @@ int kdi_match_complete(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp
     // (the common case), a second round only for the rows the exact path has to redo
     if (!ctx->h_nflag) KDI_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_nflag), 64, cudaHostAllocDefault));
     KDI_CUDA(ctx, cudaMemcpyAsync(ctx->h_nflag, job->d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    KDI_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    ctx->h_nflag[4] = 0;
+    if (job->uses_ready)  // diagnostics of a readiness wait that timed out (kdi_gemm_topk.cu)
+      KDI_CUDA(ctx, cudaMemcpyAsync(ctx->h_nflag + 4, job->tile_ready + job->plan.n_tiles + 1, 4 * sizeof(int),
+                                    cudaMemcpyDeviceToHost, st));
     KDI_TRY(copy_out());
     KDI_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ctx->h_nflag[4] != 0)
+      return kdi_fail(ctx, KDI_EINTERNAL,
+                      "the tensor-core kernel waited in vain for dictionary tile %d (%d of %d rows ready): the "
+                      "normalise kernel did not run beside it; set KDI_OPT_DEP_FLAGS to 0", ctx->h_nflag[5],
+                      ctx->h_nflag[6], ctx->h_nflag[7]);
     n_flag = *ctx->h_nflag;
     if (n_flag > 0) {
       KDI_CUDA(ctx, cudaEventRecord(ctx->ev[10], st));

@@ -55,7 +55,9 @@ struct GemmParams {
   uint2* cand;
   uint32_t* thr;
   float* out;  // MODE 1
-  const uint32_t* ready;  // optional per-tile readiness counters of the dictionary (+ "all ready" word)
+  // optional: n_tiles readiness counters of the dictionary, word n_tiles = "all ready", words
+  // n_tiles + 1 .. + 4 = diagnostics of a wait that timed out (flag, tile, counter, needed)
+  uint32_t* ready;
 };
 
 __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
@@ -167,7 +169,17 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             all_ready = ld_acquire_gpu(p.ready + p.n_tiles) != 0u;
             if (!all_ready) {
               const int64_t left = p.N - (int64_t)nt * KDI_TILE_N;
-              wait_counter_ge(p.ready + nt, (uint32_t)(left < KDI_TILE_N ? left : KDI_TILE_N));
+              const uint32_t need = (uint32_t)(left < KDI_TILE_N ? left : KDI_TILE_N);
+              if (!wait_counter_ge(p.ready + nt, need)) {
+                // the producer kernel is not making progress (it could not get onto the device beside
+                // this kernel): report it and stop waiting - the host discards the result
+                if (atomicExch(p.ready + p.n_tiles + 1, 1u) == 0u) {
+                  p.ready[p.n_tiles + 2] = (uint32_t)nt;
+                  p.ready[p.n_tiles + 3] = ld_acquire_gpu(p.ready + nt);
+                  p.ready[p.n_tiles + 4] = need;
+                }
+                all_ready = true;
+              }
             }
             fence_proxy_async_global();
           }
@@ -528,7 +540,7 @@ static int check_operands(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patte
 int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* exp,
                          const kdi_patterns* dict, const kdi_gemm_plan* plan, int strip0,
                          int strip_count, uint2* cand, uint32_t* thr, int mb0, int mb_count,
-                         const uint32_t* ready) {
+                         uint32_t* ready) {
   if (strip0 < 0 || strip_count < 1 || strip0 + strip_count > plan->n_strips)
     return kdi_fail(ctx, KDI_EINTERNAL, "GEMM strip range out of bounds");
   if (mb_count < 0) mb_count = plan->m_blocks - mb0;

@@ -85,14 +85,15 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 __device__ __forceinline__ void fence_proxy_async_global() {
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }
-// Bounded wait until *p >= need (see mbar_wait: a protocol bug traps instead of hanging)
-__device__ __forceinline__ void wait_counter_ge(const uint32_t* p, uint32_t need) {
-  if (ld_acquire_gpu(p) >= need) return;
+// Bounded wait until *p >= need; false after ~1 s (the caller reports it instead of hanging the device)
+__device__ __forceinline__ bool wait_counter_ge(const uint32_t* p, uint32_t need) {
+  if (ld_acquire_gpu(p) >= need) return true;
   const long long t0 = clock64();
   while (ld_acquire_gpu(p) < need) {
     __nanosleep(100);
-    if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s
+    if (clock64() - t0 > 2000000000LL) return false;
   }
+  return true;
 }
 
 // ---- TMA ----------------------------------------------------------------------
