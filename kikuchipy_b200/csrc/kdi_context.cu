@@ -573,7 +573,7 @@ int kdi_patterns_fill(kdi_ctx* ctx, cudaStream_t stream, kdi_patterns* p, int64_
                               ctx->mask_S ? ctx->d_cols : nullptr, n_rows, p->s_eff, p->metric,
                               p->compute_dtype, p->a32 + row_offset * p->s_pitch, p->s_pitch,
                               reinterpret_cast<uint16_t*>(p->a16) + row_offset * p->kp, p->kp, max_ctas,
-                              ready, row_offset);
+                              ready, row_offset, (int)kdi_ceil_div(p->rows, KDI_TILE_N));
 }
 
 int kdi_patterns_plan(kdi_ctx* ctx, const void* src, int src_loc, int src_dtype, int64_t rows, int64_t S,

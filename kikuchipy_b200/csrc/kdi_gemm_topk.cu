@@ -412,9 +412,11 @@ int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
   auto kern = kdi_gemm_kernel<CG, KC, MODE>;
   KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // (experiments with SM sharing: see kdi_gemm_carveout_pref)
-  if (kdi_gemm_carveout_pref() >= 0 || ctx->post_coresident > 0)
-    KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       ctx->post_coresident > 0 ? 100 : kdi_gemm_carveout_pref()));
+  // always the full shared-memory carveout: with fewer pipeline stages the kernel would fit the
+  // 196 KB configuration, and the kernels that are meant to run beside it (flag-mode normalise,
+  // co-resident post-processing) would find only ~2 KB left on the SM
+  KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     kdi_gemm_carveout_pref() >= 0 ? kdi_gemm_carveout_pref() : 100));
   // (KDI_OPT_GEMM_SMS: leave some SMs to the HBM-bound kernels of the overlapped schedule)
   int sms = (ctx->gemm_sms > 0 && ctx->gemm_sms < ctx->sm_count) ? ctx->gemm_sms : ctx->sm_count;
   if ((stream == ctx->part_gemm[0] || stream == ctx->part_gemm[1]) && stream != nullptr && ctx->part_gemm_sms < sms)

@@ -45,6 +45,10 @@ __device__ __forceinline__ void publish_row(uint32_t* ready, int64_t grow) {
   }
 }
 
+// layout of the readiness words (kdi_gemm_topk.cu): n_tiles counters, "all ready", four diagnostic
+// words, then the work counter of the normalise kernel
+__host__ __device__ inline int kdi_ready_words_before_work(int n_tiles) { return n_tiles + 5; }
+
 template <bool BF16>
 __device__ __forceinline__ uint16_t to16(float v) {
   if constexpr (BF16) {
@@ -179,9 +183,22 @@ template <typename T, int V, bool BF16>
 __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
                        float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
-                       int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0) {
+                       int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0,
+                       int n_tiles_total) {
   __shared__ double red[kNormThreads / 32];
-  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+  __shared__ uint32_t s_next;
+  // With readiness counters the rows are handed out dynamically, in order: beside the tensor-core
+  // kernel only part of this grid is resident at any time, and a static row-to-CTA assignment would
+  // leave the rows of the CTAs that are not resident undone while the consumer waits for them.
+  uint32_t* work = ready ? ready + kdi_ready_words_before_work(n_tiles_total) : nullptr;
+  for (int64_t row = blockIdx.x;; row += gridDim.x) {
+  if (work) {
+    __syncthreads();  // everyone has read the previous value
+    if (threadIdx.x == 0) s_next = atomicAdd(work, 1u);
+    __syncthreads();
+    row = s_next;
+  }
+  if (row >= n_rows) break;
   const T* x = src + row * S;
   const int n4 = (int)(S >> 2);
   float4 r[V];
@@ -274,7 +291,7 @@ int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_
 template <typename T, int V>
 void launch_regs(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int metric,
                  int bf16, float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
-                 uint32_t* ready, int64_t ready_row0) {
+                 uint32_t* ready, int64_t ready_row0, int n_tiles_total) {
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
   // This kernel is the one that runs BESIDE the tensor-core kernel in the flag-mode schedule.  An SM's
   // L1 / shared-memory split is only changed while the SM is idle, and the tensor-core kernel needs
@@ -285,22 +302,22 @@ void launch_regs(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int
   cudaFuncSetAttribute(kdi_normalize_f32_regs<T, V, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (bf16)
     kdi_normalize_f32_regs<T, V, true><<<grid, kNormThreads, 0, stream>>>(
-        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
+        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total);
   else
     kdi_normalize_f32_regs<T, V, false><<<grid, kNormThreads, 0, stream>>>(
-        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
+        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total);
 }
 
 template <typename T>
 void launch_regs_any(cudaStream_t stream, const T* s, int64_t S, int64_t rows, int metric, int bf16,
                      float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
-                     uint32_t* ready, int64_t ready_row0) {
+                     uint32_t* ready, int64_t ready_row0, int n_tiles_total) {
   const int v = (int)kdi_ceil_div(S / 4, kNormThreads);
-  if (v <= 1) launch_regs<T, 1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
-  else if (v <= 2) launch_regs<T, 2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
-  else if (v <= 4) launch_regs<T, 4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
-  else if (v <= 8) launch_regs<T, 8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
-  else launch_regs<T, 16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
+  if (v <= 1) launch_regs<T, 1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
+  else if (v <= 2) launch_regs<T, 2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
+  else if (v <= 4) launch_regs<T, 4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
+  else if (v <= 8) launch_regs<T, 8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
+  else launch_regs<T, 16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
 }
 
 }  // namespace
@@ -314,8 +331,11 @@ bool kdi_normalize_is_light(int64_t S, int64_t s_eff, bool row_gather, bool col_
 int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int src_dtype,
                          int64_t S, const int64_t* d_rowmap, const int32_t* d_cols, int64_t rows,
                          int64_t s_eff, int metric, int compute_dtype, float* a32, int64_t s_pitch,
-                         void* a16, int64_t kp, int max_ctas, uint32_t* ready, int64_t ready_row0) {
+                         void* a16, int64_t kp, int max_ctas, uint32_t* ready, int64_t ready_row0,
+                         int n_tiles_total) {
   if (rows <= 0) return KDI_OK;
+  if (ready && ready_row0 != 0)
+    return kdi_fail(ctx, KDI_EINTERNAL, "readiness counters need the whole dictionary in one launch");
   if (rows > 0x7fffffffLL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "too many rows in one pattern set");
   // max_ctas > 0: a small resident grid that loops over the rows (runs beside the GEMM kernel)
   const unsigned grid = (unsigned)((max_ctas > 0 && rows > max_ctas) ? max_ctas : rows);
@@ -325,9 +345,9 @@ int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int
   const bool reg_path = kdi_normalize_is_light(S, s_eff, d_rowmap != nullptr, d_cols != nullptr) && s_pitch == S;
   (void)plain;
   if (src_dtype == KDI_F32 && reg_path && (reinterpret_cast<uintptr_t>(src) % 16) == 0) {
-    launch_regs_any<float>(stream, reinterpret_cast<const float*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
+    launch_regs_any<float>(stream, reinterpret_cast<const float*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
   } else if (src_dtype == KDI_U8 && reg_path && (reinterpret_cast<uintptr_t>(src) % 4) == 0) {
-    launch_regs_any<uint8_t>(stream, reinterpret_cast<const uint8_t*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0);
+    launch_regs_any<uint8_t>(stream, reinterpret_cast<const uint8_t*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
   } else {
     switch (src_dtype) {
       case KDI_U8:
