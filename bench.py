@@ -320,18 +320,18 @@ def run_ours(args, rank, world, local_rank):
     value = m_total / (ms_per_step * 1e-3)
 
     # ---- parity of the TIMED objects (outside the timed region) ----------------------------------
-    from tools import di_configs as dc
+    from tools import di_configs as cfgs
 
-    dictionary = dc.ShardedDictionary(N_DICT, S, world, dev, seed=2, shard_bounds=kb.shard_bounds)
-    parity = dc.structural_checks(result["idx"], result["sc"], N_DICT)
+    dictionary = cfgs.ShardedDictionary(N_DICT, S, world, dev, seed=2, shard_bounds=kb.shard_bounds)
+    parity = cfgs.structural_checks(result["idx"], result["sc"], N_DICT)
     if rank == 0:
         rows = torch.linspace(0, m_total - 1, 256, device=dev).long().unique()
-        parity.update(dc.float64_check(exp_dev, rows, dictionary, "ncc", KEEP_N, None, result["idx"], result["sc"]))
+        parity.update(cfgs.float64_check(exp_dev, rows, dictionary, "ncc", KEEP_N, None, result["idx"], result["sc"]))
     parity["flagged_rows_last_step"] = int(tms[-1]["flagged_rows"])
     # one extra (untimed) step on PLANTED patterns of the same shape: the planted dictionary row must
     # be the best match of every pattern
     with torch.cuda.stream(stream):
-        planted, j = dc.planted_patterns(dictionary, dict_dev, rank, m_total)
+        planted, j = cfgs.planted_patterns(dictionary, dict_dev, rank, m_total)
         step_device(planted.reshape((m_total,) + SIG))
         torch.cuda.synchronize()
         parity["planted_hit_rate"] = float((result["idx"][:, 0] == j).double().mean())
@@ -432,7 +432,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_extras:
         for number in ({1: [3], 8: [4, 5]}.get(world, [])):
             try:
-                r = dc.run_config(number, ctx, rank, world, dev, steps=3, warmup=2, sample64=256)
+                r = cfgs.run_config(number, ctx, rank, world, dev, steps=3, warmup=2, sample64=256)
                 extra[f"config{number}"] = r
             except Exception as e:  # noqa: BLE001 - never lose the main line to an extra
                 extra[f"config{number}"] = {"error": f"{type(e).__name__}: {e}"}

@@ -341,7 +341,7 @@ int kdi_init(int device, kdi_ctx** out) {
   {
     // host threads for staging pageable inputs: a few are enough to outrun one PCIe link
     unsigned hw = std::thread::hardware_concurrency();
-    int n = hw >= 16 ? 6 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
+    int n = hw >= 32 ? 12 : hw >= 16 ? 10 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
     if (const char* ct = getenv("KDI_COPY_THREADS")) n = atoi(ct);
     ctx->copy_threads = n < 1 ? 1 : (n > 32 ? 32 : n);
   }

@@ -191,60 +191,81 @@ kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
   // kernel only part of this grid is resident at any time, and a static row-to-CTA assignment would
   // leave the rows of the CTAs that are not resident undone while the consumer waits for them.
   uint32_t* work = ready ? ready + kdi_ready_words_before_work(n_tiles_total) : nullptr;
-  for (int64_t row = blockIdx.x;; row += gridDim.x) {
-  if (work) {
+  const int n4 = (int)(S >> 2);
+  auto next_row = [&](int64_t prev) -> int64_t {
+    if (!work) return prev + gridDim.x;
     __syncthreads();  // everyone has read the previous value
     if (threadIdx.x == 0) s_next = atomicAdd(work, 1u);
     __syncthreads();
-    row = s_next;
-  }
-  if (row >= n_rows) break;
-  const T* x = src + row * S;
-  const int n4 = (int)(S >> 2);
-  float4 r[V];
+    return (int64_t)s_next;
+  };
+  auto load_row = [&](float4 (&dst)[V], int64_t row) {
+    const T* x = src + row * S;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int j = threadIdx.x + i * kNormThreads;
-    r[i] = (j < n4) ? load4(x, j) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  float mean = 0.f;
-  if (metric == KDI_NCC) {
-    double s = 0.0;
-#pragma unroll
-    for (int i = 0; i < V; ++i) s += ((double)r[i].x + (double)r[i].y) + ((double)r[i].z + (double)r[i].w);
-    s = block_sum(s, red);
-    mean = (float)(s / (double)S);
-  }
-  double ss = 0.0;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int j = threadIdx.x + i * kNormThreads;
-    if (j < n4) {
-      r[i].x -= mean; r[i].y -= mean; r[i].z -= mean; r[i].w -= mean;
-      ss += ((double)r[i].x * r[i].x + (double)r[i].y * r[i].y) +
-            ((double)r[i].z * r[i].z + (double)r[i].w * r[i].w);
+    for (int i = 0; i < V; ++i) {
+      const int j = threadIdx.x + i * kNormThreads;
+      dst[i] = (j < n4) ? load4(x, j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  // Rows of up to 4096 values: the NEXT row's loads are issued before the current row is reduced and
+  // written, so a CTA always has a row in flight - with few resident CTAs (beside the GEMM kernel) the
+  // chain load -> reduce -> reduce -> store would otherwise pay the memory latency once per row.
+  constexpr bool kPrefetch = V <= 4;
+  int64_t row = work ? next_row(0) : (int64_t)blockIdx.x;
+  float4 nx[kPrefetch ? V : 1];
+  if constexpr (kPrefetch) {
+    if (row < n_rows) load_row(nx, row);
   }
-  ss = block_sum(ss, red);
-  const float norm = (float)sqrt(ss);
-  float4* o32 = reinterpret_cast<float4*>(a32 + row * s_pitch);
-  uint2* o16 = reinterpret_cast<uint2*>(a16 + row * kp);
+  while (row < n_rows) {
+    const int64_t cur = row;
+    float4 r[V];
+    if constexpr (kPrefetch) {
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int j = threadIdx.x + i * kNormThreads;
-    if (j < n4) {
-      float4 v;
-      v.x = r[i].x / norm; v.y = r[i].y / norm; v.z = r[i].z / norm; v.w = r[i].w / norm;
-      o32[j] = v;
-      uint2 h;
-      h.x = (uint32_t)to16<BF16>(v.x) | ((uint32_t)to16<BF16>(v.y) << 16);
-      h.y = (uint32_t)to16<BF16>(v.z) | ((uint32_t)to16<BF16>(v.w) << 16);
-      o16[j] = h;
+      for (int i = 0; i < V; ++i) r[i] = nx[i];
+      row = next_row(cur);
+      if (row < n_rows) load_row(nx, row);
+    } else {
+      load_row(r, cur);
     }
-  }
-  // zero the K padding of the 16-bit row (s_pitch == S here)
-  for (int64_t j = S + threadIdx.x; j < kp; j += kNormThreads) a16[row * kp + j] = 0;
-  publish_row(ready, ready_row0 + row);
+    float mean = 0.f;
+    if (metric == KDI_NCC) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < V; ++i) s += ((double)r[i].x + (double)r[i].y) + ((double)r[i].z + (double)r[i].w);
+      s = block_sum(s, red);
+      mean = (float)(s / (double)S);
+    }
+    double ss = 0.0;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int j = threadIdx.x + i * kNormThreads;
+      if (j < n4) {
+        r[i].x -= mean; r[i].y -= mean; r[i].z -= mean; r[i].w -= mean;
+        ss += ((double)r[i].x * r[i].x + (double)r[i].y * r[i].y) +
+              ((double)r[i].z * r[i].z + (double)r[i].w * r[i].w);
+      }
+    }
+    ss = block_sum(ss, red);
+    const float norm = (float)sqrt(ss);
+    float4* o32 = reinterpret_cast<float4*>(a32 + cur * s_pitch);
+    uint2* o16 = reinterpret_cast<uint2*>(a16 + cur * kp);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int j = threadIdx.x + i * kNormThreads;
+      if (j < n4) {
+        float4 v;
+        v.x = r[i].x / norm; v.y = r[i].y / norm; v.z = r[i].z / norm; v.w = r[i].w / norm;
+        o32[j] = v;
+        uint2 h;
+        h.x = (uint32_t)to16<BF16>(v.x) | ((uint32_t)to16<BF16>(v.y) << 16);
+        h.y = (uint32_t)to16<BF16>(v.z) | ((uint32_t)to16<BF16>(v.w) << 16);
+        o16[j] = h;
+      }
+    }
+    // zero the K padding of the 16-bit row (s_pitch == S here)
+    for (int64_t j = S + threadIdx.x; j < kp; j += kNormThreads) a16[cur * kp + j] = 0;
+    publish_row(ready, ready_row0 + cur);
+    if constexpr (!kPrefetch) row = next_row(cur);
   }
 }
 

@@ -19,49 +19,21 @@
 // to the true top keep_n.  Rows that fail are re-done by the exact path.
 #include "kdi_internal.cuh"
 #include "kdi_ptx.cuh"
+#include "kdi_rank.cuh"
 
 namespace {
 
 using kdi::float_key;
 using kdi::key_float;
+using kdi::key_index;
+using kdi::key_score;
+using kdi::pack_key;
+using kdi::warp_dot;
+using kdi::warp_sort_desc;
 
 constexpr int kSelThreads = 128;
 constexpr int kSelBuf = 512;  // candidate keys held in shared memory between compactions
 constexpr int kSelBatch = 8;  // candidate loads in flight per thread
-
-// dot product of two zero-padded float32 rows of n4 float4 each, by one warp.  fp32 FMAs in
-// four accumulators per lane, reduction in double.  Every exact score in the library goes
-// through this function, so the fused and the exact path agree bit for bit.
-__device__ __forceinline__ float warp_dot(const float4* __restrict__ a, const float4* __restrict__ b,
-                                          int n4, int lane) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int j = lane;
-  // four independent 16-byte loads of the dictionary row in flight per lane
-  for (; j + 96 < n4; j += 128) {
-    const float4 y0 = __ldg(b + j), y1 = __ldg(b + j + 32), y2 = __ldg(b + j + 64), y3 = __ldg(b + j + 96);
-    const float4 x0 = __ldg(a + j), x1 = __ldg(a + j + 32), x2 = __ldg(a + j + 64), x3 = __ldg(a + j + 96);
-    acc.x = fmaf(x0.x, y0.x, acc.x); acc.y = fmaf(x0.y, y0.y, acc.y);
-    acc.z = fmaf(x0.z, y0.z, acc.z); acc.w = fmaf(x0.w, y0.w, acc.w);
-    acc.x = fmaf(x1.x, y1.x, acc.x); acc.y = fmaf(x1.y, y1.y, acc.y);
-    acc.z = fmaf(x1.z, y1.z, acc.z); acc.w = fmaf(x1.w, y1.w, acc.w);
-    acc.x = fmaf(x2.x, y2.x, acc.x); acc.y = fmaf(x2.y, y2.y, acc.y);
-    acc.z = fmaf(x2.z, y2.z, acc.z); acc.w = fmaf(x2.w, y2.w, acc.w);
-    acc.x = fmaf(x3.x, y3.x, acc.x); acc.y = fmaf(x3.y, y3.y, acc.y);
-    acc.z = fmaf(x3.z, y3.z, acc.z); acc.w = fmaf(x3.w, y3.w, acc.w);
-  }
-  for (; j < n4; j += 32) {
-    const float4 x = __ldg(a + j);
-    const float4 y = __ldg(b + j);
-    acc.x = fmaf(x.x, y.x, acc.x);
-    acc.y = fmaf(x.y, y.y, acc.y);
-    acc.z = fmaf(x.z, y.z, acc.z);
-    acc.w = fmaf(x.w, y.w, acc.w);
-  }
-  double d = ((double)acc.x + (double)acc.y) + ((double)acc.z + (double)acc.w);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-  return (float)d;
-}
 
 // descending bitonic sort of n (power of two) 64-bit keys in shared memory
 template <int T>
@@ -81,12 +53,6 @@ __device__ __forceinline__ void block_sort_desc(uint64_t* keys, int n) {
   }
   __syncthreads();
 }
-
-__device__ __forceinline__ uint64_t pack_key(float score, uint32_t idx) {
-  return ((uint64_t)float_key(score) << 32) | (uint64_t)(0xFFFFFFFFu - idx);
-}
-__device__ __forceinline__ float key_score(uint64_t k) { return key_float((uint32_t)(k >> 32)); }
-__device__ __forceinline__ uint32_t key_index(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
 
 // Stream one row's candidate lists through a small shared-memory buffer: entries at or above
 // the running threshold are appended; whenever the buffer could overflow it is sorted, the kc best
@@ -150,23 +116,6 @@ __device__ __forceinline__ int select_candidates(const uint2* __restrict__ c, in
 // and the threshold is raised.  One row costs a few thousand warp instructions.
 constexpr int kWarpBuf = 256;
 constexpr int kWarpSelRows = 4;  // rows (warps) per CTA
-
-__device__ __forceinline__ void warp_sort_desc(uint64_t* keys, int n, int lane) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      __syncwarp();
-      for (int i = lane; i < n; i += 32) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t a = keys[i], b = keys[ixj];
-          const bool sw = ((i & k) == 0) ? (a < b) : (a > b);
-          if (sw) { keys[i] = b; keys[ixj] = a; }
-        }
-      }
-    }
-  }
-  __syncwarp();
-}
 
 template <int KC>
 __global__ void __launch_bounds__(32 * kWarpSelRows)
