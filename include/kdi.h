@@ -272,6 +272,38 @@ int kdi_shard_exact_rows(kdi_ctx* ctx, const kdi_shard* shard, const int* rows, 
                          int keep_n, float* scores_out, int64_t* indices_out);
 int kdi_shard_release(kdi_ctx* ctx, kdi_shard* shard);
 
+/* ---- the sharded path with the exchange INSIDE the library, over peer-mapped memory -----------------
+ * (no reference equivalent; the reduction is still _dictionary_indexing.py:94-128 spread over ranks)
+ * Each rank allocates a "symmetric block" (kdi_comm_create) and exports a CUDA IPC handle; the caller
+ * all-gathers the world x KDI_IPC_HANDLE_BYTES handles with whatever it has (torch.distributed, MPI,
+ * a file) and every rank maps the others' blocks (kdi_comm_connect).  From then on
+ * kdi_shard_run_peer performs the WHOLE job in one call, collectively on all ranks: tensor-core pass
+ * over this rank's shard -> the selection kernel stores each row's candidates into the block of the
+ * rank that owns the row's slice -> merge -> rescoring requests routed to the ranks that hold the
+ * dictionary rows -> exact scores stored back into the slice owner's table -> rank + certificate ->
+ * finished slices stored into every rank's block.  Ranks meet at device-side barriers (flag words in
+ * the blocks); nothing is packed, no collective library is called, the host does not synchronise in
+ * between.  All ranks must call with the same shapes and keep_n, in the same order.
+ *   dictionary          this rank's rows [start, end) of the balanced contiguous split of dict_total
+ *                       rows over `world` ranks (the first dict_total % world ranks hold one more)
+ *   scores_out / indices_out  DEVICE, kept rows x keep_n: the complete result, identical on every rank
+ *   flags_out           DEVICE, capacity kept rows: rows whose certificate failed on their slice owner
+ *                       (the same list on every rank); *n_flag_out (host) their number.  The caller
+ *                       finishes them with kdi_shard_exact_rows on every rank + a merge.
+ *   *out                keeps the prepared sets alive for that (kdi_shard_release).
+ * kdi_comm_bytes_needed: size of the symmetric block for a job shape (kc = kdi_candidate_capacity). */
+#define KDI_IPC_HANDLE_BYTES 64
+typedef struct kdi_comm kdi_comm;
+int64_t kdi_comm_bytes_needed(int world, int64_t rows, int kc, int keep_n);
+int kdi_comm_create(kdi_ctx* ctx, int rank, int world, int64_t bytes, kdi_comm** out, uint8_t* handle_out);
+int kdi_comm_connect(kdi_ctx* ctx, kdi_comm* comm, const uint8_t* handles);
+int kdi_comm_info(const kdi_comm* comm, int* rank, int* world, int64_t* bytes);
+int kdi_comm_destroy(kdi_ctx* ctx, kdi_comm* comm);
+int kdi_shard_run_peer(kdi_ctx* ctx, kdi_comm* comm, const void* experimental, int exp_loc, int exp_dtype,
+                       int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype, int64_t dict_rows,
+                       int64_t S, int metric, int keep_n, const uint8_t* nav_mask, int64_t dict_total,
+                       float* scores_out, int64_t* indices_out, int* flags_out, int* n_flag_out, kdi_shard** out);
+
 /* ---- dictionary generation on the device (next row of the path: SURVEY.md section 8f.1) ---------
  * (signals/ebsd_master_pattern.py:97-329 EBSDMasterPattern.get_patterns with a fixed projection
  *  centre; signals/util/_master_pattern.py:299-370 _project_patterns_from_master_pattern_with_
@@ -322,6 +354,12 @@ int kdi_shard_candidates_projected(kdi_ctx* ctx, const void* experimental, int e
                                    int metric, int keep_n, const uint8_t* nav_mask,
                                    int64_t index_offset, float* approx_out, int64_t* gidx_out,
                                    kdi_shard** out);
+/* kdi_shard_run_peer with this rank's dictionary rows generated from its rotations */
+int kdi_shard_run_peer_projected(kdi_ctx* ctx, kdi_comm* comm, const void* experimental, int exp_loc, int exp_dtype,
+                                 int64_t exp_rows, int64_t S, const kdi_master_pattern* mp, const double* rotations,
+                                 int rot_loc, int64_t n_rotations, int metric, int keep_n, const uint8_t* nav_mask,
+                                 int64_t dict_total, float* scores_out, int64_t* indices_out, int* flags_out,
+                                 int* n_flag_out, kdi_shard** out);
 
 /* ---- orientation similarity map --------------------------------------------
  * (indexing/_orientation_similarity_map.py:30-152)

@@ -130,6 +130,17 @@ SIGNATURES = {
     "kdi_shard_finalize": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, C.POINTER(_i)]),
     "kdi_shard_exact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "kdi_shard_release": (_i, [_vp, _vp]),
+    "kdi_comm_bytes_needed": (_i64, [_i, _i64, _i, _i]),
+    "kdi_comm_create": (_i, [_vp, _i, _i, _i64, C.POINTER(_vp), _vp]),
+    "kdi_comm_connect": (_i, [_vp, _vp, _vp]),
+    "kdi_comm_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), _i64p]),
+    "kdi_comm_destroy": (_i, [_vp, _vp]),
+    "kdi_shard_run_peer": (
+        _i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _i, _i, _i64, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp,
+             C.POINTER(_i), C.POINTER(_vp)]),
+    "kdi_shard_run_peer_projected": (
+        _i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _i, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp,
+             C.POINTER(_i), C.POINTER(_vp)]),
     "kdi_master_pattern_create": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _i64, C.c_double, _i, C.c_double,
                                        C.c_double, C.POINTER(_vp)]),
     "kdi_master_pattern_destroy": (_i, [_vp, _vp]),
@@ -317,6 +328,40 @@ class Shard:
     def close(self):
         if self._h:
             self._ctx._lib.kdi_shard_release(self._ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+
+IPC_HANDLE_BYTES = 64
+
+
+class PeerComm:
+    """This rank's symmetric block + the mapped blocks of the other ranks (``kdi_comm`` in
+    include/kdi.h): the memory the sharded pipeline exchanges its lists through."""
+
+    def __init__(self, ctx: "Context", rank: int, world: int, nbytes: int):
+        self._ctx, self.rank, self.world, self.nbytes = ctx, rank, world, int(nbytes)
+        h = _vp()
+        self.handle = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        ctx._check(ctx._lib.kdi_comm_create(ctx._h, rank, world, int(nbytes), C.byref(h), self.handle))
+        self._h = h.value
+
+    def connect(self, handles: bytes):
+        """``handles``: the ``world`` handles (64 bytes each) in rank order."""
+        if len(handles) != self.world * IPC_HANDLE_BYTES:
+            raise ValueError("one IPC handle per rank is needed")
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._ctx._check(self._ctx._lib.kdi_comm_connect(self._ctx._h, self._h, buf))
+
+    def close(self):
+        if self._h:
+            self._ctx._lib.kdi_comm_destroy(self._ctx._h, self._h)
             self._h = None
 
     def __del__(self):
@@ -722,6 +767,62 @@ class Context:
         )
         del ekeep, dkeep
         return Shard(self, h.value, kept, kc), approx, gidx
+
+    def comm_bytes_needed(self, world: int, rows: int, keep_n: int) -> int:
+        kc = self.candidate_capacity(keep_n)
+        if kc == 0:
+            raise NotImplementedError(f"keep_n {keep_n} too large for the candidate pipeline")
+        n = int(self._lib.kdi_comm_bytes_needed(int(world), int(rows), kc, int(keep_n)))
+        if n < 0:
+            raise ValueError("bad shape for the peer exchange")
+        return n
+
+    def shard_run_peer(self, comm: PeerComm, experimental, exp_rows, dictionary, dict_rows, metric, keep_n,
+                       dict_total, nav_mask=None):
+        """The whole sharded job with the exchange over peer-mapped memory (``kdi_shard_run_peer``;
+        collective: every rank calls it with the same shapes).  ``dictionary``: this rank's rows (array
+        / CUDA tensor), or a ``(master pattern, rotations)`` pair for a generated shard.  Returns
+        ``(shard, indices, scores, flagged rows)`` - CUDA tensors, complete and identical on every rank."""
+        import torch
+
+        eptr, eloc, ecode, ekeep = _buffer(experimental, self)
+        n_e = int(np.prod(experimental.shape))
+        if exp_rows < 1 or n_e % exp_rows:
+            raise ValueError("pattern arrays cannot be reshaped to (rows, -1)")
+        S = n_e // exp_rows
+        rm, kept = None, exp_rows
+        if nav_mask is not None:
+            rm = np.ascontiguousarray(np.asarray(nav_mask).ravel().astype(np.uint8))
+            kept = int((rm == 0).sum())
+        dev = torch.device("cuda", self.device)
+        scores = torch.empty((kept, keep_n), dtype=torch.float32, device=dev)
+        idx = torch.empty((kept, keep_n), dtype=torch.int64, device=dev)
+        flags = torch.empty((max(kept, 1),), dtype=torch.int32, device=dev)
+        n_flag = C.c_int(0)
+        h = _vp()
+        self._stream_sync(dev)
+        rmp = rm.ctypes.data if rm is not None else None
+        if isinstance(dictionary, tuple):
+            mp, rotations = dictionary
+            rptr, rloc, rkeep, n = _rotations(rotations)
+            if rloc == KDI_DEVICE:
+                self._stream_sync(rkeep.device)
+            self._check(self._lib.kdi_shard_run_peer_projected(
+                self._h, comm._h, eptr, eloc, ecode, exp_rows, S, mp._h, rptr, rloc, n, metric, int(keep_n), rmp,
+                int(dict_total), scores.data_ptr(), idx.data_ptr(), flags.data_ptr(), C.byref(n_flag), C.byref(h)))
+            del rkeep
+        else:
+            dptr, dloc, dcode, dkeep = _buffer(dictionary, self)
+            n_d = int(np.prod(dictionary.shape))
+            if dict_rows < 1 or n_d % dict_rows or n_d // dict_rows != S:
+                raise ValueError(f"Experimental ({S}) and dictionary signal sizes must be identical")
+            self._check(self._lib.kdi_shard_run_peer(
+                self._h, comm._h, eptr, eloc, ecode, exp_rows, dptr, dloc, dcode, dict_rows, S, metric, int(keep_n), rmp,
+                int(dict_total), scores.data_ptr(), idx.data_ptr(), flags.data_ptr(), C.byref(n_flag), C.byref(h)))
+            del dkeep
+        del ekeep
+        kc = self.candidate_capacity(keep_n)
+        return Shard(self, h.value, kept, kc), idx, scores, flags[: n_flag.value]
 
     # -- dictionary generation -------------------------------------------------------------------
     def master_pattern(self, upper, lower, direction_cosines, scale=None, rescale=False, out_min=-1.0,

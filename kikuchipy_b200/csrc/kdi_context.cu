@@ -33,7 +33,7 @@ int kdi_fail(kdi_ctx* ctx, int code, const char* fmt, ...) {
 }
 
 static void sync_ctx_streams(kdi_ctx* ctx) {
-  cudaStream_t all[] = {ctx->stream, ctx->copy_stream, ctx->gemm_stream2, ctx->aux_stream, ctx->post_stream,
+  cudaStream_t all[] = {ctx->stream, ctx->copy_stream, ctx->gemm_stream2, ctx->aux_stream, ctx->fill_stream, ctx->post_stream,
                         ctx->part_gemm[0], ctx->part_gemm[1]};
   for (cudaStream_t s : all)
     if (s) cudaStreamSynchronize(s);
@@ -182,7 +182,7 @@ kdi_span::kdi_span(kdi_ctx* c, cudaStream_t s, const char* name) : ctx(c), strea
   cudaEvent_t a = span_event(c);
   b = span_event(c);
   cudaEventRecord(a, s);
-  const int sid = s == c->stream ? 0 : s == c->gemm_stream2 ? 1 : s == c->aux_stream ? 2 : 3;
+  const int sid = s == c->stream ? 0 : s == c->gemm_stream2 ? 1 : s == c->aux_stream ? 2 : s == c->fill_stream ? 4 : 3;
   c->spans.push_back({name, sid, a, b});
 }
 kdi_span::~kdi_span() {
@@ -194,7 +194,7 @@ void kdi_timeline_reset(kdi_ctx* ctx) {
 }
 void kdi_timeline_print(kdi_ctx* ctx) {
   if (!ctx->timeline || ctx->spans.empty()) return;
-  static const char* names[] = {"main", "gemm2", "aux", "copy"};
+  static const char* names[] = {"main", "gemm2", "aux", "other", "fill"};
   cudaDeviceSynchronize();
   fprintf(stderr, "[kdi timeline] (ms from the first launch; start = stream reached the launch, end = kernel done)\n");
   for (const auto& sp : ctx->spans) {
@@ -275,8 +275,9 @@ int kdi_setup_sm_partition(kdi_ctx* ctx, int n_small) {
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   CUstream s_post = nullptr, s_g0 = nullptr, s_g1 = nullptr;
   if (r == CUDA_SUCCESS) r = stream_create(&s_post, g_small, CU_STREAM_NON_BLOCKING, prio_hi);
-  if (r == CUDA_SUCCESS) r = stream_create(&s_g0, g_rest, CU_STREAM_NON_BLOCKING, prio_hi);
-  if (r == CUDA_SUCCESS) r = stream_create(&s_g1, g_rest, CU_STREAM_NON_BLOCKING, prio_hi);
+  const int prio_gemm = prio_hi < prio_lo ? prio_hi + 1 : prio_hi;
+  if (r == CUDA_SUCCESS) r = stream_create(&s_g0, g_rest, CU_STREAM_NON_BLOCKING, prio_gemm);
+  if (r == CUDA_SUCCESS) r = stream_create(&s_g1, g_rest, CU_STREAM_NON_BLOCKING, prio_gemm);
   ctx->post_stream = reinterpret_cast<cudaStream_t>(s_post);
   ctx->part_gemm[0] = reinterpret_cast<cudaStream_t>(s_g0);
   ctx->part_gemm[1] = reinterpret_cast<cudaStream_t>(s_g1);
@@ -328,8 +329,17 @@ int kdi_init(int device, kdi_ctx** out) {
   ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
   int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
   INIT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  INIT_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
-  INIT_CUDA(cudaStreamCreateWithPriority(&ctx->gemm_stream2, cudaStreamNonBlocking, prio_hi));
+  // Priorities.  The block scheduler serves pending CTAs strictly by priority: while CTAs of a
+  // higher-priority launch are pending - even if they cannot be placed because no SM has the shared
+  // memory for them - CTAs of lower-priority launches are not started.  The kernel that FEEDS the
+  // tensor-core launches in the flag-mode schedule (dictionary normalise, consumed tile by tile by
+  // GEMM CTAs that wait for it) therefore needs a stream of its own ABOVE the GEMM streams: with the
+  // priorities the other way round, a second GEMM launch that is queued behind the first one starves
+  // the producer the first one is waiting for (observed on B200 as a timing-dependent stall).
+  const int prio_gemm = prio_hi < prio_lo ? prio_hi + 1 : prio_hi;
+  INIT_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_gemm));
+  INIT_CUDA(cudaStreamCreateWithPriority(&ctx->gemm_stream2, cudaStreamNonBlocking, prio_gemm));
+  INIT_CUDA(cudaStreamCreateWithPriority(&ctx->fill_stream, cudaStreamNonBlocking, prio_hi));
   INIT_CUDA(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_lo));
   INIT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->dep_ev) INIT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -364,6 +374,7 @@ int kdi_destroy(kdi_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->gemm_stream2) cudaStreamSynchronize(ctx->gemm_stream2);
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+  if (ctx->fill_stream) { cudaStreamSynchronize(ctx->fill_stream); cudaStreamDestroy(ctx->fill_stream); }
   kdi_drop_sm_partition(ctx);
   if (ctx->h_nflag) cudaFreeHost(ctx->h_nflag);
   for (int i = 0; i < KDI_RING_SLOTS; ++i) {

@@ -127,6 +127,7 @@ struct kdi_post {
   int64_t index_offset = 0;
   float* approx_out = nullptr;   // candidates_only
   int64_t* gidx_out = nullptr;   // candidates_only
+  kdi_route route;               // candidates_only: lists go to the slice owners' symmetric blocks instead
 };
 
 static int launch_post(kdi_ctx* ctx, cudaStream_t st, kdi_match_job* job, const kdi_patterns* exp,
@@ -134,7 +135,7 @@ static int launch_post(kdi_ctx* ctx, cudaStream_t st, kdi_match_job* job, const 
   const float inv = 1.0f / (KDI_OP_SCALE * KDI_OP_SCALE);
   if (post.candidates_only)
     return kdi_launch_select_only(ctx, st, exp->rows, &job->plan, job->cand, job->thr, post.index_offset, inv,
-                                  post.approx_out, post.gidx_out, row0, n_rows);
+                                  post.approx_out, post.gidx_out, row0, n_rows, post.route.world > 0 ? &post.route : nullptr);
   // selection (warp per row, local indices) -> lists -> exact rescoring + ranking + certificate
   if (ctx->split_select) {
     KDI_TRY(kdi_launch_select_only(ctx, st, exp->rows, &job->plan, job->cand, job->thr, 0, inv, job->sel_approx,
@@ -153,6 +154,23 @@ static void sync_all_streams(kdi_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->gemm_stream2);
   cudaStreamSynchronize(ctx->aux_stream);
+  cudaStreamSynchronize(ctx->fill_stream);
+  if (ctx->post_stream) cudaStreamSynchronize(ctx->post_stream);
+  if (ctx->part_gemm[0]) cudaStreamSynchronize(ctx->part_gemm[0]);
+  if (ctx->part_gemm[1]) cudaStreamSynchronize(ctx->part_gemm[1]);
+}
+
+// Did a tensor-core launch of this job give up waiting for the dictionary (flag mode)?  Call after the
+// main stream has been synchronised with the words copied to ctx->h_nflag[4..7].  The job's results
+// are then invalid; the caller redoes the call with stream events (and the context stays that way).
+static int ready_wait_failed(kdi_ctx* ctx) {
+  if (ctx->h_nflag == nullptr || ctx->h_nflag[4] == 0) return KDI_OK;
+  ctx->dep_flags = 0;
+  ctx->flag_fallbacks++;
+  kdi_fail(ctx, KDI_EINTERNAL,
+           "the tensor-core kernel waited in vain for dictionary tile %d (%d of %d rows ready): the normalise "
+           "kernel did not run beside it", ctx->h_nflag[5], ctx->h_nflag[6], ctx->h_nflag[7]);
+  return KDI_ERETRY_EVENTS;
 }
 
 // Overlapped schedule of a device-resident job (fused path).  The tensor-core launches go to the
@@ -301,11 +319,7 @@ int kdi_match_complete(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp
                                     cudaMemcpyDeviceToHost, st));
     KDI_TRY(copy_out());
     KDI_CUDA(ctx, cudaStreamSynchronize(st));
-    if (ctx->h_nflag[4] != 0)
-      return kdi_fail(ctx, KDI_EINTERNAL,
-                      "the tensor-core kernel waited in vain for dictionary tile %d (%d of %d rows ready): the "
-                      "normalise kernel did not run beside it; set KDI_OPT_DEP_FLAGS to 0", ctx->h_nflag[5],
-                      ctx->h_nflag[6], ctx->h_nflag[7]);
+    KDI_TRY(ready_wait_failed(ctx));
     n_flag = *ctx->h_nflag;
     if (n_flag > 0) {
       KDI_CUDA(ctx, cudaEventRecord(ctx->ev[10], st));
@@ -650,18 +664,21 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   auto start_aux_fill = [&]() -> int {
     cudaEvent_t e0 = ctx->dep_ev[63];
     e_fill = ctx->dep_ev[62];
+    // flag mode: the stream ABOVE the GEMM streams (see kdi_init), and two CTAs per SM - their registers
+    // and the GEMM CTA's have to fit on an SM together; event mode: the low-priority stream
+    cudaStream_t sf = flag_mode ? ctx->fill_stream : ctx->aux_stream;
     // the caller's buffers may have been produced on the main stream; the counters were reset on it
     cudaError_t e = cudaEventRecord(e0, st);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, e0, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(sf, e0, 0);
     if (e != cudaSuccess) return kdi_fail(ctx, KDI_ECUDA, "stream setup failed: %s", cudaGetErrorString(e));
-    KDI_TRY(fill_dict(ctx, ctx->aux_stream, dict, g1_rows, dict_rows - g1_rows, dsrc, S, 4 * ctx->sm_count,
+    KDI_TRY(fill_dict(ctx, sf, dict, g1_rows, dict_rows - g1_rows, dsrc, S, (flag_mode ? 2 : 4) * ctx->sm_count,
                       flag_mode ? job->tile_ready : nullptr));
     if (flag_mode) {
       // "everything is ready": the producers stop polling once they have seen this word
-      KDI_CUDA(ctx, cudaMemsetAsync(job->tile_ready + job->plan.n_tiles, 0x01, sizeof(uint32_t), ctx->aux_stream));
-      KDI_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
+      KDI_CUDA(ctx, cudaMemsetAsync(job->tile_ready + job->plan.n_tiles, 0x01, sizeof(uint32_t), sf));
+      KDI_CUDA(ctx, cudaEventRecord(ctx->ev[7], sf));
     }
-    KDI_CUDA(ctx, cudaEventRecord(e_fill, ctx->aux_stream));
+    KDI_CUDA(ctx, cudaEventRecord(e_fill, sf));
     return KDI_OK;
   };
   // event mode: the rest of the dictionary starts now, beside the experimental rows and the first quarter
@@ -743,10 +760,21 @@ static int run_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int e
   kdi_match_job job;
   kdi_post post;
   post.index_offset = index_offset;
-  KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric, keep_n,
-                            nav_mask, scores_out, indices_out, out_loc, post, &job, &exp, &dict));
   cudaStream_t st = ctx->stream;
-  int rc = kdi_match_complete(ctx, &job, exp, dict, index_offset);
+  int rc = KDI_OK;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric, keep_n,
+                              nav_mask, scores_out, indices_out, out_loc, post, &job, &exp, &dict));
+    rc = kdi_match_complete(ctx, &job, exp, dict, index_offset);
+    if (rc != KDI_ERETRY_EVENTS) break;
+    // a readiness wait timed out (the producer kernel did not get onto the device beside the GEMM
+    // kernel): the context has switched to stream events; redo the call once
+    sync_all_streams(ctx);
+    kdi_patterns_destroy(ctx, exp);
+    kdi_patterns_destroy(ctx, dict);
+    exp = dict = nullptr;
+    rc = KDI_EINTERNAL;
+  }
   if (rc == KDI_OK) {
     cudaEventRecord(ctx->ev[1], st);
     if (cudaStreamSynchronize(st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
@@ -766,6 +794,18 @@ static int run_dictionary_indexing(kdi_ctx* ctx, const void* experimental, int e
   return rc;
 }
 
+// stage 1 of a sharded job has been queued: wait for it and find out whether a readiness wait failed
+static int finish_stage1(kdi_ctx* ctx, kdi_match_job* job) {
+  cudaStream_t st = ctx->stream;
+  if (!ctx->h_nflag) KDI_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_nflag), 64, cudaHostAllocDefault));
+  ctx->h_nflag[4] = 0;
+  if (job->uses_ready && job->M > 0)
+    KDI_CUDA(ctx, cudaMemcpyAsync(ctx->h_nflag + 4, job->tile_ready + job->plan.n_tiles + 1, 4 * sizeof(int),
+                                  cudaMemcpyDeviceToHost, st));
+  KDI_CUDA(ctx, cudaStreamSynchronize(st));
+  return ready_wait_failed(ctx);
+}
+
 // stage 1 of the sharded pipeline for any dictionary source
 static int run_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
                                 int64_t exp_rows, const kdi_dict_source& dsrc, int64_t dict_rows, int64_t S,
@@ -780,14 +820,23 @@ static int run_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_
   post.index_offset = index_offset;
   post.approx_out = approx_out;
   post.gidx_out = gidx_out;
-  KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric, keep_n,
-                            nav_mask, nullptr, nullptr, KDI_DEVICE, post, &job, &exp, &dict));
   cudaStream_t st = ctx->stream;
   int rc = KDI_OK;
-  if (job.M > 0 && job.plan.kc != kc) rc = kdi_fail(ctx, KDI_EINTERNAL, "candidate capacity mismatch");
-  cudaEventRecord(ctx->ev[1], st);
-  if (cudaStreamSynchronize(st) != cudaSuccess && rc == KDI_OK) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed");
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric, keep_n,
+                              nav_mask, nullptr, nullptr, KDI_DEVICE, post, &job, &exp, &dict));
+    cudaEventRecord(ctx->ev[1], st);
+    rc = finish_stage1(ctx, &job);
+    if (rc != KDI_ERETRY_EVENTS) break;
+    sync_all_streams(ctx);
+    kdi_patterns_destroy(ctx, exp);
+    kdi_patterns_destroy(ctx, dict);
+    exp = dict = nullptr;
+    rc = KDI_EINTERNAL;
+  }
+  if (rc == KDI_OK && job.M > 0 && job.plan.kc != kc) rc = kdi_fail(ctx, KDI_EINTERNAL, "candidate capacity mismatch");
   if (rc != KDI_OK) {
+    sync_all_streams(ctx);
     const std::string err = ctx->err;
     kdi_patterns_destroy(ctx, exp);
     kdi_patterns_destroy(ctx, dict);
@@ -805,6 +854,104 @@ static int run_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_
   sh->dict = dict;
   sh->kc = kc;
   sh->index_offset = index_offset;
+  *out = sh;
+  return KDI_OK;
+}
+
+// the whole sharded job with the exchange over peer-mapped memory (kdi_comm.cu)
+static int run_shard_peer(kdi_ctx* ctx, kdi_comm* comm, const void* experimental, int exp_loc, int exp_dtype,
+                          int64_t exp_rows, const kdi_dict_source& dsrc, int64_t dict_rows, int64_t S, int metric,
+                          int keep_n, const uint8_t* nav_mask, int64_t dict_total, float* scores_out,
+                          int64_t* indices_out, int* flags_out, int* n_flag_out, kdi_shard** out) {
+  *out = nullptr;
+  *n_flag_out = 0;
+  const int kc = kdi_gemm_kc_for(keep_n);
+  if (kc == 0) return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d too large for the candidate pipeline", keep_n);
+  int rank = 0, world = 1;
+  int64_t comm_bytes = 0;
+  kdi_comm_info(comm, &rank, &world, &comm_bytes);
+  if (dict_total < 1 || keep_n > dict_total)
+    return kdi_fail(ctx, KDI_EINVAL, "keep_n %d must be in [1, %lld]", keep_n, (long long)dict_total);
+  const int64_t base = dict_total / world, extra = dict_total % world;
+  const int64_t start = (int64_t)rank * base + std::min<int64_t>(rank, extra);
+  if (dict_rows != base + (rank < extra ? 1 : 0))
+    return kdi_fail(ctx, KDI_EINVAL, "rank %d of %d holds %lld dictionary rows, the balanced split of %lld rows gives it %lld",
+                    rank, world, (long long)dict_rows, (long long)dict_total, (long long)(base + (rank < extra ? 1 : 0)));
+  if (base < 1) return kdi_fail(ctx, KDI_EUNSUPPORTED, "fewer dictionary rows than ranks");
+  int64_t kept = exp_rows;
+  if (nav_mask) {
+    kept = 0;
+    for (int64_t i = 0; i < exp_rows; ++i) kept += nav_mask[i] ? 0 : 1;
+  }
+  const int64_t need = kdi_comm_bytes_needed(world, kept, kc, keep_n);
+  if (need > comm_bytes)
+    return kdi_fail(ctx, KDI_EINVAL, "the symmetric block holds %lld bytes, this job needs %lld (kdi_comm_bytes_needed)",
+                    (long long)comm_bytes, (long long)need);
+  kdi_patterns *exp = nullptr, *dict = nullptr;
+  kdi_match_job job;
+  kdi_post post;
+  post.candidates_only = true;
+  post.index_offset = start;
+  post.route = kdi_comm_route(comm, kept, kc, keep_n);
+  cudaStream_t st = ctx->stream;
+  int rc = KDI_OK;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    KDI_TRY(prepare_and_match(ctx, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric, keep_n,
+                              nav_mask, nullptr, nullptr, KDI_DEVICE, post, &job, &exp, &dict));
+    // The candidates have been stored into the slice owners' blocks; nobody reads them before the
+    // first barrier of the exchange, which this rank only joins after this check - so a stage 1 that
+    // has to be redone (readiness wait timed out) simply overwrites them.
+    rc = job.uses_ready ? finish_stage1(ctx, &job) : KDI_OK;
+    if (rc != KDI_ERETRY_EVENTS) break;
+    sync_all_streams(ctx);
+    kdi_patterns_destroy(ctx, exp);
+    kdi_patterns_destroy(ctx, dict);
+    exp = dict = nullptr;
+    rc = KDI_EINTERNAL;
+  }
+  if (rc == KDI_OK && job.M > 0 && job.plan.kc != kc) rc = kdi_fail(ctx, KDI_EINTERNAL, "candidate capacity mismatch");
+  if (rc == KDI_OK && cudaEventRecord(ctx->ev[10], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
+  // pruning margin of the owner rescoring: see kdi_shard_rescore_owned
+  const float margin = 2.0f * (float)ctx->cert_sigmas * (exp->compute_dtype == 1 ? 3.6e-5f : 4.5e-6f) + 2e-5f;
+  if (!ctx->h_nflag && rc == KDI_OK && cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_nflag), 64, cudaHostAllocDefault) != cudaSuccess)
+    rc = kdi_fail(ctx, KDI_ENOMEM, "pinned allocation failed");
+  int* d_total = nullptr;
+  if (rc == KDI_OK) {
+    // (a word of the job's workspace that nothing else uses any more: the flagged-row counter block)
+    d_total = job.d_nflag ? job.d_nflag + 8 : nullptr;
+    if (!d_total) rc = kdi_fail(ctx, KDI_EINTERNAL, "no workspace for the flag count");
+  }
+  if (rc == KDI_OK && kept > 0)
+    rc = kdi_comm_exchange(ctx, comm, exp, dict, kc, keep_n, dict_total, margin, scores_out, indices_out, flags_out, d_total);
+  if (rc == KDI_OK && kept > 0) {
+    ctx->h_nflag[8] = 0;
+    if (cudaMemcpyAsync(ctx->h_nflag + 8, d_total, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      rc = kdi_fail(ctx, KDI_ECUDA, "flag count readback failed");
+  }
+  cudaEventRecord(ctx->ev[1], st);
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == KDI_OK) rc = kdi_fail(ctx, KDI_ECUDA, "stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc != KDI_OK) {
+    sync_all_streams(ctx);
+    const std::string err = ctx->err;
+    kdi_patterns_destroy(ctx, exp);
+    kdi_patterns_destroy(ctx, dict);
+    ctx->err = err;
+    return rc;
+  }
+  if (kept > 0) *n_flag_out = ctx->h_nflag[8];
+  ctx->tm.flagged_rows = *n_flag_out;
+  ctx->tm.normalize_exp_ms = ev_ms(ctx->ev[0], ctx->ev[6]);
+  ctx->tm.normalize_dict_ms = ev_ms(ctx->ev[6], ctx->ev[7]);
+  ctx->tm.gemm_topk_ms = ev_ms(ctx->ev[8], ctx->ev[9]);
+  ctx->tm.rescore_ms = ev_ms(ctx->ev[3], ctx->ev[4]);   // selection + stores into the slice owners' blocks
+  ctx->tm.merge_ms = ev_ms(ctx->ev[10], ctx->ev[1]);    // barriers, merge + routing, request rescoring, finalize, broadcast
+  ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+  kdi_timeline_print(ctx);
+  kdi_shard* sh = new kdi_shard();
+  sh->exp = exp;
+  sh->dict = dict;
+  sh->kc = kc;
+  sh->index_offset = start;
   *out = sh;
   return KDI_OK;
 }
@@ -1001,6 +1148,45 @@ int kdi_orientation_similarity_map(kdi_ctx* ctx, const int64_t* indices, int64_t
   return KDI_OK;
 }
 
+
+int kdi_shard_run_peer(kdi_ctx* ctx, kdi_comm* comm, const void* experimental, int exp_loc, int exp_dtype,
+                       int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype, int64_t dict_rows,
+                       int64_t S, int metric, int keep_n, const uint8_t* nav_mask, int64_t dict_total,
+                       float* scores_out, int64_t* indices_out, int* flags_out, int* n_flag_out, kdi_shard** out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!comm || !experimental || !dictionary || !scores_out || !indices_out || !flags_out || !n_flag_out || !out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_run_peer: NULL argument");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  kdi_timeline_reset(ctx);
+  kdi_dict_source dsrc;
+  dsrc.data = dictionary;
+  dsrc.loc = dict_loc;
+  dsrc.dtype = dict_dtype;
+  return run_shard_peer(ctx, comm, experimental, exp_loc, exp_dtype, exp_rows, dsrc, dict_rows, S, metric, keep_n,
+                        nav_mask, dict_total, scores_out, indices_out, flags_out, n_flag_out, out);
+}
+
+int kdi_shard_run_peer_projected(kdi_ctx* ctx, kdi_comm* comm, const void* experimental, int exp_loc, int exp_dtype,
+                                 int64_t exp_rows, int64_t S, const kdi_master_pattern* mp, const double* rotations,
+                                 int rot_loc, int64_t n_rotations, int metric, int keep_n, const uint8_t* nav_mask,
+                                 int64_t dict_total, float* scores_out, int64_t* indices_out, int* flags_out,
+                                 int* n_flag_out, kdi_shard** out) {
+  if (!ctx) return KDI_EINVAL;
+  if (!comm || !experimental || !mp || !rotations || !scores_out || !indices_out || !flags_out || !n_flag_out || !out)
+    return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_run_peer_projected: NULL argument");
+  KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tm = kdi_timings();
+  kdi_timeline_reset(ctx);
+  kdi_dict_source dsrc;
+  dsrc.mp = mp;
+  kdi_rot_buffer owned;
+  KDI_TRY(upload_rotations(ctx, rotations, rot_loc, n_rotations, &dsrc.d_rot, &owned));
+  const int rc = run_shard_peer(ctx, comm, experimental, exp_loc, exp_dtype, exp_rows, dsrc, n_rotations, S, metric,
+                                keep_n, nav_mask, dict_total, scores_out, indices_out, flags_out, n_flag_out, out);
+  kdi_dev_free(ctx, owned.p, owned.bytes);
+  return rc;
+}
 
 /* ---- appendable job: the reference's chunk loop with the caller in charge of the chunks ------------ */
 

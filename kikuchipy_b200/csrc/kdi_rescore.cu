@@ -121,7 +121,7 @@ template <int KC>
 __global__ void __launch_bounds__(32 * kWarpSelRows)
 kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restrict__ thr, int n_strips,
                        int64_t row0, int64_t row_end, int64_t index_offset, float inv_scale,
-                       float* __restrict__ out_approx, int64_t* __restrict__ out_gidx) {
+                       float* __restrict__ out_approx, int64_t* __restrict__ out_gidx, const kdi_route route) {
   __shared__ uint64_t s_keys[kWarpSelRows][kWarpBuf];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = row0 + (int64_t)blockIdx.x * kWarpSelRows + warp;
@@ -203,6 +203,18 @@ kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restric
   }
   __syncwarp();
   const int nsel = count < KC ? count : KC;
+  if (route.world > 0) {
+    // sharded job: (tensor-core score, GLOBAL dictionary row) records straight into the symmetric
+    // block of the rank that owns this row's slice - a peer store over NVLink unless that is us
+    const int64_t owner = row / route.per;
+    uint2* dst = route.recv[owner] + (((int64_t)route.rank * route.per) + (row - owner * route.per)) * KC;
+    for (int i = lane; i < KC; i += 32)
+      dst[i] = i < nsel ? make_uint2(__float_as_uint(key_score(keys[i]) * inv_scale),
+                                     (uint32_t)((int64_t)key_index(keys[i]) + index_offset))
+                        : make_uint2(0xFF800000u, 0xFFFFFFFFu);
+    __threadfence_system();
+    return;
+  }
   for (int i = lane; i < KC; i += 32) {
     out_approx[row * KC + i] = i < nsel ? key_score(keys[i]) * inv_scale : -INFINITY;
     out_gidx[row * KC + i] = i < nsel ? (int64_t)key_index(keys[i]) + index_offset : -1;
@@ -652,7 +664,8 @@ int kdi_launch_extract_topk(kdi_ctx* ctx, cudaStream_t stream, const float* scor
 int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, const kdi_gemm_plan* plan,
                            const uint2* cand, const uint32_t* thr, int64_t index_offset,
                            float approx_inv_scale, float* out_approx, int64_t* out_gidx,
-                           int64_t row0, int64_t n_rows) {
+                           int64_t row0, int64_t n_rows, const kdi_route* route_in) {
+  const kdi_route route = route_in ? *route_in : kdi_route();
   if (n_rows < 0) n_rows = rows - row0;
   if (n_rows <= 0) return KDI_OK;
   const unsigned grid = (unsigned)kdi_ceil_div(n_rows, kWarpSelRows);
@@ -663,10 +676,10 @@ int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, cons
   kdi_span span(ctx, stream, "select (warp per row)");
   if (plan->kc == 32)
     kdi_select_warp_kernel<32><<<grid, 32 * kWarpSelRows, pad, stream>>>(
-        cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx);
+        cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx, route);
   else if (plan->kc == 64)
     kdi_select_warp_kernel<64><<<grid, 32 * kWarpSelRows, pad, stream>>>(
-        cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx);
+        cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx, route);
   else
     return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
   KDI_CUDA(ctx, cudaGetLastError());

@@ -20,8 +20,18 @@ row afterwards is split by rows so that no rank repeats another rank's work:
   7. all-gather of the finished slices (identical result on every rank)
   8. rows whose certificate failed anywhere: exact top-k per shard, gathered and merged
 
-The exchange logic is written against a small ``stages`` interface so that it runs under
+That is the COLLECTIVE-LIBRARY form of the exchange (``exchange="nccl"``): torch.distributed calls
+around ``kdi_shard_*`` stages, written against a small ``stages`` interface so that it also runs under
 ``gloo`` on CPU tensors in the tests (with the oracle standing in for the GPU stages).
+
+The default on a single NVLink / NVSwitch node is ``exchange="peer"``: the same pipeline inside
+libkdi (``kdi_shard_run_peer``, csrc/kdi_comm.cu).  Every rank maps every other rank's "symmetric
+block" through CUDA IPC once; the kernels then store their results straight into the block of the rank
+that needs them (selection kernel -> slice owner, merge kernel -> request queue of the dictionary-row
+owner, rescoring kernel -> slice owner's score table, finalize -> everybody) and the ranks meet at
+device-side barriers.  No pack / unpack kernels, no host synchronisation between the steps, and the
+owner rescoring walks a compact request list instead of every row.  torch.distributed is only used to
+all-gather the 64-byte IPC handles when the blocks are (re)created, and for the rare flagged rows.
 """
 
 from __future__ import annotations
@@ -137,6 +147,71 @@ def gather_rows(local: np.ndarray, counts, group=None) -> np.ndarray:
     dist.all_gather_into_tensor(out, mine, group=group)
     out = out.cpu().numpy().reshape(world, per, width)
     return np.concatenate([out[r, : int(counts[r])] for r in range(world)], axis=0)
+
+
+_PEER_COMMS: dict = {}
+
+
+def peer_comm(ctx, nbytes: int, group=None):
+    """This process's :class:`kikuchipy_b200._lib.PeerComm` for ``(ctx, group)`` with at least ``nbytes``
+    of symmetric memory; (re)created collectively - every rank must ask for the same size - with the
+    IPC handles all-gathered through torch.distributed."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    key = (id(ctx), id(group))
+    comm = _PEER_COMMS.get(key)
+    if comm is not None and comm._h and comm.nbytes >= nbytes:
+        return comm
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if comm is not None:
+        torch.cuda.synchronize()
+        dist.barrier(group)  # nobody still stores into a block that is about to go away
+        comm.close()
+    nbytes = int(nbytes * 1.25) + (1 << 20)  # head room: slightly larger jobs reuse the mapping
+    comm = _lib.PeerComm(ctx, rank, world, nbytes)
+    nccl = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", ctx.device) if nccl else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(bytes(comm.handle)), dtype=torch.uint8).to(dev)
+    allh = torch.empty((world * _lib.IPC_HANDLE_BYTES,), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh, mine, group=group)
+    comm.connect(bytes(allh.cpu().numpy().tobytes()))
+    dist.barrier(group)  # every rank has mapped every block (and zeroed its own) before anyone stores
+    _PEER_COMMS[key] = comm
+    return comm
+
+
+def _peer_pipeline(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n, navigation_mask, kept,
+                   dictionary_size, group):
+    """exchange="peer": one library call per rank + the rare flagged rows."""
+    import torch
+    import torch.distributed as dist
+
+    from .master_pattern import GeneratedDictionary
+
+    world = dist.get_world_size(group)
+    comm = peer_comm(ctx, ctx.comm_bytes_needed(world, kept, keep_n), group)
+    source = ((dictionary_shard.master_pattern, dictionary_shard.rotations)
+              if isinstance(dictionary_shard, GeneratedDictionary) else dictionary_shard)
+    shard, idx, scores, flags = ctx.shard_run_peer(comm, experimental, n_exp_all, source, n_shard, code, keep_n,
+                                                   dictionary_size, nav_mask=navigation_mask)
+    try:
+        if flags.numel() > 0:  # the same list on every rank: exact top-k per shard, gathered and merged
+            rows = torch.sort(flags).values
+            k_local = min(keep_n, n_shard)
+            fi, fs = shard.exact_rows(rows, k_local)
+            if k_local != keep_n:
+                fs = torch.nn.functional.pad(fs, (0, keep_n - k_local), value=-float("inf"))
+                fi = torch.nn.functional.pad(fi, (0, keep_n - k_local), value=-1)
+            fs_all, fi_all = gather_topk(fs, fi, group)
+            mi, ms = ctx.merge_topk(fs_all, fi_all, keep_n)
+            idx[rows.long()] = mi
+            scores[rows.long()] = ms
+    finally:
+        shard.close()
+    return idx, scores
 
 
 def _pack(scores, indices):
@@ -277,9 +352,14 @@ def dictionary_indexing_sharded(
     *,
     context=None,
     group=None,
+    exchange: str | None = None,
 ):
     """Index ``experimental`` against a dictionary whose rows ``shard_bounds(dictionary_size,
     world, rank)`` this rank holds in ``dictionary_shard``.
+
+    ``exchange``: ``"peer"`` (default; ``KDI_EXCHANGE`` overrides) - the exchange inside libkdi over
+    peer-mapped memory, for up to 8 ranks on one node - or ``"nccl"`` - torch.distributed collectives
+    around the library's stages (any number of ranks / nodes).
 
     ``experimental`` (the same array on every rank) and ``dictionary_shard`` may be host arrays
     or CUDA tensors; ``dictionary_shard`` may also be a :class:`GeneratedDictionary` holding this
@@ -333,6 +413,16 @@ def dictionary_indexing_sharded(
                 raise NotImplementedError(f"keep_n {keep_n} is too large for a generated, sharded dictionary")
             return _sharded_exact_lists(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
                                         navigation_mask, start, kept, dictionary_size, group)
+        exchange = exchange or os.environ.get("KDI_EXCHANGE", "peer")
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        if exchange == "peer" and world <= 8 and dictionary_size >= world and kept < (1 << 24):
+            idx, scores = _peer_pipeline(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n,
+                                         navigation_mask, kept, dictionary_size, group)
+            trace("peer_pipeline")
+            trace.report(ctx)
+            torch.cuda.current_stream().synchronize()
+            return idx, scores
         stages = _KdiStages(ctx, experimental, n_exp_all, dictionary_shard, n_shard, code, keep_n, navigation_mask,
                             start)
         try:

@@ -1,5 +1,6 @@
-"""Dictionary sharded over 2 GPUs (NCCL all-gather of per-shard top-k + device merge) must equal
-the unsharded result.  Skipped with fewer than 2 GPUs."""
+"""Dictionary sharded over 2 GPUs must equal the unsharded result - with the exchange inside libkdi over
+peer-mapped memory (the default) and with torch.distributed collectives, bit for bit the same.
+Skipped with fewer than 2 GPUs."""
 
 import os
 
@@ -46,6 +47,23 @@ def _worker(rank, world, port, tmp):
         gen = kb.get_patterns(mu, ml, rot[start:end], direction_cosines=dc, detector_shape=(40, 40), context=ctx)
         idx4, sc4 = kb.dictionary_indexing_sharded(exp, gen, 7001, metric="ncc", keep_n=20, navigation_mask=nav,
                                                    signal_mask=smask, context=ctx)
+        # both forms of the exchange and the single-GPU pipeline on a larger job (several strips and
+        # row-block groups, kc = 64, pruned owner rescoring): bit-identical results
+        from kikuchipy_b200 import _lib
+
+        expB = orc.synthetic_experimental(2100, (30, 30), seed=11)
+        dicB = orc.synthetic_dictionary(30001, (30, 30), seed=12)
+        sB, eB = kb.shard_bounds(30001, world, rank)
+        big = {}
+        for ex in ("peer", "nccl", "peer"):  # (peer twice: the mapped blocks are reused)
+            i5, s5 = kb.dictionary_indexing_sharded(expB, dicB[sB:eB], 30001, metric="ncc", keep_n=50, context=ctx,
+                                                    exchange=ex)
+            if ex in big:
+                assert torch.equal(big[ex][0], i5) and torch.equal(big[ex][1], s5)
+            big[ex] = (i5, s5)
+        i6, s6 = ctx.dictionary_indexing(expB, 2100, dicB, 30001, _lib.KDI_NCC, 50)
+        np.savez(os.path.join(tmp, f"big{rank}.npz"), ip=big["peer"][0].cpu().numpy(), sp=big["peer"][1].cpu().numpy(),
+                 inn=big["nccl"][0].cpu().numpy(), sn=big["nccl"][1].cpu().numpy(), i1=i6, s1=s6)
         np.savez(os.path.join(tmp, f"r{rank}.npz"), idx=idx.cpu().numpy(), sc=sc.cpu().numpy(),
                  idx2=idx2.cpu().numpy(), sc2=sc2.cpu().numpy(), idx3=idx3.cpu().numpy(), sc3=sc3.cpu().numpy(),
                  idx4=idx4.cpu().numpy(), sc4=sc4.cpu().numpy())
@@ -70,6 +88,12 @@ def test_two_gpu_shards_equal_unsharded(tmp_path):
     ridx, rsc = orc.dictionary_indexing(exp, dic, keep_n=20, navigation_mask=nav, signal_mask=smask)
     z0 = np.load(os.path.join(str(tmp_path), "r0.npz"))
     z1 = np.load(os.path.join(str(tmp_path), "r1.npz"))
+    b0 = np.load(os.path.join(str(tmp_path), "big0.npz"))
+    b1 = np.load(os.path.join(str(tmp_path), "big1.npz"))
+    for k in ("ip", "sp", "inn", "sn"):
+        assert np.array_equal(b0[k], b1[k]), k          # identical on every rank
+    assert np.array_equal(b0["ip"], b0["inn"]) and np.array_equal(b0["sp"], b0["sn"])  # peer == collectives
+    assert np.array_equal(b0["ip"], b0["i1"]) and np.array_equal(b0["sp"], b0["s1"])   # == one GPU
     assert np.array_equal(z0["idx"], z1["idx"]) and np.array_equal(z0["sc"], z1["sc"])
     r = orc.compare_topk(ridx, rsc, z0["idx"], z0["sc"], tie_tol=2e-5)
     assert r["tie_ok"] and r["scores_ok"], r
