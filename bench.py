@@ -430,7 +430,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- the other BASELINE.json configurations that fit this run (every rank takes part) --------
     extra = {}
     if not args.no_extras:
-        for number in ({1: [3], 8: [4, 5]}.get(world, [])):
+        numbers = [int(x) for x in args.extras.split(",") if x] if args.extras else {1: [3], 8: [4, 5]}.get(world, [])
+        for number in numbers:
             try:
                 r = cfgs.run_config(number, ctx, rank, world, dev, steps=3, warmup=2, sample64=256)
                 extra[f"config{number}"] = r
@@ -593,6 +594,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the other BASELINE configurations and the preprocessing / refinement timings")
+    ap.add_argument("--extras", default="", help="BASELINE configurations to run as extras (default: 3 at N = 1; 4,5 at N = 8)")
     ap.add_argument("--no-generated", action="store_true", help="skip the generated-dictionary end-to-end leg")
     ap.add_argument("--numa-bind", action="store_true",
                     help="bind each rank to its GPU's NUMA node (no effect on single-node-affinity boxes like this pool's)")

@@ -85,9 +85,11 @@ extern "C" {
 
 #define KDI_OPT_GEMM_SMS 11     /* SMs the tensor-core kernel may occupy (0 = all, default): the rest stay free
                                    for the HBM-bound kernels queued beside it                              */
-#define KDI_OPT_DEP_FLAGS 12    /* 1 (default) = device-resident float32 / uint8 dictionaries are normalised beside
-                                   the tensor-core launches, which wait per 256-row tile on device-side
-                                   readiness counters; 0 = stream events only (first quarter, then the rest)  */
+#define KDI_OPT_DEP_FLAGS 12    /* 1 = device-resident float32 / uint8 dictionaries are normalised beside the
+                                   tensor-core launches, which wait per 256-row tile on device-side readiness
+                                   counters; 0 (default) = stream events only (first quarter, then the rest).
+                                   Measured on B200: the tensor-core kernel saturates the L2 -> SM path, a
+                                   memory-bound kernel beside it crawls, and the schedule gains nothing     */
 #define KDI_OPT_MIN_GROUPS 13   /* at least this many row-block groups (= tensor-core launches) per job; 0 = one
                                    per L2 super-block of experimental rows                                 */
 #define KDI_OPT_POST_PER_GROUP 14 /* 1 = selection + rescoring of a finished row-block group is queued on the

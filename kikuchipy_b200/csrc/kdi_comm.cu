@@ -323,6 +323,9 @@ int kdi_comm_exchange(kdi_ctx* ctx, kdi_comm* comm, const kdi_patterns* exp, con
     else if (kc == 64)
       kdi_merge_route_kernel<64><<<grid, 32 * kMergeRows, 0, st>>>(recv, world, l.per, r0, n_local, keep_n, margin, base, extra,
                                                                    m_approx, m_gidx, exact, cnt, blocks, l.req, l.req_cap, rank);
+    else if (kc == 128)
+      kdi_merge_route_kernel<128><<<grid, 32 * kMergeRows, 0, st>>>(recv, world, l.per, r0, n_local, keep_n, margin, base, extra,
+                                                                    m_approx, m_gidx, exact, cnt, blocks, l.req, l.req_cap, rank);
     else
       return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", kc);
     KDI_CUDA(ctx, cudaGetLastError());
@@ -342,7 +345,8 @@ int kdi_comm_exchange(kdi_ctx* ctx, kdi_comm* comm, const kdi_patterns* exp, con
   int64_t* my_ix = reinterpret_cast<int64_t*>(mine + l.fin_ix) + r0 * keep_n;
   if (n_local > 0)
     KDI_TRY(kdi_launch_finalize(ctx, st, n_local, kc, m_approx, reinterpret_cast<const float*>(mine + l.exact), m_gidx, keep_n,
-                                dict_total, (float)ctx->cert_sigmas, r0, my_sc, my_ix, flag_list, n_flag));
+                                dict_total, (float)ctx->cert_sigmas, kdi_cert_sigma_floor(exp), r0, my_sc, my_ix, flag_list,
+                                n_flag));
   {
     kdi_span span(ctx, st, "broadcast finished slice");
     const int64_t sc_words = n_local * keep_n, ix_words = n_local * keep_n * 2;

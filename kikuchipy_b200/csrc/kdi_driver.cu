@@ -1086,7 +1086,8 @@ int kdi_shard_finalize(kdi_ctx* ctx, const kdi_shard* shard, int64_t row0, int64
   cudaStream_t st = ctx->stream;
   KDI_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int), st));
   KDI_TRY(kdi_launch_finalize(ctx, st, rows, shard->kc, approx, exact, gidx, keep_n, dict_total,
-                              (float)ctx->cert_sigmas, row0, scores_out, indices_out, flags_out, d_n));
+                              (float)ctx->cert_sigmas, kdi_cert_sigma_floor(shard->exp), row0, scores_out, indices_out,
+                              flags_out, d_n));
   KDI_CUDA(ctx, cudaMemcpyAsync(n_flag_out, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
   KDI_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->tm.flagged_rows += *n_flag_out;

@@ -264,6 +264,14 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float lmin = -INFINITY;     // smallest entry of a full list
       float gthr = -INFINITY;     // last value read from / published to the global threshold
       float thr = valid ? -INFINITY : INFINITY;
+      // the list is kept as KC / 8 groups of 8 slots with the minimum (and its slot) of every group in
+      // registers: replacing the list minimum re-scans ONE group (8 shared-memory loads) and takes
+      // the minimum of the group minima, instead of re-scanning all KC slots
+      constexpr int kGroups = KC / 8;
+      float gmin[kGroups];
+      int gpos[kGroups];
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) { gmin[g] = INFINITY; gpos[g] = g * 8; }
 
       const int rot = p.rotate ? mb % (t1 - t0) : 0;
       for (int ti = 0; ti < t1 - t0; ++ti) {
@@ -318,18 +326,44 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const float s = pick32(v, j);
                 if (s > thr) {
                   const uint32_t idx = (uint32_t)(nt * KDI_TILE_N + col0 + j);
-                  int slot;
-                  if (cnt < KC) slot = cnt++;
-                  else slot = minpos;
+                  const int slot = cnt < KC ? cnt : minpos;
                   ls[slot * KDI_TILE_M + r] = s;
                   li[slot * KDI_TILE_M + r] = idx;
+                  if (cnt < KC) {
+                    if (++cnt == KC) {  // the list has just become full: minima of all groups
+#pragma unroll
+                      for (int g = 0; g < kGroups; ++g) {
+                        float mn = ls[(g * 8) * KDI_TILE_M + r];
+                        int mp = g * 8;
+#pragma unroll
+                        for (int q = 1; q < 8; ++q) {
+                          const float x = ls[(g * 8 + q) * KDI_TILE_M + r];
+                          if (x < mn) { mn = x; mp = g * 8 + q; }
+                        }
+                        gmin[g] = mn;
+                        gpos[g] = mp;
+                      }
+                    }
+                  } else {  // the minimum was replaced: its group only
+                    const int gs = slot >> 3;
+                    float mn = ls[(gs * 8) * KDI_TILE_M + r];
+                    int mp = gs * 8;
+#pragma unroll
+                    for (int q = 1; q < 8; ++q) {
+                      const float x = ls[(gs * 8 + q) * KDI_TILE_M + r];
+                      if (x < mn) { mn = x; mp = gs * 8 + q; }
+                    }
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                      if (g == gs) { gmin[g] = mn; gpos[g] = mp; }
+                    }
+                  }
                   if (cnt == KC) {
-                    float mn = ls[r];
-                    int mp = 0;
-#pragma unroll 8
-                    for (int i = 1; i < KC; ++i) {
-                      const float x = ls[i * KDI_TILE_M + r];
-                      if (x < mn) { mn = x; mp = i; }
+                    float mn = gmin[0];
+                    int mp = gpos[0];
+#pragma unroll
+                    for (int g = 1; g < kGroups; ++g) {
+                      if (gmin[g] < mn) { mn = gmin[g]; mp = gpos[g]; }
                     }
                     lmin = mn;
                     minpos = mp;
@@ -458,6 +492,7 @@ int stages_for(int cg, int kc, int mode) {
 int kdi_gemm_kc_for(int keep_n) {
   if (keep_n <= 24) return 32;
   if (keep_n <= 52) return 64;
+  if (keep_n <= 104) return 128;
   return 0;
 }
 
@@ -578,6 +613,8 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   if (cg == 1 && plan->kc == 64) return launch_variant<1, 64, 0>(ctx, stream, tmA, tmB, p);
   if (cg == 2 && plan->kc == 32) return launch_variant<2, 32, 0>(ctx, stream, tmA, tmB, p);
   if (cg == 2 && plan->kc == 64) return launch_variant<2, 64, 0>(ctx, stream, tmA, tmB, p);
+  if (cg == 1 && plan->kc == 128) return launch_variant<1, 128, 0>(ctx, stream, tmA, tmB, p);
+  if (cg == 2 && plan->kc == 128) return launch_variant<2, 128, 0>(ctx, stream, tmA, tmB, p);
   return kdi_fail(ctx, KDI_EINTERNAL, "no GEMM variant for cta_group=%d kc=%d", cg, plan->kc);
 }
 

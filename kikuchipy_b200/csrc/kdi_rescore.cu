@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kSelThreads)
 kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
                           int64_t s_pitch, int64_t n_dict, const uint2* __restrict__ cand,
                           const uint32_t* __restrict__ thr, int n_strips, int keep_n,
-                          int64_t index_offset, float inv_scale, float cert_sigmas,
+                          int64_t index_offset, float inv_scale, float cert_sigmas, float sigma_floor,
                           float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
                           int* __restrict__ flag_list, int* __restrict__ n_flag, int64_t row0,
                           const float* __restrict__ pre_approx, const int64_t* __restrict__ pre_idx) {
@@ -235,7 +235,7 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   __shared__ float ap[KC];
   __shared__ uint32_t ci[KC];
   __shared__ int s_count;
-  __shared__ float s_red[4];
+  __shared__ float s_red[2 * (kSelThreads / 32)];
   __shared__ float s_ek;
 
   const int64_t row = row0 + blockIdx.x;
@@ -294,13 +294,17 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
     err1 += __shfl_xor_sync(0xffffffffu, err1, o);
     err2 += __shfl_xor_sync(0xffffffffu, err2, o);
   }
-  if (lane == 0 && warp < 2) { s_red[warp] = err1; s_red[2 + warp] = err2; }
+  constexpr int kW = kSelThreads / 32;
+  if (lane == 0) { s_red[warp] = err1; s_red[kW + warp] = err2; }
   if (tid == 0 && n_a < keep_n) s_ek = -INFINITY;
   __syncthreads();
   const float inv_na = 1.f / (float)(n_a > 0 ? n_a : 1);
-  const float bias = (s_red[0] + s_red[1]) * inv_na;
-  const float sigma = sqrtf(fmaxf((s_red[2] + s_red[3]) * inv_na - bias * bias, 0.f));
-  const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 0.1f * fabsf(bias) + 1e-7f;
+  const float bias = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) * inv_na;
+  const float sigma = sqrtf(fmaxf(((s_red[kW] + s_red[kW + 1]) + (s_red[kW + 2] + s_red[kW + 3])) * inv_na - bias * bias, 0.f));
+  // the noise level is estimated from a few dozen candidates of this row; it is never taken below the
+  // a-priori level of the operand rounding (sigma_floor, kdi_cert_sigma_floor), so an unluckily small
+  // sample cannot shrink the certificate's safety margin
+  const float eps = cert_sigmas * fmaxf(sigma, sigma_floor) + 0.1f * fabsf(bias) + 1e-7f;
   const float e_k = s_ek;
   for (int i = n_a + warp; i < nsel; i += kSelThreads / 32) {
     float d = -INFINITY;  // warp-uniform decision
@@ -389,17 +393,18 @@ kdi_rescore_owned_kernel(const float* __restrict__ exp32, const float* __restric
   }
 }
 
-// rank by exact score, certificate (same rule as the fused kernel), one 64-thread block per row
-__global__ void __launch_bounds__(64)
+// rank by exact score, certificate (same rule as the fused kernel), one block of max(kc, 64) threads per row
+constexpr int kFinMax = 128;
+__global__ void __launch_bounds__(kFinMax)
 kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __restrict__ exact,
                     const int64_t* __restrict__ gidx, int keep_n, int64_t n_dict_total,
-                    float cert_sigmas, int64_t row0, float* __restrict__ out_scores,
+                    float cert_sigmas, float sigma_floor, int64_t row0, float* __restrict__ out_scores,
                     int64_t* __restrict__ out_idx, int* __restrict__ flag_list, int* __restrict__ n_flag) {
-  __shared__ float ex[64];
-  __shared__ float ap[64];
-  __shared__ int64_t gi[64];
-  __shared__ float s_red[4];
-  __shared__ float s_red2[4];
+  __shared__ float ex[kFinMax];
+  __shared__ float ap[kFinMax];
+  __shared__ int64_t gi[kFinMax];
+  __shared__ float s_red[8];
+  __shared__ float s_red2[8];
   __shared__ int s_nsel;
   const int64_t row = blockIdx.x;
   const int tid = threadIdx.x;
@@ -422,7 +427,7 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
   const bool scored = valid && ex[tid] != -INFINITY;
   float err1 = 0.f, err2 = 0.f, my_s = 0.f, cnt1 = scored ? 1.f : 0.f;
   float skipped_ap = (valid && !scored) ? ap[tid] : -INFINITY;
-  int rank = 64;
+  int rank = kFinMax;
   if (scored) {
     my_s = ex[tid];
     const float d = my_s - ap[tid];
@@ -441,11 +446,13 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
     cnt1 += __shfl_xor_sync(0xffffffffu, cnt1, o);
     skipped_ap = fmaxf(skipped_ap, __shfl_xor_sync(0xffffffffu, skipped_ap, o));
   }
+  if (tid < 8) { s_red[tid] = 0.f; s_red2[tid] = tid < 4 ? 0.f : -INFINITY; }
+  __syncthreads();
   if ((tid & 31) == 0) {
-    s_red[tid >> 5] = err1; s_red[2 + (tid >> 5)] = err2; s_red2[tid >> 5] = cnt1; s_red2[2 + (tid >> 5)] = skipped_ap;
+    s_red[tid >> 5] = err1; s_red[4 + (tid >> 5)] = err2; s_red2[tid >> 5] = cnt1; s_red2[4 + (tid >> 5)] = skipped_ap;
   }
   __syncthreads();
-  const float n_scored = s_red2[0] + s_red2[1];
+  const float n_scored = (s_red2[0] + s_red2[1]) + (s_red2[2] + s_red2[3]);
   if (scored && rank < keep_n) {
     out_scores[row * keep_n + rank] = my_s;
     out_idx[row * keep_n + rank] = gi[tid];
@@ -454,13 +461,13 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
     bool ok = true;
     const bool any_skipped = n_scored < (float)nsel;
     if (n_dict_total > (int64_t)nsel || any_skipped) {
-      const float bias = (s_red[0] + s_red[1]) / n_scored;  // exact = approx + bias + noise
-      const float sigma = sqrtf(fmaxf((s_red[2] + s_red[3]) / n_scored - bias * bias, 0.f));
-      const float eps = cert_sigmas * fmaxf(sigma, 1e-7f) + 0.1f * fabsf(bias) + 1e-7f;
+      const float bias = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) / n_scored;  // exact = approx + bias + noise
+      const float sigma = sqrtf(fmaxf(((s_red[4] + s_red[5]) + (s_red[6] + s_red[7])) / n_scored - bias * bias, 0.f));
+      const float eps = cert_sigmas * fmaxf(sigma, sigma_floor) + 0.1f * fabsf(bias) + 1e-7f;
       // nothing outside the rescored set may reach the keep_n-th exact score: neither a row the
       // tensor-core pass discarded (score <= the smallest retained one) nor a pruned candidate
       if (n_dict_total > (int64_t)nsel) ok = (nsel == kc) && (my_s > ap[nsel - 1] + bias + eps);
-      if (any_skipped) ok = ok && (my_s > fmaxf(s_red2[2], s_red2[3]) + bias + eps);
+      if (any_skipped) ok = ok && (my_s > fmaxf(fmaxf(s_red2[4], s_red2[5]), fmaxf(s_red2[6], s_red2[7])) + bias + eps);
     }
     if (!ok) flag_list[atomicAdd(n_flag, 1)] = (int)(row0 + row);
   }
@@ -602,6 +609,7 @@ int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patte
                               int64_t index_offset, float approx_inv_scale, float cert_sigmas,
                               float* out_scores, int64_t* out_idx, int* flag_list, int* n_flag,
                               int64_t row0, int64_t n_rows, const float* pre_approx, const int64_t* pre_idx) {
+  const float sigma_floor = kdi_cert_sigma_floor(exp);
   if (n_rows < 0) n_rows = exp->rows - row0;
   if (n_rows <= 0) return KDI_OK;
   const unsigned grid = (unsigned)n_rows;
@@ -611,16 +619,21 @@ int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patte
   const int carve = ctx->post_coresident > 0 ? 100 : kdi_carveout_pref();
   cudaFuncSetAttribute(kdi_select_rescore_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   cudaFuncSetAttribute(kdi_select_rescore_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_rescore_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   const size_t pad = kdi_post_pad_bytes(ctx, kSelBuf * 8 + 3 * plan->kc * 4 + 64);
   kdi_span span(ctx, stream, "select_rescore");
   if (plan->kc == 32)
     kdi_select_rescore_kernel<32><<<grid, kSelThreads, pad, stream>>>(
         exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
-        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
+        index_offset, approx_inv_scale, cert_sigmas, sigma_floor, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
   else if (plan->kc == 64)
     kdi_select_rescore_kernel<64><<<grid, kSelThreads, pad, stream>>>(
         exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
-        index_offset, approx_inv_scale, cert_sigmas, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
+        index_offset, approx_inv_scale, cert_sigmas, sigma_floor, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
+  else if (plan->kc == 128)
+    kdi_select_rescore_kernel<128><<<grid, kSelThreads, pad, stream>>>(
+        exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
+        index_offset, approx_inv_scale, cert_sigmas, sigma_floor, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
   else
     return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
   KDI_CUDA(ctx, cudaGetLastError());
@@ -672,6 +685,7 @@ int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, cons
   const int carve = ctx->post_coresident > 0 ? 100 : kdi_carveout_pref();
   cudaFuncSetAttribute(kdi_select_warp_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   cudaFuncSetAttribute(kdi_select_warp_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_warp_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   const size_t pad = kdi_post_pad_bytes(ctx, (size_t)kWarpSelRows * kWarpBuf * 8);
   kdi_span span(ctx, stream, "select (warp per row)");
   if (plan->kc == 32)
@@ -679,6 +693,9 @@ int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, cons
         cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx, route);
   else if (plan->kc == 64)
     kdi_select_warp_kernel<64><<<grid, 32 * kWarpSelRows, pad, stream>>>(
+        cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx, route);
+  else if (plan->kc == 128)
+    kdi_select_warp_kernel<128><<<grid, 32 * kWarpSelRows, pad, stream>>>(
         cand, thr, plan->n_strips, row0, row0 + n_rows, index_offset, approx_inv_scale, out_approx, out_gidx, route);
   else
     return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
@@ -702,13 +719,12 @@ int kdi_launch_rescore_owned(kdi_ctx* ctx, cudaStream_t stream, const kdi_patter
 
 int kdi_launch_finalize(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, int kc, const float* approx,
                         const float* exact, const int64_t* gidx, int keep_n, int64_t n_dict_total,
-                        float cert_sigmas, int64_t row0, float* out_scores, int64_t* out_idx,
+                        float cert_sigmas, float sigma_floor, int64_t row0, float* out_scores, int64_t* out_idx,
                         int* flag_list, int* n_flag) {
   if (rows <= 0) return KDI_OK;
-  if (kc < 1 || kc > 64 || keep_n > kc) return kdi_fail(ctx, KDI_EINVAL, "finalize: need keep_n <= kc <= 64");
-  kdi_finalize_kernel<<<(unsigned)rows, 64, 0, stream>>>(kc, approx, exact, gidx, keep_n, n_dict_total,
-                                                         cert_sigmas, row0, out_scores, out_idx, flag_list,
-                                                         n_flag);
+  if (kc < 1 || kc > kFinMax || keep_n > kc) return kdi_fail(ctx, KDI_EINVAL, "finalize: need keep_n <= kc <= %d", kFinMax);
+  kdi_finalize_kernel<<<(unsigned)rows, kc > 64 ? kFinMax : 64, 0, stream>>>(
+      kc, approx, exact, gidx, keep_n, n_dict_total, cert_sigmas, sigma_floor, row0, out_scores, out_idx, flag_list, n_flag);
   KDI_CUDA(ctx, cudaGetLastError());
   ctx->tm.kernel_launches++;
   return KDI_OK;

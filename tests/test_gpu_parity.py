@@ -28,7 +28,7 @@ def ctx():
                 _lib.OPT_MAX_STAGES, _lib.OPT_GEMM_SMS, _lib.OPT_MIN_GROUPS, _lib.OPT_POST_PER_GROUP,
                 _lib.OPT_GEMM_SERIAL, _lib.OPT_SM_PARTITION):
         c.set_option(opt, 0)
-    c.set_option(_lib.OPT_DEP_FLAGS, 1)
+    c.set_option(_lib.OPT_DEP_FLAGS, 0)
     c.set_option(_lib.OPT_SPLIT_SELECT, 1)
     c.set_option(_lib.OPT_CTA_GROUP, 2)
     c.set_option(_lib.OPT_OVERLAP, 1)
@@ -352,7 +352,7 @@ def test_schedule_variants_equal_serial(ctx, name, src):
         for o in (_lib.OPT_SUPERBLOCK, _lib.OPT_STRIP_TILES, _lib.OPT_GEMM_SMS, _lib.OPT_MIN_GROUPS,
                   _lib.OPT_POST_PER_GROUP, _lib.OPT_GEMM_SERIAL, _lib.OPT_SM_PARTITION):
             ctx.set_option(o, 0)
-        ctx.set_option(_lib.OPT_DEP_FLAGS, 1)
+        ctx.set_option(_lib.OPT_DEP_FLAGS, 0)
         ctx.set_option(_lib.OPT_OVERLAP, 1)
         ctx.set_signal_mask(None)
     assert np.array_equal(res["serial"][0], res[name][0]) and np.array_equal(res["serial"][1], res[name][1])
@@ -787,3 +787,51 @@ def test_pageable_and_pinned_host_dictionaries_agree(ctx):
     assert ctx.timings()["h2d_bytes"] >= dic.nbytes
     ridx, rsc = orc.dictionary_indexing(exp, dic, metric="ndp", keep_n=5)
     _check(ridx, rsc, a[0], a[1])
+
+
+@pytest.mark.parametrize("keep_n", [53, 100, 104])
+def test_large_keep_n_stays_on_the_tensor_core_path(ctx, keep_n):
+    """keep_n up to 104 is nominated by the tensor-core kernel (128-entry candidate lists) and must equal
+    the exact float32 path bit for bit; beyond that the exact path serves the call (the reference
+    accepts any keep_n <= N, _dictionary_indexing.py:67)."""
+    exp = orc.synthetic_experimental(300, (32, 32), seed=31)
+    dic = orc.synthetic_dictionary(20_000, (32, 32), seed=32)
+    assert ctx.candidate_capacity(keep_n) == 128 and ctx.candidate_capacity(105) == 0
+    i1, s1 = ctx.dictionary_indexing(exp, 300, dic, 20_000, _lib.KDI_NCC, keep_n)
+    tm = ctx.timings()
+    assert tm["gemm_launches"] >= 1
+    ctx.set_option(_lib.OPT_FORCE_EXACT, 1)
+    try:
+        i2, s2 = ctx.dictionary_indexing(exp, 300, dic, 20_000, _lib.KDI_NCC, keep_n)
+    finally:
+        ctx.set_option(_lib.OPT_FORCE_EXACT, 0)
+    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+    assert tm["flagged_rows"] <= 60, tm["flagged_rows"]
+    ridx, rsc = orc.dictionary_indexing(exp[:40], dic, keep_n=keep_n, n_experimental_patterns=40)
+    _check(ridx, rsc, i1[:40], s1[:40])
+
+
+@pytest.mark.parametrize("compute", ["fp16", "bf16"])
+def test_adversarial_near_ties_are_caught_by_the_certificate(ctx, compute):
+    """300 dictionary rows that differ from one another by ~1e-4 relative noise have exact
+    scores ~1e-6 apart - far below what 16-bit operands resolve - and there are more of them than
+    candidate slots.  The certificate (noise level floored at the a-priori rounding noise) must send
+    every affected row through the exact path: results equal the forced-exact ones bit for bit."""
+    rng = np.random.default_rng(41)
+    dic = orc.synthetic_dictionary(6000, (30, 30), seed=42)
+    base = dic[17].copy()
+    dic[1000:1300] = base[None] * (1.0 + 1e-4 * rng.standard_normal((300, 30, 30)).astype(np.float32))
+    exp = orc.synthetic_experimental(64, (30, 30), seed=43)
+    exp[:32] = np.clip(np.rint(255 * (0.8 * base[None] + 0.2 * rng.random((32, 30, 30)))), 0, 255).astype(np.uint8)
+    ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 1 if compute == "bf16" else 0)
+    try:
+        i1, s1 = ctx.dictionary_indexing(exp, 64, dic, 6000, _lib.KDI_NCC, 20)
+        flagged = ctx.timings()["flagged_rows"]
+        ctx.set_option(_lib.OPT_FORCE_EXACT, 1)
+        i2, s2 = ctx.dictionary_indexing(exp, 64, dic, 6000, _lib.KDI_NCC, 20)
+    finally:
+        ctx.set_option(_lib.OPT_FORCE_EXACT, 0)
+        ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 0)
+    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+    assert flagged >= 32  # the planted rows cannot be certified from 32 candidates
+    assert np.all((i1[:32] >= 1000) & (i1[:32] < 1300) | (i1[:32] == 17))
