@@ -105,6 +105,9 @@ extern "C" {
                                    pipeline stage of shared memory and the post-processing kernels of a
                                    finished group are sized so that n of their CTAs fit into that hole on
                                    every SM - they then run BESIDE the next groups' launches; 0 = off     */
+#define KDI_OPT_BULK_NORMALIZE 18 /* 1 (default) = rows that need a cast, a row gather or the signal mask are staged
+                                   by asynchronous bulk copies (cp.async.bulk, double-buffered) and compacted run
+                                   by run; 0 = the older kernel with scattered loads (bit-identical results)   */
 
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;

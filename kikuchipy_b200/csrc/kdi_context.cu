@@ -387,6 +387,7 @@ int kdi_destroy(kdi_ctx* ctx) {
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
   if (ctx->d_cols) cudaFree(ctx->d_cols);
+  if (ctx->d_runs) cudaFree(ctx->d_runs);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->copy_ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->free_ev) if (ev) cudaEventDestroy(ev);
@@ -466,6 +467,9 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
     case KDI_OPT_GEMM_SERIAL:
       ctx->gemm_serial = value != 0;
       return KDI_OK;
+    case KDI_OPT_BULK_NORMALIZE:
+      ctx->bulk_normalize = value != 0;
+      return KDI_OK;
     case KDI_OPT_POST_CORESIDENT:
       if (value < 0 || value > 8) return kdi_fail(ctx, KDI_EINVAL, "post_coresident must be 0..8");
       ctx->post_coresident = (int)value;
@@ -524,10 +528,15 @@ int kdi_set_signal_mask(kdi_ctx* ctx, const uint8_t* mask, int64_t S) {
   if (!ctx) return KDI_EINVAL;
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
   if (ctx->d_cols) {
-    KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    sync_ctx_streams(ctx);
     KDI_CUDA(ctx, cudaFree(ctx->d_cols));
     ctx->d_cols = nullptr;
   }
+  if (ctx->d_runs) {
+    KDI_CUDA(ctx, cudaFree(ctx->d_runs));
+    ctx->d_runs = nullptr;
+  }
+  ctx->n_runs = 0;
   ctx->mask_S = 0;
   ctx->mask_kept = 0;
   if (!mask) return KDI_OK;
@@ -539,6 +548,17 @@ int kdi_set_signal_mask(kdi_ctx* ctx, const uint8_t* mask, int64_t S) {
   if (cols.empty()) return kdi_fail(ctx, KDI_EINVAL, "signal mask excludes every pixel");
   KDI_CUDA(ctx, cudaMalloc(&ctx->d_cols, cols.size() * sizeof(int32_t)));
   KDI_CUDA(ctx, cudaMemcpy(ctx->d_cols, cols.data(), cols.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  // runs of consecutive kept columns
+  std::vector<int3> runs;
+  for (size_t j = 0; j < cols.size();) {
+    size_t e = j + 1;
+    while (e < cols.size() && cols[e] == cols[e - 1] + 1) ++e;
+    runs.push_back(make_int3(cols[j], (int)(e - j), (int)j));
+    j = e;
+  }
+  KDI_CUDA(ctx, cudaMalloc(&ctx->d_runs, runs.size() * sizeof(int3)));
+  KDI_CUDA(ctx, cudaMemcpy(ctx->d_runs, runs.data(), runs.size() * sizeof(int3), cudaMemcpyHostToDevice));
+  ctx->n_runs = (int)runs.size();
   ctx->mask_S = S;
   ctx->mask_kept = (int64_t)cols.size();
   return KDI_OK;

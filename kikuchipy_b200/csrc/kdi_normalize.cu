@@ -11,9 +11,12 @@
 //   _normalized_dot_product.py:105-118,141-150,176-194 (no centring)
 // HBM-bound: algorithmic bytes per row = S*sizeof(src) + s_pitch*4 + kp*2.
 #include "kdi_internal.cuh"
+#include "kdi_ptx.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+
+#include <cstdlib>
 
 namespace {
 
@@ -168,6 +171,90 @@ kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __rest
   }
 }
 
+// bulk-staged path (any source type, optional row gather, optional column mask given as runs of
+// consecutive kept columns): the RAW source row is brought into shared memory by one asynchronous
+// bulk copy (cp.async.bulk, the 1-D form of TMA; completion on an mbarrier) into one of two buffers,
+// so the copy of row i + 1 is in flight while row i is compacted, reduced and written.  A warp
+// compacts whole runs (conflict-free shared-memory reads, no index list), then the same three passes
+// as the staged kernel run on the compact float32 row - same per-thread summation order, bit-identical
+// results.  Needs 16-byte aligned rows (S * sizeof(T) a multiple of 16).
+template <typename T, bool BF16>
+__global__ void __launch_bounds__(kNormThreads)
+kdi_normalize_bulk(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
+                   const int3* __restrict__ runs, int n_runs, int64_t s_eff, int metric,
+                   float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16, int64_t kp,
+                   int64_t n_rows, uint32_t raw_bytes) {
+  extern __shared__ __align__(128) uint8_t smem_bulk[];
+  __shared__ double red[kNormThreads / 32];
+  __shared__ __align__(8) uint64_t bars[2];
+  const uint32_t raw_pitch = (raw_bytes + 127u) & ~127u;
+  uint8_t* raw0 = smem_bulk;
+  float* v = reinterpret_cast<float*>(smem_bulk + 2 * raw_pitch);  // s_eff floats
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar0 = kdi::smem_u32(bars);
+  if (tid == 0) {
+    kdi::mbar_init(bar0, 1);
+    kdi::mbar_init(bar0 + 8u, 1);
+    kdi::fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int b, int64_t row) {  // thread 0: copy the raw source row into buffer b
+    const int64_t srow = rowmap ? rowmap[row] : row;
+    const uint32_t dst = kdi::smem_u32(raw0 + (size_t)b * raw_pitch);
+    const uint32_t bar = bar0 + 8u * b;
+    kdi::mbar_arrive_expect_tx(bar, raw_bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(src + srow * S)), "r"(raw_bytes), "r"(bar)
+                 : "memory");
+  };
+  int64_t row = blockIdx.x;
+  if (row < n_rows && tid == 0) issue(0, row);
+  for (int it = 0; row < n_rows; row += gridDim.x, ++it) {
+    const int b = it & 1;
+    // (every thread is past the compaction of the previous row - the barrier before its reductions -
+    // so the other buffer may be overwritten)
+    if (tid == 0 && row + gridDim.x < n_rows) issue(b ^ 1, row + gridDim.x);
+    kdi::mbar_wait(bar0 + 8u * b, (uint32_t)((it >> 1) & 1));
+    const T* x = reinterpret_cast<const T*>(raw0 + (size_t)b * raw_pitch);
+    __syncthreads();  // the previous row's output pass has finished reading v
+    if (runs) {
+      for (int q = warp; q < n_runs; q += kNormThreads / 32) {
+        const int3 run = runs[q];
+        for (int j = lane; j < run.y; j += 32) v[run.z + j] = (float)x[run.x + j];
+      }
+    } else {
+      for (int64_t j = tid; j < s_eff; j += kNormThreads) v[j] = (float)x[j];
+    }
+    __syncthreads();
+    float mean = 0.f;
+    if (metric == KDI_NCC) {
+      double s = 0.0;
+      for (int64_t j = tid; j < s_eff; j += kNormThreads) s += (double)v[j];
+      s = block_sum(s, red);
+      mean = (float)(s / (double)s_eff);
+    }
+    double ss = 0.0;
+    for (int64_t j = tid; j < s_eff; j += kNormThreads) {
+      const float c = v[j] - mean;
+      ss += (double)c * (double)c;
+    }
+    ss = block_sum(ss, red);
+    const float norm = (float)sqrt(ss);
+    float* o32 = a32 + row * s_pitch;
+    uint16_t* o16 = a16 + row * kp;
+    for (int64_t j = 4 * (int64_t)tid; j < kp; j += 4 * kNormThreads) {
+      float o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? (v[j + q] - mean) / norm : 0.f;
+      if (j < s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+      uint2 h;
+      h.x = (uint32_t)to16<BF16>(o[0]) | ((uint32_t)to16<BF16>(o[1]) << 16);
+      h.y = (uint32_t)to16<BF16>(o[2]) | ((uint32_t)to16<BF16>(o[3]) << 16);
+      *reinterpret_cast<uint2*>(o16 + j) = h;
+    }
+  }
+}
+
 // four consecutive elements of a float32 / uint8 row as float4
 __device__ __forceinline__ float4 load4(const float* row, int j) {
   return __ldg(reinterpret_cast<const float4*>(row) + j);
@@ -281,10 +368,32 @@ template <typename T>
 int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_t* rowmap,
                    const int32_t* cols, int64_t rows, int64_t s_eff, int metric, int bf16,
                    float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
-                   uint32_t* ready, int64_t ready_row0) {
+                   uint32_t* ready, int64_t ready_row0, bool use_bulk, const int3* runs, int n_runs, int sm_count) {
   const T* s = reinterpret_cast<const T*>(src);
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
   const size_t stage_bytes = (size_t)s_eff * sizeof(float);
+  // bulk-staged kernel: 16-byte aligned raw rows that fit twice beside the compact row
+  const size_t raw_bytes = (size_t)S * sizeof(T);
+  const size_t bulk_smem = 2 * ((raw_bytes + 127) & ~(size_t)127) + stage_bytes;
+  if (use_bulk && (raw_bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(src) % 16) == 0 && raw_bytes < (1u << 20) &&
+      bulk_smem <= 200 * 1024 && (cols == nullptr || runs != nullptr) && (reinterpret_cast<uintptr_t>(a32) % 16) == 0 &&
+      (reinterpret_cast<uintptr_t>(a16) % 8) == 0) {
+    // a resident grid: as many CTAs as fit (shared memory bound), each loops over its rows
+    int per_sm = (int)((220 * 1024) / (bulk_smem + 2048));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+    unsigned g = (unsigned)(per_sm * sm_count);
+    if (g > grid) g = grid;
+    if (bf16) {
+      cudaFuncSetAttribute(kdi_normalize_bulk<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      kdi_normalize_bulk<T, true><<<g, kNormThreads, bulk_smem, stream>>>(s, S, rowmap, cols ? runs : nullptr, n_runs, s_eff, metric,
+                                                                          a32, s_pitch, o16, kp, rows, (uint32_t)raw_bytes);
+    } else {
+      cudaFuncSetAttribute(kdi_normalize_bulk<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      kdi_normalize_bulk<T, false><<<g, kNormThreads, bulk_smem, stream>>>(s, S, rowmap, cols ? runs : nullptr, n_runs, s_eff, metric,
+                                                                           a32, s_pitch, o16, kp, rows, (uint32_t)raw_bytes);
+    }
+    return 0;
+  }
   if (stage_bytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(a32) % 16) == 0 &&
       (reinterpret_cast<uintptr_t>(a16) % 8) == 0) {
     // (per launch, not once per process: the attribute is per device)
@@ -364,6 +473,9 @@ int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int
   const bool plain = !d_rowmap && !d_cols && s_eff == S;
   kdi_span span(ctx, stream, max_ctas > 0 ? "normalize (resident grid)" : "normalize");
   const bool reg_path = kdi_normalize_is_light(S, s_eff, d_rowmap != nullptr, d_cols != nullptr) && s_pitch == S;
+  // bulk-staged kernel for everything else, unless switched off (KDI_BULK_NORMALIZE=0) or the rows are
+  // being consumed concurrently through readiness counters (register-resident kernel only)
+  const bool use_bulk = ctx->bulk_normalize && ready == nullptr && (d_cols == nullptr || d_cols == ctx->d_cols);
   (void)plain;
   if (src_dtype == KDI_F32 && reg_path && (reinterpret_cast<uintptr_t>(src) % 16) == 0) {
     launch_regs_any<float>(stream, reinterpret_cast<const float*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
@@ -373,19 +485,19 @@ int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int
     switch (src_dtype) {
       case KDI_U8:
         launch_generic<uint8_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                s_pitch, a16, kp, grid, ready, ready_row0);
+                                s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count);
         break;
       case KDI_U16:
         launch_generic<uint16_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                 s_pitch, a16, kp, grid, ready, ready_row0);
+                                 s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count);
         break;
       case KDI_F32:
         launch_generic<float>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                              s_pitch, a16, kp, grid, ready, ready_row0);
+                              s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count);
         break;
       case KDI_F64:
         launch_generic<double>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                               s_pitch, a16, kp, grid, ready, ready_row0);
+                               s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count);
         break;
       default:
         return kdi_fail(ctx, KDI_EINVAL, "unknown source dtype %d", src_dtype);
