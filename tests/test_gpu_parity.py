@@ -73,7 +73,7 @@ def test_bulk_staged_normalise_is_bit_identical(ctx, src_dtype, masked, nav):
             idx, sc = ctx.dictionary_indexing(raw, 700, dic, 1500, _lib.KDI_NDP, 7, nav_mask=row_mask)
             out[bulk] = (rows, idx, sc)
     finally:
-        ctx.set_option(_lib.OPT_BULK_NORMALIZE, 1)
+        ctx.set_option(_lib.OPT_BULK_NORMALIZE, 0)
         ctx.set_signal_mask(None)
     for a, b in zip(out[1], out[0]):
         assert np.array_equal(a, b)
