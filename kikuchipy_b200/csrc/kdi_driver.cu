@@ -713,7 +713,9 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
         if (cudaEventRecord(ctx->ev[8], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
         if (rc == KDI_OK) rc = run_overlapped(ctx, job, exp, dict, post, 0, nullptr, job->tile_ready, e_fill);
       } else {
-        rc = fill_dict(ctx, st, dict, 0, g1_rows, dsrc, S, 0, nullptr);
+        // (generated dictionaries: a resident grid that strides over the rotations - one short-lived
+        // CTA per rotation costs the projection kernel ~70 % more time)
+        rc = fill_dict(ctx, st, dict, 0, g1_rows, dsrc, S, dsrc.mp ? 8 * ctx->sm_count : 0, nullptr);
         if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
         if (rc == KDI_OK && overlap_ok) {
           // first quarter against every row block, then the row-block groups over the rest
