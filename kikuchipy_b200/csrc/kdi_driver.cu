@@ -656,12 +656,14 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
     // pipeline stages until a few KB of shared memory per SM are left over
     while (job->plan.stages > 3 && kdi_gemm_free_smem(ctx, &job->plan) < 8192) job->plan.stages -= 1;
   }
-  // (event mode splits the dictionary between two streams; only the register-resident normalise kernel
-  // can share SMs that way - the kernels that stage rows in shared memory, and the projection kernel,
-  // keep the SMs' shared memory for as long as they run and would only block each other and the
-  // experimental rows, so their dictionaries are prepared in one piece at full speed)
-  const bool light = !dsrc.mp && kdi_normalize_is_light(S, s_eff, false, ctx->mask_S != 0) &&
-                     (dict_dtype == KDI_F32 || dict_dtype == KDI_U8);
+  // (event mode splits the dictionary between two streams; only kernels with a small shared-memory
+  // footprint can share SMs that way - the register-resident normalise kernel, the projection kernel
+  // for small detectors - the kernels that stage whole rows in shared memory keep it for as long as
+  // they run and would only block each other and the experimental rows, so their dictionaries are
+  // prepared in one piece at full speed)
+  const bool light = dsrc.mp ? S * 4 <= 16384  // (projection kernel: one float32 pattern per CTA in shared memory)
+                             : (kdi_normalize_is_light(S, s_eff, false, ctx->mask_S != 0) &&
+                                (dict_dtype == KDI_F32 || dict_dtype == KDI_U8));
   const bool early = overlap_ok && !flag_mode && (light || ctx->overlap == 2) &&
                      (ctx->overlap == 2 ? dict_rows >= 4 * KDI_TILE_N : (dict_rows >= 16384 && exp_rows >= 2048));
   int64_t g1_rows = dict_rows;
