@@ -111,6 +111,10 @@ extern "C" {
                                    Measured on B200: the prepare step is bound by instruction issue (exact IEEE
                                    division + float64 statistics, ~68 instructions per pixel), not by memory; the
                                    bulk-staged kernel needs 2-4x the shared memory per CTA and is 1.6-2.4x slower */
+#define KDI_OPT_EARLY_SPLIT 19   /* device-resident dictionaries, event-ordered schedule: 1 = the first quarter of the
+                                   dictionary is prepared on the main stream and matched against every row block
+                                   while the rest is prepared on the other stream; 0 = the whole dictionary is
+                                   prepared at full speed first, then one tensor-core launch per row-block group */
 
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;

@@ -46,6 +46,7 @@ OPT_GEMM_SERIAL = 15
 OPT_SM_PARTITION = 16
 OPT_POST_CORESIDENT = 17
 OPT_BULK_NORMALIZE = 18
+OPT_EARLY_SPLIT = 19
 
 REFINE_ORI, REFINE_PC, REFINE_ORI_PC = 0, 1, 2
 

@@ -664,7 +664,7 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   const bool light = dsrc.mp ? S * 4 <= 16384  // (projection kernel: one float32 pattern per CTA in shared memory)
                              : (kdi_normalize_is_light(S, s_eff, false, ctx->mask_S != 0) &&
                                 (dict_dtype == KDI_F32 || dict_dtype == KDI_U8));
-  const bool early = overlap_ok && !flag_mode && (light || ctx->overlap == 2) &&
+  const bool early = overlap_ok && !flag_mode && ctx->early_split && (light || ctx->overlap == 2) &&
                      (ctx->overlap == 2 ? dict_rows >= 4 * KDI_TILE_N : (dict_rows >= 16384 && exp_rows >= 2048));
   int64_t g1_rows = dict_rows;
   cudaEvent_t e_fill = nullptr;
@@ -720,7 +720,8 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
         rc = fill_dict(ctx, st, dict, 0, g1_rows, dsrc, S, dsrc.mp ? 8 * ctx->sm_count : 0, nullptr);
         if (rc == KDI_OK && cudaEventRecord(ctx->ev[7], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
         if (rc == KDI_OK && overlap_ok) {
-          // first quarter against every row block, then the row-block groups over the rest
+          // first quarter against every row block (when the dictionary was split), then the row-block
+          // groups over the rest / over everything
           if (cudaEventRecord(ctx->ev[8], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
           const int64_t strip_rows = (int64_t)job->plan.strip_tiles * KDI_TILE_N;
           int strips_lo = g1_rows >= dict_rows ? 0 : (int)(g1_rows / strip_rows);

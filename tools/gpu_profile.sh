@@ -1,13 +1,23 @@
 #!/bin/bash
-# Final evidence for profiles/: launch list of a short bench run + one full ncu capture per kernel.
+# Evidence for profiles/ (round 2): launch list of a short bench run + one `ncu --set full` capture per
+# kernel of the path.  Reports land in gpurun_out/; tools/ncu_summary.py turns them into the summaries
+# kept under profiles/.  (The kernels of the peer-memory exchange only run with several ranks, which ncu
+# must not wrap: their times come from the KDI_TIMELINE trace, profiles/r2_timeline_n8_rank0.txt.)
 mkdir -p gpurun_out
-B="python bench.py --steps 2 --warmup 3 --no-cpu --no-generated --e2e-steps 1"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r1_launches_bench.csv $B > gpurun_out/ncu_launch.log 2>&1
+B="python bench.py --steps 2 --warmup 3 --no-cpu --no-generated --no-extras --e2e-steps 1"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv $B > gpurun_out/ncu_launch.log 2>&1
 echo "launch list exit $?"
-for k in kdi_gemm_kernel kdi_select_rescore_kernel kdi_select_warp_kernel kdi_normalize_f32_regs kdi_normalize_staged; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -o gpurun_out/prof_$k -f $B > gpurun_out/ncu_$k.log 2>&1
+S="env ROUNDS=1 REPS=3 SETTINGS=split=1 python tools/schedule_sweep.py"
+for k in kdi_gemm_kernel kdi_select_rescore_kernel kdi_select_warp_kernel kdi_normalize_f32_regs; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -o gpurun_out/r2_prof_$k -f $S > gpurun_out/ncu_$k.log 2>&1
   echo "ncu $k exit $?"
 done
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:kdi_project_kernel -s 1 -c 1 -o gpurun_out/prof_kdi_project_kernel -f python tools/project_time.py > gpurun_out/ncu_project.log 2>&1
-echo "ncu project exit $?"
+# the 64-entry-list variant at the shape of one rank's share of BASELINE configs[3]
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:kdi_gemm_kernel -s 1 -c 1 -o gpurun_out/r2_prof_kdi_gemm_kernel_kc64 -f \
+  env M=100000 N=37500 KEEP=50 ROUNDS=1 REPS=2 SETTINGS=split=1 python tools/schedule_sweep.py > gpurun_out/ncu_gemm_kc64.log 2>&1
+echo "ncu gemm kc64 exit $?"
+# masked uint8 rows (BASELINE configs[2] at quarter scale): the staged normalise kernel
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:kdi_normalize_staged -s 0 -c 1 -o gpurun_out/r2_prof_kdi_normalize_staged -f \
+  env CONFIG=3 SCALE=0.25 SAMPLE64=0 python tools/config_timeline.py > gpurun_out/ncu_normalize_staged.log 2>&1
+echo "ncu normalize_staged exit $?"
 ls -la gpurun_out/*.ncu-rep
