@@ -88,11 +88,12 @@ kdi_normalize_generic(const T* __restrict__ src, int64_t S, const int64_t* __res
   }
   ss = block_sum(ss, red);
   const float norm = (float)sqrt(ss);
+  const double rd = 1.0 / (double)norm;
   float* o32 = a32 + row * s_pitch;
   uint16_t* o16 = a16 + row * kp;
   for (int64_t j = threadIdx.x; j < kp; j += kNormThreads) {
     float v = 0.f;
-    if (j < s_eff) v = ((float)x[cols ? cols[j] : j] - mean) / norm;
+    if (j < s_eff) v = kdi_div_by_norm((float)x[cols ? cols[j] : j] - mean, rd);
     if (j < s_pitch) o32[j] = v;
     o16[j] = to16<BF16>(v);
   }
@@ -153,6 +154,7 @@ kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __rest
     }
     ss = block_sum(ss, red);
     const float norm = (float)sqrt(ss);
+    const double rd = 1.0 / (double)norm;
     float* o32 = a32 + row * s_pitch;
     uint16_t* o16 = a16 + row * kp;
     // four outputs per thread and step: 16-byte fp32 stores, 8-byte 16-bit stores (pitches are
@@ -160,7 +162,7 @@ kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __rest
     for (int64_t j = 4 * (int64_t)threadIdx.x; j < kp; j += 4 * kNormThreads) {
       float o[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? (v[j + q] - mean) / norm : 0.f;
+      for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? kdi_div_by_norm(v[j + q] - mean, rd) : 0.f;
       if (j < s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
       uint2 h;
       h.x = (uint32_t)to16<BF16>(o[0]) | ((uint32_t)to16<BF16>(o[1]) << 16);
@@ -240,12 +242,13 @@ kdi_normalize_bulk(const T* __restrict__ src, int64_t S, const int64_t* __restri
     }
     ss = block_sum(ss, red);
     const float norm = (float)sqrt(ss);
+    const double rd = 1.0 / (double)norm;
     float* o32 = a32 + row * s_pitch;
     uint16_t* o16 = a16 + row * kp;
     for (int64_t j = 4 * (int64_t)tid; j < kp; j += 4 * kNormThreads) {
       float o[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? (v[j + q] - mean) / norm : 0.f;
+      for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? kdi_div_by_norm(v[j + q] - mean, rd) : 0.f;
       if (j < s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
       uint2 h;
       h.x = (uint32_t)to16<BF16>(o[0]) | ((uint32_t)to16<BF16>(o[1]) << 16);
@@ -334,6 +337,7 @@ kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
     }
     ss = block_sum(ss, red);
     const float norm = (float)sqrt(ss);
+    const double rd = 1.0 / (double)norm;
     float4* o32 = reinterpret_cast<float4*>(a32 + cur * s_pitch);
     uint2* o16 = reinterpret_cast<uint2*>(a16 + cur * kp);
 #pragma unroll
@@ -341,7 +345,8 @@ kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
       const int j = threadIdx.x + i * kNormThreads;
       if (j < n4) {
         float4 v;
-        v.x = r[i].x / norm; v.y = r[i].y / norm; v.z = r[i].z / norm; v.w = r[i].w / norm;
+        v.x = kdi_div_by_norm(r[i].x, rd); v.y = kdi_div_by_norm(r[i].y, rd);
+        v.z = kdi_div_by_norm(r[i].z, rd); v.w = kdi_div_by_norm(r[i].w, rd);
         o32[j] = v;
         uint2 h;
         h.x = (uint32_t)to16<BF16>(v.x) | ((uint32_t)to16<BF16>(v.y) << 16);

@@ -173,12 +173,13 @@ kdi_project_kernel(const ProjParams p) {
       }
       ss = block_reduce_sum(ss, red);
       const float norm = (float)sqrt(ss);
+      const double rd = 1.0 / (double)norm;
       float* o32 = p.a32 + row * p.s_pitch;
       uint16_t* o16 = p.a16 + row * p.kp;
       for (int64_t j = 4 * (int64_t)threadIdx.x; j < p.kp; j += 4 * kProjThreads) {
         float o[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = (j + q < p.s_eff) ? (v[cols ? cols[j + q] : j + q] - mean) / norm : 0.f;
+        for (int q = 0; q < 4; ++q) o[q] = (j + q < p.s_eff) ? kdi_div_by_norm(v[cols ? cols[j + q] : j + q] - mean, rd) : 0.f;
         if (j < p.s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
         uint2 h;
         h.x = (uint32_t)op16<BF16>(o[0]) | ((uint32_t)op16<BF16>(o[1]) << 16);

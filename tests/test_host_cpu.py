@@ -514,3 +514,26 @@ def test_gpu_metrics_subclass_the_reference_abc(monkeypatch):
     finally:
         monkeypatch.undo()
         importlib.reload(kb.similarity_metrics)
+
+
+def test_division_by_the_row_norm_through_a_double_reciprocal_is_exact():
+    """The prepare kernels compute (x - mean) / norm as float32(float64(x - mean) * (1 / float64(norm)))
+    (csrc/kdi_internal.cuh, kdi_div_by_norm: one reciprocal per row instead of an IEEE division per
+    pixel).  That must be the correctly rounded float32 quotient - NumPy's - for every operand pair,
+    including divisors whose significand is all ones and quotients next to 1."""
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    for case in range(3):
+        c = (rng.standard_normal(n) * rng.choice([1e-3, 1, 30, 1e4], n)).astype(np.float32)
+        norm = np.abs(rng.standard_normal(n) * rng.choice([1e-2, 1, 500, 7e4], n)).astype(np.float32) + np.float32(1e-20)
+        if case == 1:
+            bits = (norm.view(np.uint32) & np.uint32(0xFF800000)) | np.uint32(0x7FFFC0) | rng.integers(0, 64, n).astype(np.uint32)
+            norm = bits.view(np.float32)
+        if case == 2:
+            c = np.nextafter(norm, (np.inf * rng.choice([-1, 1], n)).astype(np.float32))
+        want = c / norm
+        got = (c.astype(np.float64) * (1.0 / norm.astype(np.float64))).astype(np.float32)
+        assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        z = (np.float64(np.float32(0.0)) * (1.0 / np.float64(np.float32(0.0)))).astype(np.float32)
+    assert np.isnan(z)  # 0 / 0 (constant pattern) stays NaN

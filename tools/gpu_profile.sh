@@ -9,7 +9,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "launch list exit $?"
 S="env ROUNDS=1 REPS=3 SETTINGS=split=1 python tools/schedule_sweep.py"
 for k in kdi_gemm_kernel kdi_select_rescore_kernel kdi_select_warp_kernel kdi_normalize_f32_regs; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -o gpurun_out/r2_prof_$k -f $S > gpurun_out/ncu_$k.log 2>&1
+  skip=2; [ $k = kdi_gemm_kernel ] && skip=4
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o gpurun_out/r2_prof_$k -f $S > gpurun_out/ncu_$k.log 2>&1
   echo "ncu $k exit $?"
 done
 # the 64-entry-list variant at the shape of one rank's share of BASELINE configs[3]
