@@ -270,7 +270,7 @@ __device__ __forceinline__ float4 load4(const uint8_t* row, int j) {
 // fast path: float32 or uint8 source, no gathers, S % 4 == 0: the row lives in registers (one HBM
 // read, no shared-memory staging)
 template <typename T, int V, bool BF16>
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, V <= 4 ? 4 : 1)  // (64 registers: four CTAs with two rows in flight each)
 kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
                        float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
                        int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0,

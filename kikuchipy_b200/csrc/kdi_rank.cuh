@@ -64,4 +64,71 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t* keys, int n, int lane) 
   __syncwarp();
 }
 
+// ---- N = 32 R keys held by one warp in registers: element e = r * 32 + lane lives in x[r] -----------
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, mask);
+  const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), mask);
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// one compare-exchange layer of a bitonic network at distance j inside blocks of size k (descending
+// where (e & k) == 0); partners at distance >= 32 are registers of the same lane, closer ones are
+// fetched by shuffle
+template <int R>
+__device__ __forceinline__ void bitonic_layer_regs(uint64_t (&x)[R], int lane, int k, int j) {
+  if (j >= 32) {
+    const int dr = j >> 5;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((r & dr) == 0) {
+        const bool desc = (((r << 5) | lane) & k) == 0;
+        const uint64_t a = x[r], b = x[r | dr];
+        const uint64_t hi = a > b ? a : b, lo = a > b ? b : a;
+        x[r] = desc ? hi : lo;
+        x[r | dr] = desc ? lo : hi;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint64_t other = shfl_xor_u64(x[r], j);
+      const bool lower = (lane & j) == 0;
+      const bool desc = (((r << 5) | lane) & k) == 0;
+      const bool take_max = lower == desc;
+      const bool gt = x[r] > other;
+      x[r] = (take_max == gt) ? x[r] : other;
+    }
+  }
+}
+
+// full descending sort of the 32 R keys
+template <int R>
+__device__ __forceinline__ void warp_sort_desc_regs(uint64_t (&x)[R], int lane) {
+  constexpr int N = 32 * R;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) bitonic_layer_regs<R>(x, lane, k, j);
+  }
+}
+
+// best <- the 32 R largest of (best U chunk), both sorted descending on entry, sorted descending on exit:
+// max(best[e], chunk[N - 1 - e]) is a bitonic sequence holding the N largest; one merge stage sorts it
+template <int R>
+__device__ __forceinline__ void warp_merge_top_regs(uint64_t (&best)[R], const uint64_t (&chunk)[R], int lane) {
+  constexpr int N = 32 * R;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const uint64_t rev = shfl_u64(chunk[R - 1 - r], 31 - lane);
+    best[r] = best[r] > rev ? best[r] : rev;
+  }
+#pragma unroll
+  for (int j = N >> 1; j > 0; j >>= 1) bitonic_layer_regs<R>(best, lane, N, j);
+}
+
 }  // namespace kdi

@@ -110,11 +110,17 @@ __device__ __forceinline__ int select_candidates(const uint2* __restrict__ c, in
 }
 
 // ---- warp-per-row selection --------------------------------------------------------------------
-// The same streaming selection as select_candidates, at warp scope: no block barriers, four rows
-// per CTA.  Survivors of the threshold filter are compacted into a 256-key shared-memory buffer
-// with ballots; when the buffer could overflow it is sorted by the warp, the kc best are kept
-// and the threshold is raised.  One row costs a few thousand warp instructions.
-constexpr int kWarpBuf = 256;
+// One warp per experimental row, four rows per CTA, no block barriers.  The row's n_strips x KC
+// candidates are read twice (the second time from L1 / L2):
+//  1. a pre-pass gives a lower bound on the row's KC-th best score that is much tighter than the
+//     threshold the GEMM kernel published (which only bounds the KC-th best of the best STRIP, so
+//     nearly every entry passes it): each lane keeps the KC / 32 best keys it sees, and the smallest of
+//     those over the lanes has at least KC entries at or above it;
+//  2. the entries that pass are compacted (ballots) into a small shared-memory staging area; whenever
+//     KC of them have gathered they are sorted IN REGISTERS (32 KC/32 keys per warp, bitonic network over
+//     shuffles) and merged into the running best list, also in registers, and the threshold rises to
+//     the list's last entry.  Typically 3-5 chunks per row; ~1 k warp instructions instead of the ~5 k
+//     of sorting a 256-key shared-memory buffer.
 constexpr int kWarpSelRows = 4;  // rows (warps) per CTA
 
 template <int KC>
@@ -122,27 +128,20 @@ __global__ void __launch_bounds__(32 * kWarpSelRows)
 kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restrict__ thr, int n_strips,
                        int64_t row0, int64_t row_end, int64_t index_offset, float inv_scale,
                        float* __restrict__ out_approx, int64_t* __restrict__ out_gidx, const kdi_route route) {
-  __shared__ uint64_t s_keys[kWarpSelRows][kWarpBuf];
+  constexpr int R = KC / 32;
+  __shared__ uint64_t s_stage[kWarpSelRows][KC + 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = row0 + (int64_t)blockIdx.x * kWarpSelRows + warp;
   if (row >= row_end) return;  // whole warp
-  uint64_t* keys = s_keys[warp];
+  uint64_t* stage = s_stage[warp];
   const int64_t total = (int64_t)n_strips * KC;
   const uint2* c = cand + row * total;
   uint32_t tkey = thr[row];
-  int count = 0;  // warp-uniform
-  bool sorted = true;
   constexpr int kBatch = 4;
-  // Pre-pass: a lower bound on the row's KC-th best score that is much tighter than the threshold the
-  // GEMM kernel published (which only bounds the KC-th best of the best STRIP, so ~all n_strips x KC
-  // entries pass it).  Each lane keeps the KC/32 best keys of the entries it sees; the smallest of
-  // those over the lanes has at least KC entries at or above it.  With it ~4 KC entries survive the
-  // filter below instead of ~n_strips x KC, and the shared-memory buffer is sorted once.
   {
-    constexpr int R = KC / 32;
-    uint32_t best[R];
+    uint32_t top[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) best[r] = 0u;
+    for (int r = 0; r < R; ++r) top[r] = 0u;
     for (int64_t base = 0; base < total; base += 32 * kBatch) {
       uint2 e[kBatch];
 #pragma unroll
@@ -155,13 +154,13 @@ kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restric
         uint32_t k = e[b].y != 0xFFFFFFFFu ? float_key(__uint_as_float(e[b].x)) : 0u;
 #pragma unroll
         for (int r = 0; r < R; ++r) {  // insert into the descending list
-          const uint32_t hi = k > best[r] ? k : best[r];
-          k = k > best[r] ? best[r] : k;
-          best[r] = hi;
+          const uint32_t hi = k > top[r] ? k : top[r];
+          k = k > top[r] ? top[r] : k;
+          top[r] = hi;
         }
       }
     }
-    uint32_t lo = best[R - 1];  // 0 when the lane saw fewer than R valid entries: no tightening then
+    uint32_t lo = top[R - 1];  // 0 when the lane saw fewer than R valid entries: no tightening then
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const uint32_t other = __shfl_xor_sync(0xffffffffu, lo, o);
@@ -169,6 +168,24 @@ kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restric
     }
     tkey = lo > tkey ? lo : tkey;
   }
+  uint64_t best[R];  // running KC best, sorted descending over e = r * 32 + lane; 0 = empty
+#pragma unroll
+  for (int r = 0; r < R; ++r) best[r] = 0;
+  int staged = 0;  // warp-uniform
+  int taken = 0;   // entries merged so far (warp-uniform)
+  auto flush = [&](int n) {  // sort the first n <= KC staged keys (the rest of the chunk is empty) and merge them
+    uint64_t chunk[R];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) chunk[r] = (r * 32 + lane) < n ? stage[r * 32 + lane] : 0;
+    kdi::warp_sort_desc_regs<R>(chunk, lane);
+    kdi::warp_merge_top_regs<R>(best, chunk, lane);
+    taken += n;
+    if (taken >= KC) {  // the list is full: nothing below its last entry can enter any more
+      const uint32_t k32 = (uint32_t)(kdi::shfl_u64(best[R - 1], 31) >> 32);
+      tkey = k32 > tkey ? k32 : tkey;
+    }
+  };
   for (int64_t base = 0; base < total; base += 32 * kBatch) {
     uint2 e[kBatch];
 #pragma unroll
@@ -181,43 +198,45 @@ kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restric
       const bool pass = e[b].y != 0xFFFFFFFFu && float_key(__uint_as_float(e[b].x)) >= tkey;
       const unsigned bal = __ballot_sync(0xffffffffu, pass);
       if (bal) {
-        if (pass) keys[count + __popc(bal & ((1u << lane) - 1u))] = pack_key(__uint_as_float(e[b].x), e[b].y);
-        count += __popc(bal);
-        sorted = false;
-        if (count > kWarpBuf - 32) {  // the next ballot might not fit: keep the KC best
-          for (int j = count + lane; j < kWarpBuf; j += 32) keys[j] = 0;
-          warp_sort_desc(keys, kWarpBuf, lane);
-          count = KC;
-          const uint32_t k32 = (uint32_t)(keys[KC - 1] >> 32);
-          tkey = k32 > tkey ? k32 : tkey;
-          sorted = true;
+        if (pass) stage[staged + __popc(bal & ((1u << lane) - 1u))] = pack_key(__uint_as_float(e[b].x), e[b].y);
+        staged += __popc(bal);
+        if (staged >= KC) {
+          flush(KC);
+          // the (fewer than 32) entries beyond the chunk move to the front
+          const int rest = staged - KC;
+          __syncwarp();
+          const uint64_t mv = lane < rest ? stage[KC + lane] : 0;
+          __syncwarp();
+          if (lane < rest) stage[lane] = mv;
+          staged = rest;
         }
       }
     }
   }
-  if (!sorted) {
-    int n2 = 64;
-    while (n2 < count) n2 <<= 1;
-    for (int j = count + lane; j < n2; j += 32) keys[j] = 0;  // below every real key
-    warp_sort_desc(keys, n2, lane);
-  }
-  __syncwarp();
+  if (staged > 0) flush(staged);
+  const int count = taken;
   const int nsel = count < KC ? count : KC;
   if (route.world > 0) {
     // sharded job: (tensor-core score, GLOBAL dictionary row) records straight into the symmetric
     // block of the rank that owns this row's slice - a peer store over NVLink unless that is us
     const int64_t owner = row / route.per;
     uint2* dst = route.recv[owner] + (((int64_t)route.rank * route.per) + (row - owner * route.per)) * KC;
-    for (int i = lane; i < KC; i += 32)
-      dst[i] = i < nsel ? make_uint2(__float_as_uint(key_score(keys[i]) * inv_scale),
-                                     (uint32_t)((int64_t)key_index(keys[i]) + index_offset))
-                        : make_uint2(0xFF800000u, 0xFFFFFFFFu);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = r * 32 + lane;
+      dst[i] = (i < nsel && best[r] != 0) ? make_uint2(__float_as_uint(key_score(best[r]) * inv_scale),
+                                                       (uint32_t)((int64_t)key_index(best[r]) + index_offset))
+                                          : make_uint2(0xFF800000u, 0xFFFFFFFFu);
+    }
     __threadfence_system();
     return;
   }
-  for (int i = lane; i < KC; i += 32) {
-    out_approx[row * KC + i] = i < nsel ? key_score(keys[i]) * inv_scale : -INFINITY;
-    out_gidx[row * KC + i] = i < nsel ? (int64_t)key_index(keys[i]) + index_offset : -1;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = r * 32 + lane;
+    const bool ok = i < nsel && best[r] != 0;
+    out_approx[row * KC + i] = ok ? key_score(best[r]) * inv_scale : -INFINITY;
+    out_gidx[row * KC + i] = ok ? (int64_t)key_index(best[r]) + index_offset : -1;
   }
 }
 
@@ -686,7 +705,7 @@ int kdi_launch_select_only(kdi_ctx* ctx, cudaStream_t stream, int64_t rows, cons
   cudaFuncSetAttribute(kdi_select_warp_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   cudaFuncSetAttribute(kdi_select_warp_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   cudaFuncSetAttribute(kdi_select_warp_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-  const size_t pad = kdi_post_pad_bytes(ctx, (size_t)kWarpSelRows * kWarpBuf * 8);
+  const size_t pad = kdi_post_pad_bytes(ctx, (size_t)kWarpSelRows * (plan->kc + 32) * 8);
   kdi_span span(ctx, stream, "select (warp per row)");
   if (plan->kc == 32)
     kdi_select_warp_kernel<32><<<grid, 32 * kWarpSelRows, pad, stream>>>(
