@@ -116,6 +116,16 @@ extern "C" {
                                    while the rest is prepared on the other stream; 0 = the whole dictionary is
                                    prepared at full speed first, then one tensor-core launch per row-block group */
 
+#define KDI_OPT_DIV_DOUBLE 20    /* 1 = the prepare kernels divide by the row norm through the double reciprocal
+                                   everywhere; 0 (default) = through the float32 FMA sequence wherever that is exact
+                                   (rows in the normal range; bit-identical results, no conversions)           */
+#define KDI_OPT_DICT_VIEW 21     /* 1 (default) = a device-resident, unmasked float32 dictionary handed to a driver
+                                   entry point (kdi_dictionary_indexing, kdi_shard_*) is not copied as normalised
+                                   float32 rows: the exact scores read the caller's rows and apply the row's
+                                   (mean, norm) on the fly with the prepare kernel's arithmetic - bit-identical
+                                   scores, 40 % fewer bytes in the prepare step.  The caller's buffer must stay
+                                   alive until the call returns (shards: until kdi_shard_release).  0 = always copy */
+
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;
 

@@ -16,6 +16,7 @@ from .similarity_metrics import (
 )
 from .distributed import dictionary_indexing_sharded, gather_topk, shard_bounds
 from .io_edax import load_edax_binary
+from .io_h5ebsd import H5EBSDScan, load_h5ebsd, save_h5ebsd
 from .io_nordif import NordifScan, load, load_nordif
 from .io_oxford import load_oxford_binary
 from .master_pattern import GeneratedDictionary, direction_cosines, get_patterns
@@ -39,6 +40,7 @@ __all__ = [
     "Detector",
     "DictionaryIndexingResult",
     "GeneratedDictionary",
+    "H5EBSDScan",
     "KdiError",
     "MergedCrystalMap",
     "NordifScan",
@@ -55,6 +57,7 @@ __all__ = [
     "get_patterns",
     "load",
     "load_edax_binary",
+    "load_h5ebsd",
     "load_nordif",
     "load_oxford_binary",
     "gather_topk",
@@ -66,6 +69,7 @@ __all__ = [
     "refine_projection_center",
     "remove_dynamic_background",
     "remove_static_background",
+    "save_h5ebsd",
     "shard_bounds",
 ]
 __version__ = "0.1.0"

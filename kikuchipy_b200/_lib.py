@@ -47,6 +47,8 @@ OPT_SM_PARTITION = 16
 OPT_POST_CORESIDENT = 17
 OPT_BULK_NORMALIZE = 18
 OPT_EARLY_SPLIT = 19
+OPT_DIV_DOUBLE = 20
+OPT_DICT_VIEW = 21
 
 REFINE_ORI, REFINE_PC, REFINE_ORI_PC = 0, 1, 2
 
@@ -252,6 +254,13 @@ class Patterns:
     def compute(self):
         return np.asarray(self)
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def close(self):
         if self._h:
             self._ctx._lib.kdi_patterns_destroy(self._ctx._h, self._h)
@@ -269,8 +278,11 @@ class Shard:
     """This rank's prepared experimental set + dictionary shard between the steps of the
     sharded pipeline (``kdi_shard_*`` in include/kdi.h)."""
 
-    def __init__(self, ctx: "Context", handle: int, rows: int, kc: int):
+    def __init__(self, ctx: "Context", handle: int, rows: int, kc: int, keep=None):
         self._ctx, self._h, self.rows, self.kc = ctx, handle, rows, kc
+        # a device-resident float32 dictionary may be held as a VIEW of the caller's rows
+        # (KDI_OPT_DICT_VIEW): the buffer has to outlive the shard
+        self._keep = keep
 
     def rescore_owned(self, gidx, approx=None, keep_n: int = 0):
         """Exact scores of the candidates in ``gidx`` (at least ``rows`` x kc) whose dictionary rows
@@ -331,6 +343,7 @@ class Shard:
         if self._h:
             self._ctx._lib.kdi_shard_release(self._ctx._h, self._h)
             self._h = None
+            self._keep = None
 
     def __del__(self):
         try:
@@ -767,8 +780,8 @@ class Context:
                 gidx.data_ptr(), C.byref(h),
             )
         )
-        del ekeep, dkeep
-        return Shard(self, h.value, kept, kc), approx, gidx
+        del ekeep
+        return Shard(self, h.value, kept, kc, keep=(dictionary, dkeep)), approx, gidx
 
     def comm_bytes_needed(self, world: int, rows: int, keep_n: int) -> int:
         kc = self.candidate_capacity(keep_n)
@@ -804,6 +817,7 @@ class Context:
         h = _vp()
         self._stream_sync(dev)
         rmp = rm.ctypes.data if rm is not None else None
+        held = None
         if isinstance(dictionary, tuple):
             mp, rotations = dictionary
             rptr, rloc, rkeep, n = _rotations(rotations)
@@ -821,10 +835,10 @@ class Context:
             self._check(self._lib.kdi_shard_run_peer(
                 self._h, comm._h, eptr, eloc, ecode, exp_rows, dptr, dloc, dcode, dict_rows, S, metric, int(keep_n), rmp,
                 int(dict_total), scores.data_ptr(), idx.data_ptr(), flags.data_ptr(), C.byref(n_flag), C.byref(h)))
-            del dkeep
+            held = (dictionary, dkeep)
         del ekeep
         kc = self.candidate_capacity(keep_n)
-        return Shard(self, h.value, kept, kc), idx, scores, flags[: n_flag.value]
+        return Shard(self, h.value, kept, kc, keep=held), idx, scores, flags[: n_flag.value]
 
     # -- dictionary generation -------------------------------------------------------------------
     def master_pattern(self, upper, lower, direction_cosines, scale=None, rescale=False, out_min=-1.0,

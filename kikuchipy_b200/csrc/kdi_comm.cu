@@ -184,7 +184,8 @@ kdi_merge_route_kernel(const uint2* __restrict__ recv, int world, int64_t per, i
 
 // ---- step 3: exact scores of the requests this rank received ------------------------------------------
 __global__ void __launch_bounds__(128)
-kdi_rescore_requests_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32, int64_t s_pitch,
+kdi_rescore_requests_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
+                            const float* __restrict__ dict_raw, const float4* __restrict__ dstat, int64_t s_pitch,
                             const uint2* __restrict__ req, const uint32_t* __restrict__ req_cnt, int world,
                             int64_t req_cap, int64_t per, int kc, PeerTable blocks, size_t exact_off) {
   const int lane = threadIdx.x & 31;
@@ -208,8 +209,9 @@ kdi_rescore_requests_kernel(const float* __restrict__ exp32, const float* __rest
     const uint2 r = __ldg(req + (int64_t)s * req_cap + off);
     const int64_t row = (int64_t)(r.x >> 8);
     const int slot = (int)(r.x & 255u);
-    const float d = warp_dot(reinterpret_cast<const float4*>(exp32 + row * s_pitch),
-                             reinterpret_cast<const float4*>(dict32 + (int64_t)r.y * s_pitch), n4, lane);
+    // (a view-mode dictionary is rescored from its source rows: same value, bit for bit)
+    const float d = kdi::warp_dot_dict(reinterpret_cast<const float4*>(exp32 + row * s_pitch), dict32, dict_raw, dstat,
+                                       (int64_t)r.y, s_pitch, n4, lane);
     if (lane == 0) {
       const int64_t owner = row / per;
       reinterpret_cast<float*>(blocks.p[owner] + exact_off)[(row - owner * per) * kc + slot] = d;
@@ -335,7 +337,8 @@ int kdi_comm_exchange(kdi_ctx* ctx, kdi_comm* comm, const kdi_patterns* exp, con
   {
     kdi_span span(ctx, st, "rescore (request queue)");
     kdi_rescore_requests_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(
-        exp->a32, dict->a32, exp->s_pitch, reinterpret_cast<const uint2*>(mine + l.req),
+        exp->a32, dict->a32, dict->a32 ? nullptr : dict->raw, dict->rstat, exp->s_pitch,
+        reinterpret_cast<const uint2*>(mine + l.req),
         reinterpret_cast<const uint32_t*>(mine + l.req_cnt), world, l.req_cap, l.per, kc, blocks, l.exact);
     KDI_CUDA(ctx, cudaGetLastError());
     ctx->tm.kernel_launches++;

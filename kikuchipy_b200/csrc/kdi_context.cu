@@ -473,6 +473,12 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
     case KDI_OPT_BULK_NORMALIZE:
       ctx->bulk_normalize = value != 0;
       return KDI_OK;
+    case KDI_OPT_DIV_DOUBLE:
+      ctx->div_double = value != 0;
+      return KDI_OK;
+    case KDI_OPT_DICT_VIEW:
+      ctx->dict_view = value != 0;
+      return KDI_OK;
     case KDI_OPT_POST_CORESIDENT:
       if (value < 0 || value > 8) return kdi_fail(ctx, KDI_EINVAL, "post_coresident must be 0..8");
       ctx->post_coresident = (int)value;
@@ -571,7 +577,7 @@ int kdi_set_signal_mask(kdi_ctx* ctx, const uint8_t* mask, int64_t S) {
 
 // ---- pattern sets ------------------------------------------------------------------------
 
-int kdi_patterns_alloc(kdi_ctx* ctx, int64_t rows, int64_t S, int metric, kdi_patterns** out) {
+int kdi_patterns_alloc(kdi_ctx* ctx, int64_t rows, int64_t S, int metric, kdi_patterns** out, const float* view_of) {
   if (rows < 0 || S <= 0) return kdi_fail(ctx, KDI_EINVAL, "pattern set of %lld x %lld", (long long)rows, (long long)S);
   if (metric != KDI_NCC && metric != KDI_NDP) return kdi_fail(ctx, KDI_EINVAL, "unknown metric %d", metric);
   if (ctx->mask_S && ctx->mask_S != S)
@@ -587,10 +593,18 @@ int kdi_patterns_alloc(kdi_ctx* ctx, int64_t rows, int64_t S, int metric, kdi_pa
   p->compute_dtype = ctx->compute_dtype;
   const size_t n32 = (size_t)(rows > 0 ? rows : 1) * p->s_pitch * sizeof(float);
   const size_t n16 = (size_t)(rows > 0 ? rows : 1) * p->kp * 2;
-  int rc = kdi_dev_alloc(ctx, n32, reinterpret_cast<void**>(&p->a32), &p->a32_bytes);
+  int rc = KDI_OK;
+  if (view_of) {
+    if (ctx->mask_S || (S % 4) != 0) { delete p; return kdi_fail(ctx, KDI_EINTERNAL, "view mode needs unmasked rows of a multiple of 4 values"); }
+    p->raw = view_of;
+    rc = kdi_dev_alloc(ctx, (size_t)(rows > 0 ? rows : 1) * sizeof(float4), reinterpret_cast<void**>(&p->rstat), &p->rstat_bytes);
+  } else {
+    rc = kdi_dev_alloc(ctx, n32, reinterpret_cast<void**>(&p->a32), &p->a32_bytes);
+  }
   if (rc == KDI_OK) rc = kdi_dev_alloc(ctx, n16, &p->a16, &p->a16_bytes);
   if (rc != KDI_OK) {
     kdi_dev_free(ctx, p->a32, p->a32_bytes);
+    kdi_dev_free(ctx, p->rstat, p->rstat_bytes);
     delete p;
     return rc;
   }
@@ -598,16 +612,29 @@ int kdi_patterns_alloc(kdi_ctx* ctx, int64_t rows, int64_t S, int metric, kdi_pa
   return KDI_OK;
 }
 
+int kdi_patterns_materialize(kdi_ctx* ctx, cudaStream_t stream, kdi_patterns* p) {
+  if (p->a32 || !p->raw) return KDI_OK;
+  const size_t n32 = (size_t)(p->rows > 0 ? p->rows : 1) * p->s_pitch * sizeof(float);
+  KDI_TRY(kdi_dev_alloc(ctx, n32, reinterpret_cast<void**>(&p->a32), &p->a32_bytes));
+  // the same kernel over the same source: the 16-bit rows and the statistics are rewritten with the
+  // values they already hold
+  return kdi_launch_normalize(ctx, stream, p->raw, KDI_F32, p->S, nullptr, nullptr, p->rows, p->s_eff, p->metric,
+                              p->compute_dtype, p->a32, p->s_pitch, p->a16, p->kp, 0, nullptr, 0, 0, p->rstat);
+}
+
 int kdi_patterns_fill(kdi_ctx* ctx, cudaStream_t stream, kdi_patterns* p, int64_t row_offset,
                       const void* d_src, int src_dtype, int64_t n_rows, const int64_t* d_rowmap,
                       int max_ctas, uint32_t* ready) {
   if (row_offset < 0 || row_offset + n_rows > p->rows)
     return kdi_fail(ctx, KDI_EINTERNAL, "pattern fill out of range");
+  if (p->raw && (src_dtype != KDI_F32 || d_rowmap || d_src != static_cast<const void*>(p->raw + row_offset * p->S)))
+    return kdi_fail(ctx, KDI_EINTERNAL, "a view-mode pattern set is filled from its own source rows only");
   return kdi_launch_normalize(ctx, stream, d_src, src_dtype, p->S, d_rowmap,
                               ctx->mask_S ? ctx->d_cols : nullptr, n_rows, p->s_eff, p->metric,
-                              p->compute_dtype, p->a32 + row_offset * p->s_pitch, p->s_pitch,
+                              p->compute_dtype, p->a32 ? p->a32 + row_offset * p->s_pitch : nullptr, p->s_pitch,
                               reinterpret_cast<uint16_t*>(p->a16) + row_offset * p->kp, p->kp, max_ctas,
-                              ready, row_offset, (int)kdi_ceil_div(p->rows, KDI_TILE_N));
+                              ready, row_offset, (int)kdi_ceil_div(p->rows, KDI_TILE_N),
+                              p->rstat ? p->rstat + row_offset : nullptr);
 }
 
 int kdi_patterns_plan(kdi_ctx* ctx, const void* src, int src_loc, int src_dtype, int64_t rows, int64_t S,
@@ -697,6 +724,7 @@ int kdi_patterns_read(kdi_ctx* ctx, const kdi_patterns* p, float* dst_host) {
   if (!p || !dst_host) return kdi_fail(ctx, KDI_EINVAL, "kdi_patterns_read: NULL argument");
   if (p->rows == 0) return KDI_OK;
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!p->a32) return kdi_fail(ctx, KDI_EINVAL, "kdi_patterns_read: the set holds no float32 rows");
   KDI_CUDA(ctx, cudaMemcpy2D(dst_host, (size_t)p->s_eff * sizeof(float), p->a32,
                              (size_t)p->s_pitch * sizeof(float), (size_t)p->s_eff * sizeof(float),
                              (size_t)p->rows, cudaMemcpyDeviceToHost));
@@ -712,6 +740,7 @@ int kdi_patterns_destroy(kdi_ctx* ctx, kdi_patterns* p) {
   kdi_dev_free(ctx, p->a32, p->a32_bytes);
   kdi_dev_free(ctx, p->a16, p->a16_bytes);
   kdi_dev_free(ctx, p->d_rowmap, p->rowmap_bytes);
+  kdi_dev_free(ctx, p->rstat, p->rstat_bytes);
   delete p;
   return KDI_OK;
 }

@@ -17,6 +17,8 @@ int exact_rows(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* dict, 
                int64_t row0, int64_t n_rows, int keep_n, int64_t index_offset, float* d_scores_out,
                int64_t* d_idx_out, bool compact = false) {
   const int64_t N = dict->rows;
+  // every dictionary row is scored: a view-mode dictionary gets its float32 rows now (rare: flagged rows)
+  if (!dict->a32) KDI_TRY(kdi_patterns_materialize(ctx, ctx->stream, const_cast<kdi_patterns*>(dict)));
   // score blocks of at most ~512 MB
   int64_t batch = (512ll << 20) / (N * (int64_t)sizeof(float));
   batch = std::max<int64_t>(4, batch / 4 * 4);
@@ -623,7 +625,14 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   kdi_fill_plan exp_plan;
   KDI_TRY(kdi_patterns_plan(ctx, experimental, exp_loc, exp_dtype, exp_rows, S, metric, nav_mask, &exp, &exp_plan));
   kdi_patterns* dict = nullptr;
-  int rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict);
+  // View mode: a device-resident float32 dictionary without masks is not copied as normalised float32
+  // rows - the exact scores read the caller's rows (alive for the whole call) and apply the row's
+  // statistics on the fly.  Only the tensor-core pipeline asks for single rows; everything that scores
+  // whole blocks (forced exact path, keep_n beyond the candidate lists) keeps the stored rows.
+  const bool view = ctx->dict_view && !dsrc.mp && dict_loc == KDI_DEVICE && dict_dtype == KDI_F32 && !ctx->mask_S &&
+                    kdi_normalize_is_light(S, S, false, false) && (reinterpret_cast<uintptr_t>(dictionary) % 16) == 0 &&
+                    !ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0 && exp_rows > 0;
+  int rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict, view ? static_cast<const float*>(dictionary) : nullptr);
   if (rc != KDI_OK) {
     const std::string err = ctx->err;
     kdi_patterns_destroy(ctx, exp);

@@ -24,6 +24,8 @@
 #include "kdi_internal.cuh"
 #include "kdi_ptx.cuh"
 
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -38,6 +40,7 @@ constexpr int kABytes = KDI_TILE_M * KDI_TILE_K * 2;  // 16 KB
 struct GemmParams {
   int64_t M, N;
   int kblocks;      // kp / 64
+  int k_last_steps; // 16-wide MMA steps of the LAST K block that cover real (not padding) columns: 1..4
   int m_blocks;     // row blocks of 128*CG rows covered by this launch
   int mb0;          // first row block of this launch
   int n_tiles;      // N tiles of 256 rows
@@ -229,10 +232,13 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
             const uint64_t da = umma_smem_desc_sw128(sa);
             const uint64_t db = umma_smem_desc_sw128(sa + kABytes);
+            // (the K padding of the last block is zero in both operands: the MMAs over 16-wide steps
+            // that hold nothing but padding are skipped - 3 of 228 per tile for 60 x 60 patterns)
+            const int ksteps = (kb == p.kblocks - 1) ? p.k_last_steps : KDI_TILE_K / 16;
 #pragma unroll
             for (int k = 0; k < KDI_TILE_K / 16; ++k) {
               // advance 16 elements = 32 bytes = 2 descriptor units along K inside the swizzle atom
-              umma_f16<CG>(tmem_d, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+              if (k < ksteps) umma_f16<CG>(tmem_d, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
             }
             if constexpr (CG == 1) umma_commit(bar_empty + 8u * stage);
             else umma_commit_cg2(bar_empty + 8u * stage, 3);
@@ -592,6 +598,11 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   p.M = exp->rows;
   p.N = dict->rows;
   p.kblocks = (int)(exp->kp / KDI_TILE_K);
+  p.k_last_steps = (int)kdi_ceil_div(exp->s_eff - (int64_t)(p.kblocks - 1) * KDI_TILE_K, 16);
+  {  // KDI_GEMM_FULL_K=1: issue the padding-only MMA steps too (A/B measurements)
+    static const bool full_k = getenv("KDI_GEMM_FULL_K") != nullptr && atoi(getenv("KDI_GEMM_FULL_K")) != 0;
+    if (full_k) p.k_last_steps = KDI_TILE_K / 16;
+  }
   p.m_blocks = mb_count;
   p.mb0 = mb0;
   p.n_tiles = plan->n_tiles;
@@ -629,6 +640,7 @@ int kdi_launch_gemm_full(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   p.M = exp->rows;
   p.N = dict->rows;
   p.kblocks = (int)(exp->kp / KDI_TILE_K);
+  p.k_last_steps = (int)kdi_ceil_div(exp->s_eff - (int64_t)(p.kblocks - 1) * KDI_TILE_K, 16);
   p.m_blocks = (int)kdi_ceil_div(p.M, (int64_t)KDI_TILE_M * cg);
   p.n_tiles = (int)kdi_ceil_div(p.N, KDI_TILE_N);
   p.strip_tiles = ctx->strip_tiles > 0 ? ctx->strip_tiles : 2;

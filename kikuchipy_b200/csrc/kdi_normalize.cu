@@ -17,6 +17,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -61,6 +62,44 @@ __device__ __forceinline__ uint16_t to16(float v) {
   }
 }
 
+// two operand values in one conversion instruction (cvt.rn.{f16x2,bf16x2}.f32: round to nearest even,
+// the same rounding as the scalar conversions); a in the low half
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if constexpr (BF16) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a * KDI_OP_SCALE, b * KDI_OP_SCALE);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __half2 h = __floats2half2_rn(a * KDI_OP_SCALE, b * KDI_OP_SCALE);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
+
+__device__ __forceinline__ uint32_t block_min_u32(uint32_t v, uint32_t* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other < v ? other : v;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  uint32_t t = 0xFFFFFFFFu;
+#pragma unroll
+  for (int w = 0; w < kNormThreads / 32; ++w) t = red[w] < t ? red[w] : t;
+  return t;
+}
+
+// Does the row's division have to watch for tiny dividends (kdi_div_fma)?  Integer sources never
+// (a non-zero pixel or pixel - mean is far from the subnormal range); float sources when the row is
+// not centred or its mean is (nearly) zero.
+template <typename T>
+__device__ __forceinline__ bool needs_min_tracking(int metric, float mean) {
+  if constexpr (std::is_integral<T>::value) return false;
+  return metric != KDI_NCC || !kdi_mean_keeps_residues_normal(mean);
+}
+
 // generic path: any source type, optional row / column gathers; the row is re-read from
 // L1/L2 for the second and third pass
 template <typename T, bool BF16>
@@ -68,8 +107,9 @@ __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_generic(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
                       const int32_t* __restrict__ cols, int64_t s_eff, int metric,
                       float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
-                      int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0) {
+                      int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0, int force_double) {
   __shared__ double red[kNormThreads / 32];
+  __shared__ uint32_t redu[kNormThreads / 32];
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
   const int64_t srow = rowmap ? rowmap[row] : row;
   const T* x = src + srow * S;
@@ -82,18 +122,26 @@ kdi_normalize_generic(const T* __restrict__ src, int64_t S, const int64_t* __res
     mean = (float)(s / (double)s_eff);
   }
   double ss = 0.0;
+  const bool track = needs_min_tracking<T>(metric, mean);
+  uint32_t amin = 0xFFFFFFFFu;
   for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) {
     const float c = (float)x[cols ? cols[j] : j] - mean;
     ss += (double)c * (double)c;
+    if (track) amin = kdi_min_abs_track(amin, c);
   }
   ss = block_sum(ss, red);
+  if (track) amin = block_min_u32(amin, redu);
   const float norm = (float)sqrt(ss);
-  const double rd = 1.0 / (double)norm;
+  kdi_rowdiv dv = kdi_rowdiv_make(norm, !track || kdi_min_abs_ok(amin));
+  if (force_double) dv.fast = false;
   float* o32 = a32 + row * s_pitch;
   uint16_t* o16 = a16 + row * kp;
   for (int64_t j = threadIdx.x; j < kp; j += kNormThreads) {
     float v = 0.f;
-    if (j < s_eff) v = kdi_div_by_norm((float)x[cols ? cols[j] : j] - mean, rd);
+    if (j < s_eff) {
+      const float c = (float)x[cols ? cols[j] : j] - mean;
+      v = dv.fast ? kdi_div_fma(c, dv.n, dv.y) : kdi_div_by_norm(c, dv.rd);
+    }
     if (j < s_pitch) o32[j] = v;
     o16[j] = to16<BF16>(v);
   }
@@ -111,9 +159,10 @@ __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
                      const int32_t* __restrict__ cols, int64_t s_eff, int metric,
                      float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
-                     int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0) {
+                     int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0, int force_double) {
   extern __shared__ float v[];  // s_eff floats
   __shared__ double red[kNormThreads / 32];
+  __shared__ uint32_t redu[kNormThreads / 32];
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
     const int64_t srow = rowmap ? rowmap[row] : row;
     const T* x = src + srow * S;
@@ -148,27 +197,33 @@ kdi_normalize_staged(const T* __restrict__ src, int64_t S, const int64_t* __rest
       mean = (float)(s / (double)s_eff);
     }
     double ss = 0.0;
+    const bool track = needs_min_tracking<T>(metric, mean);
+    uint32_t amin = 0xFFFFFFFFu;
     for (int64_t j = threadIdx.x; j < s_eff; j += kNormThreads) {
       const float c = v[j] - mean;
       ss += (double)c * (double)c;
+      if (track) amin = kdi_min_abs_track(amin, c);
     }
     ss = block_sum(ss, red);
+    if (track) amin = block_min_u32(amin, redu);
     const float norm = (float)sqrt(ss);
-    const double rd = 1.0 / (double)norm;
+    kdi_rowdiv dv = kdi_rowdiv_make(norm, !track || kdi_min_abs_ok(amin));
+    if (force_double) dv.fast = false;
     float* o32 = a32 + row * s_pitch;
     uint16_t* o16 = a16 + row * kp;
     // four outputs per thread and step: 16-byte fp32 stores, 8-byte 16-bit stores (pitches are
     // multiples of 4 and the buffers 256-byte aligned)
-    for (int64_t j = 4 * (int64_t)threadIdx.x; j < kp; j += 4 * kNormThreads) {
-      float o[4];
+    auto out_pass = [&](auto div) {
+      for (int64_t j = 4 * (int64_t)threadIdx.x; j < kp; j += 4 * kNormThreads) {
+        float o[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? kdi_div_by_norm(v[j + q] - mean, rd) : 0.f;
-      if (j < s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
-      uint2 h;
-      h.x = (uint32_t)to16<BF16>(o[0]) | ((uint32_t)to16<BF16>(o[1]) << 16);
-      h.y = (uint32_t)to16<BF16>(o[2]) | ((uint32_t)to16<BF16>(o[3]) << 16);
-      *reinterpret_cast<uint2*>(o16 + j) = h;
-    }
+        for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? div(v[j + q] - mean) : 0.f;
+        if (j < s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint2*>(o16 + j) = make_uint2(pack16<BF16>(o[0], o[1]), pack16<BF16>(o[2], o[3]));
+      }
+    };
+    if (dv.fast) out_pass([&](float c) { return kdi_div_fma(c, dv.n, dv.y); });
+    else out_pass([&](float c) { return kdi_div_by_norm(c, dv.rd); });
     publish_row(ready, ready_row0 + row);
   }
 }
@@ -185,9 +240,10 @@ __global__ void __launch_bounds__(kNormThreads)
 kdi_normalize_bulk(const T* __restrict__ src, int64_t S, const int64_t* __restrict__ rowmap,
                    const int3* __restrict__ runs, int n_runs, int64_t s_eff, int metric,
                    float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16, int64_t kp,
-                   int64_t n_rows, uint32_t raw_bytes) {
+                   int64_t n_rows, uint32_t raw_bytes, int force_double) {
   extern __shared__ __align__(128) uint8_t smem_bulk[];
   __shared__ double red[kNormThreads / 32];
+  __shared__ uint32_t redu[kNormThreads / 32];
   __shared__ __align__(8) uint64_t bars[2];
   const uint32_t raw_pitch = (raw_bytes + 127u) & ~127u;
   uint8_t* raw0 = smem_bulk;
@@ -236,25 +292,31 @@ kdi_normalize_bulk(const T* __restrict__ src, int64_t S, const int64_t* __restri
       mean = (float)(s / (double)s_eff);
     }
     double ss = 0.0;
+    const bool track = needs_min_tracking<T>(metric, mean);
+    uint32_t amin = 0xFFFFFFFFu;
     for (int64_t j = tid; j < s_eff; j += kNormThreads) {
       const float c = v[j] - mean;
       ss += (double)c * (double)c;
+      if (track) amin = kdi_min_abs_track(amin, c);
     }
     ss = block_sum(ss, red);
+    if (track) amin = block_min_u32(amin, redu);
     const float norm = (float)sqrt(ss);
-    const double rd = 1.0 / (double)norm;
+    kdi_rowdiv dv = kdi_rowdiv_make(norm, !track || kdi_min_abs_ok(amin));
+    if (force_double) dv.fast = false;
     float* o32 = a32 + row * s_pitch;
     uint16_t* o16 = a16 + row * kp;
-    for (int64_t j = 4 * (int64_t)tid; j < kp; j += 4 * kNormThreads) {
-      float o[4];
+    auto out_pass = [&](auto div) {
+      for (int64_t j = 4 * (int64_t)tid; j < kp; j += 4 * kNormThreads) {
+        float o[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? kdi_div_by_norm(v[j + q] - mean, rd) : 0.f;
-      if (j < s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
-      uint2 h;
-      h.x = (uint32_t)to16<BF16>(o[0]) | ((uint32_t)to16<BF16>(o[1]) << 16);
-      h.y = (uint32_t)to16<BF16>(o[2]) | ((uint32_t)to16<BF16>(o[3]) << 16);
-      *reinterpret_cast<uint2*>(o16 + j) = h;
-    }
+        for (int q = 0; q < 4; ++q) o[q] = (j + q < s_eff) ? div(v[j + q] - mean) : 0.f;
+        if (j < s_pitch) *reinterpret_cast<float4*>(o32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint2*>(o16 + j) = make_uint2(pack16<BF16>(o[0], o[1]), pack16<BF16>(o[2], o[3]));
+      }
+    };
+    if (dv.fast) out_pass([&](float c) { return kdi_div_fma(c, dv.n, dv.y); });
+    else out_pass([&](float c) { return kdi_div_by_norm(c, dv.rd); });
   }
 }
 
@@ -274,8 +336,9 @@ __global__ void __launch_bounds__(kNormThreads, V <= 4 ? 4 : 1)  // (64 register
 kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
                        float* __restrict__ a32, int64_t s_pitch, uint16_t* __restrict__ a16,
                        int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready, int64_t ready_row0,
-                       int n_tiles_total) {
+                       int n_tiles_total, float4* __restrict__ rstat, int force_double) {
   __shared__ double red[kNormThreads / 32];
+  __shared__ uint32_t redu[kNormThreads / 32];
   __shared__ uint32_t s_next;
   // With readiness counters the rows are handed out dynamically, in order: beside the tensor-core
   // kernel only part of this grid is resident at any time, and a static row-to-CTA assignment would
@@ -326,6 +389,8 @@ kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
       mean = (float)(s / (double)S);
     }
     double ss = 0.0;
+    const bool track = needs_min_tracking<T>(metric, mean);
+    uint32_t amin = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int j = threadIdx.x + i * kNormThreads;
@@ -333,31 +398,139 @@ kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
         r[i].x -= mean; r[i].y -= mean; r[i].z -= mean; r[i].w -= mean;
         ss += ((double)r[i].x * r[i].x + (double)r[i].y * r[i].y) +
               ((double)r[i].z * r[i].z + (double)r[i].w * r[i].w);
+        if (track) {
+          amin = kdi_min_abs_track(kdi_min_abs_track(amin, r[i].x), r[i].y);
+          amin = kdi_min_abs_track(kdi_min_abs_track(amin, r[i].z), r[i].w);
+        }
       }
     }
     ss = block_sum(ss, red);
+    if (track) amin = block_min_u32(amin, redu);
     const float norm = (float)sqrt(ss);
-    const double rd = 1.0 / (double)norm;
-    float4* o32 = reinterpret_cast<float4*>(a32 + cur * s_pitch);
+    kdi_rowdiv dv = kdi_rowdiv_make(norm, !track || kdi_min_abs_ok(amin));
+    if (force_double) dv.fast = false;
+    // view mode (a32 == NULL): the float32 row is not stored; whoever needs its values recomputes them
+    // from the source row and these four numbers with the same arithmetic (kdi_rank.cuh: warp_dot_view)
+    if (rstat != nullptr && threadIdx.x == 0) rstat[cur] = make_float4(mean, dv.n, dv.y, dv.fast ? 0.f : 1.f);
+    float4* o32 = a32 ? reinterpret_cast<float4*>(a32 + cur * s_pitch) : nullptr;
     uint2* o16 = reinterpret_cast<uint2*>(a16 + cur * kp);
+    auto out_pass = [&](auto div) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int j = threadIdx.x + i * kNormThreads;
-      if (j < n4) {
-        float4 v;
-        v.x = kdi_div_by_norm(r[i].x, rd); v.y = kdi_div_by_norm(r[i].y, rd);
-        v.z = kdi_div_by_norm(r[i].z, rd); v.w = kdi_div_by_norm(r[i].w, rd);
-        o32[j] = v;
-        uint2 h;
-        h.x = (uint32_t)to16<BF16>(v.x) | ((uint32_t)to16<BF16>(v.y) << 16);
-        h.y = (uint32_t)to16<BF16>(v.z) | ((uint32_t)to16<BF16>(v.w) << 16);
-        o16[j] = h;
+      for (int i = 0; i < V; ++i) {
+        const int j = threadIdx.x + i * kNormThreads;
+        if (j < n4) {
+          float4 v;
+          v.x = div(r[i].x); v.y = div(r[i].y); v.z = div(r[i].z); v.w = div(r[i].w);
+          if (o32) o32[j] = v;
+          o16[j] = make_uint2(pack16<BF16>(v.x, v.y), pack16<BF16>(v.z, v.w));
+        }
       }
-    }
+    };
+    if (dv.fast) out_pass([&](float c) { return kdi_div_fma(c, dv.n, dv.y); });
+    else out_pass([&](float c) { return kdi_div_by_norm(c, dv.rd); });
     // zero the K padding of the 16-bit row (s_pitch == S here)
     for (int64_t j = S + threadIdx.x; j < kp; j += kNormThreads) a16[cur * kp + j] = 0;
     publish_row(ready, ready_row0 + cur);
     if constexpr (!kPrefetch) row = next_row(cur);
+  }
+}
+
+// fast path for rows of up to 4096 values (float32 or uint8 source, no gathers, S % 4 == 0): ONE WARP
+// PER ROW, the row in registers (NV float4 per lane).  No shared memory and no block barriers - the two
+// reductions are five shuffle steps each - and the per-row scalar work (mean, square root, reciprocal)
+// is amortised over ~4 x NV values per lane instead of 16: the CTA-per-row kernel above spent ~38
+// instructions per value on 60 x 60 patterns (issue-bound at 68 % of the issue slots, ncu r2b), this one
+// ~13.  Memory-level parallelism comes from the NV independent 16-byte loads every lane issues up front.
+constexpr int kWarpNormThreads = 128;
+
+template <typename T, int NV, bool BF16>
+__global__ void __launch_bounds__(kWarpNormThreads, NV <= 8 ? 6 : (NV <= 16 ? 4 : 3))
+kdi_normalize_warp_rows(const T* __restrict__ src, int64_t S, int metric, float* __restrict__ a32, int64_t s_pitch,
+                        uint16_t* __restrict__ a16, int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready,
+                        int64_t ready_row0, int n_tiles_total, float4* __restrict__ rstat, int force_double) {
+  const int lane = threadIdx.x & 31;
+  const int n4 = (int)(S >> 2);
+  // (with readiness counters the rows are handed out dynamically and in order, see kdi_normalize_f32_regs)
+  uint32_t* work = ready ? ready + kdi_ready_words_before_work(n_tiles_total) : nullptr;
+  const int64_t stride = (int64_t)gridDim.x * (kWarpNormThreads / 32);
+  auto next_row = [&](int64_t prev) -> int64_t {
+    if (!work) return prev + stride;
+    uint32_t v = 0;
+    if (lane == 0) v = atomicAdd(work, 1u);
+    return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+  };
+  int64_t row = work ? next_row(0) : (int64_t)blockIdx.x * (kWarpNormThreads / 32) + (threadIdx.x >> 5);
+  while (row < n_rows) {
+    const T* x = src + row * S;
+    float4 r[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = lane + 32 * i;
+      r[i] = (j < n4) ? load4(x, j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float mean = 0.f;
+    if (metric == KDI_NCC) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s += ((double)r[i].x + (double)r[i].y) + ((double)r[i].z + (double)r[i].w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      mean = (float)(s / (double)S);
+    }
+    double ss = 0.0;
+    const bool track = needs_min_tracking<T>(metric, mean);
+    uint32_t amin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < n4) {
+        r[i].x -= mean; r[i].y -= mean; r[i].z -= mean; r[i].w -= mean;
+        ss += ((double)r[i].x * r[i].x + (double)r[i].y * r[i].y) +
+              ((double)r[i].z * r[i].z + (double)r[i].w * r[i].w);
+        if (track) {
+          amin = kdi_min_abs_track(kdi_min_abs_track(amin, r[i].x), r[i].y);
+          amin = kdi_min_abs_track(kdi_min_abs_track(amin, r[i].z), r[i].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (track) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, amin, o);
+        amin = other < amin ? other : amin;
+      }
+    }
+    const float norm = (float)sqrt(ss);
+    kdi_rowdiv dv = kdi_rowdiv_make(norm, !track || kdi_min_abs_ok(amin));
+    if (force_double) dv.fast = false;
+    if (rstat != nullptr && lane == 0) rstat[row] = make_float4(mean, dv.n, dv.y, dv.fast ? 0.f : 1.f);
+    float4* o32 = a32 ? reinterpret_cast<float4*>(a32 + row * s_pitch) : nullptr;
+    uint2* o16 = reinterpret_cast<uint2*>(a16 + row * kp);
+    auto out_pass = [&](auto div) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int j = lane + 32 * i;
+        if (j < n4) {
+          float4 v;
+          v.x = div(r[i].x); v.y = div(r[i].y); v.z = div(r[i].z); v.w = div(r[i].w);
+          if (o32) o32[j] = v;
+          o16[j] = make_uint2(pack16<BF16>(v.x, v.y), pack16<BF16>(v.z, v.w));
+        }
+      }
+    };
+    if (dv.fast) out_pass([&](float c) { return kdi_div_fma(c, dv.n, dv.y); });
+    else out_pass([&](float c) { return kdi_div_by_norm(c, dv.rd); });
+    // zero the K padding of the 16-bit row (s_pitch == S here)
+    for (int64_t j = S + lane; j < kp; j += 32) a16[row * kp + j] = 0;
+    if (ready != nullptr) {
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(ready + (ready_row0 + row) / KDI_TILE_N, 1u);
+      }
+    }
+    row = next_row(row);
   }
 }
 
@@ -373,7 +546,8 @@ template <typename T>
 int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_t* rowmap,
                    const int32_t* cols, int64_t rows, int64_t s_eff, int metric, int bf16,
                    float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
-                   uint32_t* ready, int64_t ready_row0, bool use_bulk, const int3* runs, int n_runs, int sm_count) {
+                   uint32_t* ready, int64_t ready_row0, bool use_bulk, const int3* runs, int n_runs, int sm_count,
+                   int force_double) {
   const T* s = reinterpret_cast<const T*>(src);
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
   const size_t stage_bytes = (size_t)s_eff * sizeof(float);
@@ -391,11 +565,11 @@ int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_
     if (bf16) {
       cudaFuncSetAttribute(kdi_normalize_bulk<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       kdi_normalize_bulk<T, true><<<g, kNormThreads, bulk_smem, stream>>>(s, S, rowmap, cols ? runs : nullptr, n_runs, s_eff, metric,
-                                                                          a32, s_pitch, o16, kp, rows, (uint32_t)raw_bytes);
+                                                                          a32, s_pitch, o16, kp, rows, (uint32_t)raw_bytes, force_double);
     } else {
       cudaFuncSetAttribute(kdi_normalize_bulk<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       kdi_normalize_bulk<T, false><<<g, kNormThreads, bulk_smem, stream>>>(s, S, rowmap, cols ? runs : nullptr, n_runs, s_eff, metric,
-                                                                           a32, s_pitch, o16, kp, rows, (uint32_t)raw_bytes);
+                                                                           a32, s_pitch, o16, kp, rows, (uint32_t)raw_bytes, force_double);
     }
     return 0;
   }
@@ -406,27 +580,27 @@ int launch_generic(cudaStream_t stream, const void* src, int64_t S, const int64_
     else cudaFuncSetAttribute(kdi_normalize_staged<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (bf16)
       kdi_normalize_staged<T, true><<<grid, kNormThreads, stage_bytes, stream>>>(
-          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
+          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, force_double);
     else
       kdi_normalize_staged<T, false><<<grid, kNormThreads, stage_bytes, stream>>>(
-          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
+          s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, force_double);
     return 0;
   }
   static bool once = (prefer_max_shared(kdi_normalize_generic<T, true>), prefer_max_shared(kdi_normalize_generic<T, false>), true);
   (void)once;
   if (bf16)
     kdi_normalize_generic<T, true><<<grid, kNormThreads, 0, stream>>>(
-        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
+        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, force_double);
   else
     kdi_normalize_generic<T, false><<<grid, kNormThreads, 0, stream>>>(
-        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0);
+        s, S, rowmap, cols, s_eff, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, force_double);
   return 0;
 }
 
 template <typename T, int V>
 void launch_regs(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int metric,
                  int bf16, float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
-                 uint32_t* ready, int64_t ready_row0, int n_tiles_total) {
+                 uint32_t* ready, int64_t ready_row0, int n_tiles_total, float4* rstat, int force_double) {
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
   // This kernel is the one that runs BESIDE the tensor-core kernel in the flag-mode schedule.  An SM's
   // L1 / shared-memory split is only changed while the SM is idle, and the tensor-core kernel needs
@@ -437,22 +611,56 @@ void launch_regs(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int
   cudaFuncSetAttribute(kdi_normalize_f32_regs<T, V, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (bf16)
     kdi_normalize_f32_regs<T, V, true><<<grid, kNormThreads, 0, stream>>>(
-        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total);
+        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total, rstat, force_double);
   else
     kdi_normalize_f32_regs<T, V, false><<<grid, kNormThreads, 0, stream>>>(
-        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total);
+        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total, rstat, force_double);
+}
+
+template <typename T, int NV>
+void launch_warp_rows(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int metric, int bf16, float* a32,
+                      int64_t s_pitch, void* a16, int64_t kp, unsigned grid, uint32_t* ready, int64_t ready_row0,
+                      int n_tiles_total, float4* rstat, int force_double) {
+  uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
+  // (same shared-memory split as the tensor-core kernel, see launch_regs)
+  cudaFuncSetAttribute(kdi_normalize_warp_rows<T, NV, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(kdi_normalize_warp_rows<T, NV, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (bf16)
+    kdi_normalize_warp_rows<T, NV, true><<<grid, kWarpNormThreads, 0, stream>>>(
+        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total, rstat, force_double);
+  else
+    kdi_normalize_warp_rows<T, NV, false><<<grid, kWarpNormThreads, 0, stream>>>(
+        src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total, rstat, force_double);
 }
 
 template <typename T>
 void launch_regs_any(cudaStream_t stream, const T* s, int64_t S, int64_t rows, int metric, int bf16,
                      float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
-                     uint32_t* ready, int64_t ready_row0, int n_tiles_total) {
+                     uint32_t* ready, int64_t ready_row0, int n_tiles_total, float4* rstat, int force_double,
+                     int sm_count, bool resident) {
+  // rows of up to 4096 values: one warp per row (grid: four rows per CTA, or a resident grid that
+  // strides over the rows when the caller asked for a bounded number of CTAs)
+  const int nv = (int)kdi_ceil_div(S / 4, 32);
+  if (nv <= 32) {
+    unsigned g = (unsigned)kdi_ceil_div(rows, kWarpNormThreads / 32);
+    if (resident && g > grid) g = grid;
+    const unsigned cap = (unsigned)sm_count * 64;
+    if (g > cap) g = cap;
+#define KDI_WARP_ROWS(NV_) launch_warp_rows<T, NV_>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, g, ready, ready_row0, n_tiles_total, rstat, force_double)
+    if (nv <= 8) KDI_WARP_ROWS(8);
+    else if (nv <= 16) KDI_WARP_ROWS(16);
+    else if (nv <= 24) KDI_WARP_ROWS(24);
+    else if (nv <= 29) KDI_WARP_ROWS(29);
+    else KDI_WARP_ROWS(32);
+#undef KDI_WARP_ROWS
+    return;
+  }
   const int v = (int)kdi_ceil_div(S / 4, kNormThreads);
-  if (v <= 1) launch_regs<T, 1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
-  else if (v <= 2) launch_regs<T, 2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
-  else if (v <= 4) launch_regs<T, 4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
-  else if (v <= 8) launch_regs<T, 8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
-  else launch_regs<T, 16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
+  if (v <= 1) launch_regs<T, 1>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total, rstat, force_double);
+  else if (v <= 2) launch_regs<T, 2>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total, rstat, force_double);
+  else if (v <= 4) launch_regs<T, 4>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total, rstat, force_double);
+  else if (v <= 8) launch_regs<T, 8>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total, rstat, force_double);
+  else launch_regs<T, 16>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total, rstat, force_double);
 }
 
 }  // namespace
@@ -467,8 +675,9 @@ int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int
                          int64_t S, const int64_t* d_rowmap, const int32_t* d_cols, int64_t rows,
                          int64_t s_eff, int metric, int compute_dtype, float* a32, int64_t s_pitch,
                          void* a16, int64_t kp, int max_ctas, uint32_t* ready, int64_t ready_row0,
-                         int n_tiles_total) {
+                         int n_tiles_total, float4* rstat) {
   if (rows <= 0) return KDI_OK;
+  const int force_double = ctx->div_double;
   if (ready && ready_row0 != 0)
     return kdi_fail(ctx, KDI_EINTERNAL, "readiness counters need the whole dictionary in one launch");
   if (rows > 0x7fffffffLL) return kdi_fail(ctx, KDI_EUNSUPPORTED, "too many rows in one pattern set");
@@ -482,27 +691,29 @@ int kdi_launch_normalize(kdi_ctx* ctx, cudaStream_t stream, const void* src, int
   // being consumed concurrently through readiness counters (register-resident kernel only)
   const bool use_bulk = ctx->bulk_normalize && ready == nullptr && (d_cols == nullptr || d_cols == ctx->d_cols);
   (void)plain;
+  if ((a32 == nullptr || rstat != nullptr) && !(src_dtype == KDI_F32 && reg_path && (reinterpret_cast<uintptr_t>(src) % 16) == 0))
+    return kdi_fail(ctx, KDI_EINTERNAL, "a view-mode pattern set needs the register-resident float32 kernel");
   if (src_dtype == KDI_F32 && reg_path && (reinterpret_cast<uintptr_t>(src) % 16) == 0) {
-    launch_regs_any<float>(stream, reinterpret_cast<const float*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
+    launch_regs_any<float>(stream, reinterpret_cast<const float*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total, rstat, force_double, ctx->sm_count, max_ctas > 0);
   } else if (src_dtype == KDI_U8 && reg_path && (reinterpret_cast<uintptr_t>(src) % 4) == 0) {
-    launch_regs_any<uint8_t>(stream, reinterpret_cast<const uint8_t*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total);
+    launch_regs_any<uint8_t>(stream, reinterpret_cast<const uint8_t*>(src), S, rows, metric, bf16, a32, s_pitch, a16, kp, grid, ready, ready_row0, n_tiles_total, rstat, force_double, ctx->sm_count, max_ctas > 0);
   } else {
     switch (src_dtype) {
       case KDI_U8:
         launch_generic<uint8_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count);
+                                s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count, force_double);
         break;
       case KDI_U16:
         launch_generic<uint16_t>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                                 s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count);
+                                 s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count, force_double);
         break;
       case KDI_F32:
         launch_generic<float>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                              s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count);
+                              s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count, force_double);
         break;
       case KDI_F64:
         launch_generic<double>(stream, src, S, d_rowmap, d_cols, rows, s_eff, metric, bf16, a32,
-                               s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count);
+                               s_pitch, a16, kp, grid, ready, ready_row0, use_bulk, ctx->d_runs, ctx->n_runs, ctx->sm_count, force_double);
         break;
       default:
         return kdi_fail(ctx, KDI_EINVAL, "unknown source dtype %d", src_dtype);

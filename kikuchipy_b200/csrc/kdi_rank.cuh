@@ -3,6 +3,7 @@
 // produces bit-identical scores and the same ranking.
 #pragma once
 
+#include "kdi_internal.cuh"
 #include "kdi_ptx.cuh"
 
 namespace kdi {
@@ -39,6 +40,67 @@ __device__ __forceinline__ float warp_dot(const float4* __restrict__ a, const fl
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
   return (float)d;
+}
+
+// The same dot product against a dictionary row of a VIEW-mode set (kdi_patterns::raw / rstat): the
+// normalised value of every element is recomputed from the source row, y_i = RN((b_i - mean) / norm)
+// with the prepare kernel's own routines, and enters the same FMA chain in the same order - the result
+// is bit for bit what warp_dot gives on the stored float32 row.  n4 = S / 4 (no padding in view mode).
+template <typename DIV>
+__device__ __forceinline__ float warp_dot_view_impl(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                    float mean, int n4, int lane, DIV div) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int j = lane;
+  // Same element order and accumulators as warp_dot.  The recomputation costs ~7 float32 operations per
+  // value instead of one, so the loads of the NEXT 128 float4 of the dictionary row are issued before the
+  // current ones are consumed: the warp keeps HBM requests in flight while it computes.
+  bool more = j + 96 < n4;
+  float4 n0, n1, n2, n3;
+  if (more) { n0 = __ldg(b + j); n1 = __ldg(b + j + 32); n2 = __ldg(b + j + 64); n3 = __ldg(b + j + 96); }
+  while (more) {
+    const float4 y0 = n0, y1 = n1, y2 = n2, y3 = n3;
+    const int jc = j;
+    j += 128;
+    more = j + 96 < n4;
+    if (more) { n0 = __ldg(b + j); n1 = __ldg(b + j + 32); n2 = __ldg(b + j + 64); n3 = __ldg(b + j + 96); }
+    const float4 x0 = __ldg(a + jc), x1 = __ldg(a + jc + 32), x2 = __ldg(a + jc + 64), x3 = __ldg(a + jc + 96);
+    acc.x = fmaf(x0.x, div(y0.x - mean), acc.x); acc.y = fmaf(x0.y, div(y0.y - mean), acc.y);
+    acc.z = fmaf(x0.z, div(y0.z - mean), acc.z); acc.w = fmaf(x0.w, div(y0.w - mean), acc.w);
+    acc.x = fmaf(x1.x, div(y1.x - mean), acc.x); acc.y = fmaf(x1.y, div(y1.y - mean), acc.y);
+    acc.z = fmaf(x1.z, div(y1.z - mean), acc.z); acc.w = fmaf(x1.w, div(y1.w - mean), acc.w);
+    acc.x = fmaf(x2.x, div(y2.x - mean), acc.x); acc.y = fmaf(x2.y, div(y2.y - mean), acc.y);
+    acc.z = fmaf(x2.z, div(y2.z - mean), acc.z); acc.w = fmaf(x2.w, div(y2.w - mean), acc.w);
+    acc.x = fmaf(x3.x, div(y3.x - mean), acc.x); acc.y = fmaf(x3.y, div(y3.y - mean), acc.y);
+    acc.z = fmaf(x3.z, div(y3.z - mean), acc.z); acc.w = fmaf(x3.w, div(y3.w - mean), acc.w);
+  }
+  for (; j < n4; j += 32) {
+    const float4 x = __ldg(a + j);
+    const float4 y = __ldg(b + j);
+    acc.x = fmaf(x.x, div(y.x - mean), acc.x);
+    acc.y = fmaf(x.y, div(y.y - mean), acc.y);
+    acc.z = fmaf(x.z, div(y.z - mean), acc.z);
+    acc.w = fmaf(x.w, div(y.w - mean), acc.w);
+  }
+  double d = ((double)acc.x + (double)acc.y) + ((double)acc.z + (double)acc.w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  return (float)d;
+}
+// st = rstat[row] = (mean, norm, float(1 / norm), route)
+__device__ __forceinline__ float warp_dot_view(const float4* __restrict__ a, const float4* __restrict__ b,
+                                               const float4 st, int n4, int lane) {
+  const float n = st.y, y = st.z;
+  if (st.w == 0.f) return warp_dot_view_impl(a, b, st.x, n4, lane, [=](float c) { return kdi_div_fma(c, n, y); });
+  const double rd = 1.0 / (double)n;
+  return warp_dot_view_impl(a, b, st.x, n4, lane, [=](float c) { return kdi_div_by_norm(c, rd); });
+}
+// exact score of experimental row `a` against row g of a dictionary given either as stored float32 rows
+// (d32) or as a view (raw + stat)
+__device__ __forceinline__ float warp_dot_dict(const float4* __restrict__ a, const float* __restrict__ d32,
+                                               const float* __restrict__ raw, const float4* __restrict__ stat,
+                                               int64_t g, int64_t s_pitch, int n4, int lane) {
+  if (raw == nullptr) return warp_dot(a, reinterpret_cast<const float4*>(d32 + g * s_pitch), n4, lane);
+  return warp_dot_view(a, reinterpret_cast<const float4*>(raw + g * s_pitch), __ldg(stat + g), n4, lane);
 }
 
 __device__ __forceinline__ uint64_t pack_key(float score, uint32_t idx) {

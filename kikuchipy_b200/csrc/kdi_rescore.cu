@@ -29,6 +29,7 @@ using kdi::key_index;
 using kdi::key_score;
 using kdi::pack_key;
 using kdi::warp_dot;
+using kdi::warp_dot_dict;
 using kdi::warp_sort_desc;
 
 constexpr int kSelThreads = 128;
@@ -240,9 +241,12 @@ kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restric
   }
 }
 
-template <int KC>
+// VIEW: the dictionary is a view-mode set (no stored float32 rows): dict32 is its float32 SOURCE and
+// dstat its per-row statistics (kdi_rank.cuh: warp_dot_view)
+template <int KC, bool VIEW>
 __global__ void __launch_bounds__(kSelThreads)
 kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
+                          const float4* __restrict__ dstat,
                           int64_t s_pitch, int64_t n_dict, const uint2* __restrict__ cand,
                           const uint32_t* __restrict__ thr, int n_strips, int keep_n,
                           int64_t index_offset, float inv_scale, float cert_sigmas, float sigma_floor,
@@ -290,8 +294,7 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   int n_a = (keep_n + 4 + 3) & ~3;
   if (n_a > nsel) n_a = nsel;
   for (int i = warp; i < n_a; i += kSelThreads / 32) {
-    const float4* b = reinterpret_cast<const float4*>(dict32 + (int64_t)ci[i] * s_pitch);
-    const float d = warp_dot(a, b, n4, lane);
+    const float d = warp_dot_dict(a, dict32, VIEW ? dict32 : nullptr, dstat, (int64_t)ci[i], s_pitch, n4, lane);
     if (lane == 0) ex[i] = d;
   }
   __syncthreads();
@@ -327,10 +330,8 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   const float e_k = s_ek;
   for (int i = n_a + warp; i < nsel; i += kSelThreads / 32) {
     float d = -INFINITY;  // warp-uniform decision
-    if (ap[i] + bias + eps >= e_k) {
-      const float4* b = reinterpret_cast<const float4*>(dict32 + (int64_t)ci[i] * s_pitch);
-      d = warp_dot(a, b, n4, lane);
-    }
+    if (ap[i] + bias + eps >= e_k)
+      d = warp_dot_dict(a, dict32, VIEW ? dict32 : nullptr, dstat, (int64_t)ci[i], s_pitch, n4, lane);
     if (lane == 0) ex[i] = d;
   }
   __syncthreads();
@@ -395,7 +396,7 @@ kdi_select_only_kernel(const uint2* __restrict__ cand, const uint32_t* __restric
 // of the skipped ones could have entered the top keep_n - otherwise the row is flagged.
 __global__ void __launch_bounds__(kSelThreads)
 kdi_rescore_owned_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
-                         int64_t s_pitch, int64_t shard_start, int64_t shard_rows, int kc,
+                         const float* __restrict__ dict_raw, const float4* __restrict__ dstat, int64_t s_pitch, int64_t shard_start, int64_t shard_rows, int kc,
                          const int64_t* __restrict__ gidx, const float* __restrict__ approx, int keep_n,
                          float margin, float* __restrict__ exact) {
   const int64_t row = blockIdx.x;
@@ -407,7 +408,7 @@ kdi_rescore_owned_kernel(const float* __restrict__ exp32, const float* __restric
     const int64_t g = gidx[row * kc + i] - shard_start;  // warp-uniform
     float d = -INFINITY;
     if (g >= 0 && g < shard_rows && (i < keep_n + 4 || !approx || approx[row * kc + i] >= floor_score))
-      d = warp_dot(a, reinterpret_cast<const float4*>(dict32 + g * s_pitch), n4, lane);
+      d = warp_dot_dict(a, dict32, dict_raw, dstat, g, s_pitch, n4, lane);
     if (lane == 0) exact[row * kc + i] = d;
   }
 }
@@ -636,25 +637,28 @@ int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patte
   // kernel (the split is only changed on an idle SM) and a padded footprint so that a fixed number of
   // these CTAs fits into the stage the GEMM kernel gave up
   const int carve = ctx->post_coresident > 0 ? 100 : kdi_carveout_pref();
-  cudaFuncSetAttribute(kdi_select_rescore_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-  cudaFuncSetAttribute(kdi_select_rescore_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-  cudaFuncSetAttribute(kdi_select_rescore_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_rescore_kernel<32, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_rescore_kernel<64, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_rescore_kernel<128, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_rescore_kernel<32, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_rescore_kernel<64, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  cudaFuncSetAttribute(kdi_select_rescore_kernel<128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   const size_t pad = kdi_post_pad_bytes(ctx, kSelBuf * 8 + 3 * plan->kc * 4 + 64);
   kdi_span span(ctx, stream, "select_rescore");
-  if (plan->kc == 32)
-    kdi_select_rescore_kernel<32><<<grid, kSelThreads, pad, stream>>>(
-        exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
-        index_offset, approx_inv_scale, cert_sigmas, sigma_floor, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
-  else if (plan->kc == 64)
-    kdi_select_rescore_kernel<64><<<grid, kSelThreads, pad, stream>>>(
-        exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
-        index_offset, approx_inv_scale, cert_sigmas, sigma_floor, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
-  else if (plan->kc == 128)
-    kdi_select_rescore_kernel<128><<<grid, kSelThreads, pad, stream>>>(
-        exp->a32, dict->a32, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n,
-        index_offset, approx_inv_scale, cert_sigmas, sigma_floor, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx);
+  const bool view = dict->a32 == nullptr;
+  if (view && (!dict->raw || !dict->rstat || dict->s_pitch != dict->S || exp->s_pitch != dict->S))
+    return kdi_fail(ctx, KDI_EINTERNAL, "dictionary holds neither float32 rows nor a view of its source");
+  const float* d32 = view ? dict->raw : dict->a32;
+#define KDI_LAUNCH_SR(KC_, VIEW_)                                                                              \
+  kdi_select_rescore_kernel<KC_, VIEW_><<<grid, kSelThreads, pad, stream>>>(                                  \
+      exp->a32, d32, dict->rstat, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n, index_offset,  \
+      approx_inv_scale, cert_sigmas, sigma_floor, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx)
+  if (plan->kc == 32) { if (view) KDI_LAUNCH_SR(32, true); else KDI_LAUNCH_SR(32, false); }
+  else if (plan->kc == 64) { if (view) KDI_LAUNCH_SR(64, true); else KDI_LAUNCH_SR(64, false); }
+  else if (plan->kc == 128) { if (view) KDI_LAUNCH_SR(128, true); else KDI_LAUNCH_SR(128, false); }
   else
     return kdi_fail(ctx, KDI_EINTERNAL, "unsupported candidate capacity %d", plan->kc);
+#undef KDI_LAUNCH_SR
   KDI_CUDA(ctx, cudaGetLastError());
   ctx->tm.kernel_launches++;
   return KDI_OK;
@@ -672,6 +676,7 @@ int kdi_launch_exact_scores(kdi_ctx* ctx, cudaStream_t stream, const kdi_pattern
   if (slab < 8) slab = 8;
   slabs = kdi_ceil_div(dict->rows, slab);
   dim3 grid((unsigned)slabs, (unsigned)groups);
+  if (!dict->a32) return kdi_fail(ctx, KDI_EINTERNAL, "the exact path needs the dictionary's float32 rows (kdi_patterns_materialize)");
   kdi_exact_scores_kernel<<<grid, kExThreads, 0, stream>>>(exp->a32, dict->a32, exp->s_pitch,
                                                            dict->rows, rows_list, row0, n_rows,
                                                            scores, (int)slab);
@@ -730,7 +735,8 @@ int kdi_launch_rescore_owned(kdi_ctx* ctx, cudaStream_t stream, const kdi_patter
   if (exp->rows <= 0) return KDI_OK;
   kdi_span span(ctx, stream, "rescore (owned candidates)");
   kdi_rescore_owned_kernel<<<(unsigned)exp->rows, kSelThreads, 0, stream>>>(
-      exp->a32, dict->a32, exp->s_pitch, shard_start, dict->rows, kc, gidx, approx, keep_n, margin, exact);
+      exp->a32, dict->a32, dict->a32 ? nullptr : dict->raw, dict->rstat, exp->s_pitch, shard_start, dict->rows, kc, gidx,
+      approx, keep_n, margin, exact);
   KDI_CUDA(ctx, cudaGetLastError());
   ctx->tm.kernel_launches++;
   return KDI_OK;

@@ -168,7 +168,8 @@ def load_nordif(filename, scan_size=None, pattern_size=None, setting_file=None, 
 
 def load(filename, device=False, context=None, **kwargs):
     """Read a pattern file by its extension, like ``kikuchipy.load`` does for the binary formats
-    this package reads: ``.dat`` (NORDIF), ``.up1`` / ``.up2`` (EDAX), ``.ebsp`` (Oxford Instruments)."""
+    this package reads: ``.dat`` (NORDIF), ``.up1`` / ``.up2`` (EDAX), ``.ebsp`` (Oxford Instruments),
+    ``.h5`` / ``.hdf5`` / ``.h5ebsd`` (kikuchipy h5ebsd)."""
     ext = os.path.splitext(filename)[1].lower()
     if not os.path.isfile(filename):
         raise IOError(f"No filename matches {filename!r}")
@@ -182,4 +183,8 @@ def load(filename, device=False, context=None, **kwargs):
         from .io_oxford import load_oxford_binary
 
         return load_oxford_binary(filename, device=device, context=context, **kwargs)
-    raise IOError(f"Could not read {filename!r}: only .dat, .up1, .up2 and .ebsp files are read (the HDF5 formats need h5py)")
+    if ext in (".h5", ".hdf5", ".h5ebsd"):
+        from .io_h5ebsd import load_h5ebsd
+
+        return load_h5ebsd(filename, device=device, ctx=context, **kwargs)
+    raise IOError(f"Could not read {filename!r}: only .dat, .up1, .up2, .ebsp and kikuchipy .h5 / .hdf5 / .h5ebsd files are read")

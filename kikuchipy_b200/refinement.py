@@ -46,11 +46,13 @@ class Detector:
     """The geometry an ``EBSDDetector`` contributes to refinement: ``shape`` (rows, columns), one
     projection centre or one per map point (Bruker convention) and the tilts in degrees."""
 
-    def __init__(self, shape, pc=(0.5, 0.5, 0.5), sample_tilt=70.0, tilt=0.0, azimuthal=0.0, twist=0.0):
+    def __init__(self, shape, pc=(0.5, 0.5, 0.5), sample_tilt=70.0, tilt=0.0, azimuthal=0.0, twist=0.0,
+                 px_size=1.0, binning=1):
         self.shape = (int(shape[0]), int(shape[1]))
         self.nrows, self.ncols = self.shape
         self.pc = np.atleast_2d(np.asarray(pc, dtype=np.float64))
         self.sample_tilt, self.tilt, self.azimuthal, self.twist = sample_tilt, tilt, azimuthal, twist
+        self.px_size, self.binning = px_size, binning  # carried for the file formats; not used by refinement
 
     @property
     def navigation_shape(self):

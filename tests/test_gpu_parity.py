@@ -866,3 +866,142 @@ def test_adversarial_near_ties_are_caught_by_the_certificate(ctx, compute):
     assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
     assert flagged >= 32  # the planted rows cannot be certified from 32 candidates
     assert np.all((i1[:32] >= 1000) & (i1[:32] < 1300) | (i1[:32] == 17))
+
+
+# ---- division route of the prepare kernels, view-mode dictionaries ------------------------------------
+
+def _awkward_rows(rng, n, s):
+    """float32 rows that stress the division by the row norm: ordinary, scaled far up and down, nearly
+    and exactly constant, already centred, with zeros and with tiny (down to subnormal) values."""
+    x = rng.random((n, s), dtype=np.float32)
+    x[1] *= 1e-20
+    x[2] *= 1e20
+    x[3] = 0.5
+    x[4] = 0.5
+    x[4, 7] = np.nextafter(np.float32(0.5), np.float32(1))
+    x[5] -= x[5].mean()
+    x[6, ::3] = 0.0
+    x[7, ::5] = 1e-39          # subnormal elements among ordinary ones
+    x[8, ::2] = 1e-33
+    x[9] = 0.0
+    x[10] *= 1e-36
+    x[11] = (x[11] - 0.5) * 1e-12
+    x[12] *= 3e9               # norm beyond 2^30
+    x[13] *= 1e-11             # norm below 2^-30
+    x[14, 0] = np.float32(np.inf)
+    return x
+
+
+@pytest.mark.parametrize("src_dtype", [np.float32, np.uint8, np.uint16, np.float64])
+@pytest.mark.parametrize("masked", [False, True])
+def test_fma_division_route_is_bit_identical(ctx, src_dtype, masked):
+    """The prepare kernels divide by the row norm with a float32 FMA sequence wherever that is exactly
+    rounded and through the double reciprocal elsewhere (kdi_internal.cuh: kdi_div_fma / kdi_rowdiv):
+    every kernel variant, both metrics and awkward rows must give the bits of the all-double route -
+    float32 rows directly, the 16-bit operands through the tensor-core products."""
+    rng = np.random.default_rng(77)
+    sig = (36, 40)
+    n = 300
+    if np.issubdtype(src_dtype, np.floating):
+        raw = _awkward_rows(rng, n, sig[0] * sig[1]).astype(src_dtype).reshape((n,) + sig)
+    else:
+        raw = (rng.random((n,) + sig) * (60000 if src_dtype == np.uint16 else 255)).astype(src_dtype)
+        raw[3] = 7
+        raw[9] = 0
+    dic = orc.synthetic_dictionary(512, sig, seed=6)
+    smask = orc.circular_signal_mask(sig) if masked else None
+    out = {}
+    try:
+        ctx.set_signal_mask(smask)
+        for route in (0, 1):
+            ctx.set_option(_lib.OPT_DIV_DOUBLE, route)
+            got = []
+            for code in (_lib.KDI_NCC, _lib.KDI_NDP):
+                with ctx.patterns(raw, n, code) as p, ctx.patterns(dic, 512, code) as d:
+                    got.append(np.asarray(p).view(np.uint32))
+                    got.append(ctx.debug_gemm16(p, d).view(np.uint32))
+            out[route] = got
+    finally:
+        ctx.set_option(_lib.OPT_DIV_DOUBLE, 0)
+        ctx.set_signal_mask(None)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    # and the values are the reference's (ordinary rows)
+    want = orc.prepare_experimental(raw[20:], "ncc", n - 20, signal_mask=smask)
+    got = out[0][0].view(np.float32)[20:]
+    assert got.shape == want.shape and np.nanmax(np.abs(got - want)) < 2e-6
+
+
+@pytest.mark.parametrize("metric", ["ncc", "ndp"])
+@pytest.mark.parametrize("compute", ["fp16", "bf16"])
+def test_view_mode_dictionary_is_bit_identical(ctx, metric, compute):
+    """A device-resident float32 dictionary is kept as a VIEW by the driver (no normalised float32 copy;
+    exact scores recomputed from the caller's rows with the prepare kernel's arithmetic): indices and
+    scores must equal those of the copying mode bit for bit - ordinary rows, awkward rows (double
+    route, NaN rows), near-ties that send rows through the exact path (which materialises the copy)."""
+    import torch
+
+    rng = np.random.default_rng(91)
+    sig = (40, 40)
+    M, N, k = 700, 9000, 20
+    dic = rng.random((N, sig[0] * sig[1]), dtype=np.float32)
+    dic[:15] = _awkward_rows(rng, 15, sig[0] * sig[1])[:15]
+    dic[14, 0] = 0.25  # (no infinities: a NaN norm would poison only that row, but keep the scores comparable)
+    base = dic[4000].copy()
+    dic[5000:5100] = base[None] * (1.0 + 1e-4 * rng.standard_normal((100, sig[0] * sig[1])).astype(np.float32))
+    exp = orc.synthetic_experimental(M, sig, seed=92)
+    exp[:16] = np.clip(np.rint(255 * (0.8 * base.reshape(sig)[None] + 0.2 * rng.random((16,) + sig))), 0, 255).astype(np.uint8)
+    code = _lib.KDI_NCC if metric == "ncc" else _lib.KDI_NDP
+    d_exp, d_dic = torch.from_numpy(exp).cuda(), torch.from_numpy(dic).cuda()
+    out = {}
+    try:
+        ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 1 if compute == "bf16" else 0)
+        for view in (1, 0):
+            ctx.set_option(_lib.OPT_DICT_VIEW, view)
+            idx = torch.empty((M, k), dtype=torch.int64, device="cuda")
+            sc = torch.empty((M, k), dtype=torch.float32, device="cuda")
+            ctx.dictionary_indexing(d_exp, M, d_dic, N, code, k, out=(idx, sc))
+            out[view] = (idx.cpu().numpy(), sc.cpu().numpy().view(np.uint32), ctx.timings()["flagged_rows"])
+    finally:
+        ctx.set_option(_lib.OPT_DICT_VIEW, 1)
+        ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 0)
+    assert np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1])
+    assert out[1][2] == out[0][2] and out[1][2] >= 16
+    # the host path (always copying; what the oracle-parity tests above exercise) agrees too
+    i_h, s_h = ctx.dictionary_indexing(exp, M, dic, N, code, k)
+    assert np.array_equal(i_h, out[1][0]) and np.array_equal(s_h.view(np.uint32), out[1][1])
+    # and so does the oracle on a sample, with the awkward dictionary rows left out (NumPy's float32
+    # sums overflow / underflow on them)
+    rows = np.arange(16, M, 57)
+    d_ok = torch.from_numpy(dic[15:]).cuda()
+    idx = torch.empty((rows.size, k), dtype=torch.int64, device="cuda")
+    sc = torch.empty((rows.size, k), dtype=torch.float32, device="cuda")
+    ctx.dictionary_indexing(torch.from_numpy(exp[rows]).cuda(), rows.size, d_ok, N - 15, code, k, out=(idx, sc))
+    ridx, rsc = orc.dictionary_indexing(exp[rows], dic[15:].reshape((N - 15,) + sig), metric=metric, keep_n=k)
+    _check(ridx, rsc, idx.cpu().numpy(), sc.cpu().numpy())
+
+
+def test_view_mode_is_used_and_saves_the_float32_copy(ctx):
+    """The view really is what runs for a device-resident float32 dictionary (fewer bytes written by the
+    prepare step: its time drops), and it is not used for host or masked dictionaries."""
+    import torch
+
+    M, N, sig, k = 2048, 40_000, (60, 60), 20
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    exp = torch.randint(0, 256, (M,) + sig, dtype=torch.uint8, device="cuda", generator=g)
+    dic = torch.rand((N,) + sig, dtype=torch.float32, device="cuda", generator=g)
+    idx = torch.empty((M, k), dtype=torch.int64, device="cuda")
+    sc = torch.empty((M, k), dtype=torch.float32, device="cuda")
+    res = {}
+    try:
+        for view in (1, 0):
+            ctx.set_option(_lib.OPT_DICT_VIEW, view)
+            best = 1e9
+            for _ in range(4):
+                ctx.dictionary_indexing(exp, M, dic, N, _lib.KDI_NCC, k, out=(idx, sc))
+                best = min(best, ctx.timings()["normalize_dict_ms"])
+            res[view] = (best, idx.cpu().numpy().copy(), sc.cpu().numpy().copy())
+    finally:
+        ctx.set_option(_lib.OPT_DICT_VIEW, 1)
+    assert np.array_equal(res[1][1], res[0][1]) and np.array_equal(res[1][2], res[0][2])
+    assert res[1][0] < res[0][0], (res[1][0], res[0][0])

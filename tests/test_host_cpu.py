@@ -537,3 +537,66 @@ def test_division_by_the_row_norm_through_a_double_reciprocal_is_exact():
     with np.errstate(invalid="ignore", divide="ignore"):
         z = (np.float64(np.float32(0.0)) * (1.0 / np.float64(np.float32(0.0)))).astype(np.float32)
     assert np.isnan(z)  # 0 / 0 (constant pattern) stays NaN
+
+
+_FMA_DIV_C = r"""
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+static uint64_t s = 88172645463325252ULL;
+static inline uint64_t rnd(void) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+/* number of operand pairs (out of n) for which the FMA sequence differs from the IEEE quotient;
+   norms in [2^e_lo, 2^e_hi], dividends down to 2^-span below the norm */
+long kdi_fma_div_mismatches(long n, int e_lo, int e_hi, int span) {
+  long bad = 0;
+  for (long i = 0; i < n; ++i) {
+    uint32_t mn = (uint32_t)(rnd() & 0x7fffff);
+    if ((i & 3) == 1) mn = 0x7fffff - (uint32_t)(rnd() & 0xff);
+    if ((i & 3) == 2) mn = (uint32_t)(rnd() & 0xff);
+    const int en = 127 + e_lo + (int)(rnd() % (uint64_t)(e_hi - e_lo + 1));
+    const float nrm = u2f(((uint32_t)en << 23) | mn);
+    uint32_t mc = (uint32_t)(rnd() & 0x7fffff);
+    if (((i >> 2) & 3) == 1) mc = 0x7fffff - (uint32_t)(rnd() & 0xff);
+    if (((i >> 2) & 3) == 2) mc = (uint32_t)(rnd() & 0xff);
+    int ec = en - (int)(rnd() % (uint64_t)(span + 1));
+    if (ec < 37) ec = 37; /* |c| >= 2^-90: the range the kernels send down this route */
+    float c = u2f(((uint32_t)ec << 23) | mc | ((uint32_t)(rnd() & 1) << 31));
+    if (fabsf(c) > nrm) c *= 0.5f;
+    volatile float want = c / nrm;
+    const float y = (float)(1.0 / (double)nrm);
+    float q = c * y;
+    float r = fmaf(-nrm, q, c);
+    q = fmaf(r, y, q);
+    r = fmaf(-nrm, q, c);
+    q = fmaf(r, y, q);
+    if (memcmp(&q, (const void*)&want, 4) != 0) ++bad;
+  }
+  return bad;
+}
+"""
+
+
+def test_division_by_the_row_norm_through_the_fma_sequence_is_exact(tmp_path):
+    """The prepare kernels' default route (csrc/kdi_internal.cuh, kdi_div_fma): y = float(1 / double(n)),
+    q0 = c y, two residual corrections with FMAs.  Inside the operand range the kernels send down this
+    route (2^-30 <= n <= 2^30, non-zero |c| >= 2^-90) it must give the IEEE float32 quotient bit for
+    bit.  Checked with the host's own fmaf (a C helper built on the spot: NumPy has no fused
+    multiply-add), adversarial significands (all ones, all zeros) included."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "fma_div.c"
+    src.write_text(_FMA_DIV_C)
+    lib = tmp_path / "fma_div.so"
+    subprocess.run([gcc, "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", str(src), "-o", str(lib), "-lm"],
+                   check=True)
+    f = ctypes.CDLL(str(lib)).kdi_fma_div_mismatches
+    f.restype = ctypes.c_long
+    f.argtypes = [ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    assert f(20_000_000, -30, 30, 60) == 0   # the whole admitted range
+    assert f(20_000_000, -8, 8, 24) == 0     # where real rows live

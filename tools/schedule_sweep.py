@@ -20,8 +20,9 @@ REPS, ROUNDS = int(os.environ.get("REPS", "3")), int(os.environ.get("ROUNDS", "4
 O = _lib
 NAMES = {"flags": O.OPT_DEP_FLAGS, "groups": O.OPT_MIN_GROUPS, "post": O.OPT_POST_PER_GROUP, "sms": O.OPT_GEMM_SMS,
          "serial": O.OPT_GEMM_SERIAL, "part": O.OPT_SM_PARTITION, "cores": O.OPT_POST_CORESIDENT, "split": O.OPT_EARLY_SPLIT, "overlap": O.OPT_OVERLAP, "stages": O.OPT_MAX_STAGES,
-         "strip": O.OPT_STRIP_TILES, "sb": O.OPT_SUPERBLOCK}
-DEFAULTS = {"flags": 0, "groups": 0, "post": 0, "sms": 0, "serial": 0, "part": 0, "cores": 0, "split": 1, "overlap": 1, "stages": 0, "strip": 0, "sb": 0}
+         "strip": O.OPT_STRIP_TILES, "sb": O.OPT_SUPERBLOCK, "view": O.OPT_DICT_VIEW, "divd": O.OPT_DIV_DOUBLE}
+DEFAULTS = {"flags": 0, "groups": 0, "post": 0, "sms": 0, "serial": 0, "part": 0, "cores": 0, "split": 1, "overlap": 1, "stages": 0, "strip": 0, "sb": 0,
+            "view": 1, "divd": 0}
 SETTINGS = os.environ.get(
     "SETTINGS",
     "split=1;split=0;split=0,groups=4;flags=1;overlap=0").split(";")
