@@ -199,6 +199,17 @@ int kdi_match_topk(kdi_ctx* ctx, const kdi_patterns* experimental,
 int kdi_match_full(kdi_ctx* ctx, const kdi_patterns* experimental,
                    const kdi_patterns* dictionary, float* out, int out_loc);
 
+/* ---- float64 scores of listed pairs (the metrics' dtype=float64) ----------
+ * (similarity_metrics/_normalized_cross_correlation.py:113-126,181-183,228-233 with dtype float64)
+ * For output row r (experimental source row exp_rows[r], or r when exp_rows is NULL) and each of its k
+ * candidates (dictionary rows, -1 = none -> NaN): the NCC / NDP score computed in float64 from the RAW
+ * patterns with the context's signal mask.  All pointers are DEVICE pointers; out: rows x k doubles.
+ * The GPU metrics' float64 mode nominates candidates with the float32 pipeline and takes their final
+ * scores and order from here (kikuchipy_b200/similarity_metrics.py). */
+int kdi_scores_f64(kdi_ctx* ctx, const void* experimental, int exp_dtype, const int64_t* exp_rows,
+                   int64_t rows, const void* dictionary, int dict_dtype, int64_t dict_rows, int64_t S,
+                   int metric, const int64_t* candidates, int k, double* out);
+
 /* validation aid: the raw tensor-core block, out_host[i*dict_rows + j] = sum_k a16[i][k]*b16[j][k]
  * (16-bit operands = normalised rows * 256, fp32 accumulate), through the same TMA/tcgen05
  * pipeline as kdi_match_topk but without the fused selection.  Small blocks only. */

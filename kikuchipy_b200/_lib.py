@@ -116,6 +116,7 @@ SIGNATURES = {
     "kdi_match_topk": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _i]),
     "kdi_match_full": (_i, [_vp, _vp, _vp, _vp, _i]),
     "kdi_debug_gemm16": (_i, [_vp, _vp, _vp, _vp]),
+    "kdi_scores_f64": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _i, _i64, _i64, _i, _vp, _i, _vp]),
     "kdi_merge_topk": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _i]),
     "kdi_dictionary_indexing": (
         _i,
@@ -641,6 +642,43 @@ class Context:
         out = np.empty((exp.shape[0], dic.shape[0]), dtype=np.float32)
         self._check(self._lib.kdi_debug_gemm16(self._h, exp._h, dic._h, out.ctypes.data))
         return out
+
+    def device_rows(self, data, rows: int):
+        """``data`` reshaped to ``(rows, -1)`` as a CUDA tensor (uploaded through the pinned ring when it
+        lives on the host; 16-bit unsigned data travels as its bytes)."""
+        import torch
+
+        if hasattr(data, "is_cuda"):
+            t = data if data.is_cuda else data.to(torch.device("cuda", self.device))
+            return t.contiguous().reshape(int(rows), -1)
+        a = np.asarray(data)
+        if a.dtype not in _DTYPES:
+            a = a.astype(np.float32)
+        return self.to_device(np.ascontiguousarray(a).reshape(int(rows), -1))
+
+    def scores_f64(self, exp_rows_dev, exp_row_index, dict_rows_dev, metric: int, candidates) -> np.ndarray:
+        """float64 NCC / NDP scores of every row's listed candidates from the RAW device-resident patterns
+        (``kdi_scores_f64``; the context's signal mask applies).  ``exp_row_index``: source row of each
+        output row (``None`` = all rows in order); ``candidates``: ``(rows, k)`` dictionary rows, -1 = none."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        cand = torch.as_tensor(np.ascontiguousarray(candidates, dtype=np.int64)).to(dev)
+        rows, k = cand.shape
+        idx = None
+        if exp_row_index is not None:
+            idx = torch.as_tensor(np.ascontiguousarray(exp_row_index, dtype=np.int64)).to(dev)
+        out = torch.empty((rows, k), dtype=torch.float64, device=dev)
+        ecode, dcode = _TORCH_DTYPES[str(exp_rows_dev.dtype)], _TORCH_DTYPES[str(dict_rows_dev.dtype)]
+        S = int(exp_rows_dev.shape[1])
+        if int(dict_rows_dev.shape[1]) != S:
+            raise ValueError(f"Experimental ({S}) and dictionary ({int(dict_rows_dev.shape[1])}) signal sizes must be identical")
+        self._stream_sync(dev)
+        self._check(self._lib.kdi_scores_f64(
+            self._h, exp_rows_dev.data_ptr(), ecode, idx.data_ptr() if idx is not None else None, rows,
+            dict_rows_dev.data_ptr(), dcode, int(dict_rows_dev.shape[0]), S, int(metric), cand.data_ptr(), int(k),
+            out.data_ptr()))
+        return out.cpu().numpy()
 
     def merge_topk(self, scores, indices, k_out: int):
         """Merge ``(n_lists, rows, k_in)`` ranked lists into ``(rows, k_out)``.

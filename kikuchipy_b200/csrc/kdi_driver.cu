@@ -673,7 +673,9 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   const bool light = dsrc.mp ? S * 4 <= 16384  // (projection kernel: one float32 pattern per CTA in shared memory)
                              : (kdi_normalize_is_light(S, s_eff, false, ctx->mask_S != 0) &&
                                 (dict_dtype == KDI_F32 || dict_dtype == KDI_U8));
-  const bool early = overlap_ok && !flag_mode && ctx->early_split && (light || ctx->overlap == 2) &&
+  // (a view-mode dictionary is prepared in ~0.45 ms at 100 000 x 3 600: splitting it gains nothing and the
+  // two concurrent prepare launches slow each other down - measured 0.1-0.2 ms per step, s17 sweep)
+  const bool early = overlap_ok && !flag_mode && ctx->early_split && (!view || ctx->overlap == 2) && (light || ctx->overlap == 2) &&
                      (ctx->overlap == 2 ? dict_rows >= 4 * KDI_TILE_N : (dict_rows >= 16384 && exp_rows >= 2048));
   int64_t g1_rows = dict_rows;
   cudaEvent_t e_fill = nullptr;

@@ -435,21 +435,77 @@ kdi_normalize_f32_regs(const T* __restrict__ src, int64_t S, int metric,
   }
 }
 
-// fast path for rows of up to 4096 values (float32 or uint8 source, no gathers, S % 4 == 0): ONE WARP
-// PER ROW, the row in registers (NV float4 per lane).  No shared memory and no block barriers - the two
-// reductions are five shuffle steps each - and the per-row scalar work (mean, square root, reciprocal)
-// is amortised over ~4 x NV values per lane instead of 16: the CTA-per-row kernel above spent ~38
-// instructions per value on 60 x 60 patterns (issue-bound at 68 % of the issue slots, ncu r2b), this one
-// ~13.  Memory-level parallelism comes from the NV independent 16-byte loads every lane issues up front.
+// fast path for the common detector sizes up to 64 x 64 (float32 or uint8 source, no gathers): ONE WARP
+// PER ROW, the row in registers (NV float4 per lane, NV = ceil(S / 128) exactly).  No shared memory and
+// no block barriers - the two reductions are five shuffle steps each - and the per-row scalar work (mean,
+// square root, reciprocal) is amortised over ~4 NV values per lane instead of 16: the CTA-per-row kernel
+// above spends ~38 instructions per value on 60 x 60 patterns (issue-bound, ncu r2b), this one ~13.
+// Memory-level parallelism comes from the NV independent 16-byte loads every lane issues up front.
+// The unrolled body is kept inside the 32 KB instruction cache: rows that cannot take the FMA division
+// (tiny dividends, norm out of range, KDI_OPT_DIV_DOUBLE) are rare and go through a compact rolled
+// routine that re-reads the row from L1 / L2 with the same per-lane order of operations (identical
+// statistics, hence identical results), and the tiny-dividend tracking is compiled in only for
+// uncentred float rows (TRACK).
 constexpr int kWarpNormThreads = 128;
 
-template <typename T, int NV, bool BF16>
-__global__ void __launch_bounds__(kWarpNormThreads, NV <= 8 ? 6 : (NV <= 16 ? 4 : 3))
+template <typename T, bool BF16>
+__device__ __noinline__ void normalize_row_rolled(const T* __restrict__ x, int n4, int64_t S, int metric,
+                                                  float4* __restrict__ o32, uint2* __restrict__ o16,
+                                                  float4* __restrict__ stat, int lane, int force_double) {
+  float mean = 0.f;
+  if (metric == KDI_NCC) {
+    double s = 0.0;
+    for (int j = lane; j < n4; j += 32) {
+      const float4 v = load4(x, j);
+      s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = (float)(s / (double)S);
+  }
+  double ss = 0.0;
+  uint32_t amin = 0xFFFFFFFFu;
+  for (int j = lane; j < n4; j += 32) {
+    float4 v = load4(x, j);
+    v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+    ss += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+    amin = kdi_min_abs_track(kdi_min_abs_track(amin, v.x), v.y);
+    amin = kdi_min_abs_track(kdi_min_abs_track(amin, v.z), v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, amin, o);
+    amin = other < amin ? other : amin;
+  }
+  const float norm = (float)sqrt(ss);
+  const bool track = needs_min_tracking<T>(metric, mean);
+  kdi_rowdiv dv = kdi_rowdiv_make(norm, !track || kdi_min_abs_ok(amin));
+  if (force_double) dv.fast = false;
+  if (stat != nullptr && lane == 0) *stat = make_float4(mean, dv.n, dv.y, dv.fast ? 0.f : 1.f);
+  for (int j = lane; j < n4; j += 32) {
+    const float4 c = load4(x, j);
+    float4 v;
+    if (dv.fast) {
+      v.x = kdi_div_fma(c.x - mean, dv.n, dv.y); v.y = kdi_div_fma(c.y - mean, dv.n, dv.y);
+      v.z = kdi_div_fma(c.z - mean, dv.n, dv.y); v.w = kdi_div_fma(c.w - mean, dv.n, dv.y);
+    } else {
+      v.x = kdi_div_by_norm(c.x - mean, dv.rd); v.y = kdi_div_by_norm(c.y - mean, dv.rd);
+      v.z = kdi_div_by_norm(c.z - mean, dv.rd); v.w = kdi_div_by_norm(c.w - mean, dv.rd);
+    }
+    if (o32) o32[j] = v;
+    o16[j] = make_uint2(pack16<BF16>(v.x, v.y), pack16<BF16>(v.z, v.w));
+  }
+}
+
+template <typename T, int NV, bool BF16, bool TRACK>
+__global__ void __launch_bounds__(kWarpNormThreads, NV <= 8 ? 6 : (NV <= 20 ? 4 : 3))
 kdi_normalize_warp_rows(const T* __restrict__ src, int64_t S, int metric, float* __restrict__ a32, int64_t s_pitch,
                         uint16_t* __restrict__ a16, int64_t kp, int64_t n_rows, uint32_t* __restrict__ ready,
                         int64_t ready_row0, int n_tiles_total, float4* __restrict__ rstat, int force_double) {
   const int lane = threadIdx.x & 31;
-  const int n4 = (int)(S >> 2);
+  const int n4 = (int)(S >> 2);  // 32 (NV - 1) < n4 <= 32 NV: only the last group of float4 can be partial
+  const bool last = lane + 32 * (NV - 1) < n4;
   // (with readiness counters the rows are handed out dynamically and in order, see kdi_normalize_f32_regs)
   uint32_t* work = ready ? ready + kdi_ready_words_before_work(n_tiles_total) : nullptr;
   const int64_t stride = (int64_t)gridDim.x * (kWarpNormThreads / 32);
@@ -462,12 +518,12 @@ kdi_normalize_warp_rows(const T* __restrict__ src, int64_t S, int metric, float*
   int64_t row = work ? next_row(0) : (int64_t)blockIdx.x * (kWarpNormThreads / 32) + (threadIdx.x >> 5);
   while (row < n_rows) {
     const T* x = src + row * S;
+    float4* o32 = a32 ? reinterpret_cast<float4*>(a32 + row * s_pitch) : nullptr;
+    uint2* o16 = reinterpret_cast<uint2*>(a16 + row * kp);
     float4 r[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int j = lane + 32 * i;
-      r[i] = (j < n4) ? load4(x, j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int i = 0; i < NV - 1; ++i) r[i] = load4(x, lane + 32 * i);
+    r[NV - 1] = last ? load4(x, lane + 32 * (NV - 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
     float mean = 0.f;
     if (metric == KDI_NCC) {
       double s = 0.0;
@@ -477,50 +533,54 @@ kdi_normalize_warp_rows(const T* __restrict__ src, int64_t S, int metric, float*
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       mean = (float)(s / (double)S);
     }
-    double ss = 0.0;
-    const bool track = needs_min_tracking<T>(metric, mean);
-    uint32_t amin = 0xFFFFFFFFu;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (lane + 32 * i < n4) {
-        r[i].x -= mean; r[i].y -= mean; r[i].z -= mean; r[i].w -= mean;
-        ss += ((double)r[i].x * r[i].x + (double)r[i].y * r[i].y) +
-              ((double)r[i].z * r[i].z + (double)r[i].w * r[i].w);
-        if (track) {
-          amin = kdi_min_abs_track(kdi_min_abs_track(amin, r[i].x), r[i].y);
-          amin = kdi_min_abs_track(kdi_min_abs_track(amin, r[i].z), r[i].w);
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (track) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t other = __shfl_xor_sync(0xffffffffu, amin, o);
-        amin = other < amin ? other : amin;
-      }
-    }
-    const float norm = (float)sqrt(ss);
-    kdi_rowdiv dv = kdi_rowdiv_make(norm, !track || kdi_min_abs_ok(amin));
-    if (force_double) dv.fast = false;
-    if (rstat != nullptr && lane == 0) rstat[row] = make_float4(mean, dv.n, dv.y, dv.fast ? 0.f : 1.f);
-    float4* o32 = a32 ? reinterpret_cast<float4*>(a32 + row * s_pitch) : nullptr;
-    uint2* o16 = reinterpret_cast<uint2*>(a16 + row * kp);
-    auto out_pass = [&](auto div) {
+    bool rolled = force_double != 0 || (!TRACK && needs_min_tracking<T>(metric, mean));
+    float norm = 0.f;
+    bool elements_ok = true;
+    if (!rolled) {
+      double ss = 0.0;
+      uint32_t amin = 0xFFFFFFFFu;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const int j = lane + 32 * i;
-        if (j < n4) {
+        if (i < NV - 1 || last) {
+          r[i].x -= mean; r[i].y -= mean; r[i].z -= mean; r[i].w -= mean;
+          ss += ((double)r[i].x * r[i].x + (double)r[i].y * r[i].y) +
+                ((double)r[i].z * r[i].z + (double)r[i].w * r[i].w);
+          if (TRACK) {
+            amin = kdi_min_abs_track(kdi_min_abs_track(amin, r[i].x), r[i].y);
+            amin = kdi_min_abs_track(kdi_min_abs_track(amin, r[i].z), r[i].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (TRACK) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, amin, o);
+          amin = other < amin ? other : amin;
+        }
+        elements_ok = kdi_min_abs_ok(amin);
+      }
+      norm = (float)sqrt(ss);
+      rolled = !(elements_ok && norm >= 0x1p-30f && norm <= 0x1p30f);
+    }
+    if (rolled) {  // warp-uniform
+      normalize_row_rolled<T, BF16>(x, n4, S, metric, o32, o16, rstat ? rstat + row : nullptr, lane, force_double);
+    } else {
+      const float y = (float)(1.0 / (double)norm);
+      if (rstat != nullptr && lane == 0) rstat[row] = make_float4(mean, norm, y, 0.f);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (i < NV - 1 || last) {
+          const int j = lane + 32 * i;
           float4 v;
-          v.x = div(r[i].x); v.y = div(r[i].y); v.z = div(r[i].z); v.w = div(r[i].w);
+          v.x = kdi_div_fma(r[i].x, norm, y); v.y = kdi_div_fma(r[i].y, norm, y);
+          v.z = kdi_div_fma(r[i].z, norm, y); v.w = kdi_div_fma(r[i].w, norm, y);
           if (o32) o32[j] = v;
           o16[j] = make_uint2(pack16<BF16>(v.x, v.y), pack16<BF16>(v.z, v.w));
         }
       }
-    };
-    if (dv.fast) out_pass([&](float c) { return kdi_div_fma(c, dv.n, dv.y); });
-    else out_pass([&](float c) { return kdi_div_by_norm(c, dv.rd); });
+    }
     // zero the K padding of the 16-bit row (s_pitch == S here)
     for (int64_t j = S + lane; j < kp; j += 32) a16[row * kp + j] = 0;
     if (ready != nullptr) {
@@ -617,40 +677,51 @@ void launch_regs(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int
         src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total, rstat, force_double);
 }
 
-template <typename T, int NV>
+template <typename T, int NV, bool TRACK>
 void launch_warp_rows(cudaStream_t stream, const T* src, int64_t S, int64_t rows, int metric, int bf16, float* a32,
                       int64_t s_pitch, void* a16, int64_t kp, unsigned grid, uint32_t* ready, int64_t ready_row0,
                       int n_tiles_total, float4* rstat, int force_double) {
   uint16_t* o16 = reinterpret_cast<uint16_t*>(a16);
   // (same shared-memory split as the tensor-core kernel, see launch_regs)
-  cudaFuncSetAttribute(kdi_normalize_warp_rows<T, NV, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(kdi_normalize_warp_rows<T, NV, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(kdi_normalize_warp_rows<T, NV, true, TRACK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(kdi_normalize_warp_rows<T, NV, false, TRACK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (bf16)
-    kdi_normalize_warp_rows<T, NV, true><<<grid, kWarpNormThreads, 0, stream>>>(
+    kdi_normalize_warp_rows<T, NV, true, TRACK><<<grid, kWarpNormThreads, 0, stream>>>(
         src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total, rstat, force_double);
   else
-    kdi_normalize_warp_rows<T, NV, false><<<grid, kWarpNormThreads, 0, stream>>>(
+    kdi_normalize_warp_rows<T, NV, false, TRACK><<<grid, kWarpNormThreads, 0, stream>>>(
         src, S, metric, a32, s_pitch, o16, kp, rows, ready, ready_row0, n_tiles_total, rstat, force_double);
 }
+
+// NV values the warp-per-row kernel is built for: 30 x 30, 40 x 40, 48 x 48, 50 x 50, 60 x 60, 64 x 64 pixels
+// (and every other row length with the same number of 128-value groups)
+inline bool warp_rows_built_for(int nv) { return nv == 8 || nv == 13 || nv == 18 || nv == 20 || nv == 29 || nv == 32; }
 
 template <typename T>
 void launch_regs_any(cudaStream_t stream, const T* s, int64_t S, int64_t rows, int metric, int bf16,
                      float* a32, int64_t s_pitch, void* a16, int64_t kp, unsigned grid,
                      uint32_t* ready, int64_t ready_row0, int n_tiles_total, float4* rstat, int force_double,
                      int sm_count, bool resident) {
-  // rows of up to 4096 values: one warp per row (grid: four rows per CTA, or a resident grid that
-  // strides over the rows when the caller asked for a bounded number of CTAs)
+  // one warp per row (grid: four rows per CTA, or a resident grid that strides over the rows when the
+  // caller asked for a bounded number of CTAs)
   const int nv = (int)kdi_ceil_div(S / 4, 32);
-  if (nv <= 32) {
+  if (warp_rows_built_for(nv)) {
     unsigned g = (unsigned)kdi_ceil_div(rows, kWarpNormThreads / 32);
     if (resident && g > grid) g = grid;
     const unsigned cap = (unsigned)sm_count * 64;
     if (g > cap) g = cap;
-#define KDI_WARP_ROWS(NV_) launch_warp_rows<T, NV_>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, g, ready, ready_row0, n_tiles_total, rstat, force_double)
-    if (nv <= 8) KDI_WARP_ROWS(8);
-    else if (nv <= 16) KDI_WARP_ROWS(16);
-    else if (nv <= 24) KDI_WARP_ROWS(24);
-    else if (nv <= 29) KDI_WARP_ROWS(29);
+    // uncentred float rows carry the tiny-dividend tracking inline; integer sources never need it
+    const bool track = !std::is_integral<T>::value && metric != KDI_NCC;
+#define KDI_WARP_ROWS(NV_)                                                                                          \
+  do {                                                                                                              \
+    if (track) launch_warp_rows<T, NV_, !std::is_integral<T>::value>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, g, ready, ready_row0, n_tiles_total, rstat, force_double); \
+    else launch_warp_rows<T, NV_, false>(stream, s, S, rows, metric, bf16, a32, s_pitch, a16, kp, g, ready, ready_row0, n_tiles_total, rstat, force_double); \
+  } while (0)
+    if (nv == 8) KDI_WARP_ROWS(8);
+    else if (nv == 13) KDI_WARP_ROWS(13);
+    else if (nv == 18) KDI_WARP_ROWS(18);
+    else if (nv == 20) KDI_WARP_ROWS(20);
+    else if (nv == 29) KDI_WARP_ROWS(29);
     else KDI_WARP_ROWS(32);
 #undef KDI_WARP_ROWS
     return;

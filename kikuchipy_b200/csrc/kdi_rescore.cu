@@ -244,7 +244,7 @@ kdi_select_warp_kernel(const uint2* __restrict__ cand, const uint32_t* __restric
 // VIEW: the dictionary is a view-mode set (no stored float32 rows): dict32 is its float32 SOURCE and
 // dstat its per-row statistics (kdi_rank.cuh: warp_dot_view)
 template <int KC, bool VIEW>
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(kSelThreads, VIEW ? 6 : 1)  // (view: the prefetching dot product within 85 registers)
 kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restrict__ dict32,
                           const float4* __restrict__ dstat,
                           int64_t s_pitch, int64_t n_dict, const uint2* __restrict__ cand,

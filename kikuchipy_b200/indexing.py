@@ -227,7 +227,17 @@ def dictionary_indexing(
     t0 = time.time()
     if generated and dictionary_rotations is None:
         dictionary_rotations = dict_data.rotations
-    if isinstance(metric, _GpuMetric) and generated:
+    f64_mode = isinstance(metric, _GpuMetric) and np.dtype(metric.dtype) == np.float64
+    if f64_mode:
+        # dtype=float64 (reference: the metric casts to float64 and everything downstream is float64):
+        # the reference's chunk loop over the metric's hooks, whose match() ranks float32-nominated
+        # candidates by float64 scores computed on the device (similarity_metrics.SimilarityBlock64)
+        if generated:
+            dict_data = dict_data.compute()
+        simulation_indices, scores = _generic_driver(exp_data, dict_data, metric, keep_n, n_per_iteration)
+        simulation_indices = simulation_indices.astype(np.int64)
+        simulation_indices = simulation_indices + index_offset if index_offset else simulation_indices
+    elif isinstance(metric, _GpuMetric) and generated:
         # dictionary generated on the device from rotations of a master pattern: the reference's
         # `dictionary_chunk.compute()` (_dictionary_indexing.py:106-108) fused with the prepare step
         ctx = metric.context
@@ -321,7 +331,8 @@ def _generic_driver(exp_data, dict_data, metric, keep_n, n_per_iteration):
     keep_n = min(int(keep_n), dict_size)
     experimental = metric.prepare_experimental(exp_data)
     lazy = hasattr(dict_data, "compute")
-    dictionary = dict_data if lazy else np.asarray(dict_data)
+    on_device = hasattr(dict_data, "is_cuda")  # a CUDA tensor stays where it is; chunks are views of it
+    dictionary = dict_data if (lazy or on_device) else np.asarray(dict_data)
     dictionary = dictionary.reshape((dict_size, -1))
 
     def match_chunk(simulated, k):

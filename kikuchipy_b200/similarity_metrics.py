@@ -181,8 +181,85 @@ class SimilarityBlock:
         return out if dtype is None else out.astype(dtype)
 
 
+class _Prepared64:
+    """What ``prepare_*`` returns in float64 mode: the float32 prepared set (candidate nomination) and the
+    raw rows on the device (final float64 scores)."""
+
+    def __init__(self, patterns32, raw, row_index):
+        self.patterns32 = patterns32
+        self.raw = raw              # CUDA tensor (source rows, -1)
+        self.row_index = row_index  # source row of every kept row, or None
+        self.shape = patterns32.shape
+
+    def compute(self):
+        return self
+
+
+class SimilarityBlock64:
+    """``match()`` of two float64-mode sets.  ``topk`` / ``argtopk``: the float32 pipeline nominates
+    ``k + 16`` candidates per row (tensor-core candidates, exact float32 rescoring, certificate), the
+    float64 kernel gives them the reference's float64 scores and the order follows those.  A row whose
+    k-th float64 score does not clear the best score that can hide outside the nominated set by the
+    float32 rounding level is done again with twice as many candidates (exact duplicates in the
+    dictionary end at k' = N, i.e. every pair in float64)."""
+
+    MARGIN = 4e-6  # bound on |float32 exact score - float64 score| (unit vectors, fp32 FMA chain + rounding of the rows)
+
+    def __init__(self, ctx, experimental, dictionary, kdi_metric):
+        self._ctx, self._exp, self._dict, self._metric = ctx, experimental, dictionary, kdi_metric
+        self.shape = (experimental.shape[0], dictionary.shape[0])
+        self.dtype = np.dtype(np.float64)
+        self._cache = {}
+
+    def _topk(self, k):
+        k = int(k)
+        if k < 0:
+            raise NotImplementedError("only the k largest values are supported (k > 0)")
+        if k in self._cache:
+            return self._cache[k]
+        m, n = self.shape
+        extra = 16
+        while True:
+            kk = min(n, k + extra)
+            idx32, sc32 = self._ctx.match_topk(self._exp.patterns32, self._dict.patterns32, kk)
+            sc64 = self._ctx.scores_f64(self._exp.raw, self._exp.row_index, self._dict.raw, self._metric, idx32)
+            # rank by (float64 score descending, index ascending); NaN rows keep the float32 order
+            key = np.where(np.isnan(sc64), -np.inf, sc64)
+            order = np.lexsort((idx32, -key), axis=1)
+            idx = np.take_along_axis(idx32, order, axis=1)[:, :k]
+            sc = np.take_along_axis(sc64, order, axis=1)[:, :k]
+            if kk == n:
+                break
+            ok = np.isnan(sc[:, -1]) | np.isnan(sc32[:, -1]) | (sc[:, -1] > sc32[:, -1].astype(np.float64) + self.MARGIN)
+            if ok.all():
+                break
+            extra = 2 * (kk - k) + 16
+        self._cache = {k: (idx, sc)}
+        return self._cache[k]
+
+    def topk(self, k, axis=-1):
+        if axis not in (-1, 1):
+            raise ValueError("top-k is taken along the dictionary axis (axis=-1)")
+        return self._topk(k)[1]
+
+    def argtopk(self, k, axis=-1):
+        if axis not in (-1, 1):
+            raise ValueError("top-k is taken along the dictionary axis (axis=-1)")
+        return self._topk(k)[0]
+
+    def compute(self, **kwargs):
+        m, n = self.shape
+        cand = np.broadcast_to(np.arange(n, dtype=np.int64), (m, n))
+        return self._ctx.scores_f64(self._exp.raw, self._exp.row_index, self._dict.raw, self._metric, cand)
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.compute()
+        return out if dtype is None else out.astype(dtype)
+
+
 class _GpuMetric(SimilarityMetric):
-    _allowed_dtypes = [np.float32]
+    # float64: candidates from the float32 pipeline, final scores and order in float64 (SimilarityBlock64)
+    _allowed_dtypes = [np.float32, np.float64]
     _sign = 1
     _kdi_metric = None
 
@@ -214,9 +291,14 @@ class _GpuMetric(SimilarityMetric):
         signal mask -> normalise (``_normalized_cross_correlation.py:88-128``)."""
         self.raise_error_if_invalid()
         self._sync_signal_mask()
-        return self.context.patterns(
-            patterns, int(self.n_experimental_patterns), self._kdi_metric, self.navigation_mask
-        )
+        n = int(self.n_experimental_patterns)
+        if np.dtype(self.dtype) == np.float64:
+            raw = self.context.device_rows(patterns, n)
+            keep = None
+            if self.navigation_mask is not None:
+                keep = np.flatnonzero(~np.asarray(self.navigation_mask, dtype=bool).ravel())
+            return _Prepared64(self.context.patterns(raw, n, self._kdi_metric, self.navigation_mask), raw, keep)
+        return self.context.patterns(patterns, n, self._kdi_metric, self.navigation_mask)
 
     def prepare_dictionary(self, patterns):
         """cast -> signal mask -> normalise; ``patterns`` is 2-D
@@ -225,11 +307,19 @@ class _GpuMetric(SimilarityMetric):
         self._sync_signal_mask()
         if len(patterns.shape) != 2:
             raise ValueError("dictionary patterns must be reshaped to (n patterns, n pixels) first")
+        if np.dtype(self.dtype) == np.float64:
+            raw = self.context.device_rows(patterns, int(patterns.shape[0]))
+            return _Prepared64(self.context.patterns(raw, int(patterns.shape[0]), self._kdi_metric, None), raw, None)
         return self.context.patterns(patterns, int(patterns.shape[0]), self._kdi_metric, None)
 
     def match(self, experimental, dictionary):
         """``einsum("ik,mk->im")`` of prepared sets (``_normalized_cross_correlation.py:161-183``),
         evaluated lazily."""
+        if isinstance(experimental, _Prepared64) != isinstance(dictionary, _Prepared64):
+            raise ValueError("experimental and dictionary patterns were prepared with different metric dtypes")
+        if isinstance(experimental, _Prepared64):
+            self._sync_signal_mask()
+            return SimilarityBlock64(self.context, experimental, dictionary, self._kdi_metric)
         return SimilarityBlock(self.context, experimental, dictionary)
 
 
@@ -238,8 +328,9 @@ class NormalizedCrossCorrelationMetric(_GpuMetric):
     :math:`r = \sum (x_i-\bar x)(y_i-\bar y) / (\|x-\bar x\| \|y-\bar y\|)`.
 
     Drop-in for ``kikuchipy.indexing.NormalizedCrossCorrelationMetric``
-    (``_normalized_cross_correlation.py:26``); only ``float32`` is offered (the reference also
-    allows ``float64``)."""
+    (``_normalized_cross_correlation.py:26``).  ``dtype=float64`` like the reference: candidates are
+    nominated by the float32 pipeline, their final scores and order are computed in float64 on the
+    device (``SimilarityBlock64``)."""
 
     _kdi_metric = _lib.KDI_NCC
 

@@ -508,8 +508,11 @@ def test_gpu_metrics_subclass_the_reference_abc(monkeypatch):
             metric.raise_error_if_invalid()
             assert repr(metric) == (f"{cls.__name__}: float32, greater is better, rechunk: False, "
                                     "navigation mask: True, signal mask: True")
-            metric.dtype = np.float64  # the reference allows it; the GPU classes advertise float32 only
-            with pytest.raises(ValueError, match="Data type float64 not among supported data types"):
+            metric.dtype = np.float64  # allowed, like in the reference
+            metric.raise_error_if_invalid()
+            assert repr(metric).startswith(f"{cls.__name__}: float64, greater is better")
+            metric.dtype = np.float16  # _similarity_metric.py:244-253
+            with pytest.raises(ValueError, match="Data type float16 not among supported data types"):
                 metric.raise_error_if_invalid()
     finally:
         monkeypatch.undo()

@@ -248,5 +248,10 @@ def test_load_dispatches_on_extension(tmp_path):
     with pytest.raises(IOError, match="No filename matches"):
         kb.load(str(tmp_path / "missing.dat"))
     (tmp_path / "p.h5").write_bytes(b"x")
-    with pytest.raises(IOError, match="need h5py"):
+    with pytest.raises(IOError, match="is not an HDF5 file"):
         kb.load(str(tmp_path / "p.h5"))
+    kb.save_h5ebsd(str(tmp_path / "q.h5"), pats)
+    assert np.array_equal(kb.load(str(tmp_path / "q.h5")).data, pats)
+    (tmp_path / "p.tif").write_bytes(b"x")
+    with pytest.raises(IOError, match="only .dat, .up1"):
+        kb.load(str(tmp_path / "p.tif"))
