@@ -469,6 +469,19 @@ int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, const void*
                const double* pcs, const double* om_detector_to_sample, const kdi_refine_options* opt,
                double* results_out);
 
+/* The objective function alone - what the reference passes to scipy.optimize
+ * (_objective_functions.py:36-190) - for optimisers that run on the host (every SciPy method other than
+ * Nelder-Mead, _refinement/__init__.py:32-60): values_out[i][k] = 1 - NCC(pattern pattern_rows[i] (or i
+ * when NULL), projection with the parameters x[i][k]), i < n_rows, k < n_points.  x: n_rows x n_points x
+ * n_var; rotations (mode KDI_REFINE_PC): n_rows x n_points x 4; pcs (mode KDI_REFINE_ORI, optional):
+ * n_rows x 3.  patterns: n_source_patterns x (nrows*ncols), host or (kept there between calls) device;
+ * all other pointers host.  Same preparation, projection and float32 NCC arithmetic as kdi_refine. */
+int kdi_refine_objective(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, const void* patterns, int pat_loc,
+                         int pat_dtype, int64_t n_source_patterns, int nrows, int ncols, int rescale,
+                         const int64_t* pattern_rows, int64_t n_rows, const double* x, int n_points,
+                         const double* rotations, const double* pcs, const double* om_detector_to_sample,
+                         double* values_out);
+
 /* ---- experimental-side preprocessing (next row of the path: SURVEY.md section 8f.4) -------------
  * (EBSD.remove_static_background / remove_dynamic_background / average_neighbour_patterns,
  *  signals/ebsd.py:442-697, :943-1112; pattern/_pattern.py:96-111, :393-517; filters/fft_barnes.py

@@ -116,6 +116,7 @@ SIGNATURES = {
     "kdi_match_topk": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _i]),
     "kdi_match_full": (_i, [_vp, _vp, _vp, _vp, _i]),
     "kdi_debug_gemm16": (_i, [_vp, _vp, _vp, _vp]),
+    "kdi_refine_objective": (_i, [_vp, _vp, _i, _vp, _i, _i, _i64, _i, _i, _i, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp]),
     "kdi_scores_f64": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _i, _i64, _i64, _i, _vp, _i, _vp]),
     "kdi_merge_topk": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _i]),
     "kdi_dictionary_indexing": (
@@ -1108,6 +1109,32 @@ class Context:
                 x0.ctypes.data, n_starts, p(lo), p(hi), p(rot), p(pc), p(om), C.byref(o), out.ctypes.data,
             )
         )
+        del keep
+        return out
+
+    def refine_objective(self, mp: "MasterPattern", mode: int, patterns, nrows: int, ncols: int, rescale: bool,
+                         pattern_rows, x, rotations=None, pcs=None, om_detector_to_sample=None) -> np.ndarray:
+        """``kdi_refine_objective``: ``1 - NCC`` for row ``i`` = pattern ``pattern_rows[i]`` at each of the
+        parameter sets ``x[i]`` ``(rows, points, 3 | 6)``.  ``patterns``: ``(n, nrows * ncols)`` NumPy array
+        or (kept on the device between calls) CUDA tensor.  Returns ``(rows, points)`` float64."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        rows, n_points, nv = x.shape
+        ptr, loc, code, keep = _buffer(patterns, self)
+        n_src = int(patterns.shape[0])
+        pr = np.ascontiguousarray(pattern_rows, dtype=np.int64)
+        if pr.shape != (rows,):
+            raise ValueError(f"expected {rows} pattern rows, got {pr.shape}")
+        rot = None if rotations is None else np.ascontiguousarray(rotations, dtype=np.float64).reshape(rows, n_points, 4)
+        pc = None if pcs is None else np.ascontiguousarray(pcs, dtype=np.float64).reshape(rows, 3)
+        om = None if om_detector_to_sample is None else np.ascontiguousarray(om_detector_to_sample, dtype=np.float64).reshape(3, 3)
+        out = np.empty((rows, n_points), dtype=np.float64)
+
+        def p(a):
+            return None if a is None else a.ctypes.data
+
+        self._check(self._lib.kdi_refine_objective(
+            self._h, mp._h, int(mode), ptr, loc, code, n_src, int(nrows), int(ncols), int(bool(rescale)),
+            pr.ctypes.data, rows, x.ctypes.data, n_points, p(rot), p(pc), p(om), out.ctypes.data))
         del keep
         return out
 

@@ -44,6 +44,7 @@ struct RefineParams {
   double scale, scale_over_sqrt_pi_half;
   // experimental patterns
   const void* pat;
+  const int64_t* pat_rows;  // objective mode: source pattern of each row (null = row i is pattern i)
   int pat_dtype;
   int64_t S;            // detector pixels per pattern (nrows * ncols)
   const int32_t* cols;  // kept pixels (signal mask) or null
@@ -195,6 +196,61 @@ __device__ double evaluate(const RefineParams& p, const double* x, const double*
 __device__ __forceinline__ bool f_less(double a, double b) { return (a < b) || (b != b && a == a); }
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 
+// _prepare_pattern (_solvers.py:50-73): the kept pixels of source pattern `src_row` centred in e[],
+// optionally rescaled to [-1, 1] first; returns the squared norm
+__device__ __forceinline__ float prepare_pattern(const RefineParams& p, int64_t src_row, float* e,
+                                                 double (*red)[kRefWarps]) {
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  for (int64_t j = threadIdx.x; j < p.s_eff; j += kRefThreads) {
+    const float val = load_pixel(p.pat, p.pat_dtype, src_row * p.S + (p.cols ? (int64_t)p.cols[j] : j));
+    e[j] = val;
+    lo = fminf(lo, val);
+    hi = fmaxf(hi, val);
+  }
+  if (p.rescale) {  // (pattern - min) / float(max - min) * 2 - 1, the quotient in float64
+    block_minmax(lo, hi, red);
+    const double range = (double)__fsub_rn(hi, lo);
+    for (int64_t j = threadIdx.x; j < p.s_eff; j += kRefThreads)
+      e[j] = (float)((double)__fsub_rn(e[j], lo) / range * 2.0 + (-1.0));
+  }
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < p.s_eff; j += kRefThreads) s += (double)e[j];
+  s = block_sum(s, red);
+  const float mean = (float)(s / (double)p.s_eff);
+  double sq = 0.0;
+  for (int64_t j = threadIdx.x; j < p.s_eff; j += kRefThreads) {
+    const float cv = __fsub_rn(e[j], mean);
+    e[j] = cv;
+    sq += (double)__fmul_rn(cv, cv);
+  }
+  sq = block_sum(sq, red);
+  return (float)sq;
+}
+
+// Objective values only: row i = 1 - NCC of pattern pat_rows[i] and the projection for each of its
+// n_starts parameter sets x0[i][k] (with quat[i][k] in PC mode, pcs[i] in orientation mode).  This is the
+// function the reference hands to scipy.optimize (_objective_functions.py:36-190); optimisers other than
+// Nelder-Mead run on the host and call it in batches (kikuchipy_b200/refinement.py).
+template <int MODE, int NV>
+__global__ void __launch_bounds__(kRefThreads) kdi_refine_objective_kernel(const RefineParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int64_t pitch = (p.s_eff + 3) & ~(int64_t)3;
+  float* e = reinterpret_cast<float*>(smem_raw);
+  float* v = e + pitch;
+  __shared__ double red[2][kRefWarps];
+  for (int64_t row = blockIdx.x; row < p.n_patterns; row += gridDim.x) {
+    __syncthreads();
+    const float sqnorm = prepare_pattern(p, p.pat_rows ? p.pat_rows[row] : row, e, red);
+    for (int st = 0; st < p.n_starts; ++st) {
+      const int64_t so = (row * p.n_starts + st) * NV;
+      const double* quat = (MODE == 1) ? p.quat + (row * p.n_starts + st) * 4 : nullptr;
+      const double* pcf = (MODE == 0 && p.pcs) ? p.pcs + row * 3 : nullptr;
+      const double f = evaluate<MODE>(p, p.x0 + so, quat, pcf, e, v, sqnorm, red);
+      if (threadIdx.x == 0) p.out[row * p.n_starts + st] = f;
+    }
+  }
+}
+
 template <int MODE, int NV, int MINB>
 __global__ void __launch_bounds__(kRefThreads, MINB) kdi_refine_kernel(const RefineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -205,32 +261,7 @@ __global__ void __launch_bounds__(kRefThreads, MINB) kdi_refine_kernel(const Ref
 
   for (int64_t row = blockIdx.x; row < p.n_patterns; row += gridDim.x) {
     __syncthreads();
-    // ---- _prepare_pattern (_solvers.py:50-73) ----
-    float lo = FLT_MAX, hi = -FLT_MAX;
-    for (int64_t j = threadIdx.x; j < p.s_eff; j += kRefThreads) {
-      const float val = load_pixel(p.pat, p.pat_dtype, row * p.S + (p.cols ? (int64_t)p.cols[j] : j));
-      e[j] = val;
-      lo = fminf(lo, val);
-      hi = fmaxf(hi, val);
-    }
-    if (p.rescale) {  // (pattern - min) / float(max - min) * 2 - 1, the quotient in float64
-      block_minmax(lo, hi, red);
-      const double range = (double)__fsub_rn(hi, lo);
-      for (int64_t j = threadIdx.x; j < p.s_eff; j += kRefThreads)
-        e[j] = (float)((double)__fsub_rn(e[j], lo) / range * 2.0 + (-1.0));
-    }
-    double s = 0.0;
-    for (int64_t j = threadIdx.x; j < p.s_eff; j += kRefThreads) s += (double)e[j];
-    s = block_sum(s, red);
-    const float mean = (float)(s / (double)p.s_eff);
-    double sq = 0.0;
-    for (int64_t j = threadIdx.x; j < p.s_eff; j += kRefThreads) {
-      const float cv = __fsub_rn(e[j], mean);
-      e[j] = cv;
-      sq += (double)__fmul_rn(cv, cv);
-    }
-    sq = block_sum(sq, red);
-    const float sqnorm = (float)sq;
+    const float sqnorm = prepare_pattern(p, row, e, red);
 
     // ---- Nelder-Mead from every start; the best score wins (_solvers.py:236-254) ----
     double rho = 1.0, chi = 2.0, psi = 0.5, sigma = 0.5;
@@ -382,18 +413,22 @@ inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
-extern "C" int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, const void* patterns,
-                          int pat_loc, int pat_dtype, int64_t n_patterns, int nrows, int ncols, int rescale,
-                          const double* x0, int n_starts, const double* lower, const double* upper,
-                          const double* rotations, const double* pcs, const double* om_detector_to_sample,
-                          const kdi_refine_options* opt, double* results_out) {
+// objective == true: only evaluate the objective at the given points (pattern_rows: source pattern per row)
+static int refine_impl(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, const void* patterns,
+                       int pat_loc, int pat_dtype, int64_t n_patterns, int nrows, int ncols, int rescale,
+                       const double* x0, int n_starts, const double* lower, const double* upper,
+                       const double* rotations, const double* pcs, const double* om_detector_to_sample,
+                       const kdi_refine_options* opt, double* results_out, bool objective,
+                       const int64_t* pattern_rows, int64_t n_source_patterns) {
   if (!ctx) return KDI_EINVAL;
-  if (!mp || !patterns || !x0 || !opt || !results_out) return kdi_fail(ctx, KDI_EINVAL, "kdi_refine: NULL argument");
+  if (!mp || !patterns || !x0 || (!opt && !objective) || !results_out) return kdi_fail(ctx, KDI_EINVAL, "kdi_refine: NULL argument");
+  static const kdi_refine_options no_options = {0.0, 0.0, -1, -1, 0};
+  if (objective) opt = &no_options;
   if (mode < KDI_REFINE_ORI || mode > KDI_REFINE_ORI_PC) return kdi_fail(ctx, KDI_EINVAL, "kdi_refine: unknown mode %d", mode);
   if (n_patterns < 0 || n_starts < 1 || nrows < 1 || ncols < 1) return kdi_fail(ctx, KDI_EINVAL, "kdi_refine: bad shape");
   if (!kdi_dtype_size(pat_dtype)) return kdi_fail(ctx, KDI_EINVAL, "kdi_refine: unknown pattern dtype %d", pat_dtype);
   if ((lower == nullptr) != (upper == nullptr)) return kdi_fail(ctx, KDI_EINVAL, "kdi_refine: give both bounds or none");
-  if (mode == KDI_REFINE_PC && (!rotations || n_starts != 1))
+  if (mode == KDI_REFINE_PC && (!rotations || (n_starts != 1 && !objective)))
     return kdi_fail(ctx, KDI_EINVAL, "kdi_refine: PC refinement needs one rotation per pattern and one start");
   if (mode == KDI_REFINE_ORI && pcs == nullptr && (int64_t)nrows * ncols != mp->S)
     return kdi_fail(ctx, KDI_EINVAL, "kdi_refine: detector has %lld pixels, the master pattern's direction cosines %lld",
@@ -418,10 +453,13 @@ extern "C" int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, 
   // workspace: [patterns if on the host] [x0] [lb] [ub] [quat] [pcs] [out]
   const size_t esz = kdi_dtype_size(pat_dtype);
   const size_t n_x = (size_t)n_patterns * n_starts * nv;
-  const int out_stride = 2 + nv + (n_starts > 1 ? 1 : 0);
+  const int out_stride = objective ? n_starts : 2 + nv + (n_starts > 1 ? 1 : 0);
+  // (objective mode: `patterns` holds n_source_patterns patterns, the rows name theirs)
+  const int64_t n_stored = (objective && pattern_rows) ? n_source_patterns : n_patterns;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at = o; o = up256(o + bytes); return at; };
-  const size_t o_pat = pat_loc == KDI_HOST ? take((size_t)n_patterns * S * esz) : 0;
+  const size_t o_pat = pat_loc == KDI_HOST ? take((size_t)n_stored * S * esz) : 0;
+  const size_t o_rows = (objective && pattern_rows) ? take((size_t)n_patterns * 8) : 0;
   const size_t o_x0 = take(n_x * 8), o_lb = lower ? take(n_x * 8) : 0, o_ub = lower ? take(n_x * 8) : 0;
   const size_t o_q = rotations ? take((size_t)n_patterns * n_starts * 32) : 0;
   const size_t o_pc = pcs ? take((size_t)n_patterns * 24) : 0;
@@ -430,8 +468,14 @@ extern "C" int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, 
   uint8_t* w = reinterpret_cast<uint8_t*>(ctx->ws2);
   ctx->tm = kdi_timings();
   if (pat_loc == KDI_HOST) {
-    KDI_CUDA(ctx, cudaMemcpyAsync(w + o_pat, patterns, (size_t)n_patterns * S * esz, cudaMemcpyHostToDevice, st));
-    ctx->tm.h2d_bytes += n_patterns * S * (int64_t)esz;
+    KDI_CUDA(ctx, cudaMemcpyAsync(w + o_pat, patterns, (size_t)n_stored * S * esz, cudaMemcpyHostToDevice, st));
+    ctx->tm.h2d_bytes += n_stored * S * (int64_t)esz;
+  }
+  if (objective && pattern_rows) {
+    for (int64_t i = 0; i < n_patterns; ++i)
+      if (pattern_rows[i] < 0 || pattern_rows[i] >= n_source_patterns)
+        return kdi_fail(ctx, KDI_EINVAL, "kdi_refine_objective: pattern row %lld out of range", (long long)pattern_rows[i]);
+    KDI_CUDA(ctx, cudaMemcpyAsync(w + o_rows, pattern_rows, (size_t)n_patterns * 8, cudaMemcpyHostToDevice, st));
   }
   KDI_CUDA(ctx, cudaMemcpyAsync(w + o_x0, x0, n_x * 8, cudaMemcpyHostToDevice, st));
   if (lower) {
@@ -450,6 +494,7 @@ extern "C" int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, 
   p.scale = mp->scale;
   p.scale_over_sqrt_pi_half = mp->scale / kdi_proj::kSqrtPiHalf;
   p.pat = pat_loc == KDI_HOST ? (const void*)(w + o_pat) : patterns;
+  p.pat_rows = (objective && pattern_rows) ? reinterpret_cast<const int64_t*>(w + o_rows) : nullptr;
   p.pat_dtype = pat_dtype;
   p.S = S;
   p.cols = ctx->mask_S ? ctx->d_cols : nullptr;
@@ -497,7 +542,11 @@ extern "C" int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, 
     else if (mode == KDI_REFINE_PC) KDI_TRY(launch(kdi_refine_kernel<1, 3, MB>)); \
     else KDI_TRY(launch(kdi_refine_kernel<2, 6, MB>));                          \
   } while (0)
-  if (minb <= 2) KDI_REFINE_LAUNCH(2);
+  if (objective) {
+    if (mode == KDI_REFINE_ORI) KDI_TRY(launch(kdi_refine_objective_kernel<0, 3>));
+    else if (mode == KDI_REFINE_PC) KDI_TRY(launch(kdi_refine_objective_kernel<1, 3>));
+    else KDI_TRY(launch(kdi_refine_objective_kernel<2, 6>));
+  } else if (minb <= 2) KDI_REFINE_LAUNCH(2);
   else if (minb == 3) KDI_REFINE_LAUNCH(3);
   else KDI_REFINE_LAUNCH(4);
 #undef KDI_REFINE_LAUNCH
@@ -509,4 +558,23 @@ extern "C" int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, 
   KDI_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   ctx->tm.total_ms = ms;
   return KDI_OK;
+}
+
+extern "C" int kdi_refine(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, const void* patterns,
+                          int pat_loc, int pat_dtype, int64_t n_patterns, int nrows, int ncols, int rescale,
+                          const double* x0, int n_starts, const double* lower, const double* upper,
+                          const double* rotations, const double* pcs, const double* om_detector_to_sample,
+                          const kdi_refine_options* opt, double* results_out) {
+  return refine_impl(ctx, mp, mode, patterns, pat_loc, pat_dtype, n_patterns, nrows, ncols, rescale, x0, n_starts,
+                     lower, upper, rotations, pcs, om_detector_to_sample, opt, results_out, false, nullptr, 0);
+}
+
+extern "C" int kdi_refine_objective(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, const void* patterns,
+                                    int pat_loc, int pat_dtype, int64_t n_source_patterns, int nrows, int ncols,
+                                    int rescale, const int64_t* pattern_rows, int64_t n_rows, const double* x,
+                                    int n_points, const double* rotations, const double* pcs,
+                                    const double* om_detector_to_sample, double* values_out) {
+  return refine_impl(ctx, mp, mode, patterns, pat_loc, pat_dtype, n_rows, nrows, ncols, rescale, x, n_points, nullptr,
+                     nullptr, rotations, pcs, om_detector_to_sample, nullptr, values_out, true, pattern_rows,
+                     n_source_patterns);
 }

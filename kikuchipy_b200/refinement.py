@@ -6,8 +6,13 @@ Mirrors /root/reference/src/kikuchipy/signals/ebsd.py:1986-2560 (the three publi
 printed messages) for the reference's DEFAULT optimiser, ``scipy.optimize.minimize`` with
 ``method="Nelder-Mead"``.  The per-pattern work - pattern preparation, projection of the master
 pattern, NCC, the simplex search - is one call into ``libkdi`` (``kdi_refine``, csrc/kdi_refine.cu).
-Other optimisers (Powell, the global SciPy methods, NLopt) are not implemented and raise
-``NotImplementedError``: there is no CPU fallback.
+Every other SciPy optimiser the reference offers (``minimize`` with another ``method``,
+``basinhopping``, ``differential_evolution``, ``dual_annealing``, ``shgo``;
+``_refinement/__init__.py:32-60``) runs its own (host) search loop, as it does in the reference, and gets
+its objective values from the device: ``kdi_refine_objective`` evaluates ``1 - NCC`` for a batch of
+(pattern, parameters) pairs, and the searches of many patterns advance side by side so that the batches
+are large (``_HostDriven``).  NLopt (``ln_neldermead``) is not installed here and raises like the
+reference does without it.
 
 Inputs are read by duck typing: kikuchipy signals / orix crystal maps / ``EBSDDetector`` work, and
 so do plain arrays, :class:`~kikuchipy_b200.indexing.DictionaryIndexingResult` and
@@ -206,6 +211,142 @@ def _master_pattern_arrays(master_pattern, energy):
 
 _NM_NAMES = ("nelder-mead", "neldermead")
 
+# _refinement/__init__.py:32-60
+SUPPORTED_OPTIMIZATION_METHODS = {
+    "minimize": {"type": "local", "supports_bounds": True, "package": "scipy"},
+    "ln_neldermead": {"type": "local", "supports_bounds": True, "package": "nlopt"},
+    "basinhopping": {"type": "global", "supports_bounds": False, "package": "scipy"},
+    "differential_evolution": {"type": "global", "supports_bounds": True, "package": "scipy"},
+    "dual_annealing": {"type": "global", "supports_bounds": True, "package": "scipy"},
+    "shgo": {"type": "global", "supports_bounds": True, "package": "scipy"},
+}
+
+
+def _method_plan(method, method_kwargs):
+    """``_RefinementSetup.set_optimization_parameters`` (``_refinement.py:1053-1139``): which search runs
+    where.  Returns ``("device", options, name, "local")`` for SciPy's Nelder-Mead (the whole search on
+    the GPU) or ``("host", (function name, keyword arguments), name, type)``."""
+    method = "minimize" if method is None else str(method).lower()
+    if method not in SUPPORTED_OPTIMIZATION_METHODS:
+        raise ValueError(f"Method {method!r} not in the list of supported methods {list(SUPPORTED_OPTIMIZATION_METHODS)}")
+    info = SUPPORTED_OPTIMIZATION_METHODS[method]
+    if info["package"] == "nlopt":
+        raise ImportError(f"Optimization method {method.upper()!r} requires nlopt, which is not installed")
+    kw = dict(method_kwargs or {})
+    if method == "minimize" and "method" not in kw:
+        name = kw["method"] = "Nelder-Mead"
+    elif "method" in kw:
+        name = str(kw["method"])
+    else:
+        name = method
+    if method == "basinhopping" and "minimizer_kwargs" not in kw:
+        kw["minimizer_kwargs"] = {}
+    if method == "minimize" and name.lower() in _NM_NAMES:
+        try:
+            opts, _ = _nelder_mead_options("minimize", kw)
+            return "device", opts, name, info["type"], kw
+        except NotImplementedError:
+            pass  # an option the device search does not implement: SciPy's own loop, objective on the device
+    return "host", (method, kw), name, info["type"], kw
+
+
+def _supports_bounds(method):
+    return SUPPORTED_OPTIMIZATION_METHODS["minimize" if method is None else str(method).lower()]["supports_bounds"]
+
+
+class _HostDriven:
+    """SciPy's optimisers on the host, the objective on the device.
+
+    One Python thread per pattern in flight runs the optimiser exactly as the reference calls it
+    (``_solvers.py:186-254, 300-345, 420-470``); its objective function parks the thread until the
+    coordinator has gathered the requests of all threads that are currently waiting and evaluated them
+    in one ``kdi_refine_objective`` launch.  Vectorised calls (``differential_evolution(vectorized=True)``
+    hands over a whole population) become several points of one row."""
+
+    def __init__(self, evaluate, n_workers):
+        import threading
+
+        self._evaluate = evaluate  # (pattern ids, list of (points, nv) arrays) -> list of (points,) arrays
+        self._cv = threading.Condition()
+        self._pending = []   # (pattern id, x (points, nv), slot)
+        self._running = 0    # worker threads that are neither finished nor parked in the objective
+        self._n_workers = n_workers
+        self.launches = 0
+
+    def objective(self, pattern_id):
+        def f(x, *_):
+            x = np.asarray(x, dtype=np.float64)
+            pts = x.reshape(1, -1) if x.ndim == 1 else x.T  # vectorised callers pass (nv, points)
+            slot = {}
+            with self._cv:
+                self._pending.append((pattern_id, np.ascontiguousarray(pts), slot))
+                self._running -= 1
+                self._cv.notify_all()
+                while "y" not in slot and "err" not in slot:
+                    self._cv.wait()
+            if "err" in slot:
+                raise slot["err"]
+            return float(slot["y"][0]) if x.ndim == 1 else slot["y"]
+        return f
+
+    def run(self, jobs):
+        """``jobs``: callables taking (pattern position) -> result; returns their results in order."""
+        import queue
+        import threading
+
+        results = [None] * len(jobs)
+        errors = []
+        todo = queue.Queue()
+        for i, job in enumerate(jobs):
+            todo.put((i, job))
+        n_threads = max(1, min(self._n_workers, len(jobs)))
+
+        def worker():
+            while True:
+                try:
+                    i, job = todo.get_nowait()
+                except queue.Empty:
+                    break
+                try:
+                    results[i] = job()
+                except BaseException as e:  # noqa: BLE001
+                    errors.append(e)
+            with self._cv:
+                self._running -= 1
+                self._cv.notify_all()
+
+        with self._cv:
+            self._running = n_threads
+        threads = [threading.Thread(target=worker, daemon=True) for _ in range(n_threads)]
+        for t in threads:
+            t.start()
+        while True:
+            with self._cv:
+                while self._running > 0:
+                    self._cv.wait()
+                batch, self._pending = self._pending, []
+                if not batch:
+                    break  # every worker has finished
+            try:
+                ys = self._evaluate([b[0] for b in batch], [b[1] for b in batch])
+                self.launches += 1
+                with self._cv:
+                    for (_, _, slot), y in zip(batch, ys):
+                        slot["y"] = y
+                    self._running += len(batch)
+                    self._cv.notify_all()
+            except BaseException as e:  # noqa: BLE001
+                with self._cv:
+                    for _, _, slot in batch:
+                        slot["err"] = e
+                    self._running += len(batch)
+                    self._cv.notify_all()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results
+
 
 def _nelder_mead_options(method, method_kwargs):
     """Tolerances and limits SciPy would use (``minimize`` + ``_minimize_neldermead``)."""
@@ -256,10 +397,11 @@ def _bounds(x0, trust_region, mode):
     return np.fmax(x0 - tr, lo), np.fmin(x0 + tr, hi)
 
 
-def _info_message(method_name, trust_region, method_kwargs, n_ps):
+def _info_message(method_name, trust_region, method_kwargs, n_ps, kind="local", supports_bounds=True):
     """``_RefinementSetup.get_info_message`` (``_refinement.py:1249-1278``)."""
-    info = f"Refinement information:\n  Method: {method_name} (local) from SciPy"
-    info += "\n  Trust region (+/-): " + np.array_str(np.asarray(trust_region), precision=5)
+    info = f"Refinement information:\n  Method: {method_name} ({kind}) from SciPy"
+    if supports_bounds:
+        info += "\n  Trust region (+/-): " + np.array_str(np.asarray(trust_region), precision=5)
     info += f"\n  Keyword arguments passed to method: {method_kwargs}"
     if n_ps > 0:
         info += f"\n  No. pseudo-symmetry operators: {n_ps}"
@@ -314,7 +456,7 @@ class _Setup:
         self.mpu, self.mpl = _master_pattern_arrays(master_pattern, energy)
         self.detector = detector
 
-    def run(self, mode, x0, lower, upper, rotations, pcs, opts, fixed_dc):
+    def run(self, mode, x0, lower, upper, rotations, pcs, opts, fixed_dc, host_plan=None, trust_region_passed=False):
         """One device call for this process's patterns.  With ``sharded`` (one process per GPU,
         ``torch.distributed`` initialised) the patterns are split into contiguous balanced slices,
         every rank refines its own and the finished rows are all-gathered: the path partitions by
@@ -331,10 +473,92 @@ class _Setup:
             def cut(arr):
                 return None if arr is None else arr[a:b]
 
-            local = self._run_local(mode, x0[a:b], cut(lower), cut(upper), cut(rotations), cut(pcs), opts, fixed_dc,
-                                    self.patterns[a:b])
+            if host_plan is not None:
+                whole, self.patterns = self.patterns, self.patterns[a:b]
+                try:
+                    local = self.run_host_driven(mode, x0[a:b], cut(lower), cut(upper), cut(rotations), cut(pcs),
+                                                 host_plan, fixed_dc, trust_region_passed)
+                finally:
+                    self.patterns = whole
+            else:
+                local = self._run_local(mode, x0[a:b], cut(lower), cut(upper), cut(rotations), cut(pcs), opts, fixed_dc,
+                                        self.patterns[a:b])
             return gather_rows(local, [e - s for s, e in bounds], self.group)
+        if host_plan is not None:
+            return self.run_host_driven(mode, x0, lower, upper, rotations, pcs, host_plan, fixed_dc, trust_region_passed)
         return self._run_local(mode, x0, lower, upper, rotations, pcs, opts, fixed_dc, self.patterns)
+
+    def _master_pattern_on_device(self, fixed_dc):
+        if fixed_dc:
+            gb = [-(self.ncols / self.nrows) * (self.pc[0, 0] / self.pc[0, 2]),
+                  (self.ncols / self.nrows) * (1 - self.pc[0, 0]) / self.pc[0, 2],
+                  -(1 - self.pc[0, 1]) / self.pc[0, 2], self.pc[0, 1] / self.pc[0, 2]]
+            if hasattr(self.detector, "gnomonic_bounds"):
+                gb = np.asarray(self.detector.gnomonic_bounds, dtype=np.float64).reshape(-1, 4)[0]
+            dc = _direction_cosines(gb, self.pc[0, 2], self.nrows, self.ncols, self.om)
+        else:
+            dc = np.zeros((self.nrows * self.ncols, 3))  # unused: computed per pattern on the device
+        return self.ctx.master_pattern(self.mpu, self.mpl, dc)
+
+    def run_host_driven(self, mode, x0, lower, upper, rotations, pcs, plan, fixed_dc, trust_region_passed,
+                        n_workers=64):
+        """The reference's ``_refine_*_solver_scipy`` for every pattern, with SciPy's optimiser on the host
+        and the objective on the device (``_HostDriven``).  Same result rows as ``run``."""
+        import copy
+
+        import scipy.optimize
+
+        fname, kwargs = plan
+        func = getattr(scipy.optimize, fname)
+        supports_bounds = SUPPORTED_OPTIMIZATION_METHODS[fname]["supports_bounds"]
+        ctx = self.ctx
+        n, n_starts, nv = x0.shape
+        if n == 0:
+            return np.zeros((0, 2 + nv + (1 if n_starts > 1 else 0)))
+        ctx.set_signal_mask(self.signal_mask)
+        try:
+            mp = self._master_pattern_on_device(fixed_dc)
+            pats = ctx.device_rows(self.patterns, n)  # uploaded once, read by every objective launch
+
+            def evaluate(ids, xs):
+                # one row per request; requests with several points (vectorised optimisers) are padded to
+                # the longest of the batch with copies of their first point
+                width = max(x.shape[0] for x in xs)
+                x = np.stack([np.concatenate([xi, np.repeat(xi[:1], width - xi.shape[0], axis=0)]) for xi in xs])
+                rows = np.asarray([i // n_starts for i in ids], dtype=np.int64)
+                rot = None if rotations is None else np.repeat(rotations[rows][:, None, :], width, axis=1)
+                pc = None if pcs is None else pcs[rows]
+                y = ctx.refine_objective(mp, mode, pats, self.nrows, self.ncols, self.rescale, rows, x, rot, pc, self.om)
+                return [y[k, :xs[k].shape[0]] for k in range(len(xs))]
+
+            host = _HostDriven(evaluate, n_workers)
+
+            def job(i, st):
+                f = host.objective(i * n_starts + st)
+                kw = copy.deepcopy(kwargs)
+                if fname == "minimize":
+                    if trust_region_passed:
+                        kw["bounds"] = np.stack([lower[i, st], upper[i, st]], axis=1)
+                    return lambda: func(fun=f, x0=x0[i, st], **kw)
+                if supports_bounds:
+                    return lambda: func(func=f, bounds=np.stack([lower[i, st], upper[i, st]], axis=1), **kw)
+                return lambda: func(func=f, x0=x0[i, st], **kw)  # basinhopping
+
+            if supports_bounds and fname != "minimize" and lower is None:
+                raise ValueError(f"Method {fname!r} needs bounds: pass a trust_region")
+            res = host.run([job(i, st) for i in range(n) for st in range(n_starts)])
+        finally:
+            ctx.set_signal_mask(None)
+        out = np.zeros((n, 2 + nv + (1 if n_starts > 1 else 0)))
+        for i in range(n):
+            rs = res[i * n_starts:(i + 1) * n_starts]
+            ncc = [1 - r.fun for r in rs]
+            best = int(np.argmax(ncc))  # _solvers.py:236-254
+            out[i, 0], out[i, 1], out[i, 2:2 + nv] = ncc[best], rs[best].nfev, rs[best].x
+            if n_starts > 1:
+                out[i, -1] = best
+        self.objective_launches = host.launches
+        return out
 
     def _run_local(self, mode, x0, lower, upper, rotations, pcs, opts, fixed_dc, patterns):
         ctx = self.ctx
@@ -342,16 +566,7 @@ class _Setup:
             return np.zeros((0, 2 + x0.shape[2] + (1 if x0.shape[1] > 1 else 0)))
         ctx.set_signal_mask(self.signal_mask)
         try:
-            if fixed_dc:
-                gb = [-(self.ncols / self.nrows) * (self.pc[0, 0] / self.pc[0, 2]),
-                      (self.ncols / self.nrows) * (1 - self.pc[0, 0]) / self.pc[0, 2],
-                      -(1 - self.pc[0, 1]) / self.pc[0, 2], self.pc[0, 1] / self.pc[0, 2]]
-                if hasattr(self.detector, "gnomonic_bounds"):
-                    gb = np.asarray(self.detector.gnomonic_bounds, dtype=np.float64).reshape(-1, 4)[0]
-                dc = _direction_cosines(gb, self.pc[0, 2], self.nrows, self.ncols, self.om)
-            else:
-                dc = np.zeros((self.nrows * self.ncols, 3))  # unused: computed per pattern on the device
-            mp = ctx.master_pattern(self.mpu, self.mpl, dc)
+            mp = self._master_pattern_on_device(fixed_dc)
             return ctx.refine(mp, mode, patterns, self.nrows, self.ncols, self.rescale, x0, lower, upper,
                               rotations, pcs, self.om, **opts)
         finally:
@@ -390,16 +605,17 @@ def refine_orientation(signal, xmap, detector, master_pattern, energy=None, navi
     Limit (all three ``refine_*`` functions): the kernel keeps the pattern and its simulation in
     shared memory, so at most 25 600 matched pixels (e.g. 160x160 unmasked); larger patterns raise
     ``NotImplementedError`` (``KDI_EUNSUPPORTED``) - bin them or use a signal mask."""
-    opts, name = _nelder_mead_options(method, method_kwargs)
+    where, opts, name, kind, kw_shown = _method_plan(method, method_kwargs)
     setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context, sharded, group)
     x0, n_ps = _starts(setup, pseudo_symmetry_ops)
     lower, upper = _bounds(x0, trust_region, "ori")
     if verbose:
-        print(_info_message(name, trust_region, dict(method_kwargs or {}, method=name), n_ps))
+        print(_info_message(name, trust_region, kw_shown, n_ps, kind, _supports_bounds(method)))
         print(f"Refining {setup.n} orientation(s):", file=sys.stdout)
     t0 = time.time()
     res = setup.run(_lib.REFINE_ORI, x0, lower, upper, None, setup.pcs if setup.unique_pc else None, opts,
-                    fixed_dc=not setup.unique_pc)
+                    fixed_dc=not setup.unique_pc, host_plan=None if where == "device" else opts,
+                    trust_region_passed=trust_region is not None)
     _finish(setup, res, "orientation", verbose, t0)
     if not compute:
         return res
@@ -427,15 +643,16 @@ def refine_projection_center(signal, xmap, detector, master_pattern, energy=None
     """Refine projection centres with fixed orientations (``signals/ebsd.py:2179-2356``).  Returns
     ``(scores, detector with the refined PCs, num_evals)`` like the reference
     (``_refinement.py:133-200``), or the raw ``(n, 5)`` array with ``compute=False``."""
-    opts, name = _nelder_mead_options(method, method_kwargs)
+    where, opts, name, kind, kw_shown = _method_plan(method, method_kwargs)
     setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context, sharded, group)
     x0 = setup.pcs[:, None, :].copy()
     lower, upper = _bounds(x0, trust_region, "pc")
     if verbose:
-        print(_info_message(name, trust_region, dict(method_kwargs or {}, method=name), 0))
+        print(_info_message(name, trust_region, kw_shown, 0, kind, _supports_bounds(method)))
         print(f"Refining {setup.n} projection center(s):", file=sys.stdout)
     t0 = time.time()
-    res = setup.run(_lib.REFINE_PC, x0, lower, upper, setup.quaternions, None, opts, fixed_dc=False)
+    res = setup.run(_lib.REFINE_PC, x0, lower, upper, setup.quaternions, None, opts, fixed_dc=False,
+                    host_plan=None if where == "device" else opts, trust_region_passed=trust_region is not None)
     _finish(setup, res, "pc", verbose, t0)
     if not compute:
         return res
@@ -452,16 +669,17 @@ def refine_orientation_projection_center(signal, xmap, detector, master_pattern,
     """Refine orientations and projection centres together (``signals/ebsd.py:2358-2560``).
     Returns ``(RefinementResult, detector with the refined PCs)``, or the raw ``(n, 8 | 9)``
     array with ``compute=False``."""
-    opts, name = _nelder_mead_options(method, method_kwargs)
+    where, opts, name, kind, kw_shown = _method_plan(method, method_kwargs)
     setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context, sharded, group)
     eu, n_ps = _starts(setup, pseudo_symmetry_ops)
     x0 = np.concatenate([eu, np.repeat(setup.pcs[:, None, :], eu.shape[1], axis=1)], axis=2)
     lower, upper = _bounds(x0, trust_region, "ori_pc")
     if verbose:
-        print(_info_message(name, trust_region, dict(method_kwargs or {}, method=name), n_ps))
+        print(_info_message(name, trust_region, kw_shown, n_ps, kind, _supports_bounds(method)))
         print(f"Refining {setup.n} orientation(s) and projection center(s):", file=sys.stdout)
     t0 = time.time()
-    res = setup.run(_lib.REFINE_ORI_PC, x0, lower, upper, None, None, opts, fixed_dc=False)
+    res = setup.run(_lib.REFINE_ORI_PC, x0, lower, upper, None, None, opts, fixed_dc=False,
+                    host_plan=None if where == "device" else opts, trust_region_passed=trust_region is not None)
     _finish(setup, res, "ori_pc", verbose, t0)
     if not compute:
         return res

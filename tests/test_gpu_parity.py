@@ -997,6 +997,7 @@ def test_view_mode_is_used_and_saves_the_float32_copy(ctx):
     sc = torch.empty((M, k), dtype=torch.float32, device="cuda")
     res = {}
     try:
+        ctx.set_option(_lib.OPT_EARLY_SPLIT, 0)  # (the whole dictionary in one prepare launch, both ways)
         for view in (1, 0):
             ctx.set_option(_lib.OPT_DICT_VIEW, view)
             best = 1e9
@@ -1006,6 +1007,7 @@ def test_view_mode_is_used_and_saves_the_float32_copy(ctx):
             res[view] = (best, idx.cpu().numpy().copy(), sc.cpu().numpy().copy())
     finally:
         ctx.set_option(_lib.OPT_DICT_VIEW, 1)
+        ctx.set_option(_lib.OPT_EARLY_SPLIT, 1)
     assert np.array_equal(res[1][1], res[0][1]) and np.array_equal(res[1][2], res[0][2])
     assert res[1][0] < res[0][0], (res[1][0], res[0][0])
 
@@ -1054,9 +1056,7 @@ def test_float64_mode_matches_the_float64_oracle(ctx, metric, masked, nav):
         res = kb.dictionary_indexing(e, d, metric=metric, keep_n=k, dtype=np.float64, signal_mask=smask,
                                      navigation_mask=nmask, n_per_iteration=1700 if source == "chunks" else None,
                                      context=ctx, verbose=False)
-        sc, idx = res.scores, res.simulation_indices
-        if nav:
-            sc, idx = sc[~nmask.ravel()], idx[~nmask.ravel()]
+        sc, idx = res.scores, res.simulation_indices  # (the indexed points only)
         assert sc.dtype == np.float64 and sc.shape == rsc.shape
         assert np.max(np.abs(sc - rsc)) < 1e-12, source
         # identical order wherever the reference's float64 scores are separated at all (1e-13)

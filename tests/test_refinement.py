@@ -243,9 +243,11 @@ def test_host_mirror_errors(capsys):
     det = kb.Detector((24, 32), pc=a["pc"])
     mp = (a["mu"], a["ml"])
     ctx = _RecordingContext()
-    for method, kwargs in [("differential_evolution", None), ("ln_neldermead", None), ("minimize", dict(method="Powell"))]:
-        with pytest.raises(NotImplementedError):
-            kb.refine_orientation(pats, quats, det, mp, method=method, method_kwargs=kwargs, context=ctx)
+    # _refinement.py:1082-1088 (unknown method), nlopt missing, a bounded global method without bounds
+    with pytest.raises(ValueError, match="Method 'simplex' not in the list of supported methods"):
+        kb.refine_orientation(pats, quats, det, mp, method="simplex", context=ctx)
+    with pytest.raises(ImportError, match="LN_NELDERMEAD"):
+        kb.refine_orientation(pats, quats, det, mp, method="ln_neldermead", context=ctx)
     with pytest.raises(ValueError, match="Detector shape"):
         kb.refine_orientation(pats, quats, kb.Detector((32, 24)), mp, context=ctx)
     with pytest.raises(ValueError, match="Signal mask shape"):
@@ -442,3 +444,200 @@ def test_oracle_nelder_mead_equals_scipy_random_problems(seed):
     x, fv, nfev, nit = ro.nelder_mead(f, x0, bounds=bounds, **opts)
     assert (nfev, nit) == (ref.nfev, ref.nit)
     assert np.array_equal(x, ref.x) and fv == ref.fun
+
+
+# ---- optimisers other than Nelder-Mead: SciPy's loop on the host, the objective on the device ------
+
+class _OracleObjectiveContext(_RecordingContext):
+    """The oracle's objective functions standing in for ``kdi_refine_objective``."""
+
+    def __init__(self, problem):
+        super().__init__()
+        self.problem = problem
+        self.batches = []
+
+    def device_rows(self, data, rows):
+        return np.asarray(data).reshape(rows, -1)
+
+    def refine_objective(self, mp, mode, patterns, nrows, ncols, rescale, pattern_rows, x, rotations, pcs, om):
+        p = self.problem
+        self.batches.append(len(pattern_rows))
+        out = np.empty(x.shape[:2])
+        for i, r in enumerate(pattern_rows):
+            exp, sq = ro.prepare_pattern(patterns[r][p.keep], rescale)
+            for k in range(x.shape[1]):
+                if mode == _lib.REFINE_ORI:
+                    dc = p.dc if pcs is None else p.dc_from_pc(*pcs[i])
+                    out[i, k] = p.objective_ori(x[i, k], exp, sq, dc)
+                elif mode == _lib.REFINE_PC:
+                    out[i, k] = p.objective_pc(x[i, k], exp, sq, rotations[i, k])
+                else:
+                    out[i, k] = p.objective_ori_pc(x[i, k], exp, sq)
+        return out
+
+
+def test_method_plan():
+    from kikuchipy_b200 import refinement as rfm
+
+    assert rfm._method_plan(None, None)[:4] == ("device", dict(xatol=1e-4, fatol=1e-4, maxiter=-1, maxfev=-1, adaptive=False), "Nelder-Mead", "local")
+    assert rfm._method_plan("minimize", dict(method="nelder-mead", tol=1e-3))[0] == "device"
+    where, plan, name, kind, shown = rfm._method_plan("MINIMIZE", dict(method="Powell", tol=1e-3))
+    assert (where, plan[0], name, kind) == ("host", "minimize", "Powell", "local") and plan[1] == dict(method="Powell", tol=1e-3)
+    # a Nelder-Mead option the device search does not implement: SciPy's loop, the objective on the device
+    assert rfm._method_plan("minimize", dict(method="Nelder-Mead", options=dict(initial_simplex=np.eye(4, 3))))[0] == "host"
+    where, plan, name, kind, _ = rfm._method_plan("basinhopping", None)
+    assert (where, name, kind) == ("host", "basinhopping", "global") and plan[1] == {"minimizer_kwargs": {}}
+    assert rfm._method_plan("differential_evolution", dict(popsize=3))[3] == "global"
+
+
+@pytest.mark.parametrize("method, kwargs, tr", [
+    ("minimize", dict(method="Powell", options=dict(xtol=1e-3, ftol=1e-4)), None),
+    ("minimize", dict(method="L-BFGS-B"), [2, 2, 2]),
+    ("differential_evolution", dict(popsize=4, maxiter=4, seed=3, polish=False), [1, 1, 1]),
+    ("differential_evolution", dict(popsize=4, maxiter=3, seed=3, polish=False, vectorized=True, updating="deferred"), [1, 1, 1]),
+    ("dual_annealing", dict(maxiter=8, seed=5, no_local_search=True), [1, 1, 1]),
+    ("basinhopping", dict(niter=2, seed=7, minimizer_kwargs=dict(method="Nelder-Mead", options=dict(maxfev=40))), None),
+    ("shgo", dict(n=16, iters=1, sampling_method="sobol"), [1, 1, 1]),
+])
+def test_host_driven_optimisers_equal_scipy_on_the_same_objective(method, kwargs, tr, capsys):
+    """The threads-and-batches machinery must not change what SciPy computes: with the oracle's objective
+    behind ``refine_objective`` every pattern gets exactly the result of calling the SciPy function
+    directly, the way ``_refine_orientation_solver_scipy`` does (``_solvers.py:186-254``)."""
+    import copy
+
+    import scipy.optimize
+
+    a = _case("A")
+    p = a["problem"]
+    ctx = _OracleObjectiveContext(p)
+    pats = a["patterns"].reshape(2, 4, 24, 32)
+    quats = rf.euler_to_quaternion(a["start_eulers"])
+    det = kb.Detector((24, 32), pc=a["pc"])
+    det.gnomonic_bounds  # (fixed PC: direction cosines from the detector's bounds)
+    mask = ~a["keep"].reshape(24, 32)
+    res = kb.refine_orientation(pats, quats, det, (a["mu"], a["ml"]), signal_mask=mask, method=method,
+                                method_kwargs=copy.deepcopy(kwargs), trust_region=tr, context=ctx, compute=False)
+    assert res.shape == (8, 5) and max(ctx.batches) > 1  # searches of several patterns share launches
+    text = capsys.readouterr().out
+    kind = "local" if method == "minimize" else "global"
+    assert f"({kind}) from SciPy" in text and ("Trust region" in text) == (method != "basinhopping")
+    x0 = rf.quaternion_to_euler(quats)
+    func = getattr(scipy.optimize, method)
+    for i in range(8):
+        exp, sq = ro.prepare_pattern(a["patterns"][i][a["keep"]], False)
+        f = lambda x: p.objective_ori(x, exp, sq, p.dc)  # noqa: E731
+        kw = copy.deepcopy(kwargs)
+        kw.pop("vectorized", None)
+        if kw.get("updating") == "deferred" and "vectorized" not in kwargs:
+            kw.pop("updating")
+        bounds = None
+        if tr is not None:
+            t = np.deg2rad(tr)
+            bounds = np.stack([np.fmax(x0[i] - t, -np.deg2rad(5)),
+                               np.fmin(x0[i] + t, [2 * np.pi + np.deg2rad(5), np.pi + np.deg2rad(5), 2 * np.pi + np.deg2rad(5)])], axis=1)
+        if method == "minimize":
+            want = func(fun=f, x0=x0[i], bounds=bounds, **kw) if bounds is not None else func(fun=f, x0=x0[i], **kw)
+        elif method == "basinhopping":
+            want = func(func=f, x0=x0[i], **kw)
+        else:
+            want = func(func=f, bounds=bounds, **kw)
+        assert res[i, 0] == 1 - want.fun and np.array_equal(res[i, 2:5], want.x), (i, res[i], want.x, want.fun)
+        if "vectorized" not in kwargs:
+            assert res[i, 1] == want.nfev
+
+
+def test_host_driven_other_modes_and_errors():
+    b = _case("B")
+    p = b["problem"]
+    ctx = _OracleObjectiveContext(p)
+    pats = b["patterns"].reshape(4, 20, 20)
+    det = kb.Detector((20, 20), pc=b["pcs"])
+    quats = GOLD["B_quats"]
+    kw = dict(method="Powell", options=dict(maxfev=30))
+    scores, det2, nev = kb.refine_projection_center(pats, quats, det, (b["mu"], b["ml"]), method_kwargs=kw, context=ctx, verbose=False)
+    assert scores.shape == (4,) and det2.pc.shape == (4, 3) and np.all(nev >= 30)
+    r, det3 = kb.refine_orientation_projection_center(pats, quats, det, (b["mu"], b["ml"]), method_kwargs=kw, context=ctx, verbose=False)
+    assert r.scores.shape == (4,) and det3.pc.shape == (4, 3) and np.all(r.scores > 0.5)
+    # pseudo-symmetry starts: the best of the searches wins (_solvers.py:236-254)
+    ops = rf.euler_to_quaternion(np.array([[0.3, 0.2, 0.1]]))
+    r = kb.refine_orientation(pats, quats, det, (b["mu"], b["ml"]), pseudo_symmetry_ops=ops, method_kwargs=kw, context=ctx, verbose=False)
+    assert set(np.unique(r.prop["pseudo_symmetry_index"])) <= {0, 1} and np.all(r.prop["pseudo_symmetry_index"] == 0)
+    with pytest.raises(ValueError, match="needs bounds"):
+        kb.refine_orientation(pats, quats, det, (b["mu"], b["ml"]), method="differential_evolution", context=ctx, verbose=False)
+    # an exception inside an objective launch reaches the caller (and no thread is left waiting)
+    ctx.refine_objective = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("device lost"))
+    with pytest.raises(RuntimeError, match="device lost"):
+        kb.refine_orientation(pats, quats, det, (b["mu"], b["ml"]), method_kwargs=kw, context=ctx, verbose=False)
+
+
+@pytest.mark.gpu
+def test_gpu_objective_matches_the_oracle():
+    """``kdi_refine_objective`` = the reference's three objective functions (float32 NCC of the centred
+    pattern and the projection), for every mode, with a signal mask, per-pattern PCs, float32 rescaling
+    and several points per row."""
+    ctx = kb.default_context()
+    rng = np.random.default_rng(0)
+    for name, mode, rescale in (("A", "ori", False), ("B", "ori_pcs", False), ("B", "pc", False), ("B", "ori_pc", False), ("C", "ori", True)):
+        c = _case(name)
+        p = c["problem"]
+        n = len(c["patterns"])
+        ctx.set_signal_mask(None if c["keep"].all() else ~c["keep"])
+        try:
+            fixed = mode == "ori"
+            dc = np.zeros((p.nrows * p.ncols, 3))
+            if fixed:
+                dc = ro.Problem(p.mu, p.ml, p.nrows, p.ncols, om_detector_to_sample=p.om).dc_from_pc(*c["pc"])
+            mp = ctx.master_pattern(p.mu, p.ml, dc)
+            rows = np.array([n - 1, 0, 1, 1])
+            eu = c["start_eulers"][rows][:, None, :] + 0.01 * rng.standard_normal((4, 3, 3))
+            pcs = c["pcs"][rows]
+            if mode in ("ori", "ori_pcs"):
+                x, kmode, rot, pc = eu, _lib.REFINE_ORI, None, (None if fixed else pcs)
+            elif mode == "pc":
+                x = pcs[:, None, :] + 0.005 * rng.standard_normal((4, 3, 3))
+                kmode, rot, pc = _lib.REFINE_PC, np.repeat(GOLD["B_quats"][rows][:, None, :], 3, axis=1), None
+            else:
+                x = np.concatenate([eu, pcs[:, None, :] + 0.005 * rng.standard_normal((4, 3, 3))], axis=2)
+                kmode, rot, pc = _lib.REFINE_ORI_PC, None, None
+            got = ctx.refine_objective(mp, kmode, c["patterns"], p.nrows, p.ncols, rescale, rows, x, rot, pc, p.om)
+        finally:
+            ctx.set_signal_mask(None)
+        want = np.empty((4, 3))
+        for i, r in enumerate(rows):
+            exp, sq = ro.prepare_pattern(c["patterns"][r][c["keep"]], rescale)
+            for k in range(3):
+                if kmode == _lib.REFINE_ORI:
+                    want[i, k] = p.objective_ori(x[i, k], exp, sq, p.dc if fixed else p.dc_from_pc(*pcs[i]))
+                elif kmode == _lib.REFINE_PC:
+                    want[i, k] = p.objective_pc(x[i, k], exp, sq, rot[i, k])
+                else:
+                    want[i, k] = p.objective_ori_pc(x[i, k], exp, sq)
+        assert np.max(np.abs(got - want)) < 2e-6, (name, mode, np.max(np.abs(got - want)))
+
+
+@pytest.mark.gpu
+def test_gpu_host_driven_optimisers_refine_like_nelder_mead():
+    """Powell and differential evolution through the public API: SciPy's loop on the host, objective
+    values from the device; they must find the optimum the device's Nelder-Mead finds."""
+    c = ro.synthetic_case(n=24, seed=7, nrows=30, ncols=30, mp_size=301, noise=0.02, perturb_deg=1.5)
+    det = kb.Detector((30, 30), pc=c["pc"], sample_tilt=70.0)
+
+    class Det:
+        shape = (30, 30)
+        pc = c["pc"][None]
+        om_detector_to_sample = c["om"]
+        gnomonic_bounds = det.gnomonic_bounds
+
+    pats = c["patterns"].reshape(4, 6, 30, 30)
+    start = rf.euler_to_quaternion(c["start_eulers"])
+    nm = kb.refine_orientation(pats, start, Det, (c["mu"], c["ml"]), verbose=False)
+    pw = kb.refine_orientation(pats, start, Det, (c["mu"], c["ml"]), method_kwargs=dict(method="Powell"), verbose=False)
+    de = kb.refine_orientation(pats, start, Det, (c["mu"], c["ml"]), method="differential_evolution",
+                               method_kwargs=dict(popsize=6, maxiter=12, seed=1, vectorized=True, updating="deferred"),
+                               trust_region=[2, 2, 2], verbose=False)
+    assert np.all(np.abs(pw.scores - nm.scores) < 2e-3) and np.all(pw.num_evals > 20)
+    assert np.all(np.abs(de.scores - nm.scores) < 5e-3)
+    truth = rf.euler_to_quaternion(c["true_eulers"])
+    for r in (pw, de):
+        mis = 2 * np.arccos(np.clip(np.abs(np.sum(r.rotations * truth, axis=1)), 0, 1))
+        assert np.median(mis) < np.deg2rad(0.5)
