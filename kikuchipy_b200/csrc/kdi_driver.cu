@@ -529,7 +529,12 @@ static int append_rows(kdi_ctx* ctx, kdi_stream_state* ss, kdi_patterns* dict, k
     if (ss->rows_done >= ss->next_advance || ss->rows_done == dict->rows) {
       if (ss->rows_done == dict->rows) KDI_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
       KDI_TRY(kdi_match_advance(ctx, job, exp, dict, ss->rows_done));
-      ss->next_advance = ss->rows_done + ss->group_rows;
+      // The tensor-core pass over the rows that arrive last cannot hide behind a transfer: towards the
+      // end of the dictionary the launches cover half of what is left each (down to one strip), so that
+      // only a strip or two remain to be matched when the last row has landed.
+      const int64_t left = dict->rows - ss->rows_done;
+      const int64_t strip_rows = job->fused ? (int64_t)job->plan.strip_tiles * KDI_TILE_N : ss->group_rows;
+      ss->next_advance = ss->rows_done + std::max<int64_t>(strip_rows, std::min<int64_t>(ss->group_rows, left / 2));
     }
     return KDI_OK;
   };

@@ -75,6 +75,18 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
   }
 }
 
+// (operands already multiplied by KDI_OP_SCALE)
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack16_scaled(float a, float b) {
+  if constexpr (BF16) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
+
 __device__ __forceinline__ uint32_t block_min_u32(uint32_t v, uint32_t* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -569,15 +581,23 @@ kdi_normalize_warp_rows(const T* __restrict__ src, int64_t S, int metric, float*
     } else {
       const float y = (float)(1.0 / (double)norm);
       if (rstat != nullptr && lane == 0) rstat[row] = make_float4(mean, norm, y, 0.f);
+      // (packed float32 x 2 instructions: two quotients, two scalings per issue slot)
+      const uint64_t nn = kdi::f2_pack(-norm, -norm), yy = kdi::f2_pack(y, y);
+      const uint64_t sc = kdi::f2_pack(KDI_OP_SCALE, KDI_OP_SCALE);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         if (i < NV - 1 || last) {
           const int j = lane + 32 * i;
+          const uint64_t q01 = kdi_div_fma2(kdi::f2_pack(r[i].x, r[i].y), nn, yy);
+          const uint64_t q23 = kdi_div_fma2(kdi::f2_pack(r[i].z, r[i].w), nn, yy);
           float4 v;
-          v.x = kdi_div_fma(r[i].x, norm, y); v.y = kdi_div_fma(r[i].y, norm, y);
-          v.z = kdi_div_fma(r[i].z, norm, y); v.w = kdi_div_fma(r[i].w, norm, y);
+          kdi::f2_unpack(q01, v.x, v.y);
+          kdi::f2_unpack(q23, v.z, v.w);
           if (o32) o32[j] = v;
-          o16[j] = make_uint2(pack16<BF16>(v.x, v.y), pack16<BF16>(v.z, v.w));
+          float s0, s1, s2, s3;
+          kdi::f2_unpack(kdi::f2_mul(q01, sc), s0, s1);
+          kdi::f2_unpack(kdi::f2_mul(q23, sc), s2, s3);
+          o16[j] = make_uint2(pack16_scaled<BF16>(s0, s1), pack16_scaled<BF16>(s2, s3));
         }
       }
     }

@@ -86,11 +86,45 @@ __device__ __forceinline__ float warp_dot_view_impl(const float4* __restrict__ a
   for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
   return (float)d;
 }
+// the FMA route with packed float32 x 2 instructions: (acc.x, acc.y) and (acc.z, acc.w) are the two
+// packed accumulators, every lane-wise operation is the scalar one (same rounding, same order)
+__device__ __forceinline__ float warp_dot_view_fast(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                    float mean, float n, float y, int n4, int lane) {
+  const uint64_t nm = f2_pack(-mean, -mean), nn = f2_pack(-n, -n), yy = f2_pack(y, y);
+  uint64_t acc01 = f2_pack(0.f, 0.f), acc23 = acc01;
+  auto step = [&](const float4 x, const float4 v) {
+    const uint64_t q01 = kdi_div_fma2(f2_add(f2_pack(v.x, v.y), nm), nn, yy);
+    const uint64_t q23 = kdi_div_fma2(f2_add(f2_pack(v.z, v.w), nm), nn, yy);
+    acc01 = f2_fma(f2_pack(x.x, x.y), q01, acc01);
+    acc23 = f2_fma(f2_pack(x.z, x.w), q23, acc23);
+  };
+  int j = lane;
+  bool more = j + 96 < n4;
+  float4 n0, n1, n2, n3;
+  if (more) { n0 = __ldg(b + j); n1 = __ldg(b + j + 32); n2 = __ldg(b + j + 64); n3 = __ldg(b + j + 96); }
+  while (more) {
+    const float4 y0 = n0, y1 = n1, y2 = n2, y3 = n3;
+    const int jc = j;
+    j += 128;
+    more = j + 96 < n4;
+    if (more) { n0 = __ldg(b + j); n1 = __ldg(b + j + 32); n2 = __ldg(b + j + 64); n3 = __ldg(b + j + 96); }
+    const float4 x0 = __ldg(a + jc), x1 = __ldg(a + jc + 32), x2 = __ldg(a + jc + 64), x3 = __ldg(a + jc + 96);
+    step(x0, y0); step(x1, y1); step(x2, y2); step(x3, y3);
+  }
+  for (; j < n4; j += 32) step(__ldg(a + j), __ldg(b + j));
+  float ax, ay, az, aw;
+  f2_unpack(acc01, ax, ay);
+  f2_unpack(acc23, az, aw);
+  double d = ((double)ax + (double)ay) + ((double)az + (double)aw);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  return (float)d;
+}
 // st = rstat[row] = (mean, norm, float(1 / norm), route)
 __device__ __forceinline__ float warp_dot_view(const float4* __restrict__ a, const float4* __restrict__ b,
                                                const float4 st, int n4, int lane) {
   const float n = st.y, y = st.z;
-  if (st.w == 0.f) return warp_dot_view_impl(a, b, st.x, n4, lane, [=](float c) { return kdi_div_fma(c, n, y); });
+  if (st.w == 0.f) return warp_dot_view_fast(a, b, st.x, n, y, n4, lane);
   const double rd = 1.0 / (double)n;
   return warp_dot_view_impl(a, b, st.x, n4, lane, [=](float c) { return kdi_div_by_norm(c, rd); });
 }
