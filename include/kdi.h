@@ -123,8 +123,11 @@ extern "C" {
                                    entry point (kdi_dictionary_indexing, kdi_shard_*) is not copied as normalised
                                    float32 rows: the exact scores read the caller's rows and apply the row's
                                    (mean, norm) on the fly with the prepare kernel's arithmetic - bit-identical
-                                   scores, 40 % fewer bytes in the prepare step.  The caller's buffer must stay
-                                   alive until the call returns (shards: until kdi_shard_release).  0 = always copy */
+                                   scores, 40 % fewer bytes in the prepare step - wherever that outweighs the ~15 %
+                                   it adds to the exact rescoring (single-GPU jobs whose dictionary has at least
+                                   (keep_n + 5) / 6 rows per experimental row).  2 = wherever possible, sharded jobs
+                                   included (validation); 0 = always copy.  The caller's buffer must stay alive until
+                                   the call returns (shards: until kdi_shard_release) */
 
 typedef struct kdi_ctx kdi_ctx;
 typedef struct kdi_patterns kdi_patterns;

@@ -477,7 +477,8 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
       ctx->div_double = value != 0;
       return KDI_OK;
     case KDI_OPT_DICT_VIEW:
-      ctx->dict_view = value != 0;
+      if (value != 0 && value != 1 && value != 2) return kdi_fail(ctx, KDI_EINVAL, "dict_view must be 0, 1 or 2");
+      ctx->dict_view = (int)value;
       return KDI_OK;
     case KDI_OPT_POST_CORESIDENT:
       if (value < 0 || value > 8) return kdi_fail(ctx, KDI_EINVAL, "post_coresident must be 0..8");

@@ -634,9 +634,15 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   // rows - the exact scores read the caller's rows (alive for the whole call) and apply the row's
   // statistics on the fly.  Only the tensor-core pipeline asks for single rows; everything that scores
   // whole blocks (forced exact path, keep_n beyond the candidate lists) keeps the stored rows.
-  const bool view = ctx->dict_view && !dsrc.mp && dict_loc == KDI_DEVICE && dict_dtype == KDI_F32 && !ctx->mask_S &&
-                    kdi_normalize_is_light(S, S, false, false) && (reinterpret_cast<uintptr_t>(dictionary) % 16) == 0 &&
-                    !ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0 && exp_rows > 0;
+  // It pays when the float32 copy it saves (dict_rows rows written) outweighs the ~15 % the on-the-fly
+  // normalisation adds to the exact rescoring (exp_rows x (keep_n + 5) rows read): C2 yes (100 000 vs 250 000
+  // x 0.15), the shards of a multi-GPU job no (12 500-37 500 rows against 250 000-690 000 row reads per rank:
+  // measured +3.5 ms on the exchange of BASELINE configs[3] at 8 GPUs).  KDI_OPT_DICT_VIEW = 2 forces it.
+  const bool view_eligible = ctx->dict_view && !dsrc.mp && dict_loc == KDI_DEVICE && dict_dtype == KDI_F32 && !ctx->mask_S &&
+                             kdi_normalize_is_light(S, S, false, false) && (reinterpret_cast<uintptr_t>(dictionary) % 16) == 0 &&
+                             !ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0 && exp_rows > 0;
+  const bool view_pays = !candidates_only && dict_rows * 6 >= exp_rows * (int64_t)(keep_n + 5);
+  const bool view = view_eligible && (ctx->dict_view == 2 || view_pays);
   int rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict, view ? static_cast<const float*>(dictionary) : nullptr);
   if (rc != KDI_OK) {
     const std::string err = ctx->err;

@@ -65,6 +65,10 @@ struct RefineParams {
   int adaptive;
   double* out;          // n_patterns x out_stride
   int out_stride;
+  // patterns too large for shared memory (more than 25 600 matched pixels): per-CTA staging in global
+  // memory instead (2 * pitch floats per CTA, L2-resident; the kernel is bound by the float64 geometry,
+  // not by these reads).  null = shared memory
+  float* gws;
 };
 
 __device__ __forceinline__ double block_sum(double v, double (*red)[kRefWarps]) {
@@ -235,7 +239,7 @@ template <int MODE, int NV>
 __global__ void __launch_bounds__(kRefThreads) kdi_refine_objective_kernel(const RefineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int64_t pitch = (p.s_eff + 3) & ~(int64_t)3;
-  float* e = reinterpret_cast<float*>(smem_raw);
+  float* e = p.gws ? p.gws + (int64_t)blockIdx.x * 2 * pitch : reinterpret_cast<float*>(smem_raw);
   float* v = e + pitch;
   __shared__ double red[2][kRefWarps];
   for (int64_t row = blockIdx.x; row < p.n_patterns; row += gridDim.x) {
@@ -255,7 +259,7 @@ template <int MODE, int NV, int MINB>
 __global__ void __launch_bounds__(kRefThreads, MINB) kdi_refine_kernel(const RefineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int64_t pitch = (p.s_eff + 3) & ~(int64_t)3;
-  float* e = reinterpret_cast<float*>(smem_raw);
+  float* e = p.gws ? p.gws + (int64_t)blockIdx.x * 2 * pitch : reinterpret_cast<float*>(smem_raw);
   float* v = e + pitch;
   __shared__ double red[2][kRefWarps];
 
@@ -444,9 +448,13 @@ static int refine_impl(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, con
     return kdi_fail(ctx, KDI_EINVAL, "signal mask has %lld pixels, the detector %lld", (long long)ctx->mask_S, (long long)S);
   const int nv = mode == KDI_REFINE_ORI_PC ? 6 : 3;
   const int64_t s_eff = ctx->mask_S ? ctx->mask_kept : S;
-  const size_t smem = 2 * (size_t)((s_eff + 3) & ~(int64_t)3) * sizeof(float);
-  if (s_eff < 1 || smem > 200 * 1024)
-    return kdi_fail(ctx, KDI_EUNSUPPORTED, "kdi_refine: %lld kept pixels do not fit the kernel's shared-memory staging", (long long)s_eff);
+  size_t smem = 2 * (size_t)((s_eff + 3) & ~(int64_t)3) * sizeof(float);
+  if (s_eff < 1) return kdi_fail(ctx, KDI_EINVAL, "kdi_refine: the signal mask excludes every pixel");
+  // large patterns (e.g. 240 x 240, 480 x 480): a bounded resident grid with its staging in global memory
+  const bool global_staging = smem > 200 * 1024;
+  const int64_t max_ctas = (int64_t)ctx->sm_count * 4;
+  const size_t gws_bytes = global_staging ? (size_t)std::min<int64_t>(n_patterns, max_ctas) * smem : 0;
+  if (global_staging) smem = 0;
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
 
@@ -464,6 +472,7 @@ static int refine_impl(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, con
   const size_t o_q = rotations ? take((size_t)n_patterns * n_starts * 32) : 0;
   const size_t o_pc = pcs ? take((size_t)n_patterns * 24) : 0;
   const size_t o_out = take((size_t)n_patterns * out_stride * 8);
+  const size_t o_gws = global_staging ? take(gws_bytes) : 0;
   KDI_TRY(kdi_ws2_reserve(ctx, o));
   uint8_t* w = reinterpret_cast<uint8_t*>(ctx->ws2);
   ctx->tm = kdi_timings();
@@ -524,8 +533,9 @@ static int refine_impl(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, con
   p.adaptive = opt->adaptive != 0;
   p.out = reinterpret_cast<double*>(w + o_out);
   p.out_stride = out_stride;
+  p.gws = global_staging ? reinterpret_cast<float*>(w + o_gws) : nullptr;
 
-  const unsigned grid = (unsigned)std::min<int64_t>(n_patterns, 0x7fffffff);
+  const unsigned grid = (unsigned)std::min<int64_t>(n_patterns, global_staging ? max_ctas : 0x7fffffff);
   auto launch = [&](auto kernel) -> int {
     KDI_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     KDI_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));

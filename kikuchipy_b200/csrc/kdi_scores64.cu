@@ -9,6 +9,8 @@
 // throughput mode, and the kernel is written for clarity: one CTA per experimental row, the normalised
 // float64 row in shared memory, one warp per candidate with three passes over the dictionary row
 // (mean, centred sum of squares, dot product) - the second and third pass hit L1 / L2.
+#include <algorithm>
+
 #include "kdi_internal.cuh"
 
 namespace {
@@ -45,10 +47,12 @@ __global__ void __launch_bounds__(kS64Threads)
 kdi_scores_f64_kernel(const void* __restrict__ exp, int exp_dtype, const int64_t* __restrict__ exp_rows,
                       const void* __restrict__ dict, int dict_dtype, int64_t S, const int32_t* __restrict__ cols,
                       int s_eff, int metric, const int64_t* __restrict__ cand, int k, int64_t n_dict,
-                      double* __restrict__ out) {
-  extern __shared__ double e[];  // s_eff
+                      double* __restrict__ out, double* __restrict__ gws, int64_t n_rows) {
+  extern __shared__ double smem_e[];  // s_eff doubles, unless the row is staged in global memory (gws)
   __shared__ double red[kS64Threads / 32];
-  const int64_t r = blockIdx.x;
+  double* e = gws ? gws + (int64_t)blockIdx.x * s_eff : smem_e;
+  for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+  __syncthreads();
   const int64_t src_row = exp_rows ? exp_rows[r] : r;
   for (int j = threadIdx.x; j < s_eff; j += kS64Threads) e[j] = load_f64(exp, exp_dtype, src_row * S + (cols ? cols[j] : j));
   __syncthreads();
@@ -92,6 +96,7 @@ kdi_scores_f64_kernel(const void* __restrict__ exp, int exp_dtype, const int64_t
     }
     if (lane == 0) out[r * k + i] = score;
   }
+  }
 }
 
 }  // namespace
@@ -110,13 +115,20 @@ extern "C" int kdi_scores_f64(kdi_ctx* ctx, const void* experimental, int exp_dt
   if (n_pairs_rows == 0) return KDI_OK;
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t s_eff = ctx->mask_S ? ctx->mask_kept : S;
-  const size_t smem = (size_t)s_eff * sizeof(double);
-  if (smem > 200 * 1024)
-    return kdi_fail(ctx, KDI_EUNSUPPORTED, "kdi_scores_f64: patterns of %lld pixels do not fit the kernel's shared-memory staging", (long long)s_eff);
+  size_t smem = (size_t)s_eff * sizeof(double);
+  // rows of more than 25 600 values are staged in global memory (a bounded resident grid)
+  double* gws = nullptr;
+  int64_t grid = n_pairs_rows;
+  if (smem > 200 * 1024) {
+    grid = std::min<int64_t>(n_pairs_rows, (int64_t)ctx->sm_count * 8);
+    KDI_TRY(kdi_ws2_reserve(ctx, (size_t)grid * smem));
+    gws = reinterpret_cast<double*>(ctx->ws2);
+    smem = 0;
+  }
   KDI_CUDA(ctx, cudaFuncSetAttribute(kdi_scores_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  kdi_scores_f64_kernel<<<(unsigned)n_pairs_rows, kS64Threads, smem, ctx->stream>>>(
+  kdi_scores_f64_kernel<<<(unsigned)grid, kS64Threads, smem, ctx->stream>>>(
       experimental, exp_dtype, exp_rows, dictionary, dict_dtype, S, ctx->mask_S ? ctx->d_cols : nullptr, (int)s_eff,
-      metric, candidates, k, dict_rows, out);
+      metric, candidates, k, dict_rows, out, gws, n_pairs_rows);
   KDI_CUDA(ctx, cudaGetLastError());
   KDI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->tm.kernel_launches++;

@@ -602,9 +602,9 @@ def refine_orientation(signal, xmap, detector, master_pattern, energy=None, navi
     ``compute=False`` the raw ``(n, 5 | 6)`` array of the reference (score, evaluations, Euler
     angles[, pseudo-symmetry index]) - already computed, the GPU call is not lazy.
 
-    Limit (all three ``refine_*`` functions): the kernel keeps the pattern and its simulation in
-    shared memory, so at most 25 600 matched pixels (e.g. 160x160 unmasked); larger patterns raise
-    ``NotImplementedError`` (``KDI_EUNSUPPORTED``) - bin them or use a signal mask."""
+    Patterns of up to 25 600 matched pixels (e.g. 160x160 unmasked) are staged in shared memory for the
+    whole search; larger ones (240x240, 480x480) in global memory, L2-resident - the search is bound by the
+    float64 projection geometry either way."""
     where, opts, name, kind, kw_shown = _method_plan(method, method_kwargs)
     setup = _Setup(signal, xmap, detector, master_pattern, energy, navigation_mask, signal_mask, context, sharded, group)
     x0, n_ps = _starts(setup, pseudo_symmetry_ops)

@@ -958,12 +958,12 @@ def test_view_mode_dictionary_is_bit_identical(ctx, metric, compute):
     out = {}
     try:
         ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 1 if compute == "bf16" else 0)
-        for view in (1, 0):
+        for view in (2, 0):  # (2: wherever possible - the default only where it pays)
             ctx.set_option(_lib.OPT_DICT_VIEW, view)
             idx = torch.empty((M, k), dtype=torch.int64, device="cuda")
             sc = torch.empty((M, k), dtype=torch.float32, device="cuda")
             ctx.dictionary_indexing(d_exp, M, d_dic, N, code, k, out=(idx, sc))
-            out[view] = (idx.cpu().numpy(), sc.cpu().numpy().view(np.uint32), ctx.timings()["flagged_rows"])
+            out[min(view, 1)] = (idx.cpu().numpy(), sc.cpu().numpy().view(np.uint32), ctx.timings()["flagged_rows"])
     finally:
         ctx.set_option(_lib.OPT_DICT_VIEW, 1)
         ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 0)
@@ -1078,3 +1078,20 @@ def test_float64_metric_call_and_plugin_hooks(golden):
         idx, sc = sim.argtopk(5, axis=-1), sim.topk(5, axis=-1)
         want = np.argsort(-g[f"{name}_sim_f64"], axis=1, kind="stable")[:, :5]
         assert np.array_equal(idx, want) and np.allclose(sc, np.take_along_axis(g[f"{name}_sim_f64"], want, 1), atol=1e-13, rtol=0)
+
+
+def test_float64_scores_of_rows_beyond_the_shared_memory_staging(ctx):
+    """``kdi_scores_f64`` stages rows of more than 25 600 values in global memory."""
+    import torch
+
+    rng = np.random.default_rng(8)
+    exp = rng.integers(0, 256, (5, 170, 170), dtype=np.uint8)
+    dic = rng.random((40, 170, 170), dtype=np.float32)
+    cand = np.stack([rng.permutation(40)[:6] for _ in range(5)]).astype(np.int64)
+    ctx.set_signal_mask(None)
+    got = ctx.scores_f64(torch.from_numpy(exp.reshape(5, -1)).cuda(), None, torch.from_numpy(dic.reshape(40, -1)).cuda(),
+                         _lib.KDI_NCC, cand)
+    e = orc.prepare_experimental(exp, "ncc", 5, dtype=np.float64)
+    d = orc.prepare_dictionary(dic.reshape(40, -1), "ncc", None, np.float64)
+    want = np.take_along_axis(e @ d.T, cand, axis=1)
+    assert np.max(np.abs(got - want)) < 1e-13

@@ -62,6 +62,18 @@ def _worker(rank, world, port, tmp):
                 assert torch.equal(big[ex][0], i5) and torch.equal(big[ex][1], s5)
             big[ex] = (i5, s5)
         i6, s6 = ctx.dictionary_indexing(expB, 2100, dicB, 30001, _lib.KDI_NCC, 50)
+        # device-resident shards held as VIEWS of the caller's rows (forced: a shard is too small for the
+        # view to pay, so the default copies): the exchange kernels rescore from the raw rows, same bits
+        d_exp, d_dic = torch.from_numpy(expB).cuda(), torch.from_numpy(np.ascontiguousarray(dicB[sB:eB])).cuda()
+        try:
+            for mode in (2, 1):
+                ctx.set_option(_lib.OPT_DICT_VIEW, mode)
+                for ex in ("peer", "nccl"):
+                    i7, s7 = kb.dictionary_indexing_sharded(d_exp, d_dic, 30001, metric="ncc", keep_n=50, context=ctx,
+                                                            exchange=ex)
+                    assert torch.equal(big["peer"][0], i7) and torch.equal(big["peer"][1], s7), (mode, ex)
+        finally:
+            ctx.set_option(_lib.OPT_DICT_VIEW, 1)
         np.savez(os.path.join(tmp, f"big{rank}.npz"), ip=big["peer"][0].cpu().numpy(), sp=big["peer"][1].cpu().numpy(),
                  inn=big["nccl"][0].cpu().numpy(), sn=big["nccl"][1].cpu().numpy(), i1=i6, s1=s6)
         np.savez(os.path.join(tmp, f"r{rank}.npz"), idx=idx.cpu().numpy(), sc=sc.cpu().numpy(),

@@ -645,3 +645,24 @@ def test_gpu_host_driven_optimisers_refine_like_nelder_mead():
     for r in (pw, de):
         mis = 2 * np.arccos(np.clip(np.abs(np.sum(r.rotations * truth, axis=1)), 0, 1))
         assert np.median(mis) < np.deg2rad(0.5)
+
+
+@pytest.mark.gpu
+def test_gpu_refinement_of_patterns_beyond_the_shared_memory_staging():
+    """170 x 170 patterns (28 900 matched pixels > 25 600) used to raise; they are now staged in
+    global memory by a bounded resident grid - same search, same results as the oracle."""
+    c = ro.synthetic_case(n=3, seed=11, nrows=170, ncols=170, mp_size=401, noise=0.02, perturb_deg=1.0)
+    x0 = c["start_eulers"][:, None, :]
+    got = _gpu_run("ori", c, x0=x0, maxfev=40)
+    want = _oracle_run("ori", c, x0=x0, maxfev=40)
+    assert np.array_equal(got[:, 1], want[:, 1]) and np.max(np.abs(got[:, 0] - want[:, 0])) < 2e-5
+    assert np.max(np.abs(got[:, 2:] - want[:, 2:])) < 1e-6
+    # the objective alone, and more patterns than resident CTAs is not needed for coverage here
+    ctx = kb.default_context()
+    p = c["problem"]
+    dc = ro.Problem(p.mu, p.ml, p.nrows, p.ncols, om_detector_to_sample=p.om).dc_from_pc(*c["pc"])
+    mp = ctx.master_pattern(p.mu, p.ml, dc)
+    f = ctx.refine_objective(mp, _lib.REFINE_ORI, c["patterns"], 170, 170, False, np.arange(3), x0, None, None, p.om)
+    for i in range(3):
+        exp, sq = ro.prepare_pattern(c["patterns"][i], False)
+        assert abs(f[i, 0] - p.objective_ori(x0[i, 0], exp, sq, p.dc)) < 2e-6
