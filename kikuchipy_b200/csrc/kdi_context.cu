@@ -92,6 +92,95 @@ int kdi_ring_reserve(kdi_ctx* ctx, size_t bytes) {
   return KDI_OK;
 }
 
+// ---- copies between a caller's buffer (device, pinned host or pageable host) and device memory -------
+void kdi_parallel_copy(void* dst, const void* src, size_t bytes, int n_threads) {
+  if (n_threads <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t part = (bytes / n_threads + 4095) & ~(size_t)4095;
+  for (int t = 0; t < n_threads; ++t) {
+    const size_t a = (size_t)t * part;
+    if (a >= bytes) break;
+    const size_t n = std::min(part, bytes - a);
+    th.emplace_back([=] { memcpy(static_cast<uint8_t*>(dst) + a, static_cast<const uint8_t*>(src) + a, n); });
+  }
+  for (auto& t : th) t.join();
+}
+
+int kdi_pointer_kind(const void* p) {  // 0 pageable host, 1 pinned / registered host, 2 device (or managed)
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return 2;
+  return attr.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
+// Pageable memory goes through the context's pinned ring: a few host threads fill one block while the DMA
+// engine empties another (a cudaMemcpyAsync from pageable memory is staged by the driver, serially, at a
+// fraction of the PCIe rate).
+int kdi_copy_in(kdi_ctx* ctx, cudaStream_t st, void* d_dst, const void* src, size_t bytes) {
+  if (bytes == 0) return KDI_OK;
+  const int kind = kdi_pointer_kind(src);
+  if (kind != 0) {
+    KDI_CUDA(ctx, cudaMemcpyAsync(d_dst, src, bytes, kind == 2 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (kind == 1) ctx->tm.h2d_bytes += (int64_t)bytes;
+    return KDI_OK;
+  }
+  const size_t blk = 32u << 20;
+  if (bytes <= (1u << 20)) {  // small: the driver's own staging is fine
+    KDI_CUDA(ctx, cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, st));
+    ctx->tm.h2d_bytes += (int64_t)bytes;
+    return KDI_OK;
+  }
+  KDI_TRY(kdi_ring_reserve(ctx, blk));
+  const size_t step = ctx->ring_bytes;
+  int it = 0;
+  for (size_t off = 0; off < bytes; off += step, ++it) {
+    const int slot = it % KDI_RING_SLOTS;
+    const size_t n = std::min(step, bytes - off);
+    if (it >= KDI_RING_SLOTS || ctx->ring_used[slot]) KDI_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));
+    kdi_parallel_copy(ctx->ring[slot], static_cast<const uint8_t*>(src) + off, n, ctx->copy_threads);
+    KDI_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, ctx->ring[slot], n, cudaMemcpyHostToDevice, st));
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ring_ev[slot], st));
+    ctx->ring_used[slot] = 1;
+  }
+  ctx->tm.h2d_bytes += (int64_t)bytes;
+  return KDI_OK;
+}
+
+// (pageable destinations: returns when the data has arrived; others: queued on `st`)
+int kdi_copy_out(kdi_ctx* ctx, cudaStream_t st, void* dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return KDI_OK;
+  const int kind = kdi_pointer_kind(dst);
+  if (kind != 0 || bytes <= (1u << 20)) {
+    KDI_CUDA(ctx, cudaMemcpyAsync(dst, d_src, bytes, kind == 2 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (kind != 2) ctx->tm.d2h_bytes += (int64_t)bytes;
+    return KDI_OK;
+  }
+  KDI_TRY(kdi_ring_reserve(ctx, 32u << 20));
+  const size_t step = ctx->ring_bytes;
+  const int64_t n_chunks = (int64_t)((bytes + step - 1) / step);
+  auto drain = [&](int64_t c) -> int {  // chunk c has landed in its block: hand it to the caller's buffer
+    const int slot = (int)(c % KDI_RING_SLOTS);
+    KDI_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));
+    const size_t off = (size_t)c * step, n = std::min(step, bytes - off);
+    kdi_parallel_copy(static_cast<uint8_t*>(dst) + off, ctx->ring[slot], n, ctx->copy_threads);
+    return KDI_OK;
+  };
+  // (blocks may still be in flight as upload staging: wait for them first)
+  for (int sidx = 0; sidx < KDI_RING_SLOTS; ++sidx)
+    if (ctx->ring_used[sidx]) KDI_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[sidx]));
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    if (c >= KDI_RING_SLOTS) KDI_TRY(drain(c - KDI_RING_SLOTS));
+    const int slot = (int)(c % KDI_RING_SLOTS);
+    const size_t off = (size_t)c * step, n = std::min(step, bytes - off);
+    KDI_CUDA(ctx, cudaMemcpyAsync(ctx->ring[slot], static_cast<const uint8_t*>(d_src) + off, n, cudaMemcpyDeviceToHost, st));
+    KDI_CUDA(ctx, cudaEventRecord(ctx->ring_ev[slot], st));
+    ctx->ring_used[slot] = 1;
+  }
+  for (int64_t c = std::max<int64_t>(0, n_chunks - KDI_RING_SLOTS); c < n_chunks; ++c) KDI_TRY(drain(c));
+  ctx->tm.d2h_bytes += (int64_t)bytes;
+  return KDI_OK;
+}
+
 // ---- pooled device allocations for pattern sets -------------------------------------------
 int kdi_dev_alloc(kdi_ctx* ctx, size_t bytes, void** out, size_t* got) {
   int best = -1;

@@ -504,19 +504,6 @@ struct kdi_stream_state {
   int ring_it = 0;  // pinned-ring blocks used so far
 };
 
-static void parallel_copy(void* dst, const void* src, size_t bytes, int n_threads) {
-  if (n_threads <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
-  std::vector<std::thread> th;
-  const size_t part = (bytes / n_threads + 4095) & ~(size_t)4095;
-  for (int t = 0; t < n_threads; ++t) {
-    const size_t a = (size_t)t * part;
-    if (a >= bytes) break;
-    const size_t n = std::min(part, bytes - a);
-    th.emplace_back([=] { memcpy(static_cast<uint8_t*>(dst) + a, static_cast<const uint8_t*>(src) + a, n); });
-  }
-  for (auto& t : th) t.join();
-}
-
 static int append_rows(kdi_ctx* ctx, kdi_stream_state* ss, kdi_patterns* dict, kdi_match_job* job,
                        const kdi_patterns* exp, const void* rows_src, int loc, int dtype, int64_t n_rows) {
   cudaStream_t st = ctx->stream;
@@ -571,7 +558,7 @@ static int append_rows(kdi_ctx* ctx, kdi_stream_state* ss, kdi_patterns* dict, k
       const int rs = ss->ring_it % KDI_RING_SLOTS;
       // the DMA that last read this pinned block must have finished before the host overwrites it
       if (ss->ring_it >= KDI_RING_SLOTS || ctx->ring_used[rs]) KDI_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[rs]));
-      parallel_copy(ctx->ring[rs], from, bytes, ctx->copy_threads);
+      kdi_parallel_copy(ctx->ring[rs], from, bytes, ctx->copy_threads);
       from = static_cast<const uint8_t*>(ctx->ring[rs]);
     }
     // the device slot is free once the normalise that read it two pieces ago has finished

@@ -302,13 +302,16 @@ extern "C" int kdi_merge_crystal_maps(kdi_ctx* ctx, int n_maps, int64_t map_size
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at = o; o = up256(o + bytes); return at; };
   size_t o_sc[kMaxMaps], o_rot[kMaxMaps], o_idx[kMaxMaps], o_rows[kMaxMaps], o_ni[kMaxMaps];
+  // (arrays that already live on the device - the results of an indexing run that never left it - are
+  // used where they are; host arrays are uploaded, pageable ones through the pinned ring)
+  auto on_device = [](const void* p) { return p != nullptr && kdi_pointer_kind(p) == 2; };
   for (int k = 0; k < n_maps; ++k) {
     const size_t n = (size_t)n_points[k] * n_scores;
-    o_sc[k] = take(n * es);
-    o_rot[k] = take(n * 32);
-    o_idx[k] = with_idx ? take(n * 8) : 0;
-    o_rows[k] = (point_rows && point_rows[k]) ? take((size_t)map_size * 4) : 0;
-    o_ni[k] = (not_indexed && not_indexed[k]) ? take((size_t)map_size) : 0;
+    o_sc[k] = on_device(scores[k]) ? 0 : take(n * es);
+    o_rot[k] = on_device(rotations[k]) ? 0 : take(n * 32);
+    o_idx[k] = (with_idx && !on_device(simulation_indices[k])) ? take(n * 8) : 0;
+    o_rows[k] = (point_rows && point_rows[k] && !on_device(point_rows[k])) ? take((size_t)map_size * 4) : 0;
+    o_ni[k] = (not_indexed && not_indexed[k] && !on_device(not_indexed[k])) ? take((size_t)map_size) : 0;
   }
   const size_t n_out = (size_t)map_size * n_scores, n_mer = (size_t)map_size * total;
   const size_t o_mm = take((size_t)n_maps * 16), o_off = take((size_t)n_maps * 8), o_err = take(4);
@@ -322,21 +325,27 @@ extern "C" int kdi_merge_crystal_maps(kdi_ctx* ctx, int n_maps, int64_t map_size
   std::vector<long long> mm_init((size_t)n_maps * 2);
   for (int k = 0; k < n_maps; ++k) {
     const size_t n = (size_t)n_points[k] * n_scores;
-    KDI_CUDA(ctx, cudaMemcpyAsync(w + o_sc[k], scores[k], n * es, cudaMemcpyHostToDevice, st));
-    KDI_CUDA(ctx, cudaMemcpyAsync(w + o_rot[k], rotations[k], n * 32, cudaMemcpyHostToDevice, st));
-    a.scores[k] = w + o_sc[k];
-    a.rot[k] = reinterpret_cast<const double*>(w + o_rot[k]);
+    auto bring = [&](const void* src, size_t at, size_t bytes, const void** dev) -> int {
+      if (on_device(src)) { *dev = src; return KDI_OK; }
+      *dev = w + at;
+      return kdi_copy_in(ctx, st, w + at, src, bytes);
+    };
+    const void* dev = nullptr;
+    KDI_TRY(bring(scores[k], o_sc[k], n * es, &dev));
+    a.scores[k] = dev;
+    KDI_TRY(bring(rotations[k], o_rot[k], n * 32, &dev));
+    a.rot[k] = reinterpret_cast<const double*>(dev);
     if (with_idx) {
-      KDI_CUDA(ctx, cudaMemcpyAsync(w + o_idx[k], simulation_indices[k], n * 8, cudaMemcpyHostToDevice, st));
-      a.idx[k] = reinterpret_cast<const int64_t*>(w + o_idx[k]);
+      KDI_TRY(bring(simulation_indices[k], o_idx[k], n * 8, &dev));
+      a.idx[k] = reinterpret_cast<const int64_t*>(dev);
     }
     if (point_rows && point_rows[k]) {
-      KDI_CUDA(ctx, cudaMemcpyAsync(w + o_rows[k], point_rows[k], (size_t)map_size * 4, cudaMemcpyHostToDevice, st));
-      a.rows[k] = reinterpret_cast<const int32_t*>(w + o_rows[k]);
+      KDI_TRY(bring(point_rows[k], o_rows[k], (size_t)map_size * 4, &dev));
+      a.rows[k] = reinterpret_cast<const int32_t*>(dev);
     }
     if (not_indexed && not_indexed[k]) {
-      KDI_CUDA(ctx, cudaMemcpyAsync(w + o_ni[k], not_indexed[k], (size_t)map_size, cudaMemcpyHostToDevice, st));
-      a.not_indexed[k] = w + o_ni[k];
+      KDI_TRY(bring(not_indexed[k], o_ni[k], (size_t)map_size, &dev));
+      a.not_indexed[k] = reinterpret_cast<const uint8_t*>(dev);
     }
     a.n_rows[k] = n_points[k];
     mm_init[2 * k] = LLONG_MAX;
@@ -389,13 +398,14 @@ extern "C" int kdi_merge_crystal_maps(kdi_ctx* ctx, int n_maps, int64_t map_size
   ctx->tm.kernel_launches++;
   int h_err = 0;
   KDI_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
-  KDI_CUDA(ctx, cudaMemcpyAsync(phase_id_out, w + o_ph, (size_t)map_size * 8, cudaMemcpyDeviceToHost, st));
-  KDI_CUDA(ctx, cudaMemcpyAsync(scores_out, w + o_ns, n_out * es, cudaMemcpyDeviceToHost, st));
-  KDI_CUDA(ctx, cudaMemcpyAsync(rotations_out, w + o_nr, n_out * 32, cudaMemcpyDeviceToHost, st));
-  KDI_CUDA(ctx, cudaMemcpyAsync(merged_scores_out, w + o_ms, n_mer * es, cudaMemcpyDeviceToHost, st));
+  // (outputs go to wherever the caller's buffers live: device, pinned or - staged - pageable memory)
+  KDI_TRY(kdi_copy_out(ctx, st, phase_id_out, w + o_ph, (size_t)map_size * 8));
+  KDI_TRY(kdi_copy_out(ctx, st, scores_out, w + o_ns, n_out * es));
+  KDI_TRY(kdi_copy_out(ctx, st, rotations_out, w + o_nr, n_out * 32));
+  KDI_TRY(kdi_copy_out(ctx, st, merged_scores_out, w + o_ms, n_mer * es));
   if (with_idx) {
-    KDI_CUDA(ctx, cudaMemcpyAsync(simulation_indices_out, w + o_nx, n_out * 4, cudaMemcpyDeviceToHost, st));
-    KDI_CUDA(ctx, cudaMemcpyAsync(merged_indices_out, w + o_mi, n_mer * 8, cudaMemcpyDeviceToHost, st));
+    KDI_TRY(kdi_copy_out(ctx, st, simulation_indices_out, w + o_nx, n_out * 4));
+    KDI_TRY(kdi_copy_out(ctx, st, merged_indices_out, w + o_mi, n_mer * 8));
   }
   KDI_CUDA(ctx, cudaStreamSynchronize(st));
   float ms = 0.f;
