@@ -119,6 +119,10 @@ extern "C" {
 #define KDI_OPT_DIV_DOUBLE 20    /* 1 = the prepare kernels divide by the row norm through the double reciprocal
                                    everywhere; 0 (default) = through the float32 FMA sequence wherever that is exact
                                    (rows in the normal range; bit-identical results, no conversions)           */
+#define KDI_OPT_PROJECT_LIBM 22   /* 1 = the dictionary-generation kernel evaluates atan, the square roots and the
+                                   division of the Lambert projection with the CUDA math library (round-1
+                                   arithmetic, ~340 instructions per pixel); 0 (default) = with its own seeded
+                                   Newton / polynomial sequences (~150, the same float32 patterns)              */
 #define KDI_OPT_DICT_VIEW 21     /* 1 (default) = a device-resident, unmasked float32 dictionary handed to a driver
                                    entry point (kdi_dictionary_indexing, kdi_shard_*) is not copied as normalised
                                    float32 rows: the exact scores read the caller's rows and apply the row's

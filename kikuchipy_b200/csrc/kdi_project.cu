@@ -21,6 +21,8 @@
 #include "kdi_internal.cuh"
 #include "kdi_project_dev.cuh"
 
+#include <type_traits>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -38,6 +40,9 @@ struct ProjParams {
   double om[9];       // detector -> sample, row-major
   const void* upper;  // npy x npx, MT
   const void* lower;
+  const void* quad_upper;  // npy x npx elements of 4 MT: the bilinear taps of every position
+  const void* quad_lower;
+  const double* dc_soa;    // x | y | z, S doubles each
   int npx, npy;       // as the reference passes them (npx bounds the row index, npy the column index)
   int ld;             // row pitch of the master pattern arrays (elements)
   double scale;
@@ -92,7 +97,9 @@ __device__ __forceinline__ uint16_t op16(float v) {
   else return __half_as_ushort(__float2half_rn(v * KDI_OP_SCALE));
 }
 
-template <typename MT, bool BF16>
+// LEAN: the per-pixel arithmetic without library calls (project_pixel_lean, default); otherwise the
+// CUDA math library version that the refinement kernel shares (KDI_OPT_PROJECT_LIBM, kept for A/B runs)
+template <typename MT, bool BF16, bool LEAN>
 __global__ void __launch_bounds__(kProjThreads)
 kdi_project_kernel(const ProjParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -108,6 +115,8 @@ kdi_project_kernel(const ProjParams p) {
     const double m[9] = {__dadd_rn(__dadd_rn(__dadd_rn(aa, bb), -cc), -dd), __dadd_rn(ac, bd), __dadd_rn(bc, -ad),
                          __dadd_rn(__dadd_rn(__dadd_rn(aa, -bb), cc), -dd), __dadd_rn(ad, bc), __dadd_rn(cd, -ab),
                          __dadd_rn(__dadd_rn(__dadd_rn(aa, -bb), -cc), dd), __dadd_rn(ab, cd), __dadd_rn(bd, -ac)};
+    // (the factor 2 of the off-diagonal terms folded in: exact, 2 (u + v) == 2 u + 2 v)
+    const double m2[9] = {m[0], 2.0 * m[1], 2.0 * m[2], m[3], 2.0 * m[4], 2.0 * m[5], m[6], 2.0 * m[7], 2.0 * m[8]};
     __syncthreads();  // previous row's readers are done with v / vd
     double lo = INFINITY, hi = -INFINITY;
     double gx0 = 0, gy0 = 0, xs = 0, ys = 0, xh = 0, yh = 0, pcz = 0;
@@ -121,28 +130,74 @@ kdi_project_kernel(const ProjParams p) {
       ys = (y_max - y_min) / (double)p.nrows;
       gx0 = x_min; gy0 = y_max; xh = xs / 2.0; yh = ys / 2.0;
     }
-    for (int64_t j = threadIdx.x; j < p.S; j += kProjThreads) {
+    // (four copies of the loop, selected by block-uniform flags: instructions that are predicated off still
+    // take issue slots)
+    const int S = (int)p.S;
+    auto pixels = [&](auto with_pcs, auto with_rescale) {
+      auto direction = [&](int j, const double* dcp, double& vx, double& vy, double& vz) {
+        if constexpr (decltype(with_pcs)::value) {
+          const int r = j / p.ncols, c = j - r * p.ncols;
+          const double gx = (gx0 + (double)c * xs + xh) * pcz;
+          const double gy = (gy0 + (double)r * (-ys) - yh) * pcz;
+          vx = gx * p.om[0] + gy * p.om[1] + pcz * p.om[2];
+          vy = gx * p.om[3] + gy * p.om[4] + pcz * p.om[5];
+          vz = gx * p.om[6] + gy * p.om[7] + pcz * p.om[8];
+          const double inv = 1.0 / sqrt(vx * vx + vy * vy + vz * vz);
+          vx *= inv; vy *= inv; vz *= inv;
+        } else if constexpr (LEAN) {
+          vx = __ldg(p.dc_soa + j); vy = __ldg(p.dc_soa + p.S + j); vz = __ldg(p.dc_soa + 2 * p.S + j);
+        } else {
+          vx = __ldg(dcp); vy = __ldg(dcp + 1); vz = __ldg(dcp + 2);
+        }
+      };
+      auto keep = [&](int j, double val) {
+        if constexpr (decltype(with_rescale)::value) {
+          vd[j] = val;
+          lo = fmin(lo, val);
+          hi = fmax(hi, val);
+        } else {
+          v[j] = (float)val;
+        }
+      };
+      int j = threadIdx.x;
+      if (j >= S) return;
+      const double* dcp = p.dc + 3 * j;
       double vx, vy, vz;
-      if (p.pcs) {
-        const int64_t r = j / p.ncols, c = j - r * p.ncols;
-        const double gx = (gx0 + (double)c * xs + xh) * pcz;
-        const double gy = (gy0 + (double)r * (-ys) - yh) * pcz;
-        vx = gx * p.om[0] + gy * p.om[1] + pcz * p.om[2];
-        vy = gx * p.om[3] + gy * p.om[4] + pcz * p.om[5];
-        vz = gx * p.om[6] + gy * p.om[7] + pcz * p.om[8];
-        const double inv = 1.0 / sqrt(vx * vx + vy * vy + vz * vz);
-        vx *= inv; vy *= inv; vz *= inv;
+      direction(j, dcp, vx, vy, vz);
+      if constexpr (LEAN) {
+        // software pipeline: the master-pattern gathers of pixel j (L2 latency) and the direction cosines
+        // of pixel j + 2T are in flight while the coordinates of pixel j + T are computed - with ~6 warps
+        // per scheduler the loop is otherwise bound by those latencies, not by any pipe
+        kdi_lean_taps<MT> cur = project_pixel_lean_fetch<MT>(p, m2, vx, vy, vz);
+        int jn = j + kProjThreads;
+        if (jn < S) direction(jn, dcp + 3 * kProjThreads, vx, vy, vz);
+        while (jn < S) {
+          const int jnn = jn + kProjThreads;
+          double nx = 0, ny = 0, nz = 0;
+          if (jnn < S) direction(jnn, dcp + 6 * kProjThreads, nx, ny, nz);
+          const kdi_lean_taps<MT> nxt = project_pixel_lean_fetch<MT>(p, m2, vx, vy, vz);
+          keep(j, project_pixel_lean_blend<MT>(cur));
+          cur = nxt;
+          vx = nx; vy = ny; vz = nz;
+          j = jn;
+          jn = jnn;
+          dcp += 3 * kProjThreads;
+        }
+        keep(j, project_pixel_lean_blend<MT>(cur));
       } else {
-        vx = __ldg(p.dc + 3 * j); vy = __ldg(p.dc + 3 * j + 1); vz = __ldg(p.dc + 3 * j + 2);
+        for (;;) {
+          keep(j, project_pixel<MT>(p, m, vx, vy, vz));
+          j += kProjThreads;
+          dcp += 3 * kProjThreads;
+          if (j >= S) break;
+          direction(j, dcp, vx, vy, vz);
+        }
       }
-      const double val = project_pixel<MT>(p, m, vx, vy, vz);
-      if (p.rescale) {
-        vd[j] = val;
-        lo = fmin(lo, val);
-        hi = fmax(hi, val);
-      } else {
-        v[j] = (float)val;
-      }
+    };
+    if (p.pcs) {
+      if (p.rescale) pixels(std::true_type(), std::true_type()); else pixels(std::true_type(), std::false_type());
+    } else {
+      if (p.rescale) pixels(std::false_type(), std::true_type()); else pixels(std::false_type(), std::false_type());
     }
     if (p.rescale) {  // _rescale_with_min_max (pattern/_pattern.py:110-111), then the cast
       block_reduce_minmax(lo, hi, red);
@@ -190,6 +245,35 @@ kdi_project_kernel(const ProjParams p) {
   }
 }
 
+// tap table of one hemisphere: element (i, j) = [v(i, j), v(i, j+1), v(i+1, j), v(i+1, j+1)] with the
+// reference's clamps (_master_pattern.py:650-653: the ROW neighbour is bounded by npx, the COLUMN neighbour
+// by npy) and, for non-square arrays, by the array itself
+template <typename MT>
+__global__ void kdi_build_taps_kernel(const MT* __restrict__ src, MT* __restrict__ dst, int rows, int cols) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / cols), j = (int)(e - (int64_t)i * cols);
+    int ip = (i + 1 >= cols) ? i : i + 1;
+    int jp = (j + 1 >= rows) ? j : j + 1;
+    ip = min(ip, rows - 1);
+    jp = min(jp, cols - 1);
+    MT* q = dst + 4 * e;
+    q[0] = src[(int64_t)i * cols + j];
+    q[1] = src[(int64_t)i * cols + jp];
+    q[2] = src[(int64_t)ip * cols + j];
+    q[3] = src[(int64_t)ip * cols + jp];
+  }
+}
+
+__global__ void kdi_dc_soa_kernel(const double* __restrict__ dc, double* __restrict__ soa, int64_t S) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < S) {
+    soa[j] = dc[3 * j];
+    soa[S + j] = dc[3 * j + 1];
+    soa[2 * S + j] = dc[3 * j + 2];
+  }
+}
+
 template <typename MT>
 int launch_typed(kdi_ctx* ctx, cudaStream_t stream, const ProjParams& p, int bf16, int max_ctas) {
   size_t smem = ((size_t)p.S * sizeof(float) + 15) / 16 * 16;
@@ -198,12 +282,12 @@ int launch_typed(kdi_ctx* ctx, cudaStream_t stream, const ProjParams& p, int bf1
     return kdi_fail(ctx, KDI_EUNSUPPORTED, "detector of %lld pixels is too large for the projection kernel's shared-memory staging",
                     (long long)p.S);
   // (per launch, not once per process: the attribute is per device)
-  if (bf16) cudaFuncSetAttribute(kdi_project_kernel<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  else cudaFuncSetAttribute(kdi_project_kernel<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  auto kern = ctx->project_libm ? (bf16 ? kdi_project_kernel<MT, true, false> : kdi_project_kernel<MT, false, false>)
+                                : (bf16 ? kdi_project_kernel<MT, true, true> : kdi_project_kernel<MT, false, true>);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const unsigned grid = (unsigned)((max_ctas > 0 && p.n_rows > max_ctas) ? max_ctas : p.n_rows);
   kdi_span span(ctx, stream, "project (+normalize)");
-  if (bf16) kdi_project_kernel<MT, true><<<grid, kProjThreads, smem, stream>>>(p);
-  else kdi_project_kernel<MT, false><<<grid, kProjThreads, smem, stream>>>(p);
+  kern<<<grid, kProjThreads, smem, stream>>>(p);
   KDI_CUDA(ctx, cudaGetLastError());
   ctx->tm.kernel_launches++;
   return KDI_OK;
@@ -232,6 +316,9 @@ int kdi_launch_project_pcs(kdi_ctx* ctx, cudaStream_t stream, const kdi_master_p
   if (d_pcs) for (int i = 0; i < 9; ++i) p.om[i] = om[i];
   p.upper = mp->upper;
   p.lower = mp->lower;
+  p.quad_upper = mp->quad_upper;
+  p.quad_lower = mp->quad_lower;
+  p.dc_soa = mp->dc_soa;
   // EBSDMasterPattern.get_patterns passes npx, npy = axes_manager.signal_shape = (columns, rows)
   // and the kernels bound the ROW index by npx and the COLUMN index by npy (_master_pattern.py
   // :650-653); kept as is (master patterns are square)
@@ -324,11 +411,31 @@ int kdi_master_pattern_create(kdi_ctx* ctx, const void* upper, const void* lower
   if (e == cudaSuccess) e = cudaMemcpy(mp->upper, hu, n * dsz, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(mp->lower, hl, n * dsz, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(mp->dc, direction_cosines, (size_t)S * 3 * sizeof(double), cudaMemcpyHostToDevice);
+  // tables of the dictionary-generation kernel
+  if (e == cudaSuccess) e = cudaMalloc(&mp->quad_upper, 4 * n * dsz);
+  if (e == cudaSuccess) e = cudaMalloc(&mp->quad_lower, 4 * n * dsz);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&mp->dc_soa), (size_t)S * 3 * sizeof(double));
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    if (mp->mp_dtype == KDI_F64) {
+      kdi_build_taps_kernel<double><<<grid, 256>>>(static_cast<const double*>(mp->upper), static_cast<double*>(mp->quad_upper), (int)rows, (int)cols);
+      kdi_build_taps_kernel<double><<<grid, 256>>>(static_cast<const double*>(mp->lower), static_cast<double*>(mp->quad_lower), (int)rows, (int)cols);
+    } else {
+      kdi_build_taps_kernel<float><<<grid, 256>>>(static_cast<const float*>(mp->upper), static_cast<float*>(mp->quad_upper), (int)rows, (int)cols);
+      kdi_build_taps_kernel<float><<<grid, 256>>>(static_cast<const float*>(mp->lower), static_cast<float*>(mp->quad_lower), (int)rows, (int)cols);
+    }
+    kdi_dc_soa_kernel<<<(unsigned)((S + 255) / 256), 256>>>(mp->dc, mp->dc_soa, S);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
     if (mp->upper) cudaFree(mp->upper);
     if (mp->lower) cudaFree(mp->lower);
     if (mp->dc) cudaFree(mp->dc);
+    if (mp->quad_upper) cudaFree(mp->quad_upper);
+    if (mp->quad_lower) cudaFree(mp->quad_lower);
+    if (mp->dc_soa) cudaFree(mp->dc_soa);
     delete mp;
     return kdi_fail(ctx, e == cudaErrorMemoryAllocation ? KDI_ENOMEM : KDI_ECUDA, "master pattern upload failed: %s", cudaGetErrorString(e));
   }
@@ -345,6 +452,9 @@ int kdi_master_pattern_destroy(kdi_ctx* ctx, kdi_master_pattern* mp) {
   cudaFree(mp->upper);
   cudaFree(mp->lower);
   cudaFree(mp->dc);
+  cudaFree(mp->quad_upper);
+  cudaFree(mp->quad_lower);
+  cudaFree(mp->dc_soa);
   delete mp;
   return KDI_OK;
 }

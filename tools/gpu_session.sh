@@ -1,13 +1,5 @@
 #!/bin/bash
-# Session 23: two GPUs - whole suite (sharded tests with the forced view mode), short N = 2 bench.
+# Session 27: ncu capture of the projection kernel (own arithmetic, tap tables).
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/s23_pytest.log 2>&1
-echo "pytest exit $?"; tail -6 gpurun_out/s23_pytest.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 3 --no-generated --no-cpu > gpurun_out/s23_bench_n2.json 2> gpurun_out/s23_bench_n2.err
-echo "bench n2 exit $?"; python - <<'PY'
-import json
-for l in open('gpurun_out/s23_bench_n2.json'):
-    l=l.strip()
-    if l.startswith('{'):
-        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step','n_gpus','e2e','parity') if k in d}); print(d.get('detail'))
-PY
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:kdi_project_kernel -s 2 -c 1 -o gpurun_out/r2_prof_kdi_project_kernel -f env N=100000 CONFIGS=1001:0 python tools/project_time.py > gpurun_out/ncu_project.log 2>&1
+echo "ncu exit $?"; tail -3 gpurun_out/ncu_project.log
