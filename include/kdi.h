@@ -114,7 +114,9 @@ extern "C" {
 #define KDI_OPT_EARLY_SPLIT 19   /* device-resident dictionaries, event-ordered schedule: 1 = the first quarter of the
                                    dictionary is prepared on the main stream and matched against every row block
                                    while the rest is prepared on the other stream; 0 = the whole dictionary is
-                                   prepared at full speed first, then one tensor-core launch per row-block group */
+                                   prepared at full speed first, then one tensor-core launch per row-block group.
+                                   A GENERATED dictionary (kdi_*_projected) is projected in one piece on the other
+                                   stream, beside the upload of the experimental rows; 2 = quarter split there too */
 
 #define KDI_OPT_DIV_DOUBLE 20    /* 1 = the prepare kernels divide by the row norm through the double reciprocal
                                    everywhere; 0 (default) = through the float32 FMA sequence wherever that is exact

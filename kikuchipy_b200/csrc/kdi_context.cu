@@ -557,7 +557,7 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
       ctx->gemm_serial = value != 0;
       return KDI_OK;
     case KDI_OPT_EARLY_SPLIT:
-      ctx->early_split = value != 0;
+      ctx->early_split = value == 2 ? 2 : (value != 0);
       return KDI_OK;
     case KDI_OPT_BULK_NORMALIZE:
       ctx->bulk_normalize = value != 0;

@@ -699,8 +699,12 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
     return KDI_OK;
   };
   // event mode: the rest of the dictionary starts now, beside the experimental rows and the first quarter
+  // (a generated dictionary needs nothing but the rotations: ALL of it is projected on the other stream
+  // while the experimental rows cross PCIe and are normalised, and the tensor-core launches then run on
+  // their own - 2.6 ms of projection beside 0.8 ms of upload instead of a GEMM slowed down by sharing
+  // the SMs with three quarters of the projection; KDI_OPT_EARLY_SPLIT = 2 keeps the quarter split)
   if (rc == KDI_OK && early) {
-    g1_rows = dict_rows / 4 / KDI_TILE_N * KDI_TILE_N;
+    g1_rows = (dsrc.mp && ctx->early_split != 2) ? 0 : dict_rows / 4 / KDI_TILE_N * KDI_TILE_N;
     rc = start_aux_fill();
   }
 
