@@ -142,7 +142,7 @@ kdi_project_kernel(const ProjParams p) {
           vx = gx * p.om[0] + gy * p.om[1] + pcz * p.om[2];
           vy = gx * p.om[3] + gy * p.om[4] + pcz * p.om[5];
           vz = gx * p.om[6] + gy * p.om[7] + pcz * p.om[8];
-          const double inv = 1.0 / sqrt(vx * vx + vy * vy + vz * vz);
+          const double inv = LEAN ? kdi_proj::rsqrt_full(vx * vx + vy * vy + vz * vz) : 1.0 / sqrt(vx * vx + vy * vy + vz * vz);
           vx *= inv; vy *= inv; vz *= inv;
         } else if constexpr (LEAN) {
           vx = __ldg(p.dc_soa + j); vy = __ldg(p.dc_soa + p.S + j); vz = __ldg(p.dc_soa + 2 * p.S + j);

@@ -108,6 +108,15 @@ __device__ __forceinline__ double rsqrt_seed(double d) {
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   return y;
 }
+// 1 / sqrt(t) to float64 rounding for any normal t > 0: hardware seed (20 bits), one cubic step, one
+// residual correction (the library's 1.0 / sqrt(t) costs three times the instructions)
+__device__ __forceinline__ double rsqrt_full(double t) {
+  double y = rsqrt_seed(t);
+  const double e = fma(-(t * y), y, 1.0);
+  y = fma(y * e, fma(0.375, e, 0.5), y);
+  const double e2 = fma(-(t * y), y, 1.0);
+  return fma(0.5 * y, e2, y);
+}
 constexpr double kTanPiOver8 = 0.41421356237309504880;
 constexpr double kPiOver4 = 0.78539816339744830962;
 // atan(r) / r as a polynomial in u = r^2 on [0, tan^2(pi/8)]: relative error 2.2e-16 (interpolation at

@@ -37,9 +37,11 @@ constexpr int kRefThreads = 256;
 constexpr int kRefWarps = kRefThreads / 32;
 
 struct RefineParams {
-  // what project_pixel needs
+  // what project_pixel_lean needs
   const void* upper;
   const void* lower;
+  const void* quad_upper;
+  const void* quad_lower;
   int npx, npy, ld;
   double scale, scale_over_sqrt_pi_half;
   // experimental patterns
@@ -149,6 +151,8 @@ __device__ double evaluate(const RefineParams& p, const double* x, const double*
   const double m[9] = {__dadd_rn(__dadd_rn(__dadd_rn(aa, bb), -cc), -dd), __dadd_rn(ac, bd), __dadd_rn(bc, -ad),
                        __dadd_rn(__dadd_rn(__dadd_rn(aa, -bb), cc), -dd), __dadd_rn(ad, bc), __dadd_rn(cd2, -ab),
                        __dadd_rn(__dadd_rn(__dadd_rn(aa, -bb), -cc), dd), __dadd_rn(ab, cd2), __dadd_rn(bd, -ac)};
+  // (the factor 2 of the off-diagonal terms folded in: exact)
+  const double m2[9] = {m[0], 2.0 * m[1], 2.0 * m[2], m[3], 2.0 * m[4], 2.0 * m[5], m[6], 2.0 * m[7], 2.0 * m[8]};
   // direction cosines from a projection centre (get_gnomonic_bounds + _get_direction_cosines_for_fixed_pc)
   const double* pc = (MODE == 1) ? x : (MODE == 2 ? x + 3 : pc_fixed);
   double gx0 = 0, gy0 = 0, xs = 0, ys = 0, xh = 0, yh = 0, pcz = 0;
@@ -169,18 +173,19 @@ __device__ double evaluate(const RefineParams& p, const double* x, const double*
     const int64_t idx = p.cols ? (int64_t)p.cols[j] : j;
     double vx, vy, vz;
     if (pc) {
-      const int64_t r = idx / p.ncols, cidx = idx - r * p.ncols;
+      // (32-bit: a 64-bit division is a ~40-instruction routine, and this loop is issue-bound)
+      const unsigned r = (unsigned)idx / (unsigned)p.ncols, cidx = (unsigned)idx - r * (unsigned)p.ncols;
       const double gx = (gx0 + (double)cidx * xs + xh) * pcz;
       const double gy = (gy0 + (double)r * (-ys) - yh) * pcz;
       vx = gx * p.om[0] + gy * p.om[1] + pcz * p.om[2];
       vy = gx * p.om[3] + gy * p.om[4] + pcz * p.om[5];
       vz = gx * p.om[6] + gy * p.om[7] + pcz * p.om[8];
-      const double inv = 1.0 / sqrt(vx * vx + vy * vy + vz * vz);
+      const double inv = kdi_proj::rsqrt_full(vx * vx + vy * vy + vz * vz);
       vx *= inv; vy *= inv; vz *= inv;
     } else {
       vx = __ldg(p.dc + 3 * idx); vy = __ldg(p.dc + 3 * idx + 1); vz = __ldg(p.dc + 3 * idx + 2);
     }
-    const float fv = (float)project_pixel<float>(p, m, vx, vy, vz);
+    const float fv = (float)project_pixel_lean<float>(p, m2, vx, vy, vz);
     v[j] = fv;
     sum += (double)fv;
   }
@@ -497,6 +502,8 @@ static int refine_impl(kdi_ctx* ctx, const kdi_master_pattern* mp, int mode, con
   RefineParams p = {};
   p.upper = mp->upper;
   p.lower = mp->lower;
+  p.quad_upper = mp->quad_upper;
+  p.quad_lower = mp->quad_lower;
   p.npx = mp->npx;
   p.npy = mp->npy;
   p.ld = mp->npx;

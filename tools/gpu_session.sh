@@ -1,29 +1,18 @@
 #!/bin/bash
-# Session 28: generated dictionary projected in one piece beside the experimental upload; whole suite.
+# Session 31: refinement after the 32-bit index division; PCIe probe; timeline of the host-dictionary path.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/s28_pytest.log 2>&1
-echo "pytest exit $?"; tail -4 gpurun_out/s28_pytest.log
-for i in 1 2; do
-timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu --no-extras > gpurun_out/s28_bench_n1_$i.json 2> gpurun_out/s28_bench_n1_$i.err
-echo "bench exit $?"; python - <<PY
-import json
-for l in open('gpurun_out/s28_bench_n1_$i.json'):
-    l=l.strip()
-    if l.startswith('{'):
-        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step','e2e_generated') if k in d})
-PY
-done
-KDI_TIMELINE=1 timeout 300 python - <<'PY' > gpurun_out/s28_timeline_generated.txt 2>&1
+timeout 900 python -m pytest tests/test_refinement.py tests/test_gpu_projection.py -m gpu -q > gpurun_out/s31_pytest.log 2>&1
+echo "pytest exit $?"; tail -3 gpurun_out/s31_pytest.log
+timeout 600 python tests/gpu_tools/refine_time.py > gpurun_out/s31_refine_time.txt 2>&1; tail -3 gpurun_out/s31_refine_time.txt
+timeout 300 python tools/probes/h2d_probe.py > gpurun_out/s31_h2d_probe.txt 2>&1; cat gpurun_out/s31_h2d_probe.txt
+KDI_TIMELINE=1 timeout 300 python - <<'PY' > gpurun_out/s31_timeline_host_dict.txt 2>&1
 import numpy as np, torch, sys
 sys.path.insert(0, '.')
 import kikuchipy_b200 as kb
-from kikuchipy_b200 import synthetic as po
-mu, ml = po.synthetic_master_pattern(1001, seed=5)
-dc = kb.direction_cosines([-0.9, 0.85, -0.7, 0.95], 0.5, 60, 60, po.tilted_detector_matrix(70.0))
-rot = po.random_rotations(100000, seed=4)
-gen = kb.get_patterns(mu, ml, rot, direction_cosines=dc, detector_shape=(60, 60))
-exp = np.random.default_rng(1).integers(0, 256, (10000, 60, 60), dtype=np.uint8)
+ctx = kb.default_context(0)
+exp = ctx.pinned_empty((10000, 60, 60), np.uint8); exp[:] = np.random.default_rng(1).integers(0, 256, exp.shape, dtype=np.uint8)
+dic = ctx.pinned_empty((100000, 60, 60), np.float32); dic[:] = np.random.default_rng(2).random(dic.shape, dtype=np.float32)
 for _ in range(3):
-    res = kb.dictionary_indexing(exp, gen, metric="ncc", keep_n=20, verbose=False)
+    res = kb.dictionary_indexing(exp, dic, metric="ncc", keep_n=20, verbose=False)
 PY
-tail -30 gpurun_out/s28_timeline_generated.txt
+tail -45 gpurun_out/s31_timeline_host_dict.txt
