@@ -1,18 +1,15 @@
 #!/bin/bash
-# Session 31: refinement after the 32-bit index division; PCIe probe; timeline of the host-dictionary path.
+# Session 33: two GPUs - sharded tests, smoke(), short N = 2 bench with the generated-dictionary leg.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_refinement.py tests/test_gpu_projection.py -m gpu -q > gpurun_out/s31_pytest.log 2>&1
-echo "pytest exit $?"; tail -3 gpurun_out/s31_pytest.log
-timeout 600 python tests/gpu_tools/refine_time.py > gpurun_out/s31_refine_time.txt 2>&1; tail -3 gpurun_out/s31_refine_time.txt
-timeout 300 python tools/probes/h2d_probe.py > gpurun_out/s31_h2d_probe.txt 2>&1; cat gpurun_out/s31_h2d_probe.txt
-KDI_TIMELINE=1 timeout 300 python - <<'PY' > gpurun_out/s31_timeline_host_dict.txt 2>&1
-import numpy as np, torch, sys
-sys.path.insert(0, '.')
-import kikuchipy_b200 as kb
-ctx = kb.default_context(0)
-exp = ctx.pinned_empty((10000, 60, 60), np.uint8); exp[:] = np.random.default_rng(1).integers(0, 256, exp.shape, dtype=np.uint8)
-dic = ctx.pinned_empty((100000, 60, 60), np.float32); dic[:] = np.random.default_rng(2).random(dic.shape, dtype=np.float32)
-for _ in range(3):
-    res = kb.dictionary_indexing(exp, dic, metric="ncc", keep_n=20, verbose=False)
+timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q > gpurun_out/s33_pytest_sharded.log 2>&1
+echo "pytest sharded exit $?"; tail -3 gpurun_out/s33_pytest_sharded.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s33_smoke.log 2>&1
+echo "smoke exit $?"; tail -4 gpurun_out/s33_smoke.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 3 --no-cpu --no-extras > gpurun_out/s33_bench_n2.json 2> gpurun_out/s33_bench_n2.err
+echo "bench n2 exit $?"; python - <<'PY'
+import json
+for l in open('gpurun_out/s33_bench_n2.json'):
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step','n_gpus','e2e','e2e_generated','parity') if k in d})
 PY
-tail -45 gpurun_out/s31_timeline_host_dict.txt
