@@ -304,9 +304,17 @@ int kdi_match_complete(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp
   auto copy_out = [&]() -> int {
     if (job->out_loc != KDI_HOST && job->d_sc == job->scores_out) return KDI_OK;  // written in place
     if (!job->scores_out || !job->indices_out) return kdi_fail(ctx, KDI_EINVAL, "output buffers are NULL");
-    const cudaMemcpyKind kind = job->out_loc == KDI_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    KDI_CUDA(ctx, cudaMemcpyAsync(job->scores_out, job->d_sc, (size_t)M * keep_n * sizeof(float), kind, st));
-    KDI_CUDA(ctx, cudaMemcpyAsync(job->indices_out, job->d_ix, (size_t)M * keep_n * sizeof(int64_t), kind, st));
+    if (job->out_loc == KDI_HOST) {
+      // (pinned destination: queued; pageable - an ordinary NumPy array - through the pinned ring instead of
+      // the driver's own serial staging; the bytes are counted once, below)
+      const int64_t counted = ctx->tm.d2h_bytes;
+      KDI_TRY(kdi_copy_out(ctx, st, job->scores_out, job->d_sc, (size_t)M * keep_n * sizeof(float)));
+      KDI_TRY(kdi_copy_out(ctx, st, job->indices_out, job->d_ix, (size_t)M * keep_n * sizeof(int64_t)));
+      ctx->tm.d2h_bytes = counted;
+      return KDI_OK;
+    }
+    KDI_CUDA(ctx, cudaMemcpyAsync(job->scores_out, job->d_sc, (size_t)M * keep_n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    KDI_CUDA(ctx, cudaMemcpyAsync(job->indices_out, job->d_ix, (size_t)M * keep_n * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     return KDI_OK;
   };
   int n_flag = 0;

@@ -1,7 +1,8 @@
 """Run one BASELINE.json configuration at FULL size on the GPU(s), verify it, print one JSON line.
 
   python tests/gpu_tools/run_config.py --config 2|3                                   (one GPU)
-  python -m torch.distributed.run --nproc-per-node 8 ... tests/gpu_tools/run_config.py --config 4|5
+  python -m torch.distributed.run --nproc-per-node 8 ... tests/gpu_tools/run_config.py --config 4|5|50
+  (50 = config 5 with the dictionary generated on the device from rotations of a master pattern)
 
 The run itself and the on-device verification (structure, planted best match, float64 evaluation of
 a row sample) live in ``tools/di_configs.py``, which ``bench.py`` uses too; this script adds a
@@ -26,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True, choices=[2, 3, 4, 5])
+    ap.add_argument("--config", type=int, required=True, choices=[2, 3, 4, 5, 50])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--sample64", type=int, default=256, help="rows checked against the float64 evaluation")
@@ -74,7 +75,7 @@ def main():
         line["checks"].update({"oracle_rows": int(rows.size), "oracle_tie_ok": bool(c["tie_ok"]),
                                "oracle_scores_ok": bool(c["scores_ok"]), "oracle_max_dscore": float(c["max_dscore"]),
                                "oracle_exact_rows": float(c["exact_rows"]), "oracle_s": round(time.perf_counter() - t1, 1)})
-    if rank == 0 and args.config == 5 and line.get("osm"):
+    if rank == 0 and args.config in (5, 50) and line.get("osm"):
         nav = cfg["nav"]
         idx_h = idx.cpu().numpy()
         osm = ctx.orientation_similarity_map(idx_h, nav[0], nav[1], k, k, False, np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]]), 2)[..., 0]

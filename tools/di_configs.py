@@ -7,6 +7,10 @@ CPU-oracle sample on top).
   3: 40 000 x 100 000, 120x120, circular mask, NDP      (1 GPU)
   4: 100 000 x 300 000, 60x60, NCC, keep_n 50           (dictionary sharded over the ranks)
   5: 200x200 map x 500 000, 80x80, bf16 candidates, host dictionary streamed, + OSM (sharded)
+ 50: config 5 with the dictionary GENERATED on the device, rank by rank, from 500 000 rotations of a master
+     pattern - what the reference's lazy dictionary does chunk by chunk on the CPU
+     (``dictionary_chunk.compute()``, _dictionary_indexing.py:105-108) - instead of 12.8 GB of float32
+     patterns crossing PCIe every step
 
 Verification of a result ``(indices, scores)``:
   * structure: lists sorted best first, indices valid and unique per row;
@@ -27,6 +31,8 @@ CONFIGS = {
     3: dict(M=40_000, nav=(200, 200), N=100_000, sig=(120, 120), metric="ndp", k=20, mask=True, bf16=False, host_dict=False),
     4: dict(M=100_000, nav=(250, 400), N=300_000, sig=(60, 60), metric="ncc", k=50, mask=False, bf16=False, host_dict=False),
     5: dict(M=40_000, nav=(200, 200), N=500_000, sig=(80, 80), metric="ncc", k=20, mask=False, bf16=True, host_dict=True),
+    50: dict(M=40_000, nav=(200, 200), N=500_000, sig=(80, 80), metric="ncc", k=20, mask=False, bf16=True, host_dict=False,
+             generated=True),
 }
 
 
@@ -53,6 +59,44 @@ class ShardedDictionary:
         s0, s1 = self.bounds[r]
         g = torch.Generator(device=self.dev); g.manual_seed(self.seed + r)
         return torch.rand((s1 - s0, self.S), dtype=torch.float32, device=self.dev, generator=g)
+
+
+class GeneratedShardedDictionary:
+    """The same interface for a dictionary projected from a master pattern: N random rotations (seed 4) of a
+    smooth synthetic two-hemisphere master pattern (seed 5) seen by a ``sig`` detector; shard r is projected
+    on the device by ``kdi_project_patterns`` whenever it is asked for, so any rank can regenerate any shard.
+    ``generated(rank)`` is the lazy dictionary (rotations + master pattern) the indexing call is given."""
+
+    def __init__(self, N, sig, world, dev, ctx, shard_bounds=None, master_pattern_size=1001):
+        import kikuchipy_b200 as kb
+        from kikuchipy_b200 import synthetic as po
+
+        self.N, self.sig, self.S, self.world, self.dev, self.ctx = int(N), tuple(sig), int(sig[0] * sig[1]), int(world), dev, ctx
+        if shard_bounds is None:
+            shard_bounds = kb.shard_bounds
+        self.bounds = [shard_bounds(self.N, self.world, r) for r in range(self.world)]
+        self.mu, self.ml = po.synthetic_master_pattern(master_pattern_size, seed=5)
+        self.dc = kb.direction_cosines([-0.9, 0.85, -0.7, 0.95], 0.5, sig[0], sig[1], po.tilted_detector_matrix(70.0))
+        self.rotations = po.random_rotations(self.N, seed=4)
+        self._mp = ctx.master_pattern(self.mu, self.ml, self.dc)
+
+    def shard(self, r):
+        import torch
+
+        s0, s1 = self.bounds[r]
+        out = torch.empty((s1 - s0, self.S), dtype=torch.float32, device=self.dev)
+        self.ctx.project_patterns(self._mp, torch.from_numpy(self.rotations[s0:s1]).to(self.dev), out=out)
+        return out
+
+    def generated(self, rank):
+        import kikuchipy_b200 as kb
+
+        s0, s1 = self.bounds[rank]
+        return kb.get_patterns(self.mu, self.ml, self.rotations[s0:s1], direction_cosines=self.dc,
+                               detector_shape=self.sig, context=self.ctx)
+
+    def close(self):
+        self._mp.close()
 
 
 def planted_patterns(dictionary: ShardedDictionary, my_shard, rank, M, seed=7, noise_seed=11):
@@ -153,7 +197,11 @@ def run_config(number, ctx, rank, world, dev, steps=3, warmup=1, sample64=256, s
     S = sig[0] * sig[1]
     ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 1 if cfg["bf16"] else 0)
     smask = circular_mask(sig) if cfg["mask"] else None
-    dictionary = ShardedDictionary(N, S, world, dev, shard_bounds=kb.shard_bounds)
+    generated = bool(cfg.get("generated"))
+    if generated:
+        dictionary = GeneratedShardedDictionary(N, sig, world, dev, ctx, shard_bounds=kb.shard_bounds)
+    else:
+        dictionary = ShardedDictionary(N, S, world, dev, shard_bounds=kb.shard_bounds)
     start, end = dictionary.bounds[rank]
     n_shard = end - start
     dic = dictionary.shard(rank)
@@ -165,6 +213,11 @@ def run_config(number, ctx, rank, world, dev, steps=3, warmup=1, sample64=256, s
         pinned = ctx.pinned_empty((n_shard,) + sig, np.float32)
         pinned[...] = dic.cpu().numpy()
         dict_in = pinned
+    gen = None
+    if generated:
+        gen = dictionary.generated(rank)
+        del dic, dict_in  # (the materialised shard was only needed for the planted patterns)
+        dic = dict_in = None
     torch.cuda.synchronize()
     code = _lib.KDI_NCC if cfg["metric"] == "ncc" else _lib.KDI_NDP
 
@@ -173,10 +226,13 @@ def run_config(number, ctx, rank, world, dev, steps=3, warmup=1, sample64=256, s
             idx = torch.empty((M, k), dtype=torch.int64, device=dev)
             sc = torch.empty((M, k), dtype=torch.float32, device=dev)
             ctx.set_signal_mask(smask)
-            ctx.dictionary_indexing(exp, M, dict_in, n_shard, code, k, out=(idx, sc))
+            if generated:
+                ctx.dictionary_indexing_projected(exp, M, gen.master_pattern, gen.rotations, code, k, out=(idx, sc))
+            else:
+                ctx.dictionary_indexing(exp, M, dict_in, n_shard, code, k, out=(idx, sc))
             return idx, sc
-        return kb.dictionary_indexing_sharded(exp, dict_in, N, metric=cfg["metric"], keep_n=k, signal_mask=smask,
-                                              context=ctx)
+        return kb.dictionary_indexing_sharded(exp, gen if generated else dict_in, N, metric=cfg["metric"], keep_n=k,
+                                              signal_mask=smask, context=ctx)
 
     try:
         for _ in range(warmup):
@@ -211,7 +267,7 @@ def run_config(number, ctx, rank, world, dev, steps=3, warmup=1, sample64=256, s
         keep = None if smask is None else torch.from_numpy(~smask.ravel()).to(dev)
         checks.update(float64_check(exp, rows, dictionary, cfg["metric"], k, keep, idx, sc))
     osm_info = None
-    if number == 5 and rank == 0 and len(nav) == 2:
+    if number in (5, 50) and rank == 0 and len(nav) == 2:
         t1 = time.perf_counter()
         osm = ctx.orientation_similarity_map(idx.cpu().numpy(), nav[0], nav[1], k, k, False,
                                              np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]]), 2)[..., 0]
@@ -220,7 +276,8 @@ def run_config(number, ctx, rank, world, dev, steps=3, warmup=1, sample64=256, s
     out = {
         "config": number, "n_gpus": world, "M": M, "N": N, "signal": list(sig), "s_eff": s_eff, "metric": cfg["metric"],
         "keep_n": k, "compute_dtype": "bf16" if cfg["bf16"] else "fp16",
-        "dictionary": "pinned host, streamed" if cfg["host_dict"] else "device-resident",
+        "dictionary": ("generated on the device from rotations of a 1001x1001 master pattern" if generated
+                       else "pinned host, streamed" if cfg["host_dict"] else "device-resident"),
         "ms_per_step": round(ms, 3), "patterns_per_s": round(M / (ms * 1e-3)), "steps": steps, "warmup": warmup,
         "rank0_stage_ms": {kk: round(v, 3) for kk, v in tm.items() if kk.endswith("_ms")},
         "rank0_gemm_tflops_algorithmic": None if gemm_tflops is None else round(gemm_tflops, 1),
@@ -228,4 +285,6 @@ def run_config(number, ctx, rank, world, dev, steps=3, warmup=1, sample64=256, s
     }
     if keep_result:
         out["_result"] = (idx, sc, exp, dictionary, smask)
+    elif generated:
+        dictionary.close()
     return out

@@ -1,9 +1,13 @@
 #!/bin/bash
-# Session 35: compute-sanitizer racecheck / synccheck over smoke(); memcheck over the whole GPU suite.
+# Session 37: eight GPUs - the N = 8 bench with the full-size configurations 4, 5 and 5-generated.
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool synccheck --error-exitcode 9 --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s35_synccheck_smoke.log 2>&1
-echo "synccheck smoke exit $?"; grep -E "ERROR SUMMARY|smoke ok|Error|Barrier|barrier" gpurun_out/s35_synccheck_smoke.log | head -10
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s35_racecheck_smoke.log 2>&1
-echo "racecheck smoke exit $?"; grep -E "RACECHECK SUMMARY|ERROR SUMMARY|smoke ok|hazard|Race" gpurun_out/s35_racecheck_smoke.log | head -20
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests -m gpu -q -x > gpurun_out/s35_memcheck_all.log 2>&1
-echo "memcheck all exit $?"; grep -E "ERROR SUMMARY|Invalid|passed|failed|Error" gpurun_out/s35_memcheck_all.log | head -20
+nvidia-smi -L | wc -l
+timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu > gpurun_out/s37_bench_n8.json 2> gpurun_out/s37_bench_n8.err
+echo "bench n8 exit $?"; python - <<'PY'
+import json
+for l in open('gpurun_out/s37_bench_n8.json'):
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step','n_gpus','e2e','e2e_generated','parity') if k in d}); print(json.dumps(d.get('extra')))
+PY
+tail -3 gpurun_out/s37_bench_n8.err
