@@ -179,3 +179,70 @@ def test_projection_with_one_pc_per_rotation(ctx, golden):
     pcs = np.array([0.5, 0.3, 0.6]) + np.random.default_rng(1).normal(scale=0.03, size=(300, 3))
     many = kb.get_patterns(mu32, ml32, rot, pcs=pcs, om_detector_to_sample=z["om"], detector_shape=(nrows, ncols))
     _close(many.reshape(300, -1), po.project_patterns_varying_pc(rot, pcs, nrows, ncols, z["om"], mu32, ml32))
+
+
+def test_own_arithmetic_equals_math_library_version(ctx):
+    """The projection kernel's own Newton / polynomial sequences (default) against the CUDA math
+    library version of the same pixel (KDI_OPT_PROJECT_LIBM): float32 patterns within one ulp and
+    almost everywhere identical - for random rotations, for the symmetric rotations whose terms
+    cancel exactly (poles, hemisphere boundary, |x| == |y| diagonals), for a float64 master pattern
+    (32-byte tap elements), for quaternions that are not unit (the normalisation's long way) and
+    with the per-pattern rescale."""
+    mu, ml = po.synthetic_master_pattern(301, seed=7)
+    dc = po.direction_cosines_fixed_pc([-0.9, 0.85, -0.7, 0.95], 0.5, 48, 52, po.tilted_detector_matrix(70.0))
+    # direction cosines that hit the poles and the diagonals exactly
+    special = np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [-1, 0, 0], [0, -1, 0],
+                        [np.sqrt(0.5), np.sqrt(0.5), 0], [np.sqrt(0.5), -np.sqrt(0.5), 0],
+                        [1 / np.sqrt(3)] * 3, [0.6, 0.0, 0.8], [0.0, 0.6, -0.8]], dtype=np.float64)
+    dc = np.concatenate([dc, special])
+    s = np.sqrt(0.5)
+    sym = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1], [s, s, 0, 0], [s, 0, s, 0], [s, 0, 0, s],
+                    [0.5, 0.5, 0.5, 0.5], [0.5, -0.5, 0.5, -0.5], [0, s, s, 0]], dtype=np.float64)
+    rot = np.concatenate([sym, po.random_rotations(400, seed=11)])
+    scaled = rot * np.linspace(0.7, 1.4, rot.shape[0])[:, None]  # not unit: v / |v| has to do the work
+    cases = [
+        (ctx.master_pattern(mu, ml, dc), rot, 0.995),
+        (ctx.master_pattern(mu.astype(np.float64), ml.astype(np.float64), dc), rot, 0.995),
+        (ctx.master_pattern(mu, ml, dc), scaled, 0.995),
+        (ctx.master_pattern(mu, ml, dc, rescale=True, out_min=-1.0, out_max=1.0), rot, 0.97),
+    ]
+    try:
+        for mp, r, min_identical in cases:
+            ctx.set_option(_lib.OPT_PROJECT_LIBM, 1)
+            lib = ctx.project_patterns(mp, r)
+            ctx.set_option(_lib.OPT_PROJECT_LIBM, 0)
+            own = ctx.project_patterns(mp, r)
+            assert np.isfinite(own).all()
+            _close(own, lib, min_identical=min_identical)
+            mp.close()
+        # and against the oracle (NumPy float64) on the symmetric rotations
+        mp = ctx.master_pattern(mu, ml, dc)
+        _close(ctx.project_patterns(mp, sym), po.project_patterns(sym, dc, mu, ml), min_identical=0.99)
+        mp.close()
+    finally:
+        ctx.set_option(_lib.OPT_PROJECT_LIBM, 0)
+
+
+def test_generated_dictionary_schedules_agree(ctx):
+    """A generated dictionary projected in one piece on the second stream (default), split into a
+    quarter + three quarters (KDI_OPT_EARLY_SPLIT = 2) and prepared before anything else
+    (KDI_OPT_EARLY_SPLIT = 0): identical results."""
+    import torch
+
+    ctx.set_signal_mask(None)
+    mu, ml = po.synthetic_master_pattern(201, seed=3)
+    dc = po.direction_cosines_fixed_pc([-0.9, 0.85, -0.7, 0.95], 0.5, 30, 30, po.tilted_detector_matrix(70.0))
+    rot = po.random_rotations(20000, seed=2)
+    mp = ctx.master_pattern(mu, ml, dc)
+    exp = orc.synthetic_experimental(2500, (30, 30), seed=5)  # host rows: uploaded beside the projection
+    res = {}
+    try:
+        for mode in (1, 2, 0):
+            ctx.set_option(_lib.OPT_EARLY_SPLIT, mode)
+            res[mode] = ctx.dictionary_indexing_projected(exp, 2500, mp, rot, _lib.KDI_NCC, 20)
+            res[(mode, "dev")] = ctx.dictionary_indexing_projected(torch.from_numpy(exp).cuda(), 2500, mp, rot, _lib.KDI_NCC, 20)
+    finally:
+        ctx.set_option(_lib.OPT_EARLY_SPLIT, 1)
+    for key in res:
+        assert np.array_equal(res[key][0], res[1][0]) and np.array_equal(res[key][1], res[1][1]), key
+    mp.close()

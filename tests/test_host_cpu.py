@@ -603,3 +603,34 @@ def test_division_by_the_row_norm_through_the_fma_sequence_is_exact(tmp_path):
     f.argtypes = [ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     assert f(20_000_000, -30, 30, 60) == 0   # the whole admitted range
     assert f(20_000_000, -8, 8, 24) == 0     # where real rows live
+
+
+def test_atan_polynomial_of_the_projection_kernel():
+    """The odd polynomial the projection kernel uses for atan (kdi_project_dev.cuh, `kAtanC`), evaluated
+    here in float64 exactly as the kernel evaluates it - Horner in r^2 with fused multiply-adds being at
+    least as accurate as NumPy's separate operations - together with the reduction
+    atan(a / b) = pi / 4 + atan((a - b) / (a + b)) for a > tan(pi / 8) b: within 3e-16 of NumPy's arctan
+    over [0, 1], so the Lambert coordinates stay at float64 rounding level."""
+    import re
+
+    src = open(os.path.join(ROOT, "kikuchipy_b200", "csrc", "kdi_project_dev.cuh")).read()
+    body = src[src.index("kAtanC[11] = {"):]
+    body = body[: body.index("};")]
+    coef = [float.fromhex(h) for h in re.findall(r"-?0x1\.[0-9a-f]+p[+-]\d+", body)]
+    assert len(coef) == 11 and coef[0] == 1.0
+    rng = np.random.default_rng(0)
+    b = rng.uniform(0.1, 10.0, 400_000)
+    a = b * np.concatenate([rng.uniform(0.0, 1.0, 399_990), [0.0, 1.0, np.tan(np.pi / 8), 0.41421356237309503, 0.5, 1e-300 / 0.1, 1e-9, 0.9999999999, 0.4142135623730951, 0.25]])
+    red = a > 0.41421356237309504880 * b
+    rn = np.where(red, a - b, a)
+    rd = np.where(red, a + b, b)
+    r = rn / rd
+    u = r * r
+    p = np.full_like(u, coef[10])
+    for c in coef[9::-1]:
+        p = p * u + c
+    got = r * p + np.where(red, 0.78539816339744830962, 0.0)
+    want = np.arctan(a / b)
+    err = np.abs(got - want)
+    assert np.all(err <= 3e-16 + 3e-16 * want), float(err.max())
+    assert np.abs(np.abs(r).max()) <= 0.41421356237309515

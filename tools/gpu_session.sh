@@ -1,13 +1,5 @@
 #!/bin/bash
-# Session 38: A/B of the result copy-out (pinned ring vs the driver's staging) on the host-input legs.
+# Session 40: new projection tests (own arithmetic vs math library, schedules of a generated dictionary).
 mkdir -p gpurun_out
-for v in 0 1 0 1; do
-KDI_COPY_OUT_DIRECT=$v timeout 600 python bench.py --steps 5 --warmup 3 --e2e-steps 8 --no-cpu --no-extras --no-generated > gpurun_out/s38_bench_$v.json 2> gpurun_out/s38_bench_$v.err
-python - <<PY
-import json
-for l in open('gpurun_out/s38_bench_$v.json'):
-    l=l.strip()
-    if l.startswith('{'):
-        d=json.loads(l); print("direct=$v", round(d['e2e']['ms_per_step'],2), round(d['e2e_pageable']['ms_per_step'],2))
-PY
-done
+timeout 900 python -m pytest tests/test_gpu_projection.py -m gpu -q > gpurun_out/s40_pytest.log 2>&1
+echo "pytest exit $?"; tail -30 gpurun_out/s40_pytest.log
