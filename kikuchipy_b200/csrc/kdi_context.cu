@@ -475,6 +475,7 @@ int kdi_destroy(kdi_ctx* ctx) {
   kdi_pool_trim(ctx, 0);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
+  if (ctx->gemm_li) cudaFree(ctx->gemm_li);
   if (ctx->d_cols) cudaFree(ctx->d_cols);
   if (ctx->d_runs) cudaFree(ctx->d_runs);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);

@@ -14,7 +14,10 @@
 //   warp 1   MMA issuer     tcgen05.mma kind::f16, fp32 accumulators in TMEM (2 x 256 columns,
 //                           double-buffered so the epilogue of tile i overlaps the MMAs of i+1)
 //   warps 2-5 epilogue      tcgen05.ld (TMEM lane = experimental row => one thread owns one row),
-//                           threshold filter + per-row candidate list in shared memory
+//                           threshold filter + per-row candidate list in shared memory (kc >= 64: the
+//                           scores in shared memory, the indices - written on insertion, read once at
+//                           the end of the strip - in an L2-resident block per SM, which leaves room
+//                           for one more pipeline stage)
 // A work unit is (block of 128*CG experimental rows) x (strip of `strip_tiles` N tiles); the row
 // block keeps its candidate list in shared memory for the whole strip and publishes its
 // kc-th best score to a global per-row threshold (atomicMax) so later strips of the same rows
@@ -36,6 +39,16 @@ using namespace kdi;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kABytes = KDI_TILE_M * KDI_TILE_K * 2;  // 16 KB
+constexpr int kLiBlocks = 512;  // blocks of the index scratch: one per SM id (%smid < %nsmid, 160 on this die)
+
+// bytes of the candidate list that live in shared memory
+__host__ __device__ constexpr int list_smem_bytes(int kc, int mode) { return mode != 0 ? 0 : kc * KDI_TILE_M * (kc >= 64 ? 4 : 8); }
+
+__device__ __forceinline__ uint32_t sm_id() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
 
 struct GemmParams {
   int64_t M, N;
@@ -57,6 +70,7 @@ struct GemmParams {
   int l2_policy;  // cache hints of the A / B tile loads (KDI_OPT_L2_POLICY)
   uint2* cand;
   uint32_t* thr;
+  uint32_t* li_scratch;  // kc >= 64: kLiBlocks blocks of kc * 128 indices (one per SM id)
   float* out;  // MODE 1
   // optional: n_tiles readiness counters of the dictionary, word n_tiles = "all ready", words
   // n_tiles + 1 .. + 4 = diagnostics of a wait that timed out (flag, tile, counter, needed)
@@ -96,7 +110,8 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int kBRows = KDI_TILE_N / CG;  // dictionary rows this CTA stages per tile
   constexpr int kBBytes = kBRows * KDI_TILE_K * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kListBytes = (MODE == 0) ? KC * KDI_TILE_M * 8 : 0;
+  constexpr int kListBytes = list_smem_bytes(KC, MODE);
+  constexpr bool kIdxGlobal = MODE == 0 && KC >= 64;
 
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte alignment
@@ -104,7 +119,10 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stages = p.stages;
   float* ls = reinterpret_cast<float*>(smem + (size_t)stages * kStageBytes);
-  uint32_t* li = reinterpret_cast<uint32_t*>(ls + KC * KDI_TILE_M);
+  // (one GEMM CTA per SM at a time - the shared memory allows no second one - so the SM id names a private
+  // block whatever launches overlap)
+  uint32_t* li = kIdxGlobal ? p.li_scratch + (size_t)(sm_id() % kLiBlocks) * (KC * KDI_TILE_M)
+                            : reinterpret_cast<uint32_t*>(ls + KC * KDI_TILE_M);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * kStageBytes + kListBytes);
   // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base word
   const uint32_t bar_full = smem_u32(bars);
@@ -447,7 +465,7 @@ int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
                    const CUtensorMap& tmB, const GemmParams& p) {
   constexpr int kBBytes = (KDI_TILE_N / CG) * KDI_TILE_K * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kListBytes = (MODE == 0) ? KC * KDI_TILE_M * 8 : 0;
+  constexpr int kListBytes = list_smem_bytes(KC, MODE);
   const size_t smem = 1024 + (size_t)p.stages * kStageBytes + kListBytes + (2 * p.stages + 4) * 8 + 16;
   auto kern = kdi_gemm_kernel<CG, KC, MODE>;
   KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -486,7 +504,7 @@ int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
 
 int stages_for(int cg, int kc, int mode) {
   const int stage = kABytes + (KDI_TILE_N / cg) * KDI_TILE_K * 2;
-  const int list = mode == 0 ? kc * KDI_TILE_M * 8 : 0;
+  const int list = list_smem_bytes(kc, mode);
   const int budget = 232448 - 1024 - list - 256;
   int s = budget / stage;
   if (s > 8) s = 8;
@@ -505,7 +523,7 @@ int kdi_gemm_kc_for(int keep_n) {
 // shared memory per SM that a launch with this plan leaves to other kernels' CTAs
 int64_t kdi_gemm_free_smem(const kdi_ctx* ctx, const kdi_gemm_plan* plan) {
   const int64_t stage = kABytes + (KDI_TILE_N / plan->cta_group) * KDI_TILE_K * 2;
-  const int64_t used = 1024 + (int64_t)plan->stages * stage + (int64_t)plan->kc * KDI_TILE_M * 8 + (2 * plan->stages + 4) * 8 + 16;
+  const int64_t used = 1024 + (int64_t)plan->stages * stage + list_smem_bytes(plan->kc, 0) + (2 * plan->stages + 4) * 8 + 16;
   return (int64_t)ctx->smem_per_sm - (used + 1024);  // 1 KB per CTA is reserved by the system
 }
 
@@ -620,6 +638,22 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   p.thr = thr;
   p.out = nullptr;
   p.ready = ready;
+  if (plan->kc >= 64) {
+    const size_t need = (size_t)kLiBlocks * plan->kc * KDI_TILE_M * sizeof(uint32_t);
+    if (ctx->gemm_li_bytes < need) {
+      // (grown only between jobs of different keep_n: nothing may still be using the old block)
+      KDI_CUDA(ctx, cudaDeviceSynchronize());
+      if (ctx->gemm_li) cudaFree(ctx->gemm_li);
+      ctx->gemm_li = nullptr;
+      ctx->gemm_li_bytes = 0;
+      if (cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_li), need) != cudaSuccess) {
+        cudaGetLastError();
+        return kdi_fail(ctx, KDI_ENOMEM, "candidate index scratch of %zu bytes failed", need);
+      }
+      ctx->gemm_li_bytes = need;
+    }
+    p.li_scratch = ctx->gemm_li;
+  }
   if (cg == 1 && plan->kc == 32) return launch_variant<1, 32, 0>(ctx, stream, tmA, tmB, p);
   if (cg == 1 && plan->kc == 64) return launch_variant<1, 64, 0>(ctx, stream, tmA, tmB, p);
   if (cg == 2 && plan->kc == 32) return launch_variant<2, 32, 0>(ctx, stream, tmA, tmB, p);
