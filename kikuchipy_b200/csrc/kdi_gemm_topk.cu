@@ -70,6 +70,7 @@ struct GemmParams {
   int l2_policy;  // cache hints of the A / B tile loads (KDI_OPT_L2_POLICY)
   uint2* cand;
   uint32_t* thr;
+  int no_insert;         // measurement aid (KDI_GEMM_NO_INSERT=1): nothing passes the filter - the cost of the bare GEMM
   uint32_t* li_scratch;  // kc >= 64: kLiBlocks blocks of kc * 128 indices (one per SM id)
   float* out;  // MODE 1
   // optional: n_tiles readiness counters of the dictionary, word n_tiles = "all ready", words
@@ -287,7 +288,7 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int cnt = 0, minpos = 0;
       float lmin = -INFINITY;     // smallest entry of a full list
       float gthr = -INFINITY;     // last value read from / published to the global threshold
-      float thr = valid ? -INFINITY : INFINITY;
+      float thr = (valid && !p.no_insert) ? -INFINITY : INFINITY;
       // the list is kept as KC / 8 groups of 8 slots with the minimum (and its slot) of every group in
       // registers: replacing the list minimum re-scans ONE group (8 shared-memory loads) and takes
       // the minimum of the group minima, instead of re-scanning all KC slots
@@ -620,6 +621,8 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   {  // KDI_GEMM_FULL_K=1: issue the padding-only MMA steps too (A/B measurements)
     static const bool full_k = getenv("KDI_GEMM_FULL_K") != nullptr && atoi(getenv("KDI_GEMM_FULL_K")) != 0;
     if (full_k) p.k_last_steps = KDI_TILE_K / 16;
+    static const bool no_insert = getenv("KDI_GEMM_NO_INSERT") != nullptr && atoi(getenv("KDI_GEMM_NO_INSERT")) != 0;
+    p.no_insert = no_insert;
   }
   p.m_blocks = mb_count;
   p.mb0 = mb0;
