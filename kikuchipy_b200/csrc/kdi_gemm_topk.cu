@@ -16,7 +16,7 @@
 //   warps 2-5 epilogue      tcgen05.ld (TMEM lane = experimental row => one thread owns one row),
 //                           threshold filter + per-row candidate list in shared memory (kc >= 64: the
 //                           scores in shared memory, the indices - written on insertion, read once at
-//                           the end of the strip - in an L2-resident block per SM, which leaves room
+//                           the end of the strip - in an L2-resident block per CTA, which leaves room
 //                           for one more pipeline stage)
 // A work unit is (block of 128*CG experimental rows) x (strip of `strip_tiles` N tiles); the row
 // block keeps its candidate list in shared memory for the whole strip and publishes its
@@ -39,16 +39,11 @@ using namespace kdi;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kABytes = KDI_TILE_M * KDI_TILE_K * 2;  // 16 KB
-constexpr int kLiBlocks = 512;  // blocks of the index scratch: one per SM id (%smid < %nsmid, 160 on this die)
+constexpr int kLiBlocks = 512;  // blocks of the index scratch (more than the CTAs of two launches)
 
 // bytes of the candidate list that live in shared memory
 __host__ __device__ constexpr int list_smem_bytes(int kc, int mode) { return mode != 0 ? 0 : kc * KDI_TILE_M * (kc >= 64 ? 4 : 8); }
 
-__device__ __forceinline__ uint32_t sm_id() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
-  return r;
-}
 
 struct GemmParams {
   int64_t M, N;
@@ -71,7 +66,8 @@ struct GemmParams {
   uint2* cand;
   uint32_t* thr;
   int no_insert;         // measurement aid (KDI_GEMM_NO_INSERT=1): nothing passes the filter - the cost of the bare GEMM
-  uint32_t* li_scratch;  // kc >= 64: kLiBlocks blocks of kc * 128 indices (one per SM id)
+  uint32_t* li_scratch;  // kc >= 64: kLiBlocks blocks of kc * 128 indices, handed out by ticket
+  uint32_t* li_ticket;
   float* out;  // MODE 1
   // optional: n_tiles readiness counters of the dictionary, word n_tiles = "all ready", words
   // n_tiles + 1 .. + 4 = diagnostics of a wait that timed out (flag, tile, counter, needed)
@@ -120,10 +116,6 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stages = p.stages;
   float* ls = reinterpret_cast<float*>(smem + (size_t)stages * kStageBytes);
-  // (one GEMM CTA per SM at a time - the shared memory allows no second one - so the SM id names a private
-  // block whatever launches overlap)
-  uint32_t* li = kIdxGlobal ? p.li_scratch + (size_t)(sm_id() % kLiBlocks) * (KC * KDI_TILE_M)
-                            : reinterpret_cast<uint32_t*>(ls + KC * KDI_TILE_M);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * kStageBytes + kListBytes);
   // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base word
   const uint32_t bar_full = smem_u32(bars);
@@ -131,6 +123,7 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t bar_tfull = bar_empty + 8u * stages;
   const uint32_t bar_tempty = bar_tfull + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  uint32_t* li_slot = tmem_slot + 1;  // number of this CTA's block of the index scratch (kc >= 64)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,6 +143,9 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(bar_tempty + 8u * a, 4 * CG);  // one arrive per epilogue warp of each CTA
     }
     fence_mbar_init();
+    // a ticket names the block: at most two launches (2 x 148 persistent CTAs) are alive at any time - the
+    // launches of a job alternate between two streams - so tickets 512 apart never meet
+    if constexpr (kIdxGlobal) *li_slot = atomicAdd(p.li_ticket, 1u) % kLiBlocks;
   }
   if (warp == 1) {
     tmem_alloc<CG>(smem_u32(tmem_slot), kTmemCols);
@@ -159,6 +155,8 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  uint32_t* li = reinterpret_cast<uint32_t*>(ls + KC * KDI_TILE_M);
+  if constexpr (kIdxGlobal) li = p.li_scratch + (size_t)(*reinterpret_cast<volatile uint32_t*>(li_slot)) * (KC * KDI_TILE_M);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -649,13 +647,15 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
       if (ctx->gemm_li) cudaFree(ctx->gemm_li);
       ctx->gemm_li = nullptr;
       ctx->gemm_li_bytes = 0;
-      if (cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_li), need) != cudaSuccess) {
+      if (cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_li), need + 256) != cudaSuccess) {
         cudaGetLastError();
         return kdi_fail(ctx, KDI_ENOMEM, "candidate index scratch of %zu bytes failed", need);
       }
       ctx->gemm_li_bytes = need;
+      KDI_CUDA(ctx, cudaMemset(reinterpret_cast<uint8_t*>(ctx->gemm_li) + need, 0, 256));  // the ticket counter
     }
     p.li_scratch = ctx->gemm_li;
+    p.li_ticket = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ctx->gemm_li) + ctx->gemm_li_bytes);
   }
   if (cg == 1 && plan->kc == 32) return launch_variant<1, 32, 0>(ctx, stream, tmA, tmB, p);
   if (cg == 1 && plan->kc == 64) return launch_variant<1, 64, 0>(ctx, stream, tmA, tmB, p);
