@@ -89,10 +89,10 @@ __device__ __forceinline__ double project_pixel(const P& p, const double (&m)[9]
 // two branches of the Lambert projection diverge inside a warp), a division in each, sqrt(), rsqrt(), with
 // their special-case paths.  Here: one division for both branches, seeded by the hardware's 20-bit
 // reciprocal and finished by a cubic Newton step + one residual correction; the same for the square root;
-// an odd minimax polynomial of 11 terms for atan on |r| <= tan(pi/8) after the reduction
+// an odd polynomial of 11 terms (near-minimax) for atan on |r| <= tan(pi/8) after the reduction
 // atan(a/b) = pi/4 + atan((a - b)/(a + b)), folded into the one division; the normalisation of the rotated
 // vector as a Taylor step (it is a unit vector rotated by a unit quaternion: |n^2 - 1| ~ 1e-16); bilinear
-// blend as three lerps.  Every intermediate stays within a few ulp of float64 of the reference's value
+// blend as three lerps over ONE 16-byte load of the pixel's four taps (tap tables, kdi_master_pattern).  Every intermediate stays within a few ulp of float64 of the reference's value
 // (the reference itself is compiled with fastmath and is no better defined), and the float32 results
 // agree with the goldens exactly as often as the library version's do (tests/test_gpu_projection.py).
 // `m2`: rotation products with the factor 2 folded into the off-diagonal terms (exact).
@@ -139,9 +139,9 @@ __device__ __forceinline__ double abs_bits(double x) {
 }
 }  // namespace kdi_proj
 
-// In two halves, so that a caller can keep the four master-pattern loads of one pixel in flight while it
-// computes the coordinates of the next (the loads are L2 gathers, ~1 us each way on this part):
-// `..._fetch` ends with the loads issued, `..._blend` consumes them.
+// In two halves, so that a caller can keep the tap load of one pixel in flight while it computes the
+// coordinates of the next (the loads are L2 gathers, several hundred cycles each): `..._fetch` ends with
+// the load issued, `..._blend` consumes it.
 template <typename MT>
 struct kdi_lean_taps {
   double di, dj;
