@@ -1,7 +1,13 @@
 #!/bin/bash
-# Session 45: index scratch handed out by ticket - parity suite, keep_n = 100 timing.
+# Session 47: register-resident gather normalise for masked rows - parity, then BASELINE configs[2] A/B.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/s45_pytest.log 2>&1
-echo "pytest exit $?"; tail -3 gpurun_out/s45_pytest.log
-env M=20000 N=100000 KEEP=100 ROUNDS=3 REPS=2 SETTINGS="split=1" timeout 900 python tools/schedule_sweep.py 2>&1 | tail -1
-env M=100000 N=37500 KEEP=50 ROUNDS=3 REPS=2 SETTINGS="split=1" timeout 900 python tools/schedule_sweep.py 2>&1 | tail -1
+timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/s47_pytest.log 2>&1
+echo "pytest exit $?"; tail -4 gpurun_out/s47_pytest.log
+for regs in 1 0 1 0; do
+echo "KDI_OPT_GATHER_REGS=$regs"
+env KDI_TIMELINE=1 CONFIG=3 SAMPLE64=64 OPTS="23=$regs" timeout 600 python tools/config_timeline.py > gpurun_out/s47_c3_regs$regs.txt 2>&1
+grep "normalize" gpurun_out/s47_c3_regs$regs.txt | tail -2
+tail -1 gpurun_out/s47_c3_regs$regs.txt | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['rank0_stage_ms'], d['checks'])"
+done
