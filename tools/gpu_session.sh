@@ -1,12 +1,11 @@
 #!/bin/bash
-# Session 48: staged prepare kernel copying kept columns run by run - parity, then BASELINE configs[2] A/B.
+# What the driver runs at round end on one GPU: whole suite, smoke(), both bench arms with default flags.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/s48_pytest.log 2>&1
-echo "pytest exit $?"; tail -4 gpurun_out/s48_pytest.log
-for cols in 0 1 0 1; do
-echo "KDI_OPT_STAGED_COLS=$cols"
-env KDI_TIMELINE=1 CONFIG=3 SAMPLE64=64 OPTS="23=$cols" timeout 600 python tools/config_timeline.py > gpurun_out/s48_c3_cols$cols.txt 2>&1
-tail -1 gpurun_out/s48_c3_cols$cols.txt | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['rank0_stage_ms'], d['checks']['f64_rows_identical'])"
-done
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/final_pytest.log 2>&1
+echo "pytest exit $?"; tail -3 gpurun_out/final_pytest.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1
+echo "smoke exit $?"; tail -2 gpurun_out/final_smoke.log
+timeout 900 python bench.py --impl reference > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err
+echo "reference arm exit $?"; tail -1 gpurun_out/final_bench_ref.json | cut -c1-300
+timeout 1200 python bench.py > gpurun_out/final_bench_n1.json 2> gpurun_out/final_bench_n1.err
+echo "bench exit $?"; tail -1 gpurun_out/final_bench_n1.json | cut -c1-400
