@@ -121,6 +121,12 @@ extern "C" {
 #define KDI_OPT_DIV_DOUBLE 20    /* 1 = the prepare kernels divide by the row norm through the double reciprocal
                                    everywhere; 0 (default) = through the float32 FMA sequence wherever that is exact
                                    (rows in the normal range; bit-identical results, no conversions)           */
+#define KDI_OPT_GEMM_DUAL 23      /* the 512 x 256 tile of the tensor-core kernel: CTA pairs with 32-entry candidate
+                                   lists give every CTA two blocks of 128 experimental rows and both halves of TMEM as
+                                   accumulators - a quarter fewer bytes per flop from L2, but no overlap of a tile's
+                                   epilogue with the next tile's MMAs.  1 (default) = for K loops of at least 96 blocks
+                                   of 64 (more than ~6 100 kept pixels), where it is faster; 0 = never (256 x 256 tiles
+                                   with two accumulator buffers); 2 = wherever it fits.  Identical results             */
 #define KDI_OPT_PROJECT_LIBM 22   /* 1 = the dictionary-generation kernel evaluates atan, the square roots and the
                                    division of the Lambert projection with the CUDA math library (round-1
                                    arithmetic, ~340 instructions per pixel); 0 (default) = with its own seeded

@@ -50,6 +50,7 @@ OPT_EARLY_SPLIT = 19
 OPT_DIV_DOUBLE = 20
 OPT_DICT_VIEW = 21
 OPT_PROJECT_LIBM = 22
+OPT_GEMM_DUAL = 23
 
 REFINE_ORI, REFINE_PC, REFINE_ORI_PC = 0, 1, 2
 

@@ -570,6 +570,10 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
       if (value != 0 && value != 1 && value != 2) return kdi_fail(ctx, KDI_EINVAL, "dict_view must be 0, 1 or 2");
       ctx->dict_view = (int)value;
       return KDI_OK;
+    case KDI_OPT_GEMM_DUAL:
+      if (value != 0 && value != 1 && value != 2) return kdi_fail(ctx, KDI_EINVAL, "gemm_dual must be 0, 1 or 2");
+      ctx->gemm_dual = (int)value;
+      return KDI_OK;
     case KDI_OPT_PROJECT_LIBM:
       ctx->project_libm = value != 0;
       return KDI_OK;

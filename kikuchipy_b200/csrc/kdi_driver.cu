@@ -198,7 +198,7 @@ static int run_overlapped(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* 
   // large partition; gemm_serial keeps every launch on one stream
   cudaStream_t g0 = ctx->part_gemm[0] ? ctx->part_gemm[0] : sm;
   cudaStream_t g1 = ctx->gemm_serial ? g0 : (ctx->part_gemm[1] ? ctx->part_gemm[1] : ctx->gemm_stream2);
-  const int64_t rows_per_mb = (int64_t)KDI_TILE_M * pl.cta_group;
+  const int64_t rows_per_mb = pl.rows_per_block;
   const int n_sb = (int)kdi_ceil_div(pl.m_blocks, pl.superblock);
   const int max_groups = 24;  // bounded by the event pool
   // one launch per L2 super-block of experimental rows, or more (smaller) groups when the

@@ -37,12 +37,16 @@ namespace {
 using namespace kdi;
 
 constexpr int kThreads = 192;
+constexpr int kThreadsDual = 320;  // dual-row-block tile: a second set of four epilogue warps for the second accumulator
 constexpr int kTmemCols = 512;
 constexpr int kABytes = KDI_TILE_M * KDI_TILE_K * 2;  // 16 KB
 constexpr int kLiBlocks = 512;  // blocks of the index scratch (more than the CTAs of two launches)
 
 // bytes of the candidate list that live in shared memory
-__host__ __device__ constexpr int list_smem_bytes(int kc, int mode) { return mode != 0 ? 0 : kc * KDI_TILE_M * (kc >= 64 ? 4 : 8); }
+// (dual: two row blocks per CTA - two score lists, the indices always in the scratch)
+__host__ __device__ constexpr int list_smem_bytes(int kc, int mode, bool dual = false) {
+  return mode != 0 ? 0 : (dual ? 2 * kc * KDI_TILE_M * 4 : kc * KDI_TILE_M * (kc >= 64 ? 4 : 8));
+}
 
 
 struct GemmParams {
@@ -100,15 +104,24 @@ __device__ __forceinline__ void decode_unit(const GemmParams& p, int64_t u, int&
 }
 
 // MODE 0: candidate selection; MODE 1: write the full block (validation only)
-template <int CG, int KC, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+// DUAL (CTA pairs, kc 32): every CTA holds TWO blocks of 128 experimental rows and both halves of TMEM as
+// their accumulators - a pair computes a 512 x 256 tile, the dictionary tile in shared memory feeds two MMAs
+// per K step.  A quarter fewer bytes per flop come from L2 (the tile shape cuBLAS uses on this part); the
+// price is the second accumulator buffer: the epilogue of a tile no longer overlaps the MMAs of the next
+// (two sets of four epilogue warps drain the two accumulators side by side to keep that gap short).
+template <int CG, int KC, int MODE, bool DUAL = false>
+__global__ void __launch_bounds__(DUAL ? kThreadsDual : kThreads, 1)
 kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmParams p) {
+  static_assert(!DUAL || (CG == 2 && MODE == 0), "the dual-row-block tile is built for CTA pairs");
+  constexpr int kAccs = DUAL ? 2 : 1;      // row blocks (accumulators) per CTA and tile
   constexpr int kBRows = KDI_TILE_N / CG;  // dictionary rows this CTA stages per tile
   constexpr int kBBytes = kBRows * KDI_TILE_K * 2;
-  constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kListBytes = list_smem_bytes(KC, MODE);
-  constexpr bool kIdxGlobal = MODE == 0 && KC >= 64;
+  constexpr int kAStage = kABytes * kAccs;
+  constexpr int kStageBytes = kAStage + kBBytes;
+  constexpr int kListBytes = list_smem_bytes(KC, MODE, DUAL);
+  constexpr bool kIdxGlobal = MODE == 0 && (KC >= 64 || DUAL);
+  constexpr int kListEntries = KC * KDI_TILE_M;  // per row block
 
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte alignment
@@ -140,7 +153,7 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8u * a, 1);
-      mbar_init(bar_tempty + 8u * a, 4 * CG);  // one arrive per epilogue warp of each CTA
+      mbar_init(bar_tempty + 8u * a, 4 * CG * kAccs);  // one arrive per epilogue warp of each CTA
     }
     fence_mbar_init();
     // a ticket names the block: at most two launches (2 x 148 persistent CTAs) are alive at any time - the
@@ -156,7 +169,7 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   uint32_t* li = reinterpret_cast<uint32_t*>(ls + KC * KDI_TILE_M);
-  if constexpr (kIdxGlobal) li = p.li_scratch + (size_t)(*reinterpret_cast<volatile uint32_t*>(li_slot)) * (KC * KDI_TILE_M);
+  if constexpr (kIdxGlobal) li = p.li_scratch + (size_t)(*reinterpret_cast<volatile uint32_t*>(li_slot)) * (kAccs * kListEntries);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -178,7 +191,7 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         decode_unit(p, u, mb, strip);
         const int t0 = strip * p.strip_tiles;
         const int t1 = min(t0 + p.strip_tiles, p.n_tiles);
-        const int a_row = (mb * CG + (int)rank) * KDI_TILE_M;
+        const int a_row = (mb * CG + (int)rank) * (KDI_TILE_M * kAccs);  // (dual: one box of 256 rows)
         const int rot = p.rotate ? mb % (t1 - t0) : 0;
         for (int ti = 0; ti < t1 - t0; ++ti) {
           const int nt = t0 + (ti + rot) % (t1 - t0);
@@ -206,7 +219,7 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
             const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
-            const uint32_t sb_ = sa + kABytes;
+            const uint32_t sb_ = sa + kAStage;
             if constexpr (CG == 1) {
               mbar_arrive_expect_tx(bar_full + 8u * stage, kStageBytes);
               tma_load_2d(sa, &tmA, bar_full + 8u * stage, kb * KDI_TILE_K, a_row, pol_a);
@@ -242,20 +255,24 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int ti = 0; ti < t1 - t0; ++ti) {  // (tile order is irrelevant to the issuer)
           mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)acc * KDI_TILE_N;
+          const uint32_t tmem_d = tmem_base + (DUAL ? 0u : (uint32_t)acc * KDI_TILE_N);
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(bar_full + 8u * stage, phase);
             tc_fence_after();
             const uint32_t sa = smem_base + (uint32_t)stage * kStageBytes;
             const uint64_t da = umma_smem_desc_sw128(sa);
-            const uint64_t db = umma_smem_desc_sw128(sa + kABytes);
+            const uint64_t da1 = umma_smem_desc_sw128(sa + kABytes);  // (dual: the second row block)
+            const uint64_t db = umma_smem_desc_sw128(sa + kAStage);
             // (the K padding of the last block is zero in both operands: the MMAs over 16-wide steps
             // that hold nothing but padding are skipped - 3 of 228 per tile for 60 x 60 patterns)
             const int ksteps = (kb == p.kblocks - 1) ? p.k_last_steps : KDI_TILE_K / 16;
 #pragma unroll
             for (int k = 0; k < KDI_TILE_K / 16; ++k) {
               // advance 16 elements = 32 bytes = 2 descriptor units along K inside the swizzle atom
-              if (k < ksteps) umma_f16<CG>(tmem_d, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+              if (k < ksteps) {
+                umma_f16<CG>(tmem_d, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+                if constexpr (DUAL) umma_f16<CG>(tmem_d + KDI_TILE_N, da1 + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+              }
             }
             if constexpr (CG == 1) umma_commit(bar_empty + 8u * stage);
             else umma_commit_cg2(bar_empty + 8u * stage, 3);
@@ -263,161 +280,183 @@ kdi_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if constexpr (CG == 1) umma_commit(bar_tfull + 8u * acc);
           else umma_commit_cg2(bar_tfull + 8u * acc, 3);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1u;
+          if constexpr (DUAL) {
+            acc_phase ^= 1u;  // one buffer (both halves of TMEM): its barriers flip every tile
+          } else {
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+          }
         }
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, thread = one experimental row =====================
+    // ===================== epilogue: 4 warps, thread = one experimental row (per row block) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     int acc = 0;
     uint32_t acc_phase = 0;
+    // the list is kept as KC / 8 groups of 8 slots with the minimum (and its slot) of every group in
+    // registers: replacing the list minimum re-scans ONE group (8 shared-memory loads) and takes
+    // the minimum of the group minima, instead of re-scanning all KC slots
+    constexpr int kGroups = KC / 8;
+    struct ListState {
+      int cnt, minpos;
+      float lmin;  // smallest entry of a full list
+      float gthr;  // last value read from / published to the global threshold
+      float thr;
+      float gmin[kGroups];
+      int gpos[kGroups];
+    };
     for (int64_t u = cluster_id; u < p.units; u += n_clusters) {
       int mb, strip;
       decode_unit(p, u, mb, strip);
       const int t0 = strip * p.strip_tiles;
       const int t1 = min(t0 + p.strip_tiles, p.n_tiles);
-      const int64_t row = (int64_t)(mb * CG + (int)rank) * KDI_TILE_M + r;
+      // (dual: this CTA's 256 rows are two consecutive blocks of 128; accumulator a belongs to block a and is
+      // drained by epilogue warps 2 + 4 a .. 5 + 4 a)
+      const int a = DUAL ? ((warp - 2) >> 2) : 0;
+      const int64_t row = (int64_t)(mb * CG + (int)rank) * (KDI_TILE_M * kAccs) + a * KDI_TILE_M + r;
       const bool valid = row < p.M;
-
-      int cnt = 0, minpos = 0;
-      float lmin = -INFINITY;     // smallest entry of a full list
-      float gthr = -INFINITY;     // last value read from / published to the global threshold
-      float thr = (valid && !p.no_insert) ? -INFINITY : INFINITY;
-      // the list is kept as KC / 8 groups of 8 slots with the minimum (and its slot) of every group in
-      // registers: replacing the list minimum re-scans ONE group (8 shared-memory loads) and takes
-      // the minimum of the group minima, instead of re-scanning all KC slots
-      constexpr int kGroups = KC / 8;
-      float gmin[kGroups];
-      int gpos[kGroups];
+      float* lsa = ls + a * kListEntries;
+      uint32_t* lia = li + a * kListEntries;
+      ListState L;
+      L.cnt = 0; L.minpos = 0;
+      L.lmin = -INFINITY; L.gthr = -INFINITY;
+      L.thr = (valid && !p.no_insert) ? -INFINITY : INFINITY;
 #pragma unroll
-      for (int g = 0; g < kGroups; ++g) { gmin[g] = INFINITY; gpos[g] = g * 8; }
+      for (int g = 0; g < kGroups; ++g) { L.gmin[g] = INFINITY; L.gpos[g] = g * 8; }
 
       const int rot = p.rotate ? mb % (t1 - t0) : 0;
       for (int ti = 0; ti < t1 - t0; ++ti) {
         const int nt = t0 + (ti + rot) % (t1 - t0);
         mbar_wait(bar_tfull + 8u * acc, acc_phase);
         tc_fence_after();
-        if constexpr (MODE == 0) {
-          if (valid) {
-            gthr = fmaxf(gthr, key_float(__ldcg(p.thr + row)));
-            thr = fmaxf(thr, gthr);
-          }
-        }
         const int ncols = (int)min((int64_t)KDI_TILE_N, p.N - (int64_t)nt * KDI_TILE_N);
-#pragma unroll 1
-        for (int c = 0; c < KDI_TILE_N / 32; ++c) {
-          float v[32];
-          tmem_ld_32x32(tmem_lane + (uint32_t)(acc * KDI_TILE_N + c * 32), v);
-          if (c == KDI_TILE_N / 32 - 1) {
-            // accumulator fully read: hand the TMEM buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (CG == 1) mbar_arrive(bar_tempty + 8u * acc);
-              else mbar_arrive_cluster(bar_tempty + 8u * acc, 0);
+        {
+          if constexpr (MODE == 0) {
+            if (valid) {
+              L.gthr = fmaxf(L.gthr, key_float(__ldcg(p.thr + row)));
+              L.thr = fmaxf(L.thr, L.gthr);
             }
           }
-          const int col0 = c * 32;
-          if (col0 >= ncols) continue;  // warp-uniform
-          if constexpr (MODE == 1) {
-            if (valid) {
-              float* o = p.out + row * p.N + (int64_t)nt * KDI_TILE_N + col0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < ncols) o[j] = v[j];
+          const uint32_t tmem_acc = tmem_lane + (uint32_t)((DUAL ? a : acc) * KDI_TILE_N);
+#pragma unroll 1
+          for (int c = 0; c < KDI_TILE_N / 32; ++c) {
+            float v[32];
+            tmem_ld_32x32(tmem_acc + (uint32_t)(c * 32), v);
+            if (c == KDI_TILE_N / 32 - 1) {
+              // accumulator fully read: hand the TMEM buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (CG == 1) mbar_arrive(bar_tempty + 8u * acc);
+                else mbar_arrive_cluster(bar_tempty + 8u * acc, 0);
+              }
             }
-          } else {
-            if (col0 + 32 > ncols) {
+            const int col0 = c * 32;
+            if (col0 >= ncols) continue;  // warp-uniform
+            if constexpr (MODE == 1) {
+              if (valid) {
+                float* o = p.out + row * p.N + (int64_t)nt * KDI_TILE_N + col0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j >= ncols) v[j] = -INFINITY;
-            }
-            float m = v[0];
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < ncols) o[j] = v[j];
+              }
+            } else {
+              if (col0 + 32 > ncols) {
 #pragma unroll
-            for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-            if (m > thr) {
-              uint32_t hits = 0;
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j >= ncols) v[j] = -INFINITY;
+              }
+              float m = v[0];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) hits |= (v[j] > thr ? 1u : 0u) << j;
-              while (hits) {
-                const int j = __ffs(hits) - 1;
-                hits &= hits - 1;
-                const float s = pick32(v, j);
-                if (s > thr) {
-                  const uint32_t idx = (uint32_t)(nt * KDI_TILE_N + col0 + j);
-                  const int slot = cnt < KC ? cnt : minpos;
-                  ls[slot * KDI_TILE_M + r] = s;
-                  li[slot * KDI_TILE_M + r] = idx;
-                  if (cnt < KC) {
-                    if (++cnt == KC) {  // the list has just become full: minima of all groups
+              for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+              if (m > L.thr) {
+                uint32_t hits = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hits |= (v[j] > L.thr ? 1u : 0u) << j;
+                while (hits) {
+                  const int j = __ffs(hits) - 1;
+                  hits &= hits - 1;
+                  const float sv = pick32(v, j);
+                  if (sv > L.thr) {
+                    const uint32_t idx = (uint32_t)(nt * KDI_TILE_N + col0 + j);
+                    const int slot = L.cnt < KC ? L.cnt : L.minpos;
+                    lsa[slot * KDI_TILE_M + r] = sv;
+                    lia[slot * KDI_TILE_M + r] = idx;
+                    if (L.cnt < KC) {
+                      if (++L.cnt == KC) {  // the list has just become full: minima of all groups
+#pragma unroll
+                        for (int g = 0; g < kGroups; ++g) {
+                          float mn = lsa[(g * 8) * KDI_TILE_M + r];
+                          int mp = g * 8;
+#pragma unroll
+                          for (int qq = 1; qq < 8; ++qq) {
+                            const float x = lsa[(g * 8 + qq) * KDI_TILE_M + r];
+                            if (x < mn) { mn = x; mp = g * 8 + qq; }
+                          }
+                          L.gmin[g] = mn;
+                          L.gpos[g] = mp;
+                        }
+                      }
+                    } else {  // the minimum was replaced: its group only
+                      const int gs = slot >> 3;
+                      float mn = lsa[(gs * 8) * KDI_TILE_M + r];
+                      int mp = gs * 8;
+#pragma unroll
+                      for (int qq = 1; qq < 8; ++qq) {
+                        const float x = lsa[(gs * 8 + qq) * KDI_TILE_M + r];
+                        if (x < mn) { mn = x; mp = gs * 8 + qq; }
+                      }
 #pragma unroll
                       for (int g = 0; g < kGroups; ++g) {
-                        float mn = ls[(g * 8) * KDI_TILE_M + r];
-                        int mp = g * 8;
-#pragma unroll
-                        for (int q = 1; q < 8; ++q) {
-                          const float x = ls[(g * 8 + q) * KDI_TILE_M + r];
-                          if (x < mn) { mn = x; mp = g * 8 + q; }
-                        }
-                        gmin[g] = mn;
-                        gpos[g] = mp;
+                        if (g == gs) { L.gmin[g] = mn; L.gpos[g] = mp; }
                       }
                     }
-                  } else {  // the minimum was replaced: its group only
-                    const int gs = slot >> 3;
-                    float mn = ls[(gs * 8) * KDI_TILE_M + r];
-                    int mp = gs * 8;
+                    if (L.cnt == KC) {
+                      float mn = L.gmin[0];
+                      int mp = L.gpos[0];
 #pragma unroll
-                    for (int q = 1; q < 8; ++q) {
-                      const float x = ls[(gs * 8 + q) * KDI_TILE_M + r];
-                      if (x < mn) { mn = x; mp = gs * 8 + q; }
+                      for (int g = 1; g < kGroups; ++g) {
+                        if (L.gmin[g] < mn) { mn = L.gmin[g]; mp = L.gpos[g]; }
+                      }
+                      L.lmin = mn;
+                      L.minpos = mp;
+                      L.thr = fmaxf(L.thr, mn);
                     }
-#pragma unroll
-                    for (int g = 0; g < kGroups; ++g) {
-                      if (g == gs) { gmin[g] = mn; gpos[g] = mp; }
-                    }
-                  }
-                  if (cnt == KC) {
-                    float mn = gmin[0];
-                    int mp = gpos[0];
-#pragma unroll
-                    for (int g = 1; g < kGroups; ++g) {
-                      if (gmin[g] < mn) { mn = gmin[g]; mp = gpos[g]; }
-                    }
-                    lmin = mn;
-                    minpos = mp;
-                    thr = fmaxf(thr, mn);
                   }
                 }
               }
+              __syncwarp();
             }
-            __syncwarp();
+          }
+          if constexpr (MODE == 0) {
+            // publish a tighter bound for the other strips of this row
+            if (valid && L.cnt == KC && L.lmin > L.gthr) {
+              atomicMax(p.thr + row, float_key(L.lmin));
+              L.gthr = L.lmin;
+            }
           }
         }
-        if constexpr (MODE == 0) {
-          // publish a tighter bound for the other strips of this row
-          if (valid && cnt == KC && lmin > gthr) {
-            atomicMax(p.thr + row, float_key(lmin));
-            gthr = lmin;
-          }
+        if constexpr (DUAL) {
+          acc_phase ^= 1u;
+        } else {
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
       if constexpr (MODE == 0) {
+        const int cnt = L.cnt;
         if (valid) {
           uint2* dst = p.cand + ((size_t)row * p.n_strips + strip) * KC;
 #pragma unroll 4
           for (int i = 0; i < KC; i += 2) {
             uint4 w;
-            w.x = (i < cnt) ? __float_as_uint(ls[i * KDI_TILE_M + r]) : 0xFF800000u;
-            w.y = (i < cnt) ? li[i * KDI_TILE_M + r] : 0xFFFFFFFFu;
-            w.z = (i + 1 < cnt) ? __float_as_uint(ls[(i + 1) * KDI_TILE_M + r]) : 0xFF800000u;
-            w.w = (i + 1 < cnt) ? li[(i + 1) * KDI_TILE_M + r] : 0xFFFFFFFFu;
+            w.x = (i < cnt) ? __float_as_uint(lsa[i * KDI_TILE_M + r]) : 0xFF800000u;
+            w.y = (i < cnt) ? lia[i * KDI_TILE_M + r] : 0xFFFFFFFFu;
+            w.z = (i + 1 < cnt) ? __float_as_uint(lsa[(i + 1) * KDI_TILE_M + r]) : 0xFF800000u;
+            w.w = (i + 1 < cnt) ? lia[(i + 1) * KDI_TILE_M + r] : 0xFFFFFFFFu;
             *reinterpret_cast<uint4*>(dst + i) = w;
           }
         }
@@ -459,14 +498,14 @@ int make_tmap(kdi_ctx* ctx, CUtensorMap* out, const void* base, int64_t rows, in
   return KDI_OK;
 }
 
-template <int CG, int KC, int MODE>
+template <int CG, int KC, int MODE, bool DUAL = false>
 int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
                    const CUtensorMap& tmB, const GemmParams& p) {
   constexpr int kBBytes = (KDI_TILE_N / CG) * KDI_TILE_K * 2;
-  constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kListBytes = list_smem_bytes(KC, MODE);
+  constexpr int kStageBytes = kABytes * (DUAL ? 2 : 1) + kBBytes;
+  constexpr int kListBytes = list_smem_bytes(KC, MODE, DUAL);
   const size_t smem = 1024 + (size_t)p.stages * kStageBytes + kListBytes + (2 * p.stages + 4) * 8 + 16;
-  auto kern = kdi_gemm_kernel<CG, KC, MODE>;
+  auto kern = kdi_gemm_kernel<CG, KC, MODE, DUAL>;
   KDI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // (experiments with SM sharing: see kdi_gemm_carveout_pref)
   // always the full shared-memory carveout: with fewer pipeline stages the kernel would fit the
@@ -482,7 +521,7 @@ int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
   const int64_t n_clusters = p.units < max_clusters ? p.units : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_clusters * CG));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(DUAL ? kThreadsDual : kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -501,9 +540,9 @@ int launch_variant(kdi_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmA,
   return KDI_OK;
 }
 
-int stages_for(int cg, int kc, int mode) {
-  const int stage = kABytes + (KDI_TILE_N / cg) * KDI_TILE_K * 2;
-  const int list = list_smem_bytes(kc, mode);
+int stages_for(int cg, int kc, int mode, bool dual = false) {
+  const int stage = kABytes * (dual ? 2 : 1) + (KDI_TILE_N / cg) * KDI_TILE_K * 2;
+  const int list = list_smem_bytes(kc, mode, dual);
   const int budget = 232448 - 1024 - list - 256;
   int s = budget / stage;
   if (s > 8) s = 8;
@@ -521,8 +560,8 @@ int kdi_gemm_kc_for(int keep_n) {
 
 // shared memory per SM that a launch with this plan leaves to other kernels' CTAs
 int64_t kdi_gemm_free_smem(const kdi_ctx* ctx, const kdi_gemm_plan* plan) {
-  const int64_t stage = kABytes + (KDI_TILE_N / plan->cta_group) * KDI_TILE_K * 2;
-  const int64_t used = 1024 + (int64_t)plan->stages * stage + list_smem_bytes(plan->kc, 0) + (2 * plan->stages + 4) * 8 + 16;
+  const int64_t stage = kABytes * (plan->dual ? 2 : 1) + (KDI_TILE_N / plan->cta_group) * KDI_TILE_K * 2;
+  const int64_t used = 1024 + (int64_t)plan->stages * stage + list_smem_bytes(plan->kc, 0, plan->dual != 0) + (2 * plan->stages + 4) * 8 + 16;
   return (int64_t)ctx->smem_per_sm - (used + 1024);  // 1 KB per CTA is reserved by the system
 }
 
@@ -532,10 +571,18 @@ int kdi_gemm_make_plan(kdi_ctx* ctx, int64_t M, int64_t N, int64_t kp, int keep_
   pl.kc = kdi_gemm_kc_for(keep_n);
   if (pl.kc == 0) return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d too large for the fused path", keep_n);
   pl.cta_group = ctx->cta_group == 2 ? 2 : 1;
-  pl.stages = stages_for(pl.cta_group, pl.kc, 0);
+  // (the 512 x 256 pair tile: CTA pairs, 32-entry lists - two 64-entry lists would cost a pipeline stage -
+  // and enough rows that the coarser row blocks still fill the device)
+  // It pays once the K loop is long enough that the exposed epilogue is small beside it: measured break-even at
+  // 60 x 60 patterns (57 K blocks), +3 % at 80 x 80 and 100 x 100, +9-16 % at the 11 287 kept pixels of BASELINE
+  // configs[2] (profiles/r2_gemm_dual_tile.txt).  KDI_OPT_GEMM_DUAL: 0 never, 1 from 96 K blocks on, 2 always.
+  const bool dual_fits = pl.cta_group == 2 && pl.kc == 32 && M >= 2048;
+  pl.dual = (dual_fits && (ctx->gemm_dual == 2 || (ctx->gemm_dual == 1 && kp / KDI_TILE_K >= 96))) ? 1 : 0;
+  pl.stages = stages_for(pl.cta_group, pl.kc, 0, pl.dual != 0);
   if (ctx->max_stages > 1 && pl.stages > ctx->max_stages) pl.stages = ctx->max_stages;
   if (ctx->post_coresident > 0 && pl.stages > 3) pl.stages -= 1;  // room for post-processing CTAs beside this kernel
-  const int64_t rows_per_block = (int64_t)KDI_TILE_M * pl.cta_group;
+  const int64_t rows_per_block = (int64_t)KDI_TILE_M * pl.cta_group * (pl.dual ? 2 : 1);
+  pl.rows_per_block = (int)rows_per_block;
   pl.m_blocks = (int)kdi_ceil_div(M, rows_per_block);
   pl.n_tiles = (int)kdi_ceil_div(N, KDI_TILE_N);
   const int64_t workers = ctx->sm_count / pl.cta_group;
@@ -559,7 +606,7 @@ int kdi_gemm_make_plan(kdi_ctx* ctx, int64_t M, int64_t N, int64_t kp, int keep_
   int sb = ctx->superblock;
   if (sb <= 0) {
     // keep a super-block of experimental rows (16-bit) within ~48 MB of L2
-    const int64_t block_bytes = (int64_t)KDI_TILE_M * pl.cta_group * kp * 2;
+    const int64_t block_bytes = rows_per_block * kp * 2;
     int64_t max_sb = (48ll << 20) / block_bytes;
     if (max_sb < 1) max_sb = 1;
     const int64_t n_sb = kdi_ceil_div(pl.m_blocks, max_sb);
@@ -609,7 +656,7 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   KDI_TRY(check_operands(ctx, exp, dict));
   const int cg = plan->cta_group;
   CUtensorMap tmA, tmB;
-  KDI_TRY(make_tmap(ctx, &tmA, exp->a16, exp->rows, exp->kp, exp->compute_dtype, KDI_TILE_M));
+  KDI_TRY(make_tmap(ctx, &tmA, exp->a16, exp->rows, exp->kp, exp->compute_dtype, KDI_TILE_M * (plan->dual ? 2 : 1)));
   KDI_TRY(make_tmap(ctx, &tmB, dict->a16, dict->rows, dict->kp, dict->compute_dtype, KDI_TILE_N / cg));
   GemmParams p = {};
   p.M = exp->rows;
@@ -639,8 +686,8 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
   p.thr = thr;
   p.out = nullptr;
   p.ready = ready;
-  if (plan->kc >= 64) {
-    const size_t need = (size_t)kLiBlocks * plan->kc * KDI_TILE_M * sizeof(uint32_t);
+  if (plan->kc >= 64 || plan->dual) {
+    const size_t need = (size_t)kLiBlocks * plan->kc * KDI_TILE_M * (plan->dual ? 2 : 1) * sizeof(uint32_t);
     if (ctx->gemm_li_bytes < need) {
       // (grown only between jobs of different keep_n: nothing may still be using the old block)
       KDI_CUDA(ctx, cudaDeviceSynchronize());
@@ -656,6 +703,10 @@ int kdi_launch_gemm_topk(kdi_ctx* ctx, cudaStream_t stream, const kdi_patterns* 
     }
     p.li_scratch = ctx->gemm_li;
     p.li_ticket = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ctx->gemm_li) + ctx->gemm_li_bytes);
+  }
+  if (plan->dual) {
+    if (cg != 2 || plan->kc != 32) return kdi_fail(ctx, KDI_EINTERNAL, "dual-row-block plan without CTA pairs / 32-entry lists");
+    return launch_variant<2, 32, 0, true>(ctx, stream, tmA, tmB, p);
   }
   if (cg == 1 && plan->kc == 32) return launch_variant<1, 32, 0>(ctx, stream, tmA, tmB, p);
   if (cg == 1 && plan->kc == 64) return launch_variant<1, 64, 0>(ctx, stream, tmA, tmB, p);

@@ -1095,3 +1095,40 @@ def test_float64_scores_of_rows_beyond_the_shared_memory_staging(ctx):
     d = orc.prepare_dictionary(dic.reshape(40, -1), "ncc", None, np.float64)
     want = np.take_along_axis(e @ d.T, cand, axis=1)
     assert np.max(np.abs(got - want)) < 1e-13
+
+
+@pytest.mark.parametrize("M, N, sig, metric", [(2048, 6000, (60, 60), "ncc"), (2100, 30001, (60, 60), "ncc"),
+                                               (5000, 9000, (40, 40), "ndp"), (2600, 4000, (57, 43), "ncc")])
+def test_dual_row_block_tile_equals_default(ctx, M, N, sig, metric):
+    """The 512 x 256 pair tile of the tensor-core kernel (KDI_OPT_GEMM_DUAL = 2: two row blocks per CTA, both
+    halves of TMEM as accumulators) against the 256 x 256 tile: identical indices and scores - ragged row and
+    dictionary counts, row counts that leave the second row block of the last CTA pair empty, K that is not a
+    multiple of 64, both operand types, device-resident and host dictionaries."""
+    import torch
+
+    code = _lib.KDI_NCC if metric == "ncc" else _lib.KDI_NDP
+    exp = orc.synthetic_experimental(M, sig, seed=21)
+    dic = orc.synthetic_dictionary(N, sig, seed=22)
+    exp_d, dic_d = torch.from_numpy(exp).cuda(), torch.from_numpy(dic).cuda()
+    out = {}
+    try:
+        for dual in (0, 2):
+            ctx.set_option(_lib.OPT_GEMM_DUAL, dual)
+            res = []
+            for dt in (0, 1):
+                ctx.set_option(_lib.OPT_COMPUTE_DTYPE, dt)
+                idx = torch.empty((M, 20), dtype=torch.int64, device="cuda")
+                sc = torch.empty((M, 20), dtype=torch.float32, device="cuda")
+                ctx.dictionary_indexing(exp_d, M, dic_d, N, code, 20, out=(idx, sc))
+                res += [idx.cpu().numpy(), sc.cpu().numpy()]
+            ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 0)
+            res += list(ctx.dictionary_indexing(exp, M, dic, N, code, 20))
+            out[dual] = res
+            assert ctx.timings()["gemm_launches"] >= 1
+    finally:
+        ctx.set_option(_lib.OPT_GEMM_DUAL, 1)
+        ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 0)
+    for a, b in zip(out[0], out[2]):
+        assert np.array_equal(a, b)
+    ridx, rsc = orc.dictionary_indexing(exp[:64], dic, metric=metric, keep_n=20)
+    _check(ridx, rsc, out[2][0][:64], out[2][1][:64])

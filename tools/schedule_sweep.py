@@ -14,15 +14,16 @@ import torch
 import kikuchipy_b200 as kb
 from kikuchipy_b200 import _lib
 
-M, N, SIG = int(os.environ.get("M", "10000")), int(os.environ.get("N", "100000")), (60, 60)
+M, N = int(os.environ.get("M", "10000")), int(os.environ.get("N", "100000"))
+SIG = (int(os.environ.get("SY", "60")), int(os.environ.get("SX", "60")))
 KEEP = int(os.environ.get("KEEP", "20"))
 REPS, ROUNDS = int(os.environ.get("REPS", "3")), int(os.environ.get("ROUNDS", "4"))
 O = _lib
 NAMES = {"flags": O.OPT_DEP_FLAGS, "groups": O.OPT_MIN_GROUPS, "post": O.OPT_POST_PER_GROUP, "sms": O.OPT_GEMM_SMS,
          "serial": O.OPT_GEMM_SERIAL, "part": O.OPT_SM_PARTITION, "cores": O.OPT_POST_CORESIDENT, "split": O.OPT_EARLY_SPLIT, "overlap": O.OPT_OVERLAP, "stages": O.OPT_MAX_STAGES,
-         "strip": O.OPT_STRIP_TILES, "sb": O.OPT_SUPERBLOCK, "view": O.OPT_DICT_VIEW, "divd": O.OPT_DIV_DOUBLE}
+         "strip": O.OPT_STRIP_TILES, "sb": O.OPT_SUPERBLOCK, "view": O.OPT_DICT_VIEW, "divd": O.OPT_DIV_DOUBLE, "dual": O.OPT_GEMM_DUAL}
 DEFAULTS = {"flags": 0, "groups": 0, "post": 0, "sms": 0, "serial": 0, "part": 0, "cores": 0, "split": 1, "overlap": 1, "stages": 0, "strip": 0, "sb": 0,
-            "view": 1, "divd": 0}
+            "view": 1, "divd": 0, "dual": 0}
 SETTINGS = os.environ.get(
     "SETTINGS",
     "split=1;split=0;split=0,groups=4;flags=1;overlap=0").split(";")
