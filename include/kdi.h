@@ -125,7 +125,7 @@ extern "C" {
                                    lists give every CTA two blocks of 128 experimental rows and both halves of TMEM as
                                    accumulators - a quarter fewer bytes per flop from L2, but no overlap of a tile's
                                    epilogue with the next tile's MMAs.  1 (default) = for K loops of at least 96 blocks
-                                   of 64 (more than ~6 100 kept pixels), where it is faster; 0 = never (256 x 256 tiles
+                                   of 64 (more than ~6 100 kept pixels; 64 blocks with 16 384 rows or more), where it is faster; 0 = never (256 x 256 tiles
                                    with two accumulator buffers); 2 = wherever it fits.  Identical results             */
 #define KDI_OPT_PROJECT_LIBM 22   /* 1 = the dictionary-generation kernel evaluates atan, the square roots and the
                                    division of the Lambert projection with the CUDA math library (round-1

@@ -575,9 +575,12 @@ int kdi_gemm_make_plan(kdi_ctx* ctx, int64_t M, int64_t N, int64_t kp, int keep_
   // and enough rows that the coarser row blocks still fill the device)
   // It pays once the K loop is long enough that the exposed epilogue is small beside it: measured break-even at
   // 60 x 60 patterns (57 K blocks), +3 % at 80 x 80 and 100 x 100, +9-16 % at the 11 287 kept pixels of BASELINE
-  // configs[2] (profiles/r2_gemm_dual_tile.txt).  KDI_OPT_GEMM_DUAL: 0 never, 1 from 96 K blocks on, 2 always.
+  // configs[2]; with 20 000 rows +3 % already at 64 x 64 and 70 x 70 (profiles/r2_gemm_dual_tile.txt).
+  // KDI_OPT_GEMM_DUAL: 0 never, 1 from 96 K blocks on (from 64 with at least 16 384 rows), 2 always.
   const bool dual_fits = pl.cta_group == 2 && pl.kc == 32 && M >= 2048;
-  pl.dual = (dual_fits && (ctx->gemm_dual == 2 || (ctx->gemm_dual == 1 && kp / KDI_TILE_K >= 96))) ? 1 : 0;
+  const int64_t kblocks = kp / KDI_TILE_K;
+  const bool dual_pays = kblocks >= 96 || (kblocks >= 64 && M >= 16384);
+  pl.dual = (dual_fits && (ctx->gemm_dual == 2 || (ctx->gemm_dual == 1 && dual_pays))) ? 1 : 0;
   pl.stages = stages_for(pl.cta_group, pl.kc, 0, pl.dual != 0);
   if (ctx->max_stages > 1 && pl.stages > ctx->max_stages) pl.stages = ctx->max_stages;
   if (ctx->post_coresident > 0 && pl.stages > 3) pl.stages -= 1;  // room for post-processing CTAs beside this kernel
