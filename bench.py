@@ -328,6 +328,35 @@ def run_ours(args, rank, world, local_rank):
         rows = torch.linspace(0, m_total - 1, 256, device=dev).long().unique()
         parity.update(cfgs.float64_check(exp_dev, rows, dictionary, "ncc", KEEP_N, None, result["idx"], result["sc"]))
     parity["flagged_rows_last_step"] = int(tms[-1]["flagged_rows"])
+    # the same step with the STRICT certificate (KDI_OPT_CERT_STRICT: a worst-case bound on the
+    # tensor-core error instead of the measured model; 64-entry candidate lists): what a proof costs
+    if world == 1 and not args.no_extras and args.compute_dtype != "bf16":
+        strict = {}
+        try:
+            ref_idx, ref_sc = idx_dev.clone(), sc_dev.clone()
+            ctx.set_option(_lib.OPT_CERT_STRICT, 1)
+            n_strict = max(3, min(args.steps, 10))
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    step_device()
+                torch.cuda.synchronize()
+                s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+                s0.record(stream)
+                for _ in range(n_strict):
+                    tm_s = step_device()
+                s1.record(stream)
+                torch.cuda.synchronize()
+            strict = {"ms_per_step": round(s0.elapsed_time(s1) / n_strict, 4), "steps": n_strict,
+                      "rows_through_exact_path": int(tm_s["flagged_rows"]),
+                      "candidates_per_row": ctx.candidate_capacity(KEEP_N),
+                      "bound": ctx.certificate_bound(S, 0),
+                      "identical_to_default": bool(torch.equal(ref_idx, idx_dev) and torch.equal(ref_sc, sc_dev))}
+            del ref_idx, ref_sc
+        except Exception as e:  # noqa: BLE001 - never lose the main line to an extra
+            strict = {"error": f"{type(e).__name__}: {e}"}
+        finally:
+            ctx.set_option(_lib.OPT_CERT_STRICT, 0)
+        parity["strict_certificate"] = strict
     # one extra (untimed) step on PLANTED patterns of the same shape: the planted dictionary row must
     # be the best match of every pattern
     with torch.cuda.stream(stream):

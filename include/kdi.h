@@ -131,6 +131,17 @@ extern "C" {
                                    division of the Lambert projection with the CUDA math library (round-1
                                    arithmetic, ~340 instructions per pixel); 0 (default) = with its own seeded
                                    Newton / polynomial sequences (~150, the same float32 patterns)              */
+#define KDI_OPT_CERT_STRICT 24    /* 1 = the candidate certificate is a BOUND instead of a measured error model: the
+                                   tensor-core score of any pair differs from its float32 score by at most
+                                   E = u (2 + u) + 18 * 2^-23 * K / 16 + (K / 32 + 8) * 2^-23  (u = 2^-11 fp16, 2^-8 bf16;
+                                   K = padded row length: operand rounding by Cauchy-Schwarz on unit rows, one
+                                   truncation per addend of every 16-deep tensor-core accumulation step, the float32
+                                   summation of the exact score; 1.46e-3 for 60 x 60 patterns in fp16), and a row is
+                                   accepted only if no discarded or pruned dictionary row can reach its keep_n-th
+                                   score under that bound; the others go to the exact path.  The candidate lists are
+                                   one size larger (64 entries up to keep_n 24, 128 beyond) so that rows still
+                                   certify.  0 (default) = the measured model (KDI_OPT_CERT_SIGMAS).  Same results
+                                   either way; every rank of a sharded job must use the same setting */
 #define KDI_OPT_DICT_VIEW 21     /* 1 (default) = a device-resident, unmasked float32 dictionary handed to a driver
                                    entry point (kdi_dictionary_indexing, kdi_shard_*) is not copied as normalised
                                    float32 rows: the exact scores read the caller's rows and apply the row's
@@ -302,7 +313,11 @@ int kdi_job_abort(kdi_ctx* ctx, kdi_job* job);
  *                            instead of all-reduce) and gather the finished slices.
  * The kdi_shard handle keeps the prepared pattern sets alive between the steps. */
 typedef struct kdi_shard kdi_shard;
-int kdi_candidate_capacity(int keep_n); /* 32, 64, or 0 when keep_n is too large for this pipeline */
+int kdi_candidate_capacity(int keep_n); /* 32, 64, 128, or 0 when keep_n is too large for this pipeline */
+/* the same for a context: one size larger when KDI_OPT_CERT_STRICT is set (what kdi_shard_* then use) */
+int kdi_candidate_capacity_ctx(kdi_ctx* ctx, int keep_n);
+/* the bound E of KDI_OPT_CERT_STRICT for rows of row_length kept values and compute_dtype 0 (fp16) / 1 (bf16) */
+double kdi_certificate_bound(int compute_dtype, int64_t row_length);
 int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
                          int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
                          int64_t dict_rows, int64_t S, int metric, int keep_n,

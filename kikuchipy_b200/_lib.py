@@ -51,6 +51,7 @@ OPT_DIV_DOUBLE = 20
 OPT_DICT_VIEW = 21
 OPT_PROJECT_LIBM = 22
 OPT_GEMM_DUAL = 23
+OPT_CERT_STRICT = 24
 
 REFINE_ORI, REFINE_PC, REFINE_ORI_PC = 0, 1, 2
 
@@ -130,6 +131,8 @@ SIGNATURES = {
     "kdi_job_finish": (_i, [_vp, _vp, _vp, _vp, _i]),
     "kdi_job_abort": (_i, [_vp, _vp]),
     "kdi_candidate_capacity": (_i, [_i]),
+    "kdi_candidate_capacity_ctx": (_i, [_vp, _i]),
+    "kdi_certificate_bound": (C.c_double, [_i, _i64]),
     "kdi_shard_candidates": (
         _i,
         [_vp, _vp, _i, _i, _i64, _vp, _i, _i, _i64, _i64, _i, _i, _vp, _i64, _vp, _vp, C.POINTER(_vp)],
@@ -780,7 +783,12 @@ class Context:
 
     # -- sharded dictionary: candidate pipeline (CUDA torch tensors in and out) -------------------
     def candidate_capacity(self, keep_n: int) -> int:
-        return int(self._lib.kdi_candidate_capacity(int(keep_n)))
+        return int(self._lib.kdi_candidate_capacity_ctx(self._h, int(keep_n)))
+
+    def certificate_bound(self, row_length: int, compute_dtype: int = 0) -> float:
+        """The bound of the strict certificate (``OPT_CERT_STRICT``) on \|tensor-core score - float32
+        score\| for rows of ``row_length`` kept values."""
+        return float(self._lib.kdi_certificate_bound(int(compute_dtype), int(row_length)))
 
     def shard_candidates(self, experimental, exp_rows, dictionary, dict_rows, metric, keep_n,
                          nav_mask=None, index_offset=0, pad_rows=0):

@@ -348,7 +348,7 @@ int kdi_comm_exchange(kdi_ctx* ctx, kdi_comm* comm, const kdi_patterns* exp, con
   int64_t* my_ix = reinterpret_cast<int64_t*>(mine + l.fin_ix) + r0 * keep_n;
   if (n_local > 0)
     KDI_TRY(kdi_launch_finalize(ctx, st, n_local, kc, m_approx, reinterpret_cast<const float*>(mine + l.exact), m_gidx, keep_n,
-                                dict_total, (float)ctx->cert_sigmas, kdi_cert_sigma_floor(exp), r0, my_sc, my_ix, flag_list,
+                                dict_total, kdi_cert_param(ctx, exp), kdi_cert_sigma_floor(exp), r0, my_sc, my_ix, flag_list,
                                 n_flag));
   {
     kdi_span span(ctx, st, "broadcast finished slice");

@@ -507,6 +507,9 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
       if (!(value > 0)) return kdi_fail(ctx, KDI_EINVAL, "certificate width must be positive");
       ctx->cert_sigmas = value;
       return KDI_OK;
+    case KDI_OPT_CERT_STRICT:
+      ctx->cert_strict = value != 0;
+      return KDI_OK;
     case KDI_OPT_FORCE_EXACT:
       ctx->force_exact = value != 0;
       return KDI_OK;

@@ -66,7 +66,7 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
   job->scores_out = scores_out;
   job->indices_out = indices_out;
   if (M == 0) return KDI_OK;
-  job->fused = candidates_only || (!ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0);
+  job->fused = candidates_only || (!ctx->force_exact && kdi_gemm_kc_ctx(ctx, keep_n) != 0);
   size_t off_thr = 0, off_flags = 0, off_nflag = 0, off_sela = 0, off_seli = 0, off_ready = 0, total = 0;
   if (job->fused) {
     KDI_TRY(kdi_gemm_make_plan(ctx, M, N, exp->kp, keep_n, &job->plan));
@@ -143,11 +143,11 @@ static int launch_post(kdi_ctx* ctx, cudaStream_t st, kdi_match_job* job, const 
     KDI_TRY(kdi_launch_select_only(ctx, st, exp->rows, &job->plan, job->cand, job->thr, 0, inv, job->sel_approx,
                                    job->sel_idx, row0, n_rows));
     return kdi_launch_select_rescore(ctx, st, exp, dict, &job->plan, job->cand, job->thr, job->keep_n,
-                                     post.index_offset, inv, (float)ctx->cert_sigmas, job->d_sc, job->d_ix,
+                                     post.index_offset, inv, kdi_cert_param(ctx, exp), job->d_sc, job->d_ix,
                                      job->flags, job->d_nflag, row0, n_rows, job->sel_approx, job->sel_idx);
   }
   return kdi_launch_select_rescore(ctx, st, exp, dict, &job->plan, job->cand, job->thr, job->keep_n,
-                                   post.index_offset, inv, (float)ctx->cert_sigmas, job->d_sc, job->d_ix,
+                                   post.index_offset, inv, kdi_cert_param(ctx, exp), job->d_sc, job->d_ix,
                                    job->flags, job->d_nflag, row0, n_rows);
 }
 
@@ -635,7 +635,7 @@ static int prepare_and_match(kdi_ctx* ctx, const void* experimental, int exp_loc
   // measured +3.5 ms on the exchange of BASELINE configs[3] at 8 GPUs).  KDI_OPT_DICT_VIEW = 2 forces it.
   const bool view_eligible = ctx->dict_view && !dsrc.mp && dict_loc == KDI_DEVICE && dict_dtype == KDI_F32 && !ctx->mask_S &&
                              kdi_normalize_is_light(S, S, false, false) && (reinterpret_cast<uintptr_t>(dictionary) % 16) == 0 &&
-                             !ctx->force_exact && kdi_gemm_kc_for(keep_n) != 0 && exp_rows > 0;
+                             !ctx->force_exact && kdi_gemm_kc_ctx(ctx, keep_n) != 0 && exp_rows > 0;
   const bool view_pays = !candidates_only && dict_rows * 6 >= exp_rows * (int64_t)(keep_n + 5);
   const bool view = view_eligible && (ctx->dict_view == 2 || view_pays);
   int rc = kdi_patterns_alloc(ctx, dict_rows, S, metric, &dict, view ? static_cast<const float*>(dictionary) : nullptr);
@@ -843,7 +843,7 @@ static int run_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_
                                 int64_t exp_rows, const kdi_dict_source& dsrc, int64_t dict_rows, int64_t S,
                                 int metric, int keep_n, const uint8_t* nav_mask, int64_t index_offset,
                                 float* approx_out, int64_t* gidx_out, kdi_shard** out) {
-  const int kc = kdi_gemm_kc_for(keep_n);
+  const int kc = kdi_gemm_kc_ctx(ctx, keep_n);
   if (kc == 0) return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d too large for the candidate pipeline", keep_n);
   kdi_patterns *exp = nullptr, *dict = nullptr;
   kdi_match_job job;
@@ -897,7 +897,7 @@ static int run_shard_peer(kdi_ctx* ctx, kdi_comm* comm, const void* experimental
                           int64_t* indices_out, int* flags_out, int* n_flag_out, kdi_shard** out) {
   *out = nullptr;
   *n_flag_out = 0;
-  const int kc = kdi_gemm_kc_for(keep_n);
+  const int kc = kdi_gemm_kc_ctx(ctx, keep_n);
   if (kc == 0) return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d too large for the candidate pipeline", keep_n);
   int rank = 0, world = 1;
   int64_t comm_bytes = 0;
@@ -944,7 +944,7 @@ static int run_shard_peer(kdi_ctx* ctx, kdi_comm* comm, const void* experimental
   if (rc == KDI_OK && job.M > 0 && job.plan.kc != kc) rc = kdi_fail(ctx, KDI_EINTERNAL, "candidate capacity mismatch");
   if (rc == KDI_OK && cudaEventRecord(ctx->ev[10], st) != cudaSuccess) rc = kdi_fail(ctx, KDI_ECUDA, "event record failed");
   // pruning margin of the owner rescoring: see kdi_shard_rescore_owned
-  const float margin = 2.0f * (float)ctx->cert_sigmas * (exp->compute_dtype == 1 ? 3.6e-5f : 4.5e-6f) + 2e-5f;
+  const float margin = kdi_cert_margin(ctx, exp);
   if (!ctx->h_nflag && rc == KDI_OK && cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_nflag), 64, cudaHostAllocDefault) != cudaSuccess)
     rc = kdi_fail(ctx, KDI_ENOMEM, "pinned allocation failed");
   int* d_total = nullptr;
@@ -1041,6 +1041,13 @@ int kdi_dictionary_indexing_projected(kdi_ctx* ctx, const void* experimental, in
 }
 
 int kdi_candidate_capacity(int keep_n) { return kdi_gemm_kc_for(keep_n); }
+int kdi_candidate_capacity_ctx(kdi_ctx* ctx, int keep_n) { return kdi_gemm_kc_ctx(ctx, keep_n); }
+double kdi_certificate_bound(int compute_dtype, int64_t row_length) {
+  kdi_patterns p;
+  p.compute_dtype = compute_dtype;
+  p.kp = kdi_ceil_div(row_length > 0 ? row_length : 1, (int64_t)KDI_TILE_K) * KDI_TILE_K;
+  return (double)kdi_cert_bound(&p);
+}
 
 int kdi_shard_candidates(kdi_ctx* ctx, const void* experimental, int exp_loc, int exp_dtype,
                          int64_t exp_rows, const void* dictionary, int dict_loc, int dict_dtype,
@@ -1087,9 +1094,7 @@ int kdi_shard_rescore_owned(kdi_ctx* ctx, const kdi_shard* shard, const int64_t*
   if (!ctx) return KDI_EINVAL;
   if (!shard || !gidx || !exact_out) return kdi_fail(ctx, KDI_EINVAL, "kdi_shard_rescore_owned: NULL argument");
   KDI_CUDA(ctx, cudaSetDevice(ctx->device));
-  // pruning margin: twice the certificate width at the noise level measured for each operand type
-  // (std of tensor-core minus exact score: 4.5e-6 with fp16 operands, 3.6e-5 with bf16)
-  const float margin = 2.0f * (float)ctx->cert_sigmas * (shard->exp->compute_dtype == 1 ? 3.6e-5f : 4.5e-6f) + 2e-5f;
+  const float margin = kdi_cert_margin(ctx, shard->exp);  // pruning margin (kdi_internal.cuh)
   KDI_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
   KDI_TRY(kdi_launch_rescore_owned(ctx, ctx->stream, shard->exp, shard->dict, shard->index_offset,
                                    shard->kc, gidx, approx, keep_n, margin, exact_out));
@@ -1118,7 +1123,7 @@ int kdi_shard_finalize(kdi_ctx* ctx, const kdi_shard* shard, int64_t row0, int64
   cudaStream_t st = ctx->stream;
   KDI_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int), st));
   KDI_TRY(kdi_launch_finalize(ctx, st, rows, shard->kc, approx, exact, gidx, keep_n, dict_total,
-                              (float)ctx->cert_sigmas, kdi_cert_sigma_floor(shard->exp), row0, scores_out, indices_out,
+                              kdi_cert_param(ctx, shard->exp), kdi_cert_sigma_floor(shard->exp), row0, scores_out, indices_out,
                               flags_out, d_n));
   KDI_CUDA(ctx, cudaMemcpyAsync(n_flag_out, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
   KDI_CUDA(ctx, cudaStreamSynchronize(st));

@@ -558,6 +558,13 @@ int kdi_gemm_kc_for(int keep_n) {
   return 0;
 }
 
+// With the strict certificate the lists are one size larger: the bound is ~40 x the measured noise, and
+// the gap between the keep_n-th and the kc-th score has to exceed it for a row to certify.
+int kdi_gemm_kc_ctx(const kdi_ctx* ctx, int keep_n) {
+  const int kc = kdi_gemm_kc_for(keep_n);
+  return (ctx && ctx->cert_strict && kc != 0 && kc < 128) ? 2 * kc : kc;
+}
+
 // shared memory per SM that a launch with this plan leaves to other kernels' CTAs
 int64_t kdi_gemm_free_smem(const kdi_ctx* ctx, const kdi_gemm_plan* plan) {
   const int64_t stage = kABytes * (plan->dual ? 2 : 1) + (KDI_TILE_N / plan->cta_group) * KDI_TILE_K * 2;
@@ -568,7 +575,7 @@ int64_t kdi_gemm_free_smem(const kdi_ctx* ctx, const kdi_gemm_plan* plan) {
 int kdi_gemm_make_plan(kdi_ctx* ctx, int64_t M, int64_t N, int64_t kp, int keep_n,
                        kdi_gemm_plan* plan) {
   kdi_gemm_plan pl;
-  pl.kc = kdi_gemm_kc_for(keep_n);
+  pl.kc = kdi_gemm_kc_ctx(ctx, keep_n);
   if (pl.kc == 0) return kdi_fail(ctx, KDI_EUNSUPPORTED, "keep_n %d too large for the fused path", keep_n);
   pl.cta_group = ctx->cta_group == 2 ? 2 : 1;
   // (the 512 x 256 pair tile: CTA pairs, 32-entry lists - two 64-entry lists would cost a pipeline stage -

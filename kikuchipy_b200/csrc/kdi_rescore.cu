@@ -321,12 +321,14 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   if (tid == 0 && n_a < keep_n) s_ek = -INFINITY;
   __syncthreads();
   const float inv_na = 1.f / (float)(n_a > 0 ? n_a : 1);
-  const float bias = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) * inv_na;
+  float bias = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) * inv_na;
   const float sigma = sqrtf(fmaxf(((s_red[kW] + s_red[kW + 1]) + (s_red[kW + 2] + s_red[kW + 3])) * inv_na - bias * bias, 0.f));
   // the noise level is estimated from a few dozen candidates of this row; it is never taken below the
   // a-priori level of the operand rounding (sigma_floor, kdi_cert_sigma_floor), so an unluckily small
   // sample cannot shrink the certificate's safety margin
-  const float eps = cert_sigmas * fmaxf(sigma, sigma_floor) + 0.1f * fabsf(bias) + 1e-7f;
+  float eps = cert_sigmas * fmaxf(sigma, sigma_floor) + 0.1f * fabsf(bias) + 1e-7f;
+  // strict certificate (KDI_OPT_CERT_STRICT; cert_sigmas = -E): no model, |approx - exact| <= E for every pair
+  if (cert_sigmas < 0.f) { bias = 0.f; eps = -cert_sigmas; }
   const float e_k = s_ek;
   for (int i = n_a + warp; i < nsel; i += kSelThreads / 32) {
     float d = -INFINITY;  // warp-uniform decision
@@ -481,9 +483,10 @@ kdi_finalize_kernel(int kc, const float* __restrict__ approx, const float* __res
     bool ok = true;
     const bool any_skipped = n_scored < (float)nsel;
     if (n_dict_total > (int64_t)nsel || any_skipped) {
-      const float bias = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) / n_scored;  // exact = approx + bias + noise
+      float bias = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) / n_scored;  // exact = approx + bias + noise
       const float sigma = sqrtf(fmaxf(((s_red[4] + s_red[5]) + (s_red[6] + s_red[7])) / n_scored - bias * bias, 0.f));
-      const float eps = cert_sigmas * fmaxf(sigma, sigma_floor) + 0.1f * fabsf(bias) + 1e-7f;
+      float eps = cert_sigmas * fmaxf(sigma, sigma_floor) + 0.1f * fabsf(bias) + 1e-7f;
+      if (cert_sigmas < 0.f) { bias = 0.f; eps = -cert_sigmas; }  // strict certificate: a bound, no model
       // nothing outside the rescored set may reach the keep_n-th exact score: neither a row the
       // tensor-core pass discarded (score <= the smallest retained one) nor a pruned candidate
       if (n_dict_total > (int64_t)nsel) ok = (nsel == kc) && (my_s > ap[nsel - 1] + bias + eps);

@@ -24,7 +24,7 @@ SCORE_TOL = 1e-4
 def ctx():
     c = kb.default_context(0)
     yield c
-    for opt in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK,
+    for opt in (_lib.OPT_CERT_STRICT, _lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK,
                 _lib.OPT_MAX_STAGES, _lib.OPT_GEMM_SMS, _lib.OPT_MIN_GROUPS, _lib.OPT_POST_PER_GROUP,
                 _lib.OPT_GEMM_SERIAL, _lib.OPT_SM_PARTITION):
         c.set_option(opt, 0)
@@ -866,6 +866,100 @@ def test_adversarial_near_ties_are_caught_by_the_certificate(ctx, compute):
     assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
     assert flagged >= 32  # the planted rows cannot be certified from 32 candidates
     assert np.all((i1[:32] >= 1000) & (i1[:32] < 1300) | (i1[:32] == 17))
+
+
+@pytest.mark.parametrize("metric", ["ncc", "ndp"])
+def test_strict_certificate_is_a_bound_and_changes_nothing(ctx, metric):
+    """KDI_OPT_CERT_STRICT: the certificate uses a worst-case bound on |tensor-core score - float32 score|
+    (operand rounding by Cauchy-Schwarz, truncation in every accumulation step) instead of the measured
+    error model.  On RANDOM patterns against the 100 000-entry dictionary of BASELINE configs[1]:
+    (1) the bound holds on every one of the 128 000 measured (candidate, exact) pairs, fp16 and bf16;
+    (2) strict results == default results bit for bit, with few rows sent to the exact path (the lists are
+    one size larger; NCC - the scores of uncentred random rows under NDP lie within +-4e-3 of one another, less
+    than the bound resolves even over 64 places, so most of those rows take the exact path); (3) the shard stages (pruned owner rescoring with the 2 E margin + finalize) agree
+    with them on every row they certify."""
+    import torch
+
+    M, N, sig, k = 2000, 100_000, (60, 60), 20
+    g = torch.Generator(device="cuda"); g.manual_seed(33)
+    exp = torch.randint(0, 256, (M,) + sig, dtype=torch.uint8, device="cuda", generator=g)
+    dic = torch.rand((N,) + sig, dtype=torch.float32, device="cuda", generator=g)
+    code = _lib.KDI_NCC if metric == "ncc" else _lib.KDI_NDP
+    assert ctx.candidate_capacity(k) == 32
+    few = M // 50 if metric == "ncc" else M
+    idx0 = torch.empty((M, k), dtype=torch.int64, device="cuda")
+    sc0 = torch.empty((M, k), dtype=torch.float32, device="cuda")
+    ctx.dictionary_indexing(exp, M, dic, N, code, k, out=(idx0, sc0))
+    ratios = {}
+    try:
+        for compute in (1, 0):
+            # (1) measured error of the tensor-core scores against the bound, default list size
+            ctx.set_option(_lib.OPT_COMPUTE_DTYPE, compute)
+            shard, approx, gidx = ctx.shard_candidates(exp, M, dic, N, code, k)
+            exact = shard.rescore_owned(gidx)
+            ok = gidx >= 0
+            err = float((approx - exact)[ok].abs().max())
+            bound = ctx.certificate_bound(sig[0] * sig[1], compute)
+            ratios[compute] = err / bound
+            assert err <= bound, (compute, err, bound)
+            shard.close()
+        assert 9e-4 < ctx.certificate_bound(3600, 0) < 2e-3 and ctx.certificate_bound(3600, 1) > 7e-3
+        ctx.set_option(_lib.OPT_CERT_STRICT, 1)
+        assert ctx.candidate_capacity(k) == 64 and ctx.candidate_capacity(30) == 128
+        assert ctx.candidate_capacity(104) == 128 and ctx.candidate_capacity(105) == 0
+        # (2) the whole pipeline
+        idx1 = torch.empty((M, k), dtype=torch.int64, device="cuda")
+        sc1 = torch.empty((M, k), dtype=torch.float32, device="cuda")
+        ctx.dictionary_indexing(exp, M, dic, N, code, k, out=(idx1, sc1))
+        tm = ctx.timings()
+        assert tm["gemm_launches"] >= 1
+        assert torch.equal(idx0, idx1) and torch.equal(sc0, sc1)
+        assert tm["flagged_rows"] <= few, tm["flagged_rows"]
+        flagged_strict = tm["flagged_rows"]
+        # (3) the stages of a sharded job on one GPU
+        shard, approx, gidx = ctx.shard_candidates(exp, M, dic, N, code, k)
+        assert approx.shape[1] == 64
+        exact_all = shard.rescore_owned(gidx)
+        exact = shard.rescore_owned(gidx, approx, k)
+        pruned = torch.isinf(exact) & (gidx >= 0)
+        assert bool(pruned.any()) or metric == "ndp"  # the margin does prune something out of 64 candidates
+        kth = torch.sort(exact_all, dim=1, descending=True).values[:, k - 1:k]
+        assert bool((exact_all[pruned] < kth.expand_as(exact_all)[pruned]).all())  # nothing pruned belonged to the top k
+        i2, s2, flags = shard.finalize(approx, gidx, exact, k, N)
+        good = torch.ones(M, dtype=torch.bool, device="cuda")
+        good[flags.long()] = False
+        assert int(flags.numel()) <= few
+        assert torch.equal(i2[good], idx0[good]) and torch.equal(s2[good], sc0[good])
+        shard.close()
+    finally:
+        ctx.set_option(_lib.OPT_CERT_STRICT, 0)
+        ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 0)
+    print(f"strict certificate ({metric}): measured max error / bound = {ratios[0]:.4f} (fp16), {ratios[1]:.4f} (bf16); "
+          f"{flagged_strict} of {M} rows through the exact path")
+
+
+@pytest.mark.parametrize("keep_n", [20, 50])
+def test_strict_certificate_near_ties_and_large_keep_n(ctx, keep_n):
+    """Strict certificate on the adversarial dictionary (300 rows ~1e-6 apart in score, more than any list
+    holds) and with the 128-entry lists: equal to the forced-exact results bit for bit."""
+    rng = np.random.default_rng(41)
+    dic = orc.synthetic_dictionary(6000, (30, 30), seed=42)
+    base = dic[17].copy()
+    dic[1000:1300] = base[None] * (1.0 + 1e-4 * rng.standard_normal((300, 30, 30)).astype(np.float32))
+    exp = orc.synthetic_experimental(64, (30, 30), seed=43)
+    exp[:32] = np.clip(np.rint(255 * (0.8 * base[None] + 0.2 * rng.random((32, 30, 30)))), 0, 255).astype(np.uint8)
+    ctx.set_option(_lib.OPT_CERT_STRICT, 1)
+    try:
+        i1, s1 = ctx.dictionary_indexing(exp, 64, dic, 6000, _lib.KDI_NCC, keep_n)
+        tm = ctx.timings()
+        ctx.set_option(_lib.OPT_FORCE_EXACT, 1)
+        i2, s2 = ctx.dictionary_indexing(exp, 64, dic, 6000, _lib.KDI_NCC, keep_n)
+    finally:
+        ctx.set_option(_lib.OPT_FORCE_EXACT, 0)
+        ctx.set_option(_lib.OPT_CERT_STRICT, 0)
+    assert tm["gemm_launches"] >= 1
+    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+    assert tm["flagged_rows"] >= 32  # the planted rows cannot be certified
 
 
 # ---- division route of the prepare kernels, view-mode dictionaries ------------------------------------
