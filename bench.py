@@ -103,15 +103,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_ms: int = 20):
         self.index = index
+        self.period_ms = max(5, int(period_ms))
         self.samples = []  # (host time the line was read, fields)
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms),
                  "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
@@ -257,6 +258,8 @@ def run_ours(args, rank, world, local_rank):
         ctx.set_option(_lib.OPT_SUPERBLOCK, args.superblock)
     if args.overlap is not None:
         ctx.set_option(_lib.OPT_OVERLAP, args.overlap)
+    if args.cert_widen is not None:
+        ctx.set_option(_lib.OPT_CERT_WIDEN, args.cert_widen)
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
 
     m_total = M_PER_GPU * world
@@ -291,7 +294,7 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_sample_ms)
     if rank == 0:
         sampler.start()  # nvidia-smi needs a few hundred ms before its first sample: start early
     with torch.cuda.stream(stream):
@@ -328,35 +331,41 @@ def run_ours(args, rank, world, local_rank):
         rows = torch.linspace(0, m_total - 1, 256, device=dev).long().unique()
         parity.update(cfgs.float64_check(exp_dev, rows, dictionary, "ncc", KEEP_N, None, result["idx"], result["sc"]))
     parity["flagged_rows_last_step"] = int(tms[-1]["flagged_rows"])
-    # the same step with the STRICT certificate (KDI_OPT_CERT_STRICT: a worst-case bound on the
-    # tensor-core error instead of the measured model; 64-entry candidate lists): what a proof costs
+    if world == 1:
+        # how the rows of the last timed step were certified (KDI_OPT_CERT_STRICT = 2, the default): by the
+        # worst-case bound on the tensor-core error (a proof), on the measured error model, or not at all
+        # (exact path)
+        parity["rows_certified"] = {"by_bound": m_total - int(tms[-1]["model_rows"]) - int(tms[-1]["flagged_rows"]),
+                                    "by_model": int(tms[-1]["model_rows"]), "exact_path": int(tms[-1]["flagged_rows"]),
+                                    "bound": ctx.certificate_bound(S, 1 if args.compute_dtype == "bf16" else 0)}
+    # the same step with the STRICT certificate (KDI_OPT_CERT_STRICT = 1: the bound only, rows it cannot
+    # decide go to the exact path) and with the model only (0, 32-entry lists: round 1's certificate)
     if world == 1 and not args.no_extras and args.compute_dtype != "bf16":
-        strict = {}
-        try:
-            ref_idx, ref_sc = idx_dev.clone(), sc_dev.clone()
-            ctx.set_option(_lib.OPT_CERT_STRICT, 1)
-            n_strict = max(3, min(args.steps, 10))
-            with torch.cuda.stream(stream):
-                for _ in range(3):
-                    step_device()
-                torch.cuda.synchronize()
-                s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
-                s0.record(stream)
-                for _ in range(n_strict):
-                    tm_s = step_device()
-                s1.record(stream)
-                torch.cuda.synchronize()
-            strict = {"ms_per_step": round(s0.elapsed_time(s1) / n_strict, 4), "steps": n_strict,
-                      "rows_through_exact_path": int(tm_s["flagged_rows"]),
-                      "candidates_per_row": ctx.candidate_capacity(KEEP_N),
-                      "bound": ctx.certificate_bound(S, 0),
-                      "identical_to_default": bool(torch.equal(ref_idx, idx_dev) and torch.equal(ref_sc, sc_dev))}
-            del ref_idx, ref_sc
-        except Exception as e:  # noqa: BLE001 - never lose the main line to an extra
-            strict = {"error": f"{type(e).__name__}: {e}"}
-        finally:
-            ctx.set_option(_lib.OPT_CERT_STRICT, 0)
-        parity["strict_certificate"] = strict
+        modes = {}
+        ref_idx, ref_sc = idx_dev.clone(), sc_dev.clone()
+        n_alt = max(3, min(args.steps, 10))
+        for label, mode in (("strict", 1), ("model_only", 0)):
+            try:
+                ctx.set_option(_lib.OPT_CERT_STRICT, mode)
+                with torch.cuda.stream(stream):
+                    for _ in range(3):
+                        step_device()
+                    torch.cuda.synchronize()
+                    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+                    s0.record(stream)
+                    for _ in range(n_alt):
+                        tm_s = step_device()
+                    s1.record(stream)
+                    torch.cuda.synchronize()
+                modes[label] = {"ms_per_step": round(s0.elapsed_time(s1) / n_alt, 4), "steps": n_alt,
+                                "exact_path_rows": int(tm_s["flagged_rows"]), "by_model_rows": int(tm_s["model_rows"]),
+                                "identical_to_default": bool(torch.equal(ref_idx, idx_dev) and torch.equal(ref_sc, sc_dev))}
+            except Exception as e:  # noqa: BLE001 - never lose the main line to an extra
+                modes[label] = {"error": f"{type(e).__name__}: {e}"}
+            finally:
+                ctx.set_option(_lib.OPT_CERT_STRICT, 2)
+        del ref_idx, ref_sc
+        parity["certificate_modes"] = modes
     # one extra (untimed) step on PLANTED patterns of the same shape: the planted dictionary row must
     # be the best match of every pattern
     with torch.cuda.stream(stream):
@@ -634,6 +643,8 @@ def main():
     ap.add_argument("--compute-dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--strip-tiles", type=int, default=0)
     ap.add_argument("--superblock", type=int, default=0)
+    ap.add_argument("--cert-widen", type=int, default=None, help="KDI_OPT_CERT_WIDEN (A/B runs; default: the library's)")
+    ap.add_argument("--clock-sample-ms", type=int, default=20, help="nvidia-smi sampling period during the timed region")
     ap.add_argument("--overlap", type=int, default=None, help="0: one kernel at a time; 1 (default): overlapped schedule")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -131,17 +131,27 @@ extern "C" {
                                    division of the Lambert projection with the CUDA math library (round-1
                                    arithmetic, ~340 instructions per pixel); 0 (default) = with its own seeded
                                    Newton / polynomial sequences (~150, the same float32 patterns)              */
-#define KDI_OPT_CERT_STRICT 24    /* 1 = the candidate certificate is a BOUND instead of a measured error model: the
-                                   tensor-core score of any pair differs from its float32 score by at most
+#define KDI_OPT_CERT_STRICT 24    /* how a row's candidate list is certified to contain its true keep_n best.
+                                   The tensor-core score of any pair differs from its float32 score by at most
                                    E = u (2 + u) + 18 * 2^-23 * K / 16 + (K / 32 + 8) * 2^-23  (u = 2^-11 fp16, 2^-8 bf16;
                                    K = padded row length: operand rounding by Cauchy-Schwarz on unit rows, one
                                    truncation per addend of every 16-deep tensor-core accumulation step, the float32
-                                   summation of the exact score; 1.46e-3 for 60 x 60 patterns in fp16), and a row is
-                                   accepted only if no discarded or pruned dictionary row can reach its keep_n-th
-                                   score under that bound; the others go to the exact path.  The candidate lists are
-                                   one size larger (64 entries up to keep_n 24, 128 beyond) so that rows still
-                                   certify.  0 (default) = the measured model (KDI_OPT_CERT_SIGMAS).  Same results
-                                   either way; every rank of a sharded job must use the same setting */
+                                   summation of the exact score; 1.48e-3 for 60 x 60 patterns in fp16) - a worst
+                                   case, 50-70 x the largest error measured.
+                                   2 (default) = rows whose scores allow it are PROVEN with E (no discarded or pruned
+                                   dictionary row can reach the keep_n-th score), the others are accepted on the
+                                   measured error model (KDI_OPT_CERT_SIGMAS) and counted (kdi_timings.model_rows;
+                                   single-GPU jobs - the stages of a sharded job use the model);
+                                   1 = strict: E only, every other row goes to the exact path; candidate lists one
+                                   size larger (64 entries up to keep_n 24, 128 beyond; kdi_candidate_capacity_ctx;
+                                   every rank of a sharded job must use the same setting);
+                                   0 = the model only.  Same results in every mode */
+#define KDI_OPT_CERT_WIDEN 25     /* 1 = with KDI_OPT_CERT_STRICT = 2, NCC jobs whose candidate lists stay inside the
+                                   library (not the kdi_shard_* stages) and that would use 32-entry lists with the
+                                   256 x 256 tile use 64-entry lists, so that the gap to the last retained score
+                                   exceeds E for (practically) every row: 10 000 of 10 000 rows of BASELINE
+                                   configs[1] proven instead of 8 672, for +4.5 % per step (7.39 against 7.07 ms, same
+                                   box).  0 (default) = list size by keep_n alone */
 #define KDI_OPT_DICT_VIEW 21     /* 1 (default) = a device-resident, unmasked float32 dictionary handed to a driver
                                    entry point (kdi_dictionary_indexing, kdi_shard_*) is not copied as normalised
                                    float32 rows: the exact scores read the caller's rows and apply the row's
@@ -170,6 +180,8 @@ typedef struct kdi_timings {
   int64_t flagged_rows;    /* rows sent through the exact fallback */
   int64_t h2d_bytes;
   int64_t d2h_bytes;
+  int64_t model_rows;      /* single-GPU jobs: rows accepted on the measured error model alone; the other
+                              unflagged rows are certified by the worst-case bound (KDI_OPT_CERT_STRICT) */
 } kdi_timings;
 
 /* ---- context ----------------------------------------------------------- */

@@ -52,6 +52,7 @@ OPT_DICT_VIEW = 21
 OPT_PROJECT_LIBM = 22
 OPT_GEMM_DUAL = 23
 OPT_CERT_STRICT = 24
+OPT_CERT_WIDEN = 25
 
 REFINE_ORI, REFINE_PC, REFINE_ORI_PC = 0, 1, 2
 
@@ -91,6 +92,7 @@ class Timings(C.Structure):
         ("flagged_rows", C.c_int64),
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
+        ("model_rows", C.c_int64),
     ]
 
     def as_dict(self) -> dict:
@@ -786,8 +788,8 @@ class Context:
         return int(self._lib.kdi_candidate_capacity_ctx(self._h, int(keep_n)))
 
     def certificate_bound(self, row_length: int, compute_dtype: int = 0) -> float:
-        """The bound of the strict certificate (``OPT_CERT_STRICT``) on \|tensor-core score - float32
-        score\| for rows of ``row_length`` kept values."""
+        """The bound of the strict certificate (``OPT_CERT_STRICT``) on abs(tensor-core score - float32
+        score) for rows of ``row_length`` kept values."""
         return float(self._lib.kdi_certificate_bound(int(compute_dtype), int(row_length)))
 
     def shard_candidates(self, experimental, exp_rows, dictionary, dict_rows, metric, keep_n,

@@ -508,7 +508,11 @@ int kdi_set_option(kdi_ctx* ctx, int option, double value) {
       ctx->cert_sigmas = value;
       return KDI_OK;
     case KDI_OPT_CERT_STRICT:
-      ctx->cert_strict = value != 0;
+      if (value != 0 && value != 1 && value != 2) return kdi_fail(ctx, KDI_EINVAL, "cert_strict must be 0, 1 or 2");
+      ctx->cert_strict = (int)value;
+      return KDI_OK;
+    case KDI_OPT_CERT_WIDEN:
+      ctx->cert_widen = value != 0;
       return KDI_OK;
     case KDI_OPT_FORCE_EXACT:
       ctx->force_exact = value != 0;

@@ -69,7 +69,8 @@ int kdi_match_begin(kdi_ctx* ctx, const kdi_patterns* exp, const kdi_patterns* d
   job->fused = candidates_only || (!ctx->force_exact && kdi_gemm_kc_ctx(ctx, keep_n) != 0);
   size_t off_thr = 0, off_flags = 0, off_nflag = 0, off_sela = 0, off_seli = 0, off_ready = 0, total = 0;
   if (job->fused) {
-    KDI_TRY(kdi_gemm_make_plan(ctx, M, N, exp->kp, keep_n, &job->plan));
+    const bool may_widen = !candidates_only && ctx->cert_strict == 2 && ctx->cert_widen && exp->metric == KDI_NCC;
+    KDI_TRY(kdi_gemm_make_plan(ctx, M, N, exp->kp, keep_n, &job->plan, may_widen));
     off_thr = align_up(job->plan.cand_bytes, 256);
     off_flags = align_up(off_thr + job->plan.thr_bytes, 256);
     off_nflag = align_up(off_flags + (size_t)M * sizeof(int), 256);
@@ -322,7 +323,7 @@ int kdi_match_complete(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp
     // the flagged-row count travels with the results: one synchronisation when no row was flagged
     // (the common case), a second round only for the rows the exact path has to redo
     if (!ctx->h_nflag) KDI_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_nflag), 64, cudaHostAllocDefault));
-    KDI_CUDA(ctx, cudaMemcpyAsync(ctx->h_nflag, job->d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KDI_CUDA(ctx, cudaMemcpyAsync(ctx->h_nflag, job->d_nflag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));  // [1]: rows accepted on the model alone
     ctx->h_nflag[4] = 0;
     if (job->uses_ready)  // diagnostics of a readiness wait that timed out (kdi_gemm_topk.cu)
       KDI_CUDA(ctx, cudaMemcpyAsync(ctx->h_nflag + 4, job->tile_ready + job->plan.n_tiles + 1, 4 * sizeof(int),
@@ -351,6 +352,7 @@ int kdi_match_complete(kdi_ctx* ctx, kdi_match_job* job, const kdi_patterns* exp
   if (job->fused) ctx->tm.gemm_topk_ms += ev_ms(ctx->ev[8], ctx->ev[9]);  // last GEMM launch / GEMM span
   if (job->fused) ctx->tm.rescore_ms += ev_ms(ctx->ev[3], ctx->ev[4]);
   ctx->tm.flagged_rows += job->fused ? n_flag : M;
+  if (job->fused) ctx->tm.model_rows += ctx->h_nflag[1];
   return KDI_OK;
 }
 

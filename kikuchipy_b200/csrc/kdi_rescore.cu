@@ -249,7 +249,7 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
                           const float4* __restrict__ dstat,
                           int64_t s_pitch, int64_t n_dict, const uint2* __restrict__ cand,
                           const uint32_t* __restrict__ thr, int n_strips, int keep_n,
-                          int64_t index_offset, float inv_scale, float cert_sigmas, float sigma_floor,
+                          int64_t index_offset, float inv_scale, float cert_sigmas, float sigma_floor, float bound,
                           float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
                           int* __restrict__ flag_list, int* __restrict__ n_flag, int64_t row0,
                           const float* __restrict__ pre_approx, const int64_t* __restrict__ pre_idx) {
@@ -327,9 +327,16 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
   // a-priori level of the operand rounding (sigma_floor, kdi_cert_sigma_floor), so an unluckily small
   // sample cannot shrink the certificate's safety margin
   float eps = cert_sigmas * fmaxf(sigma, sigma_floor) + 0.1f * fabsf(bias) + 1e-7f;
-  // strict certificate (KDI_OPT_CERT_STRICT; cert_sigmas = -E): no model, |approx - exact| <= E for every pair
-  if (cert_sigmas < 0.f) { bias = 0.f; eps = -cert_sigmas; }
   const float e_k = s_ek;
+  // Certificate by the worst-case bound E (|approx - exact| <= E for every pair, kdi_internal.cuh:
+  // kdi_cert_bound) instead of the model.  Strict (KDI_OPT_CERT_STRICT = 1; cert_sigmas = -E): every row.
+  // Default (bound = E > 0): the rows whose scores allow it - the keep_n-th exact score of round A already
+  // lies more than E above the smallest retained tensor-core score (or nothing was discarded) - so that
+  // their pruning below is E wide as well and the row ends up PROVEN; the others are decided on the model
+  // and counted in n_flag[1].
+  bool by_bound = false;
+  if (cert_sigmas < 0.f) { bias = 0.f; eps = -cert_sigmas; by_bound = true; }
+  else if (bound > 0.f && (n_dict <= (int64_t)nsel || (nsel == KC && e_k > ap[nsel - 1] + bound))) { bias = 0.f; eps = bound; by_bound = true; }
   for (int i = n_a + warp; i < nsel; i += kSelThreads / 32) {
     float d = -INFINITY;  // warp-uniform decision
     if (ap[i] + bias + eps >= e_k)
@@ -363,6 +370,8 @@ kdi_select_rescore_kernel(const float* __restrict__ exp32, const float* __restri
     if (!ok) {
       const int pos = atomicAdd(n_flag, 1);
       flag_list[pos] = (int)row;
+    } else if (!by_bound) {
+      atomicAdd(n_flag + 1, 1);  // accepted on the measured error model alone
     }
   }
   if (tid == 0 && nsel < keep_n) {  // fewer candidates than requested (NaN rows): exact path decides
@@ -633,6 +642,7 @@ int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patte
                               float* out_scores, int64_t* out_idx, int* flag_list, int* n_flag,
                               int64_t row0, int64_t n_rows, const float* pre_approx, const int64_t* pre_idx) {
   const float sigma_floor = kdi_cert_sigma_floor(exp);
+  const float bound = ctx->cert_strict == 2 ? kdi_cert_bound(exp) : 0.f;  // bound first, model second (the default)
   if (n_rows < 0) n_rows = exp->rows - row0;
   if (n_rows <= 0) return KDI_OK;
   const unsigned grid = (unsigned)n_rows;
@@ -655,7 +665,7 @@ int kdi_launch_select_rescore(kdi_ctx* ctx, cudaStream_t stream, const kdi_patte
 #define KDI_LAUNCH_SR(KC_, VIEW_)                                                                              \
   kdi_select_rescore_kernel<KC_, VIEW_><<<grid, kSelThreads, pad, stream>>>(                                  \
       exp->a32, d32, dict->rstat, exp->s_pitch, dict->rows, cand, thr, plan->n_strips, keep_n, index_offset,  \
-      approx_inv_scale, cert_sigmas, sigma_floor, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx)
+      approx_inv_scale, cert_sigmas, sigma_floor, bound, out_scores, out_idx, flag_list, n_flag, row0, pre_approx, pre_idx)
   if (plan->kc == 32) { if (view) KDI_LAUNCH_SR(32, true); else KDI_LAUNCH_SR(32, false); }
   else if (plan->kc == 64) { if (view) KDI_LAUNCH_SR(64, true); else KDI_LAUNCH_SR(64, false); }
   else if (plan->kc == 128) { if (view) KDI_LAUNCH_SR(128, true); else KDI_LAUNCH_SR(128, false); }

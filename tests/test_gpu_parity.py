@@ -24,11 +24,13 @@ SCORE_TOL = 1e-4
 def ctx():
     c = kb.default_context(0)
     yield c
-    for opt in (_lib.OPT_CERT_STRICT, _lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK,
+    for opt in (_lib.OPT_COMPUTE_DTYPE, _lib.OPT_FORCE_EXACT, _lib.OPT_STRIP_TILES, _lib.OPT_SUPERBLOCK,
                 _lib.OPT_MAX_STAGES, _lib.OPT_GEMM_SMS, _lib.OPT_MIN_GROUPS, _lib.OPT_POST_PER_GROUP,
                 _lib.OPT_GEMM_SERIAL, _lib.OPT_SM_PARTITION):
         c.set_option(opt, 0)
     c.set_option(_lib.OPT_DEP_FLAGS, 0)
+    c.set_option(_lib.OPT_CERT_STRICT, 2)
+    c.set_option(_lib.OPT_CERT_WIDEN, 0)
     c.set_option(_lib.OPT_SPLIT_SELECT, 1)
     c.set_option(_lib.OPT_CTA_GROUP, 2)
     c.set_option(_lib.OPT_OVERLAP, 1)
@@ -889,7 +891,28 @@ def test_strict_certificate_is_a_bound_and_changes_nothing(ctx, metric):
     few = M // 50 if metric == "ncc" else M
     idx0 = torch.empty((M, k), dtype=torch.int64, device="cuda")
     sc0 = torch.empty((M, k), dtype=torch.float32, device="cuda")
-    ctx.dictionary_indexing(exp, M, dic, N, code, k, out=(idx0, sc0))
+    # the default: rows proven with the bound where their scores allow it, on the model elsewhere (counted);
+    # with 32-entry lists most random NCC rows are proven, with 64-entry lists (KDI_OPT_CERT_WIDEN) all of
+    # them; the model alone (mode 0) counts every row.  Same results in all of them
+    counts = {}
+    for mode, widen in ((0, 1), (2, 1), (2, 0)):
+        ctx.set_option(_lib.OPT_CERT_STRICT, mode)
+        ctx.set_option(_lib.OPT_CERT_WIDEN, widen)
+        i_m = torch.empty_like(idx0); s_m = torch.empty_like(sc0)
+        ctx.dictionary_indexing(exp, M, dic, N, code, k, out=(i_m, s_m))
+        tm = ctx.timings()
+        counts[(mode, widen)] = (int(tm["model_rows"]), int(tm["flagged_rows"]))
+        if mode == 0:
+            idx0, sc0 = i_m, s_m
+        else:
+            assert torch.equal(idx0, i_m) and torch.equal(sc0, s_m), (mode, widen)
+    assert counts[(0, 1)][0] + counts[(0, 1)][1] == M
+    if metric == "ncc":
+        assert counts[(2, 1)] == (0, 0), counts           # every row proven
+        assert 0 < counts[(2, 0)][0] < M // 2, counts      # 32-entry lists: most rows proven
+    else:
+        assert counts[(2, 1)] == counts[(2, 0)], counts   # NDP lists are not widened
+    print(f"certificate counts (model rows, flagged rows) by (mode, widen), {metric}: {counts}")
     ratios = {}
     try:
         for compute in (1, 0):
@@ -932,7 +955,8 @@ def test_strict_certificate_is_a_bound_and_changes_nothing(ctx, metric):
         assert torch.equal(i2[good], idx0[good]) and torch.equal(s2[good], sc0[good])
         shard.close()
     finally:
-        ctx.set_option(_lib.OPT_CERT_STRICT, 0)
+        ctx.set_option(_lib.OPT_CERT_STRICT, 2)
+        ctx.set_option(_lib.OPT_CERT_WIDEN, 0)
         ctx.set_option(_lib.OPT_COMPUTE_DTYPE, 0)
     print(f"strict certificate ({metric}): measured max error / bound = {ratios[0]:.4f} (fp16), {ratios[1]:.4f} (bf16); "
           f"{flagged_strict} of {M} rows through the exact path")
@@ -956,7 +980,7 @@ def test_strict_certificate_near_ties_and_large_keep_n(ctx, keep_n):
         i2, s2 = ctx.dictionary_indexing(exp, 64, dic, 6000, _lib.KDI_NCC, keep_n)
     finally:
         ctx.set_option(_lib.OPT_FORCE_EXACT, 0)
-        ctx.set_option(_lib.OPT_CERT_STRICT, 0)
+        ctx.set_option(_lib.OPT_CERT_STRICT, 2)
     assert tm["gemm_launches"] >= 1
     assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
     assert tm["flagged_rows"] >= 32  # the planted rows cannot be certified

@@ -74,6 +74,20 @@ def _worker(rank, world, port, tmp):
                     assert torch.equal(big["peer"][0], i7) and torch.equal(big["peer"][1], s7), (mode, ex)
         finally:
             ctx.set_option(_lib.OPT_DICT_VIEW, 1)
+        # strict certificate (KDI_OPT_CERT_STRICT = 1: worst-case bound, lists one size larger, 2 E pruning margin
+        # in the owner rescoring of both exchanges): the same results as the single-GPU pipeline in either mode
+        i_def, s_def = ctx.dictionary_indexing(expB, 2100, dicB, 30001, _lib.KDI_NCC, 20)
+        ctx.set_option(_lib.OPT_CERT_STRICT, 1)
+        try:
+            assert ctx.candidate_capacity(20) == 64
+            i_one, s_one = ctx.dictionary_indexing(expB, 2100, dicB, 30001, _lib.KDI_NCC, 20)
+            assert np.array_equal(i_def, i_one) and np.array_equal(s_def, s_one)
+            for ex in ("peer", "nccl"):
+                i8, s8 = kb.dictionary_indexing_sharded(expB, dicB[sB:eB], 30001, metric="ncc", keep_n=20, context=ctx,
+                                                        exchange=ex)
+                assert np.array_equal(i8.cpu().numpy(), i_one) and np.array_equal(s8.cpu().numpy(), s_one), ex
+        finally:
+            ctx.set_option(_lib.OPT_CERT_STRICT, 2)
         np.savez(os.path.join(tmp, f"big{rank}.npz"), ip=big["peer"][0].cpu().numpy(), sp=big["peer"][1].cpu().numpy(),
                  inn=big["nccl"][0].cpu().numpy(), sn=big["nccl"][1].cpu().numpy(), i1=i6, s1=s6)
         np.savez(os.path.join(tmp, f"r{rank}.npz"), idx=idx.cpu().numpy(), sc=sc.cpu().numpy(),

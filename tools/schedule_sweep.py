@@ -21,9 +21,10 @@ REPS, ROUNDS = int(os.environ.get("REPS", "3")), int(os.environ.get("ROUNDS", "4
 O = _lib
 NAMES = {"flags": O.OPT_DEP_FLAGS, "groups": O.OPT_MIN_GROUPS, "post": O.OPT_POST_PER_GROUP, "sms": O.OPT_GEMM_SMS,
          "serial": O.OPT_GEMM_SERIAL, "part": O.OPT_SM_PARTITION, "cores": O.OPT_POST_CORESIDENT, "split": O.OPT_EARLY_SPLIT, "overlap": O.OPT_OVERLAP, "stages": O.OPT_MAX_STAGES,
-         "strip": O.OPT_STRIP_TILES, "sb": O.OPT_SUPERBLOCK, "view": O.OPT_DICT_VIEW, "divd": O.OPT_DIV_DOUBLE, "dual": O.OPT_GEMM_DUAL}
+         "strip": O.OPT_STRIP_TILES, "sb": O.OPT_SUPERBLOCK, "view": O.OPT_DICT_VIEW, "divd": O.OPT_DIV_DOUBLE, "dual": O.OPT_GEMM_DUAL,
+         "cert": O.OPT_CERT_STRICT, "widen": O.OPT_CERT_WIDEN}
 DEFAULTS = {"flags": 0, "groups": 0, "post": 0, "sms": 0, "serial": 0, "part": 0, "cores": 0, "split": 1, "overlap": 1, "stages": 0, "strip": 0, "sb": 0,
-            "view": 1, "divd": 0, "dual": 0}
+            "view": 1, "divd": 0, "dual": 0, "cert": 2, "widen": 0}
 SETTINGS = os.environ.get(
     "SETTINGS",
     "split=1;split=0;split=0,groups=4;flags=1;overlap=0").split(";")
@@ -74,6 +75,7 @@ for rnd in range(ROUNDS):
                 a["total"].append(t["total_ms"]); a["gemm"].append(t["gemm_topk_ms"]); a["post"].append(t["rescore_ms"])
                 a["wall"].append(e0.elapsed_time(e1))
             a["flagged"] = t["flagged_rows"]
+            a["model_rows"] = t.get("model_rows", -1)
         except _lib.KdiError as e:
             a["error"] = str(e)
             print(json.dumps({"setting": s, "round": rnd, "error": str(e)}), file=sys.stderr, flush=True)
@@ -88,4 +90,4 @@ for s, a in acc.items():
     print(json.dumps({"setting": s, "total_ms_mean": round(float(np.mean(a["total"])), 3),
                       "total_ms_min": round(min(a["total"]), 3), "event_span_ms_mean": round(float(np.mean(a["wall"])), 3),
                       "gemm_ms_mean": round(float(np.mean(a["gemm"])), 3), "post_tail_ms_mean": round(float(np.mean(a["post"])), 3),
-                      "flagged": a["flagged"], "same_idx": a["same"], "n": len(a["total"])}), flush=True)
+                      "flagged": a["flagged"], "model_rows": a.get("model_rows"), "same_idx": a["same"], "n": len(a["total"])}), flush=True)
