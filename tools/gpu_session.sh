@@ -1,5 +1,15 @@
 #!/bin/bash
-# Session 67 (2 GPUs): the sharded test (peer and collective exchange, certificate modes) and smoke()'s 2-rank check.
+# What the driver runs at round end on one GPU: whole suite, smoke(), our bench arm with default flags.
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests/test_gpu_sharded.py -m gpu -x -q > gpurun_out/s67_sharded.log 2>&1
-echo "sharded exit $?"; tail -5 gpurun_out/s67_sharded.log | cut -c1-300
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/final_pytest.log 2>&1
+echo "pytest exit $?"; tail -3 gpurun_out/final_pytest.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1
+echo "smoke exit $?"; tail -2 gpurun_out/final_smoke.log | cut -c1-400
+timeout 1200 python bench.py > gpurun_out/final_bench_n1.json 2> gpurun_out/final_bench_n1.err
+echo "bench exit $?"; python - <<'PY'
+import json
+for l in open('gpurun_out/final_bench_n1.json'):
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step','e2e','roofline','clocks') if k in d}); print(json.dumps(d.get('parity'))[:1200]); print(json.dumps(d.get('extra'))[:600])
+PY
