@@ -133,11 +133,11 @@ extern "C" {
                                    Newton / polynomial sequences (~150, the same float32 patterns)              */
 #define KDI_OPT_CERT_STRICT 24    /* how a row's candidate list is certified to contain its true keep_n best.
                                    The tensor-core score of any pair differs from its float32 score by at most
-                                   E = u (2 + u) + 18 * 2^-23 * K / 16 + (K / 32 + 8) * 2^-23  (u = 2^-11 fp16, 2^-8 bf16;
-                                   K = padded row length: operand rounding by Cauchy-Schwarz on unit rows, one
-                                   truncation per addend of every 16-deep tensor-core accumulation step, the float32
-                                   summation of the exact score; 1.48e-3 for 60 x 60 patterns in fp16) - a worst
-                                   case, 50-70 x the largest error measured.
+                                   E = u (2 + u) + 8 * 2^-23 * K / 16 + (K / 32 + 8) * 2^-23  (u = 2^-11 fp16, 2^-8 bf16;
+                                   K = padded row length: operand rounding by Cauchy-Schwarz on unit rows, the
+                                   truncations of every 16-deep tensor-core accumulation step as measured on this part
+                                   (5 ulp, taken as 8), the float32 summation of the exact score; 1.21e-3 for 60 x 60
+                                   patterns in fp16) - a worst case, 40-60 x the largest error measured.
                                    2 (default) = rows whose scores allow it are PROVEN with E (no discarded or pruned
                                    dictionary row can reach the keep_n-th score), the others are accepted on the
                                    measured error model (KDI_OPT_CERT_SIGMAS) and counted (kdi_timings.model_rows;
@@ -150,7 +150,7 @@ extern "C" {
                                    library (not the kdi_shard_* stages) and that would use 32-entry lists with the
                                    256 x 256 tile use 64-entry lists, so that the gap to the last retained score
                                    exceeds E for (practically) every row: 10 000 of 10 000 rows of BASELINE
-                                   configs[1] proven instead of 8 672, for +4.5 % per step (7.39 against 7.07 ms, same
+                                   configs[1] proven instead of 9 569, for +4.5 % per step (7.39 against 7.07 ms, same
                                    box).  0 (default) = list size by keep_n alone */
 #define KDI_OPT_DICT_VIEW 21     /* 1 (default) = a device-resident, unmasked float32 dictionary handed to a driver
                                    entry point (kdi_dictionary_indexing, kdi_shard_*) is not copied as normalised

@@ -1,6 +1,9 @@
 #!/bin/bash
-# What the driver runs at round end on one GPU: whole suite, smoke(), our bench arm with default flags.
+# What the driver runs at round end on one GPU: whole suite, smoke(), our bench arm with default flags
+# (+ the certificate tests with their printed counts).
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -s -k "strict" > gpurun_out/final_strict.log 2>&1
+echo "strict tests exit $?"; grep -a "certificate" gpurun_out/final_strict.log | sed 's/^\.//' | head
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/final_pytest.log 2>&1
 echo "pytest exit $?"; tail -3 gpurun_out/final_pytest.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1
@@ -11,5 +14,5 @@ import json
 for l in open('gpurun_out/final_bench_n1.json'):
     l=l.strip()
     if l.startswith('{'):
-        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step','e2e','roofline','clocks') if k in d}); print(json.dumps(d.get('parity'))[:1200]); print(json.dumps(d.get('extra'))[:600])
+        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step') if k in d}, d['roofline']['achieved'], d['e2e']['ms_per_step'], d['clocks']); print(json.dumps(d.get('parity'))[:1200]); print(json.dumps(d.get('extra'))[:300])
 PY
