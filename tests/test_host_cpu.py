@@ -33,6 +33,24 @@ def test_library_exports_every_declared_symbol():
     assert lib.kdi_version() == 100
 
 
+def test_certificate_bound_formula():
+    """kdi_certificate_bound (a host function, no device needed) is the formula include/kdi.h states for
+    KDI_OPT_CERT_STRICT: operand rounding by Cauchy-Schwarz, 8 ulp per 16-deep accumulation step (5 measured,
+    profiles/r2_mma_accumulate_probe.txt), the float32 summation of the exact score; row length padded to 64."""
+    lib = _lib.load()
+    ulp = 2.0 ** -23
+    for s_eff, kp in ((3600, 3648), (11287, 11328), (6400, 6400), (9, 64), (64, 64), (65, 128)):
+        for code, u in ((0, 2.0 ** -11), (1, 2.0 ** -8)):
+            steps = kp // 16
+            want = (u * (2 + u) + 8 * steps * ulp) * (1 + 4e-6) + (0.5 * steps + 8) * ulp + 1e-6
+            got = lib.kdi_certificate_bound(code, s_eff)
+            assert abs(got - want) <= 1e-6 * want, (s_eff, code, got, want)
+    assert 1.1e-3 < lib.kdi_certificate_bound(0, 3600) < 1.3e-3
+    assert lib.kdi_certificate_bound(0, 14400) > lib.kdi_certificate_bound(0, 3600)  # grows with the K loop
+    assert lib.kdi_candidate_capacity(20) == 32 and lib.kdi_candidate_capacity(52) == 64
+    assert lib.kdi_candidate_capacity(104) == 128 and lib.kdi_candidate_capacity(105) == 0
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
 
