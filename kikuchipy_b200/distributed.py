@@ -163,9 +163,11 @@ def peer_comm(ctx, nbytes: int, group=None):
 
     key = (id(ctx), id(group))
     comm = _PEER_COMMS.get(key)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if comm is not None and (comm._ctx is not ctx or comm.rank != rank or comm.world != world):
+        comm = None  # the key of a group object that no longer exists: not this job's mapping
     if comm is not None and comm._h and comm.nbytes >= nbytes:
         return comm
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
     if comm is not None:
         torch.cuda.synchronize()
         dist.barrier(group)  # nobody still stores into a block that is about to go away
