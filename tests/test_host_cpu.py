@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_certificate_bound_formula():
     """kdi_certificate_bound (a host function, no device needed) is the formula include/kdi.h states for
-    KDI_OPT_CERT_STRICT: operand rounding by Cauchy-Schwarz, 8 ulp per 16-deep accumulation step (5 measured,
+    KDI_OPT_CERT_STRICT: operand rounding by Cauchy-Schwarz, 8 ulp per 16-deep accumulation step (5.25 measured,
     profiles/r2_mma_accumulate_probe.txt), the float32 summation of the exact score; row length padded to 64."""
     lib = _lib.load()
     ulp = 2.0 ** -23
